@@ -1,0 +1,147 @@
+/*
+ * swb200.h — C-ABI of libswb200.so: the B200-native (sm_100a) replacement for the CPU solver calls
+ * on Shockwave's per-round scheduling hot path.
+ *
+ * The reference (uw-mad-dash/shockwave) is pure Python; the arithmetic it delegates to
+ * cvxpy -> Gurobi / ECOS is what these entry points replace.  Each entry point cites the reference
+ * interface it stands in for.  Plain pointers and sizes only — no torch / pybind types.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = ok, >0 = ok-with-note (see SWB_ST_*), <0 = error
+ *     (SWB_ERR_*); swb_last_error() gives the text of the last error on the calling thread;
+ *   - buffers are caller-owned; `*_dev` flags in the argument structs say whether the pointers are
+ *     host (the default, e2e path: copies are done inside the call on the context's stream) or
+ *     device pointers (inputs already resident in HBM);
+ *   - one CUDA stream per context, no internal threads, not re-entrant per context (the reference
+ *     calls the solver with Scheduler._scheduler_lock held: scheduler/scheduler.py:2188-2192).
+ */
+#ifndef SWB200_H
+#define SWB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWB_MAX_BASES 16
+#define SWB_MAX_MODES 16
+
+#define SWB_ST_OK 0
+#define SWB_ST_FALLBACK 1 /* FTF rows infeasible -> relaxed objective + re-rank (shockwave.py:631-706) */
+
+#define SWB_ERR_CUDA (-1)
+#define SWB_ERR_ARG (-2)
+#define SWB_ERR_NOMEM (-3)
+#define SWB_ERR_STATE (-4)
+
+typedef struct swb_ctx swb_ctx;
+
+/* Scalars of one solve: the constructor kwargs of ShockwaveScheduler (scheduler/shockwave.py:21-86)
+ * plus the per-call round pointer. */
+typedef struct swb_params {
+  int32_t ngpus;        /* G  : shockwave.py:40  */
+  int32_t future_rounds;/* T  : shockwave.py:45  */
+  int32_t round_ptr;    /* r  : shockwave.py:76  */
+  int32_t nbases;       /* B  : len(logapx_bases), shockwave.py:60 */
+  double round_duration;/* D  : shockwave.py:48  */
+  double k;             /* shockwave.py:66  */
+  double lam;           /* shockwave.py:85  */
+  double rhomax;        /* shockwave.py:86  */
+  double bases[SWB_MAX_BASES];   /* logapx_bases                      */
+  double logv[SWB_MAX_BASES];    /* log(base) with log(0)->log(origin) : shockwave.py:339-347 */
+} swb_params;
+
+/* Result scalars of one solve (one per scenario). */
+typedef struct swb_result {
+  int32_t status;       /* SWB_ST_OK or SWB_ST_FALLBACK */
+  int32_t m_evals;      /* makespan candidates evaluated */
+  int32_t mu_iters;     /* price-bisection iterations in total */
+  int32_t shortfall;    /* planned job-rounds the placement could not seat (0 = all seated) */
+  double objective;     /* sum_j w_j plog_j/(J T) - k max_j rem_j of the RETURNED integral x */
+  double welfare;       /* first term */
+  double makespan;      /* max_j rem_j */
+  double price;         /* clearing price mu (welfare per GPU-round) */
+  double relaxed_objective; /* optimum of the continuous relaxation (n_j real) — upper bound */
+} swb_result;
+
+/* ---- context -------------------------------------------------------------------------------- */
+int swb_create(swb_ctx **out, int device);
+void swb_destroy(swb_ctx *ctx);
+const char *swb_last_error(void);
+int swb_version(void);
+/* raw cudaStream_t of the context (so a host framework can order its own work after ours) */
+void *swb_stream(swb_ctx *ctx);
+int swb_sync(swb_ctx *ctx);
+
+/* ---- the market solve on plain arrays ------------------------------------------------------- *
+ * Replaces dynamic_eisenberg_gale_scheduling() (scheduler/shockwave.py:504-711) — model build +
+ * Gurobi solve + infeasible->relaxed->re-rank fallback — and the rounding half of
+ * construct_schedules() (shockwave.py:213-285).
+ *
+ * S independent scenarios are solved by one launch (one CTA each).  Per-job arrays are [S][J]
+ * row-major when `per_scenario_jobs` != 0, else one shared [J] set; `prm` is [S].
+ *   nworkers g_j (JobMetaData.py:57-60), epochs E_j (:62), epoch_progress c_j (:86),
+ *   dbar_j = interpolate_epoch_duration (shockwave.py:322-324),
+ *   rem_j  = dirichlet_posterior_remaining_runtime (JobMetaData.py:315-370),
+ *   ftobj_j= finish_time_momentumed_average(share_series[j]) (shockwave.py:480-501),
+ *   bfkey_j= back-fill sort key (remaining runtime at construct_schedules time, shockwave.py:261-267)
+ * Outputs (caller-owned): x [S][J][T] uint8 (the rounded round-schedule variables),
+ *   backfill [S][J][T] uint8 (1 where construct_schedules' work-conserving pass adds the job),
+ *   nrounds [S][J] int32, weights [S][J] double (1 or the fallback priority), res [S].
+ */
+typedef struct swb_solve_args {
+  int32_t S, J;
+  int32_t per_scenario_jobs;
+  int32_t on_device;            /* 0: all pointers are host memory; 1: all are device memory */
+  const swb_params *prm;        /* [S], always HOST */
+  const int32_t *g, *E, *c;
+  const double *dbar, *rem, *ftobj, *bfkey;
+  uint8_t *x, *backfill;        /* may be NULL */
+  int32_t *nrounds;             /* may be NULL */
+  double *weights;              /* may be NULL */
+  swb_result *res;              /* [S], always HOST */
+} swb_solve_args;
+int swb_solve(swb_ctx *ctx, const swb_solve_args *a);
+
+/* ---- resident job table + dynamic-adaptation forecast ---------------------------------------- *
+ * Replaces, per active job, JobMetaData.calibrate_profiled_epoch_duration (JobMetaData.py:225-288),
+ * dirichlet_posterior_remaining_runtime (:315-370), interpolate_epoch_duration (shockwave.py:322-324)
+ * and ShockwaveScheduler.finish_time_uniform_share (shockwave.py:88-120).
+ * A job's static profile is uploaded once (add) into a device-resident table keyed by `slot`.
+ */
+int swb_job_add(swb_ctx *ctx, int32_t slot, int32_t nworkers, int32_t epochs, double epoch_nsamples,
+                double timestamp_submit, const double *epoch_duration_preprofiled,
+                const int32_t *bs_schedule);
+int swb_job_remove(swb_ctx *ctx, int32_t slot);
+
+/* One full ShockwaveScheduler.round_schedule() re-solve (shockwave.py:122-166) for the jobs listed
+ * in `slots` (metadata order).  Host inputs per job: epoch_progress, and the summary of the
+ * throughput timeline (JobMetaData.py:235-249): measured sample count and last round (-1 = empty).
+ * `gavel_round_duration` is JobMetaData.gavel_round_duration.  If `reestimate_share` the share
+ * series of every job gets a new (round_ptr, finish-time-estimate) entry (shockwave.py:92-120).
+ * `forecast_out` (may be NULL) receives 6 planes of [J] doubles: dbar, rem, ftobj, bfkey and the
+ * fallback continuation rem_fb, bfkey_fb (used when res->status == SWB_ST_FALLBACK). */
+typedef struct swb_round_args {
+  int32_t J;
+  int32_t reestimate_share;
+  double gavel_round_duration;
+  const int32_t *slots;         /* [J] host */
+  const int32_t *epoch_progress;/* [J] host */
+  const double *meas_nsamples;  /* [J] host */
+  const int32_t *meas_end_round;/* [J] host, -1 when the timeline is empty */
+  uint8_t *x, *backfill;        /* [J][T] host, out */
+  int32_t *nrounds;             /* [J] host, out (may be NULL) */
+  double *forecast_out;         /* [6][J] host, out (may be NULL) */
+  swb_result *res;              /* host, out */
+} swb_round_args;
+int swb_round_solve(swb_ctx *ctx, const swb_params *prm, const swb_round_args *a);
+
+/* Forecast only (same kernels as above, no solve); outputs [J] doubles each, host. */
+int swb_forecast(swb_ctx *ctx, const swb_params *prm, const swb_round_args *a, double *dbar,
+                 double *rem, double *ftobj, double *bfkey, double *ft_estimate);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWB200_H */

@@ -1,0 +1,447 @@
+// api.cu — the C-ABI of libswb200.so (see include/swb200.h) and the device-memory bookkeeping.
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "swb_internal.h"
+
+namespace swb {
+cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask);
+}
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call)                                                                            \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(SWB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+// growable device buffer
+struct DBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t need(size_t bytes, cudaStream_t st, bool keep = false) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t ncap = cap ? cap : 256;
+    while (ncap < bytes) ncap *= 2;
+    void *np = nullptr;
+    cudaError_t e = cudaMalloc(&np, ncap);
+    if (e != cudaSuccess) return e;
+    if (keep && p && cap) {
+      e = cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return e;
+      e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return e;
+    }
+    if (keep && ncap > cap) {
+      e = cudaMemsetAsync((char *)np + cap, 0, ncap - cap, st);
+      if (e != cudaSuccess) return e;
+    }
+    if (p) cudaFree(p);
+    p = np; cap = ncap;
+    return cudaSuccess;
+  }
+  template <class T> T *as() { return reinterpret_cast<T *>(p); }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct swb_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  // ---- work buffers of a solve
+  DBuf prm, res, g, E, c, dbar, rem, ftobj, bfkey, x, bf, nr, w;
+  DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask;
+  // ---- resident job table (by slot)
+  int nslots = 0;
+  DBuf t_off, t_E, t_nm, t_g, t_ns, t_ts, t_modes, t_mm, t_amp, s_r0, s_rl, s_cnt, s_vl, s_acc;
+  DBuf pool_pp, pool_bs;
+  int64_t pool_used = 0;
+  std::vector<int64_t> h_off;
+  std::vector<int32_t> h_E;
+  // ---- per-call forecast buffers
+  DBuf f_slots, f_prog, f_mend, f_mns, f_remfb, f_bffb, f_ampok, f_ampfb, f_ftest;
+  // pinned staging for the scalar results
+  swb_result *h_res = nullptr;
+  size_t h_res_cap = 0;
+};
+
+extern "C" {
+
+int swb_version(void) { return 100; }
+const char *swb_last_error(void) { return g_err.c_str(); }
+
+int swb_create(swb_ctx **out, int device) {
+  if (!out) return fail(SWB_ERR_ARG, "swb_create: out is null");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) return fail(SWB_ERR_CUDA, "swb_create: no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(SWB_ERR_ARG, "swb_create: bad device index");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(SWB_ERR_CUDA, "swb_create: libswb200 is built for sm_100a only (Blackwell B200)");
+  swb_ctx *c = new swb_ctx();
+  c->device = device;
+  CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  *out = c;
+  return 0;
+}
+
+void swb_destroy(swb_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  DBuf *all[] = {&c->prm, &c->res, &c->g, &c->E, &c->c, &c->dbar, &c->rem, &c->ftobj, &c->bfkey, &c->x,
+                 &c->bf, &c->nr, &c->w, &c->sa, &c->su0, &c->sR, &c->sws, &c->scap, &c->sg, &c->snF,
+                 &c->snmax, &c->sn, &c->gmask, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
+                 &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc,
+                 &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
+                 &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest};
+  for (DBuf *b : all) b->release();
+  if (c->h_res) cudaFreeHost(c->h_res);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+}
+
+void *swb_stream(swb_ctx *c) { return c ? (void *)c->st : nullptr; }
+int swb_sync(swb_ctx *c) {
+  if (!c) return fail(SWB_ERR_ARG, "null ctx");
+  CK(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+static int check_params(const swb_params *p, int S, int J) {
+  if (J <= 0 || J > SWB_MAX_J) return fail(SWB_ERR_ARG, "J must be in [1, 8192]");
+  for (int s = 0; s < S; ++s) {
+    if (p[s].future_rounds <= 0 || p[s].future_rounds > SWB_MAX_T)
+      return fail(SWB_ERR_ARG, "future_rounds must be in [1, 128]");
+    if (p[s].ngpus <= 0) return fail(SWB_ERR_ARG, "ngpus must be positive");
+    if (p[s].nbases < 2 || p[s].nbases > SWB_MAX_BASES) return fail(SWB_ERR_ARG, "nbases must be in [2,16]");
+    if (!(p[s].round_duration > 0.0)) return fail(SWB_ERR_ARG, "round_duration must be positive");
+    if (!(p[s].k > 0.0)) return fail(SWB_ERR_ARG, "k must be positive (shockwave.py:67)");
+  }
+  return 0;
+}
+
+static int ensure_scratch(swb_ctx *c, size_t n) {
+  CK(c->sa.need(n * 8, c->st));   CK(c->su0.need(n * 8, c->st)); CK(c->sR.need(n * 8, c->st));
+  CK(c->sws.need(n * 8, c->st));  CK(c->scap.need(n * 8, c->st));
+  CK(c->sg.need(n, c->st));       CK(c->snF.need(n, c->st));     CK(c->snmax.need(n, c->st));
+  CK(c->sn.need(n, c->st));       CK(c->w.need(n * 8, c->st));
+  return 0;
+}
+
+static int ensure_hres(swb_ctx *c, size_t S) {
+  if (S > c->h_res_cap) {
+    if (c->h_res) cudaFreeHost(c->h_res);
+    c->h_res = nullptr;
+    CK(cudaMallocHost((void **)&c->h_res, S * sizeof(swb_result)));
+    c->h_res_cap = S;
+  }
+  return 0;
+}
+
+// common tail: launch solve + place on device-resident inputs
+static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_prm, const int32_t *g,
+                     const int32_t *E, const int32_t *cc, const double *dbar, const double *rem,
+                     const double *ftobj, const double *bfkey, const double *rem_fb,
+                     const double *bfkey_fb, uint8_t *x, uint8_t *bf, int32_t *nr, double *weights) {
+  const size_t n = (size_t)S * J;
+  int rc = ensure_scratch(c, n);
+  if (rc) return rc;
+  CK(c->prm.need(sizeof(swb_params) * S, c->st));
+  CK(c->res.need(sizeof(swb_result) * S, c->st));
+  CK(cudaMemcpyAsync(c->prm.p, h_prm, sizeof(swb_params) * S, cudaMemcpyHostToDevice, c->st));
+  if (J > SWB_SMEM_JOBS) CK(c->gmask.need(n * 4 * sizeof(unsigned long long), c->st));
+  swb::SolveLaunch L;
+  L.S = S; L.J = J; L.per_scn = per_scn; L.jobs_in_smem = (J <= SWB_SMEM_JOBS) ? 1 : 0;
+  L.prm = c->prm.as<swb_params>();
+  L.g = g; L.E = E; L.c = cc; L.dbar = dbar; L.rem = rem; L.ftobj = ftobj; L.rem_fb = rem_fb;
+  L.sc_a = c->sa.as<double>(); L.sc_u0 = c->su0.as<double>(); L.sc_R = c->sR.as<double>();
+  L.sc_ws = c->sws.as<double>(); L.sc_cap = c->scap.as<double>();
+  L.sc_g = c->sg.as<uint8_t>(); L.sc_nF = c->snF.as<uint8_t>(); L.sc_nmax = c->snmax.as<uint8_t>();
+  L.sc_n = c->sn.as<uint8_t>();
+  L.weights = weights ? weights : c->w.as<double>();
+  L.res = c->res.as<swb_result>();
+  CK(swb::launch_solve(L, c->st));
+  swb::PlaceLaunch P;
+  P.S = S; P.J = J; P.per_scn = per_scn; P.prm = L.prm; P.bfkey = bfkey; P.bfkey_fb = bfkey_fb;
+  P.sc_a = L.sc_a; P.sc_u0 = L.sc_u0; P.sc_R = L.sc_R; P.sc_ws = L.sc_ws; P.sc_cap = L.sc_cap;
+  P.sc_g = L.sc_g; P.sc_n = L.sc_n; P.weights = L.weights;
+  P.x = x; P.backfill = bf; P.nrounds = nr; P.res = L.res;
+  CK(swb::launch_place(P, c->st, c->gmask.as<unsigned long long>()));
+  return 0;
+}
+
+int swb_solve(swb_ctx *c, const swb_solve_args *a) {
+  if (!c || !a) return fail(SWB_ERR_ARG, "swb_solve: null argument");
+  if (a->S <= 0) return fail(SWB_ERR_ARG, "swb_solve: S must be positive");
+  if (!a->prm || !a->res || !a->g || !a->E || !a->c || !a->dbar || !a->rem || !a->ftobj)
+    return fail(SWB_ERR_ARG, "swb_solve: missing input pointer");
+  int rc = check_params(a->prm, a->S, a->J);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  const int S = a->S, J = a->J, T = a->prm[0].future_rounds;
+  for (int s = 1; s < S; ++s)
+    if (a->prm[s].future_rounds != T)
+      return fail(SWB_ERR_ARG, "swb_solve: all scenarios of one call must share future_rounds");
+  const size_t nj = a->per_scenario_jobs ? (size_t)S * J : (size_t)J;
+  const size_t nx = (size_t)S * J * T;
+  const int32_t *g, *E, *cc;
+  const double *dbar, *rem, *ftobj, *bfkey;
+  uint8_t *x, *bf;
+  int32_t *nr;
+  double *w;
+  if (a->on_device) {
+    g = a->g; E = a->E; cc = a->c; dbar = a->dbar; rem = a->rem; ftobj = a->ftobj;
+    bfkey = a->bfkey ? a->bfkey : a->rem;
+    x = a->x; bf = a->backfill; nr = a->nrounds; w = a->weights;
+  } else {
+    CK(c->g.need(nj * 4, c->st)); CK(c->E.need(nj * 4, c->st)); CK(c->c.need(nj * 4, c->st));
+    CK(c->dbar.need(nj * 8, c->st)); CK(c->rem.need(nj * 8, c->st)); CK(c->ftobj.need(nj * 8, c->st));
+    CK(c->bfkey.need(nj * 8, c->st));
+    CK(cudaMemcpyAsync(c->g.p, a->g, nj * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->E.p, a->E, nj * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->c.p, a->c, nj * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->dbar.p, a->dbar, nj * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->rem.p, a->rem, nj * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->ftobj.p, a->ftobj, nj * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->bfkey.p, a->bfkey ? a->bfkey : a->rem, nj * 8, cudaMemcpyHostToDevice, c->st));
+    g = c->g.as<int32_t>(); E = c->E.as<int32_t>(); cc = c->c.as<int32_t>();
+    dbar = c->dbar.as<double>(); rem = c->rem.as<double>(); ftobj = c->ftobj.as<double>();
+    bfkey = c->bfkey.as<double>();
+    x = nullptr; bf = nullptr; nr = nullptr; w = nullptr;
+    if (a->x) { CK(c->x.need(nx, c->st)); x = c->x.as<uint8_t>(); }
+    if (a->backfill) { CK(c->bf.need(nx, c->st)); bf = c->bf.as<uint8_t>(); }
+    if (a->nrounds) { CK(c->nr.need((size_t)S * J * 4, c->st)); nr = c->nr.as<int32_t>(); }
+  }
+  rc = run_solve(c, S, J, a->per_scenario_jobs, a->prm, g, E, cc, dbar, rem, ftobj, bfkey, nullptr,
+                 nullptr, x, bf, nr, w);
+  if (rc) return rc;
+  rc = ensure_hres(c, S);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(c->h_res, c->res.p, sizeof(swb_result) * S, cudaMemcpyDeviceToHost, c->st));
+  if (!a->on_device) {
+    if (a->x) CK(cudaMemcpyAsync(a->x, x, nx, cudaMemcpyDeviceToHost, c->st));
+    if (a->backfill) CK(cudaMemcpyAsync(a->backfill, bf, nx, cudaMemcpyDeviceToHost, c->st));
+    if (a->nrounds) CK(cudaMemcpyAsync(a->nrounds, nr, (size_t)S * J * 4, cudaMemcpyDeviceToHost, c->st));
+    if (a->weights)
+      CK(cudaMemcpyAsync(a->weights, c->w.p, (size_t)S * J * 8, cudaMemcpyDeviceToHost, c->st));
+  }
+  CK(cudaStreamSynchronize(c->st));
+  memcpy(a->res, c->h_res, sizeof(swb_result) * S);
+  int any_fb = 0;
+  for (int s = 0; s < S; ++s) any_fb |= (a->res[s].status == SWB_ST_FALLBACK);
+  return any_fb ? SWB_ST_FALLBACK : SWB_ST_OK;
+}
+
+// ---- resident job table -------------------------------------------------------------------------
+static int ensure_slots(swb_ctx *c, int nslots) {
+  if (nslots <= c->nslots) return 0;
+  size_t n = (size_t)nslots;
+  CK(c->t_off.need(n * 8, c->st, true)); CK(c->t_E.need(n * 4, c->st, true));
+  CK(c->t_nm.need(n * 4, c->st, true));  CK(c->t_g.need(n * 4, c->st, true));
+  CK(c->t_ns.need(n * 8, c->st, true));  CK(c->t_ts.need(n * 8, c->st, true));
+  CK(c->t_modes.need(n * 4 * SWB_MAX_MODES, c->st, true));
+  CK(c->t_mm.need(n * 8 * SWB_MAX_MODES, c->st, true));
+  CK(c->t_amp.need(n * 8, c->st, true));
+  CK(c->s_r0.need(n * 4, c->st, true)); CK(c->s_rl.need(n * 4, c->st, true));
+  CK(c->s_cnt.need(n * 4, c->st, true)); CK(c->s_vl.need(n * 8, c->st, true));
+  CK(c->s_acc.need(n * 8, c->st, true));
+  c->nslots = nslots;
+  c->h_off.resize(n, -1);
+  c->h_E.resize(n, 0);
+  return 0;
+}
+
+int swb_job_add(swb_ctx *c, int32_t slot, int32_t nworkers, int32_t epochs, double epoch_nsamples,
+                double timestamp_submit, const double *pre, const int32_t *bs) {
+  if (!c || !pre || !bs) return fail(SWB_ERR_ARG, "swb_job_add: null argument");
+  if (slot < 0 || epochs <= 0) return fail(SWB_ERR_ARG, "swb_job_add: bad slot / epochs");
+  if (nworkers <= 0 || nworkers > 255) return fail(SWB_ERR_ARG, "swb_job_add: nworkers must be in [1,255]");
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_slots(c, slot + 1);
+  if (rc) return rc;
+  // host-side digest of the static profile: prefix sums (sequential, like the reference's running
+  // `preprofiled_time_range += duration`, JobMetaData.py:253-257), sorted bs modes
+  // (JobMetaData.py:296), per-mode mean duration (JobMetaData.py:304-312, pairwise like np.mean).
+  std::vector<double> pp((size_t)epochs + 1);
+  pp[0] = 0.0;
+  for (int e = 0; e < epochs; ++e) pp[e + 1] = pp[e] + pre[e];
+  std::vector<int32_t> modes;
+  for (int e = 0; e < epochs; ++e) {
+    bool seen = false;
+    for (int32_t m : modes) if (m == bs[e]) { seen = true; break; }
+    if (!seen) modes.push_back(bs[e]);
+  }
+  if ((int)modes.size() > SWB_MAX_MODES) return fail(SWB_ERR_ARG, "swb_job_add: more than 16 batch-size modes");
+  for (size_t i = 1; i < modes.size(); ++i)
+    for (size_t k = i; k > 0 && modes[k - 1] > modes[k]; --k) std::swap(modes[k - 1], modes[k]);
+  int32_t hm[SWB_MAX_MODES] = {0};
+  double hmm[SWB_MAX_MODES] = {0};
+  std::vector<double> tmp;
+  for (size_t m = 0; m < modes.size(); ++m) {
+    hm[m] = modes[m];
+    tmp.clear();
+    for (int e = 0; e < epochs; ++e) if (bs[e] == modes[m]) tmp.push_back(pre[e]);
+    // numpy's pairwise summation (blocks of 8 accumulators below 128 elements)
+    struct PW {
+      static double sum(const double *a, size_t n) {
+        if (n < 8) { double r = 0.0; for (size_t i = 0; i < n; ++i) r += a[i]; return r; }
+        if (n <= 128) {
+          double r[8];
+          for (int i = 0; i < 8; ++i) r[i] = a[i];
+          size_t i = 8;
+          for (; i + 8 <= n; i += 8) for (int k = 0; k < 8; ++k) r[k] += a[i + k];
+          double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+          for (; i < n; ++i) res += a[i];
+          return res;
+        }
+        size_t n2 = n / 2;
+        n2 -= n2 % 8;
+        return sum(a, n2) + sum(a + n2, n - n2);
+      }
+    };
+    hmm[m] = PW::sum(tmp.data(), tmp.size()) / (double)tmp.size();
+  }
+  const int64_t off = c->pool_used;
+  const size_t rows = (size_t)epochs + 1;
+  CK(c->pool_pp.need((off + rows) * 8, c->st, true));
+  CK(c->pool_bs.need((off + rows) * 4, c->st, true));
+  CK(cudaMemcpyAsync(c->pool_pp.as<double>() + off, pp.data(), rows * 8, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->pool_bs.as<int32_t>() + off, bs, (size_t)epochs * 4, cudaMemcpyHostToDevice, c->st));
+  c->pool_used += rows;
+  c->h_off[slot] = off;
+  c->h_E[slot] = epochs;
+  const int32_t nm = (int32_t)modes.size(), zero = 0;
+  const double one = 1.0, dzero = 0.0;
+  CK(cudaMemcpyAsync(c->t_off.as<int64_t>() + slot, &off, 8, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->t_E.as<int32_t>() + slot, &epochs, 4, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->t_nm.as<int32_t>() + slot, &nm, 4, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->t_g.as<int32_t>() + slot, &nworkers, 4, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->t_ns.as<double>() + slot, &epoch_nsamples, 8, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->t_ts.as<double>() + slot, &timestamp_submit, 8, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->t_modes.as<int32_t>() + (size_t)slot * SWB_MAX_MODES, hm, sizeof(hm),
+                     cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->t_mm.as<double>() + (size_t)slot * SWB_MAX_MODES, hmm, sizeof(hmm),
+                     cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->t_amp.as<double>() + slot, &one, 8, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->s_cnt.as<int32_t>() + slot, &zero, 4, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->s_acc.as<double>() + slot, &dzero, 8, cudaMemcpyHostToDevice, c->st));
+  CK(cudaStreamSynchronize(c->st));  // the staging vectors die with this frame
+  return 0;
+}
+
+int swb_job_remove(swb_ctx *c, int32_t slot) {
+  if (!c || slot < 0 || slot >= c->nslots || c->h_off[slot] < 0)
+    return fail(SWB_ERR_ARG, "swb_job_remove: unknown slot");
+  // pool rows of a removed job are reclaimed only when they sit at the end of the pool
+  if (c->h_off[slot] + c->h_E[slot] + 1 == c->pool_used) c->pool_used = c->h_off[slot];
+  c->h_off[slot] = -1;
+  return 0;
+}
+
+static int run_forecast(swb_ctx *c, const swb_params *prm, const swb_round_args *a) {
+  const int J = a->J;
+  for (int j = 0; j < J; ++j) {
+    const int s = a->slots[j];
+    if (s < 0 || s >= c->nslots || c->h_off[s] < 0) return fail(SWB_ERR_ARG, "unknown job slot");
+    if (a->epoch_progress[j] < 0 || a->epoch_progress[j] > c->h_E[s])
+      return fail(SWB_ERR_ARG, "epoch_progress out of range (JobMetaData.py:164)");
+  }
+  CK(c->f_slots.need(J * 4, c->st)); CK(c->f_prog.need(J * 4, c->st)); CK(c->f_mend.need(J * 4, c->st));
+  CK(c->f_mns.need(J * 8, c->st));
+  CK(c->g.need(J * 4, c->st)); CK(c->E.need(J * 4, c->st)); CK(c->c.need(J * 4, c->st));
+  CK(c->dbar.need(J * 8, c->st)); CK(c->rem.need(J * 8, c->st)); CK(c->ftobj.need(J * 8, c->st));
+  CK(c->bfkey.need(J * 8, c->st)); CK(c->f_remfb.need(J * 8, c->st)); CK(c->f_bffb.need(J * 8, c->st));
+  CK(c->f_ampok.need(J * 8, c->st)); CK(c->f_ampfb.need(J * 8, c->st)); CK(c->f_ftest.need(J * 8, c->st));
+  CK(cudaMemcpyAsync(c->f_slots.p, a->slots, J * 4, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->f_prog.p, a->epoch_progress, J * 4, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->f_mend.p, a->meas_end_round, J * 4, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->f_mns.p, a->meas_nsamples, J * 8, cudaMemcpyHostToDevice, c->st));
+  swb::ForecastLaunch F;
+  F.J = J; F.reestimate_share = a->reestimate_share; F.round_ptr = prm->round_ptr; F.ngpus = prm->ngpus;
+  F.gavel_round_duration = a->gavel_round_duration;
+  F.slots = c->f_slots.as<int32_t>(); F.progress = c->f_prog.as<int32_t>();
+  F.meas_end = c->f_mend.as<int32_t>(); F.meas_ns = c->f_mns.as<double>();
+  F.tab_off = c->t_off.as<int64_t>(); F.tab_E = c->t_E.as<int32_t>(); F.tab_nmodes = c->t_nm.as<int32_t>();
+  F.tab_g = c->t_g.as<int32_t>(); F.tab_nsamples = c->t_ns.as<double>(); F.tab_tsubmit = c->t_ts.as<double>();
+  F.tab_modes = c->t_modes.as<int32_t>(); F.tab_modemean = c->t_mm.as<double>(); F.tab_amp = c->t_amp.as<double>();
+  F.ss_r0 = c->s_r0.as<int32_t>(); F.ss_rlast = c->s_rl.as<int32_t>(); F.ss_cnt = c->s_cnt.as<int32_t>();
+  F.ss_vlast = c->s_vl.as<double>(); F.ss_acc = c->s_acc.as<double>();
+  F.pool_prefix = c->pool_pp.as<double>(); F.pool_bs = c->pool_bs.as<int32_t>();
+  F.dbar = c->dbar.as<double>(); F.rem = c->rem.as<double>(); F.ftobj = c->ftobj.as<double>();
+  F.bfkey = c->bfkey.as<double>(); F.ftest = c->f_ftest.as<double>();
+  F.rem_fb = c->f_remfb.as<double>(); F.bfkey_fb = c->f_bffb.as<double>();
+  F.amp_ok = c->f_ampok.as<double>(); F.amp_fb = c->f_ampfb.as<double>();
+  F.g_out = c->g.as<int32_t>(); F.E_out = c->E.as<int32_t>(); F.c_out = c->c.as<int32_t>();
+  CK(swb::launch_forecast(F, c->st));
+  return 0;
+}
+
+int swb_round_solve(swb_ctx *c, const swb_params *prm, const swb_round_args *a) {
+  if (!c || !prm || !a || !a->slots || !a->epoch_progress || !a->meas_nsamples || !a->meas_end_round ||
+      !a->res)
+    return fail(SWB_ERR_ARG, "swb_round_solve: null argument");
+  int rc = check_params(prm, 1, a->J);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  const int J = a->J, T = prm->future_rounds;
+  rc = run_forecast(c, prm, a);
+  if (rc) return rc;
+  const size_t nx = (size_t)J * T;
+  CK(c->x.need(nx, c->st)); CK(c->bf.need(nx, c->st)); CK(c->nr.need((size_t)J * 4, c->st));
+  rc = run_solve(c, 1, J, 0, prm, c->g.as<int32_t>(), c->E.as<int32_t>(), c->c.as<int32_t>(),
+                 c->dbar.as<double>(), c->rem.as<double>(), c->ftobj.as<double>(), c->bfkey.as<double>(),
+                 c->f_remfb.as<double>(), c->f_bffb.as<double>(), c->x.as<uint8_t>(), c->bf.as<uint8_t>(),
+                 c->nr.as<int32_t>(), nullptr);
+  if (rc) return rc;
+  CK(swb::launch_commit_amp(J, c->f_slots.as<int32_t>(), c->res.as<swb_result>(), c->f_ampok.as<double>(),
+                            c->f_ampfb.as<double>(), c->t_amp.as<double>(), c->st));
+  rc = ensure_hres(c, 1);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(c->h_res, c->res.p, sizeof(swb_result), cudaMemcpyDeviceToHost, c->st));
+  if (a->x) CK(cudaMemcpyAsync(a->x, c->x.p, nx, cudaMemcpyDeviceToHost, c->st));
+  if (a->backfill) CK(cudaMemcpyAsync(a->backfill, c->bf.p, nx, cudaMemcpyDeviceToHost, c->st));
+  if (a->nrounds) CK(cudaMemcpyAsync(a->nrounds, c->nr.p, (size_t)J * 4, cudaMemcpyDeviceToHost, c->st));
+  if (a->forecast_out) {
+    double *fo = a->forecast_out;  // [6][J] planes: dbar, rem, ftobj, bfkey, rem_fb, bfkey_fb
+    CK(cudaMemcpyAsync(fo, c->dbar.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fo + J, c->rem.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fo + 2 * (size_t)J, c->ftobj.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fo + 3 * (size_t)J, c->bfkey.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fo + 4 * (size_t)J, c->f_remfb.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fo + 5 * (size_t)J, c->f_bffb.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+  }
+  CK(cudaStreamSynchronize(c->st));
+  *a->res = *c->h_res;
+  return a->res->status == SWB_ST_FALLBACK ? SWB_ST_FALLBACK : SWB_ST_OK;
+}
+
+int swb_forecast(swb_ctx *c, const swb_params *prm, const swb_round_args *a, double *dbar, double *rem,
+                 double *ftobj, double *bfkey, double *ft_estimate) {
+  if (!c || !prm || !a) return fail(SWB_ERR_ARG, "swb_forecast: null argument");
+  if (a->J <= 0) return fail(SWB_ERR_ARG, "swb_forecast: J must be positive");
+  CK(cudaSetDevice(c->device));
+  int rc = run_forecast(c, prm, a);
+  if (rc) return rc;
+  const int J = a->J;
+  // forecast-only calls keep the "no fallback" continuation of the calibration state
+  CK(c->res.need(sizeof(swb_result), c->st));
+  CK(cudaMemsetAsync(c->res.p, 0, sizeof(swb_result), c->st));
+  CK(swb::launch_commit_amp(J, c->f_slots.as<int32_t>(), c->res.as<swb_result>(), c->f_ampok.as<double>(),
+                            c->f_ampfb.as<double>(), c->t_amp.as<double>(), c->st));
+  if (dbar) CK(cudaMemcpyAsync(dbar, c->dbar.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+  if (rem) CK(cudaMemcpyAsync(rem, c->rem.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+  if (ftobj) CK(cudaMemcpyAsync(ftobj, c->ftobj.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+  if (bfkey) CK(cudaMemcpyAsync(bfkey, c->bfkey.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+  if (ft_estimate) CK(cudaMemcpyAsync(ft_estimate, c->f_ftest.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+}  // extern "C"

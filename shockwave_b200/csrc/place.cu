@@ -1,0 +1,306 @@
+// place.cu — dense J x T placement of the solved round counts, objective re-evaluation on the
+// placed schedule, and the work-conserving back-fill.
+//
+// Reference behaviour replaced:
+//   * the x[j][t] values Gurobi returns for a given set of per-job counts (any permutation of rounds
+//     is equally optimal for the MILP) — here a deterministic least-laxity-first
+//     sweep over the T rounds: every round seats the jobs that can no longer wait, then the jobs
+//     with most planned rounds left, wider gangs first, lower job index first;
+//   * rank_in_schedule_jobs() (scheduler/shockwave.py:714-793), the second MILP of the fallback
+//     path: minimise sum_j prio_j * mean round index — here the same sweep keyed by
+//     prio_j / (n_j g_j) (the exchange-argument order for that linear objective);
+//   * construct_schedules() (shockwave.py:213-285): per round, idle GPUs are back-filled with the
+//     not-yet-scheduled jobs in descending remaining-runtime order (stable) that still fit.
+//
+// One CTA per scenario.  Round masks (128 bit per job) live in shared memory for J <= 4096.
+#include <math.h>
+
+#include "swb_common.cuh"
+#include "swb_internal.h"
+
+namespace swb {
+
+__device__ __forceinline__ unsigned long long dbl_order_key(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);  // ascending order-preserving
+}
+
+// bitonic sort, DESCENDING by (key, then ascending idx) over n = power of two entries
+__device__ void sort_desc64(unsigned long long *key, unsigned short *idx, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int p = i ^ j;
+        if (p > i) {
+          const unsigned long long a = key[i], b = key[p];
+          const unsigned short ia = idx[i], ib = idx[p];
+          const bool a_first = (a > b) || (a == b && ia < ib);  // a belongs before b
+          const bool up = (i & k) == 0;
+          if (up != a_first) { key[i] = b; key[p] = a; idx[i] = ib; idx[p] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ void sort_desc32(unsigned int *key, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int p = i ^ j;
+        if (p > i) {
+          const unsigned int a = key[i], b = key[p];
+          const bool up = (i & k) == 0;
+          if (up != (a > b)) { key[i] = b; key[p] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// exclusive block scan of one int per thread; returns the exclusive prefix, total in *tot
+__device__ __forceinline__ int block_excl_scan(int v, int *wsum, int *tot) {
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(SWB_FULL, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += t;
+  }
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();  // protect wsum from the previous use
+  if ((threadIdx.x & 31) == 31) wsum[w] = incl;
+  __syncthreads();
+  int off = 0, all = 0;
+  for (int i = 0; i < nw; ++i) { const int x = wsum[i]; all += x; if (i < w) off += x; }
+  *tot = all;
+  return off + incl - v;
+}
+
+__global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch L, unsigned long long *gmask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int s = blockIdx.x, J = L.J;
+  const swb_params &prm = L.prm[s];
+  const int T = prm.future_rounds, G = prm.ngpus;
+  const size_t so = (size_t)s * J;
+  int npad = 64;
+  while (npad < J) npad <<= 1;
+
+  // ---- shared-memory carve-up -------------------------------------------------------------
+  unsigned char *p = smem_raw;
+  double *red = reinterpret_cast<double *>(p); p += 2 * 64 * sizeof(double);
+  int *wsum = reinterpret_cast<int *>(p);      p += 32 * sizeof(int);
+  int *idle = reinterpret_cast<int *>(p);      p += SWB_MAX_T * sizeof(int);
+  // union region: {key64[npad], idx16[npad]}  or  {key32[npad], sel8[npad]}
+  unsigned long long *key64 = reinterpret_cast<unsigned long long *>(p);
+  unsigned int *key32 = reinterpret_cast<unsigned int *>(p);
+  unsigned short *idx16 = reinterpret_cast<unsigned short *>(p + 8 * (size_t)npad);
+  unsigned char *sel = p + 4 * (size_t)npad;
+  p += 10 * (size_t)npad;
+  unsigned short *rank = reinterpret_cast<unsigned short *>(p);  p += 2 * (size_t)npad;
+  unsigned short *order = reinterpret_cast<unsigned short *>(p); p += 2 * (size_t)npad;
+  unsigned char *gs = p;   p += npad;
+  unsigned char *remn = p; p += npad;
+  p = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
+  unsigned long long *xm, *bm;  // [J][2] each
+  if (J <= SWB_SMEM_JOBS) {
+    xm = reinterpret_cast<unsigned long long *>(p);
+    bm = xm + 2 * (size_t)J;
+  } else {
+    xm = gmask + (size_t)s * 4 * J;
+    bm = xm + 2 * (size_t)J;
+  }
+  BlockRed br(red);
+  const bool fallback = (L.res[s].status == SWB_ST_FALLBACK);
+  const uint8_t *nplan = L.sc_n + so;
+  const uint8_t *gI = L.sc_g + so;
+
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    gs[j] = gI[j]; remn[j] = nplan[j];
+    xm[2 * j] = 0; xm[2 * j + 1] = 0; bm[2 * j] = 0; bm[2 * j + 1] = 0;
+  }
+  __syncthreads();
+
+  // ---- back-fill order: descending remaining runtime, stable (shockwave.py:261-267) ---------
+  {
+    const double *bk = ((fallback && L.bfkey_fb) ? L.bfkey_fb : L.bfkey) + (L.per_scn ? so : 0);
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+      key64[i] = (i < J) ? dbl_order_key(bk[i]) : 0ull;
+      idx16[i] = (unsigned short)(i < J ? i : 0xffff);
+    }
+    __syncthreads();
+    sort_desc64(key64, idx16, npad);
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) order[i] = idx16[i];
+    __syncthreads();
+  }
+  // ---- fallback re-rank order: prio_j / (n_j g_j) descending ---------------------------------
+  if (fallback && L.weights) {
+    const double *wj = L.weights + so;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+      double d = -1.0;
+      if (i < J && nplan[i] > 0) d = wj[i] / ((double)nplan[i] * (double)gs[i]);
+      key64[i] = (i < J) ? dbl_order_key(d) : 0ull;
+      idx16[i] = (unsigned short)(i < J ? i : 0xffff);
+    }
+    __syncthreads();
+    sort_desc64(key64, idx16, npad);
+    for (int i = threadIdx.x; i < npad; i += blockDim.x)
+      if (idx16[i] != 0xffff) rank[idx16[i]] = (unsigned short)i;
+    __syncthreads();
+  }
+
+  // ---- least-laxity-first sweep over the rounds ----------------------------------------------
+  const int ch = (npad + blockDim.x - 1) / blockDim.x;  // consecutive sorted positions per thread
+  for (int t = 0; t < T; ++t) {
+    const int tau = T - t;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+      unsigned int k = 0;
+      if (i < J && remn[i] > 0) {
+        const unsigned int r = remn[i];
+        const unsigned int crit = (r >= (unsigned)tau) ? 1u : 0u;
+        const unsigned int prim = (fallback && L.weights)
+            ? ((unsigned)(SWB_MAX_J - rank[i]) << 13)
+            : ((r << 21) | ((unsigned)gs[i] << 13));
+        k = (crit << 30) | prim | (unsigned)(SWB_MAX_J - 1 - i);
+      }
+      key32[i] = k;
+      sel[i] = 0;
+    }
+    __syncthreads();
+    sort_desc32(key32, npad);
+    int capleft = G;
+    for (int pass = 0; pass < 64 && capleft > 0; ++pass) {
+      const int p0 = threadIdx.x * ch;
+      int lsum = 0;
+      for (int q = 0; q < ch; ++q) {
+        const int pos = p0 + q;
+        if (pos < npad) {
+          const unsigned int k = key32[pos];
+          if (k != 0 && !sel[pos]) {
+            const int g = gs[SWB_MAX_J - 1 - (k & (SWB_MAX_J - 1))];
+            if (g <= capleft) lsum += g;
+          }
+        }
+      }
+      int tot = 0;
+      int run = block_excl_scan(lsum, wsum, &tot);
+      if (tot == 0) break;
+      int took = 0;
+      for (int q = 0; q < ch; ++q) {
+        const int pos = p0 + q;
+        if (pos < npad) {
+          const unsigned int k = key32[pos];
+          if (k != 0 && !sel[pos]) {
+            const int g = gs[SWB_MAX_J - 1 - (k & (SWB_MAX_J - 1))];
+            if (g <= capleft) {
+              run += g;
+              if (run <= capleft) { sel[pos] = 1; took += g; }
+            }
+          }
+        }
+      }
+      const int taken = (int)br.sumll((long long)took);
+      capleft -= taken;
+      if (taken == tot) break;  // every eligible job seated
+      __syncthreads();
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+      if (sel[i]) {
+        const int j = SWB_MAX_J - 1 - (key32[i] & (SWB_MAX_J - 1));
+        xm[2 * j + (t >> 6)] |= 1ull << (t & 63);
+        remn[j] = (unsigned char)(remn[j] - 1);
+      }
+    }
+    if (threadIdx.x == 0) idle[t] = capleft;
+    __syncthreads();
+  }
+
+  // ---- objective of the PLACED schedule (what a checker recomputes from x) --------------------
+  {
+    Pwl P;
+    P.B = prm.nbases;
+    for (int b = 0; b < prm.nbases; ++b) { P.base[b] = prm.bases[b]; P.logv[b] = prm.logv[b]; }
+    for (int b = 0; b + 1 < prm.nbases; ++b)
+      P.slope[b] = (prm.logv[b + 1] - prm.logv[b]) / (prm.bases[b + 1] - prm.bases[b]);
+    double w = 0.0, me = 0.0;
+    long long shortf = 0;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      const int n = (int)nplan[j] - (int)remn[j];
+      shortf += remn[j];
+      w += L.sc_ws[so + j] * plog(P, fma(L.sc_a[so + j], (double)n, L.sc_u0[so + j]));
+      const double done = fmin(prm.round_duration * (double)n, L.sc_cap[so + j]);
+      me = fmax(me, fmax(0.0, L.sc_R[so + j] - done));
+      if (L.nrounds) L.nrounds[so + j] = n;
+    }
+    w = br.sum(w);
+    me = br.max(me);
+    shortf = br.sumll(shortf);
+    if (threadIdx.x == 0) {
+      swb_result &r = L.res[s];
+      r.welfare = w; r.makespan = me; r.objective = w - prm.k * me; r.shortfall = (int)shortf;
+    }
+  }
+
+  // ---- work-conserving back-fill: one warp per round walks the sorted order --------------------
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int t = warp; t < T; t += nw) {
+      int left = idle[t];
+      const int wi = t >> 6;
+      const unsigned long long bit = 1ull << (t & 63);
+      for (int base = 0; base < J && left > 0; base += 32) {
+        const int pos = base + lane;
+        int j = -1, g = 0;
+        if (pos < J) {
+          j = order[pos];
+          g = gs[j];
+          if (xm[2 * j + wi] & bit) j = -1;
+        }
+        unsigned int m = __ballot_sync(SWB_FULL, j >= 0 && g <= left);
+        while (m && left > 0) {
+          const int l = __ffs(m) - 1;
+          m &= m - 1;
+          const int gl = __shfl_sync(SWB_FULL, g, l);
+          if (gl <= left) {
+            left -= gl;
+            if (lane == l) atomicOr(&bm[2 * j + wi], bit);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- write the byte matrices, coalesced ------------------------------------------------------
+  const size_t xo = so * (size_t)T;
+  const int total = J * T;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int j = e / T, t = e - j * T;
+    const int wi = t >> 6;
+    const unsigned long long bit = 1ull << (t & 63);
+    if (L.x) L.x[xo + e] = (xm[2 * j + wi] & bit) ? 1 : 0;
+    if (L.backfill) L.backfill[xo + e] = (bm[2 * j + wi] & bit) ? 1 : 0;
+  }
+}
+
+cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask) {
+  int npad = 64;
+  while (npad < L.J) npad <<= 1;
+  size_t smem = 2 * 64 * sizeof(double) + 32 * sizeof(int) + SWB_MAX_T * sizeof(int) +
+                10 * (size_t)npad + 4 * (size_t)npad + 2 * (size_t)npad + 16;
+  if (L.J <= SWB_SMEM_JOBS) smem += 32 * (size_t)L.J;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SWB_MAX_DYN_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int nt = npad < SWB_PLACE_THREADS ? npad : SWB_PLACE_THREADS;
+  place_kernel<<<L.S, nt, smem, st>>>(L, gmask);
+  return cudaGetLastError();
+}
+
+}  // namespace swb

@@ -1,0 +1,401 @@
+// solve.cu — the per-round market solve of Shockwave on one B200 (sm_100a).
+//
+// Replaces dynamic_eisenberg_gale_scheduling() (reference scheduler/shockwave.py:504-711): the
+// cvxpy model build + Gurobi branch-and-bound.  The MILP's objective depends on x[j][t] only through
+// the per-job round counts n_j = sum_t x[j][t] (shockwave.py:371-377), p_j is best at
+// min(D n_j / dbar_j, E_j - c_j), and the SOS2 binaries (shockwave.py:403-419) are redundant for a
+// concave maximise, so the program collapses to
+//     max_n  sum_j w_j plog((c_j + min(D n_j/dbar_j, E_j-c_j))/E_j)/(J T)  -  k max_j rem_j(n_j)
+//     s.t.   sum_j g_j n_j <= G T,   nF_j <= n_j <= T            (nF_j from the FTF rows, :573-597)
+// which is solved here exactly in its Lagrangian form: a clearing price mu on GPU-rounds found by
+// bisection (every job answers a price with a closed-form best response on its piecewise-linear
+// utility) nested in a search over the makespan threshold M.  One CTA per scenario; job constants
+// are staged in shared memory; all reductions are warp shuffles + one barrier.
+// The dense J x T placement (which round each of the n_j rounds lands in) is place.cu.
+#include <math.h>
+
+#include "swb_common.cuh"
+#include "swb_internal.h"
+
+namespace swb {
+
+#define MU_ITERS 44
+
+struct JobsV {  // job constants of one scenario, in shared memory (J <= SWB_SMEM_JOBS) or global
+  double *a, *u0, *R, *ws, *cap;
+  uint8_t *g, *nF, *nmax, *n;
+};
+
+struct Ctx {
+  const Pwl *P;
+  JobsV v;
+  int J, T, GT;
+  double D;
+};
+
+// closed-form best response of job j to a price mu (welfare per GPU-round): the largest n with
+// F_j(n) - F_j(n-1) > mu g_j.  Rounds that lie wholly in PWL segments of slope > theta pass,
+// rounds wholly in flatter segments fail, the one straddling round is tested explicitly.
+__device__ __forceinline__ int pref_n(const Ctx &c, int j, double mu) {
+  const int nmax = c.v.nmax[j];
+  if (nmax == 0 || mu <= 0.0) return nmax;
+  const Pwl &P = *c.P;
+  const double a = c.v.a[j], u0 = c.v.u0[j], ws = c.v.ws[j];
+  const double mg = mu * (double)c.v.g[j];
+  const double theta = mg / (a * ws);
+  int bs = 0;
+  for (int b = 0; b < P.B - 1; ++b) bs += (P.slope[b] > theta) ? 1 : 0;
+  int n0 = 0;
+  if (bs > 0) {
+    const double nb = (P.base[bs] - u0) / a;
+    n0 = nb <= 0.0 ? 0 : (nb >= (double)nmax ? nmax : (int)floor(nb));
+  }
+  if (n0 < nmax) {
+    const double d = ws * (plog(P, fma(a, (double)(n0 + 1), u0)) - plog(P, fma(a, (double)n0, u0)));
+    n0 += (d > mg) ? 1 : 0;
+  }
+  return n0;
+}
+
+// rounds job j must get so that rem_j <= M  (rem_j = max(0, R_j - min(D n, cap_j)))
+__device__ __forceinline__ int lower_n(const Ctx &c, int j, double M) {
+  const double need = c.v.R[j] - M;
+  int L = 0;
+  if (need > 0.0) {
+    const double q = ceil(need / c.D - 1e-9);
+    L = q >= (double)c.v.nmax[j] ? c.v.nmax[j] : (int)q;
+  }
+  const int nF = c.v.nF[j];
+  return L > nF ? L : nF;
+}
+
+__device__ __forceinline__ int job_n(const Ctx &c, int j, double M, double mu) {
+  const int lb = lower_n(c, j, M), pf = pref_n(c, j, mu);
+  return lb > pf ? lb : pf;
+}
+
+__device__ __forceinline__ double rem_of(const Ctx &c, int j, int n) {
+  const double done = fmin(c.D * (double)n, c.v.cap[j]);
+  return fmax(0.0, c.v.R[j] - done);
+}
+
+__device__ __forceinline__ double util_of(const Ctx &c, int j, int n) {
+  return c.v.ws[j] * plog(*c.P, fma(c.v.a[j], (double)n, c.v.u0[j]));
+}
+
+__device__ long long cost_at(const Ctx &c, BlockRed &br, double M, double mu) {
+  long long s = 0;
+  for (int j = threadIdx.x; j < c.J; j += blockDim.x) s += (long long)c.v.g[j] * job_n(c, j, M, mu);
+  return br.sumll(s);
+}
+
+struct Price { double hi, lo; long long cost_hi; int iters; };
+
+// smallest price at which demand fits: cost(M, hi) <= GT < cost(M, lo)
+__device__ Price solve_price(const Ctx &c, BlockRed &br, double M, double mu_max) {
+  Price p;
+  p.iters = 1;
+  long long c0 = cost_at(c, br, M, 0.0);
+  if (c0 <= c.GT) { p.hi = p.lo = 0.0; p.cost_hi = c0; return p; }
+  double lo = 0.0, hi = mu_max;
+  long long chi = cost_at(c, br, M, hi);
+  p.iters++;
+  for (int it = 0; it < MU_ITERS; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    const long long cm = cost_at(c, br, M, mid);
+    p.iters++;
+    if (cm <= c.GT) { hi = mid; chi = cm; if (cm == c.GT) break; } else lo = mid;
+  }
+  p.hi = hi; p.lo = lo; p.cost_hi = chi;
+  return p;
+}
+
+struct Phi { double V, welfare, Meff, mu; long long cost; };
+
+// value of makespan threshold M: LP-style welfare at the clearing price minus k * achieved makespan
+__device__ Phi phi_at(const Ctx &c, BlockRed &br, double M, double mu_max, double k, int &iters) {
+  Price p = solve_price(c, br, M, mu_max);
+  iters += p.iters;
+  double w = 0.0, me = 0.0;
+  for (int j = threadIdx.x; j < c.J; j += blockDim.x) {
+    const int n = job_n(c, j, M, p.hi);
+    w += util_of(c, j, n);
+    me = fmax(me, rem_of(c, j, n));
+  }
+  w = br.sum(w);
+  me = br.max(me);
+  Phi r;
+  r.welfare = w; r.Meff = me; r.mu = p.hi; r.cost = p.cost_hi;
+  r.V = w + p.hi * (double)(c.GT - p.cost_hi) - k * me;
+  return r;
+}
+
+__global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch L) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int s = blockIdx.x;
+  const int J = L.J;
+  const swb_params &prm = L.prm[s];
+  const int T = prm.future_rounds, G = prm.ngpus;
+  const double D = prm.round_duration, k = prm.k;
+
+  // ---- shared-memory carve-up -------------------------------------------------------------
+  Pwl *P = reinterpret_cast<Pwl *>(smem_raw);
+  double *red = reinterpret_cast<double *>(smem_raw + SWB_PWL_BYTES);  // 2*64 doubles
+  unsigned char *p = smem_raw + SWB_PWL_BYTES + 2 * 64 * sizeof(double);
+  Ctx c;
+  const size_t so = (size_t)s * J;
+  if (L.jobs_in_smem) {
+    c.v.a = reinterpret_cast<double *>(p);   p += sizeof(double) * J;
+    c.v.u0 = reinterpret_cast<double *>(p);  p += sizeof(double) * J;
+    c.v.R = reinterpret_cast<double *>(p);   p += sizeof(double) * J;
+    c.v.ws = reinterpret_cast<double *>(p);  p += sizeof(double) * J;
+    c.v.cap = reinterpret_cast<double *>(p); p += sizeof(double) * J;
+    c.v.g = p;    p += J;
+    c.v.nF = p;   p += J;
+    c.v.nmax = p; p += J;
+  } else {
+    c.v.a = L.sc_a + so; c.v.u0 = L.sc_u0 + so; c.v.R = L.sc_R + so; c.v.ws = L.sc_ws + so;
+    c.v.cap = L.sc_cap + so; c.v.g = L.sc_g + so; c.v.nF = L.sc_nF + so; c.v.nmax = L.sc_nmax + so;
+  }
+  c.v.n = L.sc_n + so;
+  c.P = P; c.J = J; c.T = T; c.GT = G * T; c.D = D;
+  BlockRed br(red);
+
+  if (threadIdx.x == 0) {
+    P->B = prm.nbases;
+    for (int b = 0; b < prm.nbases; ++b) { P->base[b] = prm.bases[b]; P->logv[b] = prm.logv[b]; }
+    for (int b = 0; b + 1 < prm.nbases; ++b)
+      P->slope[b] = (prm.logv[b + 1] - prm.logv[b]) / (prm.bases[b + 1] - prm.bases[b]);
+  }
+  __syncthreads();
+
+  const size_t jo = L.per_scn ? so : 0;
+  const int32_t *gI = L.g + jo, *EI = L.E + jo, *cI = L.c + jo;
+  const double *dbarI = L.dbar + jo, *RI = L.rem + jo, *ftI = L.ftobj + jo;
+  const double *RfbI = L.rem_fb ? L.rem_fb + jo : RI;
+  const double share = fmin(1.0, (double)G / (double)J);
+  const double invJT = 1.0 / ((double)J * (double)T);
+  const double next_t = D * (double)(prm.round_ptr + T);
+
+  // ---- phase 1: job constants + finish-time-fairness rows (shockwave.py:573-597) -----------
+  long long infeasible = 0, forced = 0;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    const double Ef = (double)EI[j], cf = (double)cI[j], dbar = dbarI[j], R = RI[j];
+    const double cap = dbar * (Ef - cf);
+    const double a = D / (dbar * Ef);
+    int nfin = cap <= 0.0 ? 0 : (int)fmin(ceil(cap / D - 1e-9), 255.0);
+    const int nmax = nfin < T ? nfin : T;
+    c.v.a[j] = a; c.v.u0[j] = cf / Ef; c.v.R[j] = R; c.v.cap[j] = cap;
+    c.v.g[j] = (uint8_t)gI[j]; c.v.nmax[j] = (uint8_t)nmax;
+    const double capF = share * (prm.rhomax * ftI[j] - next_t);
+    int nF = 0, bad = 0;
+    if (capF < 0.0) bad = 1;
+    else {
+      const double need = R - capF;
+      if (need > 0.0) {
+        if (need > cap * (1.0 + 1e-12) + 1e-9) bad = 1;
+        else {
+          const double q = ceil(need / D - 1e-9);
+          if (q > (double)nmax) { if (q > (double)T) bad = 1; else nF = nmax; }
+          else nF = (int)q;
+        }
+      }
+    }
+    c.v.nF[j] = (uint8_t)nF;
+    infeasible += bad;
+    forced += (long long)gI[j] * nF;
+  }
+  infeasible = br.sumll(infeasible);
+  forced = br.sumll(forced);
+  const bool ftf_ok = (infeasible == 0) && (forced <= (long long)c.GT);
+
+  // fallback priorities (shockwave.py:830-911); weights stay 1 when the FTF rows are satisfiable
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    double w = 1.0;
+    if (!ftf_ok) {
+      c.v.nF[j] = 0;
+      const double R = RfbI[j];
+      const double ratio = (D * (double)prm.round_ptr + R / share) / ftI[j];
+      if (ratio > prm.rhomax) {
+        w = pow(ratio, (R < D) ? 1e2 : prm.lam);
+        w = fmin(w, 1e300);
+      }
+    }
+    c.v.ws[j] = w * invJT;
+    if (L.weights) L.weights[so + j] = w;
+  }
+  __syncthreads();
+
+  // ---- phase 2: price ceiling, makespan floor, smallest packable makespan -------------------
+  double mu_max = 0.0, mfloor = 0.0, mtop = 0.0;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    if (c.v.nmax[j] > 0)
+      mu_max = fmax(mu_max, (util_of(c, j, 1) - util_of(c, j, 0)) / (double)c.v.g[j]);
+    const double R = c.v.R[j];
+    mfloor = fmax(mfloor, fmax(R - c.v.cap[j], R - D * (double)T));
+    mtop = fmax(mtop, R);
+  }
+  mu_max = br.max(mu_max) * (1.0 + 1e-9) + 1e-300;
+  mfloor = fmax(0.0, br.max(mfloor));
+  mtop = br.max(mtop);
+  const double INF_M = 1e300;
+  const double eps = 1e-6 * D;
+
+  int m_evals = 0, iters = 0;
+  double mmin = mfloor;
+  if (cost_at(c, br, mfloor, mu_max) > c.GT) {  // forced demand only at the price ceiling
+    double lo = mfloor, hi = mtop;
+    for (int it = 0; it < 60 && hi - lo > 1e-9 * (1.0 + hi); ++it) {
+      const double mid = 0.5 * (lo + hi);
+      if (cost_at(c, br, mid, mu_max) <= c.GT) hi = mid; else lo = mid;
+      iters++;
+    }
+    mmin = hi;
+  }
+
+  // ---- phase 3: search the makespan threshold (value is concave in the relaxation) ----------
+  Phi nat = phi_at(c, br, INF_M, mu_max, k, iters); m_evals++;
+  double best_V = nat.V, best_thr = INF_M;
+  if (nat.Meff - eps >= mmin) {
+    Phi t2 = phi_at(c, br, nat.Meff - eps, mu_max, k, iters); m_evals++;
+    if (t2.V > nat.V) {
+      best_V = t2.V; best_thr = nat.Meff - eps;
+      double lo = mmin, hi = nat.Meff - eps;
+      Phi pl = phi_at(c, br, lo, mu_max, k, iters); m_evals++;
+      if (pl.V > best_V) { best_V = pl.V; best_thr = lo; }
+      for (int it = 0; it < 48 && hi - lo > eps; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        Phi p1 = phi_at(c, br, mid, mu_max, k, iters); m_evals++;
+        if (p1.V > best_V) { best_V = p1.V; best_thr = mid; }
+        const double below = p1.Meff - eps;
+        if (below < mmin) break;               // already at the smallest packable makespan
+        Phi p2 = phi_at(c, br, below, mu_max, k, iters); m_evals++;
+        if (p2.V > best_V) { best_V = p2.V; best_thr = below; }
+        if (p2.V > p1.V) hi = below; else lo = mid;
+      }
+    }
+  }
+
+  // ---- phase 4: integral allocation at the chosen threshold ----------------------------------
+  Price pr = solve_price(c, br, best_thr, mu_max);
+  iters += pr.iters;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) c.v.n[j] = (uint8_t)job_n(c, j, best_thr, pr.hi);
+  long long left = (long long)c.GT - pr.cost_hi;
+  __syncthreads();
+
+  // (a) ties at the clearing price: jobs whose demand jumps between pr.lo and pr.hi, in job order
+  __shared__ long long s_carry;
+  __shared__ long long s_wsum[32];
+  if (left > 0 && pr.lo < pr.hi) {
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < J; base += blockDim.x) {
+      const int j = base + threadIdx.x;
+      int extra = 0, gj = 1;
+      if (j < J) { gj = c.v.g[j]; extra = job_n(c, j, best_thr, pr.lo) - (int)c.v.n[j]; if (extra < 0) extra = 0; }
+      long long v = (long long)gj * extra, incl = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        long long t = __shfl_up_sync(SWB_FULL, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+      }
+      if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = incl;
+      __syncthreads();
+      long long woff = 0;
+      for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += s_wsum[w];
+      const long long carry = s_carry;
+      const long long excl = carry + woff + incl - v;
+      if (j < J && extra > 0) {
+        long long room = left - excl;
+        if (room > 0) {
+          long long take = room / gj;
+          if (take > extra) take = extra;
+          c.v.n[j] = (uint8_t)(c.v.n[j] + take);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + incl;
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // (b) completion: best remaining item that still fits, a few times
+  {
+    long long used = 0;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) used += (long long)c.v.g[j] * c.v.n[j];
+    used = br.sumll(used);
+    left = (long long)c.GT - used;
+    for (int rep = 0; rep < 32 && left > 0; ++rep) {
+      double bd = 0.0;
+      for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        const int n = c.v.n[j];
+        if (n < c.v.nmax[j] && (long long)c.v.g[j] <= left)
+          bd = fmax(bd, (util_of(c, j, n + 1) - util_of(c, j, n)) / (double)c.v.g[j]);
+      }
+      bd = br.max(bd);
+      if (!(bd > 0.0)) break;
+      double bj = 1e300;
+      for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        const int n = c.v.n[j];
+        if (n < c.v.nmax[j] && (long long)c.v.g[j] <= left &&
+            (util_of(c, j, n + 1) - util_of(c, j, n)) / (double)c.v.g[j] >= bd)
+          bj = fmin(bj, (double)j);
+      }
+      bj = br.min(bj);
+      if (bj >= 1e299) break;
+      const int wj = (int)bj;
+      if (threadIdx.x == 0) c.v.n[wj] = (uint8_t)(c.v.n[wj] + 1);
+      left -= c.v.g[wj];
+      __syncthreads();
+    }
+  }
+
+  // ---- phase 5: scalars of the plan ---------------------------------------------------------
+  double w = 0.0, me = 0.0;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    const int n = c.v.n[j];
+    w += util_of(c, j, n);
+    me = fmax(me, rem_of(c, j, n));
+  }
+  w = br.sum(w);
+  me = br.max(me);
+  if (!L.jobs_in_smem) __threadfence_block();
+  else {
+    // the placement kernel re-reads the job constants from global scratch
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      L.sc_a[so + j] = c.v.a[j]; L.sc_u0[so + j] = c.v.u0[j]; L.sc_R[so + j] = c.v.R[j];
+      L.sc_ws[so + j] = c.v.ws[j]; L.sc_cap[so + j] = c.v.cap[j]; L.sc_g[so + j] = c.v.g[j];
+      L.sc_nF[so + j] = c.v.nF[j]; L.sc_nmax[so + j] = c.v.nmax[j];
+    }
+  }
+  if (threadIdx.x == 0) {
+    swb_result &r = L.res[s];
+    r.status = ftf_ok ? SWB_ST_OK : SWB_ST_FALLBACK;
+    r.m_evals = m_evals;
+    r.mu_iters = iters;
+    r.shortfall = 0;
+    r.welfare = w;
+    r.makespan = me;
+    r.objective = w - k * me;
+    r.price = pr.hi;
+    r.relaxed_objective = best_V;
+  }
+}
+
+cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st) {
+  size_t smem = SWB_PWL_BYTES + 2 * 64 * sizeof(double);
+  if (L.jobs_in_smem) smem += (size_t)L.J * (5 * sizeof(double) + 3);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SWB_MAX_DYN_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int nt = ((L.J + 31) / 32) * 32;
+  if (nt > SWB_SOLVE_THREADS) nt = SWB_SOLVE_THREADS;
+  if (nt < 64) nt = 64;
+  solve_kernel<<<L.S, nt, smem, st>>>(L);
+  return cudaGetLastError();
+}
+
+}  // namespace swb

@@ -1,0 +1,77 @@
+// Internal launch descriptors shared by the .cu files of libswb200 (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/swb200.h"
+
+#define SWB_SOLVE_THREADS 1024
+#define SWB_PLACE_THREADS 1024
+#define SWB_SMEM_JOBS 4096          /* job constants staged in shared memory up to this J */
+#define SWB_PWL_BYTES 512           /* >= sizeof(swb::Pwl), 16-byte aligned */
+#define SWB_MAX_DYN_SMEM (227 * 1024)
+#define SWB_MAX_T 128               /* x rows are kept as 128-bit masks in the placement kernel */
+#define SWB_MAX_J 8192              /* 13 index bits in the placement sort key */
+
+namespace swb {
+
+struct SolveLaunch {
+  int S, J, per_scn, jobs_in_smem;
+  const swb_params *prm;  // device [S]
+  const int32_t *g, *E, *c;
+  const double *dbar, *rem, *ftobj;
+  const double *rem_fb;   // remaining runtime as seen by relax_finish_time_constraints (may be null -> rem)
+  // per-scenario scratch in global memory, [S][J]
+  double *sc_a, *sc_u0, *sc_R, *sc_ws, *sc_cap;
+  uint8_t *sc_g, *sc_nF, *sc_nmax, *sc_n;
+  double *weights;   // [S][J] out, may be null
+  swb_result *res;   // device [S]
+};
+
+struct PlaceLaunch {
+  int S, J, per_scn;
+  const swb_params *prm;  // device [S]
+  const double *bfkey;    // [S][J] or [J]
+  const double *bfkey_fb; // same, for the fallback continuation (may be null -> bfkey)
+  const double *sc_a, *sc_u0, *sc_R, *sc_ws, *sc_cap;
+  const uint8_t *sc_g, *sc_n;
+  const double *weights;  // [S][J] (priority, for the fallback re-rank), may be null
+  uint8_t *x, *backfill;  // [S][J][T] out, may be null
+  int32_t *nrounds;       // [S][J] out, may be null
+  swb_result *res;        // device [S] (status in, objective/shortfall updated)
+};
+
+cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st);
+cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask);
+
+struct ForecastLaunch {
+  int J;
+  int reestimate_share;
+  int round_ptr, ngpus;
+  double gavel_round_duration;
+  // per-call inputs [J]
+  const int32_t *slots, *progress, *meas_end;
+  const double *meas_ns;
+  // resident job table (indexed by slot)
+  const int64_t *tab_off;       // start of the job's rows in the pools (E+1 rows per job in both)
+  const int32_t *tab_E, *tab_nmodes, *tab_g;
+  const double *tab_nsamples, *tab_tsubmit;
+  const int32_t *tab_modes;     // [slot][SWB_MAX_MODES]
+  const double *tab_modemean;   // [slot][SWB_MAX_MODES] mean pre-profiled duration per bs mode
+  double *tab_amp;              // calibration factor state (JobMetaData.py:281-286)
+  // share-series state (shockwave.py:114-118, :480-501): first round, last round, last value,
+  // running sum of gap*value, number of entries
+  int32_t *ss_r0, *ss_rlast, *ss_cnt;
+  double *ss_vlast, *ss_acc;
+  const double *pool_prefix;    // prefix sums of the pre-profiled epoch durations (E+1 per job)
+  const int32_t *pool_bs;       // bs_schedule (E per job)
+  // outputs [J]
+  double *dbar, *rem, *ftobj, *bfkey, *ftest;
+  double *rem_fb, *bfkey_fb, *amp_ok, *amp_fb;
+  int32_t *g_out, *E_out, *c_out;
+};
+cudaError_t launch_forecast(const ForecastLaunch &L, cudaStream_t st);
+cudaError_t launch_commit_amp(int J, const int32_t *slots, const swb_result *res, const double *amp_ok,
+                              const double *amp_fb, double *tab_amp, cudaStream_t st);
+
+}  // namespace swb

@@ -1,0 +1,226 @@
+"""ctypes binding of libswb200.so (the C-ABI declared in include/swb200.h).
+
+This is the only place the product touches the shared library.  There is NO CPU path: if the
+library is missing or no B200 is visible, constructing an `Engine` raises.  numpy arrays are the
+host containers; raw device pointers (e.g. `torch.Tensor.data_ptr()`) are accepted where the header
+says `on_device`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libswb200.so")
+
+MAX_BASES = 16
+ST_OK, ST_FALLBACK = 0, 1
+
+
+class Params(C.Structure):
+    """swb_params (include/swb200.h)."""
+    _fields_ = [("ngpus", C.c_int32), ("future_rounds", C.c_int32), ("round_ptr", C.c_int32),
+                ("nbases", C.c_int32), ("round_duration", C.c_double), ("k", C.c_double),
+                ("lam", C.c_double), ("rhomax", C.c_double),
+                ("bases", C.c_double * MAX_BASES), ("logv", C.c_double * MAX_BASES)]
+
+
+class Result(C.Structure):
+    """swb_result (include/swb200.h)."""
+    _fields_ = [("status", C.c_int32), ("m_evals", C.c_int32), ("mu_iters", C.c_int32),
+                ("shortfall", C.c_int32), ("objective", C.c_double), ("welfare", C.c_double),
+                ("makespan", C.c_double), ("price", C.c_double), ("relaxed_objective", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class SolveArgs(C.Structure):
+    _fields_ = [("S", C.c_int32), ("J", C.c_int32), ("per_scenario_jobs", C.c_int32),
+                ("on_device", C.c_int32), ("prm", C.POINTER(Params)),
+                ("g", C.c_void_p), ("E", C.c_void_p), ("c", C.c_void_p),
+                ("dbar", C.c_void_p), ("rem", C.c_void_p), ("ftobj", C.c_void_p), ("bfkey", C.c_void_p),
+                ("x", C.c_void_p), ("backfill", C.c_void_p), ("nrounds", C.c_void_p),
+                ("weights", C.c_void_p), ("res", C.POINTER(Result))]
+
+
+class RoundArgs(C.Structure):
+    _fields_ = [("J", C.c_int32), ("reestimate_share", C.c_int32), ("gavel_round_duration", C.c_double),
+                ("slots", C.c_void_p), ("epoch_progress", C.c_void_p), ("meas_nsamples", C.c_void_p),
+                ("meas_end_round", C.c_void_p), ("x", C.c_void_p), ("backfill", C.c_void_p),
+                ("nrounds", C.c_void_p), ("forecast_out", C.c_void_p), ("res", C.POINTER(Result))]
+
+
+EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
+           "swb_solve", "swb_job_add", "swb_job_remove", "swb_round_solve", "swb_forecast"]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libswb200.so; raises (never falls back) when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the shockwave_b200 solver)")
+    lib = C.CDLL(LIB_PATH)
+    lib.swb_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.swb_create.restype = C.c_int
+    lib.swb_destroy.argtypes = [C.c_void_p]
+    lib.swb_destroy.restype = None
+    lib.swb_last_error.restype = C.c_char_p
+    lib.swb_version.restype = C.c_int
+    lib.swb_stream.argtypes = [C.c_void_p]
+    lib.swb_stream.restype = C.c_void_p
+    lib.swb_sync.argtypes = [C.c_void_p]
+    lib.swb_sync.restype = C.c_int
+    lib.swb_solve.argtypes = [C.c_void_p, C.POINTER(SolveArgs)]
+    lib.swb_solve.restype = C.c_int
+    lib.swb_job_add.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                C.c_void_p, C.c_void_p]
+    lib.swb_job_add.restype = C.c_int
+    lib.swb_job_remove.argtypes = [C.c_void_p, C.c_int32]
+    lib.swb_job_remove.restype = C.c_int
+    lib.swb_round_solve.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(RoundArgs)]
+    lib.swb_round_solve.restype = C.c_int
+    lib.swb_forecast.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(RoundArgs)] + [C.c_void_p] * 5
+    lib.swb_forecast.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def make_params(ngpus, future_rounds, round_duration, k, lam, rhomax, bases, origin, round_ptr=0):
+    """swb_params from the ShockwaveScheduler constructor kwargs (shockwave.py:21-86)."""
+    p = Params()
+    p.ngpus, p.future_rounds, p.round_ptr, p.nbases = int(ngpus), int(future_rounds), int(round_ptr), len(bases)
+    p.round_duration, p.k, p.lam, p.rhomax = float(round_duration), float(k), float(lam), float(rhomax)
+    assert bases[0] == 0.0 and len(bases) <= MAX_BASES
+    for i, b in enumerate(bases):
+        assert 0.0 <= b <= 1.0
+        p.bases[i] = float(b)
+        p.logv[i] = math.log(origin[0.0]) if b == 0.0 else math.log(b)   # shockwave.py:339-347
+    return p
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Engine:
+    """One swb_ctx (one CUDA stream on one B200)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.swb_create(C.byref(h), int(device))
+        if rc != 0:
+            raise RuntimeError(f"swb_create failed ({rc}): {self.lib.swb_last_error().decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.swb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.swb_last_error().decode()}")
+        return rc
+
+    # ---- plain-array market solve (swb_solve) -----------------------------------------------------
+    def solve(self, params, g, E, c, dbar, rem, ftobj, bfkey=None, want_x=True, want_backfill=True):
+        """Solve S scenarios on host arrays.  `params`: one Params or a list of S; per-job arrays are
+        [J] (shared) or [S, J].  Returns dict(x[S,J,T] u8, backfill, nrounds, weights, results[list])."""
+        plist = params if isinstance(params, (list, tuple)) else [params]
+        S = len(plist)
+        g = np.ascontiguousarray(g, dtype=np.int32)
+        per = 1 if g.ndim == 2 else 0
+        J = g.shape[-1]
+        E = np.ascontiguousarray(E, dtype=np.int32); c = np.ascontiguousarray(c, dtype=np.int32)
+        dbar = np.ascontiguousarray(dbar, dtype=np.float64); rem = np.ascontiguousarray(rem, dtype=np.float64)
+        ftobj = np.ascontiguousarray(ftobj, dtype=np.float64)
+        bfkey = rem if bfkey is None else np.ascontiguousarray(bfkey, dtype=np.float64)
+        for a in (E, c, dbar, rem, ftobj, bfkey):
+            assert a.shape == g.shape
+        T = plist[0].future_rounds
+        parr = (Params * S)(*plist)
+        res = (Result * S)()
+        x = np.zeros((S, J, T), dtype=np.uint8) if want_x else None
+        bf = np.zeros((S, J, T), dtype=np.uint8) if want_backfill else None
+        nr = np.zeros((S, J), dtype=np.int32)
+        w = np.zeros((S, J), dtype=np.float64)
+        a = SolveArgs(S, J, per, 0, parr, _ptr(g), _ptr(E), _ptr(c), _ptr(dbar), _ptr(rem), _ptr(ftobj),
+                      _ptr(bfkey), _ptr(x), _ptr(bf), _ptr(nr), _ptr(w), res)
+        self._check(self.lib.swb_solve(self.h, C.byref(a)), "swb_solve")
+        return dict(x=x, backfill=bf, nrounds=nr, weights=w, results=[r.as_dict() for r in res])
+
+    def solve_device(self, params, J, ptrs, out_ptrs, per_scenario_jobs=True):
+        """Same on raw DEVICE pointers (ints): ptrs = dict(g,E,c,dbar,rem,ftobj,bfkey),
+        out_ptrs = dict(x, backfill, nrounds, weights) (0/None = not wanted)."""
+        plist = params if isinstance(params, (list, tuple)) else [params]
+        S = len(plist)
+        parr = (Params * S)(*plist)
+        res = (Result * S)()
+        vp = lambda v: C.c_void_p(int(v)) if v else None
+        a = SolveArgs(S, J, 1 if per_scenario_jobs else 0, 1, parr, vp(ptrs["g"]), vp(ptrs["E"]), vp(ptrs["c"]),
+                      vp(ptrs["dbar"]), vp(ptrs["rem"]), vp(ptrs["ftobj"]), vp(ptrs.get("bfkey")),
+                      vp(out_ptrs.get("x")), vp(out_ptrs.get("backfill")), vp(out_ptrs.get("nrounds")),
+                      vp(out_ptrs.get("weights")), res)
+        self._check(self.lib.swb_solve(self.h, C.byref(a)), "swb_solve")
+        return [r.as_dict() for r in res]
+
+    # ---- resident job table -------------------------------------------------------------------------
+    def job_add(self, slot, nworkers, epochs, epoch_nsamples, timestamp_submit, epoch_duration_pre, bs_schedule):
+        pre = np.ascontiguousarray(epoch_duration_pre, dtype=np.float64)
+        bs = np.ascontiguousarray(bs_schedule, dtype=np.int32)
+        assert len(pre) == len(bs) == int(epochs)
+        self._check(self.lib.swb_job_add(self.h, int(slot), int(nworkers), int(epochs), float(epoch_nsamples),
+                                         float(timestamp_submit), _ptr(pre), _ptr(bs)), "swb_job_add")
+
+    def job_remove(self, slot):
+        self._check(self.lib.swb_job_remove(self.h, int(slot)), "swb_job_remove")
+
+    def _round_args(self, slots, progress, meas_ns, meas_end, reestimate, grd):
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        progress = np.ascontiguousarray(progress, dtype=np.int32)
+        meas_ns = np.ascontiguousarray(meas_ns, dtype=np.float64)
+        meas_end = np.ascontiguousarray(meas_end, dtype=np.int32)
+        a = RoundArgs()
+        a.J, a.reestimate_share, a.gavel_round_duration = len(slots), int(bool(reestimate)), float(grd)
+        a.slots, a.epoch_progress, a.meas_nsamples, a.meas_end_round = _ptr(slots), _ptr(progress), _ptr(meas_ns), _ptr(meas_end)
+        return a, (slots, progress, meas_ns, meas_end)
+
+    def round_solve(self, params, slots, progress, meas_ns, meas_end, reestimate, grd, want_forecast=False):
+        a, keep = self._round_args(slots, progress, meas_ns, meas_end, reestimate, grd)
+        J, T = a.J, params.future_rounds
+        x = np.zeros((J, T), dtype=np.uint8); bf = np.zeros((J, T), dtype=np.uint8)
+        nr = np.zeros(J, dtype=np.int32)
+        fo = np.zeros((6, J), dtype=np.float64) if want_forecast else None
+        res = Result()
+        a.x, a.backfill, a.nrounds, a.forecast_out, a.res = _ptr(x), _ptr(bf), _ptr(nr), _ptr(fo), C.pointer(res)
+        self._check(self.lib.swb_round_solve(self.h, C.byref(params), C.byref(a)), "swb_round_solve")
+        out = dict(x=x, backfill=bf, nrounds=nr, result=res.as_dict())
+        if want_forecast:
+            fb = res.status == ST_FALLBACK
+            out.update(dbar=fo[0], rem=fo[1], ftobj=fo[2], bfkey=fo[5] if fb else fo[3], rem_fb=fo[4])
+        return out
+
+    def forecast(self, params, slots, progress, meas_ns, meas_end, reestimate, grd):
+        a, keep = self._round_args(slots, progress, meas_ns, meas_end, reestimate, grd)
+        J = a.J
+        outs = [np.zeros(J, dtype=np.float64) for _ in range(5)]
+        self._check(self.lib.swb_forecast(self.h, C.byref(params), C.byref(a), *[_ptr(o) for o in outs]),
+                    "swb_forecast")
+        return dict(dbar=outs[0], rem=outs[1], ftobj=outs[2], bfkey=outs[3], ft_estimate=outs[4])

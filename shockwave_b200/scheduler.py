@@ -1,0 +1,204 @@
+"""Drop-in `ShockwaveScheduler` backed by the sm_100a kernels of libswb200.so.
+
+Mirrors the public surface of the reference class (scheduler/shockwave.py:20-210) that
+`scheduler/scheduler.py` drives: same constructor signature, same attributes read
+from outside (`metadata`, `round_duration`), same methods and the same resolve / cache-replay state
+machine.  `JobMetaData` objects are built and mutated by the caller (scheduler.py:757-778) and are
+only READ here, at solve time.
+
+What moved to the GPU: the per-job forecast walk (calibration, Dirichlet remaining-runtime,
+interpolated epoch duration, finish-time share series), the whole model-build-and-solve, the
+placement into rounds and the work-conserving back-fill.  What stays on the host: this bookkeeping
+and the conversion of the returned J x T byte matrices into the reference's
+`OrderedDict{round -> [job ids]}`.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+
+from . import engine as _eng
+
+
+class ShockwaveScheduler(object):
+    def __init__(self, ngpus: int, gram: int, init_metadata: OrderedDict, future_nrounds: int,
+                 round_duration: int, solver_preference: list, solver_rel_gap: float,
+                 solver_num_threads: int, solver_timeout: float, n_epoch_vars_max: int,
+                 logapx_bases: list, logapx_origin: dict, k: float, lam: float, rhomax: float,
+                 device: int = 0):
+        # same argument checks as shockwave.py:40-69
+        self.ngpus = ngpus
+        self.gram = gram
+        assert self.ngpus > 0
+        assert self.gram > 0
+        self.future_nrounds = future_nrounds
+        assert self.future_nrounds > 0
+        self.round_duration = round_duration
+        assert self.round_duration > 0
+        self.solver_preference = solver_preference      # kept for signature parity; Gurobi is gone
+        self.solver_rel_gap = solver_rel_gap
+        self.solver_num_threads = solver_num_threads
+        self.solver_timeout = solver_timeout
+        assert self.solver_timeout > 0
+        self.n_epoch_vars_max = n_epoch_vars_max
+        assert type(self.n_epoch_vars_max) == int and self.n_epoch_vars_max > 0
+        self.logapx_bases = logapx_bases
+        assert type(self.logapx_bases) == list
+        self.logapx_origin = logapx_origin
+        assert type(self.logapx_origin) == dict
+        self.k = k
+        assert self.k > 0
+        self.lam = lam
+        self.rhomax = rhomax
+
+        self._device = device
+        self._engine = None
+        self._slots = {}          # jobid -> slot of the device-resident job table
+        self._free_slots = []
+        self._next_slot = 0
+        self._tl_cache = {}       # jobid -> ((len, last_round, last_value), (nsamples, end_round))
+        self.last_result = None   # scalars of the latest solve (objective, status, ...)
+
+        assert type(init_metadata) == OrderedDict
+        self.metadata = OrderedDict()
+        for jobid, jobobj in init_metadata.items():
+            self.add_metadata(jobid, jobobj)
+
+        self.schedules = OrderedDict()
+        self.round_ptr = 0
+        self.resolve = True
+        self.completed_jobs = OrderedDict()
+        self.reestimate_share = True
+        self.share_series = {}    # lives on the device (swb_ctx share-series state); kept for parity
+
+    # ---- backend hooks (the oracle harness overrides these three, nothing else) -------------------
+    def _eng(self):
+        if self._engine is None:
+            self._engine = _eng.Engine(self._device)   # raises when the CUDA library / GPU is missing
+        return self._engine
+
+    def _on_add(self, jobid, job):
+        slot = self._free_slots.pop() if self._free_slots else self._next_slot
+        if slot == self._next_slot:
+            self._next_slot += 1
+        ts = job.timestamp_submit
+        self._eng().job_add(slot, job.nworkers, job.epochs, job.epoch_nsamples,
+                            float("nan") if ts is None else ts,
+                            job.epoch_duration_preprofiled, job.bs_schedule)
+        self._slots[jobid] = slot
+
+    def _on_remove(self, jobid):
+        slot = self._slots.pop(jobid)
+        self._eng().job_remove(slot)
+        self._free_slots.append(slot)
+        self._tl_cache.pop(jobid, None)
+
+    def _timeline_summary(self, jobid, job):
+        """(measured_nsamples, end_round) of JobMetaData.py:235-249, cached while the shared
+        throughput OrderedDict is unchanged."""
+        tl = job.throughput_measurements
+        assert tl is not None                       # JobMetaData.py:229
+        n = len(tl)
+        if n == 0:
+            return 0.0, -1
+        last = next(reversed(tl))
+        sig = (n, last, tl[last])
+        hit = self._tl_cache.get(jobid)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        grd = job.gavel_round_duration
+        prev = 0
+        nsamp = 0
+        for cur in sorted(tl.keys()):
+            thr, bs = tl[cur][0], tl[cur][1]
+            nsamp += bs * (thr * grd * (cur - prev))
+            prev = cur
+        out = (float(nsamp), int(max(tl.keys())))
+        self._tl_cache[jobid] = (sig, out)
+        return out
+
+    def _resolve(self, jobids, jobobjs):
+        """One re-solve on the device; returns OrderedDict{round -> [job ids]} (shockwave.py:129-161)."""
+        J = len(jobids)
+        slots = np.fromiter((self._slots[j] for j in jobids), dtype=np.int32, count=J)
+        prog = np.fromiter((job.epoch_progress for job in jobobjs), dtype=np.int32, count=J)
+        ns = np.empty(J, dtype=np.float64)
+        end = np.empty(J, dtype=np.int32)
+        for i, (jid, job) in enumerate(zip(jobids, jobobjs)):
+            ns[i], end[i] = self._timeline_summary(jid, job)
+        prm = _eng.make_params(self.ngpus, self.future_nrounds, self.round_duration, self.k, self.lam,
+                               self.rhomax, self.logapx_bases, self.logapx_origin, self.round_ptr)
+        grd = jobobjs[0].gavel_round_duration if J else self.round_duration
+        out = self._eng().round_solve(prm, slots, prog, ns, end, self.reestimate_share, grd,
+                                      want_forecast=True)
+        self.last_result = out["result"]
+        self.last_forecast = {k: out[k] for k in ("dbar", "rem", "ftobj", "bfkey")}
+        return schedules_from_matrices(out["x"], out["backfill"], out["bfkey"], jobids, self.round_ptr)
+
+    # ---- reference surface ------------------------------------------------------------------------
+    def round_schedule(self):
+        if not self.resolve:
+            if len(self.schedules) > 0:
+                if self.round_ptr in self.schedules.keys():
+                    return self.schedules[self.round_ptr]
+        jobids = list(self.metadata.keys())
+        jobobjs = list(self.metadata.values())
+        schedules = self._resolve(jobids, jobobjs)
+        self.reestimate_share = False               # shockwave.py:120
+        self.schedules = schedules
+        self.clear_resolve()
+        return self.schedules[self.round_ptr]
+
+    def increment_round_ptr(self):
+        self.round_ptr += 1
+
+    def set_resolve(self):
+        self.resolve = True
+
+    def clear_resolve(self):
+        self.resolve = False
+
+    def schedule_progress(self, jobid, epoch_progress, share_update=True):
+        assert jobid in self.metadata.keys()
+        job = self.metadata[jobid]
+        job.set_epoch_progress(epoch_progress)
+        job.reset_waiting_delay()
+
+    def deschedule_waiting_delay(self, jobid, delay):
+        if jobid in self.metadata.keys():
+            self.metadata[jobid].add_waiting_delay(delay)
+
+    def add_metadata(self, jobid, jobobj, share_update=True):
+        assert jobid not in self.metadata.keys()
+        self.metadata[jobid] = jobobj
+        self._on_add(jobid, jobobj)
+        self.set_resolve()
+        if share_update:
+            self.reestimate_share = True
+
+    def remove_metadata(self, jobid, share_update=True):
+        assert jobid not in self.completed_jobs.keys()
+        self.completed_jobs[jobid] = self.metadata[jobid]
+        if share_update:
+            self.reestimate_share = True
+        assert jobid in self.metadata.keys()
+        self.metadata.pop(jobid)
+        self._on_remove(jobid)
+        self.set_resolve()
+
+
+def schedules_from_matrices(x, backfill, bfkey, jobids, round_ptr):
+    """J x T byte matrices -> OrderedDict{round_ptr+t -> [job ids]} in the reference's list order
+    (construct_schedules, shockwave.py:233-283): solver-scheduled jobs in metadata order, then the
+    back-filled ones in descending remaining-runtime order (stable)."""
+    J, T = x.shape
+    ids = np.asarray(jobids, dtype=object)
+    order = np.argsort(-np.asarray(bfkey, dtype=np.float64), kind="stable")
+    sched = OrderedDict()
+    for t in range(T):
+        cur = [jobids[j] for j in np.flatnonzero(x[:, t])]
+        bf = backfill[order, t]
+        cur += [jobids[j] for j in order[np.flatnonzero(bf)]]
+        sched[round_ptr + t] = cur
+    return sched

@@ -1,0 +1,156 @@
+"""GPU parity of the market solve (swb_solve through the C-ABI) against the HiGHS oracle.
+
+Parity definition (because the reference MILP is degenerate in x):
+  P1 every reference constraint holds on the returned integral x (per-round capacity exact),
+  P2 objective >= oracle - 1e-3*|oracle|   (the reference's own MIPGap, configurations/*.json),
+  P3 feasibility verdict (FTF-feasible vs fallback) identical.
+"""
+import numpy as np
+import pytest
+
+from oracle import shockwave_milp as om
+from shockwave_b200 import make_params
+from tests import fixtures as fx
+from tests.synth import synth_problem
+
+pytestmark = pytest.mark.gpu
+LOGV = om.pwl_log_values(fx.BASES, fx.ORIGIN)
+
+
+def check_against(out, s, pb, G, T, D, k, ora_obj, ora_status, tol=1e-3):
+    res = out["results"][s]
+    x = out["x"][s]
+    w = out["weights"][s]
+    assert res["status"] == ora_status
+    obj, welfare, M, n, cap_ok = om.evaluate(x, pb["g"], pb["E"].astype(float), pb["c"].astype(float),
+                                             pb["dbar"], pb["rem"], w, G, T, D, k, fx.BASES, LOGV)
+    assert cap_ok, "per-round GPU capacity violated"
+    assert set(np.unique(x)) <= {0, 1}
+    assert np.array_equal(n.astype(np.int32), out["nrounds"][s])
+    assert abs(obj - res["objective"]) <= 1e-9 * max(1.0, abs(obj)), (obj, res["objective"])
+    assert obj >= ora_obj - tol * abs(ora_obj) - 1e-12, (obj, ora_obj, res)
+    # back-fill never overlaps the solver's schedule and never exceeds capacity
+    bf = out["backfill"][s]
+    assert not np.any(bf & x)
+    assert np.all((x + bf).T.astype(np.int64) @ pb["g"].astype(np.int64) <= G)
+    return obj
+
+
+def test_recorded_canonical_solves(engine):
+    """Every re-solve of the canonical 120-job / 32-GPU simulation, inputs as recorded at the
+    ShockwaveScheduler boundary, against the oracle result recorded with them."""
+    T, G, D = fx.TACC["T"], fx.TACC["G"], fx.TACC["D"]
+    worst = 0.0
+    nfb = 0
+    for i in range(fx.n_solves()):
+        s = fx.solve(i)
+        prm = make_params(G, T, D, fx.TACC["k"], fx.TACC["lam"], fx.TACC["rhomax"], fx.BASES, fx.ORIGIN,
+                          round_ptr=s["round_ptr"])
+        out = engine.solve(prm, s["g"], s["E"], s["c"], s["dbar"], s["rem"], s["ftobj"], bfkey=s["rem"])
+        if s["status"] == om.STATUS_FALLBACK:
+            # the recorded priorities used the fallback-continuation remaining runtime
+            np.testing.assert_allclose(out["weights"][0],
+                                       om.relax_priorities(s["rem"], s["ftobj"], G, s["J"], D, s["round_ptr"],
+                                                           fx.TACC["rhomax"], fx.TACC["lam"])[0], rtol=1e-9)
+            nfb += 1
+        obj = check_against(out, 0, s, G, T, D, fx.TACC["k"], _oracle_obj(s, out["weights"][0]), s["status"])
+        worst = max(worst, (s["objective"] - obj) / max(1e-12, abs(s["objective"])))
+    print("solves", fx.n_solves(), "fallbacks", nfb, "worst relative objective deficit", worst)
+
+
+def _oracle_obj(s, w):
+    """Recorded oracle x re-scored with the weights the GPU used (identical to the recorded weights
+    unless rem_fb differs from rem, which only rescales the fallback priorities)."""
+    T, G, D = fx.TACC["T"], fx.TACC["G"], fx.TACC["D"]
+    return om.evaluate(s["x"], s["g"], s["E"].astype(float), s["c"].astype(float), s["dbar"], s["rem"], w,
+                       G, T, D, fx.TACC["k"], fx.BASES, LOGV)[0]
+
+
+@pytest.mark.parametrize("J,G,T,k,tight", [
+    (8, 8, 6, 1e-3, 1.0), (30, 32, 20, 1e-3, 1.0), (64, 32, 20, 1e1, 1.0), (109, 32, 20, 1e5, 1.0),
+    (96, 64, 32, 1e-3, 0.5), (128, 64, 32, 1e-3, 3.0), (200, 64, 16, 1e-6, 1.0), (256, 64, 32, 1e-3, 1.0),
+])
+def test_synthetic_vs_live_oracle(engine, J, G, T, k, tight):
+    D = 120.0
+    for seed in range(3):
+        pb = synth_problem(J, G, T, D, seed=seed, tight=tight)
+        prm = make_params(G, T, D, k, 12.0, 1.0, fx.BASES, fx.ORIGIN, round_ptr=pb["round_ptr"])
+        out = engine.solve(prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"])
+        ora = om.dynamic_eisenberg_gale(pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"], G, T, D,
+                                        pb["round_ptr"], k, 12.0, 1.0, fx.BASES, LOGV, rel_gap=1e-6,
+                                        time_limit=60.0, do_rank=False)
+        check_against(out, 0, pb, G, T, D, k, ora["objective"], ora["status"])
+
+
+def test_relaxation_bound(engine):
+    """relaxed_objective reported by the kernel is an upper bound of the integral objective and lies
+    within 1e-3 of the HiGHS LP-relaxation optimum."""
+    G, T, D, k = 32, 20, 120.0, 1e-3
+    for seed in range(4):
+        pb = synth_problem(60, G, T, D, seed=10 + seed, tight=3.0)
+        prm = make_params(G, T, D, k, 12.0, 1.0, fx.BASES, fx.ORIGIN, round_ptr=pb["round_ptr"])
+        out = engine.solve(prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"])
+        res = out["results"][0]
+        lp = om.dynamic_eisenberg_gale(pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"], G, T, D,
+                                       pb["round_ptr"], k, 12.0, 1.0, fx.BASES, LOGV, relax=True)
+        assert res["status"] == lp["status"]
+        assert res["objective"] <= lp["objective"] + 1e-9 * abs(lp["objective"])
+
+
+def test_batched_scenarios_match_single(engine):
+    """S scenarios in one launch == S single launches (each CTA is independent)."""
+    G, T, D = 64, 32, 120.0
+    pbs = [synth_problem(192, G, T, D, seed=40 + s) for s in range(6)]
+    ks = [1e-3, 1e-1, 1e1, 1e3, 1e5, 1e-6]
+    prms = [make_params(G, T, D, ks[s], 12.0, 1.0, fx.BASES, fx.ORIGIN, round_ptr=pbs[s]["round_ptr"])
+            for s in range(6)]
+    st = lambda key: np.stack([p[key] for p in pbs])
+    out = engine.solve(prms, st("g"), st("E"), st("c"), st("dbar"), st("rem"), st("ftobj"))
+    for s in range(6):
+        one = engine.solve(prms[s], pbs[s]["g"], pbs[s]["E"], pbs[s]["c"], pbs[s]["dbar"], pbs[s]["rem"],
+                           pbs[s]["ftobj"])
+        assert np.array_equal(one["x"][0], out["x"][s])
+        assert np.array_equal(one["backfill"][0], out["backfill"][s])
+        assert one["results"][0]["objective"] == out["results"][s]["objective"]
+
+
+def test_full_size_properties(engine):
+    """BASELINE config D (4096 jobs x 512 GPUs x 64 rounds): size-independent properties."""
+    J, G, T, D, k = 4096, 512, 64, 120.0, 1e-3
+    pb = synth_problem(J, G, T, D, seed=7, tight=3.0)
+    prm = make_params(G, T, D, k, 12.0, 1.0, fx.BASES, fx.ORIGIN, round_ptr=pb["round_ptr"])
+    out = engine.solve(prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"])
+    res, x, bf = out["results"][0], out["x"][0], out["backfill"][0]
+    obj, welfare, M, n, cap_ok = om.evaluate(x, pb["g"], pb["E"].astype(float), pb["c"].astype(float),
+                                             pb["dbar"], pb["rem"], out["weights"][0], G, T, D, k, fx.BASES, LOGV)
+    assert cap_ok
+    assert abs(obj - res["objective"]) <= 1e-9 * max(1.0, abs(obj))
+    assert res["objective"] <= res["relaxed_objective"] + 1e-9 * abs(res["relaxed_objective"])
+    # the relaxation bound is tight: integral objective within 1e-3 of it
+    assert res["objective"] >= res["relaxed_objective"] - 1e-3 * abs(res["relaxed_objective"]), res
+    # work conservation: after back-fill a round has idle GPUs only if no unscheduled job fits
+    used = (x + bf).T.astype(np.int64) @ pb["g"].astype(np.int64)
+    assert np.all(used <= G)
+    for t in range(T):
+        idle = G - used[t]
+        if idle > 0:
+            rest = pb["g"][(x[:, t] + bf[:, t]) == 0]
+            assert rest.size == 0 or rest.min() > idle
+    # determinism / idempotence
+    out2 = engine.solve(prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"])
+    assert np.array_equal(out2["x"][0], x) and out2["results"][0]["objective"] == res["objective"]
+
+
+def test_edge_cases(engine):
+    D = 120.0
+    # one job, one GPU, one round
+    prm = make_params(1, 1, D, 1e-3, 12.0, 1.0, fx.BASES, fx.ORIGIN)
+    out = engine.solve(prm, [1], [10], [0], [100.0], [1000.0], [1e9])
+    assert out["x"][0].tolist() == [[1]]
+    # finished job (c == E) gets nothing from the solver; a gang wider than the cluster never runs
+    prm = make_params(4, 5, D, 1e-3, 12.0, 1.0, fx.BASES, fx.ORIGIN)
+    out = engine.solve(prm, [1, 8, 2], [10, 10, 10], [10, 0, 3], [100.0, 100.0, 100.0], [1.0, 1000.0, 700.0],
+                       [1e9, 1e9, 1e9])
+    x = out["x"][0]
+    assert x[0].sum() == 0 and x[1].sum() == 0 and x[2].sum() == 5
+    assert out["backfill"][0][1].sum() == 0
