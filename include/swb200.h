@@ -137,9 +137,14 @@ typedef struct swb_round_args {
 } swb_round_args;
 int swb_round_solve(swb_ctx *ctx, const swb_params *prm, const swb_round_args *a);
 
-/* Forecast only (same kernels as above, no solve); outputs [J] doubles each, host. */
+/* Forecast only (same kernels as above, no solve); outputs [J] doubles each, host.  The share series
+ * is advanced (when reestimate_share) but the calibration state is left untouched until
+ * swb_forecast_commit() says which continuation the caller's solve took (fallback or not) and how
+ * many times construct_schedules evaluated each job's sort key (ncal[j] = rounds with idle GPUs in
+ * which job j was not scheduled; shockwave.py:254-267 -> JobMetaData.py:355,302). */
 int swb_forecast(swb_ctx *ctx, const swb_params *prm, const swb_round_args *a, double *dbar,
                  double *rem, double *ftobj, double *bfkey, double *ft_estimate);
+int swb_forecast_commit(swb_ctx *ctx, int32_t J, int32_t fallback, const int32_t *ncal);
 
 #ifdef __cplusplus
 }

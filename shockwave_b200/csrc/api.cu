@@ -63,7 +63,9 @@ struct swb_ctx {
   std::vector<int64_t> h_off;
   std::vector<int32_t> h_E;
   // ---- per-call forecast buffers
-  DBuf f_slots, f_prog, f_mend, f_mns, f_remfb, f_bffb, f_ampok, f_ampfb, f_ftest;
+  DBuf f_slots, f_prog, f_mend, f_mns, f_remfb, f_bffb, f_ampok, f_ampfb, f_ftest, f_ncal;
+  swb::ForecastLaunch last_fc;   // descriptor of the latest forecast (for the calibration commit)
+  bool have_fc = false;
   // pinned staging for the scalar results
   swb_result *h_res = nullptr;
   size_t h_res_cap = 0;
@@ -100,7 +102,7 @@ void swb_destroy(swb_ctx *c) {
                  &c->snmax, &c->sn, &c->gmask, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
                  &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc,
                  &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
-                 &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest};
+                 &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal};
   for (DBuf *b : all) b->release();
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->st) cudaStreamDestroy(c->st);
@@ -149,7 +151,8 @@ static int ensure_hres(swb_ctx *c, size_t S) {
 static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_prm, const int32_t *g,
                      const int32_t *E, const int32_t *cc, const double *dbar, const double *rem,
                      const double *ftobj, const double *bfkey, const double *rem_fb,
-                     const double *bfkey_fb, uint8_t *x, uint8_t *bf, int32_t *nr, double *weights) {
+                     const double *bfkey_fb, uint8_t *x, uint8_t *bf, int32_t *nr, double *weights,
+                     int32_t *ncal = nullptr) {
   const size_t n = (size_t)S * J;
   int rc = ensure_scratch(c, n);
   if (rc) return rc;
@@ -172,7 +175,7 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   P.S = S; P.J = J; P.per_scn = per_scn; P.prm = L.prm; P.bfkey = bfkey; P.bfkey_fb = bfkey_fb;
   P.sc_a = L.sc_a; P.sc_u0 = L.sc_u0; P.sc_R = L.sc_R; P.sc_ws = L.sc_ws; P.sc_cap = L.sc_cap;
   P.sc_g = L.sc_g; P.sc_n = L.sc_n; P.weights = L.weights;
-  P.x = x; P.backfill = bf; P.nrounds = nr; P.res = L.res;
+  P.x = x; P.backfill = bf; P.nrounds = nr; P.ncal = ncal; P.res = L.res;
   CK(swb::launch_place(P, c->st, c->gmask.as<unsigned long long>()));
   return 0;
 }
@@ -380,6 +383,8 @@ static int run_forecast(swb_ctx *c, const swb_params *prm, const swb_round_args 
   F.amp_ok = c->f_ampok.as<double>(); F.amp_fb = c->f_ampfb.as<double>();
   F.g_out = c->g.as<int32_t>(); F.E_out = c->E.as<int32_t>(); F.c_out = c->c.as<int32_t>();
   CK(swb::launch_forecast(F, c->st));
+  c->last_fc = F;
+  c->have_fc = true;
   return 0;
 }
 
@@ -395,13 +400,13 @@ int swb_round_solve(swb_ctx *c, const swb_params *prm, const swb_round_args *a) 
   if (rc) return rc;
   const size_t nx = (size_t)J * T;
   CK(c->x.need(nx, c->st)); CK(c->bf.need(nx, c->st)); CK(c->nr.need((size_t)J * 4, c->st));
+  CK(c->f_ncal.need((size_t)J * 4, c->st));
   rc = run_solve(c, 1, J, 0, prm, c->g.as<int32_t>(), c->E.as<int32_t>(), c->c.as<int32_t>(),
                  c->dbar.as<double>(), c->rem.as<double>(), c->ftobj.as<double>(), c->bfkey.as<double>(),
                  c->f_remfb.as<double>(), c->f_bffb.as<double>(), c->x.as<uint8_t>(), c->bf.as<uint8_t>(),
-                 c->nr.as<int32_t>(), nullptr);
+                 c->nr.as<int32_t>(), nullptr, c->f_ncal.as<int32_t>());
   if (rc) return rc;
-  CK(swb::launch_commit_amp(J, c->f_slots.as<int32_t>(), c->res.as<swb_result>(), c->f_ampok.as<double>(),
-                            c->f_ampfb.as<double>(), c->t_amp.as<double>(), c->st));
+  CK(swb::launch_commit_calibration(c->last_fc, c->res.as<swb_result>(), 0, c->f_ncal.as<int32_t>(), c->st));
   rc = ensure_hres(c, 1);
   if (rc) return rc;
   CK(cudaMemcpyAsync(c->h_res, c->res.p, sizeof(swb_result), cudaMemcpyDeviceToHost, c->st));
@@ -430,17 +435,24 @@ int swb_forecast(swb_ctx *c, const swb_params *prm, const swb_round_args *a, dou
   int rc = run_forecast(c, prm, a);
   if (rc) return rc;
   const int J = a->J;
-  // forecast-only calls keep the "no fallback" continuation of the calibration state
-  CK(c->res.need(sizeof(swb_result), c->st));
-  CK(cudaMemsetAsync(c->res.p, 0, sizeof(swb_result), c->st));
-  CK(swb::launch_commit_amp(J, c->f_slots.as<int32_t>(), c->res.as<swb_result>(), c->f_ampok.as<double>(),
-                            c->f_ampfb.as<double>(), c->t_amp.as<double>(), c->st));
   if (dbar) CK(cudaMemcpyAsync(dbar, c->dbar.p, J * 8, cudaMemcpyDeviceToHost, c->st));
   if (rem) CK(cudaMemcpyAsync(rem, c->rem.p, J * 8, cudaMemcpyDeviceToHost, c->st));
   if (ftobj) CK(cudaMemcpyAsync(ftobj, c->ftobj.p, J * 8, cudaMemcpyDeviceToHost, c->st));
   if (bfkey) CK(cudaMemcpyAsync(bfkey, c->bfkey.p, J * 8, cudaMemcpyDeviceToHost, c->st));
   if (ft_estimate) CK(cudaMemcpyAsync(ft_estimate, c->f_ftest.p, J * 8, cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int swb_forecast_commit(swb_ctx *c, int32_t J, int32_t fallback, const int32_t *ncal) {
+  if (!c || !ncal) return fail(SWB_ERR_ARG, "swb_forecast_commit: null argument");
+  if (!c->have_fc || c->last_fc.J != J) return fail(SWB_ERR_STATE, "swb_forecast_commit: no matching forecast");
+  CK(cudaSetDevice(c->device));
+  CK(c->f_ncal.need((size_t)J * 4, c->st));
+  CK(cudaMemcpyAsync(c->f_ncal.p, ncal, (size_t)J * 4, cudaMemcpyHostToDevice, c->st));
+  CK(swb::launch_commit_calibration(c->last_fc, nullptr, fallback, c->f_ncal.as<int32_t>(), c->st));
+  CK(cudaStreamSynchronize(c->st));
+  c->have_fc = false;
   return 0;
 }
 

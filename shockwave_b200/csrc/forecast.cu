@@ -156,13 +156,16 @@ __global__ void __launch_bounds__(256) forecast_kernel(ForecastLaunch L) {
   const int nmean = (c + 1 < t.E) ? c + 1 : t.E;
   const double dbar = t.pp[nmean] * amp / (double)nmean;
   const double rem = dirichlet(t, c, amp);
-  // continuation without fallback: back-fill key
-  double amp_ok = amp;
-  const double bf_ok = dirichlet(t, c, amp_ok);
-  // continuation with fallback
+  // continuation without fallback: back-fill key = one more dirichlet() call (shockwave.py:261-267);
+  // the state is NOT advanced here — commit_calibration_kernel replays the calls that really happen
+  const double amp_ok = amp;
+  double tmp = amp_ok;
+  const double bf_ok = dirichlet(t, c, tmp);
+  // continuation with fallback (shockwave.py:863-866)
   double amp_fb = calibrate(t, amp);
   const double rem_fb = dirichlet(t, c, amp_fb);
-  const double bf_fb = dirichlet(t, c, amp_fb);
+  tmp = amp_fb;
+  const double bf_fb = dirichlet(t, c, tmp);
   if (lane == 0) {
     L.dbar[warp] = dbar; L.rem[warp] = rem; L.ftobj[warp] = ftobj; L.ftest[warp] = ftest;
     L.bfkey[warp] = bf_ok; L.bfkey_fb[warp] = bf_fb; L.rem_fb[warp] = rem_fb;
@@ -171,23 +174,44 @@ __global__ void __launch_bounds__(256) forecast_kernel(ForecastLaunch L) {
   }
 }
 
-__global__ void commit_amp_kernel(int J, const int32_t *slots, const swb_result *res,
-                                  const double *amp_ok, const double *amp_fb, double *tab_amp) {
+// After the solve: keep the continuation the solve took and replay the calibrate() calls that
+// construct_schedules' sort key makes — one per (round with idle GPUs, job not scheduled in it)
+// (shockwave.py:254-267 -> JobMetaData.py:355 -> :302).  dirichlet() returns before calibrating when
+// the job has no epochs left (JobMetaData.py:349-353).
+__global__ void commit_calibration_kernel(ForecastLaunch L, const swb_result *res, int fallback_host,
+                                          const int32_t *ncal) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= J) return;
-  tab_amp[slots[j]] = (res->status == SWB_ST_FALLBACK) ? amp_fb[j] : amp_ok[j];
+  if (j >= L.J) return;
+  const int slot = L.slots[j];
+  const bool fb = res ? (res->status == SWB_ST_FALLBACK) : (fallback_host != 0);
+  double amp = fb ? L.amp_fb[j] : L.amp_ok[j];
+  JobTab t;
+  const int64_t off = L.tab_off[slot];
+  t.E = L.tab_E[slot];
+  t.pp = L.pool_prefix + off;
+  t.bs = L.pool_bs + off;
+  t.nm = L.tab_nmodes[slot];
+  t.ns = L.tab_nsamples[slot];
+  t.modes = nullptr; t.modemean = nullptr;
+  t.grd = L.gavel_round_duration;
+  t.meas_end = L.meas_end[j];
+  t.has_tl = t.meas_end >= 0;
+  t.meas_ns = L.meas_ns[j];
+  const int n = (L.progress[j] < t.E) ? ncal[j] : 0;
+  for (int i = 0; i < n; ++i) amp = calibrate(t, amp);
+  L.tab_amp[slot] = amp;
+}
+
+cudaError_t launch_commit_calibration(const ForecastLaunch &L, const swb_result *res, int fallback_host,
+                                      const int32_t *ncal, cudaStream_t st) {
+  commit_calibration_kernel<<<(L.J + 127) / 128, 128, 0, st>>>(L, res, fallback_host, ncal);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_forecast(const ForecastLaunch &L, cudaStream_t st) {
   const int warps_per_block = 8;
   const int blocks = (L.J + warps_per_block - 1) / warps_per_block;
   forecast_kernel<<<blocks, warps_per_block * 32, 0, st>>>(L);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_commit_amp(int J, const int32_t *slots, const swb_result *res, const double *amp_ok,
-                              const double *amp_fb, double *tab_amp, cudaStream_t st) {
-  commit_amp_kernel<<<(J + 255) / 256, 256, 0, st>>>(J, slots, res, amp_ok, amp_fb, tab_amp);
   return cudaGetLastError();
 }
 

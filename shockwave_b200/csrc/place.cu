@@ -233,6 +233,12 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
       const double done = fmin(prm.round_duration * (double)n, L.sc_cap[so + j]);
       me = fmax(me, fmax(0.0, L.sc_R[so + j] - done));
       if (L.nrounds) L.nrounds[so + j] = n;
+      if (L.ncal) {
+        int m = 0;
+        for (int t = 0; t < T; ++t)
+          m += (idle[t] > 0 && !((xm[2 * j + (t >> 6)] >> (t & 63)) & 1ull)) ? 1 : 0;
+        L.ncal[so + j] = m;
+      }
     }
     w = br.sum(w);
     me = br.max(me);
@@ -293,8 +299,11 @@ cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long lo
   if (L.J <= SWB_SMEM_JOBS) smem += 32 * (size_t)L.J;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SWB_MAX_DYN_SMEM);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, place_kernel);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SWB_MAX_DYN_SMEM - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }

@@ -386,8 +386,11 @@ cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st) {
   if (L.jobs_in_smem) smem += (size_t)L.J * (5 * sizeof(double) + 3);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SWB_MAX_DYN_SMEM);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, solve_kernel);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SWB_MAX_DYN_SMEM - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }

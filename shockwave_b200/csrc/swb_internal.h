@@ -38,6 +38,7 @@ struct PlaceLaunch {
   const double *weights;  // [S][J] (priority, for the fallback re-rank), may be null
   uint8_t *x, *backfill;  // [S][J][T] out, may be null
   int32_t *nrounds;       // [S][J] out, may be null
+  int32_t *ncal;          // [S][J] out, may be null: rounds with idle GPUs in which the job is unscheduled
   swb_result *res;        // device [S] (status in, objective/shortfall updated)
 };
 
@@ -71,7 +72,7 @@ struct ForecastLaunch {
   int32_t *g_out, *E_out, *c_out;
 };
 cudaError_t launch_forecast(const ForecastLaunch &L, cudaStream_t st);
-cudaError_t launch_commit_amp(int J, const int32_t *slots, const swb_result *res, const double *amp_ok,
-                              const double *amp_fb, double *tab_amp, cudaStream_t st);
+cudaError_t launch_commit_calibration(const ForecastLaunch &L, const swb_result *res, int fallback_host,
+                                      const int32_t *ncal, cudaStream_t st);
 
 }  // namespace swb

@@ -55,7 +55,8 @@ class RoundArgs(C.Structure):
 
 
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
-           "swb_solve", "swb_job_add", "swb_job_remove", "swb_round_solve", "swb_forecast"]
+           "swb_solve", "swb_job_add", "swb_job_remove", "swb_round_solve", "swb_forecast",
+           "swb_forecast_commit"]
 
 _lib = None
 
@@ -91,6 +92,8 @@ def load_library():
     lib.swb_round_solve.restype = C.c_int
     lib.swb_forecast.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(RoundArgs)] + [C.c_void_p] * 5
     lib.swb_forecast.restype = C.c_int
+    lib.swb_forecast_commit.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.swb_forecast_commit.restype = C.c_int
     _lib = lib
     return lib
 
@@ -224,3 +227,8 @@ class Engine:
         self._check(self.lib.swb_forecast(self.h, C.byref(params), C.byref(a), *[_ptr(o) for o in outs]),
                     "swb_forecast")
         return dict(dbar=outs[0], rem=outs[1], ftobj=outs[2], bfkey=outs[3], ft_estimate=outs[4])
+
+    def forecast_commit(self, fallback, ncal):
+        ncal = np.ascontiguousarray(ncal, dtype=np.int32)
+        self._check(self.lib.swb_forecast_commit(self.h, len(ncal), int(bool(fallback)), _ptr(ncal)),
+                    "swb_forecast_commit")

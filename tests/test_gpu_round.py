@@ -1,0 +1,124 @@
+"""GPU parity of the forecast kernels and of the whole round_schedule() re-solve, replaying the
+recorded canonical simulation (tests/golden/tacc32_solves.npz) through the C-ABI."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+from oracle import shockwave_milp as om
+from shockwave_b200 import Engine, ShockwaveScheduler, make_params
+from tests import fixtures as fx
+from tests.replay import ncal_of
+
+pytestmark = pytest.mark.gpu
+LOGV = om.pwl_log_values(fx.BASES, fx.ORIGIN)
+FTOL = 1e-10   # float64 on both sides; the device multiplies prefix sums by the calibration factor
+               # (amp*sum) where the reference sums amp*x — a few ulps
+
+
+def _slots_for(eng, st, live, slots, free, nxt):
+    for jid in list(slots):
+        if jid not in live:
+            eng.job_remove(slots[jid]); free.append(slots.pop(jid))
+    for jid in live:
+        if jid not in slots:
+            s = free.pop() if free else nxt[0]
+            if s == nxt[0]:
+                nxt[0] += 1
+            p = st[jid]
+            eng.job_add(s, p["nworkers"], p["epochs"], p["epoch_nsamples"], p["timestamp_submit"], p["pre"], p["bs"])
+            slots[jid] = s
+
+
+def test_forecast_replay_matches_reference():
+    """dbar / rem / ftobj / rem_fb / back-fill key of every re-solve vs the values the reference's own
+    JobMetaData objects produced (stateful calibration + share series evolve over 129 solves)."""
+    eng = Engine(0)
+    st = fx.job_statics()
+    slots, free, nxt = {}, [], [0]
+    worst = dict(dbar=0.0, rem=0.0, ftobj=0.0, rem_fb=0.0, bfkey=0.0)
+    G, T, D = fx.TACC["G"], fx.TACC["T"], fx.TACC["D"]
+    for i in range(fx.n_solves()):
+        s = fx.solve(i)
+        live = [int(j) for j in s["jobids"]]
+        _slots_for(eng, st, live, slots, free, nxt)
+        prm = make_params(G, T, D, fx.TACC["k"], fx.TACC["lam"], fx.TACC["rhomax"], fx.BASES, fx.ORIGIN,
+                          round_ptr=s["round_ptr"])
+        sl = [slots[j] for j in live]
+        f = eng.forecast(prm, sl, s["c"], s["meas_ns"], s["meas_end"], s["reestimate"], st[live[0]]["grd"])
+        for key in ("dbar", "rem", "ftobj"):
+            rel = np.abs(f[key] - s[key]) / np.abs(s[key])
+            worst[key] = max(worst[key], float(rel.max()))
+        fb = s["status"] == om.STATUS_FALLBACK
+        eng.forecast_commit(fb, ncal_of(s["x"], s["g"], G))
+    print("worst relative deviation over", fx.n_solves(), "solves:", worst)
+    for key in ("dbar", "rem", "ftobj"):
+        assert worst[key] <= FTOL, (key, worst[key])
+    eng.close()
+
+
+class _Job:
+    """Duck-typed JobMetaData (scheduler/JobMetaData.py:41-98): what ShockwaveScheduler reads."""
+    def __init__(self, jid, p):
+        self.jobid = jid
+        self.nworkers, self.epochs, self.epoch_nsamples = p["nworkers"], p["epochs"], p["epoch_nsamples"]
+        self.epoch_duration_preprofiled = p["pre"].tolist()
+        self.bs_schedule = p["bs"].tolist()
+        self.timestamp_submit = p["timestamp_submit"]
+        self.gavel_round_duration = p["grd"]
+        self.throughput_measurements = OrderedDict()
+        self.epoch_progress = 0
+        self.waiting_delay = 0
+
+    def set_epoch_progress(self, c): self.epoch_progress = c
+    def reset_waiting_delay(self): self.waiting_delay = 0
+    def add_waiting_delay(self, d): self.waiting_delay += d
+
+
+def test_scheduler_class_replay():
+    """The drop-in class end to end: add/remove/progress calls as scheduler.py makes them, then
+    round_schedule(); verdict, feasibility and objective against the recorded oracle solve."""
+    G, T, D = fx.TACC["G"], fx.TACC["T"], fx.TACC["D"]
+    sw = ShockwaveScheduler(ngpus=G, gram=16, init_metadata=OrderedDict(), future_nrounds=T, round_duration=int(D),
+                            solver_preference=["GUROBI"], solver_rel_gap=1e-3, solver_num_threads=24,
+                            solver_timeout=15, n_epoch_vars_max=30, logapx_bases=fx.BASES,
+                            logapx_origin=fx.ORIGIN, k=fx.TACC["k"], lam=fx.TACC["lam"], rhomax=fx.TACC["rhomax"])
+    st = fx.job_statics()
+    agree = total = 0
+    for i in range(fx.n_solves()):
+        s = fx.solve(i)
+        live = [int(j) for j in s["jobids"]]
+        for jid in list(sw.metadata.keys()):
+            if jid not in live:
+                sw.remove_metadata(jid)
+        for k, jid in enumerate(live):
+            if jid not in sw.metadata:
+                sw.add_metadata(jid, _Job(jid, st[jid]))
+        assert list(sw.metadata.keys()) == live
+        for k, jid in enumerate(live):
+            job = sw.metadata[jid]
+            sw.schedule_progress(jid, int(s["c"][k]))
+            tl = job.throughput_measurements
+            tl.clear()
+            if s["meas_end"][k] >= 0:   # a 1-entry timeline with the same (nsamples, end_round) summary
+                end = int(s["meas_end"][k])
+                tl[end] = (float(s["meas_ns"][k]) / (job.gavel_round_duration * end), 1.0)
+        sw.round_ptr = s["round_ptr"]
+        sw.reestimate_share = s["reestimate"]
+        sw.set_resolve()
+        ids0 = sw.round_schedule()
+        res = sw.last_result
+        assert sw.resolve is False and sw.reestimate_share is False
+        assert list(sw.schedules.keys()) == list(range(s["round_ptr"], s["round_ptr"] + T))
+        used = sum(st[j]["nworkers"] for j in ids0)
+        assert used <= G and len(set(ids0)) == len(ids0)
+        # cache replay (shockwave.py:124-127)
+        assert sw.round_schedule() is sw.schedules[s["round_ptr"]]
+        total += 1
+        agree += int(res["status"] == s["status"])
+        if res["status"] == s["status"] == om.STATUS_FTF_FEASIBLE:
+            assert res["objective"] >= s["objective"] - 1e-3 * abs(s["objective"]) - 1e-6
+    print("verdict agreement", agree, "/", total)
+    # the class drives its own calibration continuation (its x differs from the oracle's), so a
+    # borderline verdict may flip late in the replay; require near-total agreement
+    assert agree >= 0.95 * total
