@@ -54,7 +54,7 @@ struct swb_ctx {
   cudaStream_t st = nullptr;
   // ---- work buffers of a solve
   DBuf prm, res, g, E, c, dbar, rem, ftobj, bfkey, x, bf, nr, w;
-  DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask;
+  DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask, sncap, seated;
   // ---- resident job table (by slot)
   int nslots = 0;
   DBuf t_off, t_E, t_nm, t_g, t_ns, t_ts, t_modes, t_mm, t_amp, s_r0, s_rl, s_cnt, s_vl, s_acc;
@@ -99,7 +99,7 @@ void swb_destroy(swb_ctx *c) {
   cudaSetDevice(c->device);
   DBuf *all[] = {&c->prm, &c->res, &c->g, &c->E, &c->c, &c->dbar, &c->rem, &c->ftobj, &c->bfkey, &c->x,
                  &c->bf, &c->nr, &c->w, &c->sa, &c->su0, &c->sR, &c->sws, &c->scap, &c->sg, &c->snF,
-                 &c->snmax, &c->sn, &c->gmask, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
+                 &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
                  &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc,
                  &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
                  &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal};
@@ -134,6 +134,7 @@ static int ensure_scratch(swb_ctx *c, size_t n) {
   CK(c->sws.need(n * 8, c->st));  CK(c->scap.need(n * 8, c->st));
   CK(c->sg.need(n, c->st));       CK(c->snF.need(n, c->st));     CK(c->snmax.need(n, c->st));
   CK(c->sn.need(n, c->st));       CK(c->w.need(n * 8, c->st));
+  CK(c->sncap.need(n, c->st));    CK(c->seated.need(n * 4, c->st));
   return 0;
 }
 
@@ -170,13 +171,25 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   L.sc_n = c->sn.as<uint8_t>();
   L.weights = weights ? weights : c->w.as<double>();
   L.res = c->res.as<swb_result>();
-  CK(swb::launch_solve(L, c->st));
+  L.ncap = c->sncap.as<uint8_t>();
+  CK(cudaMemsetAsync(c->sncap.p, 0xff, n, c->st));
   swb::PlaceLaunch P;
   P.S = S; P.J = J; P.per_scn = per_scn; P.prm = L.prm; P.bfkey = bfkey; P.bfkey_fb = bfkey_fb;
   P.sc_a = L.sc_a; P.sc_u0 = L.sc_u0; P.sc_R = L.sc_R; P.sc_ws = L.sc_ws; P.sc_cap = L.sc_cap;
-  P.sc_g = L.sc_g; P.sc_n = L.sc_n; P.weights = L.weights;
-  P.x = x; P.backfill = bf; P.nrounds = nr; P.ncal = ncal; P.res = L.res;
-  CK(swb::launch_place(P, c->st, c->gmask.as<unsigned long long>()));
+  P.sc_g = L.sc_g; P.sc_n = L.sc_n; P.weights = L.weights; P.E = E; P.c = cc; P.dbar = dbar;
+  P.x = x; P.backfill = bf; P.nrounds = nr ? nr : c->seated.as<int32_t>(); P.ncal = ncal; P.res = L.res;
+  int rc2 = ensure_hres(c, S);
+  if (rc2) return rc2;
+  for (int pass = 0; pass < SWB_MAX_REPLAN + 1; ++pass) {
+    CK(swb::launch_solve(L, c->st));
+    CK(swb::launch_place(P, c->st, c->gmask.as<unsigned long long>()));
+    CK(cudaMemcpyAsync(c->h_res, c->res.p, sizeof(swb_result) * S, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    int shortf = 0;
+    for (int s = 0; s < S; ++s) shortf += c->h_res[s].shortfall;
+    if (shortf == 0 || pass == SWB_MAX_REPLAN) break;
+    CK(swb::launch_tighten(S, J, L.res, L.sc_n, P.nrounds, c->sncap.as<uint8_t>(), c->st));
+  }
   return 0;
 }
 

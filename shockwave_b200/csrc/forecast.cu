@@ -60,13 +60,27 @@ __device__ __forceinline__ double calibrate(const JobTab &t, double amp) {
   return pre_ns / t.meas_ns;
 }
 
+// Python >= 3.12's builtin sum() over floats is Neumaier-compensated (CPython Python/bltinmodule.c);
+// the reference calls it at JobMetaData.py:330 and :347 and truncates the second result with int(),
+// so the forecast is sensitive to the last ulp of these two sums.  The golden fixtures were made
+// under Python 3.12, hence the same algorithm here.
+struct PySum {
+  double s = 0.0, c = 0.0;
+  __device__ __forceinline__ void add(double x) {
+    const double t = s + x;
+    if (fabs(s) >= fabs(x)) c += (s - t) + x; else c += (x - t) + s;
+    s = t;
+  }
+  __device__ __forceinline__ double value() const { return (c != 0.0 && isfinite(c)) ? s + c : s; }
+};
+
 // JobMetaData.py:315-370; whole warp cooperates on the histogram, scalars are lane-uniform
 __device__ double dirichlet(const JobTab &t, int c, double &amp) {
   const int lane = threadIdx.x & 31;
   const int nobs = (c + 1 < t.E) ? c + 1 : t.E;
   const double prior = (double)t.E / (double)t.nm;
   double post[SWB_MAX_MODES];
-  double csum = 0.0;
+  PySum csum_acc;
   int cnts[SWB_MAX_MODES];
 #pragma unroll 1
   for (int m = 0; m < t.nm; ++m) {
@@ -76,9 +90,10 @@ __device__ double dirichlet(const JobTab &t, int c, double &amp) {
     cnt = warp_sum(cnt);
     cnts[m] = cnt;
     post[m] = prior + (double)cnt;
-    csum += post[m];
+    csum_acc.add(post[m]);
   }
-  double rsum = 0.0;
+  const double csum = csum_acc.value();
+  PySum rsum_acc;
 #pragma unroll 1
   for (int m = 0; m < t.nm; ++m) {
     double v = (double)t.E * post[m] / csum;
@@ -86,9 +101,9 @@ __device__ double dirichlet(const JobTab &t, int c, double &amp) {
     const double dec = fmin((double)cnts[m], fl > 0.0 ? fl : 0.0);
     v -= dec;
     post[m] = v;  // rebased, after the observed epochs were taken off
-    rsum += v;
+    rsum_acc.add(v);
   }
-  long long inflated = (long long)(rsum + 1.0);
+  long long inflated = (long long)(rsum_acc.value() + 1.0);
   const long long rem_epochs = (long long)t.E - c;
   if (inflated < rem_epochs) inflated = rem_epochs;
   if (inflated <= 0 || rem_epochs <= 0) return 1.0;

@@ -13,6 +13,7 @@
 //     not-yet-scheduled jobs in descending remaining-runtime order (stable) that still fit.
 //
 // One CTA per scenario.  Round masks (128 bit per job) live in shared memory for J <= 4096.
+// G must fit 24 bits (bin keys are load<<8|bin).
 #include <math.h>
 
 #include "swb_common.cuh"
@@ -92,6 +93,11 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   double *red = reinterpret_cast<double *>(p); p += 2 * 64 * sizeof(double);
   int *wsum = reinterpret_cast<int *>(p);      p += 32 * sizeof(int);
   int *idle = reinterpret_cast<int *>(p);      p += SWB_MAX_T * sizeof(int);
+  int *load_of = reinterpret_cast<int *>(p);   p += SWB_MAX_T * sizeof(int);
+  unsigned int *binA = reinterpret_cast<unsigned int *>(p); p += SWB_MAX_T * sizeof(int);
+  unsigned int *binB = reinterpret_cast<unsigned int *>(p); p += SWB_MAX_T * sizeof(int);
+  double *score = reinterpret_cast<double *>(p); p += SWB_MAX_T * sizeof(double);
+  unsigned char *newpos = p;                   p += SWB_MAX_T;
   // union region: {key64[npad], idx16[npad]}  or  {key32[npad], sel8[npad]}
   unsigned long long *key64 = reinterpret_cast<unsigned long long *>(p);
   unsigned int *key32 = reinterpret_cast<unsigned int *>(p);
@@ -134,7 +140,8 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     for (int i = threadIdx.x; i < npad; i += blockDim.x) order[i] = idx16[i];
     __syncthreads();
   }
-  // ---- fallback re-rank order: prio_j / (n_j g_j) descending ---------------------------------
+  // ---- packing order: wider gangs first, then more planned rounds (fallback: higher
+  //      prio_j/(n_j g_j), the exchange-argument order of rank_in_schedule_jobs), then job index ----
   if (fallback && L.weights) {
     const double *wj = L.weights + so;
     for (int i = threadIdx.x; i < npad; i += blockDim.x) {
@@ -149,73 +156,123 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
       if (idx16[i] != 0xffff) rank[idx16[i]] = (unsigned short)i;
     __syncthreads();
   }
-
-  // ---- least-laxity-first sweep over the rounds ----------------------------------------------
-  const int ch = (npad + blockDim.x - 1) / blockDim.x;  // consecutive sorted positions per thread
-  for (int t = 0; t < T; ++t) {
-    const int tau = T - t;
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-      unsigned int k = 0;
-      if (i < J && remn[i] > 0) {
-        const unsigned int r = remn[i];
-        const unsigned int crit = (r >= (unsigned)tau) ? 1u : 0u;
-        const unsigned int prim = (fallback && L.weights)
-            ? ((unsigned)(SWB_MAX_J - rank[i]) << 13)
-            : ((r << 21) | ((unsigned)gs[i] << 13));
-        k = (crit << 30) | prim | (unsigned)(SWB_MAX_J - 1 - i);
-      }
-      key32[i] = k;
-      sel[i] = 0;
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+    unsigned long long k = 0ull;
+    if (i < J && nplan[i] > 0) {
+      // jobs that need (almost) every round must come first inside their width class or the rounds
+      // they need fill up; the fallback priority only breaks ties (it drives the round ORDER below)
+      const unsigned long long tie = (fallback && L.weights) ? (unsigned long long)(SWB_MAX_J - rank[i])
+                                                             : (unsigned long long)(SWB_MAX_J - 1 - i);
+      // a job present in EVERY round only lowers all capacities by g: seat those first, whatever
+      // their width — a narrow all-rounds job seated late finds some rounds already full
+      const unsigned long long all_rounds = (nplan[i] >= T) ? 1ull : 0ull;
+      k = (all_rounds << 48) | ((unsigned long long)gs[i] << 40) | ((unsigned long long)nplan[i] << 28) |
+          (tie << 14) | (unsigned long long)(SWB_MAX_J - 1 - i);
     }
-    __syncthreads();
-    sort_desc32(key32, npad);
-    int capleft = G;
-    for (int pass = 0; pass < 64 && capleft > 0; ++pass) {
-      const int p0 = threadIdx.x * ch;
-      int lsum = 0;
-      for (int q = 0; q < ch; ++q) {
-        const int pos = p0 + q;
-        if (pos < npad) {
-          const unsigned int k = key32[pos];
-          if (k != 0 && !sel[pos]) {
-            const int g = gs[SWB_MAX_J - 1 - (k & (SWB_MAX_J - 1))];
-            if (g <= capleft) lsum += g;
-          }
+    key64[i] = k;
+    idx16[i] = (unsigned short)(i < J ? i : 0xffff);
+  }
+  __syncthreads();
+  sort_desc64(key64, idx16, npad);
+
+  // ---- water-filling: each job takes its n_j least-loaded rounds ("bins") that still fit it.
+  //      With widths in descending order the loads stay multiples of the current width, so there is
+  //      no fragmentation; least-loaded-first keeps the loads level.  One warp walks the jobs; the
+  //      bins are kept sorted by (load, bin) and re-merged after every job.
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    unsigned int *A = binA, *B = binB;
+    for (int p = lane; p < T; p += 32) A[p] = (unsigned)p;  // load 0, bin p
+    __syncwarp();
+    for (int pos = 0; pos < J; ++pos) {
+      if (key64[pos] == 0ull) break;
+      const int j = idx16[pos];
+      const int g = gs[j], n = nplan[j];
+      // usable bins = prefix with load <= G - g
+      const unsigned int lim = ((unsigned)(G - g) << 8) | 0xffu;
+      int u = 0;
+      for (int p = lane; p < T; p += 32) u += (A[p] <= lim) ? 1 : 0;
+      u = warp_sum(u);
+      const int m = n < u ? n : u;
+      if (m > 0) {
+        unsigned long long m0 = 0ull, m1 = 0ull;
+        for (int p = lane; p < m; p += 32) {
+          const unsigned int b = A[p] & 0xffu;
+          if (b < 64) m0 |= 1ull << b; else m1 |= 1ull << (b - 64);
         }
-      }
-      int tot = 0;
-      int run = block_excl_scan(lsum, wsum, &tot);
-      if (tot == 0) break;
-      int took = 0;
-      for (int q = 0; q < ch; ++q) {
-        const int pos = p0 + q;
-        if (pos < npad) {
-          const unsigned int k = key32[pos];
-          if (k != 0 && !sel[pos]) {
-            const int g = gs[SWB_MAX_J - 1 - (k & (SWB_MAX_J - 1))];
-            if (g <= capleft) {
-              run += g;
-              if (run <= capleft) { sel[pos] = 1; took += g; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          m0 |= __shfl_xor_sync(SWB_FULL, m0, o);
+          m1 |= __shfl_xor_sync(SWB_FULL, m1, o);
+        }
+        if (lane == 0) { xm[2 * j] = m0; xm[2 * j + 1] = m1; remn[j] = (unsigned char)(n - m); }
+        const unsigned int add = (unsigned)g << 8;
+        if (m == T) {
+          for (int p = lane; p < T; p += 32) A[p] += add;
+        } else {
+          // merge X = A[0..m)+add with Y = A[m..T); keys are unique (bin id in the low byte)
+          for (int p = lane; p < T; p += 32) {
+            int dst;
+            if (p < m) {
+              const unsigned int v = A[p] + add;
+              int lo = m, hi = T;               // #{y in Y : y < v}
+              while (lo < hi) { const int mid = (lo + hi) >> 1; if (A[mid] < v) lo = mid + 1; else hi = mid; }
+              dst = p + (lo - m);
+              B[dst] = v;
+            } else {
+              const unsigned int v = A[p];
+              int lo = 0, hi = m;               // #{x in X : x < v}
+              while (lo < hi) { const int mid = (lo + hi) >> 1; if (A[mid] + add < v) lo = mid + 1; else hi = mid; }
+              dst = (p - m) + lo;
+              B[dst] = v;
             }
           }
+          unsigned int *tmp = A; A = B; B = tmp;
         }
-      }
-      const int taken = (int)br.sumll((long long)took);
-      capleft -= taken;
-      if (taken == tot) break;  // every eligible job seated
-      __syncthreads();
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-      if (sel[i]) {
-        const int j = SWB_MAX_J - 1 - (key32[i] & (SWB_MAX_J - 1));
-        xm[2 * j + (t >> 6)] |= 1ull << (t & 63);
-        remn[j] = (unsigned char)(remn[j] - 1);
+        __syncwarp();
       }
     }
-    if (threadIdx.x == 0) idle[t] = capleft;
-    __syncthreads();
+    // ---- order the rounds: interchangeable for the MILP objective, so put first the rounds that
+    //      carry the most planned work (fallback: the largest sum of prio_j/n_j, which minimises
+    //      sum_j prio_j * mean round index for this partition — rearrangement inequality) ----------
+    for (int p = lane; p < T; p += 32) { load_of[A[p] & 0xffu] = (int)(A[p] >> 8); score[p] = 0.0; }
   }
+  __syncthreads();
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int b = warp; b < T; b += nw) {
+      double acc = 0.0;
+      for (int j = lane; j < J; j += 32) {
+        if ((xm[2 * j + (b >> 6)] >> (b & 63)) & 1ull)
+          acc += (fallback && L.weights) ? L.weights[so + j] / (double)nplan[j]
+                                         : (double)nplan[j] * (double)gs[j];
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) score[b] = acc;
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < T; b += blockDim.x) {
+    const double sb = score[b];
+    int r = 0;
+    for (int o = 0; o < T; ++o) { const double so2 = score[o]; r += (so2 > sb || (so2 == sb && o < b)) ? 1 : 0; }
+    newpos[b] = (unsigned char)r;
+    idle[r] = G - load_of[b];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    unsigned long long o0 = 0ull, o1 = 0ull;
+    for (int wi = 0; wi < 2; ++wi) {
+      unsigned long long mm = xm[2 * j + wi];
+      while (mm) {
+        const int b = __ffsll((long long)mm) - 1; mm &= mm - 1;
+        const int t = newpos[64 * wi + b];
+        if (t < 64) o0 |= 1ull << t; else o1 |= 1ull << (t - 64);
+      }
+    }
+    xm[2 * j] = o0; xm[2 * j + 1] = o1;
+  }
+  __syncthreads();
 
   // ---- objective of the PLACED schedule (what a checker recomputes from x) --------------------
   {
@@ -229,8 +286,12 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
       const int n = (int)nplan[j] - (int)remn[j];
       shortf += remn[j];
-      w += L.sc_ws[so + j] * plog(P, fma(L.sc_a[so + j], (double)n, L.sc_u0[so + j]));
-      const double done = fmin(prm.round_duration * (double)n, L.sc_cap[so + j]);
+      // same float64 formula a checker applies to x: p = min(D n / dbar, E - c), u = (c + p) / E
+      const size_t ji = (L.per_scn ? so : 0) + j;
+      const double Ef = (double)L.E[ji], cf = (double)L.c[ji], db = L.dbar[ji];
+      const double pj = fmin(prm.round_duration * (double)n / db, Ef - cf);
+      w += L.sc_ws[so + j] * plog(P, (cf + pj) / Ef);
+      const double done = db * pj;
       me = fmax(me, fmax(0.0, L.sc_R[so + j] - done));
       if (L.nrounds) L.nrounds[so + j] = n;
       if (L.ncal) {
@@ -294,7 +355,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
 cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask) {
   int npad = 64;
   while (npad < L.J) npad <<= 1;
-  size_t smem = 2 * 64 * sizeof(double) + 32 * sizeof(int) + SWB_MAX_T * sizeof(int) +
+  size_t smem = 2 * 64 * sizeof(double) + 32 * sizeof(int) + SWB_MAX_T * (4 * sizeof(int) + sizeof(double) + 1) +
                 10 * (size_t)npad + 4 * (size_t)npad + 2 * (size_t)npad + 16;
   if (L.J <= SWB_SMEM_JOBS) smem += 32 * (size_t)L.J;
   static bool attr_set = false;

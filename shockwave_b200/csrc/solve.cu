@@ -19,7 +19,6 @@
 
 namespace swb {
 
-#define MU_ITERS 44
 
 struct JobsV {  // job constants of one scenario, in shared memory (J <= SWB_SMEM_JOBS) or global
   double *a, *u0, *R, *ws, *cap;
@@ -32,6 +31,8 @@ struct Ctx {
   int J, T, GT;
   double D;
 };
+
+__device__ __forceinline__ double util_of(const Ctx &c, int j, int n);
 
 // closed-form best response of job j to a price mu (welfare per GPU-round): the largest n with
 // F_j(n) - F_j(n-1) > mu g_j.  Rounds that lie wholly in PWL segments of slope > theta pass,
@@ -51,7 +52,7 @@ __device__ __forceinline__ int pref_n(const Ctx &c, int j, double mu) {
     n0 = nb <= 0.0 ? 0 : (nb >= (double)nmax ? nmax : (int)floor(nb));
   }
   if (n0 < nmax) {
-    const double d = ws * (plog(P, fma(a, (double)(n0 + 1), u0)) - plog(P, fma(a, (double)n0, u0)));
+    const double d = util_of(c, j, n0 + 1) - util_of(c, j, n0);
     n0 += (d > mg) ? 1 : 0;
   }
   return n0;
@@ -79,8 +80,11 @@ __device__ __forceinline__ double rem_of(const Ctx &c, int j, int n) {
   return fmax(0.0, c.v.R[j] - done);
 }
 
+// weighted PWL-log utility of n rounds.  A job that completes inside the window gets plog(1) = 0
+// EXACTLY: the fallback priorities reach 1e20 and would amplify a 1-ulp error in u to O(1).
 __device__ __forceinline__ double util_of(const Ctx &c, int j, int n) {
-  return c.v.ws[j] * plog(*c.P, fma(c.v.a[j], (double)n, c.v.u0[j]));
+  const double u = (c.D * (double)n >= c.v.cap[j]) ? 1.0 : fma(c.v.a[j], (double)n, c.v.u0[j]);
+  return c.v.ws[j] * plog(*c.P, u);
 }
 
 __device__ long long cost_at(const Ctx &c, BlockRed &br, double M, double mu) {
@@ -97,14 +101,20 @@ __device__ Price solve_price(const Ctx &c, BlockRed &br, double M, double mu_max
   p.iters = 1;
   long long c0 = cost_at(c, br, M, 0.0);
   if (c0 <= c.GT) { p.hi = p.lo = 0.0; p.cost_hi = c0; return p; }
+  // Bisection on the BIT PATTERN of the (positive) price: the fallback priorities span 20+ orders of
+  // magnitude (ratio^lam, shockwave.py:899-903), so an arithmetic midpoint would stop ~2^-44 * mu_max
+  // above the real clearing price and lump every cheaper item into one "tie".  Positive doubles are
+  // ordered like their bit patterns, so this converges to two ADJACENT doubles in <= 63 steps.
+  unsigned long long lob = 0ull, hib = (unsigned long long)__double_as_longlong(mu_max);
   double lo = 0.0, hi = mu_max;
   long long chi = cost_at(c, br, M, hi);
   p.iters++;
-  for (int it = 0; it < MU_ITERS; ++it) {
-    const double mid = 0.5 * (lo + hi);
+  while (hib - lob > 1ull) {
+    const unsigned long long midb = lob + ((hib - lob) >> 1);
+    const double mid = __longlong_as_double((long long)midb);
     const long long cm = cost_at(c, br, M, mid);
     p.iters++;
-    if (cm <= c.GT) { hi = mid; chi = cm; if (cm == c.GT) break; } else lo = mid;
+    if (cm <= c.GT) { hib = midb; hi = mid; chi = cm; if (cm == c.GT) break; } else { lob = midb; lo = mid; }
   }
   p.hi = hi; p.lo = lo; p.cost_hi = chi;
   return p;
@@ -184,7 +194,9 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
     const double cap = dbar * (Ef - cf);
     const double a = D / (dbar * Ef);
     int nfin = cap <= 0.0 ? 0 : (int)fmin(ceil(cap / D - 1e-9), 255.0);
-    const int nmax = nfin < T ? nfin : T;
+    int nmax = nfin < T ? nfin : T;
+    if (gI[j] > G) nmax = 0;  // a gang wider than the cluster violates every capacity row (shockwave.py:317)
+    if (L.ncap && (int)L.ncap[so + j] < nmax) nmax = L.ncap[so + j];  // packing feedback (see tighten_kernel)
     c.v.a[j] = a; c.v.u0[j] = cf / Ef; c.v.R[j] = R; c.v.cap[j] = cap;
     c.v.g[j] = (uint8_t)gI[j]; c.v.nmax[j] = (uint8_t)nmax;
     const double capF = share * (prm.rhomax * ftI[j] - next_t);
@@ -232,7 +244,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
     if (c.v.nmax[j] > 0)
       mu_max = fmax(mu_max, (util_of(c, j, 1) - util_of(c, j, 0)) / (double)c.v.g[j]);
     const double R = c.v.R[j];
-    mfloor = fmax(mfloor, fmax(R - c.v.cap[j], R - D * (double)T));
+    mfloor = fmax(mfloor, R - fmin(D * (double)c.v.nmax[j], c.v.cap[j]));
     mtop = fmax(mtop, R);
   }
   mu_max = br.max(mu_max) * (1.0 + 1e-9) + 1e-300;
@@ -379,6 +391,28 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
     r.price = pr.hi;
     r.relaxed_objective = best_V;
   }
+}
+
+// Packing feedback: the count-level solve assumes any counts with sum_j g_j n_j <= G T can be seated;
+// with wide gangs on a small cluster that is not always true (bin packing with distinct-round
+// constraints).  When the placement left planned rounds unseated, the counts of exactly those jobs
+// are capped at what was seated and the scenario is solved again, so the freed GPU-rounds go to
+// other jobs and the makespan threshold is re-optimised against what can really be placed.
+__global__ void tighten_kernel(int J, const swb_result *res, const uint8_t *plan, const int32_t *seated,
+                               uint8_t *ncap) {
+  const int s = blockIdx.y;
+  if (res[s].shortfall <= 0) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= J) return;
+  const size_t i = (size_t)s * J + j;
+  if (seated[i] < (int)plan[i]) ncap[i] = (uint8_t)seated[i];
+}
+
+cudaError_t launch_tighten(int S, int J, const swb_result *res, const uint8_t *plan, const int32_t *seated,
+                           uint8_t *ncap, cudaStream_t st) {
+  dim3 grid((J + 255) / 256, S);
+  tighten_kernel<<<grid, 256, 0, st>>>(J, res, plan, seated, ncap);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st) {

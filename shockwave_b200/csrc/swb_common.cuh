@@ -23,7 +23,10 @@ struct Pwl {
 };
 
 __device__ __forceinline__ double plog(const Pwl &P, double u) {
-  u = fmin(fmax(u, 0.0), 1.0);
+  u = fmax(u, 0.0);
+  // exact at the last breakpoint (lambda_B = 1 in the reference's model): the fallback priorities
+  // reach 1e21 and would turn the ~1e-17 residual of slope*(1-base)+logv into O(10) of objective
+  if (u >= P.base[P.B - 1]) return P.logv[P.B - 1];
   int b = 0;
   for (int i = 1; i < P.B - 1; ++i) b = (u >= P.base[i]) ? i : b;
   return fma(P.slope[b], u - P.base[b], P.logv[b]);

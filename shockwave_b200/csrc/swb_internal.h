@@ -11,6 +11,7 @@
 #define SWB_PWL_BYTES 512           /* >= sizeof(swb::Pwl), 16-byte aligned */
 #define SWB_MAX_DYN_SMEM (227 * 1024)
 #define SWB_MAX_T 128               /* x rows are kept as 128-bit masks in the placement kernel */
+#define SWB_MAX_REPLAN 3             /* packing-feedback re-solves (see tighten_kernel) */
 #define SWB_MAX_J 8192              /* 13 index bits in the placement sort key */
 
 namespace swb {
@@ -24,6 +25,7 @@ struct SolveLaunch {
   // per-scenario scratch in global memory, [S][J]
   double *sc_a, *sc_u0, *sc_R, *sc_ws, *sc_cap;
   uint8_t *sc_g, *sc_nF, *sc_nmax, *sc_n;
+  const uint8_t *ncap; // [S][J] per-job cap on the round count from packing feedback (255 = none)
   double *weights;   // [S][J] out, may be null
   swb_result *res;   // device [S]
 };
@@ -36,6 +38,8 @@ struct PlaceLaunch {
   const double *sc_a, *sc_u0, *sc_R, *sc_ws, *sc_cap;
   const uint8_t *sc_g, *sc_n;
   const double *weights;  // [S][J] (priority, for the fallback re-rank), may be null
+  const int32_t *E, *c;   // solver inputs again (objective re-evaluation with the checker's formula)
+  const double *dbar;
   uint8_t *x, *backfill;  // [S][J][T] out, may be null
   int32_t *nrounds;       // [S][J] out, may be null
   int32_t *ncal;          // [S][J] out, may be null: rounds with idle GPUs in which the job is unscheduled
@@ -43,6 +47,8 @@ struct PlaceLaunch {
 };
 
 cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st);
+cudaError_t launch_tighten(int S, int J, const swb_result *res, const uint8_t *plan, const int32_t *seated,
+                           uint8_t *ncap, cudaStream_t st);
 cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask);
 
 struct ForecastLaunch {
