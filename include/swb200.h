@@ -146,6 +146,10 @@ int swb_forecast(swb_ctx *ctx, const swb_params *prm, const swb_round_args *a, d
                  double *rem, double *ftobj, double *bfkey, double *ft_estimate);
 int swb_forecast_commit(swb_ctx *ctx, int32_t J, int32_t fallback, const int32_t *ncal);
 
+/* Device time (CUDA events on the context's stream) of the two kernels of the latest solve pass and
+ * the number of solve+place passes that call took (1 + packing-feedback re-solves). */
+int swb_last_timings(swb_ctx *ctx, double *ms_solve, double *ms_place, int32_t *passes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,54 +117,51 @@ def _solve(g, E, c, dbar, R, w, G, T, D, k, bases, logv, ftf_cap, rel_gap, time_
     cost[oL:oL + nl] = -(np.repeat(w, B) * np.tile(logv, J)) / (J * T)
     cost[oM] = k
 
-    rows, cols, vals, lo, hi = [], [], [], [], []
+    # constraint blocks, built vectorised (COO triplets); row order: cap, prog, pwl_u, pwl_1, [sos2], mk, [ftf]
+    R_, C_, V_, lo, hi = [], [], [], [], []
     nrow = 0
-
-    def add(rr, cc, vv, lo_, hi_):
-        nonlocal nrow
-        rows.extend(rr); cols.extend(cc); vals.extend(vv)
-        lo.extend(lo_); hi.extend(hi_)
-        nrow = len(lo)
-
     jj = np.arange(J)
-    # cap: sum_j g_j x_jt <= G
-    for t in range(T):
-        add([nrow] * J, (oX + jj * T + t).tolist(), g.astype(float).tolist(), [-np.inf], [float(G)])
-    # prog: dbar_j p_j - D sum_t x_jt <= 0
-    for j in range(J):
-        r0 = nrow
-        add([r0] * (T + 1), [oP + j] + list(range(oX + j * T, oX + (j + 1) * T)),
-            [float(dbar[j])] + [-float(D)] * T, [-np.inf], [0.0])
-    # pwl_u: sum_b lambda_jb base_b - p_j/E_j = c_j/E_j ; pwl_1: sum_b lambda_jb = 1
-    for j in range(J):
-        r0 = nrow
-        add([r0] * (B + 1), list(range(oL + j * B, oL + (j + 1) * B)) + [oP + j],
-            list(map(float, bases)) + [-1.0 / float(E[j])], [c[j] / float(E[j])], [c[j] / float(E[j])])
-        r0 = nrow
-        add([r0] * B, list(range(oL + j * B, oL + (j + 1) * B)), [1.0] * B, [1.0], [1.0])
+    gf = g.astype(float)
+    Ef, cf = E.astype(float), c.astype(float)
+
+    def block(r, cidx, v, lo_, hi_, n):
+        nonlocal nrow
+        R_.append(np.asarray(r) + nrow); C_.append(np.asarray(cidx)); V_.append(np.asarray(v, dtype=float))
+        lo.append(np.broadcast_to(np.asarray(lo_, dtype=float), (n,))); hi.append(np.broadcast_to(np.asarray(hi_, dtype=float), (n,)))
+        nrow += n
+
+    # cap: sum_j g_j x_jt <= G                                  (row t)
+    tt = np.arange(T)
+    block(np.repeat(tt, J), oX + np.tile(jj * T, T) + np.repeat(tt, J), np.tile(gf, T), -np.inf, float(G), T)
+    # prog: dbar_j p_j - D sum_t x_jt <= 0                        (row j)
+    block(np.concatenate([jj, np.repeat(jj, T)]),
+          np.concatenate([oP + jj, oX + np.arange(J * T)]),
+          np.concatenate([dbar, np.full(J * T, -float(D))]), -np.inf, 0.0, J)
+    # pwl_u: sum_b lambda_jb base_b - p_j/E_j = c_j/E_j           (row j)
+    block(np.concatenate([np.repeat(jj, B), jj]),
+          np.concatenate([oL + np.arange(J * B), oP + jj]),
+          np.concatenate([np.tile(np.asarray(bases, dtype=float), J), -1.0 / Ef]), cf / Ef, cf / Ef, J)
+    # pwl_1: sum_b lambda_jb = 1                                  (row j)
+    block(np.repeat(jj, B), oL + np.arange(J * B), np.ones(J * B), 1.0, 1.0, J)
     if with_sos2:
         for j in range(J):
             zb = oZ + j * B
-            r0 = nrow
-            add([r0] * B, list(range(zb, zb + B)), [1.0] * B, [-np.inf], [2.0])
+            block([0] * B, list(range(zb, zb + B)), [1.0] * B, -np.inf, 2.0, 1)
             for b in range(B):
-                r0 = nrow
-                add([r0, r0], [oL + j * B + b, zb + b], [1.0, -1.0], [-np.inf], [0.0])
+                block([0, 0], [oL + j * B + b, zb + b], [1.0, -1.0], -np.inf, 0.0, 1)
             for l in range(0, B - 2):
                 for rr in range(l + 2, B):
-                    r0 = nrow
-                    add([r0, r0], [zb + l, zb + rr], [1.0, 1.0], [-np.inf], [1.0])
+                    block([0, 0], [zb + l, zb + rr], [1.0, 1.0], -np.inf, 1.0, 1)
     # mk: M + dbar_j p_j >= R_j  (M >= 0 through its bound: rem_j = max(0, .))
-    for j in range(J):
-        r0 = nrow
-        add([r0, r0], [oM, oP + j], [1.0, float(dbar[j])], [float(R[j])], [np.inf])
+    block(np.concatenate([jj, jj]), np.concatenate([np.full(J, oM), oP + jj]),
+          np.concatenate([np.ones(J), dbar]), R, np.inf, J)
     # ftf: rem_j <= cap_j  <=>  cap_j >= 0  and  dbar_j p_j >= R_j - cap_j
     if ftf_cap is not None:
         if np.any(ftf_cap < 0):
             return False, None, None, None
-        for j in range(J):
-            r0 = nrow
-            add([r0], [oP + j], [float(dbar[j])], [float(R[j] - ftf_cap[j])], [np.inf])
+        block(jj, oP + jj, dbar, R - ftf_cap, np.inf, J)
+    rows, cols, vals = np.concatenate(R_), np.concatenate(C_), np.concatenate(V_)
+    lo, hi = np.concatenate(lo), np.concatenate(hi)
 
     A = sp.csr_matrix((vals, (rows, cols)), shape=(nrow, nvar))
     lb = np.zeros(nvar)

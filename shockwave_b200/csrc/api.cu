@@ -54,7 +54,7 @@ struct swb_ctx {
   cudaStream_t st = nullptr;
   // ---- work buffers of a solve
   DBuf prm, res, g, E, c, dbar, rem, ftobj, bfkey, x, bf, nr, w;
-  DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask, sncap, seated;
+  DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask, sncap, seated, scth, sths, sn0;
   // ---- resident job table (by slot)
   int nslots = 0;
   DBuf t_off, t_E, t_nm, t_g, t_ns, t_ts, t_modes, t_mm, t_amp, s_r0, s_rl, s_cnt, s_vl, s_acc;
@@ -66,6 +66,9 @@ struct swb_ctx {
   DBuf f_slots, f_prog, f_mend, f_mns, f_remfb, f_bffb, f_ampok, f_ampfb, f_ftest, f_ncal;
   swb::ForecastLaunch last_fc;   // descriptor of the latest forecast (for the calibration commit)
   bool have_fc = false;
+  // CUDA events around the two kernels of the latest solve pass (bench.py's roofline)
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  int last_passes = 0;
   // pinned staging for the scalar results
   swb_result *h_res = nullptr;
   size_t h_res_cap = 0;
@@ -90,6 +93,7 @@ int swb_create(swb_ctx **out, int device) {
   swb_ctx *c = new swb_ctx();
   c->device = device;
   CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&c->ev[i]));
   *out = c;
   return 0;
 }
@@ -99,12 +103,13 @@ void swb_destroy(swb_ctx *c) {
   cudaSetDevice(c->device);
   DBuf *all[] = {&c->prm, &c->res, &c->g, &c->E, &c->c, &c->dbar, &c->rem, &c->ftobj, &c->bfkey, &c->x,
                  &c->bf, &c->nr, &c->w, &c->sa, &c->su0, &c->sR, &c->sws, &c->scap, &c->sg, &c->snF,
-                 &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
+                 &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->scth, &c->sths, &c->sn0, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
                  &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc,
                  &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
                  &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal};
   for (DBuf *b : all) b->release();
   if (c->h_res) cudaFreeHost(c->h_res);
+  for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -160,7 +165,11 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   CK(c->prm.need(sizeof(swb_params) * S, c->st));
   CK(c->res.need(sizeof(swb_result) * S, c->st));
   CK(cudaMemcpyAsync(c->prm.p, h_prm, sizeof(swb_params) * S, cudaMemcpyHostToDevice, c->st));
-  if (J > SWB_SMEM_JOBS) CK(c->gmask.need(n * 4 * sizeof(unsigned long long), c->st));
+  if (J > SWB_SMEM_JOBS) {
+    CK(c->gmask.need(n * 4 * sizeof(unsigned long long), c->st));
+    CK(c->scth.need(n * 8, c->st)); CK(c->sths.need(n * SWB_MAX_BASES * 4, c->st));
+    CK(c->sn0.need(n * SWB_MAX_BASES, c->st));
+  }
   swb::SolveLaunch L;
   L.S = S; L.J = J; L.per_scn = per_scn; L.jobs_in_smem = (J <= SWB_SMEM_JOBS) ? 1 : 0;
   L.prm = c->prm.as<swb_params>();
@@ -169,6 +178,7 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   L.sc_ws = c->sws.as<double>(); L.sc_cap = c->scap.as<double>();
   L.sc_g = c->sg.as<uint8_t>(); L.sc_nF = c->snF.as<uint8_t>(); L.sc_nmax = c->snmax.as<uint8_t>();
   L.sc_n = c->sn.as<uint8_t>();
+  L.sc_cth = c->scth.as<double>(); L.sc_ths = c->sths.as<float>(); L.sc_n0 = c->sn0.as<uint8_t>();
   L.weights = weights ? weights : c->w.as<double>();
   L.res = c->res.as<swb_result>();
   L.ncap = c->sncap.as<uint8_t>();
@@ -181,8 +191,12 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   int rc2 = ensure_hres(c, S);
   if (rc2) return rc2;
   for (int pass = 0; pass < SWB_MAX_REPLAN + 1; ++pass) {
-    CK(swb::launch_solve(L, c->st));
+    CK(cudaEventRecord(c->ev[0], c->st));
+    CK(swb::launch_solve(L, c->st, h_prm[0].nbases));
+    CK(cudaEventRecord(c->ev[1], c->st));
     CK(swb::launch_place(P, c->st, c->gmask.as<unsigned long long>()));
+    CK(cudaEventRecord(c->ev[2], c->st));
+    c->last_passes = pass + 1;
     CK(cudaMemcpyAsync(c->h_res, c->res.p, sizeof(swb_result) * S, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     int shortf = 0;
@@ -203,8 +217,8 @@ int swb_solve(swb_ctx *c, const swb_solve_args *a) {
   CK(cudaSetDevice(c->device));
   const int S = a->S, J = a->J, T = a->prm[0].future_rounds;
   for (int s = 1; s < S; ++s)
-    if (a->prm[s].future_rounds != T)
-      return fail(SWB_ERR_ARG, "swb_solve: all scenarios of one call must share future_rounds");
+    if (a->prm[s].future_rounds != T || a->prm[s].nbases != a->prm[0].nbases)
+      return fail(SWB_ERR_ARG, "swb_solve: all scenarios of one call must share future_rounds and nbases");
   const size_t nj = a->per_scenario_jobs ? (size_t)S * J : (size_t)J;
   const size_t nx = (size_t)S * J * T;
   const int32_t *g, *E, *cc;
@@ -454,6 +468,17 @@ int swb_forecast(swb_ctx *c, const swb_params *prm, const swb_round_args *a, dou
   if (bfkey) CK(cudaMemcpyAsync(bfkey, c->bfkey.p, J * 8, cudaMemcpyDeviceToHost, c->st));
   if (ft_estimate) CK(cudaMemcpyAsync(ft_estimate, c->f_ftest.p, J * 8, cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int swb_last_timings(swb_ctx *c, double *ms_solve, double *ms_place, int32_t *passes) {
+  if (!c) return fail(SWB_ERR_ARG, "null ctx");
+  float a = 0.f, b = 0.f;
+  CK(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+  CK(cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+  if (ms_solve) *ms_solve = a;
+  if (ms_place) *ms_place = b;
+  if (passes) *passes = c->last_passes;
   return 0;
 }
 

@@ -7,11 +7,16 @@
 // concave maximise, so the program collapses to
 //     max_n  sum_j w_j plog((c_j + min(D n_j/dbar_j, E_j-c_j))/E_j)/(J T)  -  k max_j rem_j(n_j)
 //     s.t.   sum_j g_j n_j <= G T,   nF_j <= n_j <= T            (nF_j from the FTF rows, :573-597)
-// which is solved here exactly in its Lagrangian form: a clearing price mu on GPU-rounds found by
-// bisection (every job answers a price with a closed-form best response on its piecewise-linear
-// utility) nested in a search over the makespan threshold M.  One CTA per scenario; job constants
-// are staged in shared memory; all reductions are warp shuffles + one barrier.
-// The dense J x T placement (which round each of the n_j rounds lands in) is place.cu.
+// which is solved here in its Lagrangian form: a clearing price mu on GPU-rounds found by bisection
+// (every job answers a price with a closed-form best response on its piecewise-linear utility)
+// nested in a search over the makespan threshold M.  One CTA per scenario.
+//
+// Hot loop = cost(M, mu) = sum_j g_j n_j(M, mu), evaluated ~10^3 times per solve.  It runs on a
+// per-job RESPONSE TABLE staged in shared memory: in the normalised price rho = mu * g_j/(a_j ws_j)
+// the thresholds of whole PWL segments are the segment slopes (shared constants), so a job only
+// needs, per segment count bs, the number of whole rounds n0[bs] and the threshold ths[bs] of the one
+// round that straddles the breakpoint.  ~35 instructions per job and evaluation; reductions are warp
+// shuffles + one barrier.  The dense J x T placement of the counts is place.cu.
 #include <math.h>
 
 #include "swb_common.cuh"
@@ -19,54 +24,48 @@
 
 namespace swb {
 
-
-struct JobsV {  // job constants of one scenario, in shared memory (J <= SWB_SMEM_JOBS) or global
-  double *a, *u0, *R, *ws, *cap;
-  uint8_t *g, *nF, *nmax, *n;
+struct Tab {             // response table: shared memory for J <= SWB_SMEM_JOBS, else global scratch
+  double *cth, *R;       // rho = mu * cth ; remaining runtime
+  float *ths;            // [J][B] straddle-round threshold in rho units (-1: no such round)
+  uint8_t *n0;           // [J][B] whole rounds inside the segments whose slope beats rho
+  uint8_t *g, *nF, *nmax;
 };
 
 struct Ctx {
   const Pwl *P;
-  JobsV v;
-  int J, T, GT;
-  double D;
+  Tab t;
+  // exact per-job constants, global scratch (read ~20x per solve: welfare / makespan passes)
+  double *a, *u0, *ws, *cap;
+  uint8_t *n;
+  int J, T, GT, B;
+  double D, invD;
 };
 
-__device__ __forceinline__ double util_of(const Ctx &c, int j, int n);
-
-// closed-form best response of job j to a price mu (welfare per GPU-round): the largest n with
-// F_j(n) - F_j(n-1) > mu g_j.  Rounds that lie wholly in PWL segments of slope > theta pass,
-// rounds wholly in flatter segments fail, the one straddling round is tested explicitly.
+// best response of job j to the price mu: the largest n with F_j(n) - F_j(n-1) > mu g_j
 __device__ __forceinline__ int pref_n(const Ctx &c, int j, double mu) {
-  const int nmax = c.v.nmax[j];
-  if (nmax == 0 || mu <= 0.0) return nmax;
+  const int nmax = c.t.nmax[j];
+  if (mu <= 0.0) return nmax;
+  const double rho = mu * c.t.cth[j];
   const Pwl &P = *c.P;
-  const double a = c.v.a[j], u0 = c.v.u0[j], ws = c.v.ws[j];
-  const double mg = mu * (double)c.v.g[j];
-  const double theta = mg / (a * ws);
   int bs = 0;
-  for (int b = 0; b < P.B - 1; ++b) bs += (P.slope[b] > theta) ? 1 : 0;
-  int n0 = 0;
-  if (bs > 0) {
-    const double nb = (P.base[bs] - u0) / a;
-    n0 = nb <= 0.0 ? 0 : (nb >= (double)nmax ? nmax : (int)floor(nb));
-  }
-  if (n0 < nmax) {
-    const double d = util_of(c, j, n0 + 1) - util_of(c, j, n0);
-    n0 += (d > mg) ? 1 : 0;
-  }
-  return n0;
+#pragma unroll 4
+  for (int b = 0; b < c.B - 1; ++b) bs += (P.slope[b] > rho) ? 1 : 0;
+  const int i = j * c.B + bs;
+  int n = c.t.n0[i];
+  n += (rho < (double)c.t.ths[i]) ? 1 : 0;
+  return n;
 }
 
 // rounds job j must get so that rem_j <= M  (rem_j = max(0, R_j - min(D n, cap_j)))
 __device__ __forceinline__ int lower_n(const Ctx &c, int j, double M) {
-  const double need = c.v.R[j] - M;
+  const double need = c.t.R[j] - M;
   int L = 0;
   if (need > 0.0) {
-    const double q = ceil(need / c.D - 1e-9);
-    L = q >= (double)c.v.nmax[j] ? c.v.nmax[j] : (int)q;
+    const double q = ceil(need * c.invD - 1e-9);
+    const int nmax = c.t.nmax[j];
+    L = q >= (double)nmax ? nmax : (int)q;
   }
-  const int nF = c.v.nF[j];
+  const int nF = c.t.nF[j];
   return L > nF ? L : nF;
 }
 
@@ -76,20 +75,20 @@ __device__ __forceinline__ int job_n(const Ctx &c, int j, double M, double mu) {
 }
 
 __device__ __forceinline__ double rem_of(const Ctx &c, int j, int n) {
-  const double done = fmin(c.D * (double)n, c.v.cap[j]);
-  return fmax(0.0, c.v.R[j] - done);
+  const double done = fmin(c.D * (double)n, c.cap[j]);
+  return fmax(0.0, c.t.R[j] - done);
 }
 
 // weighted PWL-log utility of n rounds.  A job that completes inside the window gets plog(1) = 0
 // EXACTLY: the fallback priorities reach 1e20 and would amplify a 1-ulp error in u to O(1).
 __device__ __forceinline__ double util_of(const Ctx &c, int j, int n) {
-  const double u = (c.D * (double)n >= c.v.cap[j]) ? 1.0 : fma(c.v.a[j], (double)n, c.v.u0[j]);
-  return c.v.ws[j] * plog(*c.P, u);
+  const double u = (c.D * (double)n >= c.cap[j]) ? 1.0 : fma(c.a[j], (double)n, c.u0[j]);
+  return c.ws[j] * plog(*c.P, u);
 }
 
 __device__ long long cost_at(const Ctx &c, BlockRed &br, double M, double mu) {
   long long s = 0;
-  for (int j = threadIdx.x; j < c.J; j += blockDim.x) s += (long long)c.v.g[j] * job_n(c, j, M, mu);
+  for (int j = threadIdx.x; j < c.J; j += blockDim.x) s += (long long)c.t.g[j] * job_n(c, j, M, mu);
   return br.sumll(s);
 }
 
@@ -104,12 +103,13 @@ __device__ Price solve_price(const Ctx &c, BlockRed &br, double M, double mu_max
   // Bisection on the BIT PATTERN of the (positive) price: the fallback priorities span 20+ orders of
   // magnitude (ratio^lam, shockwave.py:899-903), so an arithmetic midpoint would stop ~2^-44 * mu_max
   // above the real clearing price and lump every cheaper item into one "tie".  Positive doubles are
-  // ordered like their bit patterns, so this converges to two ADJACENT doubles in <= 63 steps.
+  // ordered like their bit patterns; the loop ends when hi/lo - 1 < 2^-40 (everything priced inside
+  // such an interval is treated as a tie and filled in job order).
   unsigned long long lob = 0ull, hib = (unsigned long long)__double_as_longlong(mu_max);
   double lo = 0.0, hi = mu_max;
   long long chi = cost_at(c, br, M, hi);
   p.iters++;
-  while (hib - lob > 1ull) {
+  while (hib - lob > (1ull << 12)) {
     const unsigned long long midb = lob + ((hib - lob) >> 1);
     const double mid = __longlong_as_double((long long)midb);
     const long long cm = cost_at(c, br, M, mid);
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
   const int s = blockIdx.x;
   const int J = L.J;
   const swb_params &prm = L.prm[s];
-  const int T = prm.future_rounds, G = prm.ngpus;
+  const int T = prm.future_rounds, G = prm.ngpus, B = prm.nbases;
   const double D = prm.round_duration, k = prm.k;
 
   // ---- shared-memory carve-up -------------------------------------------------------------
@@ -155,26 +155,27 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
   Ctx c;
   const size_t so = (size_t)s * J;
   if (L.jobs_in_smem) {
-    c.v.a = reinterpret_cast<double *>(p);   p += sizeof(double) * J;
-    c.v.u0 = reinterpret_cast<double *>(p);  p += sizeof(double) * J;
-    c.v.R = reinterpret_cast<double *>(p);   p += sizeof(double) * J;
-    c.v.ws = reinterpret_cast<double *>(p);  p += sizeof(double) * J;
-    c.v.cap = reinterpret_cast<double *>(p); p += sizeof(double) * J;
-    c.v.g = p;    p += J;
-    c.v.nF = p;   p += J;
-    c.v.nmax = p; p += J;
+    c.t.cth = reinterpret_cast<double *>(p); p += sizeof(double) * J;
+    c.t.R = reinterpret_cast<double *>(p);   p += sizeof(double) * J;
+    c.t.ths = reinterpret_cast<float *>(p);  p += sizeof(float) * J * B;
+    c.t.n0 = p;   p += (size_t)J * B;
+    c.t.g = p;    p += J;
+    c.t.nF = p;   p += J;
+    c.t.nmax = p; p += J;
   } else {
-    c.v.a = L.sc_a + so; c.v.u0 = L.sc_u0 + so; c.v.R = L.sc_R + so; c.v.ws = L.sc_ws + so;
-    c.v.cap = L.sc_cap + so; c.v.g = L.sc_g + so; c.v.nF = L.sc_nF + so; c.v.nmax = L.sc_nmax + so;
+    c.t.cth = L.sc_cth + so; c.t.R = L.sc_R + so;
+    c.t.ths = L.sc_ths + so * SWB_MAX_BASES; c.t.n0 = L.sc_n0 + so * SWB_MAX_BASES;
+    c.t.g = L.sc_g + so; c.t.nF = L.sc_nF + so; c.t.nmax = L.sc_nmax + so;
   }
-  c.v.n = L.sc_n + so;
-  c.P = P; c.J = J; c.T = T; c.GT = G * T; c.D = D;
+  c.a = L.sc_a + so; c.u0 = L.sc_u0 + so; c.ws = L.sc_ws + so; c.cap = L.sc_cap + so;
+  c.n = L.sc_n + so;
+  c.P = P; c.J = J; c.T = T; c.GT = G * T; c.B = B; c.D = D; c.invD = 1.0 / D;
   BlockRed br(red);
 
   if (threadIdx.x == 0) {
-    P->B = prm.nbases;
-    for (int b = 0; b < prm.nbases; ++b) { P->base[b] = prm.bases[b]; P->logv[b] = prm.logv[b]; }
-    for (int b = 0; b + 1 < prm.nbases; ++b)
+    P->B = B;
+    for (int b = 0; b < B; ++b) { P->base[b] = prm.bases[b]; P->logv[b] = prm.logv[b]; }
+    for (int b = 0; b + 1 < B; ++b)
       P->slope[b] = (prm.logv[b + 1] - prm.logv[b]) / (prm.bases[b + 1] - prm.bases[b]);
   }
   __syncthreads();
@@ -196,9 +197,10 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
     int nfin = cap <= 0.0 ? 0 : (int)fmin(ceil(cap / D - 1e-9), 255.0);
     int nmax = nfin < T ? nfin : T;
     if (gI[j] > G) nmax = 0;  // a gang wider than the cluster violates every capacity row (shockwave.py:317)
-    if (L.ncap && (int)L.ncap[so + j] < nmax) nmax = L.ncap[so + j];  // packing feedback (see tighten_kernel)
-    c.v.a[j] = a; c.v.u0[j] = cf / Ef; c.v.R[j] = R; c.v.cap[j] = cap;
-    c.v.g[j] = (uint8_t)gI[j]; c.v.nmax[j] = (uint8_t)nmax;
+    if (L.ncap && (int)L.ncap[so + j] < nmax) nmax = L.ncap[so + j];  // packing feedback (tighten_kernel)
+    c.a[j] = a; c.u0[j] = cf / Ef; c.cap[j] = cap;
+    c.t.R[j] = R; L.sc_R[so + j] = R;
+    c.t.g[j] = (uint8_t)gI[j]; c.t.nmax[j] = (uint8_t)nmax;
     const double capF = share * (prm.rhomax * ftI[j] - next_t);
     int nF = 0, bad = 0;
     if (capF < 0.0) bad = 1;
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
         }
       }
     }
-    c.v.nF[j] = (uint8_t)nF;
+    c.t.nF[j] = (uint8_t)nF;
     infeasible += bad;
     forced += (long long)gI[j] * nF;
   }
@@ -221,11 +223,13 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
   forced = br.sumll(forced);
   const bool ftf_ok = (infeasible == 0) && (forced <= (long long)c.GT);
 
-  // fallback priorities (shockwave.py:830-911); weights stay 1 when the FTF rows are satisfiable
+  // fallback priorities (shockwave.py:830-911); weights stay 1 when the FTF rows are satisfiable.
+  // Then the response table of the job (see the file header).
+  double mu_max = 0.0, mfloor = 0.0, mtop = 0.0;
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
     double w = 1.0;
     if (!ftf_ok) {
-      c.v.nF[j] = 0;
+      c.t.nF[j] = 0;
       const double R = RfbI[j];
       const double ratio = (D * (double)prm.round_ptr + R / share) / ftI[j];
       if (ratio > prm.rhomax) {
@@ -233,23 +237,37 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
         w = fmin(w, 1e300);
       }
     }
-    c.v.ws[j] = w * invJT;
+    const double ws = w * invJT;
+    c.ws[j] = ws;
     if (L.weights) L.weights[so + j] = w;
-  }
-  __syncthreads();
-
-  // ---- phase 2: price ceiling, makespan floor, smallest packable makespan -------------------
-  double mu_max = 0.0, mfloor = 0.0, mtop = 0.0;
-  for (int j = threadIdx.x; j < J; j += blockDim.x) {
-    if (c.v.nmax[j] > 0)
-      mu_max = fmax(mu_max, (util_of(c, j, 1) - util_of(c, j, 0)) / (double)c.v.g[j]);
-    const double R = c.v.R[j];
-    mfloor = fmax(mfloor, R - fmin(D * (double)c.v.nmax[j], c.v.cap[j]));
+    const double a = c.a[j], u0 = c.u0[j], cap = c.cap[j];
+    const int nmax = c.t.nmax[j];
+    c.t.cth[j] = (double)c.t.g[j] / (a * ws);
+    for (int bs = 0; bs < B; ++bs) {
+      int n0 = 0;
+      if (bs > 0) {
+        const double nb = (P->base[bs] - u0) / a;
+        n0 = nb <= 0.0 ? 0 : (nb >= (double)nmax ? nmax : (int)floor(nb));
+      }
+      float th = -1.0f;
+      if (n0 < nmax) {
+        const double u1 = (D * (double)(n0 + 1) >= cap) ? 1.0 : fma(a, (double)(n0 + 1), u0);
+        const double u_0 = (D * (double)n0 >= cap) ? 1.0 : fma(a, (double)n0, u0);
+        th = (float)((plog(*P, u1) - plog(*P, u_0)) / a);
+      }
+      c.t.n0[j * B + bs] = (uint8_t)n0;
+      c.t.ths[j * B + bs] = th;
+    }
+    if (nmax > 0) mu_max = fmax(mu_max, (util_of(c, j, 1) - util_of(c, j, 0)) / (double)c.t.g[j]);
+    const double R = c.t.R[j];
+    mfloor = fmax(mfloor, R - fmin(D * (double)nmax, cap));
     mtop = fmax(mtop, R);
   }
-  mu_max = br.max(mu_max) * (1.0 + 1e-9) + 1e-300;
+  // ---- phase 2: price ceiling, makespan floor, smallest packable makespan -------------------
+  mu_max = br.max(mu_max) * (1.0 + 1e-6) + 1e-300;
   mfloor = fmax(0.0, br.max(mfloor));
   mtop = br.max(mtop);
+  __syncthreads();
   const double INF_M = 1e300;
   const double eps = 1e-6 * D;
 
@@ -291,7 +309,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
   // ---- phase 4: integral allocation at the chosen threshold ----------------------------------
   Price pr = solve_price(c, br, best_thr, mu_max);
   iters += pr.iters;
-  for (int j = threadIdx.x; j < J; j += blockDim.x) c.v.n[j] = (uint8_t)job_n(c, j, best_thr, pr.hi);
+  for (int j = threadIdx.x; j < J; j += blockDim.x) c.n[j] = (uint8_t)job_n(c, j, best_thr, pr.hi);
   long long left = (long long)c.GT - pr.cost_hi;
   __syncthreads();
 
@@ -304,7 +322,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
     for (int base = 0; base < J; base += blockDim.x) {
       const int j = base + threadIdx.x;
       int extra = 0, gj = 1;
-      if (j < J) { gj = c.v.g[j]; extra = job_n(c, j, best_thr, pr.lo) - (int)c.v.n[j]; if (extra < 0) extra = 0; }
+      if (j < J) { gj = c.t.g[j]; extra = job_n(c, j, best_thr, pr.lo) - (int)c.n[j]; if (extra < 0) extra = 0; }
       long long v = (long long)gj * extra, incl = v;
       for (int o = 1; o < 32; o <<= 1) {
         long long t = __shfl_up_sync(SWB_FULL, incl, o);
@@ -321,7 +339,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
         if (room > 0) {
           long long take = room / gj;
           if (take > extra) take = extra;
-          c.v.n[j] = (uint8_t)(c.v.n[j] + take);
+          c.n[j] = (uint8_t)(c.n[j] + take);
         }
       }
       __syncthreads();
@@ -333,52 +351,44 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
   // (b) completion: best remaining item that still fits, a few times
   {
     long long used = 0;
-    for (int j = threadIdx.x; j < J; j += blockDim.x) used += (long long)c.v.g[j] * c.v.n[j];
+    for (int j = threadIdx.x; j < J; j += blockDim.x) used += (long long)c.t.g[j] * c.n[j];
     used = br.sumll(used);
     left = (long long)c.GT - used;
     for (int rep = 0; rep < 32 && left > 0; ++rep) {
       double bd = 0.0;
       for (int j = threadIdx.x; j < J; j += blockDim.x) {
-        const int n = c.v.n[j];
-        if (n < c.v.nmax[j] && (long long)c.v.g[j] <= left)
-          bd = fmax(bd, (util_of(c, j, n + 1) - util_of(c, j, n)) / (double)c.v.g[j]);
+        const int n = c.n[j];
+        if (n < c.t.nmax[j] && (long long)c.t.g[j] <= left)
+          bd = fmax(bd, (util_of(c, j, n + 1) - util_of(c, j, n)) / (double)c.t.g[j]);
       }
       bd = br.max(bd);
       if (!(bd > 0.0)) break;
       double bj = 1e300;
       for (int j = threadIdx.x; j < J; j += blockDim.x) {
-        const int n = c.v.n[j];
-        if (n < c.v.nmax[j] && (long long)c.v.g[j] <= left &&
-            (util_of(c, j, n + 1) - util_of(c, j, n)) / (double)c.v.g[j] >= bd)
+        const int n = c.n[j];
+        if (n < c.t.nmax[j] && (long long)c.t.g[j] <= left &&
+            (util_of(c, j, n + 1) - util_of(c, j, n)) / (double)c.t.g[j] >= bd)
           bj = fmin(bj, (double)j);
       }
       bj = br.min(bj);
       if (bj >= 1e299) break;
       const int wj = (int)bj;
-      if (threadIdx.x == 0) c.v.n[wj] = (uint8_t)(c.v.n[wj] + 1);
-      left -= c.v.g[wj];
+      if (threadIdx.x == 0) c.n[wj] = (uint8_t)(c.n[wj] + 1);
+      left -= c.t.g[wj];
       __syncthreads();
     }
   }
 
-  // ---- phase 5: scalars of the plan ---------------------------------------------------------
+  // ---- phase 5: scalars of the plan; constants the placement kernel re-reads ------------------
   double w = 0.0, me = 0.0;
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
-    const int n = c.v.n[j];
+    const int n = c.n[j];
     w += util_of(c, j, n);
     me = fmax(me, rem_of(c, j, n));
+    if (L.jobs_in_smem) { L.sc_g[so + j] = c.t.g[j]; L.sc_nF[so + j] = c.t.nF[j]; L.sc_nmax[so + j] = c.t.nmax[j]; }
   }
   w = br.sum(w);
   me = br.max(me);
-  if (!L.jobs_in_smem) __threadfence_block();
-  else {
-    // the placement kernel re-reads the job constants from global scratch
-    for (int j = threadIdx.x; j < J; j += blockDim.x) {
-      L.sc_a[so + j] = c.v.a[j]; L.sc_u0[so + j] = c.v.u0[j]; L.sc_R[so + j] = c.v.R[j];
-      L.sc_ws[so + j] = c.v.ws[j]; L.sc_cap[so + j] = c.v.cap[j]; L.sc_g[so + j] = c.v.g[j];
-      L.sc_nF[so + j] = c.v.nF[j]; L.sc_nmax[so + j] = c.v.nmax[j];
-    }
-  }
   if (threadIdx.x == 0) {
     swb_result &r = L.res[s];
     r.status = ftf_ok ? SWB_ST_OK : SWB_ST_FALLBACK;
@@ -415,9 +425,9 @@ cudaError_t launch_tighten(int S, int J, const swb_result *res, const uint8_t *p
   return cudaGetLastError();
 }
 
-cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st) {
+cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st, int nbases) {
   size_t smem = SWB_PWL_BYTES + 2 * 64 * sizeof(double);
-  if (L.jobs_in_smem) smem += (size_t)L.J * (5 * sizeof(double) + 3);
+  if (L.jobs_in_smem) smem += (size_t)L.J * (2 * sizeof(double) + 5 * (size_t)nbases + 3);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncAttributes fa;

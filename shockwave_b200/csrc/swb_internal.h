@@ -25,6 +25,10 @@ struct SolveLaunch {
   // per-scenario scratch in global memory, [S][J]
   double *sc_a, *sc_u0, *sc_R, *sc_ws, *sc_cap;
   uint8_t *sc_g, *sc_nF, *sc_nmax, *sc_n;
+  // response table in global memory, only used when J > SWB_SMEM_JOBS ([S][J] and [S][J][SWB_MAX_BASES])
+  double *sc_cth;
+  float *sc_ths;
+  uint8_t *sc_n0;
   const uint8_t *ncap; // [S][J] per-job cap on the round count from packing feedback (255 = none)
   double *weights;   // [S][J] out, may be null
   swb_result *res;   // device [S]
@@ -46,7 +50,7 @@ struct PlaceLaunch {
   swb_result *res;        // device [S] (status in, objective/shortfall updated)
 };
 
-cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st);
+cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st, int nbases);
 cudaError_t launch_tighten(int S, int J, const swb_result *res, const uint8_t *plan, const int32_t *seated,
                            uint8_t *ncap, cudaStream_t st);
 cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask);

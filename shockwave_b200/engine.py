@@ -56,7 +56,7 @@ class RoundArgs(C.Structure):
 
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
            "swb_solve", "swb_job_add", "swb_job_remove", "swb_round_solve", "swb_forecast",
-           "swb_forecast_commit"]
+           "swb_forecast_commit", "swb_last_timings"]
 
 _lib = None
 
@@ -94,6 +94,8 @@ def load_library():
     lib.swb_forecast.restype = C.c_int
     lib.swb_forecast_commit.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     lib.swb_forecast_commit.restype = C.c_int
+    lib.swb_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    lib.swb_last_timings.restype = C.c_int
     _lib = lib
     return lib
 
@@ -232,3 +234,11 @@ class Engine:
         ncal = np.ascontiguousarray(ncal, dtype=np.int32)
         self._check(self.lib.swb_forecast_commit(self.h, len(ncal), int(bool(fallback)), _ptr(ncal)),
                     "swb_forecast_commit")
+
+    def last_timings(self):
+        a, b, n = C.c_double(), C.c_double(), C.c_int32()
+        self._check(self.lib.swb_last_timings(self.h, C.byref(a), C.byref(b), C.byref(n)), "swb_last_timings")
+        return dict(ms_solve=a.value, ms_place=b.value, passes=n.value)
+
+    def stream_ptr(self):
+        return int(self.lib.swb_stream(self.h) or 0)
