@@ -47,7 +47,7 @@ def test_forecast_replay_matches_reference():
         sl = [slots[j] for j in live]
         f = eng.forecast(prm, sl, s["c"], s["meas_ns"], s["meas_end"], s["reestimate"], st[live[0]]["grd"])
         for key in ("dbar", "rem", "ftobj"):
-            rel = np.abs(f[key] - s[key]) / np.abs(s[key])
+            rel = np.abs(f[key] - s[key]) / np.maximum(1e-300, np.abs(s[key]))
             worst[key] = max(worst[key], float(rel.max()))
         fb = s["status"] == om.STATUS_FALLBACK
         eng.forecast_commit(fb, ncal_of(s["x"], s["g"], G))

@@ -22,7 +22,7 @@ def test_replay_matches_reference_recorded_forecast():
             nbad += int(np.sum(rel > 1e-9))
             worst[key] = max(worst[key], float(rel.max()))
         if s["status"] == 1:
-            rel = np.abs(out["rem_fb"] - s["rem_fb"]) / np.abs(s["rem_fb"])
+            rel = np.abs(out["rem_fb"] - s["rem_fb"]) / np.maximum(1e-300, np.abs(s["rem_fb"]))
             assert rel.max() <= 1e-9
     print("worst relative deviation", worst, "entries beyond 1e-9:", nbad)
     # float64 everywhere; only summation order differs from the reference (amp*sum vs sum(amp*x))

@@ -1,0 +1,94 @@
+"""CPU tests of the HiGHS oracle itself (oracle/shockwave_milp.py) and its pinning."""
+import json
+import os
+
+import numpy as np
+
+from oracle import shockwave_milp as om
+from tests import fixtures as fx
+from tests.synth import synth_problem
+
+LOGV = om.pwl_log_values(fx.BASES, fx.ORIGIN)
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _args(pb, G, T, D=120.0, k=1e-3):
+    return (pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"], G, T, D, pb["round_ptr"], k, 12.0, 1.0,
+            fx.BASES, LOGV)
+
+
+def test_pinned_against_reference_golden_pickle():
+    """End-to-end pin: the UNMODIFIED reference simulator driven by this oracle reproduces the golden
+    pickle (scheduler/reproduce/pickles/tacc_32gpus/shockwave_*.pickle) within the 3 % spread of the
+    three Shockwave pickles the reference ships.  Numbers were recorded by
+    tests/golden/make_solve_fixtures.py."""
+    pin = json.load(open(os.path.join(HERE, "golden", "tacc32_oracle_pin.json")))
+    o, g = pin["oracle"], pin["golden"]
+    for key in ("makespan", "avg_jct", "cluster_util"):
+        assert abs(o[key] - g[key]) / g[key] < 0.03, (key, o[key], g[key])
+    assert abs(o["rounds"] - g["rounds"]) <= 6
+    assert abs(o["worst_ftf"] - g["worst_ftf"]) / g["worst_ftf"] < 0.10
+    assert abs(o["unfair_frac"] - g["unfair_frac"]) < 0.03
+
+
+def test_sos2_binaries_are_redundant():
+    """The reference's z_{j,b} SOS2 rows (shockwave.py:403-419) do not change the optimum of a concave
+    maximise: same objective with and without them."""
+    for seed in range(3):
+        pb = synth_problem(10, 8, 6, seed=seed, tight=3.0)
+        a = om.dynamic_eisenberg_gale(*_args(pb, 8, 6), rel_gap=1e-9, with_sos2=False, do_rank=False)
+        b = om.dynamic_eisenberg_gale(*_args(pb, 8, 6), rel_gap=1e-9, with_sos2=True, do_rank=False)
+        assert a["status"] == b["status"]
+        assert abs(a["objective"] - b["objective"]) <= 1e-7 * abs(a["objective"])
+
+
+def test_solution_is_feasible_and_objective_consistent():
+    pb = synth_problem(40, 16, 12, seed=5, tight=3.0)
+    r = om.dynamic_eisenberg_gale(*_args(pb, 16, 12), rel_gap=1e-6)
+    ev = om.evaluate(r["x"], pb["g"], pb["E"].astype(float), pb["c"].astype(float), pb["dbar"], pb["rem"],
+                     r["weights"], 16, 12, 120.0, 1e-3, fx.BASES, LOGV)
+    assert ev[4]
+    assert abs(ev[0] - r["objective"]) <= 1e-6 * abs(r["objective"])
+    lp = om.dynamic_eisenberg_gale(*_args(pb, 16, 12), relax=True)
+    assert lp["objective"] >= r["objective"] - 1e-9
+
+
+def test_fallback_path_and_rank():
+    pb = synth_problem(24, 16, 10, seed=2, tight=0.3)       # FTF rows infeasible
+    r = om.dynamic_eisenberg_gale(*_args(pb, 16, 10), rel_gap=1e-6, do_rank=False)
+    assert r["status"] == om.STATUS_FALLBACK
+    prio = r["weights"]
+    assert prio.max() > 1.0
+    y = om.rank_in_schedule(r["x"], prio, pb["g"].astype(np.int64), 16, 1e-6, 15.0)
+    assert np.array_equal(y.sum(axis=1), r["x"].sum(axis=1))           # counts kept
+    assert np.all(y.T @ pb["g"] <= 16)
+    assert om.rank_objective(y, prio) <= om.rank_objective(r["x"], prio) + 1e-9
+
+
+def test_recorded_solves_are_reproducible():
+    """Re-solving recorded inputs gives the recorded verdict and an objective within the MIP gap."""
+    for i in (0, 17, 60, 97, 128):
+        s = fx.solve(i)
+        r = om.dynamic_eisenberg_gale(s["g"], s["E"], s["c"], s["dbar"], s["rem"], s["ftobj"], fx.TACC["G"],
+                                      fx.TACC["T"], fx.TACC["D"], s["round_ptr"], fx.TACC["k"], fx.TACC["lam"],
+                                      fx.TACC["rhomax"], fx.BASES, LOGV, rel_gap=1e-3, do_rank=False)
+        assert r["status"] == s["status"]
+        if s["status"] == om.STATUS_FTF_FEASIBLE:
+            assert abs(r["objective"] - s["objective"]) <= 2e-3 * abs(s["objective"]) + 1e-9
+
+
+def test_construct_schedules_backfill_order():
+    x = np.array([[1, 0], [0, 0], [0, 1], [0, 0]])
+    g = np.array([2, 1, 2, 1])
+    R = np.array([5.0, 9.0, 1.0, 9.0])
+    s = om.construct_schedules(x, [10, 11, 12, 13], g, R, 7, 4)
+    assert s[7] == [10, 11, 13]      # back-fill by descending R, stable
+    assert s[8] == [12, 11, 13]
+
+
+def test_momentumed_average_matches_reference_formula():
+    series = [(3, 100.0), (5, 200.0), (9, 50.0)]
+    got = om.finish_time_momentumed_average(list(series), 11)
+    want = 0.9 * (2 / 8 * 100 + 4 / 8 * 200 + 2 / 8 * 50) + 0.1 * 50
+    assert abs(got - want) < 1e-12
+    assert om.finish_time_momentumed_average([(4, 77.0)], 4) == 0.9 * 77.0 + 0.1 * 77.0
