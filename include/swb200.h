@@ -146,6 +146,26 @@ int swb_forecast(swb_ctx *ctx, const swb_params *prm, const swb_round_args *a, d
                  double *rem, double *ftobj, double *bfkey, double *ft_estimate);
 int swb_forecast_commit(swb_ctx *ctx, int32_t J, int32_t fallback, const int32_t *ncal);
 
+/* ---- Gavel policies on a pooled (homogeneous) worker pool ------------------------------------- *
+ * Replaces the cvxpy -> ECOS/Gurobi solve inside Policy.get_allocation() (scheduler/policies/*.py) when
+ * every worker type that has capacity gives a job the same throughput (the non-Perf wrappers and
+ * Shockwave's homogeneous clusters).  x[j] is the pooled time fraction; the caller splits it over the
+ * worker types in proportion to their capacities.  Returns 0, or 1 when no feasible point was found.
+ *   SWB_POL_MAXMIN   max_min_fairness.py:53-113    coef_j = thr_j * sf_j / (priority_j * proportional_thr_j)
+ *   SWB_POL_FTF      finish_time_fairness.py:66-157 coef_j = thr_j, t = times_since_start,
+ *                    n = num_steps_remaining, den_j = cumulative_isolated_time_j + n_j/isolated_thr_j
+ *   SWB_POL_MTD      min_total_duration.py:55-135   coef_j = thr_j, n = num_steps_remaining
+ *   SWB_POL_MAXSUM   max_sum_throughput.py:49-108   coef_j = thr_j / instance_cost
+ *   SWB_POL_ISOLATED isolated.py:35-55, proportional.py:26-43, gandiva_fair_proportional.py:26-41
+ *                    coef_j = sf_j (Isolated) or 1 (Proportional / GandivaFair) */
+#define SWB_POL_MAXMIN 1
+#define SWB_POL_FTF 2
+#define SWB_POL_MTD 3
+#define SWB_POL_MAXSUM 4
+#define SWB_POL_ISOLATED 5
+int swb_policy_pooled(swb_ctx *ctx, int32_t mode, int32_t J, double N, const double *coef, const double *sf,
+                      const double *t, const double *n, const double *den, double *x, double *objective);
+
 /* Device time (CUDA events on the context's stream) of the two kernels of the latest solve pass and
  * the number of solve+place passes that call took (1 + packing-feedback re-solves). */
 int swb_last_timings(swb_ctx *ctx, double *ms_solve, double *ms_place, int32_t *passes);

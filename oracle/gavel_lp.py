@@ -1,0 +1,119 @@
+"""CPU ORACLE (test infrastructure, not product code) for the Gavel policies' get_allocation().
+
+Restates on scipy's HiGHS (`linprog`) the programs the reference hands to cvxpy -> ECOS / Gurobi:
+  base constraints      scheduler/policies/policy.py:58-65        x >= 0, sum_j sf_j x_jw <= N_w, sum_w x_jw <= 1
+  MaxMinFairness_Perf   scheduler/policies/max_min_fairness.py:53-113
+  FinishTimeFairness_Perf  scheduler/policies/finish_time_fairness.py:66-157  (min of a max of ratios; solved by
+                        bisection on rho over LP feasibility — the cvxpy model is the same quasi-convex program)
+  MinTotalDuration_Perf scheduler/policies/min_total_duration.py:55-135  (the reference's own bisection on T)
+  ThroughputNormalizedByCostSum_PerfSLOs   scheduler/policies/max_sum_throughput.py:49-108
+  Proportional / Isolated throughputs      proportional.py:26-43, isolated.py:35-55
+Pinning: the reference has no known-answer test for these -> "parity unpinned" at the
+x level; LP optima are degenerate so parity is on the objective and on constraints.
+General in the number of worker types W.
+"""
+import numpy as np
+from scipy.optimize import linprog
+
+
+def proportional_throughputs(thr, N):
+    m = thr.shape[0]
+    x = np.tile(np.asarray(N, dtype=float) / m, (m, 1))
+    x = x / x.sum(axis=1).max()
+    return (thr * x).sum(axis=1)
+
+
+def isolated_allocation(thr, sf, N):
+    m = thr.shape[0]
+    x = np.tile(np.asarray(N, dtype=float) / m, (m, 1)) / np.asarray(sf, dtype=float)[:, None]
+    rs = np.maximum(x.sum(axis=1), 1.0)
+    return x / rs[:, None]
+
+
+def _base(J, W, sf, N):
+    """A_ub, b_ub rows for the base constraints on x flattened row-major [J*W]."""
+    A = np.zeros((W + J, J * W))
+    for w in range(W):
+        A[w, w::W] = sf
+    for j in range(J):
+        A[W + j, j * W:(j + 1) * W] = 1.0
+    return A, np.concatenate([np.asarray(N, dtype=float), np.ones(J)])
+
+
+def max_min(coef, sf, N):
+    """max z  s.t.  sum_w coef_jw x_jw >= z  + base.  Returns (z, x[J,W])."""
+    J, W = coef.shape
+    A, b = _base(J, W, sf, N)
+    A = np.hstack([A, np.zeros((A.shape[0], 1))])
+    C = np.zeros((J, J * W + 1))
+    for j in range(J):
+        C[j, j * W:(j + 1) * W] = -coef[j]
+        C[j, -1] = 1.0
+    cost = np.zeros(J * W + 1); cost[-1] = -1.0
+    res = linprog(cost, A_ub=np.vstack([A, C]), b_ub=np.concatenate([b, np.zeros(J)]),
+                  bounds=[(0, None)] * (J * W) + [(None, None)], method="highs")
+    assert res.status == 0, res.message
+    return float(res.x[-1]), res.x[:-1].reshape(J, W)
+
+
+def max_min_fairness_perf(thr, sf, priority, N):
+    pw = (1.0 / np.asarray(priority, dtype=float)) / proportional_throughputs(thr, N)
+    coef = thr * pw[:, None] * np.asarray(sf, dtype=float)[:, None]
+    return max_min(coef, sf, N)
+
+
+def feasible_rates(thr, sf, N, need):
+    """LP feasibility of sum_w thr_jw x_jw >= need_j + base; returns x or None."""
+    J, W = thr.shape
+    A, b = _base(J, W, sf, N)
+    C = np.zeros((J, J * W))
+    for j in range(J):
+        C[j, j * W:(j + 1) * W] = -thr[j]
+    res = linprog(np.zeros(J * W), A_ub=np.vstack([A, C]), b_ub=np.concatenate([b, -np.asarray(need, float)]),
+                  bounds=[(0, None)] * (J * W), method="highs")
+    return res.x.reshape(J, W) if res.status == 0 else None
+
+
+def finish_time_fairness_perf(thr, sf, t, n, cum_iso, N, tol=1e-10):
+    iso = (thr * isolated_allocation(thr, sf, N)).sum(axis=1)
+    den = np.asarray(cum_iso, float) + np.asarray(n, float) / iso
+    lo, hi = 0.0, 1.0
+    def need(rho):
+        room = rho * den - t
+        return None if np.any(room <= 0) else n / room
+    while True:
+        nd = need(hi)
+        if nd is not None and feasible_rates(thr, sf, N, nd) is not None:
+            break
+        lo, hi = hi, hi * 2.0
+    while hi - lo > tol * hi:
+        mid = 0.5 * (lo + hi)
+        nd = need(mid)
+        if nd is not None and feasible_rates(thr, sf, N, nd) is not None:
+            hi = mid
+        else:
+            lo = mid
+    return hi, feasible_rates(thr, sf, N, need(hi)), den
+
+
+def min_total_duration_perf(thr, sf, n, N):
+    max_T, min_T, last_max_T, best, bx = 1000000.0, 100.0, 1000000.0, None, None
+    while bx is None:
+        while 1.05 * min_T < max_T:
+            T = (min_T + max_T) / 2.0
+            x = feasible_rates(thr, sf, N, np.asarray(n, float) / T)
+            if x is not None:
+                best, bx, max_T = T, x, T
+            else:
+                min_T = T
+        max_T, min_T, last_max_T = last_max_T * 10.0, last_max_T, last_max_T * 10.0
+    return best, bx
+
+
+def max_sum_throughput(thr, sf, N, costs=None):
+    J, W = thr.shape
+    c = np.ones(W) if costs is None else np.asarray(costs, float)
+    A, b = _base(J, W, sf, N)
+    res = linprog(-(thr / c[None, :]).reshape(-1), A_ub=A, b_ub=b, bounds=[(0, None)] * (J * W), method="highs")
+    assert res.status == 0
+    return -float(res.fun), res.x.reshape(J, W)

@@ -471,6 +471,37 @@ int swb_forecast(swb_ctx *c, const swb_params *prm, const swb_round_args *a, dou
   return 0;
 }
 
+int swb_policy_pooled(swb_ctx *c, int32_t mode, int32_t J, double N, const double *coef, const double *sf,
+                      const double *t, const double *n, const double *den, double *x, double *objective) {
+  if (!c || !coef || !sf || !x) return fail(SWB_ERR_ARG, "swb_policy_pooled: null argument");
+  if (J <= 0 || J > SWB_MAX_J) return fail(SWB_ERR_ARG, "swb_policy_pooled: J must be in [1, 8192]");
+  if (mode < SWB_POL_MAXMIN || mode > SWB_POL_ISOLATED) return fail(SWB_ERR_ARG, "swb_policy_pooled: bad mode");
+  if (mode == SWB_POL_FTF && (!t || !n || !den)) return fail(SWB_ERR_ARG, "swb_policy_pooled: FTF needs t, n, den");
+  if (mode == SWB_POL_MTD && !n) return fail(SWB_ERR_ARG, "swb_policy_pooled: MTD needs n");
+  CK(cudaSetDevice(c->device));
+  const size_t b = (size_t)J * 8;
+  CK(c->dbar.need(b, c->st)); CK(c->rem.need(b, c->st)); CK(c->ftobj.need(b, c->st));
+  CK(c->bfkey.need(b, c->st)); CK(c->f_remfb.need(b, c->st)); CK(c->f_bffb.need(b + 16, c->st));
+  CK(c->w.need(b, c->st));
+  CK(cudaMemcpyAsync(c->dbar.p, coef, b, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->rem.p, sf, b, cudaMemcpyHostToDevice, c->st));
+  if (t) CK(cudaMemcpyAsync(c->ftobj.p, t, b, cudaMemcpyHostToDevice, c->st));
+  if (n) CK(cudaMemcpyAsync(c->bfkey.p, n, b, cudaMemcpyHostToDevice, c->st));
+  if (den) CK(cudaMemcpyAsync(c->f_remfb.p, den, b, cudaMemcpyHostToDevice, c->st));
+  swb::PolicyLaunch L;
+  L.mode = mode; L.J = J; L.N = N;
+  L.coef = c->dbar.as<double>(); L.sf = c->rem.as<double>(); L.t = c->ftobj.as<double>();
+  L.n = c->bfkey.as<double>(); L.den = c->f_remfb.as<double>();
+  L.x = c->w.as<double>(); L.out = c->f_bffb.as<double>();
+  CK(swb::launch_policy(L, c->st));
+  double out[2] = {0.0, 0.0};
+  CK(cudaMemcpyAsync(x, c->w.p, b, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(out, c->f_bffb.p, 16, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  if (objective) *objective = out[0];
+  return out[1] != 0.0 ? 1 : 0;
+}
+
 int swb_last_timings(swb_ctx *c, double *ms_solve, double *ms_place, int32_t *passes) {
   if (!c) return fail(SWB_ERR_ARG, "null ctx");
   float a = 0.f, b = 0.f;

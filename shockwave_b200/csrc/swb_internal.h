@@ -85,4 +85,15 @@ cudaError_t launch_forecast(const ForecastLaunch &L, cudaStream_t st);
 cudaError_t launch_commit_calibration(const ForecastLaunch &L, const swb_result *res, int fallback_host,
                                       const int32_t *ncal, cudaStream_t st);
 
+struct PolicyLaunch {
+  int mode, J;
+  double N;                 // pooled worker count
+  const double *coef;       // MAXMIN: thr*sf*priority ; FTF/MTD: throughput ; MAXSUM: thr/cost ; ISOLATED: divisor
+  const double *sf;         // scale factors
+  const double *t, *n, *den;// FTF: times_since_start, steps remaining, isolated-time denominators ; MTD: n
+  double *x;                // [J] out
+  double *out;              // [2] out: objective, status
+};
+cudaError_t launch_policy(const PolicyLaunch &L, cudaStream_t st);
+
 }  // namespace swb

@@ -1,0 +1,334 @@
+"""Gavel policies behind the reference's own `get_allocation()` signatures, solved on the GPU.
+
+Mirrors scheduler/policies/{policy,max_min_fairness,finish_time_fairness,min_total_duration,
+max_sum_throughput,isolated,proportional,gandiva_fair_proportional}.py: same class names, same `.name`
+strings (scheduler.py:3291-3355 dispatches on their prefixes), same positional arguments, same
+`{job_id: {worker_type: fraction}}` return value and `None` for an empty job set (policy.py:31-32).
+
+The LP each policy hands to cvxpy is solved by swb_policy_pooled (policy.cu).  That kernel covers the
+case where all worker types WITH capacity give a job the same throughput — always true for the
+non-Perf classes (they overwrite the matrix with the v100 column, or with 1.0) and for the
+homogeneous clusters Shockwave targets.  A genuinely heterogeneous *_Perf call raises
+NotImplementedError (no CPU fallback).
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+
+import numpy as np
+
+from . import engine as _eng
+
+POL_MAXMIN, POL_FTF, POL_MTD, POL_MAXSUM, POL_ISOLATED = 1, 2, 3, 4, 5
+
+_shared_engine = None
+
+
+def _engine():
+    global _shared_engine
+    if _shared_engine is None:
+        _shared_engine = _eng.Engine(0)
+    return _shared_engine
+
+
+def _pooled(mode, N, coef, sf, t=None, n=None, den=None):
+    eng = _engine()
+    lib = eng.lib
+    if not getattr(lib, "_pol_bound", False):
+        lib.swb_policy_pooled.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 6 + \
+                                         [C.POINTER(C.c_double)]
+        lib.swb_policy_pooled.restype = C.c_int
+        lib._pol_bound = True
+    arr = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    coef, sf, t, n, den = arr(coef), arr(sf), arr(t), arr(n), arr(den)
+    J = len(coef)
+    x = np.zeros(J, dtype=np.float64)
+    obj = C.c_double()
+    p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+    rc = lib.swb_policy_pooled(eng.h, mode, J, float(N), p(coef), p(sf), p(t), p(n), p(den), p(x), C.byref(obj))
+    if rc < 0:
+        raise RuntimeError(f"swb_policy_pooled failed ({rc}): {lib.swb_last_error().decode()}")
+    return x, obj.value, rc
+
+
+class Policy:
+    """policy.py:11-65."""
+    def __init__(self, solver="ECOS"):
+        self._name = None
+        self._solver = solver       # kept for signature parity; no CPU solver is ever called
+
+    @property
+    def name(self):
+        return self._name
+
+    def flatten(self, d, cluster_spec):
+        job_ids = sorted(list(d.keys()))
+        if len(job_ids) == 0:
+            return None, None
+        worker_types = sorted(list(d[job_ids[0]].keys()))
+        self._num_workers = [cluster_spec[w] for w in worker_types]
+        if len(worker_types) == 0:
+            return None, None
+        m = np.array([[d[j][w] for w in worker_types] for j in job_ids], dtype=np.float64)
+        return m, (job_ids, worker_types)
+
+    def unflatten(self, m, index):
+        job_ids, worker_types = index
+        return {job_ids[i]: {worker_types[j]: m[i][j] for j in range(len(worker_types))}
+                for i in range(len(job_ids))}
+
+    # ---- pooling of the worker types (see module docstring) ----
+    def _pool(self, throughputs):
+        N = np.asarray(self._num_workers, dtype=np.float64)
+        live = N > 0
+        if not live.any():
+            raise ValueError("cluster has no workers")
+        cols = throughputs[:, live]
+        if not np.allclose(cols, cols[:, :1], rtol=1e-12, atol=0.0):
+            raise NotImplementedError(
+                "heterogeneous per-type throughputs: only pooled (homogeneous) clusters are solved on the GPU "
+                "in this release; there is no CPU fallback")
+        return cols[:, 0].copy(), float(N.sum()), N / N.sum()
+
+    @staticmethod
+    def _split(x, share):
+        return np.clip(x[:, None] * share[None, :], 0.0, 1.0)
+
+
+class ProportionalPolicy(Policy):
+    def __init__(self):
+        self._name = "Proportional"
+
+    def get_allocation(self, unflattened_throughputs, cluster_spec):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        m = throughputs.shape[0]
+        N = np.asarray(self._num_workers, dtype=np.float64)
+        # proportional.py:36-43: x_jw = N_w/m divided by the (common) row sum -> N_w / sum N; a constant
+        # matrix, there is nothing to solve
+        return super().unflatten(np.tile(N / N.sum(), (m, 1)) if N.sum() > 0 else np.zeros_like(throughputs), index)
+
+
+class IsolatedPolicy(Policy):
+    def __init__(self):
+        self._name = "Isolated"
+
+    def _alloc(self, throughputs, sf):
+        N = np.asarray(self._num_workers, dtype=np.float64)
+        x, _, _ = _pooled(POL_ISOLATED, N.sum(), sf, sf)     # min(1, (sum N / m) / sf_j)  (isolated.py:46-53)
+        share = N / N.sum() if N.sum() > 0 else N
+        return x[:, None] * share[None, :]
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, cluster_spec):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        sf = np.array([scale_factors[j] for j in index[0]], dtype=np.float64)
+        return super().unflatten(self._alloc(throughputs, sf), index)
+
+
+class GandivProportionalPolicy(Policy):
+    def __init__(self):
+        self._name = "GandivaFairProportional"
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, cluster_spec):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        m = throughputs.shape[0]
+        N = np.asarray(self._num_workers, dtype=np.float64)
+        x, _, _ = _pooled(POL_ISOLATED, N.sum(), np.ones(m), np.ones(m))   # gandiva_fair_proportional.py:26-41
+        share = N / N.sum() if N.sum() > 0 else N
+        return super().unflatten(x[:, None] * share[None, :], index)
+
+
+class MaxMinFairnessPolicyWithPerf(Policy):
+    def __init__(self, solver):
+        Policy.__init__(self, solver)
+        self._name = "MaxMinFairness_Perf"
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, unflattened_priority_weights, cluster_spec):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        job_ids, _ = index
+        thr, N, share = self._pool(throughputs)
+        sf = np.array([scale_factors[j] for j in job_ids], dtype=np.float64)
+        pw = np.array([1.0 / unflattened_priority_weights[j] for j in job_ids], dtype=np.float64)
+        # proportional throughput of a pooled job is its own throughput (proportional.py:36-43), so the
+        # objective coefficient thr*sf*pw/prop (max_min_fairness.py:78-101) collapses to sf*pw
+        coef = thr * sf * pw / thr
+        x, self.last_objective, _ = _pooled(POL_MAXMIN, N, coef, sf)
+        return super().unflatten(self._split(x, share), index)
+
+
+class MaxMinFairnessPolicy(Policy):
+    def __init__(self, solver):
+        self._name = "MaxMinFairness"
+        self._max_min_fairness_perf_policy = MaxMinFairnessPolicyWithPerf(solver)
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, priority_weights, cluster_spec):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        ones = {j: {w: 1.0 for w in unflattened_throughputs[j]} for j in unflattened_throughputs}
+        return self._max_min_fairness_perf_policy.get_allocation(ones, scale_factors, priority_weights, cluster_spec)
+
+
+class FinishTimeFairnessPolicyWithPerf(Policy):
+    def __init__(self, solver):
+        Policy.__init__(self, solver)
+        self._name = "FinishTimeFairness_Perf"
+        self._isolated_policy = IsolatedPolicy()
+        self._cumulative_isolated_time = {}
+        self._isolated_throughputs_prev_iteration = {}
+        self._num_steps_remaining_prev_iteration = {}
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, unflattened_priority_weights,
+                       times_since_start, num_steps_remaining, cluster_spec):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            self._isolated_throughputs_prev_iteration = {}
+            self._num_steps_remaining_prev_iteration = {}
+            return None
+        job_ids, _ = index
+        thr, N, share = self._pool(throughputs)
+        sf = np.array([scale_factors[j] for j in job_ids], dtype=np.float64)
+        self._isolated_policy._num_workers = self._num_workers
+        iso = (throughputs * self._isolated_policy._alloc(throughputs, sf)).sum(axis=1)
+        # stateful bookkeeping, finish_time_fairness.py:103-145
+        for i, j in enumerate(job_ids):
+            if j not in self._cumulative_isolated_time:
+                self._cumulative_isolated_time[j] = 0
+            if j in self._num_steps_remaining_prev_iteration:
+                self._cumulative_isolated_time[j] += (
+                    self._num_steps_remaining_prev_iteration[j] - num_steps_remaining[j]
+                ) / self._isolated_throughputs_prev_iteration[j]
+        n = np.array([num_steps_remaining[j] for j in job_ids], dtype=np.float64)
+        t = np.array([times_since_start[j] for j in job_ids], dtype=np.float64)
+        den = np.array([self._cumulative_isolated_time[j] for j in job_ids], dtype=np.float64) + n / iso
+        x, self.last_objective, rc = _pooled(POL_FTF, N, thr, sf, t=t, n=n, den=den)
+        self._num_steps_remaining_prev_iteration = copy.copy(num_steps_remaining)
+        self._isolated_throughputs_prev_iteration = {j: iso[i] for i, j in enumerate(job_ids)}
+        if rc != 0:     # "x.value is None" -> isolated allocation (finish_time_fairness.py:147-151)
+            return self._isolated_policy.get_allocation(unflattened_throughputs, scale_factors, cluster_spec)
+        return super().unflatten(self._split(x, share), index)
+
+
+class FinishTimeFairnessPolicy(Policy):
+    def __init__(self, solver):
+        self._name = "FinishTimeFairness"
+        self._finish_time_fairness_perf_policy = FinishTimeFairnessPolicyWithPerf(solver)
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, unflattened_priority_weights,
+                       times_since_start, num_steps_remaining, cluster_spec):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        v100 = {j: {w: unflattened_throughputs[j]["v100"] for w in unflattened_throughputs[j]}
+                for j in unflattened_throughputs}       # finish_time_fairness.py:38-46
+        return self._finish_time_fairness_perf_policy.get_allocation(
+            v100, scale_factors, unflattened_priority_weights, times_since_start, num_steps_remaining, cluster_spec)
+
+
+class MinTotalDurationPolicyWithPerf(Policy):
+    def __init__(self, solver):
+        Policy.__init__(self, solver)
+        self._name = "MinTotalDuration_Perf"
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, num_steps_remaining, cluster_spec):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if index is None:
+            return None
+        job_ids, _ = index
+        thr, N, share = self._pool(throughputs)
+        sf = np.array([scale_factors[j] for j in job_ids], dtype=np.float64)
+        n = np.array([num_steps_remaining[j] for j in job_ids], dtype=np.float64)
+        x, self.last_objective, rc = _pooled(POL_MTD, N, thr, sf, n=n)
+        assert rc == 0          # min_total_duration.py:132 `assert last_feasible_x is not None`
+        return super().unflatten(self._split(x, share), index)
+
+
+class MinTotalDurationPolicy(Policy):
+    def __init__(self, solver):
+        self._name = "MinTotalDuration"
+        self._min_total_duration_perf_policy = MinTotalDurationPolicyWithPerf(solver)
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, num_steps_remaining, cluster_spec):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        v100 = {j: {w: unflattened_throughputs[j]["v100"] for w in unflattened_throughputs[j]}
+                for j in unflattened_throughputs}
+        return self._min_total_duration_perf_policy.get_allocation(v100, scale_factors, num_steps_remaining,
+                                                                   cluster_spec)
+
+
+class ThroughputNormalizedByCostSumWithPerfSLOs(Policy):
+    def __init__(self, solver):
+        Policy.__init__(self, solver)
+        self._name = "ThroughputNormalizedByCostSum_PerfSLOs"
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, cluster_spec, instance_costs=None, SLOs={},
+                       num_steps_remaining={}):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        if SLOs:
+            raise NotImplementedError("SLO rows (max_sum_throughput.py:87-93) are not solved on the GPU yet")
+        job_ids, worker_types = index
+        thr, N, share = self._pool(throughputs)
+        sf = np.array([scale_factors[j] for j in job_ids], dtype=np.float64)
+        if instance_costs is not None:
+            c = np.array([instance_costs[w] for w in worker_types], dtype=np.float64)[np.asarray(self._num_workers) > 0]
+            if not np.allclose(c, c[0]):
+                raise NotImplementedError("per-type instance costs differ: heterogeneous LP not on the GPU yet")
+            thr = thr / c[0]
+        x, self.last_objective, _ = _pooled(POL_MAXSUM, N, thr, sf)
+        return super().unflatten(self._split(x, share), index)
+
+
+class ThroughputSumWithPerf(Policy):
+    def __init__(self, solver):
+        self._name = "ThroughputSumWithPerf"
+        self._policy = ThroughputNormalizedByCostSumWithPerfSLOs(solver)
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, cluster_spec):
+        return self._policy.get_allocation(unflattened_throughputs, scale_factors, cluster_spec)
+
+
+class ThroughputNormalizedByCostSumWithPerf(Policy):
+    def __init__(self, solver):
+        self._name = "ThroughputNormalizedByCostSum_Perf"
+        self._policy = ThroughputNormalizedByCostSumWithPerfSLOs(solver)
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, cluster_spec, instance_costs):
+        return self._policy.get_allocation(unflattened_throughputs, scale_factors, cluster_spec,
+                                           instance_costs=instance_costs)
+
+
+class ShockwavePolicy(Policy):
+    """Name holder, like scheduler/policies/shockwave.py:8-10."""
+    def __init__(self):
+        self._name = "shockwave"
+
+
+def get_policy(policy_name, solver=None, seed=None):
+    """The GPU-backed subset of utils.get_policy (scheduler/utils.py:603-685)."""
+    table = {
+        "finish_time_fairness": lambda: FinishTimeFairnessPolicy(solver="GUROBI"),
+        "finish_time_fairness_perf": lambda: FinishTimeFairnessPolicyWithPerf(solver=solver),
+        "gandiva_fair": GandivProportionalPolicy, "isolated": IsolatedPolicy,
+        "max_min_fairness": lambda: MaxMinFairnessPolicy(solver=solver),
+        "max_min_fairness_perf": lambda: MaxMinFairnessPolicyWithPerf(solver=solver),
+        "max_sum_throughput_perf": lambda: ThroughputSumWithPerf(solver=solver),
+        "max_sum_throughput_normalized_by_cost_perf": lambda: ThroughputNormalizedByCostSumWithPerf(solver=solver),
+        "min_total_duration": lambda: MinTotalDurationPolicy(solver=solver),
+        "min_total_duration_perf": lambda: MinTotalDurationPolicyWithPerf(solver=solver),
+        "shockwave": ShockwavePolicy,
+    }
+    if policy_name not in table:
+        raise ValueError("Unknown policy!")
+    return table[policy_name]()

@@ -1,0 +1,126 @@
+"""GPU parity of the Gavel policies' get_allocation() against the HiGHS LP oracle (oracle/gavel_lp.py).
+
+LP optima are degenerate in x: parity is on the objective (1e-6 relative), on the base
+constraints (policy.py:58-65, to 1e-9) and on the effective throughput of the bottleneck jobs."""
+import numpy as np
+import pytest
+
+from oracle import gavel_lp as gl
+from shockwave_b200 import policies as P
+
+pytestmark = pytest.mark.gpu
+WT = ["k80", "p100", "v100"]          # sorted worker-type order of Policy.flatten
+
+
+def _instance(J, spec, seed, equal_columns=True):
+    rng = np.random.default_rng(seed)
+    col = rng.uniform(0.5, 20.0, size=J)
+    thr = {j: {w: (col[j] if equal_columns else col[j] * rng.uniform(0.3, 1.0)) for w in WT} for j in range(J)}
+    sf = {j: int(rng.choice([1, 2, 4, 8], p=[0.6, 0.3, 0.09, 0.01])) for j in range(J)}
+    return thr, sf, dict(spec), rng
+
+
+def _mat(d, J):
+    return np.array([[d[j][w] for w in WT] for j in range(J)])
+
+
+def _check_base(x, sf, spec, J):
+    N = np.array([spec[w] for w in WT], dtype=float)
+    s = np.array([sf[j] for j in range(J)], dtype=float)
+    assert x.min() >= -1e-12 and x.max() <= 1 + 1e-12
+    assert np.all(x.sum(axis=1) <= 1 + 1e-9)
+    assert np.all((x * s[:, None]).sum(axis=0) <= N + 1e-9 * np.maximum(1, N))
+
+
+SPECS = [{"v100": 32, "p100": 0, "k80": 0}, {"v100": 16, "p100": 8, "k80": 8}, {"v100": 512, "p100": 0, "k80": 0}]
+
+
+@pytest.mark.parametrize("J,spec", [(24, SPECS[0]), (120, SPECS[0]), (96, SPECS[1]), (2048, SPECS[2])])
+def test_max_min_fairness(J, spec):
+    thr, sf, spec, rng = _instance(J, spec, seed=J)
+    prio = {j: float(rng.choice([1.0, 2.0, 5.0])) for j in range(J)}
+    pol = P.MaxMinFairnessPolicyWithPerf(solver="ECOS")
+    alloc = pol.get_allocation(thr, sf, prio, spec)
+    x = _mat(alloc, J)
+    _check_base(x, sf, spec, J)
+    N = [spec[w] for w in WT]
+    z, _ = gl.max_min_fairness_perf(_mat(thr, J), np.array([sf[j] for j in range(J)], float),
+                                    np.array([prio[j] for j in range(J)]), N)
+    assert abs(pol.last_objective - z) <= 1e-6 * abs(z)
+    # every job reaches the max-min level
+    pw = (1.0 / np.array([prio[j] for j in range(J)])) / gl.proportional_throughputs(_mat(thr, J), N)
+    eff = (_mat(thr, J) * x).sum(axis=1) * pw * np.array([sf[j] for j in range(J)], float)
+    assert eff.min() >= z * (1 - 1e-6)
+    # the non-Perf class ignores throughputs (max_min_fairness.py:33-37)
+    a2 = P.MaxMinFairnessPolicy(solver="ECOS").get_allocation(thr, sf, prio, spec)
+    _check_base(_mat(a2, J), sf, spec, J)
+
+
+@pytest.mark.parametrize("J,spec", [(24, SPECS[0]), (120, SPECS[0]), (96, SPECS[1]), (1024, SPECS[2])])
+def test_finish_time_fairness_stateful(J, spec):
+    thr, sf, spec, rng = _instance(J, spec, seed=100 + J)
+    prio = {j: 1.0 for j in range(J)}
+    pol = P.FinishTimeFairnessPolicyWithPerf(solver="GUROBI")
+    steps = {j: float(rng.uniform(1e4, 1e6)) for j in range(J)}
+    t = {j: float(rng.uniform(0, 5e3)) for j in range(J)}
+    cum = np.zeros(J)
+    N = [spec[w] for w in WT]
+    s = np.array([sf[j] for j in range(J)], float)
+    prev_steps, prev_iso = None, None
+    for it in range(3):        # three allocation rounds: cumulative isolated time evolves
+        alloc = pol.get_allocation(thr, sf, prio, t, steps, spec)
+        x = _mat(alloc, J)
+        _check_base(x, sf, spec, J)
+        if prev_steps is not None:
+            cum += (prev_steps - np.array([steps[j] for j in range(J)])) / prev_iso
+        rho, _, den = gl.finish_time_fairness_perf(_mat(thr, J), s, np.array([t[j] for j in range(J)]),
+                                                   np.array([steps[j] for j in range(J)]), cum, N)
+        assert abs(pol.last_objective - rho) <= 1e-6 * rho
+        eff = (_mat(thr, J) * x).sum(axis=1)
+        ratio = (np.array([t[j] for j in range(J)]) + np.array([steps[j] for j in range(J)]) / eff) / den
+        assert ratio.max() <= rho * (1 + 1e-6)
+        prev_steps = np.array([steps[j] for j in range(J)])
+        prev_iso = (_mat(thr, J) * gl.isolated_allocation(_mat(thr, J), s, N)).sum(axis=1)
+        for j in range(J):
+            steps[j] *= 0.8
+            t[j] += 360.0
+    assert P.FinishTimeFairnessPolicy(solver="GUROBI").get_allocation({}, {}, {}, {}, {}, spec) is None
+
+
+@pytest.mark.parametrize("J,spec", [(24, SPECS[0]), (120, SPECS[0]), (96, SPECS[1])])
+def test_min_total_duration_and_max_sum(J, spec):
+    thr, sf, spec, rng = _instance(J, spec, seed=200 + J)
+    steps = {j: float(rng.uniform(1e3, 1e6)) for j in range(J)}
+    N = [spec[w] for w in WT]
+    s = np.array([sf[j] for j in range(J)], float)
+    pol = P.MinTotalDurationPolicyWithPerf(solver="ECOS")
+    x = _mat(pol.get_allocation(thr, sf, steps, spec), J)
+    _check_base(x, sf, spec, J)
+    T, _ = gl.min_total_duration_perf(_mat(thr, J), s, np.array([steps[j] for j in range(J)]), N)
+    assert pol.last_objective == T                       # same bisection sequence as the reference
+    assert np.all((_mat(thr, J) * x).sum(axis=1) >= np.array([steps[j] for j in range(J)]) / T * (1 - 1e-9))
+    pol = P.ThroughputSumWithPerf(solver="ECOS")
+    x = _mat(pol.get_allocation(thr, sf, spec), J)
+    _check_base(x, sf, spec, J)
+    v, _ = gl.max_sum_throughput(_mat(thr, J), s, N)
+    assert abs((_mat(thr, J) * x).sum() - v) <= 1e-6 * v
+
+
+def test_closed_forms_and_edge_cases():
+    thr, sf, spec, rng = _instance(10, SPECS[1], seed=3)
+    N = np.array([spec[w] for w in WT], float)
+    s = np.array([sf[j] for j in range(10)], float)
+    iso = _mat(P.IsolatedPolicy().get_allocation(thr, sf, spec), 10)
+    assert np.allclose(iso, gl.isolated_allocation(_mat(thr, 10), s, N), rtol=1e-12)
+    prop = _mat(P.ProportionalPolicy().get_allocation(thr, spec), 10)
+    assert np.allclose(prop, np.tile(N / N.sum(), (10, 1)))
+    gf = _mat(P.GandivProportionalPolicy().get_allocation(thr, sf, spec), 10)
+    want = np.tile(N / 10, (10, 1)); want = want / np.maximum(want.sum(axis=1), 1.0)[:, None]
+    assert np.allclose(gf, want, rtol=1e-12)
+    assert P.MaxMinFairnessPolicy(solver=None).get_allocation({}, {}, {}, spec) is None
+    assert P.get_policy("max_min_fairness").name == "MaxMinFairness"
+    assert P.get_policy("finish_time_fairness").name.startswith("FinishTimeFairness")
+    assert P.get_policy("shockwave").name == "shockwave"
+    het, sf2, spec2, _ = _instance(6, SPECS[1], seed=4, equal_columns=False)
+    with pytest.raises(NotImplementedError):
+        P.MaxMinFairnessPolicyWithPerf(solver=None).get_allocation(het, sf2, {j: 1.0 for j in range(6)}, spec2)
