@@ -166,6 +166,17 @@ int swb_forecast_commit(swb_ctx *ctx, int32_t J, int32_t fallback, const int32_t
 int swb_policy_pooled(swb_ctx *ctx, int32_t mode, int32_t J, double N, const double *coef, const double *sf,
                       const double *t, const double *n, const double *den, double *x, double *objective);
 
+/* ---- Monte-Carlo (geometric Brownian motion) throughput forecast -------------------------------- *
+ * New capability, no reference counterpart (the reference's forecast is the deterministic
+ * JobMetaData.dirichlet_posterior_remaining_runtime, JobMetaData.py:315-370, which this reduces to when
+ * sigma = mu = 0).  For job j and LOCAL paths p in [0, P_local): global path id = path_offset + p,
+ *   R = R0_j * mean_{h=1..H_j} exp((mu_j - sigma_j^2/2) h + sigma_j W_h).
+ * out = [2][J] float64: sum_p R and sum_p R^2 (divide by the GLOBAL path count after the allreduce).
+ * out_on_device != 0: `out` is a device pointer (e.g. the tensor handed to ncclAllReduce). */
+int swb_gbm_forecast(swb_ctx *ctx, int32_t J, const double *R0, const int32_t *H, const double *mu,
+                     const double *sigma, int64_t P_local, int64_t path_offset, uint64_t seed, double *out,
+                     int32_t out_on_device);
+
 /* Device time (CUDA events on the context's stream) of the two kernels of the latest solve pass and
  * the number of solve+place passes that call took (1 + packing-feedback re-solves). */
 int swb_last_timings(swb_ctx *ctx, double *ms_solve, double *ms_place, int32_t *passes);

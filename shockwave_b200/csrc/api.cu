@@ -502,6 +502,32 @@ int swb_policy_pooled(swb_ctx *c, int32_t mode, int32_t J, double N, const doubl
   return out[1] != 0.0 ? 1 : 0;
 }
 
+int swb_gbm_forecast(swb_ctx *c, int32_t J, const double *R0, const int32_t *H, const double *mu,
+                     const double *sigma, int64_t P_local, int64_t path_offset, uint64_t seed, double *out,
+                     int32_t out_on_device) {
+  if (!c || !R0 || !H || !mu || !sigma || !out) return fail(SWB_ERR_ARG, "swb_gbm_forecast: null argument");
+  if (J <= 0 || P_local < 0) return fail(SWB_ERR_ARG, "swb_gbm_forecast: bad J / P_local");
+  CK(cudaSetDevice(c->device));
+  const size_t b = (size_t)J * 8;
+  CK(c->dbar.need(b, c->st)); CK(c->rem.need(b, c->st)); CK(c->ftobj.need(b, c->st)); CK(c->g.need((size_t)J * 4, c->st));
+  CK(c->bfkey.need(2 * b, c->st));
+  CK(cudaMemcpyAsync(c->dbar.p, R0, b, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->rem.p, mu, b, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->ftobj.p, sigma, b, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->g.p, H, (size_t)J * 4, cudaMemcpyHostToDevice, c->st));
+  swb::GbmLaunch L;
+  L.J = J; L.P_local = P_local; L.path_offset = path_offset; L.seed = seed;
+  L.R0 = c->dbar.as<double>(); L.mu = c->rem.as<double>(); L.sigma = c->ftobj.as<double>(); L.H = c->g.as<int32_t>();
+  L.out = out_on_device ? out : c->bfkey.as<double>();
+  CK(cudaEventRecord(c->ev[0], c->st));
+  CK(swb::launch_gbm(L, c->st));
+  CK(cudaEventRecord(c->ev[1], c->st));
+  CK(cudaEventRecord(c->ev[2], c->st));
+  if (!out_on_device) CK(cudaMemcpyAsync(out, c->bfkey.p, 2 * b, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
 int swb_last_timings(swb_ctx *c, double *ms_solve, double *ms_place, int32_t *passes) {
   if (!c) return fail(SWB_ERR_ARG, "null ctx");
   float a = 0.f, b = 0.f;

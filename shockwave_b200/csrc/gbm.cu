@@ -1,0 +1,84 @@
+// gbm.cu — Monte-Carlo throughput forecast: geometric-Brownian-motion sample paths of the per-epoch
+// duration of every active job.  NOT in the reference (the reference's only forecast is
+// the deterministic Dirichlet-posterior remaining runtime, JobMetaData.py:315-370) — this kernel is the
+// stochastic generalisation BASELINE.json's north_star asks for, and it reduces to that quantity
+// exactly when sigma = mu = 0:
+//     R_j^(p) = R0_j * (1/H_j) * sum_{h=1..H_j} exp((mu_j - sigma_j^2/2) h + sigma_j W_h^(p)),
+//     W_h = sum of h iid N(0,1)   (a running sum = the prefix scan along the path),
+// R0_j the deterministic forecast.  Per job the kernel returns sum_p R^(p) and sum_p (R^(p))^2 over the
+// LOCAL paths; paths shard across GPUs and ONE allreduce of the [2][J] float64 vector follows
+// (SURVEY.md §8e).  Every path's random stream is keyed by (seed, job, GLOBAL path id), so results do
+// not depend on how the paths are sharded (up to float64 summation order).
+// Bound: ALU/SFU (xorshift128+, Box-Muller, exp), not HBM: 40 bytes in and 16 bytes out per job.
+#include <math.h>
+
+#include "swb_common.cuh"
+#include "swb_internal.h"
+
+namespace swb {
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long &x) {
+  unsigned long long z = (x += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+struct XorShift128p {
+  unsigned long long s0, s1;
+  __device__ __forceinline__ unsigned long long next() {
+    unsigned long long x = s0;
+    const unsigned long long y = s1;
+    s0 = y;
+    x ^= x << 23;
+    s1 = x ^ y ^ (x >> 17) ^ (y >> 26);
+    return s1 + y;
+  }
+};
+
+__global__ void __launch_bounds__(256) gbm_kernel(GbmLaunch L) {
+  __shared__ double red[2 * 64];
+  const int j = blockIdx.x;
+  const int H = L.H[j];
+  const float mu = (float)L.mu[j], sg = (float)L.sigma[j];
+  const float drift = mu - 0.5f * sg * sg;
+  const float invH = H > 0 ? 1.0f / (float)H : 0.0f;
+  const double R0 = L.R0[j];
+  double s1 = 0.0, s2 = 0.0;
+  for (long long p = threadIdx.x; p < L.P_local; p += blockDim.x) {
+    const unsigned long long gp = (unsigned long long)(L.path_offset + p);
+    unsigned long long sm = L.seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(j + 1)) ^ (gp * 0x9E3779B97F4A7C15ull);
+    XorShift128p rng;
+    rng.s0 = splitmix64(sm);
+    rng.s1 = splitmix64(sm) | 1ull;
+    float W = 0.0f, acc = 0.0f;
+    for (int h = 1; h <= H; h += 2) {
+      // Box-Muller: two normals per pair of 24-bit uniforms
+      const unsigned long long r = rng.next();
+      const float u1 = ((float)((unsigned)(r >> 40)) + 1.0f) * (1.0f / 16777217.0f);  // (0,1)
+      const float u2 = (float)((unsigned)(r >> 8) & 0xffffffu) * (1.0f / 16777216.0f);
+      const float rad = sqrtf(-2.0f * __logf(u1));
+      float sn, cs;
+      __sincosf(6.283185307179586f * u2, &sn, &cs);
+      W += rad * cs;
+      acc += __expf(fmaf(drift, (float)h, sg * W));
+      if (h + 1 <= H) {
+        W += rad * sn;
+        acc += __expf(fmaf(drift, (float)(h + 1), sg * W));
+      }
+    }
+    const double R = H > 0 ? R0 * (double)(acc * invH) : R0;
+    s1 += R;
+    s2 += R * R;
+  }
+  BlockRed br(red);
+  br.sum2(s1, s2);
+  if (threadIdx.x == 0) { L.out[j] = s1; L.out[L.J + j] = s2; }
+}
+
+cudaError_t launch_gbm(const GbmLaunch &L, cudaStream_t st) {
+  gbm_kernel<<<L.J, 256, 0, st>>>(L);
+  return cudaGetLastError();
+}
+
+}  // namespace swb

@@ -96,4 +96,14 @@ struct PolicyLaunch {
 };
 cudaError_t launch_policy(const PolicyLaunch &L, cudaStream_t st);
 
+struct GbmLaunch {
+  int J;
+  long long P_local, path_offset;
+  unsigned long long seed;
+  const double *R0, *mu, *sigma;
+  const int32_t *H;
+  double *out;   // [2][J]: sum R, sum R^2 over the local paths
+};
+cudaError_t launch_gbm(const GbmLaunch &L, cudaStream_t st);
+
 }  // namespace swb

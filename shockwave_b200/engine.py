@@ -56,7 +56,7 @@ class RoundArgs(C.Structure):
 
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
            "swb_solve", "swb_job_add", "swb_job_remove", "swb_round_solve", "swb_forecast",
-           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled"]
+           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_gbm_forecast"]
 
 _lib = None
 
@@ -96,6 +96,8 @@ def load_library():
     lib.swb_forecast_commit.restype = C.c_int
     lib.swb_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     lib.swb_last_timings.restype = C.c_int
+    lib.swb_gbm_forecast.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4 + [C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_int32]
+    lib.swb_gbm_forecast.restype = C.c_int
     _lib = lib
     return lib
 
@@ -242,3 +244,18 @@ class Engine:
 
     def stream_ptr(self):
         return int(self.lib.swb_stream(self.h) or 0)
+
+    def gbm_forecast(self, R0, H, mu, sigma, P_local, path_offset=0, seed=0, out_device_ptr=None):
+        """Sums over the local sample paths: returns [2, J] (host) or writes them to `out_device_ptr`."""
+        R0 = np.ascontiguousarray(R0, dtype=np.float64); mu = np.ascontiguousarray(mu, dtype=np.float64)
+        sigma = np.ascontiguousarray(sigma, dtype=np.float64); H = np.ascontiguousarray(H, dtype=np.int32)
+        J = len(R0)
+        if out_device_ptr:
+            self._check(self.lib.swb_gbm_forecast(self.h, J, _ptr(R0), _ptr(H), _ptr(mu), _ptr(sigma), int(P_local),
+                                                  int(path_offset), int(seed), C.c_void_p(int(out_device_ptr)), 1),
+                        "swb_gbm_forecast")
+            return None
+        out = np.zeros((2, J), dtype=np.float64)
+        self._check(self.lib.swb_gbm_forecast(self.h, J, _ptr(R0), _ptr(H), _ptr(mu), _ptr(sigma), int(P_local),
+                                              int(path_offset), int(seed), _ptr(out), 0), "swb_gbm_forecast")
+        return out
