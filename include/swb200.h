@@ -177,6 +177,32 @@ int swb_gbm_forecast(swb_ctx *ctx, int32_t J, const double *R0, const int32_t *H
                      const double *sigma, int64_t P_local, int64_t path_offset, uint64_t seed, double *out,
                      int32_t out_on_device);
 
+/* ---- dense market iteration over X[S][J][W][T] ------------------------------------------------ *
+ * Projected-gradient / price-response iterations on the dense allocation tensor (fp32, t innermost) of
+ * the general volatile-Fisher-market relaxation: per-(job, type) progress rates, one capacity price per
+ * (type, round).  Objective pieces as in scheduler/shockwave.py:565-568; base constraints as in
+ * scheduler/policies/policy.py:58-65 applied per round.  `iters` iterations of (small dual pass + dense
+ * pass); the dense pass reads X once and writes X once.  obj = [S][3]: relaxed objective, makespan,
+ * worst relative capacity violation of the final X.  dense_ms (may be NULL) = device time of the last
+ * dense pass (CUDA events). */
+typedef struct swb_market_args {
+  int32_t S, J, W, T;
+  int32_t per_scenario_jobs;    /* job arrays are [S][J] (else shared [J]) */
+  int32_t on_device;            /* g,E,c,dbar,rem,rate,X are device pointers */
+  int32_t iters;
+  float eta, sigma;             /* primal step, price step */
+  double theta_scale;           /* multiplies the marginal utilities (gradient normalisation) */
+  const swb_params *prm;        /* [S] host: k, bases/logv, round_duration are used */
+  const int32_t *g;
+  const double *E, *c, *dbar, *rem;
+  const float *rate;            /* [J][W] epochs of progress per round on worker type w */
+  const double *Gw;             /* [W] host: workers per type */
+  float *X;                     /* [S][J][W][T] in/out */
+  double *obj;                  /* [S][3] host out, may be NULL */
+  float *dense_ms;              /* host out, may be NULL */
+} swb_market_args;
+int swb_market_pgd(swb_ctx *ctx, const swb_market_args *a);
+
 /* Device time (CUDA events on the context's stream) of the two kernels of the latest solve pass and
  * the number of solve+place passes that call took (1 + packing-feedback re-solves). */
 int swb_last_timings(swb_ctx *ctx, double *ms_solve, double *ms_place, int32_t *passes);

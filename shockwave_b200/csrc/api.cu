@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "swb_internal.h"
+#define MK_CHECK_Q(T) (((T) / 4) > 256)
 
 namespace swb {
 cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask);
@@ -66,6 +67,9 @@ struct swb_ctx {
   DBuf f_slots, f_prog, f_mend, f_mns, f_remfb, f_bffb, f_ampok, f_ampfb, f_ftest, f_ncal;
   swb::ForecastLaunch last_fc;   // descriptor of the latest forecast (for the calibration commit)
   bool have_fc = false;
+  DBuf m_theta, m_rowp, m_colload, m_colscale, m_price, m_obj, m_X, m_rate, m_E, m_c, m_Gw;
+  cudaEvent_t mev[2] = {nullptr, nullptr};
+  double last_market_ms = 0.0;
   // CUDA events around the two kernels of the latest solve pass (bench.py's roofline)
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   int last_passes = 0;
@@ -94,6 +98,7 @@ int swb_create(swb_ctx **out, int device) {
   c->device = device;
   CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
   for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->mev[i]));
   *out = c;
   return 0;
 }
@@ -106,7 +111,8 @@ void swb_destroy(swb_ctx *c) {
                  &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->scth, &c->sths, &c->sn0, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
                  &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc,
                  &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
-                 &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal};
+                 &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal, &c->m_theta, &c->m_rowp, &c->m_colload,
+                 &c->m_colscale, &c->m_price, &c->m_obj, &c->m_X, &c->m_rate, &c->m_E, &c->m_c, &c->m_Gw};
   for (DBuf *b : all) b->release();
   if (c->h_res) cudaFreeHost(c->h_res);
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -525,6 +531,83 @@ int swb_gbm_forecast(swb_ctx *c, int32_t J, const double *R0, const int32_t *H, 
   CK(cudaEventRecord(c->ev[2], c->st));
   if (!out_on_device) CK(cudaMemcpyAsync(out, c->bfkey.p, 2 * b, cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int swb_market_pgd(swb_ctx *c, const swb_market_args *a) {
+  if (!c || !a || !a->prm || !a->g || !a->E || !a->c || !a->dbar || !a->rem || !a->rate || !a->Gw || !a->X)
+    return fail(SWB_ERR_ARG, "swb_market_pgd: null argument");
+  const int S = a->S, J = a->J, W = a->W, T = a->T;
+  if (S <= 0 || J <= 0 || W <= 0 || W > SWB_MK_MAXW || T <= 0 || (T & 3) || T > 1024)
+    return fail(SWB_ERR_ARG, "swb_market_pgd: need W in [1,4], T a multiple of 4, T <= 1024");
+  if (MK_CHECK_Q(T)) return fail(SWB_ERR_ARG, "swb_market_pgd: T/4 must not exceed 256");
+  CK(cudaSetDevice(c->device));
+  const size_t nj = a->per_scenario_jobs ? (size_t)S * J : (size_t)J, sj = (size_t)S * J;
+  const size_t nx = sj * W * T, nwt = (size_t)S * W * T;
+  CK(c->prm.need(sizeof(swb_params) * S, c->st));
+  CK(cudaMemcpyAsync(c->prm.p, a->prm, sizeof(swb_params) * S, cudaMemcpyHostToDevice, c->st));
+  CK(c->m_theta.need(sj * 4, c->st)); CK(c->m_rowp.need(sj * 4, c->st));
+  CK(c->m_colload.need(nwt * 4, c->st)); CK(c->m_colscale.need(nwt * 4, c->st)); CK(c->m_price.need(nwt * 4, c->st));
+  CK(c->m_obj.need((size_t)S * 3 * 8, c->st)); CK(c->m_Gw.need((size_t)W * 8, c->st));
+  CK(cudaMemcpyAsync(c->m_Gw.p, a->Gw, (size_t)W * 8, cudaMemcpyHostToDevice, c->st));
+  swb::MarketLaunch L;
+  L.S = S; L.J = J; L.W = W; L.T = T; L.per_scn = a->per_scenario_jobs;
+  L.prm = c->prm.as<swb_params>(); L.Gw = c->m_Gw.as<double>();
+  if (a->on_device) {
+    L.g = a->g; L.E = a->E; L.c = a->c; L.dbar = a->dbar; L.rem = a->rem; L.rate = a->rate; L.X = a->X;
+  } else {
+    CK(c->g.need(nj * 4, c->st)); CK(c->m_E.need(nj * 8, c->st)); CK(c->m_c.need(nj * 8, c->st));
+    CK(c->dbar.need(nj * 8, c->st)); CK(c->rem.need(nj * 8, c->st)); CK(c->m_rate.need(nj * W * 4, c->st));
+    CK(c->m_X.need(nx * 4, c->st));
+    CK(cudaMemcpyAsync(c->g.p, a->g, nj * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->m_E.p, a->E, nj * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->m_c.p, a->c, nj * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->dbar.p, a->dbar, nj * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->rem.p, a->rem, nj * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->m_rate.p, a->rate, nj * W * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->m_X.p, a->X, nx * 4, cudaMemcpyHostToDevice, c->st));
+    L.g = c->g.as<int32_t>(); L.E = c->m_E.as<double>(); L.c = c->m_c.as<double>();
+    L.dbar = c->dbar.as<double>(); L.rem = c->rem.as<double>(); L.rate = c->m_rate.as<float>();
+    L.X = c->m_X.as<float>();
+  }
+  L.theta = c->m_theta.as<float>(); L.rowp = c->m_rowp.as<float>();
+  L.colload = c->m_colload.as<float>(); L.colscale = c->m_colscale.as<float>(); L.price = c->m_price.as<float>();
+  L.obj = c->m_obj.as<double>();
+  L.sigma = a->sigma; L.theta_scale = a->theta_scale;
+  // jobs per CTA: enough CTAs to fill the GPU a few times, but long sweeps so the column accumulators pay
+  int per = (J + 15) / 16;
+  const int sweep = 256 / (T / 4) > 0 ? 256 / (T / 4) : 1;
+  per = ((per + sweep - 1) / sweep) * sweep;
+  L.jobs_per_cta = per < sweep ? sweep : per;
+  // state: theta = 0, rowp = colload = 0, colscale = 1, prices = caller's or 0
+  CK(cudaMemsetAsync(L.theta, 0, sj * 4, c->st)); CK(cudaMemsetAsync(L.rowp, 0, sj * 4, c->st));
+  CK(cudaMemsetAsync(L.colload, 0, nwt * 4, c->st)); CK(cudaMemsetAsync(L.price, 0, nwt * 4, c->st));
+  {
+    std::vector<float> ones(nwt, 1.0f);
+    CK(cudaMemcpyAsync(L.colscale, ones.data(), nwt * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+  }
+  L.eta = 0.f;                                           // measurement pass: X unchanged, reductions filled
+  CK(swb::launch_market_iter(L, c->st, true));
+  float dense_ms = 0.f;
+  for (int it = 0; it < a->iters; ++it) {
+    CK(swb::launch_market_iter(L, c->st, false));
+    L.eta = a->eta;
+    if (it == a->iters - 1) CK(cudaEventRecord(c->mev[0], c->st));
+    CK(swb::launch_market_iter(L, c->st, true));
+    if (it == a->iters - 1) CK(cudaEventRecord(c->mev[1], c->st));
+  }
+  // make the final X feasible (apply the last capacity scaling without a gradient step), then score it
+  CK(swb::launch_market_iter(L, c->st, false));
+  L.eta = 0.f;
+  CK(swb::launch_market_iter(L, c->st, true));
+  CK(swb::launch_market_iter(L, c->st, false));
+  if (a->obj) CK(cudaMemcpyAsync(a->obj, L.obj, (size_t)S * 3 * 8, cudaMemcpyDeviceToHost, c->st));
+  if (!a->on_device) CK(cudaMemcpyAsync(a->X, L.X, nx * 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  if (a->iters > 0) { CK(cudaEventElapsedTime(&dense_ms, c->mev[0], c->mev[1])); }
+  c->last_market_ms = dense_ms;
+  if (a->dense_ms) *a->dense_ms = dense_ms;
   return 0;
 }
 

@@ -96,6 +96,23 @@ struct PolicyLaunch {
 };
 cudaError_t launch_policy(const PolicyLaunch &L, cudaStream_t st);
 
+#define SWB_MK_MAXW 4
+struct MarketLaunch {
+  int S, J, W, T, per_scn, jobs_per_cta;
+  const swb_params *prm;          // device [S]
+  const int32_t *g;               // [J] or [S][J]
+  const double *E, *c, *dbar, *rem;
+  const float *rate;              // [J][W] or [S][J][W]: epochs of progress per round on worker type w
+  const double *Gw;               // [W] capacities
+  float *X;                       // [S][J][W][T]
+  float *theta, *rowp;            // [S][J]
+  float *colload, *colscale, *price;  // [S][W][T]
+  double *obj;                    // [S][3]: objective, makespan, worst relative capacity violation
+  float eta, sigma;
+  double theta_scale;
+};
+cudaError_t launch_market_iter(const MarketLaunch &L, cudaStream_t st, bool dense);
+
 struct GbmLaunch {
   int J;
   long long P_local, path_offset;

@@ -56,7 +56,7 @@ class RoundArgs(C.Structure):
 
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
            "swb_solve", "swb_job_add", "swb_job_remove", "swb_round_solve", "swb_forecast",
-           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_gbm_forecast"]
+           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_gbm_forecast", "swb_market_pgd"]
 
 _lib = None
 
@@ -259,3 +259,53 @@ class Engine:
         self._check(self.lib.swb_gbm_forecast(self.h, J, _ptr(R0), _ptr(H), _ptr(mu), _ptr(sigma), int(P_local),
                                               int(path_offset), int(seed), _ptr(out), 0), "swb_gbm_forecast")
         return out
+
+
+class MarketArgs(C.Structure):
+    """swb_market_args (include/swb200.h)."""
+    _fields_ = [("S", C.c_int32), ("J", C.c_int32), ("W", C.c_int32), ("T", C.c_int32),
+                ("per_scenario_jobs", C.c_int32), ("on_device", C.c_int32), ("iters", C.c_int32),
+                ("eta", C.c_float), ("sigma", C.c_float), ("theta_scale", C.c_double),
+                ("prm", C.POINTER(Params)), ("g", C.c_void_p), ("E", C.c_void_p), ("c", C.c_void_p),
+                ("dbar", C.c_void_p), ("rem", C.c_void_p), ("rate", C.c_void_p), ("Gw", C.c_void_p),
+                ("X", C.c_void_p), ("obj", C.c_void_p), ("dense_ms", C.POINTER(C.c_float))]
+
+
+def market_pgd(eng, params, g, E, c, dbar, rem, rate, Gw, X, iters, eta, sigma, theta_scale=1.0,
+               device_ptrs=None):
+    """Dense projected-gradient iterations on X[S,J,W,T] (fp32).  Host arrays by default (X is updated in
+    place); `device_ptrs` = dict(g,E,c,dbar,rem,rate,X) of raw device pointers for resident data.
+    Returns (obj[S,3] = objective, makespan, capacity violation ; ms of the last dense pass)."""
+    lib = eng.lib
+    if not getattr(lib, "_mk_bound", False):
+        lib.swb_market_pgd.argtypes = [C.c_void_p, C.POINTER(MarketArgs)]
+        lib.swb_market_pgd.restype = C.c_int
+        lib._mk_bound = True
+    plist = params if isinstance(params, (list, tuple)) else [params]
+    S = len(plist)
+    a = MarketArgs()
+    Gw = np.ascontiguousarray(Gw, dtype=np.float64)
+    obj = np.zeros((S, 3), dtype=np.float64)
+    ms = C.c_float()
+    a.iters, a.eta, a.sigma, a.theta_scale = int(iters), float(eta), float(sigma), float(theta_scale)
+    a.prm = (Params * S)(*plist)
+    a.Gw, a.obj, a.dense_ms = _ptr(Gw), _ptr(obj), C.pointer(ms)
+    if device_ptrs is None:
+        g = np.ascontiguousarray(g, dtype=np.int32)
+        f64 = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+        E, c, dbar, rem = f64(E), f64(c), f64(dbar), f64(rem)
+        rate = np.ascontiguousarray(rate, dtype=np.float32)
+        assert X.dtype == np.float32 and X.flags.c_contiguous and X.ndim == 4
+        a.S, a.J, a.W, a.T = X.shape
+        a.per_scenario_jobs, a.on_device = (1 if g.ndim == 2 else 0), 0
+        a.g, a.E, a.c, a.dbar, a.rem, a.rate, a.X = _ptr(g), _ptr(E), _ptr(c), _ptr(dbar), _ptr(rem), _ptr(rate), _ptr(X)
+        keep = (g, E, c, dbar, rem, rate)
+    else:
+        a.S, a.J, a.W, a.T = device_ptrs["shape"]
+        a.per_scenario_jobs, a.on_device = int(device_ptrs.get("per_scenario_jobs", 0)), 1
+        vp = lambda k: C.c_void_p(int(device_ptrs[k]))
+        a.g, a.E, a.c, a.dbar, a.rem, a.rate, a.X = vp("g"), vp("E"), vp("c"), vp("dbar"), vp("rem"), vp("rate"), vp("X")
+    rc = lib.swb_market_pgd(eng.h, C.byref(a))
+    if rc < 0:
+        raise RuntimeError(f"swb_market_pgd failed ({rc}): {lib.swb_last_error().decode()}")
+    return obj, float(ms.value)

@@ -1,0 +1,74 @@
+"""Dense market iteration (market.cu): numerics against the plain numpy fp32 reference of the same
+operation, constraint invariants, and the cross-check against the exact collapsed solver."""
+import numpy as np
+import pytest
+
+from oracle import shockwave_milp as om
+from shockwave_b200 import make_params
+from shockwave_b200.engine import market_pgd
+from tests import fixtures as fx
+from tests.ref_market import RefMarket
+from tests.synth import synth_problem
+
+pytestmark = pytest.mark.gpu
+LOGV = om.pwl_log_values(fx.BASES, fx.ORIGIN)
+
+
+def _setup(J, G, T, W, seed, k):
+    D = 120.0
+    pb = synth_problem(J, G, T, D, seed=seed, tight=3.0)
+    rng = np.random.default_rng(seed)
+    base = D / pb["dbar"]                                   # epochs per round on the reference type
+    rate = np.stack([base * f for f in [1.0, 0.6, 0.35, 0.2][:W]], axis=1).astype(np.float32)
+    Gw = np.array([G, G // 2, G // 4, G // 4][:W], dtype=float)
+    prm = make_params(G, T, D, k, 12.0, 1.0, fx.BASES, fx.ORIGIN, round_ptr=pb["round_ptr"])
+    X0 = (rng.random((1, J, W, T)) * 0.2).astype(np.float32)
+    return pb, rate, Gw, prm, X0, D
+
+
+@pytest.mark.parametrize("J,G,T,W", [(64, 32, 20, 1), (300, 64, 32, 3), (1000, 128, 64, 2), (257, 64, 8, 4)])
+def test_matches_numpy_reference(engine, J, G, T, W):
+    pb, rate, Gw, prm, X0, D = _setup(J, G, T, W, seed=J, k=1e-3)
+    ts = float(J * T)
+    for iters in (1, 5):
+        X = X0.copy()
+        obj, _ = market_pgd(engine, prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, X, iters,
+                            eta=0.5, sigma=0.05, theta_scale=ts)
+        ref = RefMarket(pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, 1e-3, D, fx.BASES, LOGV, T)
+        Xr, objr = ref.run(X0[0], iters, 0.5, 0.05, ts)
+        assert np.allclose(X[0], Xr, rtol=2e-4, atol=2e-5), np.abs(X[0] - Xr).max()
+        assert abs(obj[0, 0] - objr[0]) <= 1e-4 * abs(objr[0]) + 1e-7
+        assert abs(obj[0, 1] - objr[1]) <= 1e-4 * abs(objr[1]) + 1e-3
+
+
+def test_constraints_hold_and_objective_improves(engine):
+    J, G, T, W = 512, 64, 32, 2
+    pb, rate, Gw, prm, X0, D = _setup(J, G, T, W, seed=9, k=1e-9)
+    X = np.zeros_like(X0)
+    o0, _ = market_pgd(engine, prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, X.copy(), 0, 0.5, 0.05)
+    o, _ = market_pgd(engine, prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, X, 400,
+                      eta=0.5, sigma=0.02, theta_scale=float(J * T))
+    assert X.min() >= 0.0 and X.max() <= 1.0
+    assert np.all(X[0].sum(axis=1) <= 1.0 + 1e-5)                       # sum_w x_jwt <= 1
+    load = (pb["g"][:, None, None] * X[0]).sum(axis=0)
+    assert np.all(load <= Gw[:, None] * (1 + 1e-4))                      # per (type, round) capacity
+    assert o[0, 2] <= 1e-4
+    assert o[0, 0] > o0[0, 0]                                            # welfare went up from the empty schedule
+
+
+def test_homogeneous_case_approaches_exact_relaxation(engine):
+    """W = 1, r_j = D/dbar_j: the dense iteration's fixed point is the relaxation that solve.cu solves
+    exactly; after a few hundred iterations the dense objective is within a few percent of that bound
+    and never above it."""
+    J, G, T = 256, 64, 32
+    pb, rate, Gw, prm, X0, D = _setup(J, G, T, 1, seed=21, k=1e-9)
+    X = np.zeros((1, J, 1, T), dtype=np.float32)
+    o, _ = market_pgd(engine, prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, X, 800,
+                      eta=0.5, sigma=0.02, theta_scale=float(J * T))
+    lp = om.dynamic_eisenberg_gale(pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], 1e30 * np.ones(J), G, T, D,
+                                   pb["round_ptr"], 1e-9, 12.0, 1.0, fx.BASES, LOGV, relax=True)
+    assert lp["status"] == om.STATUS_FTF_FEASIBLE
+    assert o[0, 0] <= lp["objective"] + 1e-4 * abs(lp["objective"])
+    gap = (lp["objective"] - o[0, 0]) / abs(lp["objective"])
+    print("dense PGD vs exact LP relaxation: gap", gap)
+    assert gap < 0.05
