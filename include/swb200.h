@@ -190,7 +190,8 @@ typedef struct swb_market_args {
   int32_t per_scenario_jobs;    /* job arrays are [S][J] (else shared [J]) */
   int32_t on_device;            /* g,E,c,dbar,rem,rate,X are device pointers */
   int32_t iters;
-  float eta, sigma;             /* primal step, price step */
+  float eta, sigma;             /* primal step (on the relative surplus), multiplicative price step */
+  float eta_decay;              /* step of iteration i is eta / (1 + i/eta_decay); 0 = constant */
   double theta_scale;           /* multiplies the marginal utilities (gradient normalisation) */
   const swb_params *prm;        /* [S] host: k, bases/logv, round_duration are used */
   const int32_t *g;

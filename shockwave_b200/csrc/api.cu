@@ -587,12 +587,15 @@ int swb_market_pgd(swb_ctx *c, const swb_market_args *a) {
     CK(cudaMemcpyAsync(L.colscale, ones.data(), nwt * 4, cudaMemcpyHostToDevice, c->st));
     CK(cudaStreamSynchronize(c->st));
   }
+  L.init_price = 0;
   L.eta = 0.f;                                           // measurement pass: X unchanged, reductions filled
   CK(swb::launch_market_iter(L, c->st, true));
   float dense_ms = 0.f;
+  L.init_price = 1;
   for (int it = 0; it < a->iters; ++it) {
     CK(swb::launch_market_iter(L, c->st, false));
-    L.eta = a->eta;
+    L.init_price = 0;
+    L.eta = a->eta_decay > 0.f ? a->eta / (1.0f + (float)it / a->eta_decay) : a->eta;
     if (it == a->iters - 1) CK(cudaEventRecord(c->mev[0], c->st));
     CK(swb::launch_market_iter(L, c->st, true));
     if (it == a->iters - 1) CK(cudaEventRecord(c->mev[1], c->st));

@@ -10,7 +10,8 @@
 //     s.t. sum_j g_j x_jwt <= G_w  (per worker type and round),  sum_w x_jwt <= 1,  0 <= x <= 1.
 // One iteration = market_dual_kernel (O(J + W T) per scenario: marginal utilities theta_j, capacity
 // scale factors and price update from the previous pass' reductions) + market_step_kernel (the dense
-// pass): x <- clip(x * colscale_wt + eta (theta_j r_jw - pi_wt g_j), 0, 1), per-(job, round) budget
+// pass): x <- clip(x * colscale_wt + eta (theta_j r_jw - pi_wt g_j)/(theta_j r_jw + pi_wt g_j), 0, 1)
+// (a proportional-response style, scale-free step), per-(job, round) budget
 // normalisation over worker types, and — fused in the same pass — the row reduction P_j (warp
 // shuffles) and the column reduction sum_j g_j x_jwt (registers -> shared memory -> one atomicAdd per
 // column and CTA).  The dense pass reads X once and writes X once: 8 bytes per element, HBM bound.
@@ -77,12 +78,17 @@ __global__ void __launch_bounds__(MK_THREADS) market_step_kernel(MarketLaunch L)
           const float r = L.rate[(L.per_scn ? sj : (size_t)j) * W + w];
           const float4 x = ld_stream(xrow + w * Q + q);
           const int c0 = w * T + 4 * q;
-          const float up = eta * theta * r;
+          // scale-free response: relative surplus (gain - cost)/(gain + cost) in [-1, 1] — marginal
+          // utilities span many orders of magnitude across jobs (PWL slope 61 vs 1.1, fallback priorities)
+          const float gain = theta * r;
           float4 y;
-          y.x = fminf(fmaxf(fmaf(x.x, cs[c0 + 0], up - eta * pi[c0 + 0] * gj), 0.f), 1.f);
-          y.y = fminf(fmaxf(fmaf(x.y, cs[c0 + 1], up - eta * pi[c0 + 1] * gj), 0.f), 1.f);
-          y.z = fminf(fmaxf(fmaf(x.z, cs[c0 + 2], up - eta * pi[c0 + 2] * gj), 0.f), 1.f);
-          y.w = fminf(fmaxf(fmaf(x.w, cs[c0 + 3], up - eta * pi[c0 + 3] * gj), 0.f), 1.f);
+          {
+            const float k0 = pi[c0 + 0] * gj, k1 = pi[c0 + 1] * gj, k2 = pi[c0 + 2] * gj, k3 = pi[c0 + 3] * gj;
+            y.x = fminf(fmaxf(fmaf(x.x, cs[c0 + 0], eta * __fdividef(gain - k0, gain + k0 + 1e-30f)), 0.f), 1.f);
+            y.y = fminf(fmaxf(fmaf(x.y, cs[c0 + 1], eta * __fdividef(gain - k1, gain + k1 + 1e-30f)), 0.f), 1.f);
+            y.z = fminf(fmaxf(fmaf(x.z, cs[c0 + 2], eta * __fdividef(gain - k2, gain + k2 + 1e-30f)), 0.f), 1.f);
+            y.w = fminf(fmaxf(fmaf(x.w, cs[c0 + 3], eta * __fdividef(gain - k3, gain + k3 + 1e-30f)), 0.f), 1.f);
+          }
           v[w] = y;
           tot.x += y.x; tot.y += y.y; tot.z += y.z; tot.w += y.w;
         }
@@ -182,6 +188,21 @@ __global__ void __launch_bounds__(1024) market_dual_kernel(MarketLaunch L) {
     L.theta[sj] = (float)(th * L.theta_scale);
     if (Q_ROW_ATOMICS(L.T)) L.rowp[sj] = 0.f;
   }
+  // first call: start every price at the mean marginal density of that worker type
+  __shared__ double s_init[SWB_MK_MAXW];
+  if (L.init_price) {
+    for (int w = 0; w < L.W; ++w) {
+      double num = 0.0, den = 0.0;
+      for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        const size_t sj = (size_t)s * J + j, ji = L.per_scn ? sj : j;
+        num += (double)L.theta[sj] * (double)L.rate[ji * L.W + w];
+        den += (double)L.g[ji];
+      }
+      br.sum2(num, den);
+      if (threadIdx.x == 0) s_init[w] = den > 0.0 ? num / den : 0.0;
+      __syncthreads();
+    }
+  }
   double viol = 0.0;
   for (int i = threadIdx.x; i < WT; i += blockDim.x) {
     const size_t si = (size_t)s * WT + i;
@@ -189,7 +210,8 @@ __global__ void __launch_bounds__(1024) market_dual_kernel(MarketLaunch L) {
     const float load = L.colload[si];
     viol = fmax(viol, (double)(load / cap - 1.f));
     L.colscale[si] = (load > cap && load > 0.f) ? cap / load : 1.f;
-    L.price[si] = fmaxf(0.f, L.price[si] + L.sigma * (load / cap - 1.f));
+    const float p0 = L.init_price ? (float)s_init[i / L.T] : L.price[si];
+    L.price[si] = fmaxf(1e-30f, p0 * __expf(L.sigma * (load / cap - 1.f)));   // tatonnement, multiplicative
     L.colload[si] = 0.f;
   }
   viol = br.max(viol);

@@ -110,6 +110,7 @@ struct MarketLaunch {
   double *obj;                    // [S][3]: objective, makespan, worst relative capacity violation
   float eta, sigma;
   double theta_scale;
+  int init_price;
 };
 cudaError_t launch_market_iter(const MarketLaunch &L, cudaStream_t st, bool dense);
 

@@ -265,14 +265,14 @@ class MarketArgs(C.Structure):
     """swb_market_args (include/swb200.h)."""
     _fields_ = [("S", C.c_int32), ("J", C.c_int32), ("W", C.c_int32), ("T", C.c_int32),
                 ("per_scenario_jobs", C.c_int32), ("on_device", C.c_int32), ("iters", C.c_int32),
-                ("eta", C.c_float), ("sigma", C.c_float), ("theta_scale", C.c_double),
+                ("eta", C.c_float), ("sigma", C.c_float), ("eta_decay", C.c_float), ("theta_scale", C.c_double),
                 ("prm", C.POINTER(Params)), ("g", C.c_void_p), ("E", C.c_void_p), ("c", C.c_void_p),
                 ("dbar", C.c_void_p), ("rem", C.c_void_p), ("rate", C.c_void_p), ("Gw", C.c_void_p),
                 ("X", C.c_void_p), ("obj", C.c_void_p), ("dense_ms", C.POINTER(C.c_float))]
 
 
 def market_pgd(eng, params, g, E, c, dbar, rem, rate, Gw, X, iters, eta, sigma, theta_scale=1.0,
-               device_ptrs=None):
+               device_ptrs=None, eta_decay=0.0):
     """Dense projected-gradient iterations on X[S,J,W,T] (fp32).  Host arrays by default (X is updated in
     place); `device_ptrs` = dict(g,E,c,dbar,rem,rate,X) of raw device pointers for resident data.
     Returns (obj[S,3] = objective, makespan, capacity violation ; ms of the last dense pass)."""
@@ -288,6 +288,7 @@ def market_pgd(eng, params, g, E, c, dbar, rem, rate, Gw, X, iters, eta, sigma, 
     obj = np.zeros((S, 3), dtype=np.float64)
     ms = C.c_float()
     a.iters, a.eta, a.sigma, a.theta_scale = int(iters), float(eta), float(sigma), float(theta_scale)
+    a.eta_decay = float(eta_decay)
     a.prm = (Params * S)(*plist)
     a.Gw, a.obj, a.dense_ms = _ptr(Gw), _ptr(obj), C.pointer(ms)
     if device_ptrs is None:

@@ -29,8 +29,9 @@ class RefMarket:
 
     def dense(self, X, eta):
         eta = np.float32(eta)
-        up = eta * self.theta[:, None, None] * self.rate[:, :, None]
-        Y = X * self.colscale[None] + (up - eta * self.price[None] * self.g[:, None, None])
+        gain = self.theta[:, None, None] * self.rate[:, :, None]
+        cost = self.price[None] * self.g[:, None, None]
+        Y = X * self.colscale[None] + eta * ((gain - cost) / (gain + cost + np.float32(1e-30)))
         Y = np.clip(Y, 0.0, 1.0).astype(np.float32)
         tot = Y.sum(axis=1, keepdims=True)
         Y = np.where(tot > 1.0, Y / np.maximum(tot, 1e-30), Y).astype(np.float32)
@@ -38,7 +39,7 @@ class RefMarket:
         self.colload = (self.g[:, None, None] * Y).sum(axis=0).astype(np.float32)
         return Y
 
-    def dual(self, sigma, theta_scale=1.0):
+    def dual(self, sigma, theta_scale=1.0, init_price=False):
         J = len(self.E)
         P = np.minimum(self.rowp.astype(float), self.E - self.c)
         u = (self.c + P) / self.E
@@ -57,14 +58,18 @@ class RefMarket:
         viol = float((self.colload / cap - 1.0).max())
         self.colscale = np.where((self.colload > cap) & (self.colload > 0), cap / np.maximum(self.colload, 1e-30),
                                  1.0).astype(np.float32)
-        self.price = np.maximum(0.0, self.price + np.float32(sigma) * (self.colload / cap - 1.0)).astype(np.float32)
+        if init_price:
+            dens = (self.theta.astype(float)[:, None] * self.rate.astype(float)).sum(axis=0) / self.g.astype(float).sum()
+            self.price = np.broadcast_to(dens[:, None], self.price.shape).astype(np.float32)
+        self.price = np.maximum(np.float32(1e-30), self.price * np.exp(np.float32(sigma) * (self.colload / cap - 1.0))
+                                ).astype(np.float32)
         return welfare - self.k * mx, mx, viol
 
-    def run(self, X, iters, eta, sigma, theta_scale=1.0):
+    def run(self, X, iters, eta, sigma, theta_scale=1.0, eta_decay=0.0):
         X = self.dense(X.astype(np.float32), 0.0)
-        for _ in range(iters):
-            self.dual(sigma, theta_scale)
-            X = self.dense(X, eta)
+        for it in range(iters):
+            self.dual(sigma, theta_scale, init_price=(it == 0))
+            X = self.dense(X, eta / (1.0 + it / eta_decay) if eta_decay > 0 else eta)
         self.dual(sigma, theta_scale)
         X = self.dense(X, 0.0)
         obj = self.dual(sigma, theta_scale)

@@ -33,9 +33,9 @@ def test_matches_numpy_reference(engine, J, G, T, W):
     for iters in (1, 5):
         X = X0.copy()
         obj, _ = market_pgd(engine, prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, X, iters,
-                            eta=0.5, sigma=0.05, theta_scale=ts)
+                            eta=0.2, sigma=0.1, theta_scale=ts, eta_decay=50.0)
         ref = RefMarket(pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, 1e-3, D, fx.BASES, LOGV, T)
-        Xr, objr = ref.run(X0[0], iters, 0.5, 0.05, ts)
+        Xr, objr = ref.run(X0[0], iters, 0.2, 0.1, ts, eta_decay=50.0)
         assert np.allclose(X[0], Xr, rtol=2e-4, atol=2e-5), np.abs(X[0] - Xr).max()
         assert abs(obj[0, 0] - objr[0]) <= 1e-4 * abs(objr[0]) + 1e-7
         assert abs(obj[0, 1] - objr[1]) <= 1e-4 * abs(objr[1]) + 1e-3
@@ -47,7 +47,7 @@ def test_constraints_hold_and_objective_improves(engine):
     X = np.zeros_like(X0)
     o0, _ = market_pgd(engine, prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, X.copy(), 0, 0.5, 0.05)
     o, _ = market_pgd(engine, prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, X, 400,
-                      eta=0.5, sigma=0.02, theta_scale=float(J * T))
+                      eta=0.1, sigma=0.3, theta_scale=float(J * T), eta_decay=50.0)
     assert X.min() >= 0.0 and X.max() <= 1.0
     assert np.all(X[0].sum(axis=1) <= 1.0 + 1e-5)                       # sum_w x_jwt <= 1
     load = (pb["g"][:, None, None] * X[0]).sum(axis=0)
@@ -59,16 +59,16 @@ def test_constraints_hold_and_objective_improves(engine):
 def test_homogeneous_case_approaches_exact_relaxation(engine):
     """W = 1, r_j = D/dbar_j: the dense iteration's fixed point is the relaxation that solve.cu solves
     exactly; after a few hundred iterations the dense objective is within a few percent of that bound
-    and never above it."""
+    and never above it (the numpy prototype reaches 0.6 % in 400 iterations)."""
     J, G, T = 256, 64, 32
     pb, rate, Gw, prm, X0, D = _setup(J, G, T, 1, seed=21, k=1e-9)
     X = np.zeros((1, J, 1, T), dtype=np.float32)
-    o, _ = market_pgd(engine, prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, X, 800,
-                      eta=0.5, sigma=0.02, theta_scale=float(J * T))
+    o, _ = market_pgd(engine, prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, X, 400,
+                      eta=0.1, sigma=0.3, theta_scale=float(J * T), eta_decay=50.0)
     lp = om.dynamic_eisenberg_gale(pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], 1e30 * np.ones(J), G, T, D,
                                    pb["round_ptr"], 1e-9, 12.0, 1.0, fx.BASES, LOGV, relax=True)
     assert lp["status"] == om.STATUS_FTF_FEASIBLE
     assert o[0, 0] <= lp["objective"] + 1e-4 * abs(lp["objective"])
     gap = (lp["objective"] - o[0, 0]) / abs(lp["objective"])
     print("dense PGD vs exact LP relaxation: gap", gap)
-    assert gap < 0.05
+    assert gap < 0.02
