@@ -213,6 +213,27 @@ def main():
     h2d = S * J * (3 * 4 + 4 * 8) + S * 256
     d2h = S * J * T * 2 + S * J * (4 + 8) + S * 56
 
+    # ---- dense PR-dynamics pass over X[S][J][W][T]: S*J*W*T*4 B = 512 MiB > L2 ----
+    from shockwave_b200.engine import market_pgd
+    Sd, Wd = 512, 1
+    Xd = torch.zeros((Sd, J, Wd, T), dtype=torch.float32, device=dev)
+    dj = {k: torch.from_numpy(np.ascontiguousarray(arrs[k][0]).astype(np.float64 if k != "g" else np.int32)).to(dev)
+          for k in ("g", "E", "c", "dbar", "rem")}
+    drate = torch.from_numpy((D / arrs["dbar"][0])[:, None].astype(np.float32)).to(dev)
+    mptr = dict(shape=(Sd, J, Wd, T), per_scenario_jobs=0, g=dj["g"].data_ptr(), E=dj["E"].data_ptr(),
+                c=dj["c"].data_ptr(), dbar=dj["dbar"].data_ptr(), rem=dj["rem"].data_ptr(), rate=drate.data_ptr(),
+                X=Xd.data_ptr())
+    mprm = [make_params(G, T, D, 1e-9, 12.0, 1.0, BASES, ORIGIN) for _ in range(Sd)]
+    dense_ms = []
+    for i in range(W + K):
+        _, ms = market_pgd(eng, mprm, None, None, None, None, None, None, [G], None, 8, 0.1, 0.3, float(J * T),
+                           device_ptrs=mptr, eta_decay=50.0)
+        if i >= W:
+            dense_ms.append(ms)
+    dense_ms = float(np.mean(dense_ms))
+    dense_bytes = 8.0 * Sd * J * Wd * T + Sd * (24.0 * J + 8.0 * Wd * T)
+    del Xd
+
     if rank != 0:
         return
     clocks = sampler.summary()
@@ -248,6 +269,13 @@ def main():
                              "barrier-latency bound, not HBM bound — the HBM fraction is reported for the contract; "
                              "peak = MEASURED_PEAKS.json hbm_gbs" + ("" if peaks else " (fallback 6650)")},
     }
+    line["roofline_dense"] = {
+        "bound": "hbm", "kernel": "market_step_kernel<1,4> (dense PR-dynamics pass over X[S][J][W][T], fp32)",
+        "achieved": dense_bytes / (dense_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": dense_bytes / (dense_ms * 1e-3) / 1e9 / peak, "traffic": None,
+        "shape": [Sd, J, Wd, T], "ms_per_pass": dense_ms,
+        "note": "algorithmic bytes = 8*S*J*W*T + S*(24*J + 8*W*T) (SURVEY.md §8d); the tensor (512 MiB) is larger "
+                "than L2; CUDA events around one dense pass inside a run of 8 iterations"}
     if world == 1 and not args.no_cpu_baseline:
         from oracle import shockwave_milp as om
         from tests.synth import synth_problem

@@ -39,13 +39,15 @@ __device__ __forceinline__ void st_stream(float4 *p, const float4 &v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Dense pass.  Grid (job tiles, S).  A thread owns one float4 of rounds (4 consecutive t) of one
-// worker type... for W > 1 it loops over the worker types of the same (job, 4 rounds) so the budget
-// normalisation over w is thread-local.  Q = T/4 threads cover a job; MK_THREADS/Q jobs per sweep.
+// Dense pass.  Grid (job tiles, S).  A thread owns one float4 of rounds (4 consecutive t) of a job and
+// loops over that job's worker types, so the budget normalisation over w is thread-local.  Q = T/4
+// threads cover a job; MK_THREADS/Q jobs per sweep; U sweeps are loaded before any is used so that
+// U*W 16-byte loads per thread are in flight (the pass is HBM bound: memory-level parallelism first).
+template <int W, int U>
 __global__ void __launch_bounds__(MK_THREADS) market_step_kernel(MarketLaunch L) {
-  extern __shared__ float sm[];           // [W*T] colscale | [W*T] price*? | [W*T] column accumulators
+  extern __shared__ float sm[];           // [W*T] colscale | [W*T] price | [W*T] column accumulators
   const int s = blockIdx.y;
-  const int W = L.W, T = L.T, J = L.J, WT = W * T;
+  const int T = L.T, J = L.J, WT = W * T;
   const int Q = T >> 2;                   // float4 groups per (job, type) row
   float *cs = sm, *pi = sm + WT, *acc = sm + 2 * WT;
   const float *cs_g = L.colscale + (size_t)s * WT, *pi_g = L.price + (size_t)s * WT;
@@ -57,76 +59,89 @@ __global__ void __launch_bounds__(MK_THREADS) market_step_kernel(MarketLaunch L)
   const int jobs_per_sweep = MK_THREADS / Q;
   const int j0 = blockIdx.x * L.jobs_per_cta;
   const int j1 = min(J, j0 + L.jobs_per_cta);
-  float colacc[SWB_MK_MAXW][4];
-#pragma unroll
-  for (int w = 0; w < SWB_MK_MAXW; ++w) { colacc[w][0] = colacc[w][1] = colacc[w][2] = colacc[w][3] = 0.f; }
   const bool active_lane = jl < jobs_per_sweep;
-  for (int jb = j0; jb < j1; jb += jobs_per_sweep) {
-    const int j = jb + jl;
-    const bool live = active_lane && j < j1;
-    float rowp = 0.f;
-    if (live) {
-      const size_t sj = (size_t)s * J + j;
-      const float theta = L.theta[sj];
-      const float gj = (float)L.g[L.per_scn ? sj : j];
-      float4 *xrow = reinterpret_cast<float4 *>(L.X + sj * WT);
-      float4 v[SWB_MK_MAXW];
-      float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+  float colacc[W][4];
+  float csr[W][4], pir[W][4];             // this thread's columns never change: keep them in registers
 #pragma unroll
-      for (int w = 0; w < SWB_MK_MAXW; ++w) {
-        if (w < W) {
-          const float r = L.rate[(L.per_scn ? sj : (size_t)j) * W + w];
-          const float4 x = ld_stream(xrow + w * Q + q);
-          const int c0 = w * T + 4 * q;
+  for (int w = 0; w < W; ++w)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      colacc[w][e] = 0.f;
+      csr[w][e] = active_lane ? cs[w * T + 4 * q + e] : 1.f;
+      pir[w][e] = active_lane ? pi[w * T + 4 * q + e] : 0.f;
+    }
+  for (int jb = j0; jb < j1; jb += U * jobs_per_sweep) {
+    float4 x[U][W];
+    float theta[U], gj[U], r[U][W];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = jb + u * jobs_per_sweep + jl;
+      live[u] = active_lane && j < j1;
+      if (live[u]) {
+        const size_t sj = (size_t)s * J + j;
+        const float4 *xrow = reinterpret_cast<const float4 *>(L.X + sj * WT);
+#pragma unroll
+        for (int w = 0; w < W; ++w) x[u][w] = ld_stream(xrow + w * Q + q);
+        theta[u] = L.theta[sj];
+        gj[u] = (float)L.g[L.per_scn ? sj : j];
+#pragma unroll
+        for (int w = 0; w < W; ++w) r[u][w] = L.rate[(L.per_scn ? sj : (size_t)j) * W + w];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = jb + u * jobs_per_sweep + jl;
+      float rowp = 0.f;
+      if (live[u]) {
+        const size_t sj = (size_t)s * J + j;
+        float4 *xrow = reinterpret_cast<float4 *>(L.X + sj * WT);
+        float4 v[W];
+        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
           // scale-free response: relative surplus (gain - cost)/(gain + cost) in [-1, 1] — marginal
           // utilities span many orders of magnitude across jobs (PWL slope 61 vs 1.1, fallback priorities)
-          const float gain = theta * r;
+          const float gain = theta[u] * r[u][w];
+          const float k0 = pir[w][0] * gj[u], k1 = pir[w][1] * gj[u], k2 = pir[w][2] * gj[u], k3 = pir[w][3] * gj[u];
           float4 y;
-          {
-            const float k0 = pi[c0 + 0] * gj, k1 = pi[c0 + 1] * gj, k2 = pi[c0 + 2] * gj, k3 = pi[c0 + 3] * gj;
-            y.x = fminf(fmaxf(fmaf(x.x, cs[c0 + 0], eta * __fdividef(gain - k0, gain + k0 + 1e-30f)), 0.f), 1.f);
-            y.y = fminf(fmaxf(fmaf(x.y, cs[c0 + 1], eta * __fdividef(gain - k1, gain + k1 + 1e-30f)), 0.f), 1.f);
-            y.z = fminf(fmaxf(fmaf(x.z, cs[c0 + 2], eta * __fdividef(gain - k2, gain + k2 + 1e-30f)), 0.f), 1.f);
-            y.w = fminf(fmaxf(fmaf(x.w, cs[c0 + 3], eta * __fdividef(gain - k3, gain + k3 + 1e-30f)), 0.f), 1.f);
-          }
+          y.x = fminf(fmaxf(fmaf(x[u][w].x, csr[w][0], eta * __fdividef(gain - k0, gain + k0 + 1e-30f)), 0.f), 1.f);
+          y.y = fminf(fmaxf(fmaf(x[u][w].y, csr[w][1], eta * __fdividef(gain - k1, gain + k1 + 1e-30f)), 0.f), 1.f);
+          y.z = fminf(fmaxf(fmaf(x[u][w].z, csr[w][2], eta * __fdividef(gain - k2, gain + k2 + 1e-30f)), 0.f), 1.f);
+          y.w = fminf(fmaxf(fmaf(x[u][w].w, csr[w][3], eta * __fdividef(gain - k3, gain + k3 + 1e-30f)), 0.f), 1.f);
           v[w] = y;
           tot.x += y.x; tot.y += y.y; tot.z += y.z; tot.w += y.w;
         }
-      }
-      // per-(job, round) budget normalisation: sum_w x_jwt <= 1   (policy.py:64 generalised per round)
-      const float nx = tot.x > 1.f ? 1.f / tot.x : 1.f, ny = tot.y > 1.f ? 1.f / tot.y : 1.f;
-      const float nz = tot.z > 1.f ? 1.f / tot.z : 1.f, nw = tot.w > 1.f ? 1.f / tot.w : 1.f;
+        // per-(job, round) budget normalisation: sum_w x_jwt <= 1   (policy.py:64 generalised per round)
+        const float nx = tot.x > 1.f ? 1.f / tot.x : 1.f, ny = tot.y > 1.f ? 1.f / tot.y : 1.f;
+        const float nz = tot.z > 1.f ? 1.f / tot.z : 1.f, nw = tot.w > 1.f ? 1.f / tot.w : 1.f;
 #pragma unroll
-      for (int w = 0; w < SWB_MK_MAXW; ++w) {
-        if (w < W) {
+        for (int w = 0; w < W; ++w) {
           float4 y = v[w];
-          y.x *= nx; y.y *= ny; y.z *= nz; y.w *= nw;
+          if (W > 1) { y.x *= nx; y.y *= ny; y.z *= nz; y.w *= nw; }
           st_stream(xrow + w * Q + q, y);
-          const float r = L.rate[(L.per_scn ? sj : (size_t)j) * W + w];
-          rowp = fmaf(r, (y.x + y.y) + (y.z + y.w), rowp);
-          colacc[w][0] = fmaf(gj, y.x, colacc[w][0]); colacc[w][1] = fmaf(gj, y.y, colacc[w][1]);
-          colacc[w][2] = fmaf(gj, y.z, colacc[w][2]); colacc[w][3] = fmaf(gj, y.w, colacc[w][3]);
+          rowp = fmaf(r[u][w], (y.x + y.y) + (y.z + y.w), rowp);
+          colacc[w][0] = fmaf(gj[u], y.x, colacc[w][0]); colacc[w][1] = fmaf(gj[u], y.y, colacc[w][1]);
+          colacc[w][2] = fmaf(gj[u], y.z, colacc[w][2]); colacc[w][3] = fmaf(gj[u], y.w, colacc[w][3]);
         }
       }
-    }
-    // row reduction over the Q threads of the job (Q is a power of two <= 32: shuffles inside the warp;
-    // for Q > 32 the partial sums go through global atomics)
-    if (!Q_ROW_ATOMICS(T)) {
-      for (int o = Q >> 1; o > 0; o >>= 1) rowp += __shfl_xor_sync(SWB_FULL, rowp, o);
-      if (live && q == 0) L.rowp[(size_t)s * J + j] = rowp;
-    } else if (live) {
-      atomicAdd(&L.rowp[(size_t)s * J + j], rowp);
+      // row reduction over the Q threads of the job: shuffles inside the warp when Q is a power of two
+      // <= 32, else the partial sums go through global atomics (rowp is zeroed by the dual pass)
+      if (!Q_ROW_ATOMICS(T)) {
+        for (int o = Q >> 1; o > 0; o >>= 1) rowp += __shfl_xor_sync(SWB_FULL, rowp, o);
+        if (live[u] && q == 0) L.rowp[(size_t)s * J + j] = rowp;
+      } else if (live[u]) {
+        atomicAdd(&L.rowp[(size_t)s * J + j], rowp);
+      }
     }
   }
   // column reduction: registers -> shared -> global
   if (active_lane) {
 #pragma unroll
-    for (int w = 0; w < SWB_MK_MAXW; ++w) {
-      if (w < W) {
-        const int c0 = w * T + 4 * q;
-        atomicAdd(&acc[c0 + 0], colacc[w][0]); atomicAdd(&acc[c0 + 1], colacc[w][1]);
-        atomicAdd(&acc[c0 + 2], colacc[w][2]); atomicAdd(&acc[c0 + 3], colacc[w][3]);
-      }
+    for (int w = 0; w < W; ++w) {
+      const int c0 = w * T + 4 * q;
+      atomicAdd(&acc[c0 + 0], colacc[w][0]); atomicAdd(&acc[c0 + 1], colacc[w][1]);
+      atomicAdd(&acc[c0 + 2], colacc[w][2]); atomicAdd(&acc[c0 + 3], colacc[w][3]);
     }
   }
   __syncthreads();
@@ -228,7 +243,12 @@ cudaError_t launch_market_iter(const MarketLaunch &L, cudaStream_t st, bool dens
   dim3 grid((L.J + L.jobs_per_cta - 1) / L.jobs_per_cta, L.S);
   const size_t smem = 3 * (size_t)L.W * L.T * sizeof(float);
   (void)Q;
-  market_step_kernel<<<grid, MK_THREADS, smem, st>>>(L);
+  switch (L.W) {
+    case 1: market_step_kernel<1, 4><<<grid, MK_THREADS, smem, st>>>(L); break;
+    case 2: market_step_kernel<2, 4><<<grid, MK_THREADS, smem, st>>>(L); break;
+    case 3: market_step_kernel<3, 2><<<grid, MK_THREADS, smem, st>>>(L); break;
+    default: market_step_kernel<4, 2><<<grid, MK_THREADS, smem, st>>>(L); break;
+  }
   return cudaGetLastError();
 }
 
