@@ -184,12 +184,49 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     unsigned int *A = binA, *B = binB;
     for (int p = lane; p < T; p += 32) A[p] = (unsigned)p;  // load 0, bin p
     __syncwarp();
+    int head = 0;   // the sorted bins are a RING: logical position p lives in A[(head + p) mod T]
     for (int pos = 0; pos < J; ++pos) {
       if (key64[pos] == 0ull) break;
       const int j = idx16[pos];
       const int g = gs[j], n = nplan[j];
-      // usable bins = prefix with load <= G - g
       const unsigned int lim = ((unsigned)(G - g) << 8) | 0xffu;
+      const unsigned int add = (unsigned)g << 8;
+      // Fast path (the common, load-balanced state): the n least-loaded bins all fit the job and, once
+      // raised by g, are at least as loaded as the currently most loaded bin -> moving them to the END
+      // of the order keeps it sorted by load; in a ring that is just `head += n`, no data moves.
+      // (Ties between equal loads are broken by age instead of bin id; any least-loaded choice is valid.)
+      int hn = head + n - 1; if (hn >= T) hn -= T;
+      int hl = head + T - 1; if (hl >= T) hl -= T;
+      const unsigned int vn = A[hn], vl = A[hl], v0 = A[head];
+      // every moved bin must end up at least as loaded as the most loaded unmoved one: test the SMALLEST
+      if (vn <= lim && (v0 >> 8) + (unsigned)g >= (vl >> 8)) {
+        unsigned int w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        for (int p = lane; p < n; p += 32) {
+          int ix = head + p; if (ix >= T) ix -= T;
+          const unsigned int v = A[ix];
+          A[ix] = v + add;
+          const unsigned int b = v & 0xffu;
+          const unsigned int bit = 1u << (b & 31);
+          if (b < 32) w0 |= bit; else if (b < 64) w1 |= bit; else if (b < 96) w2 |= bit; else w3 |= bit;
+        }
+        w0 = __reduce_or_sync(SWB_FULL, w0); w1 = __reduce_or_sync(SWB_FULL, w1);
+        w2 = __reduce_or_sync(SWB_FULL, w2); w3 = __reduce_or_sync(SWB_FULL, w3);
+        if (lane == 0) {
+          xm[2 * j] = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
+          xm[2 * j + 1] = (unsigned long long)w2 | ((unsigned long long)w3 << 32);
+          remn[j] = 0;
+        }
+        head += n; if (head >= T) head -= T;
+        __syncwarp();
+        continue;
+      }
+      // General path: linearise the ring, then take the usable prefix and re-merge.
+      if (head != 0) {
+        for (int p = lane; p < T; p += 32) { int ix = head + p; if (ix >= T) ix -= T; B[p] = A[ix]; }
+        unsigned int *tmp0 = A; A = B; B = tmp0;
+        head = 0;
+        __syncwarp();
+      }
       int u = 0;
       for (int p = lane; p < T; p += 32) u += (A[p] <= lim) ? 1 : 0;
       u = warp_sum(u);
@@ -206,23 +243,23 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
           m1 |= __shfl_xor_sync(SWB_FULL, m1, o);
         }
         if (lane == 0) { xm[2 * j] = m0; xm[2 * j + 1] = m1; remn[j] = (unsigned char)(n - m); }
-        const unsigned int add = (unsigned)g << 8;
         if (m == T) {
           for (int p = lane; p < T; p += 32) A[p] += add;
         } else {
-          // merge X = A[0..m)+add with Y = A[m..T); keys are unique (bin id in the low byte)
+          // stable merge BY LOAD of X = A[0..m)+add with Y = A[m..T): equal loads keep the unmoved bins
+          // first (both runs are sorted by load; the bin id in the low byte is not part of the order)
           for (int p = lane; p < T; p += 32) {
             int dst;
             if (p < m) {
-              const unsigned int v = A[p] + add;
-              int lo = m, hi = T;               // #{y in Y : y < v}
-              while (lo < hi) { const int mid = (lo + hi) >> 1; if (A[mid] < v) lo = mid + 1; else hi = mid; }
+              const unsigned int v = A[p] + add, lv = v >> 8;
+              int lo = m, hi = T;               // #{y in Y : load(y) <= load(v)}
+              while (lo < hi) { const int mid = (lo + hi) >> 1; if ((A[mid] >> 8) <= lv) lo = mid + 1; else hi = mid; }
               dst = p + (lo - m);
               B[dst] = v;
             } else {
-              const unsigned int v = A[p];
-              int lo = 0, hi = m;               // #{x in X : x < v}
-              while (lo < hi) { const int mid = (lo + hi) >> 1; if (A[mid] + add < v) lo = mid + 1; else hi = mid; }
+              const unsigned int v = A[p], lv = v >> 8;
+              int lo = 0, hi = m;               // #{x in X : load(x) < load(v)}
+              while (lo < hi) { const int mid = (lo + hi) >> 1; if (((A[mid] + add) >> 8) < lv) lo = mid + 1; else hi = mid; }
               dst = (p - m) + lo;
               B[dst] = v;
             }
