@@ -2,8 +2,9 @@
 """bench.py — schedule rounds/sec of the per-round market solve on B200 (BASELINE.json metric).
 
 Workload (config.workload): BASELINE.json config D — 4096 jobs x 512 GPUs x 64-round planning window.
-One "step" = one pass of the hot path (market solve + round placement + work-conserving back-fill)
-over a batch of S independent scenarios of that size (a hyper-parameter / trace-ensemble sweep: every
+One "step" = the Monte-Carlo (GBM) throughput forecast of the live job set (8192 paths/job, sharded over
+the ranks, one NCCL allreduce) followed by one pass of the market solve + round placement +
+work-conserving back-fill over a batch of S independent scenarios of that size (a hyper-parameter / trace-ensemble sweep: every
 scenario has its own synthetic job set and its own k).  A scenario is one CTA, so S = 2 x 148 fills
 the GPU twice.  `value` = scenarios solved per second with the inputs resident in HBM; `e2e` = the
 same through the public host API (Engine.solve, pinned host buffers, H2D + D2H inside the call);
@@ -113,6 +114,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenarios", type=int, default=296, help="scenarios per GPU per step (2 x 148 SMs)")
+    ap.add_argument("--mc-paths", type=int, default=8192, help="GBM sample paths per job (global, sharded over ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -147,9 +149,25 @@ def main():
     ptrs["bfkey"] = dten["rem"].data_ptr()
     optrs = {k: v.data_ptr() for k, v in outs.items()}
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    est = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+    # Engine calls are synchronous (they end with a stream synchronize), so events recorded on torch's
+    # current stream bracket everything a step launches: our kernels on the engine stream and NCCL.
+    est = torch.cuda.current_stream(dev)
+
+    # ---- Monte-Carlo (GBM) forecast of the live job set: P paths/job sharded over the ranks, ONE allreduce ----
+    from shockwave_b200.forecast_mc import path_range
+    P_MC = args.mc_paths
+    rng = np.random.default_rng(12345)
+    mc_R0 = arrs["rem"][0].copy()
+    mc_H = np.minimum(arrs["E"][0] - arrs["c"][0], 256).astype(np.int32)
+    mc_mu = rng.uniform(-1e-3, 1e-3, J)
+    mc_sg = rng.uniform(0.0, 0.05, J)
+    mc_lo, mc_n = path_range(P_MC, rank, world)
+    mc_out = torch.zeros((2, J), dtype=torch.float64, device=dev)
 
     def step_resident():
+        eng.gbm_forecast(mc_R0, mc_H, mc_mu, mc_sg, mc_n, mc_lo, 7, out_device_ptr=mc_out.data_ptr())
+        if world > 1:
+            dist.all_reduce(mc_out, op=dist.ReduceOp.SUM)      # NCCL over NVLink: 2*J float64 = 64 KiB
         return eng.solve_device(prms, J, ptrs, optrs)
 
     for _ in range(W):
@@ -170,7 +188,7 @@ def main():
         ev[i][1].record(est)
         tm = eng.last_timings()
         ksolve.append(tm["ms_solve"]); kplace.append(tm["ms_place"])
-        launches += 2 * tm["passes"] + (tm["passes"] - 1)
+        launches += 1 + 2 * tm["passes"] + (tm["passes"] - 1)       # gbm + (solve, place) per pass + tighten
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -204,14 +222,22 @@ def main():
         dist.barrier()
     t0 = time.perf_counter()
     for i in range(K):
+        sums = eng.gbm_forecast(mc_R0, mc_H, mc_mu, mc_sg, mc_n, mc_lo, 7)
+        if world > 1:
+            tsum = torch.from_numpy(sums).to(dev)
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            sums = tsum.cpu().numpy()
         o = eng.solve(prms, hnp["g"], hnp["E"], hnp["c"], hnp["dbar"], hnp["rem"], hnp["ftobj"])
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * S * K / float(te.item())
-    h2d = S * J * (3 * 4 + 4 * 8) + S * 256
-    d2h = S * J * T * 2 + S * J * (4 + 8) + S * 56
+    h2d = S * J * (3 * 4 + 4 * 8) + S * 256 + J * (3 * 8 + 4)
+    d2h = S * J * T * 2 + S * J * (4 + 8) + S * 56 + 2 * J * 8
+    # MC kernel alone (device time)
+    eng.gbm_forecast(mc_R0, mc_H, mc_mu, mc_sg, mc_n, mc_lo, 7, out_device_ptr=mc_out.data_ptr())
+    mc_ms = eng.last_timings()["ms_solve"]
 
     # ---- dense PR-dynamics pass over X[S][J][W][T]: S*J*W*T*4 B = 512 MiB > L2 ----
     from shockwave_b200.engine import market_pgd
@@ -257,6 +283,8 @@ def main():
         "config": {"workload": "BASELINE config D: 4096 jobs x 512 GPUs x 64-round window",
                    "scenarios_per_gpu_per_step": S, "k_sweep": K_SWEEP, "fallback_scenarios": nfallback,
                    "latency_ms_S1": lat_ms, "latency_kernels_ms_S1": lat_k,
+                   "mc_forecast": {"paths_per_job": P_MC, "paths_this_rank": mc_n, "horizon_epochs": "min(E-c, 256)",
+                                   "kernel_ms": mc_ms, "allreduce": "NCCL SUM of [2][J] float64 (64 KiB)" if world > 1 else "none (1 GPU)"},
                    "l2": "flushed between timed steps (256 MiB write); per-step CUDA events on the launching stream, summed",
                    "parallelism": f"scenario-sharded x{world}, no data-path collective"},
         "clocks": clocks,
