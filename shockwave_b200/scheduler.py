@@ -14,6 +14,7 @@ and the conversion of the returned J x T byte matrices into the reference's
 """
 from __future__ import annotations
 
+import random
 from collections import OrderedDict
 
 import numpy as np
@@ -144,6 +145,11 @@ class ShockwaveScheduler(object):
                     return self.schedules[self.round_ptr]
         jobids = list(self.metadata.keys())
         jobobjs = list(self.metadata.values())
+        # the reference re-seeds both global RNGs on every solver call (call_cvxpy_solver,
+        # shockwave.py:451-452); the simulator draws from them afterwards, so this side effect is part
+        # of the drop-in contract
+        random.seed(0)
+        np.random.seed(0)
         schedules = self._resolve(jobids, jobobjs)
         self.reestimate_share = False               # shockwave.py:120
         self.schedules = schedules
