@@ -8,7 +8,7 @@ installable here (no package, no licence, no network) so every number produced b
 `cpu_baseline` / `--impl reference` legs may import it.
 
 Pinning status: the reference holds NO known-answer test for the solver, so at
-the x-matrix level this oracle is "parity unpinned".  What pins it: (1) `oracle/pin_against_reference.py`
+the x-matrix level this oracle is "parity unpinned".  What pins it: (1) `tests/golden/make_solve_fixtures.py` (via oracle/ref_harness.py)
 runs the UNMODIFIED reference simulator (`scheduler/scheduler.py`) with this module substituted for
 the Gurobi call and compares the end-to-end metrics with the golden pickle the reference ships
 (`scheduler/reproduce/pickles/tacc_32gpus/shockwave_*.pickle`); (2) the forecast half is checked

@@ -133,7 +133,7 @@ static int check_params(const swb_params *p, int S, int J) {
     if (p[s].future_rounds <= 0 || p[s].future_rounds > SWB_MAX_T)
       return fail(SWB_ERR_ARG, "future_rounds must be in [1, 128]");
     if (p[s].ngpus <= 0) return fail(SWB_ERR_ARG, "ngpus must be positive");
-    if (p[s].nbases < 2 || p[s].nbases > SWB_MAX_BASES) return fail(SWB_ERR_ARG, "nbases must be in [2,16]");
+    if (p[s].nbases < 2 || p[s].nbases > 9) return fail(SWB_ERR_ARG, "nbases must be in [2,9]");
     if (!(p[s].round_duration > 0.0)) return fail(SWB_ERR_ARG, "round_duration must be positive");
     if (!(p[s].k > 0.0)) return fail(SWB_ERR_ARG, "k must be positive (shockwave.py:67)");
   }

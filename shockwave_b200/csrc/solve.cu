@@ -25,7 +25,7 @@
 namespace swb {
 
 struct Tab {             // response table: shared memory for J <= SWB_SMEM_JOBS, else global scratch
-  double *cth, *R;       // rho = mu * cth ; remaining runtime
+  double *cth, *R;       // rho = mu * cth ; remaining runtime IN ROUNDS (R_j / D)
   float *ths;            // [J][B] straddle-round threshold in rho units (-1: no such round)
   uint8_t *n0;           // [J][B] whole rounds inside the segments whose slope beats rho
   uint8_t *g, *nF, *nmax;
@@ -34,6 +34,8 @@ struct Tab {             // response table: shared memory for J <= SWB_SMEM_JOBS
 struct Ctx {
   const Pwl *P;
   Tab t;
+  float sl[8];           // PWL segment slopes as float registers (B <= 9), padded with -inf
+  const double *Rsec;    // remaining runtime in seconds (global scratch) for the exact makespan passes
   // exact per-job constants, global scratch (read ~20x per solve: welfare / makespan passes)
   double *a, *u0, *ws, *cap;
   uint8_t *n;
@@ -41,42 +43,34 @@ struct Ctx {
   double D, invD;
 };
 
-// best response of job j to the price mu: the largest n with F_j(n) - F_j(n-1) > mu g_j
+// best response of job j to the price mu: the largest n with F_j(n) - F_j(n-1) > mu g_j.
+// The normalised price is compared in fp32 (thresholds are O(1..60) slopes); every caller goes through
+// this one function, so the step function it defines is consistent (monotone in mu) everywhere.
 __device__ __forceinline__ int pref_n(const Ctx &c, int j, double mu) {
-  const int nmax = c.t.nmax[j];
-  if (mu <= 0.0) return nmax;
-  const double rho = mu * c.t.cth[j];
-  const Pwl &P = *c.P;
+  if (mu <= 0.0) return c.t.nmax[j];
+  const float rho = __double2float_rn(mu * c.t.cth[j]);
   int bs = 0;
-#pragma unroll 4
-  for (int b = 0; b < c.B - 1; ++b) bs += (P.slope[b] > rho) ? 1 : 0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) bs += (c.sl[b] > rho) ? 1 : 0;
   const int i = j * c.B + bs;
-  int n = c.t.n0[i];
-  n += (rho < (double)c.t.ths[i]) ? 1 : 0;
-  return n;
+  return (int)c.t.n0[i] + ((rho < c.t.ths[i]) ? 1 : 0);
 }
 
-// rounds job j must get so that rem_j <= M  (rem_j = max(0, R_j - min(D n, cap_j)))
-__device__ __forceinline__ int lower_n(const Ctx &c, int j, double M) {
-  const double need = c.t.R[j] - M;
+// rounds job j must get so that rem_j <= M  (rem_j = max(0, R_j - min(D n, cap_j))); Md = M / D
+__device__ __forceinline__ int lower_n(const Ctx &c, int j, double Md) {
+  const double need = c.t.R[j] - Md;
   int L = 0;
-  if (need > 0.0) {
-    const double q = ceil(need * c.invD - 1e-9);
-    const int nmax = c.t.nmax[j];
-    L = q >= (double)nmax ? nmax : (int)q;
-  }
-  const int nF = c.t.nF[j];
-  return L > nF ? L : nF;
+  if (need > 0.0) L = min((int)c.t.nmax[j], __double2int_ru(need - 1e-9));
+  return max(L, (int)c.t.nF[j]);
 }
 
-__device__ __forceinline__ int job_n(const Ctx &c, int j, double M, double mu) {
-  const int lb = lower_n(c, j, M), pf = pref_n(c, j, mu);
-  return lb > pf ? lb : pf;
+__device__ __forceinline__ int job_n(const Ctx &c, int j, double Md, double mu) {
+  return max(lower_n(c, j, Md), pref_n(c, j, mu));
 }
 
 __device__ __forceinline__ double rem_of(const Ctx &c, int j, int n) {
   const double done = fmin(c.D * (double)n, c.cap[j]);
-  return fmax(0.0, c.t.R[j] - done);
+  return fmax(0.0, c.Rsec[j] - done);
 }
 
 // weighted PWL-log utility of n rounds.  A job that completes inside the window gets plog(1) = 0
@@ -87,9 +81,10 @@ __device__ __forceinline__ double util_of(const Ctx &c, int j, int n) {
 }
 
 __device__ long long cost_at(const Ctx &c, BlockRed &br, double M, double mu) {
-  long long s = 0;
-  for (int j = threadIdx.x; j < c.J; j += blockDim.x) s += (long long)c.t.g[j] * job_n(c, j, M, mu);
-  return br.sumll(s);
+  const double Md = M * c.invD;
+  int s = 0;
+  for (int j = threadIdx.x; j < c.J; j += blockDim.x) s += (int)c.t.g[j] * job_n(c, j, Md, mu);
+  return br.sumll((long long)s);
 }
 
 struct Price { double hi, lo; long long cost_hi; int iters; };
@@ -103,13 +98,13 @@ __device__ Price solve_price(const Ctx &c, BlockRed &br, double M, double mu_max
   // Bisection on the BIT PATTERN of the (positive) price: the fallback priorities span 20+ orders of
   // magnitude (ratio^lam, shockwave.py:899-903), so an arithmetic midpoint would stop ~2^-44 * mu_max
   // above the real clearing price and lump every cheaper item into one "tie".  Positive doubles are
-  // ordered like their bit patterns; the loop ends when hi/lo - 1 < 2^-40 (everything priced inside
+  // ordered like their bit patterns; the loop ends when hi/lo - 1 < 2^-24 (everything priced inside
   // such an interval is treated as a tie and filled in job order).
   unsigned long long lob = 0ull, hib = (unsigned long long)__double_as_longlong(mu_max);
   double lo = 0.0, hi = mu_max;
   long long chi = cost_at(c, br, M, hi);
   p.iters++;
-  while (hib - lob > (1ull << 12)) {
+  while (hib - lob > (1ull << 28)) {   // 2^-24 relative: the fp32 resolution of the response function
     const unsigned long long midb = lob + ((hib - lob) >> 1);
     const double mid = __longlong_as_double((long long)midb);
     const long long cm = cost_at(c, br, M, mid);
@@ -127,8 +122,9 @@ __device__ Phi phi_at(const Ctx &c, BlockRed &br, double M, double mu_max, doubl
   Price p = solve_price(c, br, M, mu_max);
   iters += p.iters;
   double w = 0.0, me = 0.0;
+  const double Md = M * c.invD;
   for (int j = threadIdx.x; j < c.J; j += blockDim.x) {
-    const int n = job_n(c, j, M, p.hi);
+    const int n = job_n(c, j, Md, p.hi);
     w += util_of(c, j, n);
     me = fmax(me, rem_of(c, j, n));
   }
@@ -170,7 +166,11 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
   c.a = L.sc_a + so; c.u0 = L.sc_u0 + so; c.ws = L.sc_ws + so; c.cap = L.sc_cap + so;
   c.n = L.sc_n + so;
   c.P = P; c.J = J; c.T = T; c.GT = G * T; c.B = B; c.D = D; c.invD = 1.0 / D;
+  c.Rsec = L.sc_R + so;
   BlockRed br(red);
+#pragma unroll
+  for (int b = 0; b < 8; ++b)
+    c.sl[b] = (b + 1 < B) ? (float)((prm.logv[b + 1] - prm.logv[b]) / (prm.bases[b + 1] - prm.bases[b])) : -INFINITY;
 
   if (threadIdx.x == 0) {
     P->B = B;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
     if (gI[j] > G) nmax = 0;  // a gang wider than the cluster violates every capacity row (shockwave.py:317)
     if (L.ncap && (int)L.ncap[so + j] < nmax) nmax = L.ncap[so + j];  // packing feedback (tighten_kernel)
     c.a[j] = a; c.u0[j] = cf / Ef; c.cap[j] = cap;
-    c.t.R[j] = R; L.sc_R[so + j] = R;
+    c.t.R[j] = R * c.invD; L.sc_R[so + j] = R;
     c.t.g[j] = (uint8_t)gI[j]; c.t.nmax[j] = (uint8_t)nmax;
     const double capF = share * (prm.rhomax * ftI[j] - next_t);
     int nF = 0, bad = 0;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
       c.t.ths[j * B + bs] = th;
     }
     if (nmax > 0) mu_max = fmax(mu_max, (util_of(c, j, 1) - util_of(c, j, 0)) / (double)c.t.g[j]);
-    const double R = c.t.R[j];
+    const double R = c.Rsec[j];
     mfloor = fmax(mfloor, R - fmin(D * (double)nmax, cap));
     mtop = fmax(mtop, R);
   }
@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
   // ---- phase 4: integral allocation at the chosen threshold ----------------------------------
   Price pr = solve_price(c, br, best_thr, mu_max);
   iters += pr.iters;
-  for (int j = threadIdx.x; j < J; j += blockDim.x) c.n[j] = (uint8_t)job_n(c, j, best_thr, pr.hi);
+  const double thr_d = best_thr * c.invD;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) c.n[j] = (uint8_t)job_n(c, j, thr_d, pr.hi);
   long long left = (long long)c.GT - pr.cost_hi;
   __syncthreads();
 
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
     for (int base = 0; base < J; base += blockDim.x) {
       const int j = base + threadIdx.x;
       int extra = 0, gj = 1;
-      if (j < J) { gj = c.t.g[j]; extra = job_n(c, j, best_thr, pr.lo) - (int)c.n[j]; if (extra < 0) extra = 0; }
+      if (j < J) { gj = c.t.g[j]; extra = job_n(c, j, thr_d, pr.lo) - (int)c.n[j]; if (extra < 0) extra = 0; }
       long long v = (long long)gj * extra, incl = v;
       for (int o = 1; o < 32; o <<= 1) {
         long long t = __shfl_up_sync(SWB_FULL, incl, o);
