@@ -216,8 +216,12 @@ def main():
     # ---- e2e through the public host API, pinned host buffers, copies inside the timed region ----
     hin = {k: torch.from_numpy(v).pin_memory() for k, v in arrs.items()}
     hnp = {k: v.numpy() for k, v in hin.items()}
+    hout = {"xmask": torch.empty((S, J, 2), dtype=torch.uint64).pin_memory().numpy(),
+            "bfmask": torch.empty((S, J, 2), dtype=torch.uint64).pin_memory().numpy(),
+            "nrounds": torch.empty((S, J), dtype=torch.int32).pin_memory().numpy(),
+            "weights": torch.empty((S, J), dtype=torch.float64).pin_memory().numpy()}
     for _ in range(2):
-        eng.solve(prms, hnp["g"], hnp["E"], hnp["c"], hnp["dbar"], hnp["rem"], hnp["ftobj"])
+        eng.solve(prms, hnp["g"], hnp["E"], hnp["c"], hnp["dbar"], hnp["rem"], hnp["ftobj"], packed=True, out=hout)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -227,17 +231,51 @@ def main():
             tsum = torch.from_numpy(sums).to(dev)
             dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
             sums = tsum.cpu().numpy()
-        o = eng.solve(prms, hnp["g"], hnp["E"], hnp["c"], hnp["dbar"], hnp["rem"], hnp["ftobj"])
+        o = eng.solve(prms, hnp["g"], hnp["E"], hnp["c"], hnp["dbar"], hnp["rem"], hnp["ftobj"], packed=True, out=hout)
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * S * K / float(te.item())
     h2d = S * J * (3 * 4 + 4 * 8) + S * 256 + J * (3 * 8 + 4)
-    d2h = S * J * T * 2 + S * J * (4 + 8) + S * 56 + 2 * J * 8
+    d2h = S * J * 16 * 2 + S * J * (4 + 8) + S * 56 + 2 * J * 8      # round masks (128 bit/job) x2, counts, weights
     # MC kernel alone (device time)
     eng.gbm_forecast(mc_R0, mc_H, mc_mu, mc_sg, mc_n, mc_lo, 7, out_device_ptr=mc_out.data_ptr())
     mc_ms = eng.last_timings()["ms_solve"]
+
+    # ---- the drop-in class itself: ShockwaveScheduler.round_schedule() with a forced re-solve (S = 1) ----
+    from collections import OrderedDict
+    from shockwave_b200 import ShockwaveScheduler
+
+    class _Job:                      # what scheduler.py hands over (scheduler/JobMetaData.py:41-98), duck-typed
+        def __init__(self, jid, r):
+            E = int(arrs["E"][0][jid])
+            self.jobid, self.nworkers, self.epochs, self.epoch_nsamples = jid, int(arrs["g"][0][jid]), E, 50000
+            dur = max(1.0, round(float(arrs["dbar"][0][jid])))
+            self.epoch_duration_preprofiled = [dur] * E
+            self.bs_schedule = [32] * (E // 2) + [64] * (E - E // 2)
+            self.timestamp_submit, self.gavel_round_duration = 0.0, D
+            self.throughput_measurements = OrderedDict()
+            self.epoch_progress, self.waiting_delay = int(arrs["c"][0][jid]), 0
+        def set_epoch_progress(self, c): self.epoch_progress = c
+        def reset_waiting_delay(self): self.waiting_delay = 0
+        def add_waiting_delay(self, d): self.waiting_delay += d
+
+    sw = ShockwaveScheduler(ngpus=G, gram=16, init_metadata=OrderedDict(), future_nrounds=T, round_duration=int(D),
+                            solver_preference=["GUROBI"], solver_rel_gap=1e-3, solver_num_threads=24, solver_timeout=15,
+                            n_epoch_vars_max=64, logapx_bases=BASES, logapx_origin=ORIGIN, k=1e-3, lam=12.0, rhomax=1.0,
+                            device=local)
+    for jid in range(J):
+        sw.add_metadata(jid, _Job(jid, None))
+    rs_ms = []
+    for i in range(W + 5):
+        sw.round_ptr = 10 + i
+        sw.set_resolve()
+        t0 = time.perf_counter()
+        sw.round_schedule()
+        rs_ms.append((time.perf_counter() - t0) * 1e3)
+    rs_ms = float(np.median(rs_ms[W:]))
+    del sw
 
     # ---- dense PR-dynamics pass over X[S][J][W][T]: S*J*W*T*4 B = 512 MiB > L2 ----
     from shockwave_b200.engine import market_pgd
@@ -283,6 +321,7 @@ def main():
         "config": {"workload": "BASELINE config D: 4096 jobs x 512 GPUs x 64-round window",
                    "scenarios_per_gpu_per_step": S, "k_sweep": K_SWEEP, "fallback_scenarios": nfallback,
                    "latency_ms_S1": lat_ms, "latency_kernels_ms_S1": lat_k,
+                   "round_schedule_ms": rs_ms,   # ShockwaveScheduler.round_schedule(): host packing + forecast + solve + lists
                    "mc_forecast": {"paths_per_job": P_MC, "paths_this_rank": mc_n, "horizon_epochs": "min(E-c, 256)",
                                    "kernel_ms": mc_ms, "allreduce": "NCCL SUM of [2][J] float64 (64 KiB)" if world > 1 else "none (1 GPU)"},
                    "l2": "flushed between timed steps (256 MiB write); per-step CUDA events on the launching stream, summed",

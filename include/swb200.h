@@ -101,6 +101,9 @@ typedef struct swb_solve_args {
   int32_t *nrounds;             /* may be NULL */
   double *weights;              /* may be NULL */
   swb_result *res;              /* [S], always HOST */
+  /* optional packed outputs, [S][J][2] uint64 each: bit t of a job's 128-bit row = round t.  16 B per job
+   * instead of T bytes — use these and leave x/backfill NULL when the device->host copy matters. */
+  uint64_t *xmask, *bfmask;
 } swb_solve_args;
 int swb_solve(swb_ctx *ctx, const swb_solve_args *a);
 

@@ -54,7 +54,7 @@ struct swb_ctx {
   int device = 0;
   cudaStream_t st = nullptr;
   // ---- work buffers of a solve
-  DBuf prm, res, g, E, c, dbar, rem, ftobj, bfkey, x, bf, nr, w;
+  DBuf prm, res, g, E, c, dbar, rem, ftobj, bfkey, x, bf, nr, w, xmk, bmk;
   DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask, sncap, seated, scth, sths, sn0;
   // ---- resident job table (by slot)
   int nslots = 0;
@@ -107,7 +107,7 @@ void swb_destroy(swb_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   DBuf *all[] = {&c->prm, &c->res, &c->g, &c->E, &c->c, &c->dbar, &c->rem, &c->ftobj, &c->bfkey, &c->x,
-                 &c->bf, &c->nr, &c->w, &c->sa, &c->su0, &c->sR, &c->sws, &c->scap, &c->sg, &c->snF,
+                 &c->bf, &c->nr, &c->w, &c->xmk, &c->bmk, &c->sa, &c->su0, &c->sR, &c->sws, &c->scap, &c->sg, &c->snF,
                  &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->scth, &c->sths, &c->sn0, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
                  &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc,
                  &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
@@ -164,7 +164,8 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
                      const int32_t *E, const int32_t *cc, const double *dbar, const double *rem,
                      const double *ftobj, const double *bfkey, const double *rem_fb,
                      const double *bfkey_fb, uint8_t *x, uint8_t *bf, int32_t *nr, double *weights,
-                     int32_t *ncal = nullptr) {
+                     int32_t *ncal = nullptr, unsigned long long *xmask = nullptr,
+                     unsigned long long *bfmask = nullptr) {
   const size_t n = (size_t)S * J;
   int rc = ensure_scratch(c, n);
   if (rc) return rc;
@@ -194,6 +195,7 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   P.sc_a = L.sc_a; P.sc_u0 = L.sc_u0; P.sc_R = L.sc_R; P.sc_ws = L.sc_ws; P.sc_cap = L.sc_cap;
   P.sc_g = L.sc_g; P.sc_n = L.sc_n; P.weights = L.weights; P.E = E; P.c = cc; P.dbar = dbar;
   P.x = x; P.backfill = bf; P.nrounds = nr ? nr : c->seated.as<int32_t>(); P.ncal = ncal; P.res = L.res;
+  P.xmask = xmask; P.bfmask = bfmask;
   int rc2 = ensure_hres(c, S);
   if (rc2) return rc2;
   for (int pass = 0; pass < SWB_MAX_REPLAN + 1; ++pass) {
@@ -232,7 +234,9 @@ int swb_solve(swb_ctx *c, const swb_solve_args *a) {
   uint8_t *x, *bf;
   int32_t *nr;
   double *w;
+  unsigned long long *xmk = nullptr, *bmk = nullptr;
   if (a->on_device) {
+    xmk = (unsigned long long *)a->xmask; bmk = (unsigned long long *)a->bfmask;
     g = a->g; E = a->E; cc = a->c; dbar = a->dbar; rem = a->rem; ftobj = a->ftobj;
     bfkey = a->bfkey ? a->bfkey : a->rem;
     x = a->x; bf = a->backfill; nr = a->nrounds; w = a->weights;
@@ -254,9 +258,11 @@ int swb_solve(swb_ctx *c, const swb_solve_args *a) {
     if (a->x) { CK(c->x.need(nx, c->st)); x = c->x.as<uint8_t>(); }
     if (a->backfill) { CK(c->bf.need(nx, c->st)); bf = c->bf.as<uint8_t>(); }
     if (a->nrounds) { CK(c->nr.need((size_t)S * J * 4, c->st)); nr = c->nr.as<int32_t>(); }
+    if (a->xmask) { CK(c->xmk.need((size_t)S * J * 16, c->st)); xmk = c->xmk.as<unsigned long long>(); }
+    if (a->bfmask) { CK(c->bmk.need((size_t)S * J * 16, c->st)); bmk = c->bmk.as<unsigned long long>(); }
   }
   rc = run_solve(c, S, J, a->per_scenario_jobs, a->prm, g, E, cc, dbar, rem, ftobj, bfkey, nullptr,
-                 nullptr, x, bf, nr, w);
+                 nullptr, x, bf, nr, w, nullptr, xmk, bmk);
   if (rc) return rc;
   rc = ensure_hres(c, S);
   if (rc) return rc;
@@ -267,6 +273,8 @@ int swb_solve(swb_ctx *c, const swb_solve_args *a) {
     if (a->nrounds) CK(cudaMemcpyAsync(a->nrounds, nr, (size_t)S * J * 4, cudaMemcpyDeviceToHost, c->st));
     if (a->weights)
       CK(cudaMemcpyAsync(a->weights, c->w.p, (size_t)S * J * 8, cudaMemcpyDeviceToHost, c->st));
+    if (a->xmask) CK(cudaMemcpyAsync(a->xmask, xmk, (size_t)S * J * 16, cudaMemcpyDeviceToHost, c->st));
+    if (a->bfmask) CK(cudaMemcpyAsync(a->bfmask, bmk, (size_t)S * J * 16, cudaMemcpyDeviceToHost, c->st));
   }
   CK(cudaStreamSynchronize(c->st));
   memcpy(a->res, c->h_res, sizeof(swb_result) * S);

@@ -377,15 +377,39 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   }
   __syncthreads();
 
-  // ---- write the byte matrices, coalesced ------------------------------------------------------
+  // ---- outputs: 128-bit round masks (16 B per job and matrix) and/or byte matrices, coalesced ---------
+  if (L.xmask || L.bfmask) {
+    for (int e = threadIdx.x; e < 2 * J; e += blockDim.x) {
+      if (L.xmask) L.xmask[2 * so + e] = xm[e];
+      if (L.bfmask) L.bfmask[2 * so + e] = bm[e];
+    }
+  }
   const size_t xo = so * (size_t)T;
-  const int total = J * T;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int j = e / T, t = e - j * T;
-    const int wi = t >> 6;
-    const unsigned long long bit = 1ull << (t & 63);
-    if (L.x) L.x[xo + e] = (xm[2 * j + wi] & bit) ? 1 : 0;
-    if (L.backfill) L.backfill[xo + e] = (bm[2 * j + wi] & bit) ? 1 : 0;
+  if ((T & 3) == 0) {
+    const int total4 = J * (T >> 2), q4 = T >> 2;
+    unsigned int *x4 = reinterpret_cast<unsigned int *>(L.x ? L.x + xo : nullptr);
+    unsigned int *b4 = reinterpret_cast<unsigned int *>(L.backfill ? L.backfill + xo : nullptr);
+    for (int e = threadIdx.x; e < total4; e += blockDim.x) {
+      const int j = e / q4, t = (e - j * q4) << 2;
+      const int sh = t & 63, wi = t >> 6;
+      if (x4) {
+        const unsigned int m = (unsigned int)(xm[2 * j + wi] >> sh) & 0xfu;
+        x4[e] = (m & 1u) | ((m & 2u) << 7) | ((m & 4u) << 14) | ((m & 8u) << 21);
+      }
+      if (b4) {
+        const unsigned int m = (unsigned int)(bm[2 * j + wi] >> sh) & 0xfu;
+        b4[e] = (m & 1u) | ((m & 2u) << 7) | ((m & 4u) << 14) | ((m & 8u) << 21);
+      }
+    }
+  } else {
+    const int total = J * T;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int j = e / T, t = e - j * T;
+      const int wi = t >> 6;
+      const unsigned long long bit = 1ull << (t & 63);
+      if (L.x) L.x[xo + e] = (xm[2 * j + wi] & bit) ? 1 : 0;
+      if (L.backfill) L.backfill[xo + e] = (bm[2 * j + wi] & bit) ? 1 : 0;
+    }
   }
 }
 

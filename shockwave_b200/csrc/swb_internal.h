@@ -45,6 +45,7 @@ struct PlaceLaunch {
   const int32_t *E, *c;   // solver inputs again (objective re-evaluation with the checker's formula)
   const double *dbar;
   uint8_t *x, *backfill;  // [S][J][T] out, may be null
+  unsigned long long *xmask, *bfmask;  // [S][J][2] out, may be null: bit t of the 128-bit row = round t
   int32_t *nrounds;       // [S][J] out, may be null
   int32_t *ncal;          // [S][J] out, may be null: rounds with idle GPUs in which the job is unscheduled
   swb_result *res;        // device [S] (status in, objective/shortfall updated)

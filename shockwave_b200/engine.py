@@ -44,7 +44,7 @@ class SolveArgs(C.Structure):
                 ("g", C.c_void_p), ("E", C.c_void_p), ("c", C.c_void_p),
                 ("dbar", C.c_void_p), ("rem", C.c_void_p), ("ftobj", C.c_void_p), ("bfkey", C.c_void_p),
                 ("x", C.c_void_p), ("backfill", C.c_void_p), ("nrounds", C.c_void_p),
-                ("weights", C.c_void_p), ("res", C.POINTER(Result))]
+                ("weights", C.c_void_p), ("res", C.POINTER(Result)), ("xmask", C.c_void_p), ("bfmask", C.c_void_p)]
 
 
 class RoundArgs(C.Structure):
@@ -119,6 +119,12 @@ def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
+def unpack_masks(mask, T):
+    """[..., J, 2] uint64 round masks -> [..., J, T] uint8 (bit t of the 128-bit row = round t)."""
+    b = np.unpackbits(np.ascontiguousarray(mask).view(np.uint8), axis=-1, bitorder="little")
+    return b.reshape(mask.shape[:-1] + (128,))[..., :T]
+
+
 class Engine:
     """One swb_ctx (one CUDA stream on one B200)."""
 
@@ -147,7 +153,8 @@ class Engine:
         return rc
 
     # ---- plain-array market solve (swb_solve) -----------------------------------------------------
-    def solve(self, params, g, E, c, dbar, rem, ftobj, bfkey=None, want_x=True, want_backfill=True):
+    def solve(self, params, g, E, c, dbar, rem, ftobj, bfkey=None, want_x=True, want_backfill=True, packed=False,
+              out=None):
         """Solve S scenarios on host arrays.  `params`: one Params or a list of S; per-job arrays are
         [J] (shared) or [S, J].  Returns dict(x[S,J,T] u8, backfill, nrounds, weights, results[list])."""
         plist = params if isinstance(params, (list, tuple)) else [params]
@@ -164,14 +171,23 @@ class Engine:
         T = plist[0].future_rounds
         parr = (Params * S)(*plist)
         res = (Result * S)()
-        x = np.zeros((S, J, T), dtype=np.uint8) if want_x else None
-        bf = np.zeros((S, J, T), dtype=np.uint8) if want_backfill else None
-        nr = np.zeros((S, J), dtype=np.int32)
-        w = np.zeros((S, J), dtype=np.float64)
+        # packed=True: 128-bit round masks instead of the byte matrices (16 B/job instead of T B/job on the
+        # device->host copy); unpack with unpack_masks().  `out`: preallocated (e.g. pinned) output arrays.
+        out = out or {}
+        x = bf = xm = bm = None
+        if packed:
+            xm = out.get("xmask") if out.get("xmask") is not None else np.zeros((S, J, 2), dtype=np.uint64)
+            bm = out.get("bfmask") if out.get("bfmask") is not None else np.zeros((S, J, 2), dtype=np.uint64)
+        else:
+            x = np.zeros((S, J, T), dtype=np.uint8) if want_x else None
+            bf = np.zeros((S, J, T), dtype=np.uint8) if want_backfill else None
+        nr = out.get("nrounds") if out.get("nrounds") is not None else np.zeros((S, J), dtype=np.int32)
+        w = out.get("weights") if out.get("weights") is not None else np.zeros((S, J), dtype=np.float64)
         a = SolveArgs(S, J, per, 0, parr, _ptr(g), _ptr(E), _ptr(c), _ptr(dbar), _ptr(rem), _ptr(ftobj),
-                      _ptr(bfkey), _ptr(x), _ptr(bf), _ptr(nr), _ptr(w), res)
+                      _ptr(bfkey), _ptr(x), _ptr(bf), _ptr(nr), _ptr(w), res, _ptr(xm), _ptr(bm))
         self._check(self.lib.swb_solve(self.h, C.byref(a)), "swb_solve")
-        return dict(x=x, backfill=bf, nrounds=nr, weights=w, results=[r.as_dict() for r in res])
+        return dict(x=x, backfill=bf, xmask=xm, bfmask=bm, nrounds=nr, weights=w,
+                    results=[r.as_dict() for r in res])
 
     def solve_device(self, params, J, ptrs, out_ptrs, per_scenario_jobs=True):
         """Same on raw DEVICE pointers (ints): ptrs = dict(g,E,c,dbar,rem,ftobj,bfkey),
@@ -184,7 +200,7 @@ class Engine:
         a = SolveArgs(S, J, 1 if per_scenario_jobs else 0, 1, parr, vp(ptrs["g"]), vp(ptrs["E"]), vp(ptrs["c"]),
                       vp(ptrs["dbar"]), vp(ptrs["rem"]), vp(ptrs["ftobj"]), vp(ptrs.get("bfkey")),
                       vp(out_ptrs.get("x")), vp(out_ptrs.get("backfill")), vp(out_ptrs.get("nrounds")),
-                      vp(out_ptrs.get("weights")), res)
+                      vp(out_ptrs.get("weights")), res, vp(out_ptrs.get("xmask")), vp(out_ptrs.get("bfmask")))
         self._check(self.lib.swb_solve(self.h, C.byref(a)), "swb_solve")
         return [r.as_dict() for r in res]
 

@@ -116,6 +116,17 @@ def test_batched_scenarios_match_single(engine):
         assert one["results"][0]["objective"] == out["results"][s]["objective"]
 
 
+def test_packed_masks_equal_byte_matrices(engine):
+    from shockwave_b200.engine import unpack_masks
+    for (J, G, T) in [(50, 32, 20), (300, 64, 64), (128, 64, 7)]:
+        pb = synth_problem(J, G, T, 120.0, seed=J)
+        prm = make_params(G, T, 120.0, 1e-3, 12.0, 1.0, fx.BASES, fx.ORIGIN, round_ptr=pb["round_ptr"])
+        a = engine.solve(prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"])
+        b = engine.solve(prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"], packed=True)
+        assert np.array_equal(unpack_masks(b["xmask"], T), a["x"])
+        assert np.array_equal(unpack_masks(b["bfmask"], T), a["backfill"])
+
+
 def test_full_size_properties(engine):
     """BASELINE config D (4096 jobs x 512 GPUs x 64 rounds): size-independent properties."""
     J, G, T, D, k = 4096, 512, 64, 120.0, 1e-3
