@@ -74,6 +74,13 @@ int swb_version(void);
 void *swb_stream(swb_ctx *ctx);
 int swb_sync(swb_ctx *ctx);
 
+/* Options.  SWB_OPT_RELAXED_OPTIMUM: swb_solve / swb_round_solve additionally compute the EXACT optimum of
+ * the continuous relaxation (x in [0,1]) into swb_result.relaxed_objective (about 10x slower; used by the
+ * parity tests against the HiGHS LP relaxation).  Off: relaxed_objective holds the solver's own LP-style
+ * upper estimate. */
+#define SWB_OPT_RELAXED_OPTIMUM 1
+int swb_set_option(swb_ctx *ctx, int32_t option, int32_t value);
+
 /* ---- the market solve on plain arrays ------------------------------------------------------- *
  * Replaces dynamic_eisenberg_gale_scheduling() (scheduler/shockwave.py:504-711) — model build +
  * Gurobi solve + infeasible->relaxed->re-rank fallback — and the rounding half of

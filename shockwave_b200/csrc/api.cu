@@ -55,7 +55,8 @@ struct swb_ctx {
   cudaStream_t st = nullptr;
   // ---- work buffers of a solve
   DBuf prm, res, g, E, c, dbar, rem, ftobj, bfkey, x, bf, nr, w, xmk, bmk;
-  DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask, sncap, seated, scth, sths, sn0;
+  DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask, sncap, seated, scth, sths, sn0, snfc;
+  int want_relaxed = 0;
   // ---- resident job table (by slot)
   int nslots = 0;
   DBuf t_off, t_E, t_nm, t_g, t_ns, t_ts, t_modes, t_mm, t_amp, s_r0, s_rl, s_cnt, s_vl, s_acc;
@@ -108,7 +109,7 @@ void swb_destroy(swb_ctx *c) {
   cudaSetDevice(c->device);
   DBuf *all[] = {&c->prm, &c->res, &c->g, &c->E, &c->c, &c->dbar, &c->rem, &c->ftobj, &c->bfkey, &c->x,
                  &c->bf, &c->nr, &c->w, &c->xmk, &c->bmk, &c->sa, &c->su0, &c->sR, &c->sws, &c->scap, &c->sg, &c->snF,
-                 &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->scth, &c->sths, &c->sn0, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
+                 &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->scth, &c->sths, &c->sn0, &c->snfc, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
                  &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc,
                  &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
                  &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal, &c->m_theta, &c->m_rowp, &c->m_colload,
@@ -146,6 +147,7 @@ static int ensure_scratch(swb_ctx *c, size_t n) {
   CK(c->sg.need(n, c->st));       CK(c->snF.need(n, c->st));     CK(c->snmax.need(n, c->st));
   CK(c->sn.need(n, c->st));       CK(c->w.need(n * 8, c->st));
   CK(c->sncap.need(n, c->st));    CK(c->seated.need(n * 4, c->st));
+  CK(c->snfc.need(n * 8, c->st));
   return 0;
 }
 
@@ -189,6 +191,7 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   L.weights = weights ? weights : c->w.as<double>();
   L.res = c->res.as<swb_result>();
   L.ncap = c->sncap.as<uint8_t>();
+  L.sc_nfc = c->snfc.as<double>(); L.want_relaxed = c->want_relaxed;
   CK(cudaMemsetAsync(c->sncap.p, 0xff, n, c->st));
   swb::PlaceLaunch P;
   P.S = S; P.J = J; P.per_scn = per_scn; P.prm = L.prm; P.bfkey = bfkey; P.bfkey_fb = bfkey_fb;
@@ -620,6 +623,12 @@ int swb_market_pgd(swb_ctx *c, const swb_market_args *a) {
   c->last_market_ms = dense_ms;
   if (a->dense_ms) *a->dense_ms = dense_ms;
   return 0;
+}
+
+int swb_set_option(swb_ctx *c, int32_t option, int32_t value) {
+  if (!c) return fail(SWB_ERR_ARG, "null ctx");
+  if (option == SWB_OPT_RELAXED_OPTIMUM) { c->want_relaxed = value ? 1 : 0; return 0; }
+  return fail(SWB_ERR_ARG, "swb_set_option: unknown option");
 }
 
 int swb_last_timings(swb_ctx *c, double *ms_solve, double *ms_place, int32_t *passes) {

@@ -136,6 +136,101 @@ __device__ Phi phi_at(const Ctx &c, BlockRed &br, double M, double mu_max, doubl
   return r;
 }
 
+// ---- exact optimum of the CONTINUOUS relaxation (x in [0,1], hence n_j real): parity item P4 ----------
+// Same Lagrangian structure with real-valued responses: a job's best n is a breakpoint of its PWL utility,
+// ties at the clearing price absorb the left-over capacity fractionally (their utility is linear there),
+// and the value is concave in the makespan threshold, so a golden-section search is exact.
+struct RelaxCtx { const double *nfc; double Tr; };
+
+__device__ __forceinline__ double nmax_real(const Ctx &c, const RelaxCtx &r, int j) {
+  return c.t.nmax[j] == 0 ? 0.0 : fmin(r.Tr, fmin(c.cap[j] * c.invD, (double)c.t.nmax[j]));
+}
+
+__device__ __forceinline__ double job_nc(const Ctx &c, const RelaxCtx &r, int j, double Md, double mu) {
+  const double nm = nmax_real(c, r, j);
+  double lb = fmax(r.nfc[j], fmax(0.0, c.t.R[j] - Md));
+  lb = fmin(lb, nm);
+  double pf = nm;
+  if (mu > 0.0) {
+    const float rho = __double2float_rn(mu * c.t.cth[j]);
+    int bs = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) bs += (c.sl[b] > rho) ? 1 : 0;
+    pf = bs == 0 ? 0.0 : fmin(nm, fmax(0.0, (c.P->base[bs] - c.u0[j]) / c.a[j]));
+  }
+  return fmax(lb, pf);
+}
+
+__device__ __forceinline__ double util_c(const Ctx &c, int j, double n) {
+  const double u = (c.D * n >= c.cap[j]) ? 1.0 : fma(c.a[j], n, c.u0[j]);
+  return c.ws[j] * plog(*c.P, u);
+}
+
+__device__ double cost_c(const Ctx &c, const RelaxCtx &r, BlockRed &br, double Md, double mu) {
+  double s = 0.0;
+  for (int j = threadIdx.x; j < c.J; j += blockDim.x) s += (double)c.t.g[j] * job_nc(c, r, j, Md, mu);
+  return br.sum(s);
+}
+
+__device__ double phi_c(const Ctx &c, const RelaxCtx &r, BlockRed &br, double M, double mu_max, double k) {
+  const double Md = M * c.invD, cap = (double)c.GT;
+  double mu = 0.0, c_hi = cost_c(c, r, br, Md, 0.0), c_lo = c_hi;
+  if (c_hi > cap * (1.0 + 1e-13)) {
+    unsigned long long lob = 0ull, hib = (unsigned long long)__double_as_longlong(mu_max);
+    c_lo = c_hi;
+    c_hi = cost_c(c, r, br, Md, mu_max);
+    mu = mu_max;
+    while (hib - lob > (1ull << 20)) {
+      const unsigned long long midb = lob + ((hib - lob) >> 1);
+      const double mid = __longlong_as_double((long long)midb);
+      const double cm = cost_c(c, r, br, Md, mid);
+      if (cm <= cap * (1.0 + 1e-13)) { hib = midb; mu = mid; c_hi = cm; } else { lob = midb; c_lo = cm; }
+    }
+  }
+  double w = 0.0, me = 0.0;
+  for (int j = threadIdx.x; j < c.J; j += blockDim.x) {
+    const double n = job_nc(c, r, j, Md, mu);
+    w += util_c(c, j, n);
+    me = fmax(me, fmax(0.0, c.Rsec[j] - fmin(c.D * n, c.cap[j])));
+  }
+  w = br.sum(w);
+  me = br.max(me);
+  const double fill = fmax(0.0, fmin(cap - c_hi, c_lo - c_hi));   // tied jobs take the rest, utility linear
+  return w + mu * fill - k * me;
+}
+
+__device__ double relaxed_optimum(const Ctx &c, const RelaxCtx &r, BlockRed &br, double mu_max, double k) {
+  // makespan threshold range: floor (everybody at its continuous maximum) .. natural (no threshold)
+  double mfl = 0.0, mtop = 0.0;
+  for (int j = threadIdx.x; j < c.J; j += blockDim.x) {
+    const double nm = nmax_real(c, r, j);
+    mfl = fmax(mfl, c.Rsec[j] - fmin(c.D * nm, c.cap[j]));
+    mtop = fmax(mtop, c.Rsec[j]);
+  }
+  mfl = fmax(0.0, br.max(mfl));
+  mtop = br.max(mtop);
+  // smallest threshold whose forced demand fits
+  double lo = mfl, hi = mtop;
+  if (cost_c(c, r, br, mfl * c.invD, mu_max) > (double)c.GT) {
+    for (int it = 0; it < 80; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      if (cost_c(c, r, br, mid * c.invD, mu_max) <= (double)c.GT) hi = mid; else lo = mid;
+    }
+    lo = hi;
+  }
+  hi = mtop;
+  double best = fmax(phi_c(c, r, br, lo, mu_max, k), phi_c(c, r, br, hi, mu_max, k));
+  const double gr = 0.6180339887498949;
+  double x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo);
+  double f1 = phi_c(c, r, br, x1, mu_max, k), f2 = phi_c(c, r, br, x2, mu_max, k);
+  for (int it = 0; it < 70 && hi - lo > 1e-9 * (1.0 + hi); ++it) {
+    if (f1 < f2) { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); f2 = phi_c(c, r, br, x2, mu_max, k); }
+    else { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); f1 = phi_c(c, r, br, x1, mu_max, k); }
+    best = fmax(best, fmax(f1, f2));
+  }
+  return best;
+}
+
 __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int s = blockIdx.x;
@@ -216,6 +311,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
       }
     }
     c.t.nF[j] = (uint8_t)nF;
+    if (L.sc_nfc) L.sc_nfc[so + j] = (!bad && R - capF > 0.0) ? (R - capF) / D : 0.0;
     infeasible += bad;
     forced += (long long)gI[j] * nF;
   }
@@ -230,6 +326,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
     double w = 1.0;
     if (!ftf_ok) {
       c.t.nF[j] = 0;
+      if (L.sc_nfc) L.sc_nfc[so + j] = 0.0;
       const double R = RfbI[j];
       const double ratio = (D * (double)prm.round_ptr + R / share) / ftI[j];
       if (ratio > prm.rhomax) {
@@ -401,6 +498,13 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
     r.objective = w - k * me;
     r.price = pr.hi;
     r.relaxed_objective = best_V;
+  }
+  if (L.want_relaxed && L.sc_nfc) {
+    __syncthreads();
+    RelaxCtx rc;
+    rc.nfc = L.sc_nfc + so; rc.Tr = (double)T;
+    const double rv = relaxed_optimum(c, rc, br, mu_max, k);
+    if (threadIdx.x == 0) L.res[s].relaxed_objective = rv;
   }
 }
 

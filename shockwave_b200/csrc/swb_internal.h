@@ -29,6 +29,8 @@ struct SolveLaunch {
   double *sc_cth;
   float *sc_ths;
   uint8_t *sc_n0;
+  double *sc_nfc;      // [S][J] continuous FTF lower bounds (relaxation only)
+  int want_relaxed;    // also compute the exact optimum of the continuous relaxation (slow; parity item P4)
   const uint8_t *ncap; // [S][J] per-job cap on the round count from packing feedback (255 = none)
   double *weights;   // [S][J] out, may be null
   swb_result *res;   // device [S]

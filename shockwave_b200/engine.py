@@ -56,7 +56,7 @@ class RoundArgs(C.Structure):
 
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
            "swb_solve", "swb_job_add", "swb_job_remove", "swb_round_solve", "swb_forecast",
-           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_gbm_forecast", "swb_market_pgd"]
+           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_gbm_forecast", "swb_market_pgd", "swb_set_option"]
 
 _lib = None
 
@@ -252,6 +252,10 @@ class Engine:
         ncal = np.ascontiguousarray(ncal, dtype=np.int32)
         self._check(self.lib.swb_forecast_commit(self.h, len(ncal), int(bool(fallback)), _ptr(ncal)),
                     "swb_forecast_commit")
+
+    def set_option(self, option, value):
+        self.lib.swb_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        self._check(self.lib.swb_set_option(self.h, int(option), int(value)), "swb_set_option")
 
     def last_timings(self):
         a, b, n = C.c_double(), C.c_double(), C.c_int32()
