@@ -18,6 +18,7 @@
 // round that straddles the breakpoint.  ~35 instructions per job and evaluation; reductions are warp
 // shuffles + one barrier.  The dense J x T placement of the counts is place.cu.
 #include <math.h>
+#include <stdlib.h>
 
 #include "swb_common.cuh"
 #include "swb_internal.h"
@@ -83,6 +84,7 @@ __device__ __forceinline__ double util_of(const Ctx &c, int j, int n) {
 __device__ long long cost_at(const Ctx &c, BlockRed &br, double M, double mu) {
   const double Md = M * c.invD;
   int s = 0;
+#pragma unroll 4
   for (int j = threadIdx.x; j < c.J; j += blockDim.x) s += (int)c.t.g[j] * job_n(c, j, Md, mu);
   return br.sumll((long long)s);
 }
@@ -231,7 +233,10 @@ __device__ double relaxed_optimum(const Ctx &c, const RelaxCtx &r, BlockRed &br,
   return best;
 }
 
-__global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch L) {
+// SMEM = the response table lives in shared memory (J <= SWB_SMEM_JOBS).  A compile-time switch so that
+// the hot loop's accesses are LDS with 32-bit addresses instead of generic 64-bit loads.
+template <bool SMEM, int NT>
+__global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int s = blockIdx.x;
   const int J = L.J;
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
   unsigned char *p = smem_raw + SWB_PWL_BYTES + 2 * 64 * sizeof(double);
   Ctx c;
   const size_t so = (size_t)s * J;
-  if (L.jobs_in_smem) {
+  if constexpr (SMEM) {
     c.t.cth = reinterpret_cast<double *>(p); p += sizeof(double) * J;
     c.t.R = reinterpret_cast<double *>(p);   p += sizeof(double) * J;
     c.t.ths = reinterpret_cast<float *>(p);  p += sizeof(float) * J * B;
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(SWB_SOLVE_THREADS, 1) solve_kernel(SolveLaunch
     const int n = c.n[j];
     w += util_of(c, j, n);
     me = fmax(me, rem_of(c, j, n));
-    if (L.jobs_in_smem) { L.sc_g[so + j] = c.t.g[j]; L.sc_nF[so + j] = c.t.nF[j]; L.sc_nmax[so + j] = c.t.nmax[j]; }
+    if constexpr (SMEM) { L.sc_g[so + j] = c.t.g[j]; L.sc_nF[so + j] = c.t.nF[j]; L.sc_nmax[so + j] = c.t.nmax[j]; }
   }
   w = br.sum(w);
   me = br.max(me);
@@ -530,23 +535,32 @@ cudaError_t launch_tighten(int S, int J, const swb_result *res, const uint8_t *p
   return cudaGetLastError();
 }
 
+static int g_solve_nt = 1024;   // threads per CTA of the shared-memory variant (SWB_SOLVE_NT=512 for experiments)
+
 cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st, int nbases) {
   size_t smem = SWB_PWL_BYTES + 2 * 64 * sizeof(double);
   if (L.jobs_in_smem) smem += (size_t)L.J * (2 * sizeof(double) + 5 * (size_t)nbases + 3);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, solve_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&fa, solve_kernel<true, 1024>);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(solve_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SWB_MAX_DYN_SMEM - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(solve_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SWB_MAX_DYN_SMEM - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return e;
+    const char *env = getenv("SWB_SOLVE_NT");
+    if (env) g_solve_nt = atoi(env) == 512 ? 512 : 1024;
     attr_set = true;
   }
   int nt = ((L.J + 31) / 32) * 32;
-  if (nt > SWB_SOLVE_THREADS) nt = SWB_SOLVE_THREADS;
+  if (nt > g_solve_nt) nt = g_solve_nt;
   if (nt < 64) nt = 64;
-  solve_kernel<<<L.S, nt, smem, st>>>(L);
+  if (!L.jobs_in_smem) solve_kernel<false, 1024><<<L.S, nt, smem, st>>>(L);
+  else if (g_solve_nt == 512) solve_kernel<true, 512><<<L.S, nt, smem, st>>>(L);
+  else solve_kernel<true, 1024><<<L.S, nt, smem, st>>>(L);
   return cudaGetLastError();
 }
 
