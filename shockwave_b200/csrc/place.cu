@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     for (int pos = 0; pos < J; ++pos) {
       if (key64[pos] == 0ull) break;
       const int j = idx16[pos];
-      const int g = gs[j], n = nplan[j];
+      const int g = gs[j], n = remn[j];   // remn == plan until the job is seated (shared memory; nplan is global)
       const unsigned int lim = ((unsigned)(G - g) << 8) | 0xffu;
       const unsigned int add = (unsigned)g << 8;
       // Fast path (the common, load-balanced state): the n least-loaded bins all fit the job and, once

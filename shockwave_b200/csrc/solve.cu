@@ -91,22 +91,35 @@ __device__ long long cost_at(const Ctx &c, BlockRed &br, double M, double mu) {
 
 struct Price { double hi, lo; long long cost_hi; int iters; };
 
-// smallest price at which demand fits: cost(M, hi) <= GT < cost(M, lo)
-__device__ Price solve_price(const Ctx &c, BlockRed &br, double M, double mu_max) {
+// smallest price at which demand fits: cost(M, hi) <= GT < cost(M, lo).
+// Bisection on the BIT PATTERN of the (positive) price: the fallback priorities span 20+ orders of
+// magnitude (ratio^lam, shockwave.py:899-903), so an arithmetic midpoint would stop far above the real
+// clearing price and lump every cheaper item into one "tie".  Positive doubles are ordered like their bit
+// patterns.  The loop ends when hi/lo - 1 < 2^-prec; everything priced inside such an interval is treated
+// as a tie and filled in job order (prec = 12 while searching the makespan threshold, 22 for the final
+// allocation; the response function itself has fp32 resolution).  `hint` (> 0) is the clearing price of a
+// neighbouring threshold: the search then starts from [hint/4, 4 hint] when that bracket holds.
+__device__ Price solve_price(const Ctx &c, BlockRed &br, double M, double mu_max, int prec, double hint) {
   Price p;
   p.iters = 1;
   long long c0 = cost_at(c, br, M, 0.0);
   if (c0 <= c.GT) { p.hi = p.lo = 0.0; p.cost_hi = c0; return p; }
-  // Bisection on the BIT PATTERN of the (positive) price: the fallback priorities span 20+ orders of
-  // magnitude (ratio^lam, shockwave.py:899-903), so an arithmetic midpoint would stop ~2^-44 * mu_max
-  // above the real clearing price and lump every cheaper item into one "tie".  Positive doubles are
-  // ordered like their bit patterns; the loop ends when hi/lo - 1 < 2^-24 (everything priced inside
-  // such an interval is treated as a tie and filled in job order).
   unsigned long long lob = 0ull, hib = (unsigned long long)__double_as_longlong(mu_max);
   double lo = 0.0, hi = mu_max;
-  long long chi = cost_at(c, br, M, hi);
-  p.iters++;
-  while (hib - lob > (1ull << 28)) {   // 2^-24 relative: the fp32 resolution of the response function
+  long long chi = -1;
+  if (hint > 0.0) {
+    const double h4 = fmin(mu_max, hint * 4.0), l4 = hint * 0.25;
+    const long long ch = cost_at(c, br, M, h4);
+    p.iters++;
+    if (ch <= c.GT) { hi = h4; hib = (unsigned long long)__double_as_longlong(h4); chi = ch; }
+    const long long cl = cost_at(c, br, M, l4);
+    p.iters++;
+    if (cl > c.GT) { lo = l4; lob = (unsigned long long)__double_as_longlong(l4); }
+    else if (chi >= 0 || l4 < hi) { hi = l4; hib = (unsigned long long)__double_as_longlong(l4); chi = cl; }
+  }
+  if (chi < 0) { chi = cost_at(c, br, M, hi); p.iters++; }
+  const unsigned long long width = 1ull << (52 - prec);
+  while (hib - lob > width) {
     const unsigned long long midb = lob + ((hib - lob) >> 1);
     const double mid = __longlong_as_double((long long)midb);
     const long long cm = cost_at(c, br, M, mid);
@@ -120,8 +133,8 @@ __device__ Price solve_price(const Ctx &c, BlockRed &br, double M, double mu_max
 struct Phi { double V, welfare, Meff, mu; long long cost; };
 
 // value of makespan threshold M: LP-style welfare at the clearing price minus k * achieved makespan
-__device__ Phi phi_at(const Ctx &c, BlockRed &br, double M, double mu_max, double k, int &iters) {
-  Price p = solve_price(c, br, M, mu_max);
+__device__ Phi phi_at(const Ctx &c, BlockRed &br, double M, double mu_max, double k, int &iters, double hint) {
+  Price p = solve_price(c, br, M, mu_max, 12, hint);
   iters += p.iters;
   double w = 0.0, me = 0.0;
   const double Md = M * c.invD;
@@ -386,22 +399,24 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   }
 
   // ---- phase 3: search the makespan threshold (value is concave in the relaxation) ----------
-  Phi nat = phi_at(c, br, INF_M, mu_max, k, iters); m_evals++;
+  Phi nat = phi_at(c, br, INF_M, mu_max, k, iters, 0.0); m_evals++;
+  double hint = nat.mu;
   double best_V = nat.V, best_thr = INF_M;
   if (nat.Meff - eps >= mmin) {
-    Phi t2 = phi_at(c, br, nat.Meff - eps, mu_max, k, iters); m_evals++;
+    Phi t2 = phi_at(c, br, nat.Meff - eps, mu_max, k, iters, hint); m_evals++;
     if (t2.V > nat.V) {
       best_V = t2.V; best_thr = nat.Meff - eps;
       double lo = mmin, hi = nat.Meff - eps;
-      Phi pl = phi_at(c, br, lo, mu_max, k, iters); m_evals++;
+      Phi pl = phi_at(c, br, lo, mu_max, k, iters, hint); m_evals++;
       if (pl.V > best_V) { best_V = pl.V; best_thr = lo; }
       for (int it = 0; it < 48 && hi - lo > eps; ++it) {
         const double mid = 0.5 * (lo + hi);
-        Phi p1 = phi_at(c, br, mid, mu_max, k, iters); m_evals++;
+        Phi p1 = phi_at(c, br, mid, mu_max, k, iters, hint); m_evals++;
+        if (p1.mu > 0.0) hint = p1.mu;
         if (p1.V > best_V) { best_V = p1.V; best_thr = mid; }
         const double below = p1.Meff - eps;
         if (below < mmin) break;               // already at the smallest packable makespan
-        Phi p2 = phi_at(c, br, below, mu_max, k, iters); m_evals++;
+        Phi p2 = phi_at(c, br, below, mu_max, k, iters, p1.mu > 0.0 ? p1.mu : hint); m_evals++;
         if (p2.V > best_V) { best_V = p2.V; best_thr = below; }
         if (p2.V > p1.V) hi = below; else lo = mid;
       }
@@ -409,7 +424,7 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   }
 
   // ---- phase 4: integral allocation at the chosen threshold ----------------------------------
-  Price pr = solve_price(c, br, best_thr, mu_max);
+  Price pr = solve_price(c, br, best_thr, mu_max, 22, hint);
   iters += pr.iters;
   const double thr_d = best_thr * c.invD;
   for (int j = threadIdx.x; j < J; j += blockDim.x) c.n[j] = (uint8_t)job_n(c, j, thr_d, pr.hi);
