@@ -187,6 +187,53 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     int head = 0;   // the sorted bins are a RING: logical position p lives in A[(head + p) mod T]
     for (int pos = 0; pos < J; ++pos) {
       if (key64[pos] == 0ull) break;
+      // ---- chunk-parallel path: 32 consecutive jobs of the SAME width on a balanced ring -------------
+      // With the bins sorted by load and max - min <= g, least-loaded-first over jobs of width g is a
+      // round-robin over the ring: job i takes the ring positions [head + P_i, head + P_i + n_i) (P =
+      // exclusive prefix sum of the counts), the order stays sorted and the spread stays <= g.  The bin
+      // behind every ring position does not change, so the 32 jobs compute their round masks
+      // independently; only the fit (no bin above G at the END of the chunk) has to be checked first.
+      // The result is identical to seating the 32 jobs one after the other below.
+      {
+        const int pp = pos + lane;
+        const bool valid = pp < J && key64[pp] != 0ull;
+        const int jj = valid ? (int)idx16[pp] : 0;
+        const int gg = valid ? (int)gs[jj] : 0, nn = valid ? (int)remn[jj] : 0;
+        const unsigned int vmask = __ballot_sync(SWB_FULL, valid);
+        const int cnt = __popc(vmask);
+        const int g0 = __shfl_sync(SWB_FULL, gg, 0);
+        const bool same = __all_sync(SWB_FULL, !valid || gg == g0);
+        int hl0 = head + T - 1; if (hl0 >= T) hl0 -= T;
+        const int lmin = (int)(A[head] >> 8), lmax = (int)(A[hl0] >> 8);
+        int incl = nn;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(SWB_FULL, incl, o); if (lane >= o) incl += t2; }
+        const int Ptot = __shfl_sync(SWB_FULL, incl, 31);
+        const int cfull = Ptot / T, rpart = Ptot - cfull * T;
+        int hr = head + rpart - 1; if (hr >= T) hr -= T; if (hr < 0) hr += T;
+        const int top = max(rpart > 0 ? (int)(A[hr] >> 8) + g0 * (cfull + 1) : 0, lmax + g0 * cfull);
+        if (cnt >= 4 && same && lmax - lmin <= g0 && top <= G) {
+          if (valid) {
+            int st = head + (incl - nn) % T; if (st >= T) st -= T;
+            unsigned long long m0 = 0ull, m1 = 0ull;
+            for (int q = 0; q < nn; ++q) {
+              int ix = st + q; if (ix >= T) ix -= T;
+              const unsigned int b = A[ix] & 0xffu;
+              if (b < 64) m0 |= 1ull << b; else m1 |= 1ull << (b - 64);
+            }
+            xm[2 * jj] = m0; xm[2 * jj + 1] = m1; remn[jj] = 0;
+          }
+          __syncwarp();
+          for (int p = lane; p < T; p += 32) {           // loads after the whole chunk
+            int off = p - head; if (off < 0) off += T;
+            A[p] += (unsigned)(g0 * (cfull + (off < rpart ? 1 : 0))) << 8;
+          }
+          head += rpart; if (head >= T) head -= T;
+          pos += cnt - 1;
+          __syncwarp();
+          continue;
+        }
+      }
       const int j = idx16[pos];
       const int g = gs[j], n = remn[j];   // remn == plan until the job is seated (shared memory; nplan is global)
       const unsigned int lim = ((unsigned)(G - g) << 8) | 0xffu;
