@@ -196,7 +196,7 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   swb::PlaceLaunch P;
   P.S = S; P.J = J; P.per_scn = per_scn; P.prm = L.prm; P.bfkey = bfkey; P.bfkey_fb = bfkey_fb;
   P.sc_a = L.sc_a; P.sc_u0 = L.sc_u0; P.sc_R = L.sc_R; P.sc_ws = L.sc_ws; P.sc_cap = L.sc_cap;
-  P.sc_g = L.sc_g; P.sc_n = L.sc_n; P.weights = L.weights; P.E = E; P.c = cc; P.dbar = dbar;
+  P.sc_g = L.sc_g; P.sc_n = L.sc_n; P.sc_nmax = L.sc_nmax; P.weights = L.weights; P.E = E; P.c = cc; P.dbar = dbar;
   P.x = x; P.backfill = bf; P.nrounds = nr ? nr : c->seated.as<int32_t>(); P.ncal = ncal; P.res = L.res;
   P.xmask = xmask; P.bfmask = bfmask;
   int rc2 = ensure_hres(c, S);

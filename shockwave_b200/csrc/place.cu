@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   unsigned short *order = reinterpret_cast<unsigned short *>(p); p += 2 * (size_t)npad;
   unsigned char *gs = p;   p += npad;
   unsigned char *remn = p; p += npad;
+  unsigned char *ext = p;  p += npad;     // rounds added by the improvement pass beyond the plan
   p = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
   unsigned long long *xm, *bm;  // [J][2] each
   if (J <= SWB_SMEM_JOBS) {
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   const uint8_t *gI = L.sc_g + so;
 
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
-    gs[j] = gI[j]; remn[j] = nplan[j];
+    gs[j] = gI[j]; remn[j] = nplan[j]; ext[j] = 0;
     xm[2 * j] = 0; xm[2 * j + 1] = 0; bm[2 * j] = 0; bm[2 * j + 1] = 0;
   }
   __syncthreads();
@@ -358,17 +359,72 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   }
   __syncthreads();
 
+  Pwl P;
+  P.B = prm.nbases;
+  for (int b = 0; b < prm.nbases; ++b) { P.base[b] = prm.bases[b]; P.logv[b] = prm.logv[b]; }
+  for (int b = 0; b + 1 < prm.nbases; ++b)
+    P.slope[b] = (prm.logv[b + 1] - prm.logv[b]) / (prm.bases[b + 1] - prm.bases[b]);
+
+  // ---- improvement pass: GPU-rounds the packing left idle go to the job with the best marginal utility
+  //      per GPU that is not yet in that round and still fits (only matters when the counts could not be
+  //      packed perfectly: wide gangs on a small cluster) ------------------------------------------------
+  {
+    int any = 0;
+    for (int j = threadIdx.x; j < J; j += blockDim.x)
+      any |= ((int)nplan[j] - (int)remn[j] < (int)L.sc_nmax[so + j]) ? 1 : 0;
+    any = (int)br.sumll((long long)any);
+    int idle_tot = 0;
+    for (int t = 0; t < T; ++t) idle_tot += idle[t];
+    if (any && idle_tot > 0) {
+      const double Dd = prm.round_duration;
+      int budget = 64;
+      for (int t = 0; t < T && budget > 0; ++t) {
+        while (idle[t] > 0 && budget > 0) {
+          const int room = idle[t];
+          double bd = 0.0;
+          for (int j = threadIdx.x; j < J; j += blockDim.x) {
+            const int n = (int)nplan[j] - (int)remn[j] + (int)ext[j];
+            if (n < (int)L.sc_nmax[so + j] && (int)gs[j] <= room && !((xm[2 * j + (t >> 6)] >> (t & 63)) & 1ull)) {
+              const double a = L.sc_a[so + j], u0 = L.sc_u0[so + j], cap = L.sc_cap[so + j];
+              const double u1 = (Dd * (double)(n + 1) >= cap) ? 1.0 : fma(a, (double)(n + 1), u0);
+              const double u_0 = (Dd * (double)n >= cap) ? 1.0 : fma(a, (double)n, u0);
+              bd = fmax(bd, L.sc_ws[so + j] * (plog(P, u1) - plog(P, u_0)) / (double)gs[j]);
+            }
+          }
+          bd = br.max(bd);
+          if (!(bd > 0.0)) break;
+          double bj = 1e300;
+          for (int j = threadIdx.x; j < J; j += blockDim.x) {
+            const int n = (int)nplan[j] - (int)remn[j] + (int)ext[j];
+            if (n < (int)L.sc_nmax[so + j] && (int)gs[j] <= room && !((xm[2 * j + (t >> 6)] >> (t & 63)) & 1ull)) {
+              const double a = L.sc_a[so + j], u0 = L.sc_u0[so + j], cap = L.sc_cap[so + j];
+              const double u1 = (Dd * (double)(n + 1) >= cap) ? 1.0 : fma(a, (double)(n + 1), u0);
+              const double u_0 = (Dd * (double)n >= cap) ? 1.0 : fma(a, (double)n, u0);
+              if (L.sc_ws[so + j] * (plog(P, u1) - plog(P, u_0)) / (double)gs[j] >= bd) bj = fmin(bj, (double)j);
+            }
+          }
+          bj = br.min(bj);
+          if (bj >= 1e299) break;
+          const int wj = (int)bj;
+          if (threadIdx.x == 0) {
+            xm[2 * wj + (t >> 6)] |= 1ull << (t & 63);
+            ext[wj] = (unsigned char)(ext[wj] + 1);
+            idle[t] = room - (int)gs[wj];
+          }
+          --budget;
+          __syncthreads();
+        }
+      }
+    }
+  }
+  __syncthreads();
+
   // ---- objective of the PLACED schedule (what a checker recomputes from x) --------------------
   {
-    Pwl P;
-    P.B = prm.nbases;
-    for (int b = 0; b < prm.nbases; ++b) { P.base[b] = prm.bases[b]; P.logv[b] = prm.logv[b]; }
-    for (int b = 0; b + 1 < prm.nbases; ++b)
-      P.slope[b] = (prm.logv[b + 1] - prm.logv[b]) / (prm.bases[b + 1] - prm.bases[b]);
     double w = 0.0, me = 0.0;
     long long shortf = 0;
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
-      const int n = (int)nplan[j] - (int)remn[j];
+      const int n = (int)nplan[j] - (int)remn[j] + (int)ext[j];
       shortf += remn[j];
       // same float64 formula a checker applies to x: p = min(D n / dbar, E - c), u = (c + p) / E
       const size_t ji = (L.per_scn ? so : 0) + j;
@@ -464,7 +520,7 @@ cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long lo
   int npad = 64;
   while (npad < L.J) npad <<= 1;
   size_t smem = 2 * 64 * sizeof(double) + 32 * sizeof(int) + SWB_MAX_T * (4 * sizeof(int) + sizeof(double) + 1) +
-                10 * (size_t)npad + 4 * (size_t)npad + 2 * (size_t)npad + 16;
+                10 * (size_t)npad + 4 * (size_t)npad + 3 * (size_t)npad + 16;
   if (L.J <= SWB_SMEM_JOBS) smem += 32 * (size_t)L.J;
   static bool attr_set = false;
   if (!attr_set) {

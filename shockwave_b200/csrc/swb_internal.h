@@ -42,7 +42,7 @@ struct PlaceLaunch {
   const double *bfkey;    // [S][J] or [J]
   const double *bfkey_fb; // same, for the fallback continuation (may be null -> bfkey)
   const double *sc_a, *sc_u0, *sc_R, *sc_ws, *sc_cap;
-  const uint8_t *sc_g, *sc_n;
+  const uint8_t *sc_g, *sc_n, *sc_nmax;
   const double *weights;  // [S][J] (priority, for the fallback re-rank), may be null
   const int32_t *E, *c;   // solver inputs again (objective re-evaluation with the checker's formula)
   const double *dbar;
