@@ -96,18 +96,11 @@ class ShockwaveScheduler(object):
         self._tl_cache.pop(jobid, None)
 
     def _timeline_summary(self, jobid, job):
-        """(measured_nsamples, end_round) of JobMetaData.py:235-249, cached while the shared
-        throughput OrderedDict is unchanged."""
+        """(measured_nsamples, end_round) of JobMetaData.py:235-249 for one job."""
         tl = job.throughput_measurements
         assert tl is not None                       # JobMetaData.py:229
-        n = len(tl)
-        if n == 0:
+        if len(tl) == 0:
             return 0.0, -1
-        last = next(reversed(tl))
-        sig = (n, last, tl[last])
-        hit = self._tl_cache.get(jobid)
-        if hit is not None and hit[0] == sig:
-            return hit[1]
         grd = job.gavel_round_duration
         prev = 0
         nsamp = 0
@@ -115,22 +108,38 @@ class ShockwaveScheduler(object):
             thr, bs = tl[cur][0], tl[cur][1]
             nsamp += bs * (thr * grd * (cur - prev))
             prev = cur
-        out = (float(nsamp), int(max(tl.keys())))
-        self._tl_cache[jobid] = (sig, out)
-        return out
+        return float(nsamp), int(max(tl.keys()))
+
+    def _timeline_summaries(self, jobids, jobobjs):
+        """Vector form, cached per job while its shared throughput OrderedDict is unchanged (signature =
+        length + last (round, value) entry; the caller only appends / rewrites the current round,
+        scheduler.py:568-571)."""
+        J = len(jobids)
+        tls = [job.throughput_measurements for job in jobobjs]
+        sigs = [(len(t), next(reversed(t.items()), None)) for t in tls]
+        cache = self._tl_cache
+        ns = np.empty(J, dtype=np.float64)
+        end = np.empty(J, dtype=np.int32)
+        old = [cache.get(j) for j in jobids]
+        for i in range(J):
+            hit = old[i]
+            if hit is None or hit[0] != sigs[i]:
+                hit = (sigs[i], self._timeline_summary(jobids[i], jobobjs[i]))
+                cache[jobids[i]] = hit
+            ns[i], end[i] = hit[1]
+        return ns, end
 
     def _resolve(self, jobids, jobobjs):
         """One re-solve on the device; returns OrderedDict{round -> [job ids]} (shockwave.py:129-161)."""
         J = len(jobids)
+        if J == 0:      # nothing to schedule: an empty window (the reference is never called like this)
+            return OrderedDict((self.round_ptr + t, []) for t in range(self.future_nrounds))
         slots = np.fromiter((self._slots[j] for j in jobids), dtype=np.int32, count=J)
         prog = np.fromiter((job.epoch_progress for job in jobobjs), dtype=np.int32, count=J)
-        ns = np.empty(J, dtype=np.float64)
-        end = np.empty(J, dtype=np.int32)
-        for i, (jid, job) in enumerate(zip(jobids, jobobjs)):
-            ns[i], end[i] = self._timeline_summary(jid, job)
+        ns, end = self._timeline_summaries(jobids, jobobjs)
         prm = _eng.make_params(self.ngpus, self.future_nrounds, self.round_duration, self.k, self.lam,
                                self.rhomax, self.logapx_bases, self.logapx_origin, self.round_ptr)
-        grd = jobobjs[0].gavel_round_duration if J else self.round_duration
+        grd = jobobjs[0].gavel_round_duration
         out = self._eng().round_solve(prm, slots, prog, ns, end, self.reestimate_share, grd,
                                       want_forecast=True)
         self.last_result = out["result"]
@@ -194,17 +203,41 @@ class ShockwaveScheduler(object):
         self.set_resolve()
 
 
+class LazySchedules(OrderedDict):
+    """OrderedDict{round -> [job ids]} whose lists are built on first access.
+
+    The reference materialises all T lists in construct_schedules (shockwave.py:233-283), but only
+    `schedules[round_ptr]` is ever read (shockwave.py:127,166) and a window is usually replaced by the next
+    re-solve after one or a few rounds; at 4096 jobs x 64 rounds building every list costs more host time
+    than the whole GPU solve."""
+
+    def __init__(self, x, backfill, bfkey, jobids, round_ptr):
+        super().__init__()
+        self._x, self._bf, self._ids, self._r0 = x, backfill, list(jobids), round_ptr
+        self._order = np.argsort(-np.asarray(bfkey, dtype=np.float64), kind="stable")
+        for t in range(x.shape[1]):
+            super().__setitem__(round_ptr + t, None)
+
+    def __getitem__(self, rnd):
+        cur = super().__getitem__(rnd)
+        if cur is None:
+            t = rnd - self._r0
+            ids = self._ids
+            cur = [ids[j] for j in np.flatnonzero(self._x[:, t]).tolist()]
+            order = self._order
+            cur += [ids[j] for j in order[np.flatnonzero(self._bf[order, t])].tolist()]
+            super().__setitem__(rnd, cur)
+        return cur
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+
 def schedules_from_matrices(x, backfill, bfkey, jobids, round_ptr):
-    """J x T byte matrices -> OrderedDict{round_ptr+t -> [job ids]} in the reference's list order
+    """J x T byte matrices -> {round_ptr+t -> [job ids]} in the reference's list order
     (construct_schedules, shockwave.py:233-283): solver-scheduled jobs in metadata order, then the
     back-filled ones in descending remaining-runtime order (stable)."""
-    J, T = x.shape
-    ids = np.asarray(jobids, dtype=object)
-    order = np.argsort(-np.asarray(bfkey, dtype=np.float64), kind="stable")
-    sched = OrderedDict()
-    for t in range(T):
-        cur = [jobids[j] for j in np.flatnonzero(x[:, t])]
-        bf = backfill[order, t]
-        cur += [jobids[j] for j in order[np.flatnonzero(bf)]]
-        sched[round_ptr + t] = cur
-    return sched
+    return LazySchedules(x, backfill, bfkey, jobids, round_ptr)
