@@ -522,7 +522,11 @@ cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long lo
   size_t smem = 2 * 64 * sizeof(double) + 32 * sizeof(int) + SWB_MAX_T * (4 * sizeof(int) + sizeof(double) + 1) +
                 10 * (size_t)npad + 4 * (size_t)npad + 3 * (size_t)npad + 16;
   if (L.J <= SWB_SMEM_JOBS) smem += 32 * (size_t)L.J;
-  static bool attr_set = false;
+  // function attributes are per device: one flag per device ordinal (one process may drive several GPUs)
+  static bool attr_done[64] = {false};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool &attr_set = attr_done[dev_ & 63];
   if (!attr_set) {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, place_kernel);

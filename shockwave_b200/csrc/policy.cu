@@ -154,7 +154,11 @@ cudaError_t launch_policy(const PolicyLaunch &L, cudaStream_t st) {
   int npad = 64;
   while (npad < L.J) npad <<= 1;
   size_t smem = 2 * 64 * sizeof(double) + (size_t)npad * (8 + 2) + 64;
-  static bool attr_set = false;
+  // function attributes are per device: one flag per device ordinal (one process may drive several GPUs)
+  static bool attr_done[64] = {false};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool &attr_set = attr_done[dev_ & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;

@@ -555,7 +555,11 @@ static int g_solve_nt = 1024;   // threads per CTA of the shared-memory variant 
 cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st, int nbases) {
   size_t smem = SWB_PWL_BYTES + 2 * 64 * sizeof(double);
   if (L.jobs_in_smem) smem += (size_t)L.J * (2 * sizeof(double) + 5 * (size_t)nbases + 3);
-  static bool attr_set = false;
+  // function attributes are per device: one flag per device ordinal (one process may drive several GPUs)
+  static bool attr_done[64] = {false};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool &attr_set = attr_done[dev_ & 63];
   if (!attr_set) {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, solve_kernel<true, 1024>);
