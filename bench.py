@@ -47,31 +47,57 @@ def synth_batch(S, seed0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons DURING the timed region, through NVML (nvidia_ml_py) every 5 ms — the timed
+    region is ~50 ms, far too short for spawning nvidia-smi (B200_PROFILING.md's query, same fields)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
+        self.index, self.stop_flag, self.sm, self.reasons, self.mx, self.power = index, False, [], set(), None, []
+        self.t0, self.t1, self.ts, self.bits = None, None, [], []
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                self.ts.append(time.perf_counter())
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    self.bits.append(int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+                except Exception:
+                    self.power.append(0.0); self.bits.append(0)
+                time.sleep(0.002)
+        except Exception as e:                      # NVML missing: fall back to one nvidia-smi query
+            self.error = repr(e)
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.rows.append([v.strip() for v in out.stdout.strip().split(",")])
+                a, b = [float(v) for v in out.stdout.strip().split(",")]
+                self.sm.append(a); self.mx = b
             except Exception:
                 pass
-            time.sleep(0.2)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        """Samples taken inside [t0, t1] (the timed region); the sampler itself starts before the warm-up."""
+        idx = [i for i, t in enumerate(self.ts) if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e300)]
+        if not idx:
+            idx = list(range(len(self.sm)))
+        sm = [self.sm[i] for i in idx]
+        reasons = set(self.reasons)
+        for i in idx:
+            if i < len(self.bits):
+                for b, name in self.REASONS.items():
+                    if self.bits[i] & b:
+                        reasons.add(name)
+        pw = [self.power[i] for i in idx if i < len(self.power)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 def _ref_one(seed):
@@ -182,13 +208,14 @@ def main():
             dist.all_reduce(mc_out, op=dist.ReduceOp.SUM)      # NCCL over NVLink: 2*J float64 = 64 KiB
         return eng.solve_device(prms, J, ptrs, optrs)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(W):
         step_resident()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.t0 = time.perf_counter()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     ksolve, kplace, launches = [], [], 0
     torch.cuda.synchronize()
@@ -204,6 +231,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    sampler.t1 = time.perf_counter()
     sampler.stop_flag = True
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -321,11 +349,22 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ms_solve, ms_place = float(np.mean(ksolve)), float(np.mean(kplace))
-    bytes_solve = S * J * (3 * 4 + 3 * 8) + S * J * (1 + 8)          # inputs + plan + weights
-    bytes_place = S * J * (1 + 8 + 8) + S * J * T * 2 + S * J * 4      # plan, key, weights in; x, backfill, n out
-    dom = "solve_kernel" if ms_solve >= ms_place else "place_kernel"
-    dom_ms, dom_bytes = (ms_solve, bytes_solve) if dom == "solve_kernel" else (ms_place, bytes_place)
+    # algorithmic bytes per launch: inputs + outputs each kernel must touch once
+    kern = {
+        "solve_kernel": (ms_solve, S * J * (3 * 4 + 3 * 8) + S * J * (1 + 8)),
+        "place_kernel": (ms_place, S * J * (1 + 8 + 8) + S * J * T * 2 + S * J * 4),
+        "gbm_kernel": (mc_ms, J * (3 * 8 + 4) + 2 * J * 8),
+    }
+    dom = max(kern, key=lambda k: kern[k][0])
+    dom_ms, dom_bytes = kern[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    bound_note = {
+        "solve_kernel": "price/makespan search on per-job scalars staged in shared memory: instruction-issue bound "
+                        "(79 % issue-active in profiles/), not HBM bound",
+        "place_kernel": "sorts + water-filling over 64 rounds in shared memory: latency bound, not HBM bound",
+        "gbm_kernel": "Monte-Carlo paths (xorshift128+, Box-Muller, exp): ALU/SFU bound (86 % issue-active in profiles/), "
+                      "28 bytes in / 16 bytes out per job — the HBM fraction is reported only because the contract asks for it",
+    }[dom]
     line = {
         "metric": METRIC, "value": value, "unit": "rounds/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -340,12 +379,11 @@ def main():
                    "parallelism": f"scenario-sharded x{world}, no data-path collective"},
         "clocks": clocks,
         "gpu_launches": launches,
-        "kernels_ms": {"solve_kernel": ms_solve, "place_kernel": ms_place},
+        "kernels_ms": {"solve_kernel": ms_solve, "place_kernel": ms_place, "gbm_kernel": mc_ms},
         "e2e": {"value": e2e_val, "unit": "rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None,
-                     "note": "price/makespan search on per-job scalars staged in shared memory: FP64-issue and "
-                             "barrier-latency bound, not HBM bound — the HBM fraction is reported for the contract; "
+                     "note": bound_note + "; the HBM-bound kernel of this repo is the dense pass in roofline_dense; "
                              "peak = MEASURED_PEAKS.json hbm_gbs" + ("" if peaks else " (fallback 6650)")},
     }
     line["roofline_dense"] = {
