@@ -68,6 +68,8 @@ struct swb_ctx {
   DBuf f_slots, f_prog, f_mend, f_mns, f_remfb, f_bffb, f_ampok, f_ampfb, f_ftest, f_ncal;
   swb::ForecastLaunch last_fc;   // descriptor of the latest forecast (for the calibration commit)
   bool have_fc = false;
+  DBuf pol_coef, pol_sf, pol_t, pol_n, pol_den, pol_x, pol_out;          // swb_policy_pooled
+  DBuf mc_R0, mc_mu, mc_sigma, mc_H, mc_out;                                 // swb_gbm_forecast
   DBuf m_theta, m_rowp, m_colload, m_colscale, m_price, m_obj, m_X, m_rate, m_E, m_c, m_Gw;
   cudaEvent_t mev[2] = {nullptr, nullptr};
   double last_market_ms = 0.0;
@@ -112,7 +114,9 @@ void swb_destroy(swb_ctx *c) {
                  &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->scth, &c->sths, &c->sn0, &c->snfc, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
                  &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc,
                  &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
-                 &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal, &c->m_theta, &c->m_rowp, &c->m_colload,
+                 &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal, &c->pol_coef, &c->pol_sf, &c->pol_t,
+                 &c->pol_n, &c->pol_den, &c->pol_x, &c->pol_out, &c->mc_R0, &c->mc_mu, &c->mc_sigma, &c->mc_H, &c->mc_out,
+                 &c->m_theta, &c->m_rowp, &c->m_colload,
                  &c->m_colscale, &c->m_price, &c->m_obj, &c->m_X, &c->m_rate, &c->m_E, &c->m_c, &c->m_Gw};
   for (DBuf *b : all) b->release();
   if (c->h_res) cudaFreeHost(c->h_res);
@@ -497,23 +501,23 @@ int swb_policy_pooled(swb_ctx *c, int32_t mode, int32_t J, double N, const doubl
   if (mode == SWB_POL_MTD && !n) return fail(SWB_ERR_ARG, "swb_policy_pooled: MTD needs n");
   CK(cudaSetDevice(c->device));
   const size_t b = (size_t)J * 8;
-  CK(c->dbar.need(b, c->st)); CK(c->rem.need(b, c->st)); CK(c->ftobj.need(b, c->st));
-  CK(c->bfkey.need(b, c->st)); CK(c->f_remfb.need(b, c->st)); CK(c->f_bffb.need(b + 16, c->st));
-  CK(c->w.need(b, c->st));
-  CK(cudaMemcpyAsync(c->dbar.p, coef, b, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->rem.p, sf, b, cudaMemcpyHostToDevice, c->st));
-  if (t) CK(cudaMemcpyAsync(c->ftobj.p, t, b, cudaMemcpyHostToDevice, c->st));
-  if (n) CK(cudaMemcpyAsync(c->bfkey.p, n, b, cudaMemcpyHostToDevice, c->st));
-  if (den) CK(cudaMemcpyAsync(c->f_remfb.p, den, b, cudaMemcpyHostToDevice, c->st));
+  CK(c->pol_coef.need(b, c->st)); CK(c->pol_sf.need(b, c->st)); CK(c->pol_t.need(b, c->st));
+  CK(c->pol_n.need(b, c->st)); CK(c->pol_den.need(b, c->st)); CK(c->pol_x.need(b, c->st));
+  CK(c->pol_out.need(16, c->st));
+  CK(cudaMemcpyAsync(c->pol_coef.p, coef, b, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->pol_sf.p, sf, b, cudaMemcpyHostToDevice, c->st));
+  if (t) CK(cudaMemcpyAsync(c->pol_t.p, t, b, cudaMemcpyHostToDevice, c->st));
+  if (n) CK(cudaMemcpyAsync(c->pol_n.p, n, b, cudaMemcpyHostToDevice, c->st));
+  if (den) CK(cudaMemcpyAsync(c->pol_den.p, den, b, cudaMemcpyHostToDevice, c->st));
   swb::PolicyLaunch L;
   L.mode = mode; L.J = J; L.N = N;
-  L.coef = c->dbar.as<double>(); L.sf = c->rem.as<double>(); L.t = c->ftobj.as<double>();
-  L.n = c->bfkey.as<double>(); L.den = c->f_remfb.as<double>();
-  L.x = c->w.as<double>(); L.out = c->f_bffb.as<double>();
+  L.coef = c->pol_coef.as<double>(); L.sf = c->pol_sf.as<double>(); L.t = c->pol_t.as<double>();
+  L.n = c->pol_n.as<double>(); L.den = c->pol_den.as<double>();
+  L.x = c->pol_x.as<double>(); L.out = c->pol_out.as<double>();
   CK(swb::launch_policy(L, c->st));
   double out[2] = {0.0, 0.0};
-  CK(cudaMemcpyAsync(x, c->w.p, b, cudaMemcpyDeviceToHost, c->st));
-  CK(cudaMemcpyAsync(out, c->f_bffb.p, 16, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(x, c->pol_x.p, b, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(out, c->pol_out.p, 16, cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
   if (objective) *objective = out[0];
   return out[1] != 0.0 ? 1 : 0;
@@ -526,21 +530,22 @@ int swb_gbm_forecast(swb_ctx *c, int32_t J, const double *R0, const int32_t *H, 
   if (J <= 0 || P_local < 0) return fail(SWB_ERR_ARG, "swb_gbm_forecast: bad J / P_local");
   CK(cudaSetDevice(c->device));
   const size_t b = (size_t)J * 8;
-  CK(c->dbar.need(b, c->st)); CK(c->rem.need(b, c->st)); CK(c->ftobj.need(b, c->st)); CK(c->g.need((size_t)J * 4, c->st));
-  CK(c->bfkey.need(2 * b, c->st));
-  CK(cudaMemcpyAsync(c->dbar.p, R0, b, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->rem.p, mu, b, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->ftobj.p, sigma, b, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->g.p, H, (size_t)J * 4, cudaMemcpyHostToDevice, c->st));
+  CK(c->mc_R0.need(b, c->st)); CK(c->mc_mu.need(b, c->st)); CK(c->mc_sigma.need(b, c->st));
+  CK(c->mc_H.need((size_t)J * 4, c->st)); CK(c->mc_out.need(2 * b, c->st));
+  CK(cudaMemcpyAsync(c->mc_R0.p, R0, b, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->mc_mu.p, mu, b, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->mc_sigma.p, sigma, b, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->mc_H.p, H, (size_t)J * 4, cudaMemcpyHostToDevice, c->st));
   swb::GbmLaunch L;
   L.J = J; L.P_local = P_local; L.path_offset = path_offset; L.seed = seed;
-  L.R0 = c->dbar.as<double>(); L.mu = c->rem.as<double>(); L.sigma = c->ftobj.as<double>(); L.H = c->g.as<int32_t>();
-  L.out = out_on_device ? out : c->bfkey.as<double>();
+  L.R0 = c->mc_R0.as<double>(); L.mu = c->mc_mu.as<double>(); L.sigma = c->mc_sigma.as<double>();
+  L.H = c->mc_H.as<int32_t>();
+  L.out = out_on_device ? out : c->mc_out.as<double>();
   CK(cudaEventRecord(c->ev[0], c->st));
   CK(swb::launch_gbm(L, c->st));
   CK(cudaEventRecord(c->ev[1], c->st));
   CK(cudaEventRecord(c->ev[2], c->st));
-  if (!out_on_device) CK(cudaMemcpyAsync(out, c->bfkey.p, 2 * b, cudaMemcpyDeviceToHost, c->st));
+  if (!out_on_device) CK(cudaMemcpyAsync(out, c->mc_out.p, 2 * b, cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
   return 0;
 }
