@@ -176,6 +176,16 @@ int swb_forecast_commit(swb_ctx *ctx, int32_t J, int32_t fallback, const int32_t
 int swb_policy_pooled(swb_ctx *ctx, int32_t mode, int32_t J, double N, const double *coef, const double *sf,
                       const double *t, const double *n, const double *den, double *x, double *objective);
 
+/* ---- AlloX min-cost assignment --------------------------------------------------------------- *
+ * Replaces scipy.optimize.linear_sum_assignment(q) in AlloXPolicy.get_allocation
+ * (scheduler/policies/allox.py:108-144).  q is implicit: for job i and column col = k*n + j,
+ *   q[i][col] = (k+1) * p[i][wtype[j]] + t[i],  p = num_steps_remaining / throughput, t = times_since_start,
+ * m jobs, n workers (each with a type in [0, W)), m*n columns.  Output: the column assigned to every job
+ * (worker = col % n, queue position = col / n) and the optimal total cost.  Exact (shortest augmenting
+ * path, float64), like the reference's solver; optimal assignments are not unique. */
+int swb_allox_assign(swb_ctx *ctx, int32_t m, int32_t n, int32_t W, const double *p, const double *t,
+                     const int32_t *wtype, int32_t *col_of_job, double *total_cost);
+
 /* ---- Monte-Carlo (geometric Brownian motion) throughput forecast -------------------------------- *
  * New capability, no reference counterpart (the reference's forecast is the deterministic
  * JobMetaData.dirichlet_posterior_remaining_runtime, JobMetaData.py:315-370, which this reduces to when

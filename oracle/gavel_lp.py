@@ -117,3 +117,72 @@ def max_sum_throughput(thr, sf, N, costs=None):
     res = linprog(-(thr / c[None, :]).reshape(-1), A_ub=A, b_ub=b, bounds=[(0, None)] * (J * W), method="highs")
     assert res.status == 0
     return -float(res.fun), res.x.reshape(J, W)
+
+
+# ---- AlloX (scheduler/policies/allox.py:19-188) -------------------------------------------------------
+def allox_q_matrix(p, t, wtype):
+    """q[i][k*n + j] = (k+1) * p[i][wtype[j]] + t[i]   (allox.py:108-138), p = steps_remaining / throughput."""
+    p, t, wtype = np.asarray(p, float), np.asarray(t, float), np.asarray(wtype, int)
+    m, n = p.shape[0], len(wtype)
+    q_base = p[:, wtype]                                   # [m, n]
+    q = np.concatenate([(k + 1) * q_base for k in range(m)], axis=1)
+    return q + t[:, None]
+
+
+def allox_assignment(p, t, wtype):
+    """The reference's solver call (allox.py:144): scipy's Jonker-Volgenant linear_sum_assignment."""
+    from scipy.optimize import linear_sum_assignment
+    q = allox_q_matrix(p, t, wtype)
+    rows, cols = linear_sum_assignment(q)
+    return cols[np.argsort(rows)], float(q[rows, cols].sum())
+
+
+def allox_allocation(job_ids, worker_types, unflattened_throughputs, scale_factors, times_since_start,
+                     num_steps_remaining, cluster_spec, prev_allocation, alpha, assign=allox_assignment):
+    """Restatement of AlloXPolicy.get_allocation (allox.py:46-188) around a pluggable assignment solver."""
+    unalloc, already = [], []
+    for job_id in unflattened_throughputs:
+        if job_id not in prev_allocation:
+            unalloc.append(job_id)
+        else:
+            tot = 0.0
+            for w in worker_types:
+                tot += prev_allocation[job_id][w]
+            (already if tot == 1.0 else unalloc).append(job_id)
+    m = len(unalloc)
+    n = 0
+    w_of = {}
+    for w in worker_types:
+        num = cluster_spec[w]
+        for j in already:
+            if prev_allocation[j][w] == 1.0:
+                num -= 1
+        for wid in range(n, n + num):
+            w_of[wid] = w
+            n += 1
+    unalloc.sort(key=lambda x: -times_since_start[x])
+    unalloc = unalloc[: max(int(alpha * m), n)]
+    m = len(unalloc)
+    allocation = {j: {w: 0.0 for w in cluster_spec} for j in job_ids}
+    for j in job_ids:
+        if j in prev_allocation:
+            allocation[j] = dict(prev_allocation[j])
+    if m > 0 and n > 0:
+        wt_index = {w: i for i, w in enumerate(worker_types)}
+        p = np.zeros((m, len(worker_types)))
+        for i, j in enumerate(unalloc):
+            for w in worker_types:
+                thr = unflattened_throughputs[j][w]
+                p[i, wt_index[w]] = num_steps_remaining[j] / (thr if thr != 0.0 else 1e-10)
+        t = np.array([times_since_start[j] for j in unalloc], float)
+        wtype = np.array([wt_index[w_of[wid]] for wid in range(n)])
+        cols, _ = assign(p, t, wtype)
+        per_worker = {i: [] for i in range(n)}
+        for row, col in enumerate(cols):
+            per_worker[int(col) % n].append((unalloc[row], int(col) // n))
+        for wid in range(n):
+            lst = [(x[0], len(per_worker[wid]) - 1 - x[1]) for x in per_worker[wid]]
+            lst.sort(key=lambda x: x[1])
+            if lst:
+                allocation[lst[0][0]][w_of[wid]] = 1.0 / scale_factors[lst[0][0]]
+    return allocation

@@ -68,6 +68,7 @@ struct swb_ctx {
   DBuf f_slots, f_prog, f_mend, f_mns, f_remfb, f_bffb, f_ampok, f_ampfb, f_ftest, f_ncal;
   swb::ForecastLaunch last_fc;   // descriptor of the latest forecast (for the calibration commit)
   bool have_fc = false;
+  DBuf ax_p, ax_t, ax_wt, ax_u, ax_v, ax_spc, ax_c4r, ax_r4c, ax_path, ax_sc, ax_sr, ax_out;   // swb_allox_assign
   DBuf pol_coef, pol_sf, pol_t, pol_n, pol_den, pol_x, pol_out;          // swb_policy_pooled
   DBuf mc_R0, mc_mu, mc_sigma, mc_H, mc_out;                                 // swb_gbm_forecast
   DBuf m_theta, m_rowp, m_colload, m_colscale, m_price, m_obj, m_X, m_rate, m_E, m_c, m_Gw;
@@ -114,7 +115,8 @@ void swb_destroy(swb_ctx *c) {
                  &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->scth, &c->sths, &c->sn0, &c->snfc, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
                  &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc,
                  &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
-                 &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal, &c->pol_coef, &c->pol_sf, &c->pol_t,
+                 &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal, &c->ax_p, &c->ax_t, &c->ax_wt, &c->ax_u, &c->ax_v, &c->ax_spc, &c->ax_c4r, &c->ax_r4c,
+                 &c->ax_path, &c->ax_sc, &c->ax_sr, &c->ax_out, &c->pol_coef, &c->pol_sf, &c->pol_t,
                  &c->pol_n, &c->pol_den, &c->pol_x, &c->pol_out, &c->mc_R0, &c->mc_mu, &c->mc_sigma, &c->mc_H, &c->mc_out,
                  &c->m_theta, &c->m_rowp, &c->m_colload,
                  &c->m_colscale, &c->m_price, &c->m_obj, &c->m_X, &c->m_rate, &c->m_E, &c->m_c, &c->m_Gw};
@@ -634,6 +636,36 @@ int swb_set_option(swb_ctx *c, int32_t option, int32_t value) {
   if (!c) return fail(SWB_ERR_ARG, "null ctx");
   if (option == SWB_OPT_RELAXED_OPTIMUM) { c->want_relaxed = value ? 1 : 0; return 0; }
   return fail(SWB_ERR_ARG, "swb_set_option: unknown option");
+}
+
+int swb_allox_assign(swb_ctx *c, int32_t m, int32_t n, int32_t W, const double *p, const double *t,
+                     const int32_t *wtype, int32_t *col_of_job, double *total_cost) {
+  if (!c || !p || !t || !wtype || !col_of_job) return fail(SWB_ERR_ARG, "swb_allox_assign: null argument");
+  if (m <= 0 || n <= 0 || W <= 0 || (long long)m * n > (1ll << 26))
+    return fail(SWB_ERR_ARG, "swb_allox_assign: need m, n > 0 and m*n <= 2^26");
+  CK(cudaSetDevice(c->device));
+  const size_t N = (size_t)m * n;
+  CK(c->ax_p.need((size_t)m * W * 8, c->st)); CK(c->ax_t.need((size_t)m * 8, c->st));
+  CK(c->ax_wt.need((size_t)n * 4, c->st)); CK(c->ax_u.need((size_t)m * 8, c->st));
+  CK(c->ax_v.need(N * 8, c->st)); CK(c->ax_spc.need(N * 8, c->st));
+  CK(c->ax_c4r.need((size_t)m * 4, c->st)); CK(c->ax_r4c.need(N * 4, c->st)); CK(c->ax_path.need(N * 4, c->st));
+  CK(c->ax_sc.need(N, c->st)); CK(c->ax_sr.need((size_t)m, c->st)); CK(c->ax_out.need(8, c->st));
+  CK(cudaMemcpyAsync(c->ax_p.p, p, (size_t)m * W * 8, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->ax_t.p, t, (size_t)m * 8, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->ax_wt.p, wtype, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+  swb::AssignLaunch L;
+  L.m = m; L.n = n; L.W = W;
+  L.p = c->ax_p.as<double>(); L.t = c->ax_t.as<double>(); L.wtype = c->ax_wt.as<int32_t>();
+  L.u = c->ax_u.as<double>(); L.v = c->ax_v.as<double>(); L.spc = c->ax_spc.as<double>();
+  L.col4row = c->ax_c4r.as<int32_t>(); L.row4col = c->ax_r4c.as<int32_t>(); L.path = c->ax_path.as<int32_t>();
+  L.inSC = c->ax_sc.as<unsigned char>(); L.inSR = c->ax_sr.as<unsigned char>(); L.out = c->ax_out.as<double>();
+  CK(swb::launch_assign(L, c->st));
+  double tot = 0.0;
+  CK(cudaMemcpyAsync(col_of_job, L.col4row, (size_t)m * 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(&tot, L.out, 8, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  if (total_cost) *total_cost = tot;
+  return 0;
 }
 
 int swb_last_timings(swb_ctx *c, double *ms_solve, double *ms_place, int32_t *passes) {

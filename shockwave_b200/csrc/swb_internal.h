@@ -99,6 +99,18 @@ struct PolicyLaunch {
 };
 cudaError_t launch_policy(const PolicyLaunch &L, cudaStream_t st);
 
+struct AssignLaunch {
+  int m, n, W;              // jobs, workers, worker types
+  const double *p;          // [m][W] processing time of job i on a worker of type w (steps / throughput)
+  const double *t;          // [m] times_since_start
+  const int32_t *wtype;     // [n] type of worker j
+  double *u, *v, *spc;      // duals [m], [m*n]; shortest-path costs [m*n]
+  int32_t *col4row, *row4col, *path;
+  unsigned char *inSC, *inSR;
+  double *out;              // [1] total cost
+};
+cudaError_t launch_assign(const AssignLaunch &L, cudaStream_t st);
+
 #define SWB_MK_MAXW 4
 struct MarketLaunch {
   int S, J, W, T, per_scn, jobs_per_cta;

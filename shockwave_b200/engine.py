@@ -56,7 +56,7 @@ class RoundArgs(C.Structure):
 
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
            "swb_solve", "swb_job_add", "swb_job_remove", "swb_round_solve", "swb_forecast",
-           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_gbm_forecast", "swb_market_pgd", "swb_set_option"]
+           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_gbm_forecast", "swb_market_pgd", "swb_set_option", "swb_allox_assign"]
 
 _lib = None
 
@@ -256,6 +256,21 @@ class Engine:
     def set_option(self, option, value):
         self.lib.swb_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         self._check(self.lib.swb_set_option(self.h, int(option), int(value)), "swb_set_option")
+
+    def allox_assign(self, p, t, wtype):
+        """min-cost assignment of m jobs to (worker, position) columns; p [m, W], t [m], wtype [n] int."""
+        p = np.ascontiguousarray(p, dtype=np.float64); t = np.ascontiguousarray(t, dtype=np.float64)
+        wtype = np.ascontiguousarray(wtype, dtype=np.int32)
+        m, W = p.shape
+        n = len(wtype)
+        cols = np.zeros(m, dtype=np.int32)
+        tot = C.c_double()
+        self.lib.swb_allox_assign.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 4 + \
+                                             [C.POINTER(C.c_double)]
+        self.lib.swb_allox_assign.restype = C.c_int
+        self._check(self.lib.swb_allox_assign(self.h, m, n, W, _ptr(p), _ptr(t), _ptr(wtype), _ptr(cols),
+                                              C.byref(tot)), "swb_allox_assign")
+        return cols, tot.value
 
     def last_timings(self):
         a, b, n = C.c_double(), C.c_double(), C.c_int32()

@@ -309,6 +309,71 @@ class ThroughputNormalizedByCostSumWithPerf(Policy):
                                            instance_costs=instance_costs)
 
 
+class AlloXPolicy(Policy):
+    """allox.py:12-188: Hungarian-style min-cost assignment of the oldest unallocated jobs to (worker, queue
+    position) slots; the assignment itself runs on the GPU (swb_allox_assign)."""
+
+    def __init__(self, alpha=1.0):
+        self._name = "AlloX_Perf"
+        self._alpha = alpha
+        self._prev_allocation = {}
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, times_since_start, num_steps_remaining,
+                       per_round_schedule, cluster_spec):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        job_ids, worker_types = index
+        prev = self._prev_allocation
+        unalloc, already = [], []
+        for job_id in unflattened_throughputs:                      # allox.py:46-60
+            if job_id not in prev:
+                unalloc.append(job_id)
+            else:
+                total = 0.0
+                for w in worker_types:
+                    total += prev[job_id][w]
+                (already if total == 1.0 else unalloc).append(job_id)
+        m = len(unalloc)
+        n = 0
+        w_of = {}
+        for w in worker_types:                                      # allox.py:65-80
+            num = cluster_spec[w]
+            for j in already:
+                if prev[j][w] == 1.0:
+                    num -= 1
+            for wid in range(n, n + num):
+                w_of[wid] = w
+                n += 1
+        unalloc.sort(key=lambda x: -times_since_start[x])           # allox.py:101-104
+        unalloc = unalloc[: max(int(self._alpha * m), n)]
+        m = len(unalloc)
+        allocation = {j: {w: 0.0 for w in cluster_spec} for j in job_ids}
+        for j in job_ids:
+            if j in prev:
+                allocation[j] = copy.copy(prev[j])
+        if m > 0 and n > 0:
+            wt_index = {w: i for i, w in enumerate(worker_types)}
+            p = np.zeros((m, len(worker_types)))
+            for i, j in enumerate(unalloc):                          # allox.py:111-124
+                for w in worker_types:
+                    thr = unflattened_throughputs[j][w]
+                    p[i, wt_index[w]] = num_steps_remaining[j] / (thr if thr != 0.0 else 1e-10)
+            t = np.array([times_since_start[j] for j in unalloc], dtype=np.float64)
+            wtype = np.array([wt_index[w_of[wid]] for wid in range(n)], dtype=np.int32)
+            cols, self.last_objective = _engine().allox_assign(p, t, wtype)
+            per_worker = {i: [] for i in range(n)}                   # allox.py:147-163
+            for row, col in enumerate(cols):
+                per_worker[int(col) % n].append((unalloc[row], int(col) // n))
+            for wid in range(n):
+                lst = [(x[0], len(per_worker[wid]) - 1 - x[1]) for x in per_worker[wid]]
+                lst.sort(key=lambda x: x[1])
+                if lst:
+                    allocation[lst[0][0]][w_of[wid]] = 1.0 / scale_factors[lst[0][0]]
+        self._prev_allocation = copy.copy(allocation)
+        return allocation
+
+
 class ShockwavePolicy(Policy):
     """Name holder, like scheduler/policies/shockwave.py:8-10."""
     def __init__(self):
@@ -329,6 +394,8 @@ def get_policy(policy_name, solver=None, seed=None):
         "min_total_duration_perf": lambda: MinTotalDurationPolicyWithPerf(solver=solver),
         "shockwave": ShockwavePolicy,
     }
+    if policy_name.startswith("allox"):
+        return AlloXPolicy(alpha=0.2 if policy_name == "allox" else float(policy_name.split("allox_alpha=")[1]))
     if policy_name not in table:
         raise ValueError("Unknown policy!")
     return table[policy_name]()

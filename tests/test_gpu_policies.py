@@ -124,3 +124,45 @@ def test_closed_forms_and_edge_cases():
     het, sf2, spec2, _ = _instance(6, SPECS[1], seed=4, equal_columns=False)
     with pytest.raises(NotImplementedError):
         P.MaxMinFairnessPolicyWithPerf(solver=None).get_allocation(het, sf2, {j: 1.0 for j in range(6)}, spec2)
+
+
+def test_allox_assignment_and_policy(engine):
+    """AlloX: the GPU shortest-augmenting-path solver reaches the same optimal cost as the reference's
+    scipy.optimize.linear_sum_assignment on the implicit q matrix (allox.py:108-144), with a valid assignment;
+    the policy (stateful _prev_allocation) returns a valid allocation round after round."""
+    rng = np.random.default_rng(11)
+    same_alloc = total = 0
+    for trial in range(12):
+        m = int(rng.integers(1, 60)); n = int(rng.integers(1, 40)); W = int(rng.integers(1, 4))
+        p = rng.uniform(10.0, 1e5, size=(m, W)); t = rng.uniform(0.0, 1e4, size=m)
+        wtype = np.sort(rng.integers(0, W, size=n)).astype(np.int32)
+        cols, cost = engine.allox_assign(p, t, wtype)
+        ref_cols, ref_cost = gl.allox_assignment(p, t, wtype)
+        assert len(set(cols.tolist())) == m and cols.min() >= 0 and cols.max() < m * n
+        q = gl.allox_q_matrix(p, t, wtype)
+        assert abs(q[np.arange(m), cols].sum() - cost) <= 1e-9 * cost
+        assert abs(cost - ref_cost) <= 1e-9 * ref_cost, (trial, m, n, W, cost, ref_cost)
+    # policy level, three consecutive calls with jobs finishing in between
+    J, spec = 40, {"v100": 6, "p100": 4, "k80": 3}
+    thr = {j: {"v100": float(rng.uniform(5, 20)), "p100": float(rng.uniform(2, 10)), "k80": float(rng.uniform(0.5, 5))}
+           for j in range(J)}
+    sf = {j: 1 for j in range(J)}
+    tss = {j: float(rng.uniform(0, 5000)) for j in range(J)}
+    steps = {j: float(rng.uniform(1e3, 1e6)) for j in range(J)}
+    pol = P.AlloXPolicy(alpha=0.2)
+    prev = {}
+    live = list(range(J))
+    for it in range(3):
+        sub = {j: thr[j] for j in live}
+        alloc = pol.get_allocation(sub, sf, tss, steps, [], spec)
+        want = gl.allox_allocation(sorted(sub), WT, sub, sf, tss, steps, spec, prev, 0.2)
+        prev = {j: dict(v) for j, v in want.items()}
+        for w in WT:
+            assert sum(alloc[j][w] for j in live) <= spec[w] + 1e-9
+        assert all(sum(alloc[j].values()) <= 1 + 1e-9 for j in live)
+        total += 1
+        same_alloc += int(all(alloc[j] == want[j] for j in live))
+        pol._prev_allocation = {j: dict(v) for j, v in want.items()}     # keep both histories identical
+        live = [j for j in live if rng.random() > 0.2]
+    print("AlloX allocations identical to the scipy-backed restatement:", same_alloc, "/", total)
+    assert P.get_policy("allox").name == "AlloX_Perf"
