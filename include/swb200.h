@@ -58,6 +58,8 @@ typedef struct swb_result {
   int32_t m_evals;      /* makespan candidates evaluated */
   int32_t mu_iters;     /* price-bisection iterations in total */
   int32_t shortfall;    /* planned job-rounds the placement could not seat (0 = all seated) */
+  int32_t placement;    /* fallback path: leading rounds seated by the priority round-sweep (the rest by the water-filling packer); 0 otherwise */
+  int32_t reserved;
   double objective;     /* sum_j w_j plog_j/(J T) - k max_j rem_j of the RETURNED integral x */
   double welfare;       /* first term */
   double makespan;      /* max_j rem_j */

