@@ -178,6 +178,19 @@ int swb_forecast_commit(swb_ctx *ctx, int32_t J, int32_t fallback, const int32_t
 int swb_policy_pooled(swb_ctx *ctx, int32_t mode, int32_t J, double N, const double *coef, const double *sf,
                       const double *t, const double *n, const double *den, double *x, double *objective);
 
+/* ---- Gavel policies with heterogeneous worker types ------------------------------------------- *
+ * Same programs as swb_policy_pooled (MAXMIN, FTF, MTD, MAXSUM without SLOs) when the per-type throughputs of a
+ * job differ — the general case of max_min_fairness.py:53-113, finish_time_fairness.py:66-157,
+ * min_total_duration.py:55-135, max_sum_throughput.py:49-108 on a k80/p100/v100 cluster.  W <= 3 worker types,
+ * each with N[w] > 0 workers (the caller drops empty types).  a is the J x W row-major matrix named per mode in
+ * swb_policy_pooled (coef / throughput / throughput over cost); x is the J x W allocation (time fractions).
+ * Solved exactly (bisection on the scalar objective, Dantzig-Wolfe on the W capacity rows with an exact master),
+ * objective within 1e-12 relative of the LP optimum, every constraint certified.  stats (optional, int32[2]):
+ * pricing passes, feasibility checks.  Returns 0, or 1 when no feasible point was found. */
+int swb_policy_hetero(swb_ctx *ctx, int32_t mode, int32_t J, int32_t W, const double *N, const double *a,
+                      const double *sf, const double *t, const double *n, const double *den, double *x,
+                      double *objective, int32_t *stats);
+
 /* ---- AlloX min-cost assignment --------------------------------------------------------------- *
  * Replaces scipy.optimize.linear_sum_assignment(q) in AlloXPolicy.get_allocation
  * (scheduler/policies/allox.py:108-144).  q is implicit: for job i and column col = k*n + j,

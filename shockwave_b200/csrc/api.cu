@@ -70,6 +70,7 @@ struct swb_ctx {
   bool have_fc = false;
   DBuf ax_p, ax_t, ax_wt, ax_u, ax_v, ax_spc, ax_c4r, ax_r4c, ax_path, ax_sc, ax_sr, ax_out;   // swb_allox_assign
   DBuf pol_coef, pol_sf, pol_t, pol_n, pol_den, pol_x, pol_out;          // swb_policy_pooled
+  DBuf het_a, het_N, het_x;                                                 // swb_policy_hetero
   DBuf mc_R0, mc_mu, mc_sigma, mc_H, mc_out;                                 // swb_gbm_forecast
   DBuf m_theta, m_rowp, m_colload, m_colscale, m_price, m_obj, m_X, m_rate, m_E, m_c, m_Gw;
   cudaEvent_t mev[2] = {nullptr, nullptr};
@@ -522,6 +523,44 @@ int swb_policy_pooled(swb_ctx *c, int32_t mode, int32_t J, double N, const doubl
   CK(cudaMemcpyAsync(out, c->pol_out.p, 16, cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
   if (objective) *objective = out[0];
+  return out[1] != 0.0 ? 1 : 0;
+}
+
+int swb_policy_hetero(swb_ctx *c, int32_t mode, int32_t J, int32_t W, const double *N, const double *a,
+                      const double *sf, const double *t, const double *n, const double *den, double *x,
+                      double *objective, int32_t *stats) {
+  if (!c || !N || !a || !sf || !x) return fail(SWB_ERR_ARG, "swb_policy_hetero: null argument");
+  if (J <= 0 || J > SWB_MAX_J) return fail(SWB_ERR_ARG, "swb_policy_hetero: J must be in [1, 8192]");
+  if (W <= 0 || W > 3) return fail(SWB_ERR_ARG, "swb_policy_hetero: W must be in [1, 3]");
+  if (mode < SWB_POL_MAXMIN || mode > SWB_POL_MAXSUM) return fail(SWB_ERR_ARG, "swb_policy_hetero: bad mode");
+  if (mode == SWB_POL_FTF && (!t || !n || !den)) return fail(SWB_ERR_ARG, "swb_policy_hetero: FTF needs t, n, den");
+  if (mode == SWB_POL_MTD && !n) return fail(SWB_ERR_ARG, "swb_policy_hetero: MTD needs n");
+  for (int w = 0; w < W; ++w)
+    if (!(N[w] > 0.0)) return fail(SWB_ERR_ARG, "swb_policy_hetero: every worker type needs capacity > 0 (drop empty types)");
+  CK(cudaSetDevice(c->device));
+  const size_t b = (size_t)J * 8, bw = b * (size_t)W;
+  CK(c->het_a.need(bw, c->st)); CK(c->het_x.need(bw, c->st)); CK(c->het_N.need(32, c->st));
+  CK(c->pol_sf.need(b, c->st)); CK(c->pol_t.need(b, c->st));
+  CK(c->pol_n.need(b, c->st)); CK(c->pol_den.need(b, c->st));
+  CK(c->pol_out.need(32, c->st));
+  CK(cudaMemcpyAsync(c->het_a.p, a, bw, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->het_N.p, N, (size_t)W * 8, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->pol_sf.p, sf, b, cudaMemcpyHostToDevice, c->st));
+  if (t) CK(cudaMemcpyAsync(c->pol_t.p, t, b, cudaMemcpyHostToDevice, c->st));
+  if (n) CK(cudaMemcpyAsync(c->pol_n.p, n, b, cudaMemcpyHostToDevice, c->st));
+  if (den) CK(cudaMemcpyAsync(c->pol_den.p, den, b, cudaMemcpyHostToDevice, c->st));
+  swb::HeteroLaunch L;
+  L.mode = mode; L.J = J; L.W = W;
+  L.N = c->het_N.as<double>(); L.a = c->het_a.as<double>(); L.sf = c->pol_sf.as<double>();
+  L.t = c->pol_t.as<double>(); L.n = c->pol_n.as<double>(); L.den = c->pol_den.as<double>();
+  L.x = c->het_x.as<double>(); L.out = c->pol_out.as<double>();
+  CK(swb::launch_hetero(L, c->st));
+  double out[4] = {0.0, 0.0, 0.0, 0.0};
+  CK(cudaMemcpyAsync(x, c->het_x.p, bw, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(out, c->pol_out.p, 32, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  if (objective) *objective = out[0];
+  if (stats) { stats[0] = (int32_t)out[2]; stats[1] = (int32_t)out[3]; }
   return out[1] != 0.0 ? 1 : 0;
 }
 

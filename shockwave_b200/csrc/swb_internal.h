@@ -99,6 +99,17 @@ struct PolicyLaunch {
 };
 cudaError_t launch_policy(const PolicyLaunch &L, cudaStream_t st);
 
+struct HeteroLaunch {
+  int mode, J, W;           // SWB_POL_MAXMIN / FTF / MTD / MAXSUM, jobs, worker types (<= 3)
+  const double *N;          // [W] workers per type (device)
+  const double *a;          // [J][W] MAXMIN: objective coefficients ; FTF/MTD: throughputs ; MAXSUM: thr/cost
+  const double *sf;         // [J] scale factors
+  const double *t, *n, *den;// as in PolicyLaunch
+  double *x;                // [J][W] out
+  double *out;              // [4] out: objective, status, pricing passes, feasibility checks
+};
+cudaError_t launch_hetero(const HeteroLaunch &L, cudaStream_t st);
+
 struct AssignLaunch {
   int m, n, W;              // jobs, workers, worker types
   const double *p;          // [m][W] processing time of job i on a worker of type w (steps / throughput)

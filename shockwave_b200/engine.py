@@ -57,7 +57,7 @@ class RoundArgs(C.Structure):
 
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
            "swb_solve", "swb_job_add", "swb_job_remove", "swb_round_solve", "swb_forecast",
-           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_gbm_forecast", "swb_market_pgd", "swb_set_option", "swb_allox_assign"]
+           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_policy_hetero", "swb_gbm_forecast", "swb_market_pgd", "swb_set_option", "swb_allox_assign"]
 
 _lib = None
 

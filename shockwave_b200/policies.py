@@ -5,11 +5,13 @@ max_sum_throughput,isolated,proportional,gandiva_fair_proportional}.py: same cla
 strings (scheduler.py:3291-3355 dispatches on their prefixes), same positional arguments, same
 `{job_id: {worker_type: fraction}}` return value and `None` for an empty job set (policy.py:31-32).
 
-The LP each policy hands to cvxpy is solved by swb_policy_pooled (policy.cu).  That kernel covers the
-case where all worker types WITH capacity give a job the same throughput — always true for the
-non-Perf classes (they overwrite the matrix with the v100 column, or with 1.0) and for the
-homogeneous clusters Shockwave targets.  A genuinely heterogeneous *_Perf call raises
-NotImplementedError (no CPU fallback).
+The LP each policy hands to cvxpy is solved on the GPU (no CPU fallback):
+  * swb_policy_pooled (policy.cu) when all worker types WITH capacity give a job the same throughput — always
+    true for the non-Perf classes (they overwrite the matrix with the v100 column, or with 1.0) and for the
+    homogeneous clusters Shockwave targets: closed forms / 1-D searches;
+  * swb_policy_hetero (hetero.cu) for genuinely heterogeneous *_Perf calls with up to 3 worker types that have
+    capacity (k80 / p100 / v100): bisection on the scalar objective + Dantzig-Wolfe on the capacity rows.
+More than 3 live worker types, and SLO rows, raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -52,6 +54,32 @@ def _pooled(mode, N, coef, sf, t=None, n=None, den=None):
     return x, obj.value, rc
 
 
+def _hetero(mode, N, a, sf, t=None, n=None, den=None):
+    """swb_policy_hetero on the live worker types: a is J x W, N has W entries > 0.  Returns (x[J,W], objective, rc)."""
+    eng = _engine()
+    lib = eng.lib
+    if not getattr(lib, "_het_bound", False):
+        lib.swb_policy_hetero.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7 + \
+                                         [C.POINTER(C.c_double), C.c_void_p]
+        lib.swb_policy_hetero.restype = C.c_int
+        lib._het_bound = True
+    arr = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+    a, sf, t, n, den, N = arr(a), arr(sf), arr(t), arr(n), arr(den), arr(N)
+    J, W = a.shape
+    if W > 3:
+        raise NotImplementedError("more than 3 worker types with capacity: not solved on the GPU in this release")
+    x = np.zeros((J, W), dtype=np.float64)
+    obj = C.c_double()
+    stats = np.zeros(2, dtype=np.int32)
+    p = lambda v: None if v is None else C.c_void_p(v.ctypes.data)
+    rc = lib.swb_policy_hetero(eng.h, mode, J, W, p(N), p(a), p(sf), p(t), p(n), p(den), p(x), C.byref(obj),
+                               p(stats))
+    if rc < 0:
+        raise RuntimeError(f"swb_policy_hetero failed ({rc}): {lib.swb_last_error().decode()}")
+    _hetero.last_stats = (int(stats[0]), int(stats[1]))
+    return x, obj.value, rc
+
+
 class Policy:
     """policy.py:11-65."""
     def __init__(self, solver="ECOS"):
@@ -86,10 +114,17 @@ class Policy:
             raise ValueError("cluster has no workers")
         cols = throughputs[:, live]
         if not np.allclose(cols, cols[:, :1], rtol=1e-12, atol=0.0):
-            raise NotImplementedError(
-                "heterogeneous per-type throughputs: only pooled (homogeneous) clusters are solved on the GPU "
-                "in this release; there is no CPU fallback")
+            return None, float(N.sum()), N / N.sum()       # heterogeneous: the caller goes through _solve_hetero
         return cols[:, 0].copy(), float(N.sum()), N / N.sum()
+
+    def _solve_hetero(self, mode, a, sf, t=None, n=None, den=None):
+        """a: J x W matrix over ALL worker types; types without capacity get x = 0."""
+        N = np.asarray(self._num_workers, dtype=np.float64)
+        live = N > 0
+        x_live, obj, rc = _hetero(mode, N[live], a[:, live], sf, t=t, n=n, den=den)
+        x = np.zeros_like(a, dtype=np.float64)
+        x[:, live] = x_live
+        return np.clip(x, 0.0, 1.0), obj, rc
 
     @staticmethod
     def _split(x, share):
@@ -157,6 +192,12 @@ class MaxMinFairnessPolicyWithPerf(Policy):
         thr, N, share = self._pool(throughputs)
         sf = np.array([scale_factors[j] for j in job_ids], dtype=np.float64)
         pw = np.array([1.0 / unflattened_priority_weights[j] for j in job_ids], dtype=np.float64)
+        if thr is None:
+            # proportional.py:20-43: x_jw = N_w / sum N for every job -> proportional throughput sum_w thr_jw N_w / sum N
+            prop = throughputs @ share
+            coef = throughputs * (pw / prop * sf)[:, None]          # max_min_fairness.py:78-101
+            x, self.last_objective, _ = self._solve_hetero(POL_MAXMIN, coef, sf)
+            return super().unflatten(x, index)
         # proportional throughput of a pooled job is its own throughput (proportional.py:36-43), so the
         # objective coefficient thr*sf*pw/prop (max_min_fairness.py:78-101) collapses to sf*pw
         coef = thr * sf * pw / thr
@@ -209,12 +250,16 @@ class FinishTimeFairnessPolicyWithPerf(Policy):
         n = np.array([num_steps_remaining[j] for j in job_ids], dtype=np.float64)
         t = np.array([times_since_start[j] for j in job_ids], dtype=np.float64)
         den = np.array([self._cumulative_isolated_time[j] for j in job_ids], dtype=np.float64) + n / iso
-        x, self.last_objective, rc = _pooled(POL_FTF, N, thr, sf, t=t, n=n, den=den)
+        if thr is None:
+            x2, self.last_objective, rc = self._solve_hetero(POL_FTF, throughputs, sf, t=t, n=n, den=den)
+        else:
+            x, self.last_objective, rc = _pooled(POL_FTF, N, thr, sf, t=t, n=n, den=den)
+            x2 = self._split(x, share)
         self._num_steps_remaining_prev_iteration = copy.copy(num_steps_remaining)
         self._isolated_throughputs_prev_iteration = {j: iso[i] for i, j in enumerate(job_ids)}
         if rc != 0:     # "x.value is None" -> isolated allocation (finish_time_fairness.py:147-151)
             return self._isolated_policy.get_allocation(unflattened_throughputs, scale_factors, cluster_spec)
-        return super().unflatten(self._split(x, share), index)
+        return super().unflatten(x2, index)
 
 
 class FinishTimeFairnessPolicy(Policy):
@@ -246,9 +291,13 @@ class MinTotalDurationPolicyWithPerf(Policy):
         thr, N, share = self._pool(throughputs)
         sf = np.array([scale_factors[j] for j in job_ids], dtype=np.float64)
         n = np.array([num_steps_remaining[j] for j in job_ids], dtype=np.float64)
-        x, self.last_objective, rc = _pooled(POL_MTD, N, thr, sf, n=n)
+        if thr is None:
+            x2, self.last_objective, rc = self._solve_hetero(POL_MTD, throughputs, sf, n=n)
+        else:
+            x, self.last_objective, rc = _pooled(POL_MTD, N, thr, sf, n=n)
+            x2 = self._split(x, share)
         assert rc == 0          # min_total_duration.py:132 `assert last_feasible_x is not None`
-        return super().unflatten(self._split(x, share), index)
+        return super().unflatten(x2, index)
 
 
 class MinTotalDurationPolicy(Policy):
@@ -281,12 +330,14 @@ class ThroughputNormalizedByCostSumWithPerfSLOs(Policy):
         job_ids, worker_types = index
         thr, N, share = self._pool(throughputs)
         sf = np.array([scale_factors[j] for j in job_ids], dtype=np.float64)
+        cost = np.ones(len(worker_types))
         if instance_costs is not None:
-            c = np.array([instance_costs[w] for w in worker_types], dtype=np.float64)[np.asarray(self._num_workers) > 0]
-            if not np.allclose(c, c[0]):
-                raise NotImplementedError("per-type instance costs differ: heterogeneous LP not on the GPU yet")
-            thr = thr / c[0]
-        x, self.last_objective, _ = _pooled(POL_MAXSUM, N, thr, sf)
+            cost = np.array([instance_costs[w] for w in worker_types], dtype=np.float64)
+        live_cost = cost[np.asarray(self._num_workers) > 0]
+        if thr is None or not np.allclose(live_cost, live_cost[0]):
+            x, self.last_objective, _ = self._solve_hetero(POL_MAXSUM, throughputs / cost[None, :], sf)
+            return super().unflatten(x, index)
+        x, self.last_objective, _ = _pooled(POL_MAXSUM, N, thr / live_cost[0], sf)
         return super().unflatten(self._split(x, share), index)
 
 

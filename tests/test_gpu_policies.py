@@ -122,8 +122,9 @@ def test_closed_forms_and_edge_cases():
     assert P.get_policy("finish_time_fairness").name.startswith("FinishTimeFairness")
     assert P.get_policy("shockwave").name == "shockwave"
     het, sf2, spec2, _ = _instance(6, SPECS[1], seed=4, equal_columns=False)
-    with pytest.raises(NotImplementedError):
-        P.MaxMinFairnessPolicyWithPerf(solver=None).get_allocation(het, sf2, {j: 1.0 for j in range(6)}, spec2)
+    with pytest.raises(NotImplementedError):      # SLO rows are not on the GPU
+        P.ThroughputNormalizedByCostSumWithPerfSLOs(solver=None).get_allocation(
+            het, sf2, spec2, SLOs={0: 100.0}, num_steps_remaining={0: 10.0})
 
 
 def test_allox_assignment_and_policy(engine):
