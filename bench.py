@@ -338,6 +338,33 @@ def main():
     dense_bytes = 8.0 * Sd * J * Wd * T + Sd * (24.0 * J + 8.0 * Wd * T)
     del Xd
 
+    # ---- config E (J=2048 policy sweep): Gavel get_allocation() latency, W=1 (pooled) and W=3 (heterogeneous) ----
+    pol_ms = {}
+    if rank == 0:
+        from shockwave_b200 import policies as GP
+        GP._shared_engine = eng
+        rngp = np.random.default_rng(7)
+        JE = 2048
+        mE = rngp.uniform(0.5, 20.0, size=(JE, 1)) * np.sort(rngp.uniform(0.1, 1.0, size=(JE, 3)), axis=1)
+        wts = ["k80", "p100", "v100"]
+        thr3 = {j: {w: float(mE[j, i]) for i, w in enumerate(wts)} for j in range(JE)}
+        thr1 = {j: {w: float(mE[j, 2]) for w in wts} for j in range(JE)}
+        sfE = {j: int(rngp.choice([1, 2, 4, 8], p=[0.6, 0.3, 0.09, 0.01])) for j in range(JE)}
+        prE = {j: 1.0 for j in range(JE)}
+        stE = {j: float(rngp.uniform(1e4, 1e6)) for j in range(JE)}
+        tE = {j: float(rngp.uniform(0, 5e3)) for j in range(JE)}
+        for tag, thr_, spec_ in (("W1", thr1, {"k80": 0, "p100": 0, "v100": 512}),
+                                 ("W3", thr3, {"k80": 256, "p100": 128, "v100": 128})):
+            for name, call in (
+                    ("max_min_fairness_perf", lambda: GP.MaxMinFairnessPolicyWithPerf("ECOS").get_allocation(thr_, sfE, prE, spec_)),
+                    ("finish_time_fairness_perf", lambda: GP.FinishTimeFairnessPolicyWithPerf("GUROBI").get_allocation(
+                        thr_, sfE, prE, tE, stE, spec_))):
+                call()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    call()
+                pol_ms[f"{name}_{tag}"] = (time.perf_counter() - t0) / 3 * 1e3
+
     if rank != 0:
         return
     clocks = sampler.summary()
@@ -372,6 +399,7 @@ def main():
         "config": {"workload": "BASELINE config D: 4096 jobs x 512 GPUs x 64-round window",
                    "scenarios_per_gpu_per_step": S, "k_sweep": K_SWEEP, "fallback_scenarios": nfallback,
                    "latency_ms_S1": lat_ms, "latency_kernels_ms_S1": lat_k,
+                   "gavel_get_allocation_ms_J2048": pol_ms,   # config E: dict in -> dict out, host packing included
                    "round_schedule_ms": rs_ms,   # ShockwaveScheduler.round_schedule(): host packing + forecast + solve + lists
                    "mc_forecast": {"paths_per_job": P_MC, "paths_this_rank": mc_n, "horizon_epochs": "min(E-c, 256)",
                                    "kernel_ms": mc_ms, "allreduce": "NCCL SUM of [2][J] float64 (64 KiB)" if world > 1 else "none (1 GPU)"},
@@ -381,18 +409,29 @@ def main():
         "gpu_launches": launches,
         "kernels_ms": {"solve_kernel": ms_solve, "place_kernel": ms_place, "gbm_kernel": mc_ms},
         "e2e": {"value": e2e_val, "unit": "rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
-                     "note": bound_note + "; the HBM-bound kernel of this repo is the dense pass in roofline_dense; "
-                             "peak = MEASURED_PEAKS.json hbm_gbs" + ("" if peaks else " (fallback 6650)")},
+        # the bounding roofline of this path is HBM bandwidth of the dense PR-dynamics kernel in its
+        # scenario-batched form; the Monte-Carlo / search kernels of the timed step are ALU- and issue-bound and are
+        # listed with those bounds in step_kernels (never against HBM).
+        "roofline": {
+            "bound": "hbm", "kernel": "market_step_kernel<1,4> (dense PR-dynamics pass over X[S][J][W][T], fp32)",
+            "achieved": dense_bytes / (dense_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": dense_bytes / (dense_ms * 1e-3) / 1e9 / peak,
+            "traffic": 1031965952,      # dram__bytes_read+write per launch, profiles/ncu_summary_r01.txt (ncu --set full)
+            "algorithmic_bytes_per_launch": dense_bytes, "shape": [Sd, J, Wd, T], "ms_per_launch": dense_ms,
+            "note": "kernel designated by SURVEY.md §8(d); algorithmic bytes = 8*S*J*W*T + S*(24*J + 8*W*T); tensor "
+                    "(512 MiB) larger than L2; timed live in this run with CUDA events on the launching stream around "
+                    "each pass of an 8-iteration run, in its own leg (the collapsed Shockwave solve of the timed step "
+                    "never materialises X, DESIGN.md §2); peak = MEASURED_PEAKS.json hbm_gbs"
+                    + ("" if peaks else " (fallback 6650)")},
+        "step_kernels": [
+            {"kernel": "gbm_kernel", "ms": mc_ms, "bound": "alu/sfu",
+             "evidence": "86 % issue-active, 75 % SM throughput (profiles/ncu_summary_r01.txt); 28 B in / 16 B out per job"},
+            {"kernel": "solve_kernel", "ms": ms_solve, "bound": "instruction issue",
+             "evidence": "77-79 % issue-active; per-job scalars staged once in shared memory, 27 MB DRAM per launch"},
+            {"kernel": "place_kernel", "ms": ms_place, "bound": "latency (sorts, scans and a sequential packer in shared memory)",
+             "evidence": "42 % issue-active, 72 MB DRAM per launch (the J x T byte matrices it writes)"}],
+        "step_dominant_kernel": {"kernel": dom, "hbm_gbs": achieved, "note": bound_note},
     }
-    line["roofline_dense"] = {
-        "bound": "hbm", "kernel": "market_step_kernel<1,4> (dense PR-dynamics pass over X[S][J][W][T], fp32)",
-        "achieved": dense_bytes / (dense_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-        "frac": dense_bytes / (dense_ms * 1e-3) / 1e9 / peak, "traffic": None,
-        "shape": [Sd, J, Wd, T], "ms_per_pass": dense_ms,
-        "note": "algorithmic bytes = 8*S*J*W*T + S*(24*J + 8*W*T) (SURVEY.md §8d); the tensor (512 MiB) is larger "
-                "than L2; CUDA events around one dense pass inside a run of 8 iterations"}
     if world == 1 and not args.no_cpu_baseline:
         from oracle import shockwave_milp as om
         from tests.synth import synth_problem
