@@ -23,6 +23,70 @@ __device__ __forceinline__ unsigned long long pol_order_key(double v) {
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
+// ---- which optimal x: the interior-point selection -------------------------------------------------------
+// These LPs are degenerate in x.  The reference solves them with interior-point codes (ECOS; Gurobi barrier for the
+// finish-time-fairness cone program, utils.py:603-685) whose iterates converge to the ANALYTIC CENTRE of the optimal
+// face, and the closed loop is sensitive to that choice (a simplex vertex with the same objective moves the avg JCT of
+// the canonical trace by 6 %; the centre reproduces the golden pickles within 0.8 %, tests/golden/tacc32_policy_pins.json).
+// Pooled form (definition and numpy restatement: oracle/gavel_lp.py:analytic_centre_box):
+//     maximise  sum_j [ w_lo log(x_j - lo_j) + w_x log x_j + log(1 - x_j) ] + log(N - sum_j sf_j x_j)
+// On entry L.x holds lo_j (the job's requirement at the optimal scalar); on exit the centre.  Stationarity gives
+// x_j(lam) as the root of a decreasing function (safeguarded Newton per job) and lam (N - sum sf x(lam)) = 1, which is
+// monotone in lam (log-space bisection, one block reduction per step).
+#define POL_MAXJ_PER_THREAD 8
+__device__ void analytic_centre_box(const PolicyLaunch &L, BlockRed &br, double w_lo, double w_x) {
+  const int J = L.J;
+  const double N = L.N;
+  double lo[POL_MAXJ_PER_THREAD], xs[POL_MAXJ_PER_THREAD], sfj[POL_MAXJ_PER_THREAD];
+  double used0 = 0.0, usedfix = 0.0;
+  int cnt = 0;
+  for (int j = threadIdx.x; j < J; j += blockDim.x, ++cnt) {
+    const double l = fmin(L.x[j], 1.0);
+    sfj[cnt] = L.sf[j];
+    const bool fixed = l >= 1.0 - 1e-15;
+    lo[cnt] = fixed ? 2.0 : fmax(l, 0.0);            // 2.0 marks "fixed at 1"
+    xs[cnt] = fixed ? 1.0 : fmax(l, 0.0);
+    used0 += sfj[cnt] * xs[cnt];
+    if (fixed) usedfix += sfj[cnt];
+  }
+  br.sum2(used0, usedfix);
+  if (N - used0 <= 1e-12 * N) {                       // capacity is active on the whole face: x = lo is the only point
+    cnt = 0;
+    for (int j = threadIdx.x; j < J; j += blockDim.x, ++cnt) L.x[j] = xs[cnt];
+    return;
+  }
+  const double Nf = N - usedfix;
+  for (int q = 0; q < cnt; ++q) if (lo[q] < 2.0) xs[q] = 0.5 * (lo[q] + 1.0);
+  double a = 1e-12, b = 1e15;
+  for (int it = 0; it < 64; ++it) {
+    const double lam = sqrt(a * b);
+    double load = 0.0;
+    for (int q = 0; q < cnt; ++q) {
+      if (lo[q] >= 2.0) continue;
+      const double l0 = lo[q], ls = lam * sfj[q];
+      double l = l0, h = 1.0, x = xs[q];
+      for (int k = 0; k < 60; ++k) {
+        const double d0 = x - l0, d1 = 1.0 - x;
+        const double f = w_x / x - 1.0 / d1 + w_lo / d0 - ls;
+        if (f > 0.0) l = x; else h = x;
+        const double fp = w_x / (x * x) + 1.0 / (d1 * d1) + w_lo / (d0 * d0);    // = -f'
+        double xn = x + f / fp;
+        if (!(xn > l && xn < h)) xn = 0.5 * (l + h);
+        const bool done = fabs(xn - x) <= 4e-16 * xn;
+        x = xn;
+        if (done) break;
+      }
+      xs[q] = x;
+      load += sfj[q] * x;
+    }
+    load = br.sum(load);
+    const double sl = Nf - load;
+    if (sl > 0.0 && lam * sl > 1.0) b = lam; else a = lam;
+  }
+  cnt = 0;
+  for (int j = threadIdx.x; j < J; j += blockDim.x, ++cnt) L.x[j] = xs[cnt];
+}
+
 __global__ void __launch_bounds__(1024, 1) policy_kernel(PolicyLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *red = reinterpret_cast<double *>(smem_raw);
@@ -44,6 +108,8 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(PolicyLaunch L) {
     s = br.sum(s);
     const double z = fmin(mn, N / s);
     for (int j = threadIdx.x; j < J; j += blockDim.x) L.x[j] = fmin(1.0, z / L.coef[j]);
+    __syncthreads();
+    analytic_centre_box(L, br, 1.0, 1.0);
     obj = z;
   } else if (L.mode == SWB_POL_FTF) {
     // min rho : (t_j + n_j/(thr_j x_j)) / den_j <= rho   ->  x_j(rho) = n_j / (thr_j (rho den_j - t_j))
@@ -70,6 +136,9 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(PolicyLaunch L) {
       if (feasible(mid, false)) hi = mid; else lo = mid;
     }
     feasible(hi, true);
+    __syncthreads();
+    // cone program: t_j + n_j inv_pos(thr_j x_j) <= rho den_j -> barrier 2 log(x - lo) - log x, see gavel_lp.py
+    if (status == 0) analytic_centre_box(L, br, 2.0, 0.0);
     obj = hi;
   } else if (L.mode == SWB_POL_MTD) {
     // the reference's own bisection on T (min_total_duration.py:105-131), LP feasibility in closed form
@@ -96,6 +165,8 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(PolicyLaunch L) {
     }
     if (best < 0.0) { status = 1; best = max_T; }
     feasible(best, true);
+    __syncthreads();
+    if (status == 0) analytic_centre_box(L, br, 1.0, 1.0);
     obj = best;
   } else if (L.mode == SWB_POL_MAXSUM) {
     // max sum_j v_j x_j : fractional knapsack by v_j/sf_j (coef = v_j), stable by job index
@@ -103,7 +174,6 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(PolicyLaunch L) {
     while (npad < J) npad <<= 1;
     unsigned long long *key = reinterpret_cast<unsigned long long *>(smem_raw + 2 * 64 * sizeof(double));
     unsigned short *idx = reinterpret_cast<unsigned short *>(key + npad);
-    double *pref = reinterpret_cast<double *>(idx + npad);
     for (int i = threadIdx.x; i < npad; i += blockDim.x) {
       key[i] = i < J ? pol_order_key(L.coef[i] / L.sf[i]) : 0ull;
       idx[i] = (unsigned short)(i < J ? i : 0xffff);
@@ -122,22 +192,60 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(PolicyLaunch L) {
         }
         __syncthreads();
       }
-    // sequential prefix in sorted order (J <= 8192; one thread, the sums must be order-exact)
+    // jobs strictly above the threshold ratio get x = 1, below 0; the group TIED at the threshold shares what is
+    // left: interior-point selection = max sum log x + log(1-x) s.t. sum sf x = C over the group
+    // (oracle/gavel_lp.py:max_sum_pooled_centre).  One thread finds the group (order-exact sums).
+    __shared__ int s_i0, s_i1;
+    __shared__ double s_C, s_tot;
     if (threadIdx.x == 0) {
       double used = 0.0, tot = 0.0;
-      for (int i = 0; i < J; ++i) {
-        const int j = idx[i];
-        const double room = N - used;
-        double xj = 0.0;
-        if (room > 0.0 && L.coef[j] > 0.0) xj = fmin(1.0, room / L.sf[j]);
-        used += xj * L.sf[j];
-        tot += xj * L.coef[j];
-        L.x[j] = xj;
+      int i = 0, g0 = J, g1 = J;
+      double C = 0.0;
+      while (i < J) {
+        const int i0 = i;
+        const double r = L.coef[idx[i]] / L.sf[idx[i]];
+        double need = 0.0, val = 0.0;
+        while (i < J) {
+          const int j = idx[i];
+          const double rj = L.coef[j] / L.sf[j];
+          if (fabs(rj - r) > 1e-12 * fabs(r)) break;
+          need += L.sf[j]; val += L.coef[j];
+          ++i;
+        }
+        if (!(r > 0.0)) { g0 = g1 = i0; break; }
+        if (used + need <= N) { used += need; tot += val; g0 = g1 = i; }
+        else { g0 = i0; g1 = i; C = N - used; break; }
       }
-      pref[0] = tot;
+      s_i0 = g0; s_i1 = g1; s_C = C; s_tot = tot;
     }
     __syncthreads();
-    obj = pref[0];
+    const int i0 = s_i0, i1 = s_i1;
+    const double C = s_C;
+    for (int i = threadIdx.x; i < J; i += blockDim.x) L.x[idx[i]] = i < i0 ? 1.0 : 0.0;
+    double part = 0.0;
+    if (i1 > i0 && C > 1e-12 * N) {
+      double lo = -1e12, hi = 1e12;
+      for (int it = 0; it < 130; ++it) {
+        const double nu = 0.5 * (lo + hi);
+        double load = 0.0;
+        for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+          const double a = nu * L.sf[idx[i]];
+          load += L.sf[idx[i]] * (2.0 / ((a + 2.0) + sqrt(a * a + 4.0)));
+        }
+        load = br.sum(load);
+        if (load > C) lo = nu; else hi = nu;
+      }
+      const double nu = 0.5 * (lo + hi);
+      for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const int j = idx[i];
+        const double a = nu * L.sf[j];
+        const double xj = 2.0 / ((a + 2.0) + sqrt(a * a + 4.0));
+        L.x[j] = xj;
+        part += xj * L.coef[j];
+      }
+    }
+    part = br.sum(part);
+    obj = s_tot + part;
   } else if (L.mode == SWB_POL_ISOLATED) {
     // isolated.py:35-55 / proportional.py:26-43 / gandiva_fair_proportional.py:26-41 (pooled):
     // coef_j carries the per-job divisor (sf_j for Isolated, 1 otherwise); rows are normalised to <= 1

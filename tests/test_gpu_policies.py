@@ -167,3 +167,29 @@ def test_allox_assignment_and_policy(engine):
         live = [j for j in live if rng.random() > 0.2]
     print("AlloX allocations identical to the scipy-backed restatement:", same_alloc, "/", total)
     assert P.get_policy("allox").name == "AlloX_Perf"
+
+
+@pytest.mark.parametrize("J,N,kinds", [(12, 32.0, 0), (120, 32.0, 0), (60, 48.0, 3), (700, 512.0, 0), (2048, 512.0, 21), (3000, 300.0, 6)])
+def test_pooled_selection_is_the_analytic_centre(J, N, kinds):
+    """Which optimal x: the interior-point selection of the reference's solvers (oracle/gavel_lp.py, pinned closed-loop
+    in tests/golden/tacc32_policy_pins.json).  policy.cu against the numpy restatement, every mode, to 1e-6; the
+    objective against the HiGHS LP to 1e-7."""
+    from oracle import gavel_backend as gb
+    rng = np.random.default_rng(J)
+    thr = rng.uniform(0.5, 20.0, J) if not kinds else rng.uniform(0.5, 20.0, kinds)[rng.integers(0, kinds, J)]
+    sf = rng.choice([1.0, 2.0, 4.0, 8.0], J, p=[0.6, 0.3, 0.09, 0.01])
+    pw = rng.choice([1.0, 2.0, 5.0], J)
+    n = rng.uniform(1e4, 1e6, J)
+    t = rng.uniform(0, 5e3, J)
+    iso = thr * np.minimum(1.0, (N / J) / sf)
+    den = rng.uniform(0, 2e3, J) + n / iso
+    cases = [(P.POL_MAXMIN, dict(coef=sf / pw)), (P.POL_FTF, dict(coef=thr, t=t, n=n, den=den)),
+             (P.POL_MTD, dict(coef=thr, n=n)), (P.POL_MAXSUM, dict(coef=thr))]
+    for mode, kw in cases:
+        coef = kw.pop("coef")
+        x, obj, rc = P._pooled(mode, N, coef, sf, **kw)
+        xo, oo, rco = gb.pooled_cpu(mode, N, coef, sf, **kw)
+        assert rc == rco == 0
+        assert abs(obj - oo) <= 1e-7 * abs(oo), (mode, obj, oo)      # HiGHS' own feasibility tolerance is 1e-7
+        assert np.abs(x - xo).max() <= 1e-6, (mode, np.abs(x - xo).max())
+        assert x.min() >= 0 and x.max() <= 1 + 1e-12 and (sf * x).sum() <= N * (1 + 1e-9)
