@@ -427,9 +427,9 @@ def main():
             {"kernel": "gbm_kernel", "ms": mc_ms, "bound": "alu/sfu",
              "evidence": "86 % issue-active, 75 % SM throughput (profiles/ncu_summary_r01.txt); 28 B in / 16 B out per job"},
             {"kernel": "solve_kernel", "ms": ms_solve, "bound": "instruction issue",
-             "evidence": "77-79 % issue-active; per-job scalars staged once in shared memory, 27 MB DRAM per launch"},
+             "evidence": "77 % issue-active, 59 % SM throughput; per-job scalars staged once in shared memory, 76 MB DRAM per launch"},
             {"kernel": "place_kernel", "ms": ms_place, "bound": "latency (sorts, scans and a sequential packer in shared memory)",
-             "evidence": "42 % issue-active, 72 MB DRAM per launch (the J x T byte matrices it writes)"}],
+             "evidence": "44 % issue-active, 202 MB DRAM per launch (145 MB of it the J x T byte matrices it writes)"}],
         "step_dominant_kernel": {"kernel": dom, "hbm_gbs": achieved, "note": bound_note},
     }
     if world == 1 and not args.no_cpu_baseline:

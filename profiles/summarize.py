@@ -33,5 +33,46 @@ def main(tag):
     print("\n".join(out))
 
 
+
+
+def shares(tag, csv_path=None):
+    """Per-kernel totals of the ncu launch list (gpu__time_duration.sum per launch), and the shares of the three
+    kernels of the TIMED STEP (their batched launches: grid > 1) — the other kernels belong to the bench's side legs
+    (S=1 latency probes, dense-market roofline leg, Gavel-policy latency)."""
+    csv_path = csv_path or f"gpurun_out/launches_{tag}.csv"
+    rows = [r for r in csv.reader(open(csv_path)) if len(r) > 5]
+    hdr = next(r for r in rows if "Kernel Name" in r)
+    ki, vi, mi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name"), hdr.index("Grid Size")
+    tot, step = {}, {}
+    for r in rows:
+        if r is hdr or len(r) <= vi or r[mi] != "gpu__time_duration.sum":
+            continue
+        name = r[ki].split("(")[0]
+        ms = float(r[vi].replace(",", "")) / 1e6          # ns -> ms
+        t = tot.setdefault(name, [0, 0.0])
+        t[0] += 1
+        t[1] += ms
+        grid = int(r[gi].strip("()").split(",")[0])
+        if grid > 1 and any(k in name for k in ("solve_kernel", "place_kernel", "gbm_kernel")):
+            u = step.setdefault(name, [0, 0.0])
+            u[0] += 1
+            u[1] += ms
+    total = sum(v[1] for v in tot.values())
+    lines = ["ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (cold-cache, serialised: compare SHARES)",
+             "", "-- kernels of the timed step (batched launches, mean per launch; share of the step) --"]
+    smean = {k: v[1] / v[0] for k, v in step.items()}
+    ssum = sum(smean.values())
+    for name, ms in sorted(smean.items(), key=lambda kv: -kv[1]):
+        lines.append(f"{name:<70s} n={step[name][0]:3d} mean_ms={ms:9.3f} share={ms / ssum:6.3f}")
+    lines += ["", "-- every launch of the command (side legs included) --"]
+    for name, (n, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"{name:<70s} n={n:3d} total_ms={ms:9.3f} share={ms / total:6.3f}")
+    open(f"profiles/launch_shares_{tag}.txt", "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "r01")
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    main(tag)
+    if os.path.exists(f"gpurun_out/launches_{tag}.csv"):
+        shares(tag)
