@@ -542,7 +542,7 @@ int swb_policy_hetero(swb_ctx *c, int32_t mode, int32_t J, int32_t W, const doub
   CK(c->het_a.need(bw, c->st)); CK(c->het_x.need(bw, c->st)); CK(c->het_N.need(32, c->st));
   CK(c->pol_sf.need(b, c->st)); CK(c->pol_t.need(b, c->st));
   CK(c->pol_n.need(b, c->st)); CK(c->pol_den.need(b, c->st));
-  CK(c->pol_out.need(32, c->st));
+  CK(c->pol_out.need(128, c->st));
   CK(cudaMemcpyAsync(c->het_a.p, a, bw, cudaMemcpyHostToDevice, c->st));
   CK(cudaMemcpyAsync(c->het_N.p, N, (size_t)W * 8, cudaMemcpyHostToDevice, c->st));
   CK(cudaMemcpyAsync(c->pol_sf.p, sf, b, cudaMemcpyHostToDevice, c->st));
@@ -555,12 +555,17 @@ int swb_policy_hetero(swb_ctx *c, int32_t mode, int32_t J, int32_t W, const doub
   L.t = c->pol_t.as<double>(); L.n = c->pol_n.as<double>(); L.den = c->pol_den.as<double>();
   L.x = c->het_x.as<double>(); L.out = c->pol_out.as<double>();
   CK(swb::launch_hetero(L, c->st));
-  double out[4] = {0.0, 0.0, 0.0, 0.0};
+  double out[16] = {0.0};
   CK(cudaMemcpyAsync(x, c->het_x.p, bw, cudaMemcpyDeviceToHost, c->st));
-  CK(cudaMemcpyAsync(out, c->pol_out.p, 32, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(out, c->pol_out.p, 128, cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
   if (objective) *objective = out[0];
   if (stats) { stats[0] = (int32_t)out[2]; stats[1] = (int32_t)out[3]; }
+  if (getenv("SWB_HETERO_DEBUG")) {
+    fprintf(stderr, "hetero dbg:");
+    for (int i = 4; i < 16; ++i) fprintf(stderr, " %.17g", out[i]);
+    fprintf(stderr, "\n");
+  }
   return out[1] != 0.0 ? 1 : 0;
 }
 

@@ -55,6 +55,7 @@ struct HtShared {
   int tK;
   double red[2][32][HT_MAXR + 2];
   double candv[32];
+  double dbg[12];                // reason counters of the infeasibility claims (diagnostics)
   int candt[32];
 };
 
@@ -276,6 +277,14 @@ __device__ void ht_master(HtCtx &C, int forced) {
       double sm[HT_MAXR + 1];
       if (!ht_solve(A, k + 1, sm)) continue;
       for (int i = 0; i < k; ++i) if (sm[i] < -1e-9) good = false;
+      // ... and the rows outside the base (pi = 0 there) must not exceed the value under this column mix; a base that
+      // passes both tests is primal AND dual feasible, hence optimal, and its mix certifies  max_w sum mu e = v
+      for (int r = 0; r < R && good; ++r) {
+        if (rowmask >> r & 1) continue;
+        double d = 0.0;
+        for (int i = 0; i < k; ++i) d += sm[i] * S.E[cols[i]][r];
+        if (d > v + slack) good = false;
+      }
       if (!good) continue;
       bestv = v; bk = k;
       double tot = 0.0;
@@ -313,19 +322,29 @@ __device__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
   HtShared &S = C.S;
   if (threadIdx.x == 0) S.M = 0;
   __syncthreads();
-  // seeds: the prices that refuted / supported the previous theta, the unit vectors, the uniform vector
+  // seeds: the prices that refuted / supported the previous theta, the prices of the support of the best feasible
+  // point so far (near the optimum the same job vertices stay optimal, so these columns usually certify the new
+  // theta at once), the unit vectors, the uniform vector
   double keep[HT_MAXR];
   for (int r = 0; r < R; ++r) keep[r] = S.pi[r];
-  for (int sd = 0; sd < R + 2; ++sd) {
+  const int nb = S.bK;
+  __syncthreads();
+  for (int sd = 0; sd < nb + R + 2; ++sd) {
     if (threadIdx.x == 0) {
-      for (int r = 0; r < R; ++r)
-        S.pi[r] = sd == 0 ? keep[r] : (sd <= R ? (r == sd - 1 ? 1.0 : 0.0) : 1.0 / R);
+      for (int r = 0; r < R; ++r) {
+        double p;
+        if (sd == 0) p = keep[r];
+        else if (sd <= nb) p = S.bPI[sd - 1][r];
+        else if (sd <= nb + R) p = (r == sd - nb - 1) ? 1.0 : 0.0;
+        else p = 1.0 / R;
+        S.pi[r] = p;
+      }
     }
     __syncthreads();
     ht_price<W, R>(C, theta);
     ++rounds;
-    if (S.bad) return false;
-    if (S.lb > HT_TOL) return false;          // Farkas certificate: no x at this theta
+    if (S.bad) { if (threadIdx.x == 0) S.dbg[0] += 1; return false; }
+    if (S.lb > HT_TOL) { if (threadIdx.x == 0) S.dbg[1] += 1; return false; }   // Farkas certificate: no x at this theta
     bool done = true;
     for (int r = 0; r < R; ++r) if (S.e[r] > 0.0) done = false;
     if (threadIdx.x == 0) {
@@ -336,12 +355,37 @@ __device__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
     }
     __syncthreads();
     if (done) return true;                    // this single vertex already fits every row
+    if (nb > 0 && sd == nb) {
+      // early master over {last prices, previous support}
+      ht_master<R>(C, -1);
+      if (S.ok) {
+        double U = -1e300;
+        for (int r = 0; r < R; ++r) {
+          double t = 0.0;
+          for (int i = 0; i < S.M; ++i) t += S.mu[i] * S.E[i][r];
+          U = fmax(U, t);
+        }
+        if (U <= 0.0) {
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            int k = 0;
+            for (int i = 0; i < S.M; ++i)
+              if (S.mu[i] > 0.0 && k < HT_MAXR) { S.tMU[k] = S.mu[i]; for (int r = 0; r < R; ++r) S.tPI[k][r] = S.PI[i][r]; ++k; }
+            S.tK = k;
+          }
+          __syncthreads();
+          return true;
+        }
+      }
+      __syncthreads();
+    }
   }
   int forced = -1;
   for (int it = 0; it < 400; ++it) {
     ht_master<R>(C, forced);
     if (!S.ok) {
       if (forced >= 0) { forced = -1; continue; }    // numerical trouble with the restricted search: full search
+      if (threadIdx.x == 0) S.dbg[2] += 1;
       return false;
     }
     // certificate: the column mix fits every row
@@ -364,7 +408,15 @@ __device__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
     const double v = S.v;
     ht_price<W, R>(C, theta);
     ++rounds;
-    if (S.lb > HT_TOL || v - S.lb <= HT_TOL) return false;
+    if (S.lb > HT_TOL) { if (threadIdx.x == 0) S.dbg[3] += 1; return false; }   // Farkas certificate
+    if (v - S.lb <= HT_TOL) {
+      // the master value and the pricing bound meet: no x.  The restricted base search is only guaranteed to find
+      // the optimum when the master optimum was unique, so the claim is confirmed with the full search first
+      // (the column just priced is not added: at this point it cuts nothing).
+      if (forced >= 0) { forced = -1; continue; }
+      if (threadIdx.x == 0) { S.dbg[4] += 1; S.dbg[6] = v; S.dbg[7] = S.lb; S.dbg[8] = theta; S.dbg[9] = S.M; }
+      return false;
+    }
     if (threadIdx.x == 0) {
       int m = S.M;
       if (m == HT_MAXC) {
@@ -386,6 +438,7 @@ __device__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
     __syncthreads();
     forced = S.M - 1;
   }
+  if (threadIdx.x == 0) S.dbg[5] += 1;
   return false;
 }
 
@@ -409,6 +462,7 @@ __global__ void __launch_bounds__(1024, 1) hetero_kernel(HeteroLaunch L) {
   C.vscale = 1.0;
   if (threadIdx.x == 0) {
     S.bK = 0; S.bTheta = 0.0; S.M = 0;
+    for (int i = 0; i < 12; ++i) S.dbg[i] = 0.0;
     for (int r = 0; r < C.R; ++r) S.pi[r] = 1.0 / C.R;
   }
   __syncthreads();
@@ -507,7 +561,8 @@ __global__ void __launch_bounds__(1024, 1) hetero_kernel(HeteroLaunch L) {
     }
     for (int w = 0; w < W; ++w) L.x[(size_t)j * W + w] = out[w];
   }
-  if (threadIdx.x == 0) { L.out[0] = obj; L.out[1] = (double)status; L.out[2] = (double)rounds; L.out[3] = (double)checks; }
+  if (threadIdx.x == 0) { L.out[0] = obj; L.out[1] = (double)status; L.out[2] = (double)rounds; L.out[3] = (double)checks;
+    for (int i = 0; i < 12; ++i) L.out[4 + i] = S.dbg[i]; }
 }
 
 cudaError_t launch_hetero(const HeteroLaunch &L, cudaStream_t st) {

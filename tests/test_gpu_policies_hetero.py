@@ -126,3 +126,37 @@ def test_min_total_duration_and_max_sum_hetero(J, spec, kinds, zero):
         got = ((m / c[None, :]) * x).sum()
         assert abs(got - v) <= 1e-6 * v, (got, v, P._hetero.last_stats)
         print("max-sum J", J, "costs", bool(costs), "value", got, "lp", v, "passes / checks", P._hetero.last_stats)
+
+
+def test_random_sweep_hetero():
+    """80 random small instances straight through swb_policy_hetero (W = 2 and 3, capacities from scarce to ample,
+    duplicated jobs, zero throughputs, wide gangs): max-min and max-sum objectives against the HiGHS LPs."""
+    rng = np.random.default_rng(77)
+    worst = 0.0
+    for it in range(80):
+        W = int(rng.integers(2, 4))
+        J = int(rng.integers(2, 70))
+        a = rng.uniform(0.2, 10.0, size=(J, 1)) * rng.uniform(0.05, 1.0, size=(J, W))
+        if it % 3 == 0:
+            a = a[rng.integers(0, max(1, J // 6), J)]           # few distinct rows: ties everywhere
+        if it % 4 == 1:
+            a[rng.integers(0, J, max(1, J // 5)), rng.integers(0, W)] = 0.0
+        a[a.max(axis=1) == 0.0, 0] = 1.0
+        sf = rng.choice([1.0, 2.0, 4.0, 8.0], J)
+        N = rng.integers(1, 4 * J + 2, W).astype(float) * rng.choice([0.25, 1.0, 4.0])
+        N = np.maximum(np.round(N), 1.0)
+        x, obj, rc = P._hetero(P.POL_MAXMIN, N, a, sf)
+        z, _ = gl.max_min(a, sf, N)
+        assert rc == 0 and abs(obj - z) <= 1e-6 * abs(z), (it, J, W, obj, z)
+        assert x.min() >= -1e-12 and np.all(x.sum(axis=1) <= 1 + 1e-9)
+        assert np.all((x * sf[:, None]).sum(axis=0) <= N * (1 + 1e-9))
+        assert (a * x).sum(axis=1).min() >= z * (1 - 1e-6)
+        worst = max(worst, abs(obj - z) / abs(z))
+        x, obj, rc = P._hetero(P.POL_MAXSUM, N, a, sf)
+        v, _ = gl.max_sum_throughput(a, sf, N)
+        assert rc == 0 and abs(obj - v) <= 1e-6 * abs(v), (it, J, W, obj, v)
+        assert x.min() >= -1e-12 and np.all(x.sum(axis=1) <= 1 + 1e-9)
+        assert np.all((x * sf[:, None]).sum(axis=0) <= N * (1 + 1e-9))
+        assert abs((a * x).sum() - v) <= 1e-6 * v
+        worst = max(worst, abs(obj - v) / abs(v))
+    print("hetero random sweep: worst relative objective difference vs HiGHS", worst)
