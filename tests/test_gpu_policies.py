@@ -193,3 +193,31 @@ def test_pooled_selection_is_the_analytic_centre(J, N, kinds):
         assert abs(obj - oo) <= 1e-7 * abs(oo), (mode, obj, oo)      # HiGHS' own feasibility tolerance is 1e-7
         assert np.abs(x - xo).max() <= 1e-6, (mode, np.abs(x - xo).max())
         assert x.min() >= 0 and x.max() <= 1 + 1e-12 and (sf * x).sum() <= N * (1 + 1e-9)
+
+
+def test_pooled_random_sweep_against_oracle_centre():
+    """36 random small pooled instances, capacity from scarce to ample (everything fits), J from 1: objective and the
+    selected x against the oracle (HiGHS objective + analytic-centre selection), every mode."""
+    from oracle import gavel_backend as gb
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for it in range(36):
+        J = int(rng.integers(1, 60))
+        thr = rng.uniform(0.5, 20.0, J) if it % 3 else rng.uniform(0.5, 20.0, 3)[rng.integers(0, 3, J)]
+        sf = rng.choice([1.0, 2.0, 4.0, 8.0], J)
+        N = float(max(1, round(sf.sum() * rng.choice([0.1, 0.4, 0.9, 1.0, 1.5, 4.0]))))
+        pw = rng.choice([1.0, 2.0, 5.0], J)
+        n = rng.uniform(1e4, 1e6, J)
+        t = rng.uniform(0, 5e3, J)
+        den = rng.uniform(0, 2e3, J) + n / (thr * np.minimum(1.0, (N / J) / sf))
+        for mode, kw in ((P.POL_MAXMIN, dict(coef=sf / pw)), (P.POL_FTF, dict(coef=thr, t=t, n=n, den=den)),
+                         (P.POL_MTD, dict(coef=thr, n=n)), (P.POL_MAXSUM, dict(coef=thr))):
+            coef = kw.pop("coef")
+            x, obj, rc = P._pooled(mode, N, coef, sf, **kw)
+            xo, oo, rco = gb.pooled_cpu(mode, N, coef, sf, **kw)
+            assert rc == rco == 0, (it, mode)
+            assert abs(obj - oo) <= 1e-7 * abs(oo), (it, mode, obj, oo)
+            assert np.abs(x - xo).max() <= 2e-6, (it, mode, J, N, np.abs(x - xo).max())
+            assert x.min() >= 0 and x.max() <= 1 + 1e-12 and (sf * x).sum() <= N * (1 + 1e-9)
+            worst = max(worst, np.abs(x - xo).max())
+    print("pooled random sweep: worst |x - x_oracle|", worst)
