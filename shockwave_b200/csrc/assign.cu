@@ -23,7 +23,7 @@ __device__ __forceinline__ double ax_cost(const AssignLaunch &L, int i, int col)
 __global__ void __launch_bounds__(1024, 1) assign_kernel(AssignLaunch L) {
   __shared__ double s_val[32];
   __shared__ int s_idx[32];
-  __shared__ int s_i, s_sink, s_jstar;
+  __shared__ int s_i, s_sink;
   __shared__ double s_min;
   const int m = L.m, N = L.m * L.n;
   double *u = L.u, *v = L.v, *spc = L.spc;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(1024, 1) assign_kernel(AssignLaunch L) {
           if (take) { bv = ov; bj = oj; }
         }
         if (threadIdx.x == 0) {
-          s_jstar = bj; s_min = bv; SC[bj] = 1;
+          s_min = bv; SC[bj] = 1;
           if (row4col[bj] < 0) s_sink = bj; else s_i = row4col[bj];
         }
       }

@@ -45,22 +45,6 @@ __device__ void sort_desc64(unsigned long long *key, unsigned short *idx, int n)
   }
 }
 
-__device__ void sort_desc32(unsigned int *key, int n) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int p = i ^ j;
-        if (p > i) {
-          const unsigned int a = key[i], b = key[p];
-          const bool up = (i & k) == 0;
-          if (up != (a > b)) { key[i] = b; key[p] = a; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
 // exclusive block scan of one int per thread; returns the exclusive prefix, total in *tot.
 // wsum needs 33 ints.  Two barriers; the 32 warp totals are scanned by warp 0 with shuffles.
 __device__ __forceinline__ int block_excl_scan(int v, int *wsum, int *tot) {
@@ -106,11 +90,9 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   unsigned int *binB = reinterpret_cast<unsigned int *>(p); p += SWB_MAX_T * sizeof(int);
   double *score = reinterpret_cast<double *>(p); p += SWB_MAX_T * sizeof(double);
   unsigned char *newpos = p;                   p += SWB_MAX_T;
-  // union region: {key64[npad], idx16[npad]}  or  {key32[npad], sel8[npad]}
+  // sort scratch: key64[npad] + idx16[npad]
   unsigned long long *key64 = reinterpret_cast<unsigned long long *>(p);
-  unsigned int *key32 = reinterpret_cast<unsigned int *>(p);
   unsigned short *idx16 = reinterpret_cast<unsigned short *>(p + 8 * (size_t)npad);
-  unsigned char *sel = p + 4 * (size_t)npad;
   p += 10 * (size_t)npad;
   unsigned short *rank = reinterpret_cast<unsigned short *>(p);  p += 2 * (size_t)npad;
   unsigned short *order = reinterpret_cast<unsigned short *>(p); p += 2 * (size_t)npad;
