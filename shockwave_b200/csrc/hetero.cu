@@ -46,7 +46,6 @@ struct HtShared {
   double e[HT_MAXR];             // last priced column
   double lb;                     // pi.e of the last priced column
   int bad;                       // some job cannot meet its requirement at all
-  int M;                         // columns
   int ok;                        // master found a base
   // support of the best feasible point so far
   double bPI[HT_MAXR][HT_MAXR], bMU[HT_MAXR], bTheta;
@@ -218,9 +217,8 @@ __device__ __forceinline__ void ht_unrank(int q, int k, int *c) {
 // master: exact solution of the matrix game over the M columns in S.E.  `forced` >= 0: only bases that contain
 // that column are enumerated (the optimum must contain the column that was just added).  Fills S.pi, S.mu, S.v, S.ok.
 template <int R>
-__device__ void ht_master(HtCtx &C, int forced) {
+__device__ void ht_master(HtCtx &C, int M, int forced) {
   HtShared &S = C.S;
-  const int M = S.M;
   double bestv = -1e300;
   int bk = 0, bcols[HT_MAXR];
   double bpi[HT_MAXR], bmu[HT_MAXR];
@@ -320,7 +318,7 @@ __device__ void ht_master(HtCtx &C, int forced) {
 template <int W, int R>
 __device__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
   HtShared &S = C.S;
-  if (threadIdx.x == 0) S.M = 0;
+  int M = 0;      // columns; every thread keeps the same count
   __syncthreads();
   // seeds: the prices that refuted / supported the previous theta, the prices of the support of the best feasible
   // point so far (near the optimum the same job vertices stay optimal, so these columns usually certify the new
@@ -348,28 +346,27 @@ __device__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
     bool done = true;
     for (int r = 0; r < R; ++r) if (S.e[r] > 0.0) done = false;
     if (threadIdx.x == 0) {
-      const int m = S.M;
-      for (int r = 0; r < R; ++r) { S.E[m][r] = S.e[r]; S.PI[m][r] = S.pi[r]; }
-      S.M = m + 1;
+      for (int r = 0; r < R; ++r) { S.E[M][r] = S.e[r]; S.PI[M][r] = S.pi[r]; }
       if (done) { S.tK = 1; S.tMU[0] = 1.0; for (int r = 0; r < R; ++r) S.tPI[0][r] = S.pi[r]; }
     }
+    ++M;
     __syncthreads();
     if (done) return true;                    // this single vertex already fits every row
     if (nb > 0 && sd == nb) {
       // early master over {last prices, previous support}
-      ht_master<R>(C, -1);
+      ht_master<R>(C, M, -1);
       if (S.ok) {
         double U = -1e300;
         for (int r = 0; r < R; ++r) {
           double t = 0.0;
-          for (int i = 0; i < S.M; ++i) t += S.mu[i] * S.E[i][r];
+          for (int i = 0; i < M; ++i) t += S.mu[i] * S.E[i][r];
           U = fmax(U, t);
         }
         if (U <= 0.0) {
           __syncthreads();
           if (threadIdx.x == 0) {
             int k = 0;
-            for (int i = 0; i < S.M; ++i)
+            for (int i = 0; i < M; ++i)
               if (S.mu[i] > 0.0 && k < HT_MAXR) { S.tMU[k] = S.mu[i]; for (int r = 0; r < R; ++r) S.tPI[k][r] = S.PI[i][r]; ++k; }
             S.tK = k;
           }
@@ -382,7 +379,7 @@ __device__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
   }
   int forced = -1;
   for (int it = 0; it < 400; ++it) {
-    ht_master<R>(C, forced);
+    ht_master<R>(C, M, forced);
     if (!S.ok) {
       if (forced >= 0) { forced = -1; continue; }    // numerical trouble with the restricted search: full search
       if (threadIdx.x == 0) S.dbg[2] += 1;
@@ -392,13 +389,13 @@ __device__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
     double U = -1e300;
     for (int r = 0; r < R; ++r) {
       double s = 0.0;
-      for (int i = 0; i < S.M; ++i) s += S.mu[i] * S.E[i][r];
+      for (int i = 0; i < M; ++i) s += S.mu[i] * S.E[i][r];
       U = fmax(U, s);
     }
     if (U <= 0.0) {
       if (threadIdx.x == 0) {
         int k = 0;
-        for (int i = 0; i < S.M; ++i)
+        for (int i = 0; i < M; ++i)
           if (S.mu[i] > 0.0 && k < HT_MAXR) { S.tMU[k] = S.mu[i]; for (int r = 0; r < R; ++r) S.tPI[k][r] = S.PI[i][r]; ++k; }
         S.tK = k;
       }
@@ -414,11 +411,11 @@ __device__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
       // the optimum when the master optimum was unique, so the claim is confirmed with the full search first
       // (the column just priced is not added: at this point it cuts nothing).
       if (forced >= 0) { forced = -1; continue; }
-      if (threadIdx.x == 0) { S.dbg[4] += 1; S.dbg[6] = v; S.dbg[7] = S.lb; S.dbg[8] = theta; S.dbg[9] = S.M; }
+      if (threadIdx.x == 0) { S.dbg[4] += 1; S.dbg[6] = v; S.dbg[7] = S.lb; S.dbg[8] = theta; S.dbg[9] = M; }
       return false;
     }
     if (threadIdx.x == 0) {
-      int m = S.M;
+      int m = M;
       if (m == HT_MAXC) {
         // evict the column with the largest slack at the current prices (never a base column: their slack is 0)
         int worst = 0; double ws = -1.0;
@@ -433,10 +430,10 @@ __device__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
         m = m - 1;
       }
       for (int r = 0; r < R; ++r) { S.E[m][r] = S.e[r]; S.PI[m][r] = S.pi[r]; }
-      S.M = m + 1;
     }
+    if (M < HT_MAXC) ++M;                     // at the cap one column was evicted and the new one took the last slot
     __syncthreads();
-    forced = S.M - 1;
+    forced = M - 1;
   }
   if (threadIdx.x == 0) S.dbg[5] += 1;
   return false;
@@ -461,7 +458,7 @@ __global__ void __launch_bounds__(1024, 1) hetero_kernel(HeteroLaunch L) {
   C.R = R;
   C.vscale = 1.0;
   if (threadIdx.x == 0) {
-    S.bK = 0; S.bTheta = 0.0; S.M = 0;
+    S.bK = 0; S.bTheta = 0.0;
     for (int i = 0; i < 12; ++i) S.dbg[i] = 0.0;
     for (int r = 0; r < C.R; ++r) S.pi[r] = 1.0 / C.R;
   }

@@ -74,3 +74,21 @@ def test_backend_selection_keeps_the_lp_objective():
             assert abs((thr * xc).sum() - (thr * xv).sum()) <= 1e-7 * (thr * xv).sum()
         if mode == gb.POL_MTD:
             assert np.all(thr * xc >= n / oc * (1 - 1e-9))
+
+
+def test_live_closed_loop_max_min_fairness_reproduces_golden():
+    """Live version of the pin above for one policy (needs /root/reference; ~5 s): the unmodified reference
+    simulator + policies.py + the HiGHS backend reproduce the max_min_fairness golden pickle exactly."""
+    import pickle
+    import pytest
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("reference tree not present")
+    with gb.cpu_backend() as P:
+        res = rh.simulate("max_min_fairness", policy_obj=P.get_policy("max_min_fairness", solver="ECOS", seed=0))
+    gold = pickle.load(open(os.path.join(
+        rh.REF, "reproduce/pickles/tacc_32gpus",
+        "max_min_fairness_120_0.2_5_100_40_25_0,0.5,0.5_0.6,0.3,0.09,0.01_multigpu_dynamic_simulation.pickle"), "rb"))
+    assert abs(res["makespan"] - gold["makespan"]) <= 1e-9 * gold["makespan"]
+    assert abs(res["avg_jct"] - gold["avg_jct"]) <= 1e-9 * gold["avg_jct"]
+    assert len(res["per_round_schedule"]) == len(gold["per_round_schedule"])
