@@ -441,6 +441,7 @@ def get_policy(policy_name, solver=None, seed=None):
         "max_min_fairness_perf": lambda: MaxMinFairnessPolicyWithPerf(solver=solver),
         "max_sum_throughput_perf": lambda: ThroughputSumWithPerf(solver=solver),
         "max_sum_throughput_normalized_by_cost_perf": lambda: ThroughputNormalizedByCostSumWithPerf(solver=solver),
+        "max_sum_throughput_normalized_by_cost_perf_SLOs": lambda: ThroughputNormalizedByCostSumWithPerfSLOs(solver=solver),
         "min_total_duration": lambda: MinTotalDurationPolicy(solver=solver),
         "min_total_duration_perf": lambda: MinTotalDurationPolicyWithPerf(solver=solver),
         "shockwave": ShockwavePolicy,
