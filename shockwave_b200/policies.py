@@ -179,6 +179,13 @@ class GandivProportionalPolicy(Policy):
         return super().unflatten(x[:, None] * share[None, :], index)
 
 
+class IsolatedPlusPolicy(GandivProportionalPolicy):
+    """isolated_plus.py:10-76: the equal split without the scale-factor division — the same closed form as
+    gandiva_fair_proportional.py (x_jw = N_w/m, rows normalised to <= 1)."""
+    def __init__(self):
+        self._name = "Isolated_plus"
+
+
 class MaxMinFairnessPolicyWithPerf(Policy):
     def __init__(self, solver):
         Policy.__init__(self, solver)
@@ -436,7 +443,7 @@ def get_policy(policy_name, solver=None, seed=None):
     table = {
         "finish_time_fairness": lambda: FinishTimeFairnessPolicy(solver="GUROBI"),
         "finish_time_fairness_perf": lambda: FinishTimeFairnessPolicyWithPerf(solver=solver),
-        "gandiva_fair": GandivProportionalPolicy, "isolated": IsolatedPolicy,
+        "gandiva_fair": GandivProportionalPolicy, "isolated": IsolatedPolicy, "isolated_plus": IsolatedPlusPolicy,
         "max_min_fairness": lambda: MaxMinFairnessPolicy(solver=solver),
         "max_min_fairness_perf": lambda: MaxMinFairnessPolicyWithPerf(solver=solver),
         "max_sum_throughput_perf": lambda: ThroughputSumWithPerf(solver=solver),

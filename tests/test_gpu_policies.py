@@ -117,6 +117,8 @@ def test_closed_forms_and_edge_cases():
     gf = _mat(P.GandivProportionalPolicy().get_allocation(thr, sf, spec), 10)
     want = np.tile(N / 10, (10, 1)); want = want / np.maximum(want.sum(axis=1), 1.0)[:, None]
     assert np.allclose(gf, want, rtol=1e-12)
+    ip = _mat(P.get_policy("isolated_plus").get_allocation(thr, sf, spec), 10)     # isolated_plus.py:36-55: same closed form
+    assert np.allclose(ip, want, rtol=1e-12) and P.get_policy("isolated_plus").name == "Isolated_plus"
     assert P.MaxMinFairnessPolicy(solver=None).get_allocation({}, {}, {}, spec) is None
     assert P.get_policy("max_min_fairness").name == "MaxMinFairness"
     assert P.get_policy("finish_time_fairness").name.startswith("FinishTimeFairness")
