@@ -47,3 +47,34 @@ def test_random_sweep(engine):
           "share within 1e-3", (gaps <= 1e-3).mean(), "worst gap at J>=16", gaps[sizes >= 16].max())
     assert gaps[sizes >= 16].max() <= 1e-3
     assert gaps.max() <= 1e-2
+
+
+def test_recorded_random_sweep(engine):
+    """240 random instances up to J = 320, T = 32, G = 128 whose oracle verdicts / objectives were computed offline
+    (tests/golden/make_random_sweep.py, HiGHS gap 1e-6): P1 + P3 on every instance, P2 (1e-3) on every instance with
+    J >= 16."""
+    import json
+    import os
+    recs = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "random_sweep_oracle.json")))
+    gaps, sizes, verdict_miss = [], [], []
+    for p in recs:
+        pb = synth_problem(p["J"], p["G"], p["T"], p["D"], seed=p["seed"], tight=p["tight"])
+        prm = make_params(p["G"], p["T"], p["D"], p["k"], p["lam"], 1.0, fx.BASES, fx.ORIGIN, round_ptr=pb["round_ptr"])
+        out = engine.solve(prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"])
+        res, x, w = out["results"][0], out["x"][0], out["weights"][0]
+        if res["status"] != p["status"]:
+            verdict_miss.append(p["it"])
+            continue
+        obj, _, _, n, cap_ok = om.evaluate(x, pb["g"], pb["E"].astype(float), pb["c"].astype(float), pb["dbar"],
+                                           pb["rem"], w, p["G"], p["T"], p["D"], p["k"], fx.BASES, LOGV)
+        assert cap_ok, p
+        assert abs(obj - res["objective"]) <= 1e-9 * max(1.0, abs(obj)), p
+        gaps.append((p["objective"] - obj) / max(1e-12, abs(p["objective"])))
+        sizes.append(p["J"])
+    gaps, sizes = np.array(gaps), np.array(sizes)
+    print("recorded sweep:", len(recs), "instances, verdict mismatches", verdict_miss, "worst gap", gaps.max(),
+          "p95", np.quantile(gaps, 0.95), "worst at J>=16", gaps[sizes >= 16].max(),
+          "share within 1e-3", (gaps <= 1e-3).mean())
+    assert not verdict_miss
+    assert gaps[sizes >= 16].max() <= 1e-3
+    assert gaps.max() <= 1e-2
