@@ -56,23 +56,34 @@ __device__ void analytic_centre_box(const PolicyLaunch &L, BlockRed &br, double 
     return;
   }
   const double Nf = N - usedfix;
-  for (int q = 0; q < cnt; ++q) if (lo[q] < 2.0) xs[q] = 0.5 * (lo[q] + 1.0);
-  double a = 1e-12, b = 1e15;
-  for (int it = 0; it < 64; ++it) {
-    const double lam = sqrt(a * b);
+  double nfree = 0.0;
+  for (int q = 0; q < cnt; ++q) if (lo[q] < 2.0) { xs[q] = 0.5 * (lo[q] + 1.0); nfree += 1.0; }
+  nfree = br.sum(nfree);
+  // bracket of the multiplier: slack(lam) <= S = N - used0 gives lam >= 1/S; multiplying the stationarity condition
+  // of job j by (x_j - lo_j) and summing gives lam (S - slack) <= nfree (w_lo + w_x), i.e. lam <= (nfree (w_lo + w_x) + 1)/S.
+  // G(lam) = lam * slack(lam) - 1 is increasing: Illinois (regula falsi) with a geometric-bisection safeguard.
+  const double S = N - used0;
+  double a = 1.0 / S, b = (nfree * (w_lo + w_x) + 1.0) / S * (1.0 + 1e-9);
+  double Ga = -1.0, Gb = 1.0;          // signs only until both ends have been evaluated
+  bool have_a = false, have_b = false;
+  int last = 0;
+  double lam = sqrt(a * b);
+  for (int it = 0; it < 80; ++it) {
     double load = 0.0;
     for (int q = 0; q < cnt; ++q) {
       if (lo[q] >= 2.0) continue;
       const double l0 = lo[q], ls = lam * sfj[q];
       double l = l0, h = 1.0, x = xs[q];
-      for (int k = 0; k < 60; ++k) {
+      for (int k = 0; k < 80; ++k) {
         const double d0 = x - l0, d1 = 1.0 - x;
         const double f = w_x / x - 1.0 / d1 + w_lo / d0 - ls;
+        if (f == 0.0) break;
         if (f > 0.0) l = x; else h = x;
         const double fp = w_x / (x * x) + 1.0 / (d1 * d1) + w_lo / (d0 * d0);    // = -f'
         double xn = x + f / fp;
+        if (xn == x) break;                                  // the Newton step is below one ulp: converged
         if (!(xn > l && xn < h)) xn = 0.5 * (l + h);
-        const bool done = fabs(xn - x) <= 4e-16 * xn;
+        const bool done = fabs(xn - x) <= 2e-15 * xn;
         x = xn;
         if (done) break;
       }
@@ -80,8 +91,18 @@ __device__ void analytic_centre_box(const PolicyLaunch &L, BlockRed &br, double 
       load += sfj[q] * x;
     }
     load = br.sum(load);
-    const double sl = Nf - load;
-    if (sl > 0.0 && lam * sl > 1.0) b = lam; else a = lam;
+    const double Gl = lam * (Nf - load) - 1.0;
+    if (Gl > 0.0) {
+      if (last == 1 && have_a) Ga *= 0.5;  // Illinois: an end that survives twice in a row gets half its weight
+      b = lam; Gb = Gl; have_b = true; last = 1;
+    } else {
+      if (last == -1 && have_b) Gb *= 0.5;
+      a = lam; Ga = Gl; have_a = true; last = -1;
+    }
+    if (b - a <= 1e-13 * b || fabs(Gl) <= 1e-13) break;
+    double nl = (have_a && have_b) ? a - Ga * (b - a) / (Gb - Ga) : sqrt(a * b);
+    if (!(nl > a && nl < b)) nl = sqrt(a * b);
+    lam = nl;
   }
   cnt = 0;
   for (int j = threadIdx.x; j < J; j += blockDim.x, ++cnt) L.x[j] = xs[cnt];
