@@ -205,7 +205,7 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   P.sc_a = L.sc_a; P.sc_u0 = L.sc_u0; P.sc_R = L.sc_R; P.sc_ws = L.sc_ws; P.sc_cap = L.sc_cap;
   P.sc_g = L.sc_g; P.sc_n = L.sc_n; P.sc_nmax = L.sc_nmax; P.weights = L.weights; P.E = E; P.c = cc; P.dbar = dbar;
   P.x = x; P.backfill = bf; P.nrounds = nr ? nr : c->seated.as<int32_t>(); P.ncal = ncal; P.res = L.res;
-  P.xmask = xmask; P.bfmask = bfmask;
+  P.xmask = xmask; P.bfmask = bfmask; P.ncap = c->sncap.as<uint8_t>();
   int rc2 = ensure_hres(c, S);
   if (rc2) return rc2;
   for (int pass = 0; pass < SWB_MAX_REPLAN + 1; ++pass) {
@@ -220,7 +220,7 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
     int shortf = 0;
     for (int s = 0; s < S; ++s) shortf += c->h_res[s].shortfall;
     if (shortf == 0 || pass == SWB_MAX_REPLAN) break;
-    CK(swb::launch_tighten(S, J, L.res, L.sc_n, P.nrounds, c->sncap.as<uint8_t>(), c->st));
+    // place_kernel has already written the tighter per-job caps for the next pass (packing feedback)
   }
   return 0;
 }

@@ -546,6 +546,8 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   __syncthreads();
 
   // ---- objective of the PLACED schedule (what a checker recomputes from x) --------------------
+  double me_all = 0.0;
+  long long shortf_all = 0;
   {
     double w = 0.0, me = 0.0;
     long long shortf = 0;
@@ -570,11 +572,63 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     w = br.sum(w);
     me = br.max(me);
     shortf = br.sumll(shortf);
+    me_all = me; shortf_all = shortf;
     if (threadIdx.x == 0) {
       swb_result &r = L.res[s];
       r.welfare = w; r.makespan = me; r.objective = w - prm.k * me; r.shortfall = (int)shortf;
       r.placement = t0; r.reserved = 0;
     }
+  }
+
+  // ---- packing feedback for the next pass (api.cu re-solves while rounds stay unseated) --------------------------
+  //      The price-based counts only know the aggregate capacity G*T; when gang widths do not nest in G (one 8-gang
+  //      per 12-GPU round) a width class can be over-planned and the packer strands whoever comes last in its order.
+  //      Which job-rounds of that class to give up is an economic choice, not a packing one: for every stranded
+  //      job-round, the job of the SAME width whose last planned round is worth least (welfare slope + makespan
+  //      term) loses one round via ncap; the next solve re-prices everything else around the tighter class.
+  if (L.ncap && shortf_all > 0) {
+    unsigned char *cuts = remr, *covered = ext;       // both arrays are free at this point
+    for (int j = threadIdx.x; j < J; j += blockDim.x) { cuts[j] = 0; covered[j] = 0; }
+    __syncthreads();
+    const double Dd = prm.round_duration;
+    const int budget = shortf_all < 96 ? (int)shortf_all : 96;
+    for (int it = 0; it < budget; ++it) {
+      double fk = -1.0;                                // stranded job: widest first, then lowest index
+      for (int j = threadIdx.x; j < J; j += blockDim.x)
+        if ((int)remn[j] > (int)covered[j]) fk = fmax(fk, (double)gs[j] * 16384.0 + (double)(SWB_MAX_J - 1 - j));
+      fk = br.max(fk);
+      if (fk < 0.0) break;
+      const int gf = (int)(fk / 16384.0);
+      const int f = SWB_MAX_J - 1 - (int)(fk - (double)gf * 16384.0);
+      double bl = 1e300;
+      for (int pass2 = 0; pass2 < 2; ++pass2) {
+        double v = 1e300;
+        for (int j = threadIdx.x; j < J; j += blockDim.x) {
+          const int n = (int)nplan[j] - (int)cuts[j];
+          if ((int)gs[j] != gf || n < 1) continue;
+          const double a = L.sc_a[so + j], u0 = L.sc_u0[so + j], cap = L.sc_cap[so + j];
+          const double u1 = (Dd * (double)n >= cap) ? 1.0 : fma(a, (double)n, u0);
+          const double u_0 = (Dd * (double)(n - 1) >= cap) ? 1.0 : fma(a, (double)(n - 1), u0);
+          const size_t ji = (L.per_scn ? so : 0) + j;
+          const double db = L.dbar[ji], room = (double)L.E[ji] - (double)L.c[ji];
+          const double rem0 = fmax(0.0, L.sc_R[so + j] - db * fmin(Dd * (double)(n - 1) / db, room));
+          const double loss = L.sc_ws[so + j] * (plog(P, u1) - plog(P, u_0)) + prm.k * fmax(0.0, rem0 - me_all);
+          if (pass2 == 0) v = fmin(v, loss);
+          else if (loss <= bl) v = fmin(v, (double)j);
+        }
+        v = br.min(v);
+        if (pass2 == 0) bl = v; else bl = v;           // second pass: bl = index of the cheapest round
+      }
+      if (bl >= 1e299) break;
+      if (threadIdx.x == 0) { cuts[(int)bl] = (unsigned char)(cuts[(int)bl] + 1); covered[f] = (unsigned char)(covered[f] + 1); }
+      __syncthreads();
+    }
+    for (int j = threadIdx.x; j < J; j += blockDim.x)
+      if (cuts[j] > 0) {
+        const int capn = (int)nplan[j] - (int)cuts[j];
+        if (capn < (int)L.ncap[so + j]) L.ncap[so + j] = (uint8_t)capn;
+      }
+    __syncthreads();
   }
 
   // ---- work-conserving back-fill: one warp per round walks the sorted order --------------------

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
     int nfin = cap <= 0.0 ? 0 : (int)fmin(ceil(cap / D - 1e-9), 255.0);
     int nmax = nfin < T ? nfin : T;
     if (gI[j] > G) nmax = 0;  // a gang wider than the cluster violates every capacity row (shockwave.py:317)
-    if (L.ncap && (int)L.ncap[so + j] < nmax) nmax = L.ncap[so + j];  // packing feedback (tighten_kernel)
+    if (L.ncap && (int)L.ncap[so + j] < nmax) nmax = L.ncap[so + j];  // packing feedback (written by place_kernel)
     c.a[j] = a; c.u0[j] = cf / Ef; c.cap[j] = cap;
     c.t.R[j] = R * c.invD; L.sc_R[so + j] = R;
     c.t.g[j] = (uint8_t)gI[j]; c.t.nmax[j] = (uint8_t)nmax;
@@ -526,28 +526,6 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
     const double rv = relaxed_optimum(c, rc, br, mu_max, k);
     if (threadIdx.x == 0) L.res[s].relaxed_objective = rv;
   }
-}
-
-// Packing feedback: the count-level solve assumes any counts with sum_j g_j n_j <= G T can be seated;
-// with wide gangs on a small cluster that is not always true (bin packing with distinct-round
-// constraints).  When the placement left planned rounds unseated, the counts of exactly those jobs
-// are capped at what was seated and the scenario is solved again, so the freed GPU-rounds go to
-// other jobs and the makespan threshold is re-optimised against what can really be placed.
-__global__ void tighten_kernel(int J, const swb_result *res, const uint8_t *plan, const int32_t *seated,
-                               uint8_t *ncap) {
-  const int s = blockIdx.y;
-  if (res[s].shortfall <= 0) return;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= J) return;
-  const size_t i = (size_t)s * J + j;
-  if (seated[i] < (int)plan[i]) ncap[i] = (uint8_t)seated[i];
-}
-
-cudaError_t launch_tighten(int S, int J, const swb_result *res, const uint8_t *plan, const int32_t *seated,
-                           uint8_t *ncap, cudaStream_t st) {
-  dim3 grid((J + 255) / 256, S);
-  tighten_kernel<<<grid, 256, 0, st>>>(J, res, plan, seated, ncap);
-  return cudaGetLastError();
 }
 
 static int g_solve_nt = 1024;   // threads per CTA of the shared-memory variant (SWB_SOLVE_NT=512 for experiments)

@@ -11,7 +11,7 @@
 #define SWB_PWL_BYTES 512           /* >= sizeof(swb::Pwl), 16-byte aligned */
 #define SWB_MAX_DYN_SMEM (227 * 1024)
 #define SWB_MAX_T 128               /* x rows are kept as 128-bit masks in the placement kernel */
-#define SWB_MAX_REPLAN 3             /* packing-feedback re-solves (see tighten_kernel) */
+#define SWB_MAX_REPLAN 3             /* packing-feedback re-solves (caps written by place_kernel) */
 #define SWB_MAX_J 8192              /* 13 index bits in the placement sort key */
 
 namespace swb {
@@ -51,11 +51,10 @@ struct PlaceLaunch {
   int32_t *nrounds;       // [S][J] out, may be null
   int32_t *ncal;          // [S][J] out, may be null: rounds with idle GPUs in which the job is unscheduled
   swb_result *res;        // device [S] (status in, objective/shortfall updated)
+  uint8_t *ncap;          // [S][J] in/out, may be null: per-job count caps for the next pass (packing feedback)
 };
 
 cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st, int nbases);
-cudaError_t launch_tighten(int S, int J, const swb_result *res, const uint8_t *plan, const int32_t *seated,
-                           uint8_t *ncap, cudaStream_t st);
 cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask);
 
 struct ForecastLaunch {
