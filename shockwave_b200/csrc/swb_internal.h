@@ -11,7 +11,7 @@
 #define SWB_PWL_BYTES 512           /* >= sizeof(swb::Pwl), 16-byte aligned */
 #define SWB_MAX_DYN_SMEM (227 * 1024)
 #define SWB_MAX_T 128               /* x rows are kept as 128-bit masks in the placement kernel */
-#define SWB_MAX_REPLAN 3             /* packing-feedback re-solves (caps written by place_kernel) */
+#define SWB_MAX_REPLAN 6             /* packing-feedback re-solves (caps written by place_kernel) */
 #define SWB_MAX_J 8192              /* 13 index bits in the placement sort key */
 
 namespace swb {
