@@ -73,7 +73,32 @@ __device__ __forceinline__ int block_excl_scan(int v, int *wsum, int *tot) {
 
 __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch L, unsigned long long *gmask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int s = blockIdx.x, J = L.J;
+  // CTA -> scenario: longest first.  A fallback scenario costs about twice a plain one here (priority sweep), and with
+  // two waves of CTAs the launch ends when the slowest SM finishes: CTA b takes the b-th fallback scenario while
+  // there are any, then the plain ones (the result does not depend on the mapping).
+  __shared__ int s_scan[33], s_scn;
+  {
+    const int chunk = (L.S + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int c0 = min(L.S, (int)threadIdx.x * chunk), c1 = min(L.S, c0 + chunk);
+    int cnt = 0;
+    for (int i = c0; i < c1; ++i) cnt += (L.res[i].status == SWB_ST_FALLBACK) ? 1 : 0;
+    int tot = 0;
+    const int pre = block_excl_scan(cnt, s_scan, &tot);
+    const int b = blockIdx.x;
+    const bool want_fb = b < tot;
+    const int target = want_fb ? b : b - tot;
+    const int mypre = want_fb ? pre : (c0 - pre);
+    const int mycnt = want_fb ? cnt : (c1 - c0 - cnt);
+    if (target >= mypre && target < mypre + mycnt) {
+      int seen = mypre;
+      for (int i = c0; i < c1; ++i) {
+        const bool fb = (L.res[i].status == SWB_ST_FALLBACK);
+        if (fb == want_fb) { if (seen == target) { s_scn = i; break; } ++seen; }
+      }
+    }
+    __syncthreads();
+  }
+  const int s = s_scn, J = L.J;
   const swb_params &prm = L.prm[s];
   const int T = prm.future_rounds, G = prm.ngpus;
   const size_t so = (size_t)s * J;
