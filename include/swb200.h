@@ -167,7 +167,8 @@ int swb_forecast_commit(swb_ctx *ctx, int32_t J, int32_t fallback, const int32_t
  *   SWB_POL_FTF      finish_time_fairness.py:66-157 coef_j = thr_j, t = times_since_start,
  *                    n = num_steps_remaining, den_j = cumulative_isolated_time_j + n_j/isolated_thr_j
  *   SWB_POL_MTD      min_total_duration.py:55-135   coef_j = thr_j, n = num_steps_remaining
- *   SWB_POL_MAXSUM   max_sum_throughput.py:49-108   coef_j = thr_j / instance_cost
+ *   SWB_POL_MAXSUM   max_sum_throughput.py:49-108   coef_j = thr_j / instance_cost; optional SLO floors in t:
+ *                    t_j = num_steps_remaining_j / (SLO_j * thr_j) (0 = no SLO); returns 1 if the floors do not fit
  *   SWB_POL_ISOLATED isolated.py:35-55, proportional.py:26-43, gandiva_fair_proportional.py:26-41
  *                    coef_j = sf_j (Isolated) or 1 (Proportional / GandivaFair) */
 #define SWB_POL_MAXMIN 1

@@ -55,7 +55,10 @@ def hetero_cpu(mode, N, a, sf, t=None, n=None, den=None):
         T, x = gl.min_total_duration_perf(a, sf, np.asarray(n, float), N)
         return x, T, 0
     if mode == POL_MAXSUM:
-        v, x = gl.max_sum_throughput(a, sf, N)
+        need = None if t is None else np.asarray(t, float) * a[:, 0]        # pooled SLO floors lo_j -> thr_j x_j >= need_j
+        v, x = gl.max_sum_throughput(a, sf, N, need=need)
+        if v is None:
+            return np.zeros_like(a), 0.0, 1
         return x, v, 0
     raise ValueError(mode)
 
@@ -81,7 +84,7 @@ def pooled_cpu(mode, N, coef, sf, t=None, n=None, den=None, select="centre"):
     elif mode == POL_MTD:
         x = gl.analytic_centre_box(np.asarray(n, float) / (obj * coef), sf, N)
     elif mode == POL_MAXSUM:
-        x, _ = gl.max_sum_pooled_centre(coef, sf, N)
+        x, _ = gl.max_sum_pooled_centre(coef, sf, N, lo=t)
     return x, obj, rc
 
 

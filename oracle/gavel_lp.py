@@ -110,11 +110,20 @@ def min_total_duration_perf(thr, sf, n, N):
     return best, bx
 
 
-def max_sum_throughput(thr, sf, N, costs=None):
+def max_sum_throughput(thr, sf, N, costs=None, need=None):
+    """max sum_jw thr_jw x_jw / cost_w + base  [+ SLO rows sum_w thr_jw x_jw >= need_j, max_sum_throughput.py:87-93].
+    Returns (value, x), or (None, None) when the SLO rows make it infeasible (the reference then re-solves without them)."""
     J, W = thr.shape
     c = np.ones(W) if costs is None else np.asarray(costs, float)
     A, b = _base(J, W, sf, N)
+    if need is not None:
+        C = np.zeros((J, J * W))
+        for j in range(J):
+            C[j, j * W:(j + 1) * W] = -thr[j]
+        A, b = np.vstack([A, C]), np.concatenate([b, -np.asarray(need, float)])
     res = linprog(-(thr / c[None, :]).reshape(-1), A_ub=A, b_ub=b, bounds=[(0, None)] * (J * W), method="highs")
+    if need is not None and res.status != 0:
+        return None, None
     assert res.status == 0
     return -float(res.fun), res.x.reshape(J, W)
 
@@ -164,36 +173,48 @@ def analytic_centre_box(lo, sf, N, w_lo=1.0, w_x=1.0):
     return x
 
 
-def analytic_centre_tied(sf, C):
-    """max sum_j log x_j + log(1 - x_j)  s.t.  sum_j sf_j x_j = C   (the tied group of a fractional knapsack)."""
+def analytic_centre_tied(sf, C, lo=None):
+    """max sum_j [ 1{lo_j>0} log(x_j - lo_j) + log x_j + log(1 - x_j) ]  s.t.  sum_j sf_j x_j = C
+    (the tied group of a fractional knapsack; lo_j = the job's SLO floor, 0 without one)."""
     sf = np.asarray(sf, dtype=float)
+    lo = np.zeros(len(sf)) if lo is None else np.asarray(lo, dtype=float)
+    w = (lo > 0).astype(float)
 
     def xj(nu):
-        a = nu * sf
-        return 2.0 / ((a + 2.0) + np.sqrt(a * a + 4.0))
-    lo, hi = -1e12, 1e12
+        l, h = lo.copy(), np.ones(len(sf))
+        for _ in range(100):
+            m = 0.5 * (l + h)
+            f = 1.0 / m - 1.0 / (1.0 - m) + w / np.maximum(m - lo, 1e-300) - nu * sf
+            l = np.where(f > 0, m, l)
+            h = np.where(f > 0, h, m)
+        return 0.5 * (l + h)
+    a, b = -1e12, 1e12
     for _ in range(300):
-        nu = 0.5 * (lo + hi)
+        nu = 0.5 * (a + b)
         if float((sf * xj(nu)).sum()) > C:
-            lo = nu
+            a = nu
         else:
-            hi = nu
-    return xj(0.5 * (lo + hi))
+            b = nu
+    return xj(0.5 * (a + b))
 
 
-def max_sum_pooled_centre(v, sf, N):
-    """Pooled max-sum (fractional knapsack by v_j/sf_j) with the interior-point selection inside the tied group."""
+def max_sum_pooled_centre(v, sf, N, lo=None):
+    """Pooled max-sum (fractional knapsack by v_j/sf_j, optional SLO floors lo_j <= x_j) with the interior-point
+    selection inside the tied group.  Returns (x, value), or (None, None) if the floors alone do not fit."""
     v, sf = np.asarray(v, float), np.asarray(sf, float)
+    lo = np.zeros(len(v)) if lo is None else np.asarray(lo, float)
+    if np.any(lo > 1.0 + 1e-12) or float((sf * lo).sum()) > N * (1.0 + 1e-12):
+        return None, None
     ratio = v / sf
     order = np.argsort(-ratio, kind="stable")
-    x = np.zeros(len(v))
-    used, i = 0.0, 0
+    x = np.minimum(lo, 1.0).copy()
+    used, i = float((sf * x).sum()), 0
     while i < len(order):
         i0, r = i, ratio[order[i]]
         while i < len(order) and abs(ratio[order[i]] - r) <= 1e-12 * abs(r):
             i += 1
         grp = order[i0:i]
-        need = float(sf[grp].sum())
+        need = float((sf[grp] * (1.0 - x[grp])).sum())
         if not r > 0.0:
             break
         if used + need <= N:
@@ -201,7 +222,7 @@ def max_sum_pooled_centre(v, sf, N):
             used += need
         else:
             if N - used > 1e-12 * N:
-                x[grp] = analytic_centre_tied(sf[grp], N - used)
+                x[grp] = analytic_centre_tied(sf[grp], (N - used) + float((sf[grp] * x[grp]).sum()), lo[grp])
             break
     return x, float((v * x).sum())
 

@@ -514,8 +514,9 @@ int swb_policy_pooled(swb_ctx *c, int32_t mode, int32_t J, double N, const doubl
   if (den) CK(cudaMemcpyAsync(c->pol_den.p, den, b, cudaMemcpyHostToDevice, c->st));
   swb::PolicyLaunch L;
   L.mode = mode; L.J = J; L.N = N;
-  L.coef = c->pol_coef.as<double>(); L.sf = c->pol_sf.as<double>(); L.t = c->pol_t.as<double>();
-  L.n = c->pol_n.as<double>(); L.den = c->pol_den.as<double>();
+  L.coef = c->pol_coef.as<double>(); L.sf = c->pol_sf.as<double>();
+  L.t = t ? c->pol_t.as<double>() : nullptr;        // MAXSUM: optional SLO floors
+  L.n = n ? c->pol_n.as<double>() : nullptr; L.den = den ? c->pol_den.as<double>() : nullptr;
   L.x = c->pol_x.as<double>(); L.out = c->pol_out.as<double>();
   CK(swb::launch_policy(L, c->st));
   double out[2] = {0.0, 0.0};

@@ -213,60 +213,115 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(PolicyLaunch L) {
         }
         __syncthreads();
       }
-    // jobs strictly above the threshold ratio get x = 1, below 0; the group TIED at the threshold shares what is
-    // left: interior-point selection = max sum log x + log(1-x) s.t. sum sf x = C over the group
+    // Optional SLO floors lo_j <= x_j (max_sum_throughput.py:87-93; L.t carries lo, null = none).  Jobs strictly
+    // above the threshold ratio get x = 1, below it their floor; the group TIED at the threshold shares what is left:
+    // interior-point selection = max sum 1{lo>0} log(x-lo) + log x + log(1-x) s.t. sum sf x = C over the group
     // (oracle/gavel_lp.py:max_sum_pooled_centre).  One thread finds the group (order-exact sums).
     __shared__ int s_i0, s_i1;
     __shared__ double s_C, s_tot;
+    const double *lob = L.t;
+    {
+      double base = 0.0, bad = 0.0;
+      for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        const double l = lob ? lob[j] : 0.0;
+        if (l > 1.0 + 1e-12) bad += 1.0;
+        base += L.sf[j] * l;
+      }
+      br.sum2(base, bad);
+      if (bad > 0.0 || base > N * (1.0 + 1e-12)) status = 1;    // the floors alone do not fit: caller re-solves without them
+    }
+    if (status == 0) {
     if (threadIdx.x == 0) {
       double used = 0.0, tot = 0.0;
+      for (int j = 0; j < J; ++j) { const double l = lob ? fmin(lob[j], 1.0) : 0.0; used += L.sf[j] * l; tot += L.coef[j] * l; }
       int i = 0, g0 = J, g1 = J;
       double C = 0.0;
       while (i < J) {
         const int i0 = i;
         const double r = L.coef[idx[i]] / L.sf[idx[i]];
-        double need = 0.0, val = 0.0;
+        double need = 0.0, val = 0.0, floor_w = 0.0;
         while (i < J) {
           const int j = idx[i];
           const double rj = L.coef[j] / L.sf[j];
           if (fabs(rj - r) > 1e-12 * fabs(r)) break;
-          need += L.sf[j]; val += L.coef[j];
+          const double l = lob ? fmin(lob[j], 1.0) : 0.0;
+          need += L.sf[j] * (1.0 - l); val += L.coef[j] * (1.0 - l); floor_w += L.sf[j] * l;
           ++i;
         }
         if (!(r > 0.0)) { g0 = g1 = i0; break; }
         if (used + need <= N) { used += need; tot += val; g0 = g1 = i; }
-        else { g0 = i0; g1 = i; C = N - used; break; }
+        else { g0 = i0; g1 = i; C = (N - used) + floor_w; if (!(N - used > 1e-12 * N)) g1 = g0; break; }
       }
       s_i0 = g0; s_i1 = g1; s_C = C; s_tot = tot;
     }
     __syncthreads();
     const int i0 = s_i0, i1 = s_i1;
     const double C = s_C;
-    for (int i = threadIdx.x; i < J; i += blockDim.x) L.x[idx[i]] = i < i0 ? 1.0 : 0.0;
+    for (int i = threadIdx.x; i < J; i += blockDim.x) {
+      const int j = idx[i];
+      L.x[j] = i < i0 ? 1.0 : (lob ? fmin(lob[j], 1.0) : 0.0);
+    }
     double part = 0.0;
-    if (i1 > i0 && C > 1e-12 * N) {
-      double lo = -1e12, hi = 1e12;
-      for (int it = 0; it < 130; ++it) {
-        const double nu = 0.5 * (lo + hi);
-        double load = 0.0;
-        for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-          const double a = nu * L.sf[idx[i]];
-          load += L.sf[idx[i]] * (2.0 / ((a + 2.0) + sqrt(a * a + 4.0)));
-        }
-        load = br.sum(load);
-        if (load > C) lo = nu; else hi = nu;
+    if (i1 > i0) {
+      // x_j(nu): root of 1/x - 1/(1-x) + w/(x-lo) = nu sf on (lo, 1) (decreasing in x and in nu); sum sf x_j(nu) = C
+      double xs[POL_MAXJ_PER_THREAD];
+      int cnt = 0;
+      for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x, ++cnt) {
+        const double l = lob ? fmin(lob[idx[i]], 1.0) : 0.0;
+        xs[cnt] = 0.5 * (l + 1.0);
       }
-      const double nu = 0.5 * (lo + hi);
-      for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+      auto load_at = [&](double nu) -> double {
+        double load = 0.0;
+        int q = 0;
+        for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x, ++q) {
+          const int j = idx[i];
+          const double l0 = lob ? fmin(lob[j], 1.0) : 0.0, w = l0 > 0.0 ? 1.0 : 0.0, ls = nu * L.sf[j];
+          double x = xs[q];
+          if (l0 >= 1.0) { x = 1.0; }
+          else {
+            double l = l0, h = 1.0;
+            for (int k = 0; k < 80; ++k) {
+              const double d1 = 1.0 - x;
+              double f = 1.0 / x - 1.0 / d1 - ls, fp = 1.0 / (x * x) + 1.0 / (d1 * d1);
+              if (w > 0.0) { const double d0 = x - l0; f += 1.0 / d0; fp += 1.0 / (d0 * d0); }
+              if (f == 0.0) break;
+              if (f > 0.0) l = x; else h = x;
+              double xn = x + f / fp;
+              if (xn == x) break;
+              if (!(xn > l && xn < h)) xn = 0.5 * (l + h);
+              const bool done = fabs(xn - x) <= 2e-15 * xn;
+              x = xn;
+              if (done) break;
+            }
+          }
+          xs[q] = x;
+          load += L.sf[j] * x;
+        }
+        return br.sum(load);
+      };
+      // bracket nu by expansion from 0, then bisection (load is decreasing in nu)
+      double lo_nu, hi_nu;
+      if (load_at(0.0) > C) { lo_nu = 0.0; hi_nu = 1.0; for (int e = 0; e < 60 && load_at(hi_nu) > C; ++e) { lo_nu = hi_nu; hi_nu *= 4.0; } }
+      else { hi_nu = 0.0; lo_nu = -1.0; for (int e = 0; e < 60 && load_at(lo_nu) <= C; ++e) { hi_nu = lo_nu; lo_nu *= 4.0; } }
+      for (int it = 0; it < 100; ++it) {
+        const double nu = 0.5 * (lo_nu + hi_nu);
+        if (load_at(nu) > C) lo_nu = nu; else hi_nu = nu;
+        if (hi_nu - lo_nu <= 1e-15 * fmax(fabs(hi_nu), fabs(lo_nu))) break;
+      }
+      load_at(0.5 * (lo_nu + hi_nu));
+      int q = 0;
+      for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x, ++q) {
         const int j = idx[i];
-        const double a = nu * L.sf[j];
-        const double xj = 2.0 / ((a + 2.0) + sqrt(a * a + 4.0));
-        L.x[j] = xj;
-        part += xj * L.coef[j];
+        const double l = lob ? fmin(lob[j], 1.0) : 0.0;
+        L.x[j] = xs[q];
+        part += (xs[q] - l) * L.coef[j];
       }
     }
     part = br.sum(part);
     obj = s_tot + part;
+    } else {
+      for (int j = threadIdx.x; j < J; j += blockDim.x) L.x[j] = 0.0;
+    }
   } else if (L.mode == SWB_POL_ISOLATED) {
     // isolated.py:35-55 / proportional.py:26-43 / gandiva_fair_proportional.py:26-41 (pooled):
     // coef_j carries the per-job divisor (sf_j for Isolated, 1 otherwise); rows are normalised to <= 1

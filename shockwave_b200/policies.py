@@ -11,7 +11,7 @@ The LP each policy hands to cvxpy is solved on the GPU (no CPU fallback):
     homogeneous clusters Shockwave targets: closed forms / 1-D searches;
   * swb_policy_hetero (hetero.cu) for genuinely heterogeneous *_Perf calls with up to 3 worker types that have
     capacity (k80 / p100 / v100): bisection on the scalar objective + Dantzig-Wolfe on the capacity rows.
-More than 3 live worker types, and SLO rows, raise NotImplementedError.
+More than 3 live worker types, and SLO rows on heterogeneous types, raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -332,8 +332,6 @@ class ThroughputNormalizedByCostSumWithPerfSLOs(Policy):
         throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
         if throughputs is None:
             return None
-        if SLOs:
-            raise NotImplementedError("SLO rows (max_sum_throughput.py:87-93) are not solved on the GPU yet")
         job_ids, worker_types = index
         thr, N, share = self._pool(throughputs)
         sf = np.array([scale_factors[j] for j in job_ids], dtype=np.float64)
@@ -342,9 +340,22 @@ class ThroughputNormalizedByCostSumWithPerfSLOs(Policy):
             cost = np.array([instance_costs[w] for w in worker_types], dtype=np.float64)
         live_cost = cost[np.asarray(self._num_workers) > 0]
         if thr is None or not np.allclose(live_cost, live_cost[0]):
+            if SLOs:
+                raise NotImplementedError("SLO rows (max_sum_throughput.py:87-93) with heterogeneous worker types "
+                                          "are not solved on the GPU")
             x, self.last_objective, _ = self._solve_hetero(POL_MAXSUM, throughputs / cost[None, :], sf)
             return super().unflatten(x, index)
-        x, self.last_objective, _ = _pooled(POL_MAXSUM, N, thr / live_cost[0], sf)
+        lo = None
+        if SLOs:        # max_sum_throughput.py:87-93: sum_w thr_jw x_jw >= num_steps_remaining_j / SLO_j
+            lo = np.zeros(len(job_ids))
+            for job_id in SLOs:
+                i = job_ids.index(job_id)
+                assert job_id in num_steps_remaining
+                lo[i] = (num_steps_remaining[job_id] / SLOs[job_id]) / thr[i]
+        x, self.last_objective, rc = _pooled(POL_MAXSUM, N, thr / live_cost[0], sf, t=lo)
+        if rc != 0:     # "x.value is None": the reference warns and solves again without the SLO rows (:100-104)
+            print("WARNING: No allocation possible with provided SLOs!")
+            x, self.last_objective, rc = _pooled(POL_MAXSUM, N, thr / live_cost[0], sf)
         return super().unflatten(self._split(x, share), index)
 
 

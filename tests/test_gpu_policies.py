@@ -124,7 +124,7 @@ def test_closed_forms_and_edge_cases():
     assert P.get_policy("finish_time_fairness").name.startswith("FinishTimeFairness")
     assert P.get_policy("shockwave").name == "shockwave"
     het, sf2, spec2, _ = _instance(6, SPECS[1], seed=4, equal_columns=False)
-    with pytest.raises(NotImplementedError):      # SLO rows are not on the GPU
+    with pytest.raises(NotImplementedError):      # SLO rows with heterogeneous types are not on the GPU
         P.ThroughputNormalizedByCostSumWithPerfSLOs(solver=None).get_allocation(
             het, sf2, spec2, SLOs={0: 100.0}, num_steps_remaining={0: 10.0})
 
@@ -223,3 +223,41 @@ def test_pooled_random_sweep_against_oracle_centre():
             assert x.min() >= 0 and x.max() <= 1 + 1e-12 and (sf * x).sum() <= N * (1 + 1e-9)
             worst = max(worst, np.abs(x - xo).max())
     print("pooled random sweep: worst |x - x_oracle|", worst)
+
+
+@pytest.mark.parametrize("J,spec,kinds", [(20, SPECS[0], 0), (120, SPECS[0], 3), (96, SPECS[1], 0), (600, SPECS[2], 5)])
+def test_max_sum_with_slos(J, spec, kinds):
+    """ThroughputNormalizedByCostSum_PerfSLOs (max_sum_throughput.py:49-108): SLO rows as floors on x, the reference's
+    fall-back to the SLO-free program when they do not fit, objective vs the HiGHS LP, x vs the oracle selection."""
+    from oracle import gavel_backend as gb
+    rng = np.random.default_rng(4000 + J)
+    col = rng.uniform(0.5, 20.0, J) if not kinds else rng.uniform(0.5, 20.0, kinds)[rng.integers(0, kinds, J)]
+    thr = {j: {w: float(col[j]) for w in WT} for j in range(J)}
+    sf = {j: int(rng.choice([1, 2, 4, 8], p=[0.6, 0.3, 0.09, 0.01])) for j in range(J)}
+    steps = {j: float(rng.uniform(1e3, 1e5)) for j in range(J)}
+    N = np.array([spec[w] for w in WT], float)
+    s = np.array([sf[j] for j in range(J)], float)
+    costs = {"k80": 1.5, "p100": 1.5, "v100": 1.5}
+    # SLOs that fit: a fifth of the jobs must finish within 2-20x their full-speed time, scaled so the floors use < 60 % of the cluster
+    slo_jobs = [j for j in range(J) if rng.random() < 0.2] or [0]
+    slos = {j: steps[j] / col[j] * float(rng.uniform(2.0, 20.0)) for j in slo_jobs}
+    lo = np.zeros(J)
+    for j in slo_jobs:
+        lo[j] = steps[j] / slos[j] / col[j]
+    scale = max(1.0, (s * lo).sum() / (0.6 * N.sum()))
+    slos = {j: v * scale for j, v in slos.items()}
+    lo = lo / scale
+    pol = P.ThroughputNormalizedByCostSumWithPerfSLOs(solver="ECOS")
+    x = _mat(pol.get_allocation(thr, sf, dict(spec), instance_costs=costs, SLOs=slos, num_steps_remaining=steps), J)
+    _check_base(x, sf, spec, J)
+    xj = x.sum(axis=1)
+    assert np.all(xj >= lo * (1 - 1e-9))
+    v, _ = gl.max_sum_throughput((col / 1.5)[:, None], s, [N.sum()], need=lo * col / 1.5)
+    assert abs(pol.last_objective - v) <= 1e-7 * v
+    xo, _, rco = gb.pooled_cpu(P.POL_MAXSUM, N.sum(), col / 1.5, s, t=lo)
+    assert rco == 0 and np.abs(xj - xo).max() <= 1e-6, np.abs(xj - xo).max()
+    # SLOs that cannot be met: the reference re-solves without them
+    hard = {j: slos[j] * 1e-6 for j in slo_jobs}
+    x2 = _mat(pol.get_allocation(thr, sf, dict(spec), instance_costs=costs, SLOs=hard, num_steps_remaining=steps), J)
+    x3 = _mat(P.ThroughputNormalizedByCostSumWithPerf(solver="ECOS").get_allocation(thr, sf, dict(spec), costs), J)
+    assert np.allclose(x2, x3)
