@@ -14,8 +14,10 @@ and the conversion of the returned J x T byte matrices into the reference's
 """
 from __future__ import annotations
 
+import operator
 import random
 from collections import OrderedDict
+from itertools import repeat
 
 import numpy as np
 
@@ -58,7 +60,13 @@ class ShockwaveScheduler(object):
         self._slots = {}          # jobid -> slot of the device-resident job table
         self._free_slots = []
         self._next_slot = 0
-        self._tl_cache = {}       # jobid -> ((len, last_round, last_value), (nsamples, end_round))
+        # per-slot cache of the throughput-timeline summaries (see _timeline_summaries)
+        self._tl_len = np.full(64, -1, dtype=np.int64)      # signature: number of entries ...
+        self._tl_key = np.full(64, -2, dtype=np.int64)      # ... last round ...
+        self._tl_val = np.empty(64, dtype=object)           # ... and its value
+        self._tl_ns = np.zeros(64, dtype=np.float64)        # summary: measured samples
+        self._tl_end = np.full(64, -1, dtype=np.int32)      # summary: last measured round
+        self._slot_arr = None     # slots in metadata order, rebuilt after add / remove
         self.last_result = None   # scalars of the latest solve (objective, status, ...)
 
         assert type(init_metadata) == OrderedDict
@@ -88,12 +96,22 @@ class ShockwaveScheduler(object):
                             float("nan") if ts is None else ts,
                             job.epoch_duration_preprofiled, job.bs_schedule)
         self._slots[jobid] = slot
+        self._slot_arr = None
+        if slot >= len(self._tl_len):
+            grow = max(2 * len(self._tl_len), slot + 1)
+            for name, fill in (("_tl_len", -1), ("_tl_key", -2), ("_tl_val", None), ("_tl_ns", 0.0), ("_tl_end", -1)):
+                old = getattr(self, name)
+                new = np.empty(grow, dtype=old.dtype)
+                new[:len(old)] = old
+                new[len(old):] = fill
+                setattr(self, name, new)
+        self._tl_len[slot] = -1           # a new tenant of the slot: force a recompute
 
     def _on_remove(self, jobid):
         slot = self._slots.pop(jobid)
         self._eng().job_remove(slot)
         self._free_slots.append(slot)
-        self._tl_cache.pop(jobid, None)
+        self._slot_arr = None
 
     def _timeline_summary(self, jobid, job):
         """(measured_nsamples, end_round) of JobMetaData.py:235-249 for one job."""
@@ -110,33 +128,37 @@ class ShockwaveScheduler(object):
             prev = cur
         return float(nsamp), int(max(tl.keys()))
 
-    def _timeline_summaries(self, jobids, jobobjs):
-        """Vector form, cached per job while its shared throughput OrderedDict is unchanged (signature =
+    def _timeline_summaries(self, jobids, jobobjs, slots):
+        """Vector form, cached per slot while the job's shared throughput OrderedDict is unchanged (signature =
         length + last (round, value) entry; the caller only appends / rewrites the current round,
-        scheduler.py:568-571)."""
+        scheduler.py:568-571).  The per-job work runs in C (map / numpy); Python only touches the jobs whose
+        timeline changed since the previous re-solve."""
         J = len(jobids)
-        tls = [job.throughput_measurements for job in jobobjs]
-        sigs = [(len(t), next(reversed(t.items()), None)) for t in tls]
-        cache = self._tl_cache
-        ns = np.empty(J, dtype=np.float64)
-        end = np.empty(J, dtype=np.int32)
-        old = [cache.get(j) for j in jobids]
-        for i in range(J):
-            hit = old[i]
-            if hit is None or hit[0] != sigs[i]:
-                hit = (sigs[i], self._timeline_summary(jobids[i], jobobjs[i]))
-                cache[jobids[i]] = hit
-            ns[i], end[i] = hit[1]
-        return ns, end
+        tls = list(map(operator.attrgetter("throughput_measurements"), jobobjs))
+        assert None not in tls                      # JobMetaData.py:229
+        lens = np.fromiter(map(len, tls), dtype=np.int64, count=J)
+        lastk_l = list(map(next, map(reversed, tls), repeat(-1)))
+        lastk = np.fromiter(lastk_l, dtype=np.int64, count=J)
+        lastv = list(map(dict.get, tls, lastk_l))
+        changed = (lens != self._tl_len[slots]) | (lastk != self._tl_key[slots])
+        changed |= np.fromiter(map(operator.ne, lastv, self._tl_val[slots]), dtype=bool, count=J)
+        for i in np.flatnonzero(changed).tolist():
+            sl = slots[i]
+            ns_i, end_i = self._timeline_summary(jobids[i], jobobjs[i])
+            self._tl_len[sl], self._tl_key[sl], self._tl_val[sl] = lens[i], lastk[i], lastv[i]
+            self._tl_ns[sl], self._tl_end[sl] = ns_i, end_i
+        return self._tl_ns[slots], self._tl_end[slots]
 
     def _resolve(self, jobids, jobobjs):
         """One re-solve on the device; returns OrderedDict{round -> [job ids]} (shockwave.py:129-161)."""
         J = len(jobids)
         if J == 0:      # nothing to schedule: an empty window (the reference is never called like this)
             return OrderedDict((self.round_ptr + t, []) for t in range(self.future_nrounds))
-        slots = np.fromiter((self._slots[j] for j in jobids), dtype=np.int32, count=J)
-        prog = np.fromiter((job.epoch_progress for job in jobobjs), dtype=np.int32, count=J)
-        ns, end = self._timeline_summaries(jobids, jobobjs)
+        if self._slot_arr is None or len(self._slot_arr) != J:
+            self._slot_arr = np.fromiter(map(self._slots.__getitem__, jobids), dtype=np.int32, count=J)
+        slots = self._slot_arr
+        prog = np.fromiter(map(operator.attrgetter("epoch_progress"), jobobjs), dtype=np.int32, count=J)
+        ns, end = self._timeline_summaries(jobids, jobobjs, slots)
         prm = _eng.make_params(self.ngpus, self.future_nrounds, self.round_duration, self.k, self.lam,
                                self.rhomax, self.logapx_bases, self.logapx_origin, self.round_ptr)
         grd = jobobjs[0].gavel_round_duration
