@@ -204,3 +204,18 @@ def test_edge_cases(engine):
     x = out["x"][0]
     assert x[0].sum() == 0 and x[1].sum() == 0 and x[2].sum() == 5
     assert out["backfill"][0][1].sum() == 0
+
+
+def test_config_c_size_against_recorded_oracle(engine):
+    """BASELINE config C (1024 jobs x 128 GPUs, 20/32-round windows): oracle verdicts / objectives recorded offline
+    (HiGHS, gap 1e-4, 3-9 s each; tests/golden/config_c_oracle.json).  P1 + P2 (1e-3) + P3."""
+    import json
+    import os
+    recs = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config_c_oracle.json")))
+    for p in recs:
+        pb = synth_problem(p["J"], p["G"], p["T"], p["D"], seed=p["seed"], tight=p["tight"])
+        prm = make_params(p["G"], p["T"], p["D"], p["k"], p["lam"], 1.0, fx.BASES, fx.ORIGIN, round_ptr=pb["round_ptr"])
+        out = engine.solve(prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"])
+        obj = check_against(out, 0, pb, p["G"], p["T"], p["D"], p["k"], p["objective"], p["status"])
+        print("config C", p["J"], p["G"], p["T"], "k", p["k"], "status", p["status"], "gap",
+              (p["objective"] - obj) / abs(p["objective"]))
