@@ -219,3 +219,31 @@ def test_config_c_size_against_recorded_oracle(engine):
         obj = check_against(out, 0, pb, p["G"], p["T"], p["D"], p["k"], p["objective"], p["status"])
         print("config C", p["J"], p["G"], p["T"], "k", p["k"], "status", p["status"], "gap",
               (p["objective"] - obj) / abs(p["objective"]))
+
+
+def test_config_d_size_against_recorded_lp_relaxation(engine):
+    """BASELINE config D (4096 jobs x 512 GPUs x 64 rounds): the MILP oracle finds no incumbent at this size, but the
+    HiGHS LP relaxation (70 s, recorded in tests/golden/config_d_lp.json) bounds it.  P4 at full size: the GPU's exact
+    relaxed optimum equals the LP optimum to 1e-4, and the integral schedule is within 1e-3 of that bound — hence
+    within 1e-3 of the (unknown) MILP optimum."""
+    import json
+    import os
+    recs = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config_d_lp.json")))
+    engine.set_option(1, 1)        # SWB_OPT_RELAXED_OPTIMUM
+    try:
+        for p in recs:
+            pb = synth_problem(p["J"], p["G"], p["T"], p["D"], seed=p["seed"], tight=p["tight"])
+            prm = make_params(p["G"], p["T"], p["D"], p["k"], p["lam"], 1.0, fx.BASES, fx.ORIGIN, round_ptr=pb["round_ptr"])
+            out = engine.solve(prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"])
+            res = out["results"][0]
+            assert res["status"] == p["status"]
+            lp = p["lp_objective"]
+            rel = abs(res["relaxed_objective"] - lp) / abs(lp)
+            gap = (lp - res["objective"]) / abs(lp)
+            print("config D", p["k"], "relaxed", res["relaxed_objective"], "LP", lp, "rel", rel, "integral gap to the bound", gap)
+            assert rel <= 1e-4
+            assert -1e-9 <= gap <= 1e-3
+            x = out["x"][0]
+            assert np.all(x.T.astype(np.int64) @ pb["g"].astype(np.int64) <= p["G"])
+    finally:
+        engine.set_option(1, 0)
