@@ -137,12 +137,16 @@ def _solve(g, E, c, dbar, R, w, G, T, D, k, bases, logv, ftf_cap, rel_gap, time_
     block(np.concatenate([jj, np.repeat(jj, T)]),
           np.concatenate([oP + jj, oX + np.arange(J * T)]),
           np.concatenate([dbar, np.full(J * T, -float(D))]), -np.inf, 0.0, J)
-    # pwl_u: sum_b lambda_jb base_b - p_j/E_j = c_j/E_j           (row j)
-    block(np.concatenate([np.repeat(jj, B), jj]),
-          np.concatenate([oL + np.arange(J * B), oP + jj]),
-          np.concatenate([np.tile(np.asarray(bases, dtype=float), J), -1.0 / Ef]), cf / Ef, cf / Ef, J)
-    # pwl_1: sum_b lambda_jb = 1                                  (row j)
-    block(np.repeat(jj, B), oL + np.arange(J * B), np.ones(J * B), 1.0, 1.0, J)
+    # pwl_u: sum_b lambda_jb base_b - p_j/E_j = c_j/E_j           (row 2j)
+    # pwl_1: sum_b lambda_jb = 1                                  (row 2j+1)
+    # interleaved per job: the row order is part of what the end-to-end pin (tests/golden/tacc32_oracle_pin.json) was
+    # recorded with — HiGHS' branch and bound returns a different, equally optimal-within-gap incumbent otherwise
+    rhs = np.empty(2 * J)
+    rhs[0::2] = cf / Ef
+    rhs[1::2] = 1.0
+    block(np.concatenate([np.repeat(2 * jj, B), 2 * jj, np.repeat(2 * jj + 1, B)]),
+          np.concatenate([oL + np.arange(J * B), oP + jj, oL + np.arange(J * B)]),
+          np.concatenate([np.tile(np.asarray(bases, dtype=float), J), -1.0 / Ef, np.ones(J * B)]), rhs, rhs, 2 * J)
     if with_sos2:
         for j in range(J):
             zb = oZ + j * B

@@ -3,6 +3,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 from oracle import shockwave_milp as om
 from tests import fixtures as fx
@@ -92,3 +93,17 @@ def test_momentumed_average_matches_reference_formula():
     want = 0.9 * (2 / 8 * 100 + 4 / 8 * 200 + 2 / 8 * 50) + 0.1 * 50
     assert abs(got - want) < 1e-12
     assert om.finish_time_momentumed_average([(4, 77.0)], 4) == 0.9 * 77.0 + 0.1 * 77.0
+
+
+def test_live_pin_is_what_the_current_oracle_produces():
+    """The pin above is a recorded number; this re-runs the unmodified reference simulator with the CURRENT oracle
+    (needs /root/reference, ~1 min) and demands the recorded metrics exactly — HiGHS is deterministic, so any drift
+    means the oracle's model changed (even a row reordering moves the closed loop by a few per cent)."""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("reference tree not present")
+    pin = json.load(open(os.path.join(HERE, "golden", "tacc32_oracle_pin.json")))["oracle"]
+    out = rh.simulate("shockwave", shockwave_scheduler_cls=rh.make_oracle_scheduler_cls())
+    assert abs(out["makespan"] - pin["makespan"]) <= 1e-9 * pin["makespan"], (out["makespan"], pin["makespan"])
+    assert abs(out["avg_jct"] - pin["avg_jct"]) <= 1e-9 * pin["avg_jct"]
+    assert len(out["per_round_schedule"]) == pin["rounds"]
