@@ -149,7 +149,10 @@ def simulate(policy_name, shockwave_scheduler_cls=None, policy_obj=None,
 # by (a) the REFERENCE's own JobMetaData methods for the forecast and (b) oracle/shockwave_milp.py
 # (HiGHS) for the solve.  Used to pin the oracle against the golden pickles and to record fixtures.
 # ---------------------------------------------------------------------------------------------
-def make_oracle_scheduler_cls(record=None, rel_gap=1e-3, time_limit=15.0):
+def make_oracle_scheduler_cls(record=None, rel_gap=1e-3, time_limit=15.0, placement=None):
+    """placement: optional callable(n, g, G, T, bfkey, fallback=, w=) -> dict(x=...) that replaces the solver's own x
+    (and the re-rank MILP) by a placement RULE applied to the solver's round counts — used to run the product's placement
+    rule (tests/ref_placement.py, the numpy restatement of place.cu) closed-loop."""
     import random as _random
 
     import numpy as _np
@@ -219,7 +222,13 @@ def make_oracle_scheduler_cls(record=None, rel_gap=1e-3, time_limit=15.0):
                 ok, x, p, obj = om._solve(g, E.astype(float), c.astype(float), dbar, R, weights, G, T, D,
                                           self.k, self.logapx_bases, logv, None, rel_gap, time_limit)
                 assert ok
-                x = om.rank_in_schedule(x, weights, g, G, rel_gap, time_limit)
+                if placement is None:
+                    x = om.rank_in_schedule(x, weights, g, G, rel_gap, time_limit)
+            if placement is not None:
+                counts = _np.round(_np.asarray(x)).sum(axis=1).astype(_np.int64)
+                placed = placement(counts, g, G, T, _np.zeros(J), fallback=(status == om.STATUS_FALLBACK), w=weights)
+                assert placed["shortfall"] == 0, "the placement rule could not seat the solver's counts"
+                x = placed["x"].astype(float)
             # construct_schedules, shockwave.py:213-285, with the reference's per-round sort-key calls
             sched = OrderedDict()
             bfkey0 = _np.full(J, _np.nan)

@@ -107,3 +107,17 @@ def test_live_pin_is_what_the_current_oracle_produces():
     assert abs(out["makespan"] - pin["makespan"]) <= 1e-9 * pin["makespan"], (out["makespan"], pin["makespan"])
     assert abs(out["avg_jct"] - pin["avg_jct"]) <= 1e-9 * pin["avg_jct"]
     assert len(out["per_round_schedule"]) == pin["rounds"]
+
+
+def test_product_placement_rule_closed_loop_pin():
+    """P5 as far as it can be taken without a GPU next to the reference: the unmodified reference simulator with HiGHS
+    for the round counts and the PRODUCT's placement rule (tests/ref_placement.py, which place.cu matches bit for bit)
+    for the rounds themselves stays inside the 3 % spread of the reference's own Shockwave pickles
+    (tests/golden/make_placement_pin.py)."""
+    pin = json.load(open(os.path.join(HERE, "golden", "tacc32_placement_pin.json")))
+    o, g = pin["product_placement"], pin["golden"]
+    for key in ("makespan", "avg_jct", "cluster_util"):
+        assert abs(o[key] - g[key]) / g[key] < 0.03, (key, o[key], g[key])
+    assert abs(o["rounds"] - g["rounds"]) <= 6
+    assert abs(o["worst_ftf"] - g["worst_ftf"]) / g["worst_ftf"] < 0.10
+    assert abs(o["unfair_frac"] - g["unfair_frac"]) < 0.03
