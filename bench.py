@@ -120,13 +120,10 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    # one single-threaded HiGHS process per host core (~0.35 GB each at this size), bounded by the memory that is free
-    try:
-        import psutil
-        mem_cap = int(psutil.virtual_memory().available / 2**30 / 1.0)
-    except Exception:
-        mem_cap = 16
-    cores = max(1, min(os.cpu_count() or 1, 64, mem_cap))
+    # one single-threaded HiGHS process per host core, at most 16: with 64 concurrent processes on the 128-core GPU box
+    # one step took 416 s instead of ~70 s (memory-bandwidth contention) for barely more throughput (0.154 vs 0.10
+    # rounds/s) — past 16 the run no longer finishes "within a few minutes"
+    cores = max(1, min(os.cpu_count() or 1, 16))
     steps = max(1, min(args.steps, 2))          # one step is ~70-100 s of CPU at this size
     solved, walls = [], []
     with mp.get_context("spawn").Pool(cores) as pool:
