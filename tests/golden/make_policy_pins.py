@@ -23,7 +23,7 @@ SUFFIX = "_120_0.2_5_100_40_25_0,0.5,0.5_0.6,0.3,0.09,0.01_multigpu_dynamic_simu
 def summary(r):
     ftf = np.asarray(r["finish_time_fairness_list"], dtype=float)
     return dict(makespan=float(r["makespan"]), avg_jct=float(r["avg_jct"]), cluster_util=float(r["cluster_util"]),
-                rounds=len(r["per_round_schedule"]), worst_ftf=float(ftf.max()), unfair_frac=float((ftf > 1.1).mean()))
+                rounds=len(r["per_round_schedule"]), worst_ftf=float(ftf.max()), unfair_frac=float((ftf > 1.05).mean()))
 
 
 def main():
