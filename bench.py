@@ -407,7 +407,10 @@ def main():
                    "mc_forecast": {"paths_per_job": P_MC, "paths_this_rank": mc_n, "horizon_epochs": "min(E-c, 256)",
                                    "kernel_ms": mc_ms, "allreduce": "NCCL SUM of [2][J] float64 (64 KiB)" if world > 1 else "none (1 GPU)"},
                    "l2": "flushed between timed steps (256 MiB write); per-step CUDA events on the launching stream, summed",
-                   "parallelism": f"scenario-sharded x{world}, no data-path collective"},
+                   "parallelism": f"scenario-sharded x{world}, no data-path collective",
+                   "scaling_note": "scenarios per GPU are fixed (weak scaling); the 8192 Monte-Carlo paths per job are a fixed "
+                                   "TOTAL sharded over the ranks (BASELINE config D), so the forecast's share of the step "
+                                   "shrinks with N and value can grow faster than N"},
         "clocks": clocks,
         "gpu_launches": launches,
         "kernels_ms": {"solve_kernel": ms_solve, "place_kernel": ms_place, "gbm_kernel": mc_ms},
