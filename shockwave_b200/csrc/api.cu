@@ -532,7 +532,8 @@ int swb_policy_hetero(swb_ctx *c, int32_t mode, int32_t J, int32_t W, const doub
                       double *objective, int32_t *stats) {
   if (!c || !N || !a || !sf || !x) return fail(SWB_ERR_ARG, "swb_policy_hetero: null argument");
   if (J <= 0 || J > SWB_MAX_J) return fail(SWB_ERR_ARG, "swb_policy_hetero: J must be in [1, 8192]");
-  if (W <= 0 || W > 3) return fail(SWB_ERR_ARG, "swb_policy_hetero: W must be in [1, 3]");
+  if (W <= 0 || W > 4 || (mode == SWB_POL_MAXSUM && W > 3))
+    return fail(SWB_ERR_ARG, "swb_policy_hetero: W must be in [1, 4] (max-sum: [1, 3])");
   if (mode < SWB_POL_MAXMIN || mode > SWB_POL_MAXSUM) return fail(SWB_ERR_ARG, "swb_policy_hetero: bad mode");
   if (mode == SWB_POL_FTF && (!t || !n || !den)) return fail(SWB_ERR_ARG, "swb_policy_hetero: FTF needs t, n, den");
   if (mode == SWB_POL_MTD && !n) return fail(SWB_ERR_ARG, "swb_policy_hetero: MTD needs n");

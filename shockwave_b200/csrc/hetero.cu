@@ -1,4 +1,4 @@
-// hetero.cu — Gavel policies' get_allocation() on the GPU for HETEROGENEOUS worker types (W <= 3).
+// hetero.cu — Gavel policies' get_allocation() on the GPU for HETEROGENEOUS worker types (W <= 4; max-sum W <= 3).
 //
 // Replaces the cvxpy -> ECOS / Gurobi LP solves of
 //   MaxMinFairnessPolicyWithPerf        scheduler/policies/max_min_fairness.py:53-113
@@ -568,6 +568,7 @@ cudaError_t launch_hetero(const HeteroLaunch &L, cudaStream_t st) {
     case 1: if (sum) hetero_kernel<1, 2><<<1, 1024, 0, st>>>(L); else hetero_kernel<1, 1><<<1, 1024, 0, st>>>(L); break;
     case 2: if (sum) hetero_kernel<2, 3><<<1, 1024, 0, st>>>(L); else hetero_kernel<2, 2><<<1, 1024, 0, st>>>(L); break;
     case 3: if (sum) hetero_kernel<3, 4><<<1, 1024, 0, st>>>(L); else hetero_kernel<3, 3><<<1, 1024, 0, st>>>(L); break;
+    case 4: if (sum) return cudaErrorInvalidValue; hetero_kernel<4, 4><<<1, 1024, 0, st>>>(L); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -66,8 +66,8 @@ def _hetero(mode, N, a, sf, t=None, n=None, den=None):
     arr = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
     a, sf, t, n, den, N = arr(a), arr(sf), arr(t), arr(n), arr(den), arr(N)
     J, W = a.shape
-    if W > 3:
-        raise NotImplementedError("more than 3 worker types with capacity: not solved on the GPU in this release")
+    if W > 4 or (mode == POL_MAXSUM and W > 3):
+        raise NotImplementedError("more than 4 worker types with capacity (3 for max-sum): not solved on the GPU in this release")
     x = np.zeros((J, W), dtype=np.float64)
     obj = C.c_double()
     stats = np.zeros(2, dtype=np.int32)

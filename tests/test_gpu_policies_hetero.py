@@ -160,3 +160,22 @@ def test_random_sweep_hetero():
         assert abs((a * x).sum() - v) <= 1e-6 * v
         worst = max(worst, abs(obj - v) / abs(v))
     print("hetero random sweep: worst relative objective difference vs HiGHS", worst)
+
+
+def test_four_worker_types():
+    """W = 4 (one more type than Gavel's k80 / p100 / v100) for the three programs with a per-job requirement."""
+    rng = np.random.default_rng(91)
+    for it in range(12):
+        J = int(rng.integers(3, 60))
+        a = rng.uniform(0.2, 10.0, size=(J, 1)) * rng.uniform(0.05, 1.0, size=(J, 4))
+        sf = rng.choice([1.0, 2.0, 4.0], J)
+        N = np.maximum(np.round(rng.integers(1, 2 * J + 2, 4) * rng.choice([0.25, 1.0])), 1.0)
+        x, obj, rc = P._hetero(P.POL_MAXMIN, N, a, sf)
+        z, _ = gl.max_min(a, sf, N)
+        assert rc == 0 and abs(obj - z) <= 1e-6 * abs(z), (it, obj, z)
+        assert np.all(x.sum(axis=1) <= 1 + 1e-9) and np.all((x * sf[:, None]).sum(axis=0) <= N * (1 + 1e-9))
+        n = rng.uniform(1e3, 1e5, J)
+        x, T, rc = P._hetero(P.POL_MTD, N, a, sf, n=n)
+        To, _ = gl.min_total_duration_perf(a, sf, n, N)
+        assert rc == 0 and T == To
+        assert np.all((a * x).sum(axis=1) >= n / T * (1 - 1e-9))
