@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import copy
 import ctypes as C
+import operator
 
 import numpy as np
 
@@ -98,13 +99,18 @@ class Policy:
         self._num_workers = [cluster_spec[w] for w in worker_types]
         if len(worker_types) == 0:
             return None, None
-        m = np.array([[d[j][w] for w in worker_types] for j in job_ids], dtype=np.float64)
+        # the dict-of-dicts walk runs in C: map + itemgetter instead of a nested Python loop
+        rows = map(d.__getitem__, job_ids)
+        if len(worker_types) == 1:
+            m = np.fromiter(map(operator.itemgetter(worker_types[0]), rows), dtype=np.float64,
+                            count=len(job_ids)).reshape(-1, 1)
+        else:
+            m = np.array(list(map(operator.itemgetter(*worker_types), rows)), dtype=np.float64)
         return m, (job_ids, worker_types)
 
     def unflatten(self, m, index):
         job_ids, worker_types = index
-        return {job_ids[i]: {worker_types[j]: m[i][j] for j in range(len(worker_types))}
-                for i in range(len(job_ids))}
+        return {jid: dict(zip(worker_types, row)) for jid, row in zip(job_ids, np.asarray(m).tolist())}
 
     # ---- pooling of the worker types (see module docstring) ----
     def _pool(self, throughputs):
