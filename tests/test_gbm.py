@@ -49,6 +49,24 @@ def test_result_does_not_depend_on_path_sharding(engine):
     assert not np.allclose(other[0], full[0], rtol=1e-9)    # the seed matters
 
 
+@pytest.mark.gpu
+def test_single_paths_match_the_numpy_restatement(engine):
+    """The kernel against tests/ref_gbm.py path by path (P_local = 1 at several global path ids): stream keying,
+    Box-Muller pairing and the running sum; tolerance = the fast fp32 intrinsics of the kernel."""
+    from tests.ref_gbm import path_value
+    R0, H, mu, sigma = _params(24, seed=5)
+    H[:4] = [1, 2, 3, 256]
+    worst = 0.0
+    for gp in (0, 1, 7, 4095, 8191, 123456789):
+        out = engine.gbm_forecast(R0, H, mu, sigma, 1, gp, 99)
+        for j in range(len(R0)):
+            want = path_value(99, j, gp, R0[j], int(H[j]), mu[j], sigma[j])
+            worst = max(worst, abs(out[0, j] - want) / want)
+            assert abs(out[0, j] - want) <= 2e-4 * want, (gp, j, out[0, j], want)
+            assert abs(out[1, j] - out[0, j] ** 2) <= 1e-9 * out[0, j] ** 2
+    print("gbm kernel vs numpy path restatement: worst relative difference", worst)
+
+
 def test_path_range_partitions_exactly():
     for P in (1, 7, 8192, 8193):
         for w in (1, 2, 3, 8):
