@@ -42,12 +42,13 @@ def test_shockwave_closed_loop_matches_golden_pickle():
 
 @pytest.mark.skipif(not _have_both(), reason="needs a B200 and /root/reference at the same time")
 @pytest.mark.parametrize("policy", ["max_min_fairness", "finish_time_fairness", "min_total_duration",
-                                    "max_sum_throughput_perf", "gandiva_fair"])
+                                    "max_sum_throughput_perf", "allox", "gandiva_fair"])
 def test_gavel_policy_closed_loop_matches_golden_pickle(policy):
     from oracle import ref_harness as rh
     from shockwave_b200 import policies
     out = rh.simulate(policy, policy_obj=policies.get_policy(policy, solver="ECOS", seed=0))
     gold = pickle.load(open(glob.glob(os.path.join(GOLD, policy + "_120_*"))[0], "rb"))
-    # LP optima are degenerate in x, so the trajectories differ in detail; the aggregate metrics must agree
-    assert abs(out["makespan"] - gold["makespan"]) / gold["makespan"] < 0.03
-    assert abs(out["avg_jct"] - gold["avg_jct"]) / gold["avg_jct"] < 0.05
+    # LP optima are degenerate in x; with the interior-point selection the HiGHS-backed run of the same host code
+    # is within 0.8 % (tests/golden/tacc32_policy_pins.json), the GPU-backed one must be too
+    assert abs(out["makespan"] - gold["makespan"]) / gold["makespan"] < 0.015
+    assert abs(out["avg_jct"] - gold["avg_jct"]) / gold["avg_jct"] < 0.015

@@ -121,3 +121,16 @@ def test_product_placement_rule_closed_loop_pin():
     assert abs(o["rounds"] - g["rounds"]) <= 6
     assert abs(o["worst_ftf"] - g["worst_ftf"]) / g["worst_ftf"] < 0.10
     assert abs(o["unfair_frac"] - g["unfair_frac"]) < 0.03
+
+
+def test_live_placement_pin_is_what_the_current_rule_produces():
+    """Live version of the placement pin (needs /root/reference, ~1 min): guards tacc32_placement_pin.json against going
+    stale when tests/ref_placement.py (i.e. place.cu) changes."""
+    from oracle import ref_harness as rh
+    from tests.ref_placement import place
+    if not rh.reference_available():
+        pytest.skip("reference tree not present")
+    pin = json.load(open(os.path.join(HERE, "golden", "tacc32_placement_pin.json")))["product_placement"]
+    out = rh.simulate("shockwave", shockwave_scheduler_cls=rh.make_oracle_scheduler_cls(placement=place))
+    assert abs(out["makespan"] - pin["makespan"]) <= 1e-9 * pin["makespan"], (out["makespan"], pin["makespan"])
+    assert abs(out["avg_jct"] - pin["avg_jct"]) <= 1e-9 * pin["avg_jct"]
