@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
         }
       }
       const int j = idx16[pos];
-      const int g = gs[j], n = remn[j];   // remn == plan until the job is seated (shared memory; nplan is global)
+      // remn == plan until the job is seated (shared memory; nplan is global).  Only lane 0 touches remn[] on this
+      // path (it also writes it below), the count reaches the other lanes by shuffle.
+      const int g = gs[j], n = __shfl_sync(SWB_FULL, lane == 0 ? (int)remn[j] : 0, 0);
       const unsigned int lim = ((unsigned)(G - g) << 8) | 0xffu;
       const unsigned int add = (unsigned)g << 8;
       // Fast path (the common, load-balanced state): the n least-loaded bins all fit the job and, once
