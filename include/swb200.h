@@ -186,7 +186,9 @@ int swb_policy_pooled(swb_ctx *ctx, int32_t mode, int32_t J, double N, const dou
  * each with N[w] > 0 workers (the caller drops empty types).  a is the J x W row-major matrix named per mode in
  * swb_policy_pooled (coef / throughput / throughput over cost); x is the J x W allocation (time fractions).
  * Solved exactly (bisection on the scalar objective, Dantzig-Wolfe on the W capacity rows with an exact master),
- * objective within 1e-12 relative of the LP optimum, every constraint certified.  stats (optional, int32[2]):
+ * objective within 1e-12 relative of the LP optimum, every constraint certified.  MAXSUM accepts SLO floors
+ * (max_sum_throughput.py:87-93): t[j] = needed throughput num_steps_remaining_j / SLO_j (0 = none) together with
+ * den[w] = instance cost of worker type w (a = throughput / cost); returns 1 when the floors do not fit.  stats (optional, int32[2]):
  * pricing passes, feasibility checks.  Returns 0, or 1 when no feasible point was found. */
 int swb_policy_hetero(swb_ctx *ctx, int32_t mode, int32_t J, int32_t W, const double *N, const double *a,
                       const double *sf, const double *t, const double *n, const double *den, double *x,

@@ -55,8 +55,17 @@ def hetero_cpu(mode, N, a, sf, t=None, n=None, den=None):
         T, x = gl.min_total_duration_perf(a, sf, np.asarray(n, float), N)
         return x, T, 0
     if mode == POL_MAXSUM:
-        need = None if t is None else np.asarray(t, float) * a[:, 0]        # pooled SLO floors lo_j -> thr_j x_j >= need_j
-        v, x = gl.max_sum_throughput(a, sf, N, need=need)
+        # SLO floors: pooled callers (W = 1, den None) pass t = lo_j (a time fraction); heterogeneous callers pass
+        # t = needed throughput and den = instance cost per type (a = thr / cost)
+        need, thr_rows = None, None
+        if t is not None and den is None:
+            need = np.asarray(t, float) * a[:, 0]
+        elif t is not None:
+            need, thr_rows = np.asarray(t, float), a * np.asarray(den, float)[None, :]
+        if thr_rows is None:
+            v, x = gl.max_sum_throughput(a, sf, N, need=need)
+        else:
+            v, x = gl.max_sum_throughput(thr_rows, sf, N, costs=np.asarray(den, float), need=need)
         if v is None:
             return np.zeros_like(a), 0.0, 1
         return x, v, 0

@@ -550,12 +550,16 @@ int swb_policy_hetero(swb_ctx *c, int32_t mode, int32_t J, int32_t W, const doub
   CK(cudaMemcpyAsync(c->pol_sf.p, sf, b, cudaMemcpyHostToDevice, c->st));
   if (t) CK(cudaMemcpyAsync(c->pol_t.p, t, b, cudaMemcpyHostToDevice, c->st));
   if (n) CK(cudaMemcpyAsync(c->pol_n.p, n, b, cudaMemcpyHostToDevice, c->st));
-  if (den) CK(cudaMemcpyAsync(c->pol_den.p, den, b, cudaMemcpyHostToDevice, c->st));
+  // MAXSUM with SLO floors: t = needed throughput per job, den = instance cost per worker type (W entries)
+  if (den) CK(cudaMemcpyAsync(c->pol_den.p, den, mode == SWB_POL_MAXSUM ? (size_t)W * 8 : b, cudaMemcpyHostToDevice, c->st));
   swb::HeteroLaunch L;
   L.mode = mode; L.J = J; L.W = W;
   L.N = c->het_N.as<double>(); L.a = c->het_a.as<double>(); L.sf = c->pol_sf.as<double>();
-  L.t = c->pol_t.as<double>(); L.n = c->pol_n.as<double>(); L.den = c->pol_den.as<double>();
+  L.t = t ? c->pol_t.as<double>() : nullptr; L.n = n ? c->pol_n.as<double>() : nullptr;
+  L.den = den ? c->pol_den.as<double>() : nullptr;
   L.x = c->het_x.as<double>(); L.out = c->pol_out.as<double>();
+  if (mode == SWB_POL_MAXSUM && ((t != nullptr) != (den != nullptr)))
+    return fail(SWB_ERR_ARG, "swb_policy_hetero: MAXSUM SLO floors need both t (needed throughput) and den (cost per type)");
   CK(swb::launch_hetero(L, c->st));
   double out[16] = {0.0};
   CK(cudaMemcpyAsync(x, c->het_x.p, bw, cudaMemcpyDeviceToHost, c->st));

@@ -121,6 +121,40 @@ __device__ __forceinline__ void ht_response_sum(const double *a, int W, double s
   if (bu >= 0) x[bu] = 1.0;
 }
 
+// MAXSUM with an SLO floor (max_sum_throughput.py:87-93): the job must also reach thr.x >= need.  The best vertex of
+// { x >= 0, sum x <= 1, thr.x >= need } for the gains c_w = value price * a_w - capacity price * sf: idle (need = 0),
+// full time on one type, the floor met exactly on one type, or both rows tight on two types.  false: no type can
+// meet the floor even at full time.
+__device__ __forceinline__ bool ht_response_sum_slo(const double *a, const double *thr, int W, double sf, double need,
+                                                    double p0, const double *q, double *x) {
+  double c[HT_MAXR];
+  for (int w = 0; w < W; ++w) c[w] = p0 * a[w] - q[w] * sf;
+  double best = -1e300;
+  int bu = -1, bv = -1;
+  double bxu = 0.0;
+  if (need <= 0.0) { best = 0.0; }
+  for (int u = 0; u < W; ++u) {
+    if (thr[u] >= need && thr[u] > 0.0) {
+      if (c[u] > best) { best = c[u]; bu = u; bv = -1; bxu = 1.0; }                  // full time on u
+      if (need > 0.0) {
+        const double xu = need / thr[u], gn = c[u] * xu;                             // floor met exactly on u
+        if (gn > best) { best = gn; bu = u; bv = -1; bxu = xu; }
+      }
+    }
+  }
+  if (need > 0.0)
+    for (int u = 0; u < W; ++u)
+      for (int v = 0; v < W; ++v)
+        if (u != v && thr[u] > need && thr[v] < need) {                              // both rows tight
+          const double xu = (need - thr[v]) / (thr[u] - thr[v]), gn = c[u] * xu + c[v] * (1.0 - xu);
+          if (gn > best) { best = gn; bu = u; bv = v; bxu = xu; }
+        }
+  for (int w = 0; w < W; ++w) x[w] = 0.0;
+  if (best <= -1e299) return false;
+  if (bu >= 0) { x[bu] = bxu; if (bv >= 0) x[bv] = 1.0 - bxu; }
+  return true;
+}
+
 // block-wide sum of n <= HT_MAXR + 2 doubles per thread (one barrier, ping-pong scratch)
 __device__ __forceinline__ void ht_block_sum(HtCtx &C, double *v, int n) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
@@ -145,7 +179,15 @@ __device__ void ht_price(HtCtx &C, double theta) {
     for (int w = 0; w < W; ++w) a[w] = L.a[(size_t)j * W + w];
     const double sf = L.sf[j];
     if (sum_mode) {
-      ht_response_sum(a, W, sf, p0, q, x);
+      bool okj = true;
+      if (L.t) {      // SLO floors: t = needed throughput, den = instance cost per type (thr = a * cost)
+        double thr[HT_MAXR];
+        for (int w = 0; w < W; ++w) thr[w] = a[w] * L.den[w];
+        okj = ht_response_sum_slo(a, thr, W, sf, L.t[j], p0, q, x);
+      } else {
+        ht_response_sum(a, W, sf, p0, q, x);
+      }
+      if (!okj) acc[HT_MAXR] += 1.0;
       double val = 0.0;
       for (int w = 0; w < W; ++w) { val += a[w] * x[w]; acc[w + 1] += sf * x[w]; }
       acc[0] += val;
@@ -525,12 +567,20 @@ __global__ void __launch_bounds__(1024, 1) hetero_kernel(HeteroLaunch L) {
     { BlockRed br(&S.red[0][0][0]); ub = br.sum(ub); __syncthreads(); }
     C.vscale = ub > 0.0 ? ub : 1.0;
     double lo = 0.0, hi = ub;
-    ++checks;
-    if (ht_feasible<W, R>(C, hi, rounds)) { ht_accept(C, hi); lo = hi; }
-    for (int it = 0; it < 200 && hi - lo > 1e-12 * hi; ++it) {
-      const double mid = 0.5 * (lo + hi);
+    bool base_ok = true;
+    if (L.t) {          // with SLO floors even theta = 0 has to be shown feasible
       ++checks;
-      if (ht_feasible<W, R>(C, mid, rounds)) { ht_accept(C, mid); lo = mid; } else hi = mid;
+      base_ok = ht_feasible<W, R>(C, 0.0, rounds);
+      if (base_ok) ht_accept(C, 0.0); else status = 1;
+    }
+    if (base_ok) {
+      ++checks;
+      if (ht_feasible<W, R>(C, hi, rounds)) { ht_accept(C, hi); lo = hi; }
+      for (int it = 0; it < 200 && hi - lo > 1e-12 * hi; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        ++checks;
+        if (ht_feasible<W, R>(C, mid, rounds)) { ht_accept(C, mid); lo = mid; } else hi = mid;
+      }
     }
     obj = lo;
   }
@@ -548,7 +598,13 @@ __global__ void __launch_bounds__(1024, 1) hetero_kernel(HeteroLaunch L) {
       double q[HT_MAXR], x[HT_MAXR];
       for (int w = 0; w < W; ++w) q[w] = S.bPI[i][sum_mode ? w + 1 : w] / L.N[w];
       if (sum_mode) {
-        ht_response_sum(a, W, sf, S.bPI[i][0] / C.vscale, q, x);
+        if (L.t) {
+          double thr[HT_MAXR];
+          for (int w = 0; w < W; ++w) thr[w] = a[w] * L.den[w];
+          ht_response_sum_slo(a, thr, W, sf, L.t[j], S.bPI[i][0] / C.vscale, q, x);
+        } else {
+          ht_response_sum(a, W, sf, S.bPI[i][0] / C.vscale, q, x);
+        }
       } else {
         double r = 0.0;
         ht_requirement(L, j, theta, r);

@@ -11,7 +11,7 @@ The LP each policy hands to cvxpy is solved on the GPU (no CPU fallback):
     homogeneous clusters Shockwave targets: closed forms / 1-D searches;
   * swb_policy_hetero (hetero.cu) for genuinely heterogeneous *_Perf calls with up to 3 worker types that have
     capacity (k80 / p100 / v100): bisection on the scalar objective + Dantzig-Wolfe on the capacity rows.
-More than 3 live worker types, and SLO rows on heterogeneous types, raise NotImplementedError.
+More than 4 live worker types (3 for max-sum) raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -346,10 +346,17 @@ class ThroughputNormalizedByCostSumWithPerfSLOs(Policy):
             cost = np.array([instance_costs[w] for w in worker_types], dtype=np.float64)
         live_cost = cost[np.asarray(self._num_workers) > 0]
         if thr is None or not np.allclose(live_cost, live_cost[0]):
-            if SLOs:
-                raise NotImplementedError("SLO rows (max_sum_throughput.py:87-93) with heterogeneous worker types "
-                                          "are not solved on the GPU")
-            x, self.last_objective, _ = self._solve_hetero(POL_MAXSUM, throughputs / cost[None, :], sf)
+            need = None
+            if SLOs:    # max_sum_throughput.py:87-93: sum_w thr_jw x_jw >= num_steps_remaining_j / SLO_j
+                need = np.zeros(len(job_ids))
+                for job_id in SLOs:
+                    assert job_id in num_steps_remaining
+                    need[job_ids.index(job_id)] = num_steps_remaining[job_id] / SLOs[job_id]
+            x, self.last_objective, rc = self._solve_hetero(POL_MAXSUM, throughputs / cost[None, :], sf, t=need,
+                                                            den=None if need is None else live_cost)
+            if rc != 0:     # the reference warns and solves again without the SLO rows (:100-104)
+                print("WARNING: No allocation possible with provided SLOs!")
+                x, self.last_objective, rc = self._solve_hetero(POL_MAXSUM, throughputs / cost[None, :], sf)
             return super().unflatten(x, index)
         lo = None
         if SLOs:        # max_sum_throughput.py:87-93: sum_w thr_jw x_jw >= num_steps_remaining_j / SLO_j

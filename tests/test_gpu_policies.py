@@ -123,10 +123,6 @@ def test_closed_forms_and_edge_cases():
     assert P.get_policy("max_min_fairness").name == "MaxMinFairness"
     assert P.get_policy("finish_time_fairness").name.startswith("FinishTimeFairness")
     assert P.get_policy("shockwave").name == "shockwave"
-    het, sf2, spec2, _ = _instance(6, SPECS[1], seed=4, equal_columns=False)
-    with pytest.raises(NotImplementedError):      # SLO rows with heterogeneous types are not on the GPU
-        P.ThroughputNormalizedByCostSumWithPerfSLOs(solver=None).get_allocation(
-            het, sf2, spec2, SLOs={0: 100.0}, num_steps_remaining={0: 10.0})
 
 
 def test_allox_assignment_and_policy(engine):

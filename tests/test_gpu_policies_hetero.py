@@ -179,3 +179,36 @@ def test_four_worker_types():
         To, _ = gl.min_total_duration_perf(a, sf, n, N)
         assert rc == 0 and T == To
         assert np.all((a * x).sum(axis=1) >= n / T * (1 - 1e-9))
+
+
+@pytest.mark.parametrize("J,spec,kinds", [(12, SPECS[0], 0), (60, SPECS[0], 4), (90, SPECS[1], 0), (300, SPECS[3], 0)])
+def test_max_sum_with_slos_hetero(J, spec, kinds):
+    """SLO rows (max_sum_throughput.py:87-93) with different per-type throughputs and per-type instance costs."""
+    thr, sf, spec, rng, m = _instance(J, spec, 5000 + J, kinds, False)
+    N = np.array([spec[w] for w in WT], float)
+    live = N > 0
+    s = np.array([sf[j] for j in range(J)], float)
+    costs = {"k80": 0.9, "p100": 1.46, "v100": 2.48}
+    c = np.array([costs[w] for w in WT])
+    steps = {j: float(rng.uniform(1e3, 1e5)) for j in range(J)}
+    slo_jobs = [j for j in range(J) if rng.random() < 0.25] or [0]
+    need = np.zeros(J)
+    for j in slo_jobs:
+        need[j] = m[j, live].max() * float(rng.uniform(0.05, 0.6))
+    # keep the floors inside ~half of the cluster so that they fit
+    while (s * need / m[:, live].max(axis=1)).sum() > 0.5 * N.sum():
+        need *= 0.7
+    slos = {j: steps[j] / need[j] for j in slo_jobs}
+    pol = P.ThroughputNormalizedByCostSumWithPerfSLOs(solver="ECOS")
+    x = _mat(pol.get_allocation(thr, sf, spec, instance_costs=costs, SLOs=slos, num_steps_remaining=steps), J)
+    _check_base(x, sf, spec, J)
+    assert np.all((m * x).sum(axis=1) >= need * (1 - 1e-9))
+    v, _ = gl.max_sum_throughput(m[:, live], s, N[live], costs=c[live], need=need)
+    got = ((m / c[None, :]) * x).sum()
+    assert v is not None and abs(got - v) <= 1e-6 * v, (got, v, P._hetero.last_stats)
+    assert abs(pol.last_objective - v) <= 1e-6 * v
+    # floors that cannot be met: fall back to the SLO-free program, like the reference
+    hard = {j: 1e-9 for j in slo_jobs}
+    x2 = _mat(pol.get_allocation(thr, sf, spec, instance_costs=costs, SLOs=hard, num_steps_remaining=steps), J)
+    v0, _ = gl.max_sum_throughput(m[:, live], s, N[live], costs=c[live])
+    assert abs(((m / c[None, :]) * x2).sum() - v0) <= 1e-6 * v0
