@@ -180,7 +180,7 @@ int swb_policy_pooled(swb_ctx *ctx, int32_t mode, int32_t J, double N, const dou
                       const double *t, const double *n, const double *den, double *x, double *objective);
 
 /* ---- Gavel policies with heterogeneous worker types ------------------------------------------- *
- * Same programs as swb_policy_pooled (MAXMIN, FTF, MTD, MAXSUM without SLOs) when the per-type throughputs of a
+ * Same programs as swb_policy_pooled (MAXMIN, FTF, MTD, MAXSUM with optional SLO floors) when the per-type throughputs of a
  * job differ — the general case of max_min_fairness.py:53-113, finish_time_fairness.py:66-157,
  * min_total_duration.py:55-135, max_sum_throughput.py:49-108 on a k80/p100/v100 cluster.  W <= 4 worker types (3 for MAXSUM),
  * each with N[w] > 0 workers (the caller drops empty types).  a is the J x W row-major matrix named per mode in

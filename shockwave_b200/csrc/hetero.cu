@@ -4,7 +4,7 @@
 //   MaxMinFairnessPolicyWithPerf        scheduler/policies/max_min_fairness.py:53-113
 //   FinishTimeFairnessPolicyWithPerf    scheduler/policies/finish_time_fairness.py:66-157
 //   MinTotalDurationPolicyWithPerf      scheduler/policies/min_total_duration.py:55-135
-//   ThroughputNormalizedByCostSumWithPerf[SLOs] without SLOs   scheduler/policies/max_sum_throughput.py:49-108
+//   ThroughputNormalizedByCostSumWithPerf[SLOs]                  scheduler/policies/max_sum_throughput.py:49-108
 // when the per-type throughputs of a job differ (k80 / p100 / v100 columns of the throughput table).
 //
 // All four programs share the base constraints (policy.py:58-65)  x >= 0, sum_w x_jw <= 1, sum_j sf_j x_jw <= N_w
