@@ -167,7 +167,7 @@ __device__ __forceinline__ void ht_block_sum(HtCtx &C, double *v, int n) {
 
 // pricing pass at S.pi: fills S.e, S.lb, S.bad (block-uniform after return)
 template <int W, int R>
-__device__ void ht_price(HtCtx &C, double theta) {
+__device__ __noinline__ void ht_price(HtCtx &C, double theta) {
   const HeteroLaunch &L = C.L;
   double q[HT_MAXR], acc[HT_MAXR + 2];
   const bool sum_mode = (L.mode == SWB_POL_MAXSUM);
@@ -259,7 +259,7 @@ __device__ __forceinline__ void ht_unrank(int q, int k, int *c) {
 // master: exact solution of the matrix game over the M columns in S.E.  `forced` >= 0: only bases that contain
 // that column are enumerated (the optimum must contain the column that was just added).  Fills S.pi, S.mu, S.v, S.ok.
 template <int R>
-__device__ void ht_master(HtCtx &C, int M, int forced) {
+__device__ __noinline__ void ht_master(HtCtx &C, int M, int forced) {
   HtShared &S = C.S;
   double bestv = -1e300;
   int bk = 0, bcols[HT_MAXR];
@@ -358,7 +358,7 @@ __device__ void ht_master(HtCtx &C, int M, int forced) {
 
 // is there an x at parameter theta?  On success the support (<= R columns) is left in S.tPI / S.tMU / S.tK.
 template <int W, int R>
-__device__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
+__device__ __noinline__ bool ht_feasible(HtCtx &C, double theta, int &rounds) {
   HtShared &S = C.S;
   int M = 0;      // columns; every thread keeps the same count
   __syncthreads();
