@@ -12,8 +12,9 @@ generated gRPC stubs are absent.  This module
      and returns the same result dictionary that script pickles.
 
 Nothing here is imported by the product; it exists to (a) pin the oracle against the reference's
-golden pickles and (b) record solver-input fixtures for the GPU parity tests.  It only works where
-/root/reference exists (this container), never on the GPU box.
+golden pickles and (b) record solver-input fixtures for the GPU parity tests.  It works where /root/reference
+exists (this container) or where oracle/stage_ref.py staged the reference files (baseline/_ref, untracked, shipped to
+the GPU box by gpurun).
 """
 from __future__ import annotations
 
@@ -25,7 +26,21 @@ import sys
 import tempfile
 import types
 
-REF = "/root/reference/scheduler"
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_ref():
+    """The reference's scheduler/ directory: $SWB_REF_SCHEDULER, else /root/reference (build container), else the
+    byte-for-byte staged copy under baseline/_ref (git-ignored, shipped to the GPU box; see oracle/stage_ref.py)."""
+    for cand in (os.environ.get("SWB_REF_SCHEDULER"), "/root/reference/scheduler",
+                 os.path.join(_ROOT, "baseline", "_ref", "scheduler")):
+        if cand and os.path.isdir(cand):
+            return cand
+    return "/root/reference/scheduler"
+
+
+REF = _find_ref()
+GOLDEN_DIR = os.path.join(REF, "reproduce", "pickles", "tacc_32gpus")
 CANONICAL_TRACE = "traces/reproduce/120_0.2_5_100_40_25_0,0.5,0.5_0.6,0.3,0.09,0.01_multigpu_dynamic.trace"
 
 _STUB_NAMES = [
@@ -68,7 +83,7 @@ def prepare_tree(scratch=None, trace=CANONICAL_TRACE):
     scratch = scratch or tempfile.mkdtemp(prefix="swref_")
     dst = os.path.join(scratch, "repo", "scheduler")
     if not os.path.isdir(dst):
-        shutil.copytree(REF, dst, ignore=shutil.ignore_patterns("traces", "reproduce", "*.png", "__pycache__"))
+        shutil.copytree(REF, dst, ignore=shutil.ignore_patterns("traces", "reproduce", "scripts", "*.png", "__pycache__"))
         os.makedirs(os.path.join(dst, os.path.dirname(trace)), exist_ok=True)
         shutil.copy(os.path.join(REF, trace), os.path.join(dst, trace))
     return dst

@@ -1,23 +1,30 @@
-"""P5 — closed loop: the UNMODIFIED reference simulator (scheduler/scheduler.py) driving the product's
-ShockwaveScheduler / Gavel policies on the canonical 120-job trace, end-to-end metrics against the golden
-pickles the reference ships (within the 3 % spread of its own three Shockwave pickles).
+"""P5 — closed loop: the UNMODIFIED reference simulator (scheduler/scheduler.py:1728-2268) driving the product's
+ShockwaveScheduler / Gavel policies — libswb200.so in the loop — on the canonical 120-job trace
+(reproduce/tacc_32gpus.sh), end-to-end metrics against the golden pickles the reference ships (within the 3 % spread of
+its own three Shockwave pickles).
 
-Needs BOTH a B200 and /root/reference.  The build container has the reference but no GPU, the GPU box has
-the GPU but no reference, so in this environment the test is skipped on both sides; it is here so that the
-check runs wherever the two meet (and documents exactly what "drop-in" means)."""
+Needs a B200 AND the reference's python files.  The build container has /root/reference but no GPU; the GPU box gets
+the byte-for-byte staged copy `baseline/_ref/scheduler` (git-ignored, made by `python -m oracle.stage_ref`, shipped by
+gpurun like a pip --target install of the reference would be).  Every run appends its metrics to
+gpurun_out/closed_loop.json (copied to profiles/closed_loop_rNN.json for the record)."""
 import glob
+import json
 import os
 import pickle
+import time
 
 import numpy as np
 import pytest
 
+from oracle import ref_harness as rh
+
 pytestmark = [pytest.mark.gpu, pytest.mark.reference]
-GOLD = "/root/reference/scheduler/reproduce/pickles/tacc_32gpus"
+GOLD = rh.GOLDEN_DIR
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _have_both():
-    if not os.path.isdir("/root/reference/scheduler"):
+    if not (os.path.isdir(rh.REF) and os.path.isdir(GOLD)):
         return False
     try:
         import torch
@@ -26,12 +33,51 @@ def _have_both():
         return False
 
 
-@pytest.mark.skipif(not _have_both(), reason="needs a B200 and /root/reference at the same time")
+def _record(name, out, gold, seconds, extra=None):
+    ftf, gftf = np.array(out["finish_time_fairness_list"]), np.array(gold["finish_time_fairness_list"])
+    row = dict(policy=name, seconds=round(seconds, 2),
+               makespan=out["makespan"], golden_makespan=gold["makespan"],
+               avg_jct=out["avg_jct"], golden_avg_jct=gold["avg_jct"],
+               cluster_util=out["cluster_util"], golden_cluster_util=gold["cluster_util"],
+               worst_ftf=float(ftf.max()), golden_worst_ftf=float(gftf.max()),
+               unfair_fraction=float((ftf > 1.05).mean()), golden_unfair_fraction=float((gftf > 1.05).mean()),
+               rounds=len(out["per_round_schedule"]), golden_rounds=len(gold["per_round_schedule"]))
+    row.update(extra or {})
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, "closed_loop.json")
+    rows = json.load(open(path)) if os.path.exists(path) else []
+    rows = [r for r in rows if r["policy"] != name] + [row]
+    json.dump(rows, open(path, "w"), indent=1)
+    return row
+
+
+def _native_loaded():
+    return any("libswb200.so" in line for line in open("/proc/self/maps"))
+
+
+@pytest.mark.skipif(not _have_both(), reason="needs a B200 and the (staged) reference simulator at the same time")
 def test_shockwave_closed_loop_matches_golden_pickle():
-    from oracle import ref_harness as rh
     from shockwave_b200 import ShockwaveScheduler
-    out = rh.simulate("shockwave", shockwave_scheduler_cls=ShockwaveScheduler)
+    stats = dict(solves=0, fallback=0, ms=0.0)
+
+    class Counting(ShockwaveScheduler):
+        def _resolve(self, jobids, jobobjs):
+            t0 = time.perf_counter()
+            out = super()._resolve(jobids, jobobjs)
+            stats["ms"] += (time.perf_counter() - t0) * 1e3
+            stats["solves"] += 1
+            stats["fallback"] += int(self.last_result["status"] != 0)
+            return out
+
+    t0 = time.perf_counter()
+    out = rh.simulate("shockwave", shockwave_scheduler_cls=Counting)
+    assert _native_loaded() and stats["solves"] > 50
     gold = pickle.load(open(glob.glob(os.path.join(GOLD, "shockwave_*"))[0], "rb"))
+    row = _record("shockwave", out, gold, time.perf_counter() - t0,
+                  dict(resolves=stats["solves"], fallback_resolves=stats["fallback"],
+                       mean_resolve_ms=stats["ms"] / max(1, stats["solves"])))
+    print(row)
     assert abs(out["makespan"] - gold["makespan"]) / gold["makespan"] < 0.03
     assert abs(out["avg_jct"] - gold["avg_jct"]) / gold["avg_jct"] < 0.03
     assert abs(out["cluster_util"] - gold["cluster_util"]) / gold["cluster_util"] < 0.03
@@ -40,14 +86,16 @@ def test_shockwave_closed_loop_matches_golden_pickle():
     assert abs((ftf > 1.05).mean() - (gftf > 1.05).mean()) < 0.03
 
 
-@pytest.mark.skipif(not _have_both(), reason="needs a B200 and /root/reference at the same time")
+@pytest.mark.skipif(not _have_both(), reason="needs a B200 and the (staged) reference simulator at the same time")
 @pytest.mark.parametrize("policy", ["max_min_fairness", "finish_time_fairness", "min_total_duration",
                                     "max_sum_throughput_perf", "allox", "gandiva_fair"])
 def test_gavel_policy_closed_loop_matches_golden_pickle(policy):
-    from oracle import ref_harness as rh
     from shockwave_b200 import policies
+    t0 = time.perf_counter()
     out = rh.simulate(policy, policy_obj=policies.get_policy(policy, solver="ECOS", seed=0))
+    assert _native_loaded()
     gold = pickle.load(open(glob.glob(os.path.join(GOLD, policy + "_120_*"))[0], "rb"))
+    print(_record(policy, out, gold, time.perf_counter() - t0))
     # LP optima are degenerate in x; with the interior-point selection the HiGHS-backed run of the same host code
     # is within 0.8 % (tests/golden/tacc32_policy_pins.json), the GPU-backed one must be too
     assert abs(out["makespan"] - gold["makespan"]) / gold["makespan"] < 0.015
