@@ -59,7 +59,7 @@ typedef struct swb_result {
   int32_t mu_iters;     /* price-bisection iterations in total */
   int32_t shortfall;    /* planned job-rounds the placement could not seat (0 = all seated) */
   int32_t placement;    /* fallback path: leading rounds seated by the priority round-sweep (the rest by the water-filling packer); 0 otherwise */
-  int32_t reserved;
+  int32_t flags;        /* bit 0: a gang width outside [1,255] was met in device-resident input (the call returns SWB_ERR_ARG) */
   double objective;     /* sum_j w_j plog_j/(J T) - k max_j rem_j of the RETURNED integral x */
   double welfare;       /* first term */
   double makespan;      /* max_j rem_j */
@@ -126,6 +126,9 @@ int swb_job_add(swb_ctx *ctx, int32_t slot, int32_t nworkers, int32_t epochs, do
                 double timestamp_submit, const double *epoch_duration_preprofiled,
                 const int32_t *bs_schedule);
 int swb_job_remove(swb_ctx *ctx, int32_t slot);
+/* Rows of the profile pools in use (high-water mark) and rows sitting in reusable holes: removed jobs give their
+ * rows back, so `used_rows` tracks the LIVE jobs, not every job ever added.  Either pointer may be NULL. */
+int swb_job_table_stats(swb_ctx *ctx, int64_t *used_rows, int64_t *hole_rows);
 
 /* One full ShockwaveScheduler.round_schedule() re-solve (shockwave.py:122-166) for the jobs listed
  * in `slots` (metadata order).  Host inputs per job: epoch_progress, and the summary of the

@@ -62,6 +62,9 @@ struct swb_ctx {
   DBuf t_off, t_E, t_nm, t_g, t_ns, t_ts, t_modes, t_mm, t_amp, s_r0, s_rl, s_cnt, s_vl, s_acc;
   DBuf pool_pp, pool_bs;
   int64_t pool_used = 0;
+  // holes left by removed jobs in pool_pp / pool_bs: (offset, rows), sorted by offset, adjacent holes merged;
+  // swb_job_add takes the first hole that fits, so the pools grow with the LIVE jobs, not with all jobs ever seen
+  std::vector<std::pair<int64_t, int64_t>> pool_holes;
   std::vector<int64_t> h_off;
   std::vector<int32_t> h_E;
   // ---- per-call forecast buffers
@@ -85,7 +88,8 @@ struct swb_ctx {
 
 extern "C" {
 
-int swb_version(void) { return 100; }
+void swb_destroy(swb_ctx *c);
+int swb_version(void) { return 101; }
 const char *swb_last_error(void) { return g_err.c_str(); }
 
 int swb_create(swb_ctx **out, int device) {
@@ -101,9 +105,13 @@ int swb_create(swb_ctx **out, int device) {
     return fail(SWB_ERR_CUDA, "swb_create: libswb200 is built for sm_100a only (Blackwell B200)");
   swb_ctx *c = new swb_ctx();
   c->device = device;
-  CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-  for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&c->ev[i]));
-  for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->mev[i]));
+  cudaError_t e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->mev[i]);
+  if (e != cudaSuccess) {
+    swb_destroy(c);      // releases whatever was created
+    return fail(SWB_ERR_CUDA, std::string("swb_create: ") + cudaGetErrorString(e));
+  }
   *out = c;
   return 0;
 }
@@ -124,6 +132,7 @@ void swb_destroy(swb_ctx *c) {
   for (DBuf *b : all) b->release();
   if (c->h_res) cudaFreeHost(c->h_res);
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2; ++i) if (c->mev[i]) cudaEventDestroy(c->mev[i]);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -245,6 +254,12 @@ int swb_solve(swb_ctx *c, const swb_solve_args *a) {
   int32_t *nr;
   double *w;
   unsigned long long *xmk = nullptr, *bmk = nullptr;
+  if (!a->on_device) {
+    // gang widths are kept as bytes on the device (solve.cu, place.cu): reject what does not fit instead of
+    // truncating it (on_device inputs are checked by the kernel itself, which reports SWB_ERR_ARG through res)
+    for (size_t i = 0; i < nj; ++i)
+      if (a->g[i] < 1 || a->g[i] > 255) return fail(SWB_ERR_ARG, "swb_solve: gang width g[j] must be in [1, 255]");
+  }
   if (a->on_device) {
     xmk = (unsigned long long *)a->xmask; bmk = (unsigned long long *)a->bfmask;
     g = a->g; E = a->E; cc = a->c; dbar = a->dbar; rem = a->rem; ftobj = a->ftobj;
@@ -288,12 +303,39 @@ int swb_solve(swb_ctx *c, const swb_solve_args *a) {
   }
   CK(cudaStreamSynchronize(c->st));
   memcpy(a->res, c->h_res, sizeof(swb_result) * S);
+  for (int s = 0; s < S; ++s)
+    if (a->res[s].flags & 1) return fail(SWB_ERR_ARG, "swb_solve: gang width g[j] must be in [1, 255] (device input)");
   int any_fb = 0;
   for (int s = 0; s < S; ++s) any_fb |= (a->res[s].status == SWB_ST_FALLBACK);
   return any_fb ? SWB_ST_FALLBACK : SWB_ST_OK;
 }
 
 // ---- resident job table -------------------------------------------------------------------------
+// the per-slot scalars of one job, passed BY VALUE as the kernel parameter: one launch writes the whole row
+// (no staging buffer, nothing to keep alive, no stream synchronize on the add path)
+struct JobRow {
+  int64_t off;
+  int32_t slot, E, nmodes, g;
+  double nsamples, tsubmit;
+  int32_t modes[SWB_MAX_MODES];
+  double modemean[SWB_MAX_MODES];
+};
+struct JobTablePtrs {
+  int64_t *off; int32_t *E, *nm, *g; double *ns, *ts; int32_t *modes; double *mm, *amp; int32_t *cnt; double *acc;
+};
+__global__ void job_row_kernel(JobRow r, JobTablePtrs t) {
+  const int i = threadIdx.x;
+  if (i < SWB_MAX_MODES) {
+    t.modes[(size_t)r.slot * SWB_MAX_MODES + i] = r.modes[i];
+    t.mm[(size_t)r.slot * SWB_MAX_MODES + i] = r.modemean[i];
+  }
+  if (i == 0) {
+    t.off[r.slot] = r.off; t.E[r.slot] = r.E; t.nm[r.slot] = r.nmodes; t.g[r.slot] = r.g;
+    t.ns[r.slot] = r.nsamples; t.ts[r.slot] = r.tsubmit;
+    t.amp[r.slot] = 1.0; t.cnt[r.slot] = 0; t.acc[r.slot] = 0.0;
+  }
+}
+
 static int ensure_slots(swb_ctx *c, int nslots) {
   if (nslots <= c->nslots) return 0;
   size_t n = (size_t)nslots;
@@ -320,6 +362,8 @@ int swb_job_add(swb_ctx *c, int32_t slot, int32_t nworkers, int32_t epochs, doub
   CK(cudaSetDevice(c->device));
   int rc = ensure_slots(c, slot + 1);
   if (rc) return rc;
+  if (c->h_off[slot] >= 0)
+    return fail(SWB_ERR_STATE, "swb_job_add: slot is occupied (swb_job_remove it first)");
   // host-side digest of the static profile: prefix sums (sequential, like the reference's running
   // `preprofiled_time_range += duration`, JobMetaData.py:253-257), sorted bs modes
   // (JobMetaData.py:296), per-mode mean duration (JobMetaData.py:304-312, pairwise like np.mean).
@@ -362,40 +406,71 @@ int swb_job_add(swb_ctx *c, int32_t slot, int32_t nworkers, int32_t epochs, doub
     };
     hmm[m] = PW::sum(tmp.data(), tmp.size()) / (double)tmp.size();
   }
-  const int64_t off = c->pool_used;
   const size_t rows = (size_t)epochs + 1;
-  CK(c->pool_pp.need((off + rows) * 8, c->st, true));
-  CK(c->pool_bs.need((off + rows) * 4, c->st, true));
+  // first hole that fits (left by removed jobs), else the end of the pool
+  int64_t off = -1;
+  for (size_t h = 0; h < c->pool_holes.size(); ++h) {
+    if (c->pool_holes[h].second >= (int64_t)rows) {
+      off = c->pool_holes[h].first;
+      c->pool_holes[h].first += (int64_t)rows;
+      c->pool_holes[h].second -= (int64_t)rows;
+      if (c->pool_holes[h].second == 0) c->pool_holes.erase(c->pool_holes.begin() + h);
+      break;
+    }
+  }
+  if (off < 0) {
+    off = c->pool_used;
+    CK(c->pool_pp.need((off + rows) * 8, c->st, true));
+    CK(c->pool_bs.need((off + rows) * 4, c->st, true));
+    c->pool_used += rows;
+  }
+  // pageable sources: cudaMemcpyAsync returns once they are staged, so the vectors may die with this frame
   CK(cudaMemcpyAsync(c->pool_pp.as<double>() + off, pp.data(), rows * 8, cudaMemcpyHostToDevice, c->st));
   CK(cudaMemcpyAsync(c->pool_bs.as<int32_t>() + off, bs, (size_t)epochs * 4, cudaMemcpyHostToDevice, c->st));
-  c->pool_used += rows;
   c->h_off[slot] = off;
   c->h_E[slot] = epochs;
-  const int32_t nm = (int32_t)modes.size(), zero = 0;
-  const double one = 1.0, dzero = 0.0;
-  CK(cudaMemcpyAsync(c->t_off.as<int64_t>() + slot, &off, 8, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->t_E.as<int32_t>() + slot, &epochs, 4, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->t_nm.as<int32_t>() + slot, &nm, 4, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->t_g.as<int32_t>() + slot, &nworkers, 4, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->t_ns.as<double>() + slot, &epoch_nsamples, 8, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->t_ts.as<double>() + slot, &timestamp_submit, 8, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->t_modes.as<int32_t>() + (size_t)slot * SWB_MAX_MODES, hm, sizeof(hm),
-                     cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->t_mm.as<double>() + (size_t)slot * SWB_MAX_MODES, hmm, sizeof(hmm),
-                     cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->t_amp.as<double>() + slot, &one, 8, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->s_cnt.as<int32_t>() + slot, &zero, 4, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->s_acc.as<double>() + slot, &dzero, 8, cudaMemcpyHostToDevice, c->st));
-  CK(cudaStreamSynchronize(c->st));  // the staging vectors die with this frame
+  JobRow r;
+  r.off = off; r.slot = slot; r.E = epochs; r.nmodes = (int32_t)modes.size(); r.g = nworkers;
+  r.nsamples = epoch_nsamples; r.tsubmit = timestamp_submit;
+  memcpy(r.modes, hm, sizeof(hm)); memcpy(r.modemean, hmm, sizeof(hmm));
+  JobTablePtrs t;
+  t.off = c->t_off.as<int64_t>(); t.E = c->t_E.as<int32_t>(); t.nm = c->t_nm.as<int32_t>(); t.g = c->t_g.as<int32_t>();
+  t.ns = c->t_ns.as<double>(); t.ts = c->t_ts.as<double>(); t.modes = c->t_modes.as<int32_t>();
+  t.mm = c->t_mm.as<double>(); t.amp = c->t_amp.as<double>(); t.cnt = c->s_cnt.as<int32_t>(); t.acc = c->s_acc.as<double>();
+  job_row_kernel<<<1, 32, 0, c->st>>>(r, t);
+  CK(cudaGetLastError());
+  c->have_fc = false;      // the tables may have moved: a pending forecast can no longer be committed
   return 0;
 }
 
 int swb_job_remove(swb_ctx *c, int32_t slot) {
   if (!c || slot < 0 || slot >= c->nslots || c->h_off[slot] < 0)
     return fail(SWB_ERR_ARG, "swb_job_remove: unknown slot");
-  // pool rows of a removed job are reclaimed only when they sit at the end of the pool
-  if (c->h_off[slot] + c->h_E[slot] + 1 == c->pool_used) c->pool_used = c->h_off[slot];
+  // return the job's rows to the hole list (sorted by offset, neighbours merged); a hole that reaches the end
+  // of the pool shrinks pool_used instead
+  const int64_t off = c->h_off[slot], rows = (int64_t)c->h_E[slot] + 1;
+  auto &H = c->pool_holes;
+  size_t pos = 0;
+  while (pos < H.size() && H[pos].first < off) ++pos;
+  H.insert(H.begin() + pos, std::make_pair(off, rows));
+  if (pos + 1 < H.size() && H[pos].first + H[pos].second == H[pos + 1].first) {
+    H[pos].second += H[pos + 1].second; H.erase(H.begin() + pos + 1);
+  }
+  if (pos > 0 && H[pos - 1].first + H[pos - 1].second == H[pos].first) {
+    H[pos - 1].second += H[pos].second; H.erase(H.begin() + pos);
+  }
+  if (!H.empty() && H.back().first + H.back().second == c->pool_used) { c->pool_used = H.back().first; H.pop_back(); }
   c->h_off[slot] = -1;
+  c->have_fc = false;
+  return 0;
+}
+
+int swb_job_table_stats(swb_ctx *c, int64_t *used_rows, int64_t *hole_rows) {
+  if (!c) return fail(SWB_ERR_ARG, "null ctx");
+  int64_t h = 0;
+  for (auto &p : c->pool_holes) h += p.second;
+  if (used_rows) *used_rows = c->pool_used;
+  if (hole_rows) *hole_rows = h;
   return 0;
 }
 
@@ -480,7 +555,8 @@ int swb_round_solve(swb_ctx *c, const swb_params *prm, const swb_round_args *a) 
 
 int swb_forecast(swb_ctx *c, const swb_params *prm, const swb_round_args *a, double *dbar, double *rem,
                  double *ftobj, double *bfkey, double *ft_estimate) {
-  if (!c || !prm || !a) return fail(SWB_ERR_ARG, "swb_forecast: null argument");
+  if (!c || !prm || !a || !a->slots || !a->epoch_progress || !a->meas_nsamples || !a->meas_end_round)
+    return fail(SWB_ERR_ARG, "swb_forecast: null argument");
   if (a->J <= 0) return fail(SWB_ERR_ARG, "swb_forecast: J must be positive");
   CK(cudaSetDevice(c->device));
   int rc = run_forecast(c, prm, a);

@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     if (threadIdx.x == 0) {
       swb_result &r = L.res[s];
       r.welfare = w; r.makespan = me; r.objective = w - prm.k * me; r.shortfall = (int)shortf;
-      r.placement = t0; r.reserved = 0;
+      r.placement = t0;
     }
   }
 

@@ -303,17 +303,20 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
 
   // ---- phase 1: job constants + finish-time-fairness rows (shockwave.py:573-597) -----------
   long long infeasible = 0, forced = 0;
+  int badw = 0;      // gang widths are bytes from here on: anything outside [1,255] is reported, never truncated
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
     const double Ef = (double)EI[j], cf = (double)cI[j], dbar = dbarI[j], R = RI[j];
     const double cap = dbar * (Ef - cf);
     const double a = D / (dbar * Ef);
     int nfin = cap <= 0.0 ? 0 : (int)fmin(ceil(cap / D - 1e-9), 255.0);
     int nmax = nfin < T ? nfin : T;
-    if (gI[j] > G) nmax = 0;  // a gang wider than the cluster violates every capacity row (shockwave.py:317)
+    const int gw = gI[j];
+    if (gw < 1 || gw > 255) { badw = 1; nmax = 0; }
+    if (gw > G) nmax = 0;  // a gang wider than the cluster violates every capacity row (shockwave.py:317)
     if (L.ncap && (int)L.ncap[so + j] < nmax) nmax = L.ncap[so + j];  // packing feedback (written by place_kernel)
     c.a[j] = a; c.u0[j] = cf / Ef; c.cap[j] = cap;
     c.t.R[j] = R * c.invD; L.sc_R[so + j] = R;
-    c.t.g[j] = (uint8_t)gI[j]; c.t.nmax[j] = (uint8_t)nmax;
+    c.t.g[j] = (uint8_t)(gw < 1 ? 1 : (gw > 255 ? 255 : gw)); c.t.nmax[j] = (uint8_t)nmax;
     const double capF = share * (prm.rhomax * ftI[j] - next_t);
     int nF = 0, bad = 0;
     if (capF < 0.0) bad = 1;
@@ -323,7 +326,10 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
         if (need > cap * (1.0 + 1e-12) + 1e-9) bad = 1;
         else {
           const double q = ceil(need / D - 1e-9);
-          if (q > (double)nmax) { if (q > (double)T) bad = 1; else nF = nmax; }
+          // q > nmax with q <= T: either the packing feedback capped the job (ncap: keep the plan, seat what fits)
+          // or the gang is wider than the cluster — then the reference's row shockwave.py:586-590 cannot hold with
+          // x_j = 0 and its MILP is infeasible -> fallback verdict
+          if (q > (double)nmax) { if (q > (double)T || gw > G) bad = 1; else nF = nmax; }
           else nF = (int)q;
         }
       }
@@ -331,10 +337,11 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
     c.t.nF[j] = (uint8_t)nF;
     if (L.sc_nfc) L.sc_nfc[so + j] = (!bad && R - capF > 0.0) ? (R - capF) / D : 0.0;
     infeasible += bad;
-    forced += (long long)gI[j] * nF;
+    forced += (long long)gw * nF;
   }
   infeasible = br.sumll(infeasible);
   forced = br.sumll(forced);
+  badw = (int)br.sumll((long long)badw);
   const bool ftf_ok = (infeasible == 0) && (forced <= (long long)c.GT);
 
   // fallback priorities (shockwave.py:830-911); weights stay 1 when the FTF rows are satisfiable.
@@ -513,6 +520,7 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
     r.m_evals = m_evals;
     r.mu_iters = iters;
     r.shortfall = 0;
+    r.flags = badw ? 1 : 0;
     r.welfare = w;
     r.makespan = me;
     r.objective = w - k * me;

@@ -31,7 +31,7 @@ class Params(C.Structure):
 class Result(C.Structure):
     """swb_result (include/swb200.h)."""
     _fields_ = [("status", C.c_int32), ("m_evals", C.c_int32), ("mu_iters", C.c_int32),
-                ("shortfall", C.c_int32), ("placement", C.c_int32), ("reserved", C.c_int32),
+                ("shortfall", C.c_int32), ("placement", C.c_int32), ("flags", C.c_int32),
                 ("objective", C.c_double), ("welfare", C.c_double),
                 ("makespan", C.c_double), ("price", C.c_double), ("relaxed_objective", C.c_double)]
 
@@ -56,7 +56,7 @@ class RoundArgs(C.Structure):
 
 
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
-           "swb_solve", "swb_job_add", "swb_job_remove", "swb_round_solve", "swb_forecast",
+           "swb_solve", "swb_job_add", "swb_job_remove", "swb_job_table_stats", "swb_round_solve", "swb_forecast",
            "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_policy_hetero", "swb_gbm_forecast", "swb_market_pgd", "swb_set_option", "swb_allox_assign"]
 
 _lib = None
@@ -215,6 +215,12 @@ class Engine:
 
     def job_remove(self, slot):
         self._check(self.lib.swb_job_remove(self.h, int(slot)), "swb_job_remove")
+
+    def job_table_stats(self):
+        used, holes = C.c_int64(), C.c_int64()
+        self.lib.swb_job_table_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        self._check(self.lib.swb_job_table_stats(self.h, C.byref(used), C.byref(holes)), "swb_job_table_stats")
+        return dict(used_rows=used.value, hole_rows=holes.value)
 
     def _round_args(self, slots, progress, meas_ns, meas_end, reestimate, grd):
         slots = np.ascontiguousarray(slots, dtype=np.int32)

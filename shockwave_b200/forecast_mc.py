@@ -39,6 +39,11 @@ def gbm_forecast(engine, R0, H, mu, sigma, P, seed=0, rank=0, world=1, reduce_fn
     if kernel_fn is None:
         kernel_fn = engine.gbm_forecast
     if device_tensor is not None:
+        try:        # the kernel runs on the engine's own (non-blocking) stream: whatever torch still has queued on
+            import torch   # ITS stream for this tensor (a zero-fill, a previous reduce) must be finished first
+            torch.cuda.current_stream(device_tensor.device).synchronize()
+        except ImportError:
+            pass
         kernel_fn(R0, H, mu, sigma, n_local, lo, seed, out_device_ptr=device_tensor.data_ptr())
         if reduce_fn is not None:
             reduce_fn(device_tensor)

@@ -18,6 +18,7 @@ from __future__ import annotations
 import copy
 import ctypes as C
 import operator
+import os
 
 import numpy as np
 
@@ -26,12 +27,22 @@ from . import engine as _eng
 POL_MAXMIN, POL_FTF, POL_MTD, POL_MAXSUM, POL_ISOLATED = 1, 2, 3, 4, 5
 
 _shared_engine = None
+_device = int(os.environ.get("SWB_DEVICE", "0"))
+
+
+def set_device(device):
+    """CUDA device the policy kernels run on (default: $SWB_DEVICE or 0).  Drops the engine of another device."""
+    global _shared_engine, _device
+    if int(device) != _device and _shared_engine is not None:
+        _shared_engine.close()
+        _shared_engine = None
+    _device = int(device)
 
 
 def _engine():
     global _shared_engine
     if _shared_engine is None:
-        _shared_engine = _eng.Engine(0)
+        _shared_engine = _eng.Engine(_device)
     return _shared_engine
 
 
