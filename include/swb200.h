@@ -81,6 +81,19 @@ int swb_sync(swb_ctx *ctx);
  * parity tests against the HiGHS LP relaxation).  Off: relaxed_objective holds the solver's own LP-style
  * upper estimate. */
 #define SWB_OPT_RELAXED_OPTIMUM 1
+/* SWB_OPT_SOLVE_CLUSTER: CTAs per scenario on the latency path of the market solve (8 = a thread-block cluster of 8
+ * CTAs shares one scenario over distributed shared memory when few scenarios of >= 512 jobs are solved; 1 = always one
+ * CTA per scenario).  Process-wide.  Default 8. */
+#define SWB_OPT_SOLVE_CLUSTER 2
+/* Monte-Carlo (GBM) forecast inside swb_round_solve.  SWB_OPT_GBM_PATHS = P > 0: between the deterministic forecast
+ * and the solve the remaining runtime of every job whose volatility model (swb_job_set_gbm) has drift or volatility
+ * is replaced ON THE DEVICE by the mean of P geometric-Brownian-motion sample paths started at the deterministic
+ * value (gbm.cu); jobs with mu = sigma = 0 keep the deterministic value bit for bit, so P > 0 with all-zero models
+ * reproduces the reference's forecast exactly.  0 (default) = off.  SWB_OPT_GBM_SEED: stream seed;
+ * SWB_OPT_GBM_HORIZON: horizon cap in epochs (default 256). */
+#define SWB_OPT_GBM_PATHS 3
+#define SWB_OPT_GBM_SEED 4
+#define SWB_OPT_GBM_HORIZON 5
 int swb_set_option(swb_ctx *ctx, int32_t option, int32_t value);
 
 /* ---- the market solve on plain arrays ------------------------------------------------------- *
@@ -129,6 +142,10 @@ int swb_job_remove(swb_ctx *ctx, int32_t slot);
 /* Rows of the profile pools in use (high-water mark) and rows sitting in reusable holes: removed jobs give their
  * rows back, so `used_rows` tracks the LIVE jobs, not every job ever added.  Either pointer may be NULL. */
 int swb_job_table_stats(swb_ctx *ctx, int64_t *used_rows, int64_t *hole_rows);
+/* Volatility model of a resident job for the Monte-Carlo forecast: drift mu and volatility sigma per epoch of the
+ * log epoch duration.  swb_job_add sets mu = 0 and sigma = the relative spread of the pre-profiled epoch durations
+ * inside their batch-size modes (0 for the profiles the reference generates, utils.py:1350-1430). */
+int swb_job_set_gbm(swb_ctx *ctx, int32_t slot, double mu, double sigma);
 
 /* One full ShockwaveScheduler.round_schedule() re-solve (shockwave.py:122-166) for the jobs listed
  * in `slots` (metadata order).  Host inputs per job: epoch_progress, and the summary of the
@@ -149,6 +166,9 @@ typedef struct swb_round_args {
   int32_t *nrounds;             /* [J] host, out (may be NULL) */
   double *forecast_out;         /* [6][J] host, out (may be NULL) */
   swb_result *res;              /* host, out */
+  /* optional packed outputs, [J][2] uint64 each (bit t of a job's 128-bit row = round t); x / backfill may then
+   * be NULL: 16 B per job and matrix on the device->host copy instead of T bytes */
+  uint64_t *xmask, *bfmask;
 } swb_round_args;
 int swb_round_solve(swb_ctx *ctx, const swb_params *prm, const swb_round_args *a);
 
@@ -217,6 +237,12 @@ int swb_allox_assign(swb_ctx *ctx, int32_t m, int32_t n, int32_t W, const double
 int swb_gbm_forecast(swb_ctx *ctx, int32_t J, const double *R0, const int32_t *H, const double *mu,
                      const double *sigma, int64_t P_local, int64_t path_offset, uint64_t seed, double *out,
                      int32_t out_on_device);
+
+/* Scenario ensemble from ONE Monte-Carlo forecast: rem_out[s][j] = max(0, mean_j + z[s] * std_j) with mean / std from
+ * the (all-reduced) path sums — scenario s plans against the z[s]-sigma quantile of the remaining-runtime forecast.
+ * sums_dev [2][J] and rem_out_dev [S][J] are DEVICE pointers, z [S] is host. */
+int swb_gbm_ensemble(swb_ctx *ctx, int32_t S, int32_t J, double P_total, const double *sums_dev, const double *z,
+                     double *rem_out_dev);
 
 /* ---- dense market iteration over X[S][J][W][T] ------------------------------------------------ *
  * Projected-gradient / price-response iterations on the dense allocation tensor (fp32, t innermost) of

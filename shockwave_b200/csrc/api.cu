@@ -1,4 +1,5 @@
 // api.cu — the C-ABI of libswb200.so (see include/swb200.h) and the device-memory bookkeeping.
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -55,11 +56,16 @@ struct swb_ctx {
   cudaStream_t st = nullptr;
   // ---- work buffers of a solve
   DBuf prm, res, g, E, c, dbar, rem, ftobj, bfkey, x, bf, nr, w, xmk, bmk;
-  DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask, sncap, seated, scth, sths, sn0, snfc;
+  DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask, sncap, seated, scth, sths, sn0, snfc, sRr;
   int want_relaxed = 0;
   // ---- resident job table (by slot)
   int nslots = 0;
-  DBuf t_off, t_E, t_nm, t_g, t_ns, t_ts, t_modes, t_mm, t_amp, s_r0, s_rl, s_cnt, s_vl, s_acc;
+  DBuf t_off, t_E, t_nm, t_g, t_ns, t_ts, t_modes, t_mm, t_amp, s_r0, s_rl, s_cnt, s_vl, s_acc, t_mu, t_sg;
+  // Monte-Carlo (GBM) forecast inside swb_round_solve: 0 paths = off (the reference's deterministic forecast)
+  int64_t gbm_paths = 0;
+  uint64_t gbm_seed = 0;
+  int gbm_hmax = 256;
+  DBuf ens_z;
   DBuf pool_pp, pool_bs;
   int64_t pool_used = 0;
   // holes left by removed jobs in pool_pp / pool_bs: (offset, rows), sorted by offset, adjacent holes merged;
@@ -121,8 +127,8 @@ void swb_destroy(swb_ctx *c) {
   cudaSetDevice(c->device);
   DBuf *all[] = {&c->prm, &c->res, &c->g, &c->E, &c->c, &c->dbar, &c->rem, &c->ftobj, &c->bfkey, &c->x,
                  &c->bf, &c->nr, &c->w, &c->xmk, &c->bmk, &c->sa, &c->su0, &c->sR, &c->sws, &c->scap, &c->sg, &c->snF,
-                 &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->scth, &c->sths, &c->sn0, &c->snfc, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
-                 &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc,
+                 &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->scth, &c->sRr, &c->sths, &c->sn0, &c->snfc, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
+                 &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc, &c->t_mu, &c->t_sg, &c->ens_z,
                  &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
                  &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal, &c->ax_p, &c->ax_t, &c->ax_wt, &c->ax_u, &c->ax_v, &c->ax_spc, &c->ax_c4r, &c->ax_r4c,
                  &c->ax_path, &c->ax_sc, &c->ax_sr, &c->ax_out, &c->pol_coef, &c->pol_sf, &c->pol_t,
@@ -192,7 +198,7 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   CK(cudaMemcpyAsync(c->prm.p, h_prm, sizeof(swb_params) * S, cudaMemcpyHostToDevice, c->st));
   if (J > SWB_SMEM_JOBS) {
     CK(c->gmask.need(n * 4 * sizeof(unsigned long long), c->st));
-    CK(c->scth.need(n * 8, c->st)); CK(c->sths.need(n * SWB_MAX_BASES * 4, c->st));
+    CK(c->scth.need(n * 8, c->st)); CK(c->sRr.need(n * 8, c->st)); CK(c->sths.need(n * SWB_MAX_BASES * 4, c->st));
     CK(c->sn0.need(n * SWB_MAX_BASES, c->st));
   }
   swb::SolveLaunch L;
@@ -203,7 +209,7 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   L.sc_ws = c->sws.as<double>(); L.sc_cap = c->scap.as<double>();
   L.sc_g = c->sg.as<uint8_t>(); L.sc_nF = c->snF.as<uint8_t>(); L.sc_nmax = c->snmax.as<uint8_t>();
   L.sc_n = c->sn.as<uint8_t>();
-  L.sc_cth = c->scth.as<double>(); L.sc_ths = c->sths.as<float>(); L.sc_n0 = c->sn0.as<uint8_t>();
+  L.sc_cth = c->scth.as<double>(); L.sc_Rr = c->sRr.as<double>(); L.sc_ths = c->sths.as<float>(); L.sc_n0 = c->sn0.as<uint8_t>();
   L.weights = weights ? weights : c->w.as<double>();
   L.res = c->res.as<swb_result>();
   L.ncap = c->sncap.as<uint8_t>();
@@ -316,12 +322,13 @@ int swb_solve(swb_ctx *c, const swb_solve_args *a) {
 struct JobRow {
   int64_t off;
   int32_t slot, E, nmodes, g;
-  double nsamples, tsubmit;
+  double nsamples, tsubmit, mu, sigma;
   int32_t modes[SWB_MAX_MODES];
   double modemean[SWB_MAX_MODES];
 };
 struct JobTablePtrs {
   int64_t *off; int32_t *E, *nm, *g; double *ns, *ts; int32_t *modes; double *mm, *amp; int32_t *cnt; double *acc;
+  double *mu, *sg;
 };
 __global__ void job_row_kernel(JobRow r, JobTablePtrs t) {
   const int i = threadIdx.x;
@@ -333,7 +340,11 @@ __global__ void job_row_kernel(JobRow r, JobTablePtrs t) {
     t.off[r.slot] = r.off; t.E[r.slot] = r.E; t.nm[r.slot] = r.nmodes; t.g[r.slot] = r.g;
     t.ns[r.slot] = r.nsamples; t.ts[r.slot] = r.tsubmit;
     t.amp[r.slot] = 1.0; t.cnt[r.slot] = 0; t.acc[r.slot] = 0.0;
+    t.mu[r.slot] = r.mu; t.sg[r.slot] = r.sigma;
   }
+}
+__global__ void job_gbm_kernel(int slot, double mu, double sigma, double *tmu, double *tsg) {
+  tmu[slot] = mu; tsg[slot] = sigma;
 }
 
 static int ensure_slots(swb_ctx *c, int nslots) {
@@ -348,6 +359,7 @@ static int ensure_slots(swb_ctx *c, int nslots) {
   CK(c->s_r0.need(n * 4, c->st, true)); CK(c->s_rl.need(n * 4, c->st, true));
   CK(c->s_cnt.need(n * 4, c->st, true)); CK(c->s_vl.need(n * 8, c->st, true));
   CK(c->s_acc.need(n * 8, c->st, true));
+  CK(c->t_mu.need(n * 8, c->st, true)); CK(c->t_sg.need(n * 8, c->st, true));
   c->nslots = nslots;
   c->h_off.resize(n, -1);
   c->h_E.resize(n, 0);
@@ -432,11 +444,28 @@ int swb_job_add(swb_ctx *c, int32_t slot, int32_t nworkers, int32_t epochs, doub
   JobRow r;
   r.off = off; r.slot = slot; r.E = epochs; r.nmodes = (int32_t)modes.size(); r.g = nworkers;
   r.nsamples = epoch_nsamples; r.tsubmit = timestamp_submit;
+  // default volatility model of the job (only read when the GBM forecast is switched on): no drift, sigma = the
+  // relative spread of the pre-profiled epoch durations INSIDE their batch-size modes — zero for the profiles the
+  // reference generates (utils.py:1350-1430: one duration per mode), so the default reproduces the reference
+  {
+    double ss = 0.0, tot = 0.0;
+    for (int e = 0; e < epochs; ++e) {
+      size_t m = 0;
+      while (m + 1 < modes.size() && modes[m] != bs[e]) ++m;
+      const double d = pre[e] - hmm[m];
+      ss += d * d; tot += pre[e];
+    }
+    const double mean = tot / (double)epochs;
+    r.mu = 0.0;
+    r.sigma = mean > 0.0 ? sqrt(ss / (double)epochs) / mean : 0.0;
+    if (r.sigma < 1e-12) r.sigma = 0.0;
+  }
   memcpy(r.modes, hm, sizeof(hm)); memcpy(r.modemean, hmm, sizeof(hmm));
   JobTablePtrs t;
   t.off = c->t_off.as<int64_t>(); t.E = c->t_E.as<int32_t>(); t.nm = c->t_nm.as<int32_t>(); t.g = c->t_g.as<int32_t>();
   t.ns = c->t_ns.as<double>(); t.ts = c->t_ts.as<double>(); t.modes = c->t_modes.as<int32_t>();
   t.mm = c->t_mm.as<double>(); t.amp = c->t_amp.as<double>(); t.cnt = c->s_cnt.as<int32_t>(); t.acc = c->s_acc.as<double>();
+  t.mu = c->t_mu.as<double>(); t.sg = c->t_sg.as<double>();
   job_row_kernel<<<1, 32, 0, c->st>>>(r, t);
   CK(cudaGetLastError());
   c->have_fc = false;      // the tables may have moved: a pending forecast can no longer be committed
@@ -462,6 +491,17 @@ int swb_job_remove(swb_ctx *c, int32_t slot) {
   if (!H.empty() && H.back().first + H.back().second == c->pool_used) { c->pool_used = H.back().first; H.pop_back(); }
   c->h_off[slot] = -1;
   c->have_fc = false;
+  return 0;
+}
+
+int swb_job_set_gbm(swb_ctx *c, int32_t slot, double mu, double sigma) {
+  if (!c || slot < 0 || slot >= c->nslots || c->h_off[slot] < 0)
+    return fail(SWB_ERR_ARG, "swb_job_set_gbm: unknown slot");
+  if (!(sigma >= 0.0) || !isfinite(mu) || !isfinite(sigma))
+    return fail(SWB_ERR_ARG, "swb_job_set_gbm: need finite mu and sigma >= 0");
+  CK(cudaSetDevice(c->device));
+  job_gbm_kernel<<<1, 1, 0, c->st>>>(slot, mu, sigma, c->t_mu.as<double>(), c->t_sg.as<double>());
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -524,13 +564,37 @@ int swb_round_solve(swb_ctx *c, const swb_params *prm, const swb_round_args *a) 
   const int J = a->J, T = prm->future_rounds;
   rc = run_forecast(c, prm, a);
   if (rc) return rc;
+  if (c->gbm_paths > 0) {
+    // Monte-Carlo forecast on the device, between the deterministic forecast and the solve (no host round trip):
+    // R0 = the Dirichlet forecast just computed, horizon min(E - c, Hmax) epochs, per-job (mu, sigma) from the table
+    CK(c->mc_out.need((size_t)J * 16, c->st));
+    swb::GbmLaunch Gm;
+    Gm.J = J; Gm.P_local = c->gbm_paths; Gm.path_offset = 0; Gm.seed = c->gbm_seed ^ (uint64_t)prm->round_ptr * 0x9E3779B97F4A7C15ull;
+    Gm.R0 = c->rem.as<double>(); Gm.mu = nullptr; Gm.sigma = nullptr; Gm.H = nullptr;
+    Gm.out = c->mc_out.as<double>();
+    Gm.slots = c->f_slots.as<int32_t>(); Gm.Eo = c->E.as<int32_t>(); Gm.co = c->c.as<int32_t>();
+    Gm.tab_mu = c->t_mu.as<double>(); Gm.tab_sigma = c->t_sg.as<double>(); Gm.Hmax = c->gbm_hmax;
+    CK(swb::launch_gbm(Gm, c->st));
+    swb::GbmApplyLaunch Ga;
+    Ga.J = J; Ga.P_total = (double)c->gbm_paths; Ga.sums = Gm.out; Ga.slots = Gm.slots;
+    Ga.tab_mu = Gm.tab_mu; Ga.tab_sigma = Gm.tab_sigma;
+    Ga.rem = c->rem.as<double>(); Ga.rem_fb = c->f_remfb.as<double>();
+    Ga.bfkey = c->bfkey.as<double>(); Ga.bfkey_fb = c->f_bffb.as<double>(); Ga.var_out = nullptr;
+    CK(swb::launch_gbm_apply(Ga, c->st));
+  }
   const size_t nx = (size_t)J * T;
-  CK(c->x.need(nx, c->st)); CK(c->bf.need(nx, c->st)); CK(c->nr.need((size_t)J * 4, c->st));
+  uint8_t *dx = nullptr, *dbf = nullptr;
+  unsigned long long *dxm = nullptr, *dbm = nullptr;
+  if (a->x) { CK(c->x.need(nx, c->st)); dx = c->x.as<uint8_t>(); }
+  if (a->backfill) { CK(c->bf.need(nx, c->st)); dbf = c->bf.as<uint8_t>(); }
+  if (a->xmask) { CK(c->xmk.need((size_t)J * 16, c->st)); dxm = c->xmk.as<unsigned long long>(); }
+  if (a->bfmask) { CK(c->bmk.need((size_t)J * 16, c->st)); dbm = c->bmk.as<unsigned long long>(); }
+  CK(c->nr.need((size_t)J * 4, c->st));
   CK(c->f_ncal.need((size_t)J * 4, c->st));
   rc = run_solve(c, 1, J, 0, prm, c->g.as<int32_t>(), c->E.as<int32_t>(), c->c.as<int32_t>(),
                  c->dbar.as<double>(), c->rem.as<double>(), c->ftobj.as<double>(), c->bfkey.as<double>(),
-                 c->f_remfb.as<double>(), c->f_bffb.as<double>(), c->x.as<uint8_t>(), c->bf.as<uint8_t>(),
-                 c->nr.as<int32_t>(), nullptr, c->f_ncal.as<int32_t>());
+                 c->f_remfb.as<double>(), c->f_bffb.as<double>(), dx, dbf,
+                 c->nr.as<int32_t>(), nullptr, c->f_ncal.as<int32_t>(), dxm, dbm);
   if (rc) return rc;
   CK(swb::launch_commit_calibration(c->last_fc, c->res.as<swb_result>(), 0, c->f_ncal.as<int32_t>(), c->st));
   rc = ensure_hres(c, 1);
@@ -538,6 +602,8 @@ int swb_round_solve(swb_ctx *c, const swb_params *prm, const swb_round_args *a) 
   CK(cudaMemcpyAsync(c->h_res, c->res.p, sizeof(swb_result), cudaMemcpyDeviceToHost, c->st));
   if (a->x) CK(cudaMemcpyAsync(a->x, c->x.p, nx, cudaMemcpyDeviceToHost, c->st));
   if (a->backfill) CK(cudaMemcpyAsync(a->backfill, c->bf.p, nx, cudaMemcpyDeviceToHost, c->st));
+  if (a->xmask) CK(cudaMemcpyAsync(a->xmask, dxm, (size_t)J * 16, cudaMemcpyDeviceToHost, c->st));
+  if (a->bfmask) CK(cudaMemcpyAsync(a->bfmask, dbm, (size_t)J * 16, cudaMemcpyDeviceToHost, c->st));
   if (a->nrounds) CK(cudaMemcpyAsync(a->nrounds, c->nr.p, (size_t)J * 4, cudaMemcpyDeviceToHost, c->st));
   if (a->forecast_out) {
     double *fo = a->forecast_out;  // [6][J] planes: dbar, rem, ftobj, bfkey, rem_fb, bfkey_fb
@@ -668,12 +734,25 @@ int swb_gbm_forecast(swb_ctx *c, int32_t J, const double *R0, const int32_t *H, 
   L.J = J; L.P_local = P_local; L.path_offset = path_offset; L.seed = seed;
   L.R0 = c->mc_R0.as<double>(); L.mu = c->mc_mu.as<double>(); L.sigma = c->mc_sigma.as<double>();
   L.H = c->mc_H.as<int32_t>();
+  L.slots = nullptr; L.Eo = nullptr; L.co = nullptr; L.tab_mu = nullptr; L.tab_sigma = nullptr; L.Hmax = 0;
   L.out = out_on_device ? out : c->mc_out.as<double>();
   CK(cudaEventRecord(c->ev[0], c->st));
   CK(swb::launch_gbm(L, c->st));
   CK(cudaEventRecord(c->ev[1], c->st));
   CK(cudaEventRecord(c->ev[2], c->st));
   if (!out_on_device) CK(cudaMemcpyAsync(out, c->mc_out.p, 2 * b, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int swb_gbm_ensemble(swb_ctx *c, int32_t S, int32_t J, double P_total, const double *sums_dev, const double *z,
+                     double *rem_out_dev) {
+  if (!c || !sums_dev || !z || !rem_out_dev) return fail(SWB_ERR_ARG, "swb_gbm_ensemble: null argument");
+  if (S <= 0 || J <= 0 || !(P_total > 0.0)) return fail(SWB_ERR_ARG, "swb_gbm_ensemble: bad S / J / P_total");
+  CK(cudaSetDevice(c->device));
+  CK(c->ens_z.need((size_t)S * 8, c->st));
+  CK(cudaMemcpyAsync(c->ens_z.p, z, (size_t)S * 8, cudaMemcpyHostToDevice, c->st));
+  CK(swb::launch_gbm_ensemble(S, J, P_total, sums_dev, c->ens_z.as<double>(), rem_out_dev, c->st));
   CK(cudaStreamSynchronize(c->st));
   return 0;
 }
@@ -763,6 +842,10 @@ int swb_market_pgd(swb_ctx *c, const swb_market_args *a) {
 int swb_set_option(swb_ctx *c, int32_t option, int32_t value) {
   if (!c) return fail(SWB_ERR_ARG, "null ctx");
   if (option == SWB_OPT_RELAXED_OPTIMUM) { c->want_relaxed = value ? 1 : 0; return 0; }
+  if (option == SWB_OPT_SOLVE_CLUSTER) { swb::set_solve_cluster(value); return 0; }
+  if (option == SWB_OPT_GBM_PATHS) { if (value < 0) return fail(SWB_ERR_ARG, "paths < 0"); c->gbm_paths = value; return 0; }
+  if (option == SWB_OPT_GBM_SEED) { c->gbm_seed = (uint64_t)(uint32_t)value; return 0; }
+  if (option == SWB_OPT_GBM_HORIZON) { if (value < 1) return fail(SWB_ERR_ARG, "horizon < 1"); c->gbm_hmax = value; return 0; }
   return fail(SWB_ERR_ARG, "swb_set_option: unknown option");
 }
 

@@ -39,8 +39,18 @@ struct XorShift128p {
 __global__ void __launch_bounds__(256) gbm_kernel(GbmLaunch L) {
   __shared__ double red[2 * 64];
   const int j = blockIdx.x;
-  const int H = L.H[j];
-  const float mu = (float)L.mu[j], sg = (float)L.sigma[j];
+  int H;
+  float mu, sg;
+  if (L.slots) {
+    const int slot = L.slots[j];
+    mu = (float)L.tab_mu[slot]; sg = (float)L.tab_sigma[slot];
+    H = L.Eo[j] - L.co[j];
+    H = H < 0 ? 0 : (H > L.Hmax ? L.Hmax : H);
+    if (mu == 0.0f && sg == 0.0f) H = 0;      // deterministic model: nothing to simulate (R = R0 on every path)
+  } else {
+    H = L.H[j];
+    mu = (float)L.mu[j]; sg = (float)L.sigma[j];
+  }
   const float drift = mu - 0.5f * sg * sg;
   const float invH = H > 0 ? 1.0f / (float)H : 0.0f;
   const double R0 = L.R0[j];
@@ -78,6 +88,43 @@ __global__ void __launch_bounds__(256) gbm_kernel(GbmLaunch L) {
 
 cudaError_t launch_gbm(const GbmLaunch &L, cudaStream_t st) {
   gbm_kernel<<<L.J, 256, 0, st>>>(L);
+  return cudaGetLastError();
+}
+
+__global__ void gbm_apply_kernel(GbmApplyLaunch L) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= L.J) return;
+  const double mean = L.sums[j] / L.P_total;
+  const double var = fmax(0.0, L.sums[L.J + j] / L.P_total - mean * mean);
+  if (L.var_out) L.var_out[j] = var;
+  const int slot = L.slots[j];
+  if (L.tab_mu[slot] == 0.0 && L.tab_sigma[slot] == 0.0) return;   // deterministic job: forecast untouched
+  const double R0 = L.rem[j];
+  if (!(R0 > 0.0)) return;
+  const double ratio = mean / R0;
+  L.rem[j] = mean;
+  if (L.rem_fb) L.rem_fb[j] *= ratio;
+  if (L.bfkey) L.bfkey[j] *= ratio;
+  if (L.bfkey_fb) L.bfkey_fb[j] *= ratio;
+}
+
+cudaError_t launch_gbm_apply(const GbmApplyLaunch &L, cudaStream_t st) {
+  gbm_apply_kernel<<<(L.J + 255) / 256, 256, 0, st>>>(L);
+  return cudaGetLastError();
+}
+
+__global__ void gbm_ensemble_kernel(int S, int J, double P, const double *sums, const double *z, double *rem_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= J) return;
+  const double mean = sums[j] / P;
+  const double sd = sqrt(fmax(0.0, sums[J + j] / P - mean * mean));
+  for (int s = blockIdx.y; s < S; s += gridDim.y) rem_out[(size_t)s * J + j] = fmax(0.0, fma(z[s], sd, mean));
+}
+
+cudaError_t launch_gbm_ensemble(int S, int J, double P_total, const double *sums, const double *z, double *rem_out,
+                                cudaStream_t st) {
+  dim3 grid((J + 255) / 256, S < 64 ? S : 64);
+  gbm_ensemble_kernel<<<grid, 256, 0, st>>>(S, J, P_total, sums, z, rem_out);
   return cudaGetLastError();
 }
 

@@ -17,6 +17,7 @@
 // needs, per segment count bs, the number of whole rounds n0[bs] and the threshold ths[bs] of the one
 // round that straddles the breakpoint.  ~35 instructions per job and evaluation; reductions are warp
 // shuffles + one barrier.  The dense J x T placement of the counts is place.cu.
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -24,6 +25,67 @@
 #include "swb_internal.h"
 
 namespace swb {
+
+namespace cg = cooperative_groups;
+
+// Reductions over ALL jobs of a scenario.  CL = 1: the CTA owns every job, plain BlockRed.  CL > 1 (single-scenario
+// latency path): a thread-block cluster of CL CTAs splits the jobs; every CTA reduces its slice, publishes the partial
+// in its own shared memory and, after one cluster barrier, every thread of every CTA adds up the CL partials through
+// distributed shared memory IN RANK ORDER — all CTAs see bit-identical totals, so the (data-dependent) control flow
+// of the price / makespan searches stays uniform across the cluster.  Two slots used alternately: a CTA that races
+// ahead into reduction k+1 writes the other slot and cannot reach k+2 before everyone has left k's barrier.
+template <int CL>
+struct ClusterRed {
+  BlockRed br;
+  double *xs;        // this CTA's published partials: [2 slots][2 values]
+  int xphase;
+  __device__ __forceinline__ ClusterRed(double *scratch, double *xslots) : br(scratch), xs(xslots), xphase(0) {}
+
+  __device__ __forceinline__ void exchange2(double &a, double &b, int op) {   // op 0: sum, 1: max
+    if constexpr (CL > 1) {
+      cg::cluster_group cl = cg::this_cluster();
+      if (threadIdx.x == 0) { xs[xphase * 2] = a; xs[xphase * 2 + 1] = b; }
+      cl.sync();
+      double ra = op ? -1.0e300 : 0.0, rb = 0.0;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) {
+        const double *rem = cl.map_shared_rank(xs, r);
+        const double va = rem[xphase * 2], vb = rem[xphase * 2 + 1];
+        if (op) ra = fmax(ra, va); else { ra += va; rb += vb; }
+      }
+      a = ra; b = rb;
+      xphase ^= 1;
+    }
+  }
+  __device__ __forceinline__ void sum2(double &a, double &b) { br.sum2(a, b); exchange2(a, b, 0); }
+  __device__ __forceinline__ double sum(double a) { double b = 0.0; sum2(a, b); return a; }
+  __device__ __forceinline__ long long sumll(long long a) {
+    a = br.sumll(a);
+    if constexpr (CL > 1) {
+      // exact in a double pair: hi = a / 2^26, lo = a mod 2^26 (|a| < 2^52 here: GPU-rounds, counts)
+      double hi = (double)(a >> 26), lo = (double)(a & ((1ll << 26) - 1));
+      exchange2(hi, lo, 0);
+      a = ((long long)hi << 26) + (long long)lo;
+    }
+    return a;
+  }
+  __device__ __forceinline__ double max(double a) { a = br.max(a); double b = 0.0; exchange2(a, b, 1); return a; }
+  __device__ __forceinline__ double min(double a) { return -max(-a); }
+  // all-gather of one value per CTA (rank order) — used for the prefix of the tie-fill
+  __device__ __forceinline__ long long prefix_of_rank(long long mine, int rank) {
+    if constexpr (CL > 1) {
+      cg::cluster_group cl = cg::this_cluster();
+      if (threadIdx.x == 0) { xs[xphase * 2] = (double)mine; xs[xphase * 2 + 1] = 0.0; }
+      cl.sync();
+      long long pre = 0;
+      for (int r = 0; r < rank; ++r) pre += (long long)cl.map_shared_rank(xs, r)[xphase * 2];
+      xphase ^= 1;
+      return pre;
+    } else {
+      return 0;
+    }
+  }
+};
 
 struct Tab {             // response table: shared memory for J <= SWB_SMEM_JOBS, else global scratch
   double *cth, *R;       // rho = mu * cth ; remaining runtime IN ROUNDS (R_j / D)
@@ -41,6 +103,7 @@ struct Ctx {
   double *a, *u0, *ws, *cap;
   uint8_t *n;
   int J, T, GT, B;
+  int j0, j1;           // this CTA's slice of the jobs ([0, J) unless the scenario is split over a cluster)
   double D, invD;
 };
 
@@ -81,11 +144,12 @@ __device__ __forceinline__ double util_of(const Ctx &c, int j, int n) {
   return c.ws[j] * plog(*c.P, u);
 }
 
-__device__ long long cost_at(const Ctx &c, BlockRed &br, double M, double mu) {
+template <class Red>
+__device__ long long cost_at(const Ctx &c, Red &br, double M, double mu) {
   const double Md = M * c.invD;
   int s = 0;
 #pragma unroll 4
-  for (int j = threadIdx.x; j < c.J; j += blockDim.x) s += (int)c.t.g[j] * job_n(c, j, Md, mu);
+  for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) s += (int)c.t.g[j] * job_n(c, j, Md, mu);
   return br.sumll((long long)s);
 }
 
@@ -99,7 +163,8 @@ struct Price { double hi, lo; long long cost_hi; int iters; };
 // as a tie and filled in job order (prec = 12 while searching the makespan threshold, 22 for the final
 // allocation; the response function itself has fp32 resolution).  `hint` (> 0) is the clearing price of a
 // neighbouring threshold: the search then starts from [hint/4, 4 hint] when that bracket holds.
-__device__ Price solve_price(const Ctx &c, BlockRed &br, double M, double mu_max, int prec, double hint) {
+template <class Red>
+__device__ Price solve_price(const Ctx &c, Red &br, double M, double mu_max, int prec, double hint) {
   Price p;
   p.iters = 1;
   long long c0 = cost_at(c, br, M, 0.0);
@@ -133,12 +198,13 @@ __device__ Price solve_price(const Ctx &c, BlockRed &br, double M, double mu_max
 struct Phi { double V, welfare, Meff, mu; long long cost; };
 
 // value of makespan threshold M: LP-style welfare at the clearing price minus k * achieved makespan
-__device__ Phi phi_at(const Ctx &c, BlockRed &br, double M, double mu_max, double k, int &iters, double hint) {
+template <class Red>
+__device__ Phi phi_at(const Ctx &c, Red &br, double M, double mu_max, double k, int &iters, double hint) {
   Price p = solve_price(c, br, M, mu_max, 12, hint);
   iters += p.iters;
   double w = 0.0, me = 0.0;
   const double Md = M * c.invD;
-  for (int j = threadIdx.x; j < c.J; j += blockDim.x) {
+  for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) {
     const int n = job_n(c, j, Md, p.hi);
     w += util_of(c, j, n);
     me = fmax(me, rem_of(c, j, n));
@@ -181,13 +247,15 @@ __device__ __forceinline__ double util_c(const Ctx &c, int j, double n) {
   return c.ws[j] * plog(*c.P, u);
 }
 
-__device__ double cost_c(const Ctx &c, const RelaxCtx &r, BlockRed &br, double Md, double mu) {
+template <class Red>
+__device__ double cost_c(const Ctx &c, const RelaxCtx &r, Red &br, double Md, double mu) {
   double s = 0.0;
-  for (int j = threadIdx.x; j < c.J; j += blockDim.x) s += (double)c.t.g[j] * job_nc(c, r, j, Md, mu);
+  for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) s += (double)c.t.g[j] * job_nc(c, r, j, Md, mu);
   return br.sum(s);
 }
 
-__device__ double phi_c(const Ctx &c, const RelaxCtx &r, BlockRed &br, double M, double mu_max, double k) {
+template <class Red>
+__device__ double phi_c(const Ctx &c, const RelaxCtx &r, Red &br, double M, double mu_max, double k) {
   const double Md = M * c.invD, cap = (double)c.GT;
   double mu = 0.0, c_hi = cost_c(c, r, br, Md, 0.0), c_lo = c_hi;
   if (c_hi > cap * (1.0 + 1e-13)) {
@@ -203,7 +271,7 @@ __device__ double phi_c(const Ctx &c, const RelaxCtx &r, BlockRed &br, double M,
     }
   }
   double w = 0.0, me = 0.0;
-  for (int j = threadIdx.x; j < c.J; j += blockDim.x) {
+  for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) {
     const double n = job_nc(c, r, j, Md, mu);
     w += util_c(c, j, n);
     me = fmax(me, fmax(0.0, c.Rsec[j] - fmin(c.D * n, c.cap[j])));
@@ -214,10 +282,11 @@ __device__ double phi_c(const Ctx &c, const RelaxCtx &r, BlockRed &br, double M,
   return w + mu * fill - k * me;
 }
 
-__device__ double relaxed_optimum(const Ctx &c, const RelaxCtx &r, BlockRed &br, double mu_max, double k) {
+template <class Red>
+__device__ double relaxed_optimum(const Ctx &c, const RelaxCtx &r, Red &br, double mu_max, double k) {
   // makespan threshold range: floor (everybody at its continuous maximum) .. natural (no threshold)
   double mfl = 0.0, mtop = 0.0;
-  for (int j = threadIdx.x; j < c.J; j += blockDim.x) {
+  for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) {
     const double nm = nmax_real(c, r, j);
     mfl = fmax(mfl, c.Rsec[j] - fmin(c.D * nm, c.cap[j]));
     mtop = fmax(mtop, c.Rsec[j]);
@@ -248,11 +317,16 @@ __device__ double relaxed_optimum(const Ctx &c, const RelaxCtx &r, BlockRed &br,
 
 // SMEM = the response table lives in shared memory (J <= SWB_SMEM_JOBS).  A compile-time switch so that
 // the hot loop's accesses are LDS with 32-bit addresses instead of generic 64-bit loads.
-template <bool SMEM, int NT>
+template <bool SMEM, int NT, int CL>
 __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int s = blockIdx.x;
+  const int s = blockIdx.x / CL;
+  int rank = 0;
+  if constexpr (CL > 1) rank = (int)cg::this_cluster().block_rank();
   const int J = L.J;
+  // this CTA's slice of the jobs (whole warps, so that the slices of a cluster are contiguous in job order)
+  const int Jc = CL > 1 ? ((((J + CL - 1) / CL) + 31) & ~31) : J;
+  const int jbeg = rank * Jc < J ? rank * Jc : J, jend = (jbeg + Jc < J) ? jbeg + Jc : J;
   const swb_params &prm = L.prm[s];
   const int T = prm.future_rounds, G = prm.ngpus, B = prm.nbases;
   const double D = prm.round_duration, k = prm.k;
@@ -260,19 +334,22 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   // ---- shared-memory carve-up -------------------------------------------------------------
   Pwl *P = reinterpret_cast<Pwl *>(smem_raw);
   double *red = reinterpret_cast<double *>(smem_raw + SWB_PWL_BYTES);  // 2*64 doubles
-  unsigned char *p = smem_raw + SWB_PWL_BYTES + 2 * 64 * sizeof(double);
+  double *xslots = red + 2 * 64;                                       // 4 doubles: cluster exchange slots
+  unsigned char *p = smem_raw + SWB_PWL_BYTES + (2 * 64 + 4) * sizeof(double);
   Ctx c;
+  c.j0 = jbeg; c.j1 = jend;
   const size_t so = (size_t)s * J;
   if constexpr (SMEM) {
-    c.t.cth = reinterpret_cast<double *>(p); p += sizeof(double) * J;
-    c.t.R = reinterpret_cast<double *>(p);   p += sizeof(double) * J;
-    c.t.ths = reinterpret_cast<float *>(p);  p += sizeof(float) * J * B;
-    c.t.n0 = p;   p += (size_t)J * B;
-    c.t.g = p;    p += J;
-    c.t.nF = p;   p += J;
-    c.t.nmax = p; p += J;
+    // the table holds this CTA's Jc jobs; the pointers are shifted so that the GLOBAL job index addresses it
+    c.t.cth = reinterpret_cast<double *>(p) - jbeg; p += sizeof(double) * Jc;
+    c.t.R = reinterpret_cast<double *>(p) - jbeg;   p += sizeof(double) * Jc;
+    c.t.ths = reinterpret_cast<float *>(p) - (size_t)jbeg * B;  p += sizeof(float) * Jc * B;
+    c.t.n0 = p - (size_t)jbeg * B;   p += (size_t)Jc * B;
+    c.t.g = p - jbeg;    p += Jc;
+    c.t.nF = p - jbeg;   p += Jc;
+    c.t.nmax = p - jbeg; p += Jc;
   } else {
-    c.t.cth = L.sc_cth + so; c.t.R = L.sc_R + so;
+    c.t.cth = L.sc_cth + so; c.t.R = L.sc_Rr + so;
     c.t.ths = L.sc_ths + so * SWB_MAX_BASES; c.t.n0 = L.sc_n0 + so * SWB_MAX_BASES;
     c.t.g = L.sc_g + so; c.t.nF = L.sc_nF + so; c.t.nmax = L.sc_nmax + so;
   }
@@ -280,7 +357,7 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   c.n = L.sc_n + so;
   c.P = P; c.J = J; c.T = T; c.GT = G * T; c.B = B; c.D = D; c.invD = 1.0 / D;
   c.Rsec = L.sc_R + so;
-  BlockRed br(red);
+  ClusterRed<CL> br(red, xslots);
 #pragma unroll
   for (int b = 0; b < 8; ++b)
     c.sl[b] = (b + 1 < B) ? (float)((prm.logv[b + 1] - prm.logv[b]) / (prm.bases[b + 1] - prm.bases[b])) : -INFINITY;
@@ -304,7 +381,7 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   // ---- phase 1: job constants + finish-time-fairness rows (shockwave.py:573-597) -----------
   long long infeasible = 0, forced = 0;
   int badw = 0;      // gang widths are bytes from here on: anything outside [1,255] is reported, never truncated
-  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+  for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) {
     const double Ef = (double)EI[j], cf = (double)cI[j], dbar = dbarI[j], R = RI[j];
     const double cap = dbar * (Ef - cf);
     const double a = D / (dbar * Ef);
@@ -315,7 +392,7 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
     if (gw > G) nmax = 0;  // a gang wider than the cluster violates every capacity row (shockwave.py:317)
     if (L.ncap && (int)L.ncap[so + j] < nmax) nmax = L.ncap[so + j];  // packing feedback (written by place_kernel)
     c.a[j] = a; c.u0[j] = cf / Ef; c.cap[j] = cap;
-    c.t.R[j] = R * c.invD; L.sc_R[so + j] = R;
+    c.t.R[j] = R * c.invD; L.sc_R[so + j] = R;   // rounds (table) and seconds (exact passes): distinct buffers
     c.t.g[j] = (uint8_t)(gw < 1 ? 1 : (gw > 255 ? 255 : gw)); c.t.nmax[j] = (uint8_t)nmax;
     const double capF = share * (prm.rhomax * ftI[j] - next_t);
     int nF = 0, bad = 0;
@@ -347,7 +424,7 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   // fallback priorities (shockwave.py:830-911); weights stay 1 when the FTF rows are satisfiable.
   // Then the response table of the job (see the file header).
   double mu_max = 0.0, mfloor = 0.0, mtop = 0.0;
-  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+  for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) {
     double w = 1.0;
     if (!ftf_ok) {
       c.t.nF[j] = 0;
@@ -434,20 +511,30 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   Price pr = solve_price(c, br, best_thr, mu_max, 22, hint);
   iters += pr.iters;
   const double thr_d = best_thr * c.invD;
-  for (int j = threadIdx.x; j < J; j += blockDim.x) c.n[j] = (uint8_t)job_n(c, j, thr_d, pr.hi);
+  for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) c.n[j] = (uint8_t)job_n(c, j, thr_d, pr.hi);
   long long left = (long long)c.GT - pr.cost_hi;
   __syncthreads();
 
   // (a) ties at the clearing price: jobs whose demand jumps between pr.lo and pr.hi, in job order
+  //     (cluster: the carry into this CTA's slice is the tie demand of the lower ranks)
   __shared__ long long s_carry;
   __shared__ long long s_wsum[32];
   if (left > 0 && pr.lo < pr.hi) {
-    if (threadIdx.x == 0) s_carry = 0;
+    long long mine = 0;
+    if constexpr (CL > 1) {
+      for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) {
+        int extra = job_n(c, j, thr_d, pr.lo) - (int)c.n[j];
+        if (extra > 0) mine += (long long)c.t.g[j] * extra;
+      }
+      mine = br.br.sumll(mine);
+    }
+    const long long carry0 = br.prefix_of_rank(mine, rank);
+    if (threadIdx.x == 0) s_carry = carry0;
     __syncthreads();
-    for (int base = 0; base < J; base += blockDim.x) {
+    for (int base = c.j0; base < c.j1; base += blockDim.x) {
       const int j = base + threadIdx.x;
       int extra = 0, gj = 1;
-      if (j < J) { gj = c.t.g[j]; extra = job_n(c, j, thr_d, pr.lo) - (int)c.n[j]; if (extra < 0) extra = 0; }
+      if (j < c.j1) { gj = c.t.g[j]; extra = job_n(c, j, thr_d, pr.lo) - (int)c.n[j]; if (extra < 0) extra = 0; }
       long long v = (long long)gj * extra, incl = v;
       for (int o = 1; o < 32; o <<= 1) {
         long long t = __shfl_up_sync(SWB_FULL, incl, o);
@@ -459,7 +546,7 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
       for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += s_wsum[w];
       const long long carry = s_carry;
       const long long excl = carry + woff + incl - v;
-      if (j < J && extra > 0) {
+      if (j < c.j1 && extra > 0) {
         long long room = left - excl;
         if (room > 0) {
           long long take = room / gj;
@@ -476,12 +563,12 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   // (b) completion: best remaining item that still fits, a few times
   {
     long long used = 0;
-    for (int j = threadIdx.x; j < J; j += blockDim.x) used += (long long)c.t.g[j] * c.n[j];
+    for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) used += (long long)c.t.g[j] * c.n[j];
     used = br.sumll(used);
     left = (long long)c.GT - used;
     for (int rep = 0; rep < 32 && left > 0; ++rep) {
       double bd = 0.0;
-      for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) {
         const int n = c.n[j];
         if (n < c.t.nmax[j] && (long long)c.t.g[j] <= left)
           bd = fmax(bd, (util_of(c, j, n + 1) - util_of(c, j, n)) / (double)c.t.g[j]);
@@ -489,7 +576,7 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
       bd = br.max(bd);
       if (!(bd > 0.0)) break;
       double bj = 1e300;
-      for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) {
         const int n = c.n[j];
         if (n < c.t.nmax[j] && (long long)c.t.g[j] <= left &&
             (util_of(c, j, n + 1) - util_of(c, j, n)) / (double)c.t.g[j] >= bd)
@@ -498,15 +585,20 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
       bj = br.min(bj);
       if (bj >= 1e299) break;
       const int wj = (int)bj;
-      if (threadIdx.x == 0) c.n[wj] = (uint8_t)(c.n[wj] + 1);
-      left -= c.t.g[wj];
+      // the CTA that owns job wj applies the step; its width reaches the others through a cluster reduction
+      double gw = 0.0;
+      if (wj >= c.j0 && wj < c.j1) {
+        if (threadIdx.x == 0) { c.n[wj] = (uint8_t)(c.n[wj] + 1); gw = (double)c.t.g[wj]; }
+      }
+      if constexpr (CL > 1) gw = br.max(gw); else gw = (double)c.t.g[wj];
+      left -= (long long)gw;
       __syncthreads();
     }
   }
 
   // ---- phase 5: scalars of the plan; constants the placement kernel re-reads ------------------
   double w = 0.0, me = 0.0;
-  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+  for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) {
     const int n = c.n[j];
     w += util_of(c, j, n);
     me = fmax(me, rem_of(c, j, n));
@@ -514,7 +606,7 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   }
   w = br.sum(w);
   me = br.max(me);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && rank == 0) {
     swb_result &r = L.res[s];
     r.status = ftf_ok ? SWB_ST_OK : SWB_ST_FALLBACK;
     r.m_evals = m_evals;
@@ -532,15 +624,23 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
     RelaxCtx rc;
     rc.nfc = L.sc_nfc + so; rc.Tr = (double)T;
     const double rv = relaxed_optimum(c, rc, br, mu_max, k);
-    if (threadIdx.x == 0) L.res[s].relaxed_objective = rv;
+    if (threadIdx.x == 0 && rank == 0) L.res[s].relaxed_objective = rv;
   }
+  if constexpr (CL > 1) cg::this_cluster().sync();   // nobody leaves while its exchange slots may still be read
 }
 
 static int g_solve_nt = 1024;   // threads per CTA of the shared-memory variant (SWB_SOLVE_NT=512 for experiments)
+static int g_solve_cl = 8;      // CTAs per scenario on the latency path (SWB_SOLVE_CLUSTER=1 switches the cluster off)
+
+void set_solve_cluster(int v) { g_solve_cl = (v == 8) ? 8 : 1; }
+
+template <class K>
+static cudaError_t set_smem_attr(K kern, int static_bytes) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SWB_MAX_DYN_SMEM - static_bytes);
+}
 
 cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st, int nbases) {
-  size_t smem = SWB_PWL_BYTES + 2 * 64 * sizeof(double);
-  if (L.jobs_in_smem) smem += (size_t)L.J * (2 * sizeof(double) + 5 * (size_t)nbases + 3);
+  const size_t smem_fixed = SWB_PWL_BYTES + (2 * 64 + 4) * sizeof(double);
   // function attributes are per device: one flag per device ordinal (one process may drive several GPUs)
   static bool attr_done[64] = {false};
   int dev_ = 0;
@@ -548,24 +648,41 @@ cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st, int nbases) {
   bool &attr_set = attr_done[dev_ & 63];
   if (!attr_set) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, solve_kernel<true, 1024>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, solve_kernel<true, 1024, 1>);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(solve_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SWB_MAX_DYN_SMEM - (int)fa.sharedSizeBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(solve_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SWB_MAX_DYN_SMEM - (int)fa.sharedSizeBytes);
-    if (e != cudaSuccess) return e;
+    if ((e = set_smem_attr(solve_kernel<true, 1024, 1>, (int)fa.sharedSizeBytes)) != cudaSuccess) return e;
+    if ((e = set_smem_attr(solve_kernel<true, 512, 1>, (int)fa.sharedSizeBytes)) != cudaSuccess) return e;
+    if ((e = set_smem_attr(solve_kernel<true, 512, 8>, (int)fa.sharedSizeBytes)) != cudaSuccess) return e;
     const char *env = getenv("SWB_SOLVE_NT");
     if (env) g_solve_nt = atoi(env) == 512 ? 512 : 1024;
+    env = getenv("SWB_SOLVE_CLUSTER");
+    if (env) g_solve_cl = atoi(env) == 8 ? 8 : 1;
     attr_set = true;
   }
+  // Latency path: few scenarios of many jobs leave most of the 148 SMs idle with one CTA per scenario — a cluster of
+  // 8 CTAs (portable size, same die) shares one scenario over distributed shared memory instead.
+  if (L.jobs_in_smem && g_solve_cl == 8 && L.J >= 512 && L.S * 8 <= 144) {
+    const int Jc = ((((L.J + 7) / 8) + 31) & ~31);
+    const size_t smem = smem_fixed + (size_t)Jc * (2 * sizeof(double) + 5 * (size_t)nbases + 3);
+    int nt = Jc < 512 ? Jc : 512;
+    if (nt < 64) nt = 64;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(L.S * 8)); cfg.blockDim = dim3((unsigned)nt);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, solve_kernel<true, 512, 8>, L);
+  }
+  size_t smem = smem_fixed;
+  if (L.jobs_in_smem) smem += (size_t)L.J * (2 * sizeof(double) + 5 * (size_t)nbases + 3);
   int nt = ((L.J + 31) / 32) * 32;
   if (nt > g_solve_nt) nt = g_solve_nt;
   if (nt < 64) nt = 64;
-  if (!L.jobs_in_smem) solve_kernel<false, 1024><<<L.S, nt, smem, st>>>(L);
-  else if (g_solve_nt == 512) solve_kernel<true, 512><<<L.S, nt, smem, st>>>(L);
-  else solve_kernel<true, 1024><<<L.S, nt, smem, st>>>(L);
+  if (!L.jobs_in_smem) solve_kernel<false, 1024, 1><<<L.S, nt, smem, st>>>(L);
+  else if (g_solve_nt == 512) solve_kernel<true, 512, 1><<<L.S, nt, smem, st>>>(L);
+  else solve_kernel<true, 1024, 1><<<L.S, nt, smem, st>>>(L);
   return cudaGetLastError();
 }
 

@@ -26,7 +26,7 @@ struct SolveLaunch {
   double *sc_a, *sc_u0, *sc_R, *sc_ws, *sc_cap;
   uint8_t *sc_g, *sc_nF, *sc_nmax, *sc_n;
   // response table in global memory, only used when J > SWB_SMEM_JOBS ([S][J] and [S][J][SWB_MAX_BASES])
-  double *sc_cth;
+  double *sc_cth, *sc_Rr;   // sc_Rr: remaining runtime in rounds (the table copy; sc_R keeps seconds)
   float *sc_ths;
   uint8_t *sc_n0;
   double *sc_nfc;      // [S][J] continuous FTF lower bounds (relaxation only)
@@ -55,6 +55,7 @@ struct PlaceLaunch {
 };
 
 cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st, int nbases);
+void set_solve_cluster(int ctas_per_scenario);
 cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask);
 
 struct ForecastLaunch {
@@ -146,7 +147,27 @@ struct GbmLaunch {
   const double *R0, *mu, *sigma;
   const int32_t *H;
   double *out;   // [2][J]: sum R, sum R^2 over the local paths
+  // table-driven variant (swb_round_solve): mu / sigma come from the resident job table through `slots`, the
+  // horizon is min(E - c, Hmax) from the forecast kernel's own outputs; null -> the plain arrays above
+  const int32_t *slots, *Eo, *co;
+  const double *tab_mu, *tab_sigma;
+  int Hmax;
 };
 cudaError_t launch_gbm(const GbmLaunch &L, cudaStream_t st);
+// rem / bfkey (both continuations) *= E_mc[R] / R0 for the jobs whose model has drift or volatility; jobs with
+// mu = sigma = 0 keep the deterministic forecast bit for bit
+struct GbmApplyLaunch {
+  int J;
+  double P_total;
+  const double *sums;      // [2][J] after the allreduce
+  const int32_t *slots;
+  const double *tab_mu, *tab_sigma;
+  double *rem, *rem_fb, *bfkey, *bfkey_fb;   // in/out, may be null
+  double *var_out;         // [J] variance of the forecast, may be null
+};
+cudaError_t launch_gbm_apply(const GbmApplyLaunch &L, cudaStream_t st);
+// scenario ensemble from one Monte-Carlo forecast: rem[s][j] = max(0, mean_j + z_s * std_j)  (forecast quantiles)
+cudaError_t launch_gbm_ensemble(int S, int J, double P_total, const double *sums, const double *z, double *rem_out,
+                                cudaStream_t st);
 
 }  // namespace swb

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libswb200.so")
 
 MAX_BASES = 16
 ST_OK, ST_FALLBACK = 0, 1
+OPT_RELAXED_OPTIMUM, OPT_SOLVE_CLUSTER, OPT_GBM_PATHS, OPT_GBM_SEED, OPT_GBM_HORIZON = 1, 2, 3, 4, 5
 
 
 class Params(C.Structure):
@@ -52,11 +53,12 @@ class RoundArgs(C.Structure):
     _fields_ = [("J", C.c_int32), ("reestimate_share", C.c_int32), ("gavel_round_duration", C.c_double),
                 ("slots", C.c_void_p), ("epoch_progress", C.c_void_p), ("meas_nsamples", C.c_void_p),
                 ("meas_end_round", C.c_void_p), ("x", C.c_void_p), ("backfill", C.c_void_p),
-                ("nrounds", C.c_void_p), ("forecast_out", C.c_void_p), ("res", C.POINTER(Result))]
+                ("nrounds", C.c_void_p), ("forecast_out", C.c_void_p), ("res", C.POINTER(Result)),
+                ("xmask", C.c_void_p), ("bfmask", C.c_void_p)]
 
 
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
-           "swb_solve", "swb_job_add", "swb_job_remove", "swb_job_table_stats", "swb_round_solve", "swb_forecast",
+           "swb_solve", "swb_job_add", "swb_job_remove", "swb_job_table_stats", "swb_job_set_gbm", "swb_gbm_ensemble", "swb_round_solve", "swb_forecast",
            "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_policy_hetero", "swb_gbm_forecast", "swb_market_pgd", "swb_set_option", "swb_allox_assign"]
 
 _lib = None
@@ -216,6 +218,18 @@ class Engine:
     def job_remove(self, slot):
         self._check(self.lib.swb_job_remove(self.h, int(slot)), "swb_job_remove")
 
+    def job_set_gbm(self, slot, mu, sigma):
+        self.lib.swb_job_set_gbm.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double]
+        self._check(self.lib.swb_job_set_gbm(self.h, int(slot), float(mu), float(sigma)), "swb_job_set_gbm")
+
+    def gbm_ensemble(self, S, J, P_total, sums_device_ptr, z, rem_out_device_ptr):
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        assert len(z) == S
+        self.lib.swb_gbm_ensemble.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]
+        self._check(self.lib.swb_gbm_ensemble(self.h, int(S), int(J), float(P_total), C.c_void_p(int(sums_device_ptr)),
+                                              _ptr(z), C.c_void_p(int(rem_out_device_ptr))), "swb_gbm_ensemble")
+
     def job_table_stats(self):
         used, holes = C.c_int64(), C.c_int64()
         self.lib.swb_job_table_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -232,16 +246,23 @@ class Engine:
         a.slots, a.epoch_progress, a.meas_nsamples, a.meas_end_round = _ptr(slots), _ptr(progress), _ptr(meas_ns), _ptr(meas_end)
         return a, (slots, progress, meas_ns, meas_end)
 
-    def round_solve(self, params, slots, progress, meas_ns, meas_end, reestimate, grd, want_forecast=False):
+    def round_solve(self, params, slots, progress, meas_ns, meas_end, reestimate, grd, want_forecast=False,
+                    packed=False):
+        """packed=True: x / backfill come back as [J, 2] uint64 round masks (`xmask`, `bfmask`) instead of J x T bytes."""
         a, keep = self._round_args(slots, progress, meas_ns, meas_end, reestimate, grd)
         J, T = a.J, params.future_rounds
-        x = np.zeros((J, T), dtype=np.uint8); bf = np.zeros((J, T), dtype=np.uint8)
-        nr = np.zeros(J, dtype=np.int32)
-        fo = np.zeros((6, J), dtype=np.float64) if want_forecast else None
+        x = bf = xm = bm = None
+        if packed:
+            xm = np.empty((J, 2), dtype=np.uint64); bm = np.empty((J, 2), dtype=np.uint64)
+        else:
+            x = np.zeros((J, T), dtype=np.uint8); bf = np.zeros((J, T), dtype=np.uint8)
+        nr = np.empty(J, dtype=np.int32)
+        fo = np.empty((6, J), dtype=np.float64) if want_forecast else None
         res = Result()
         a.x, a.backfill, a.nrounds, a.forecast_out, a.res = _ptr(x), _ptr(bf), _ptr(nr), _ptr(fo), C.pointer(res)
+        a.xmask, a.bfmask = _ptr(xm), _ptr(bm)
         self._check(self.lib.swb_round_solve(self.h, C.byref(params), C.byref(a)), "swb_round_solve")
-        out = dict(x=x, backfill=bf, nrounds=nr, result=res.as_dict())
+        out = dict(x=x, backfill=bf, xmask=xm, bfmask=bm, nrounds=nr, result=res.as_dict())
         if want_forecast:
             fb = res.status == ST_FALLBACK
             out.update(dbar=fo[0], rem=fo[1], ftobj=fo[2], bfkey=fo[5] if fb else fo[3], rem_fb=fo[4])

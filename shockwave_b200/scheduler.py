@@ -29,7 +29,8 @@ class ShockwaveScheduler(object):
                  round_duration: int, solver_preference: list, solver_rel_gap: float,
                  solver_num_threads: int, solver_timeout: float, n_epoch_vars_max: int,
                  logapx_bases: list, logapx_origin: dict, k: float, lam: float, rhomax: float,
-                 device: int = 0):
+                 device: int = 0, timeline_check: str = "dirty", forecast: str = "dirichlet",
+                 gbm_paths: int = 8192, gbm_seed: int = 0, gbm_volatility=None, gbm_horizon: int = 256):
         # same argument checks as shockwave.py:40-69
         self.ngpus = ngpus
         self.gram = gram
@@ -56,8 +57,27 @@ class ShockwaveScheduler(object):
         self.rhomax = rhomax
 
         self._device = device
+        # how changes of the caller-owned JobMetaData objects are noticed at re-solve time.  "dirty": only the jobs
+        # touched through this class since the previous re-solve (add_metadata / schedule_progress — the simulator
+        # appends a throughput measurement exactly for the jobs it then reports progress for, scheduler.py:555-571,
+        # :2274-2341) are re-read; "exact": every job's timeline signature and epoch_progress are re-read each time
+        # (for callers that mutate JobMetaData behind this class's back).  Identical results on the reference's loops.
+        # forecast = "dirichlet": the reference's deterministic remaining-runtime estimate (JobMetaData.py:315-370);
+        # "gbm": that estimate becomes the start of `gbm_paths` geometric-Brownian-motion sample paths per job on the
+        # device (gbm.cu) and the solve plans against their mean.  gbm_volatility: None -> per-job sigma from the spread
+        # of the profile inside its batch-size modes (0 for reference-generated profiles); a float -> that sigma for
+        # every job; a (mu, sigma) pair; or a callable(jobid, JobMetaData) -> (mu, sigma).  Jobs with mu = sigma = 0
+        # keep the deterministic value bit for bit.
+        assert forecast in ("dirichlet", "gbm")
+        self.forecast, self.gbm_paths, self.gbm_seed = forecast, int(gbm_paths), int(gbm_seed)
+        self.gbm_volatility, self.gbm_horizon = gbm_volatility, int(gbm_horizon)
+        assert timeline_check in ("dirty", "exact")
+        self._timeline_check = timeline_check
+        self._dirty = set()
+        self._prog = np.zeros(64, dtype=np.int32)           # epoch_progress by slot (kept by schedule_progress)
         self._engine = None
         self._slots = {}          # jobid -> slot of the device-resident job table
+        self._slot_job = {}       # slot -> jobid
         self._free_slots = []
         self._next_slot = 0
         # per-slot cache of the throughput-timeline summaries (see _timeline_summaries)
@@ -66,7 +86,10 @@ class ShockwaveScheduler(object):
         self._tl_val = np.empty(64, dtype=object)           # ... and its value
         self._tl_ns = np.zeros(64, dtype=np.float64)        # summary: measured samples
         self._tl_end = np.full(64, -1, dtype=np.int32)      # summary: last measured round
+        self._tl_base = np.zeros(64, dtype=np.float64)      # running sum WITHOUT the last entry ...
+        self._tl_prev = np.zeros(64, dtype=np.int64)        # ... and the round before the last one (incremental update)
         self._slot_arr = None     # slots in metadata order, rebuilt after add / remove
+        self._ids_cache = None    # (job ids, job objects) in metadata order, rebuilt after add / remove
         self.last_result = None   # scalars of the latest solve (objective, status, ...)
 
         assert type(init_metadata) == OrderedDict
@@ -85,7 +108,21 @@ class ShockwaveScheduler(object):
     def _eng(self):
         if self._engine is None:
             self._engine = _eng.Engine(self._device)   # raises when the CUDA library / GPU is missing
+            if self.forecast == "gbm":
+                self._engine.set_option(_eng.OPT_GBM_PATHS, self.gbm_paths)
+                self._engine.set_option(_eng.OPT_GBM_SEED, self.gbm_seed)
+                self._engine.set_option(_eng.OPT_GBM_HORIZON, self.gbm_horizon)
         return self._engine
+
+    def _gbm_model(self, jobid, job):
+        v = self.gbm_volatility
+        if v is None:
+            return None
+        if callable(v):
+            return tuple(float(a) for a in v(jobid, job))
+        if isinstance(v, (tuple, list)):
+            return float(v[0]), float(v[1])
+        return 0.0, float(v)
 
     def _on_add(self, jobid, job):
         slot = self._free_slots.pop() if self._free_slots else self._next_slot
@@ -95,20 +132,30 @@ class ShockwaveScheduler(object):
         self._eng().job_add(slot, job.nworkers, job.epochs, job.epoch_nsamples,
                             float("nan") if ts is None else ts,
                             job.epoch_duration_preprofiled, job.bs_schedule)
+        if self.forecast == "gbm":
+            ms = self._gbm_model(jobid, job)
+            if ms is not None:
+                self._eng().job_set_gbm(slot, ms[0], ms[1])
         self._slots[jobid] = slot
+        self._slot_job[slot] = jobid
         self._slot_arr = None
         if slot >= len(self._tl_len):
             grow = max(2 * len(self._tl_len), slot + 1)
-            for name, fill in (("_tl_len", -1), ("_tl_key", -2), ("_tl_val", None), ("_tl_ns", 0.0), ("_tl_end", -1)):
+            for name, fill in (("_tl_len", -1), ("_tl_key", -2), ("_tl_val", None), ("_tl_ns", 0.0), ("_tl_end", -1),
+                               ("_prog", 0), ("_tl_base", 0.0), ("_tl_prev", 0)):
                 old = getattr(self, name)
                 new = np.empty(grow, dtype=old.dtype)
                 new[:len(old)] = old
                 new[len(old):] = fill
                 setattr(self, name, new)
         self._tl_len[slot] = -1           # a new tenant of the slot: force a recompute
+        self._prog[slot] = job.epoch_progress
+        self._dirty.add(slot)
 
     def _on_remove(self, jobid):
         slot = self._slots.pop(jobid)
+        self._slot_job.pop(slot, None)
+        self._dirty.discard(slot)
         self._eng().job_remove(slot)
         self._free_slots.append(slot)
         self._slot_arr = None
@@ -128,12 +175,59 @@ class ShockwaveScheduler(object):
             prev = cur
         return float(nsamp), int(max(tl.keys()))
 
+    def _touch_timeline(self, sl, jobid, job):
+        """O(1) refresh of one job's summary after the caller appended (or rewrote) the measurement of the latest
+        round: the reference's sum runs over the sorted rounds (JobMetaData.py:235-249), so continuing it with the new
+        last term gives the same float; anything but "same entries" / "one entry appended at the end" falls back to
+        the full walk."""
+        tl = job.throughput_measurements
+        assert tl is not None                       # JobMetaData.py:229
+        n = len(tl)
+        if n == 0:
+            self._tl_len[sl], self._tl_ns[sl], self._tl_end[sl] = 0, 0.0, -1
+            return
+        lk = next(reversed(tl))
+        lv = tl[lk]
+        cl, ck = self._tl_len[sl], self._tl_key[sl]
+        if n == cl and lk == ck:
+            base, pk = self._tl_base[sl], int(self._tl_prev[sl])
+        elif cl >= 0 and n == cl + 1 and (cl == 0 or (lk > ck and tl.get(int(ck)) == self._tl_val[sl])):
+            base, pk = (self._tl_ns[sl], int(ck)) if cl > 0 else (0.0, 0)
+        else:
+            ns_i, end_i = self._timeline_summary(jobid, job)
+            ks = sorted(tl.keys())
+            if ks[-1] == lk:                        # insertion order == sorted order: the cache can continue from here
+                last = tl[lk]
+                pk = ks[-2] if n > 1 else 0
+                base = 0
+                prev = 0
+                for cur in ks[:-1]:
+                    base += tl[cur][1] * (tl[cur][0] * job.gavel_round_duration * (cur - prev))
+                    prev = cur
+                self._tl_len[sl], self._tl_key[sl], self._tl_val[sl] = n, lk, last
+                self._tl_base[sl], self._tl_prev[sl] = float(base), pk
+            else:
+                self._tl_len[sl] = -1
+            self._tl_ns[sl], self._tl_end[sl] = ns_i, end_i
+            return
+        ns = base + lv[1] * (lv[0] * job.gavel_round_duration * (lk - pk))
+        self._tl_len[sl], self._tl_key[sl], self._tl_val[sl] = n, lk, lv
+        self._tl_base[sl], self._tl_prev[sl] = base, pk
+        self._tl_ns[sl], self._tl_end[sl] = ns, lk
+
     def _timeline_summaries(self, jobids, jobobjs, slots):
         """Vector form, cached per slot while the job's shared throughput OrderedDict is unchanged (signature =
         length + last (round, value) entry; the caller only appends / rewrites the current round,
         scheduler.py:568-571).  The per-job work runs in C (map / numpy); Python only touches the jobs whose
         timeline changed since the previous re-solve."""
         J = len(jobids)
+        if self._timeline_check == "dirty":
+            for sl in self._dirty:                  # jobs added since the previous re-solve
+                jid = self._slot_job.get(sl)
+                if jid is not None:
+                    self._touch_timeline(sl, jid, self.metadata[jid])
+            self._dirty.clear()
+            return self._tl_ns[slots], self._tl_end[slots]
         tls = list(map(operator.attrgetter("throughput_measurements"), jobobjs))
         assert None not in tls                      # JobMetaData.py:229
         lens = np.fromiter(map(len, tls), dtype=np.int64, count=J)
@@ -157,16 +251,20 @@ class ShockwaveScheduler(object):
         if self._slot_arr is None or len(self._slot_arr) != J:
             self._slot_arr = np.fromiter(map(self._slots.__getitem__, jobids), dtype=np.int32, count=J)
         slots = self._slot_arr
-        prog = np.fromiter(map(operator.attrgetter("epoch_progress"), jobobjs), dtype=np.int32, count=J)
+        if self._timeline_check == "dirty":
+            prog = self._prog[slots]
+        else:
+            prog = np.fromiter(map(operator.attrgetter("epoch_progress"), jobobjs), dtype=np.int32, count=J)
         ns, end = self._timeline_summaries(jobids, jobobjs, slots)
         prm = _eng.make_params(self.ngpus, self.future_nrounds, self.round_duration, self.k, self.lam,
                                self.rhomax, self.logapx_bases, self.logapx_origin, self.round_ptr)
         grd = jobobjs[0].gavel_round_duration
         out = self._eng().round_solve(prm, slots, prog, ns, end, self.reestimate_share, grd,
-                                      want_forecast=True)
+                                      want_forecast=True, packed=True)
         self.last_result = out["result"]
         self.last_forecast = {k: out[k] for k in ("dbar", "rem", "ftobj", "bfkey")}
-        return schedules_from_matrices(out["x"], out["backfill"], out["bfkey"], jobids, self.round_ptr)
+        return LazySchedules(None, None, out["bfkey"], jobids, self.round_ptr, xmask=out["xmask"],
+                             bfmask=out["bfmask"], T=self.future_nrounds)
 
     # ---- reference surface ------------------------------------------------------------------------
     def round_schedule(self):
@@ -174,8 +272,9 @@ class ShockwaveScheduler(object):
             if len(self.schedules) > 0:
                 if self.round_ptr in self.schedules.keys():
                     return self.schedules[self.round_ptr]
-        jobids = list(self.metadata.keys())
-        jobobjs = list(self.metadata.values())
+        if self._ids_cache is None:                 # rebuilt after add / remove only
+            self._ids_cache = (list(self.metadata.keys()), list(self.metadata.values()))
+        jobids, jobobjs = self._ids_cache
         # the reference re-seeds both global RNGs on every solver call (call_cvxpy_solver,
         # shockwave.py:451-452); the simulator draws from them afterwards, so this side effect is part
         # of the drop-in contract
@@ -201,6 +300,11 @@ class ShockwaveScheduler(object):
         job = self.metadata[jobid]
         job.set_epoch_progress(epoch_progress)
         job.reset_waiting_delay()
+        slot = self._slots.get(jobid)
+        if slot is not None:
+            self._prog[slot] = job.epoch_progress
+            if self._timeline_check == "dirty":
+                self._touch_timeline(slot, jobid, job)
 
     def deschedule_waiting_delay(self, jobid, delay):
         if jobid in self.metadata.keys():
@@ -209,6 +313,7 @@ class ShockwaveScheduler(object):
     def add_metadata(self, jobid, jobobj, share_update=True):
         assert jobid not in self.metadata.keys()
         self.metadata[jobid] = jobobj
+        self._ids_cache = None
         self._on_add(jobid, jobobj)
         self.set_resolve()
         if share_update:
@@ -221,6 +326,7 @@ class ShockwaveScheduler(object):
             self.reestimate_share = True
         assert jobid in self.metadata.keys()
         self.metadata.pop(jobid)
+        self._ids_cache = None
         self._on_remove(jobid)
         self.set_resolve()
 
@@ -233,21 +339,33 @@ class LazySchedules(OrderedDict):
     re-solve after one or a few rounds; at 4096 jobs x 64 rounds building every list costs more host time
     than the whole GPU solve."""
 
-    def __init__(self, x, backfill, bfkey, jobids, round_ptr):
+    def __init__(self, x, backfill, bfkey, jobids, round_ptr, xmask=None, bfmask=None, T=None):
         super().__init__()
-        self._x, self._bf, self._ids, self._r0 = x, backfill, list(jobids), round_ptr
-        self._order = np.argsort(-np.asarray(bfkey, dtype=np.float64), kind="stable")
-        for t in range(x.shape[1]):
+        self._x, self._bf, self._ids, self._r0 = x, backfill, jobids, round_ptr
+        self._xm, self._bm = xmask, bfmask      # packed form: [J, 2] uint64, bit t of the 128-bit row = round t
+        self._bfkey, self._order = bfkey, None
+        for t in range(x.shape[1] if x is not None else T):
             super().__setitem__(round_ptr + t, None)
+
+    def _column(self, which, t):
+        if self._xm is not None:
+            m = self._xm if which == 0 else self._bm
+            return np.flatnonzero((m[:, t >> 6] >> np.uint64(t & 63)) & np.uint64(1))
+        return np.flatnonzero((self._x if which == 0 else self._bf)[:, t])
 
     def __getitem__(self, rnd):
         cur = super().__getitem__(rnd)
         if cur is None:
             t = rnd - self._r0
             ids = self._ids
-            cur = [ids[j] for j in np.flatnonzero(self._x[:, t]).tolist()]
-            order = self._order
-            cur += [ids[j] for j in order[np.flatnonzero(self._bf[order, t])].tolist()]
+            cur = [ids[j] for j in self._column(0, t).tolist()]
+            bfj = self._column(1, t)
+            if len(bfj):
+                if self._order is None:      # descending remaining runtime, stable (shockwave.py:261-267)
+                    self._order = np.argsort(-np.asarray(self._bfkey, dtype=np.float64), kind="stable")
+                    self._rank = np.empty(len(self._order), dtype=np.int64)
+                    self._rank[self._order] = np.arange(len(self._order))
+                cur += [ids[j] for j in bfj[np.argsort(self._rank[bfj], kind="stable")].tolist()]
             super().__setitem__(rnd, cur)
         return cur
 

@@ -82,3 +82,24 @@ def test_profile_pool_tracks_live_jobs_not_history(engine):
     for s in slots:
         engine.job_remove(s)
     assert engine.job_table_stats()["used_rows"] == base
+
+
+@pytest.mark.parametrize("J,G,T,k", [(512, 128, 32, 1e-3), (1000, 128, 20, 1e1), (4096, 512, 64, 1e-3),
+                                     (4096, 512, 64, 1e5), (3000, 96, 64, 1e1)])
+def test_cluster_solve_equals_single_cta_solve(engine, J, G, T, k):
+    """Latency path: a cluster of 8 CTAs shares one scenario (DSMEM reductions in rank order).  Same searches on the
+    same step functions -> the same round counts as the one-CTA kernel; the objective may differ in the last bits
+    (summation order)."""
+    for seed, tight in ((0, 3.0), (1, 0.5)):
+        pb = synth_problem(J, G, T, 120.0, seed=seed, tight=tight)
+        prm = make_params(G, T, 120.0, k, 12.0, 1.0, fx.BASES, fx.ORIGIN, round_ptr=pb["round_ptr"])
+        outs = []
+        for cl in (1, 8):
+            engine.set_option(2, cl)       # SWB_OPT_SOLVE_CLUSTER
+            outs.append(engine.solve(prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"]))
+        engine.set_option(2, 8)
+        a, b = outs
+        assert a["results"][0]["status"] == b["results"][0]["status"]
+        assert np.array_equal(a["nrounds"], b["nrounds"])
+        assert np.array_equal(a["x"], b["x"])
+        assert abs(a["results"][0]["objective"] - b["results"][0]["objective"]) <= 1e-9 * abs(a["results"][0]["objective"])
