@@ -233,7 +233,8 @@ int swb_allox_assign(swb_ctx *ctx, int32_t m, int32_t n, int32_t W, const double
  * sigma = mu = 0).  For job j and LOCAL paths p in [0, P_local): global path id = path_offset + p,
  *   R = R0_j * mean_{h=1..H_j} exp((mu_j - sigma_j^2/2) h + sigma_j W_h).
  * out = [2][J] float64: sum_p R and sum_p R^2 (divide by the GLOBAL path count after the allreduce).
- * out_on_device != 0: `out` is a device pointer (e.g. the tensor handed to ncclAllReduce). */
+ * out_on_device bit 0: `out` is a device pointer (e.g. the tensor handed to ncclAllReduce); bit 1: R0, H, mu and sigma
+ * are device pointers as well (inputs resident in HBM). */
 int swb_gbm_forecast(swb_ctx *ctx, int32_t J, const double *R0, const int32_t *H, const double *mu,
                      const double *sigma, int64_t P_local, int64_t path_offset, uint64_t seed, double *out,
                      int32_t out_on_device);

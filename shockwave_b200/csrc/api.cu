@@ -724,16 +724,23 @@ int swb_gbm_forecast(swb_ctx *c, int32_t J, const double *R0, const int32_t *H, 
   if (J <= 0 || P_local < 0) return fail(SWB_ERR_ARG, "swb_gbm_forecast: bad J / P_local");
   CK(cudaSetDevice(c->device));
   const size_t b = (size_t)J * 8;
-  CK(c->mc_R0.need(b, c->st)); CK(c->mc_mu.need(b, c->st)); CK(c->mc_sigma.need(b, c->st));
-  CK(c->mc_H.need((size_t)J * 4, c->st)); CK(c->mc_out.need(2 * b, c->st));
-  CK(cudaMemcpyAsync(c->mc_R0.p, R0, b, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->mc_mu.p, mu, b, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->mc_sigma.p, sigma, b, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->mc_H.p, H, (size_t)J * 4, cudaMemcpyHostToDevice, c->st));
+  const int in_dev = (out_on_device & 2) ? 1 : 0;      // bit 1: R0, H, mu, sigma are device pointers as well
+  out_on_device &= 1;
   swb::GbmLaunch L;
   L.J = J; L.P_local = P_local; L.path_offset = path_offset; L.seed = seed;
-  L.R0 = c->mc_R0.as<double>(); L.mu = c->mc_mu.as<double>(); L.sigma = c->mc_sigma.as<double>();
-  L.H = c->mc_H.as<int32_t>();
+  CK(c->mc_out.need(2 * b, c->st));
+  if (in_dev) {
+    L.R0 = R0; L.mu = mu; L.sigma = sigma; L.H = H;
+  } else {
+    CK(c->mc_R0.need(b, c->st)); CK(c->mc_mu.need(b, c->st)); CK(c->mc_sigma.need(b, c->st));
+    CK(c->mc_H.need((size_t)J * 4, c->st));
+    CK(cudaMemcpyAsync(c->mc_R0.p, R0, b, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->mc_mu.p, mu, b, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->mc_sigma.p, sigma, b, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->mc_H.p, H, (size_t)J * 4, cudaMemcpyHostToDevice, c->st));
+    L.R0 = c->mc_R0.as<double>(); L.mu = c->mc_mu.as<double>(); L.sigma = c->mc_sigma.as<double>();
+    L.H = c->mc_H.as<int32_t>();
+  }
   L.slots = nullptr; L.Eo = nullptr; L.co = nullptr; L.tab_mu = nullptr; L.tab_sigma = nullptr; L.Hmax = 0;
   L.out = out_on_device ? out : c->mc_out.as<double>();
   CK(cudaEventRecord(c->ev[0], c->st));

@@ -69,6 +69,22 @@ struct ClusterRed {
     }
     return a;
   }
+  // demand sums: int32 (J * 255 * T < 2^31), REDUX inside the CTA, one 32-bit slot per CTA across the cluster
+  __device__ __forceinline__ int sumi(int a) {
+    a = br.sumi(a);
+    if constexpr (CL > 1) {
+      cg::cluster_group cl = cg::this_cluster();
+      int *xi = reinterpret_cast<int *>(xs);
+      if (threadIdx.x == 0) xi[xphase * 4] = a;
+      cl.sync();
+      int r = 0;
+#pragma unroll
+      for (int q = 0; q < CL; ++q) r += reinterpret_cast<const int *>(cl.map_shared_rank(xs, q))[xphase * 4];
+      a = r;
+      xphase ^= 1;
+    }
+    return a;
+  }
   __device__ __forceinline__ double max(double a) { a = br.max(a); double b = 0.0; exchange2(a, b, 1); return a; }
   __device__ __forceinline__ double min(double a) { return -max(-a); }
   // all-gather of one value per CTA (rank order) — used for the prefix of the tie-fill
@@ -150,7 +166,7 @@ __device__ long long cost_at(const Ctx &c, Red &br, double M, double mu) {
   int s = 0;
 #pragma unroll 4
   for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) s += (int)c.t.g[j] * job_n(c, j, Md, mu);
-  return br.sumll((long long)s);
+  return (long long)br.sumi(s);
 }
 
 struct Price { double hi, lo; long long cost_hi; int iters; };
@@ -171,7 +187,7 @@ __device__ Price solve_price(const Ctx &c, Red &br, double M, double mu_max, int
   if (c0 <= c.GT) { p.hi = p.lo = 0.0; p.cost_hi = c0; return p; }
   unsigned long long lob = 0ull, hib = (unsigned long long)__double_as_longlong(mu_max);
   double lo = 0.0, hi = mu_max;
-  long long chi = -1;
+  long long chi = -1, clo = -1;     // demand at hi / at lo (-1: not evaluated; lo = 0 has no log-scale position)
   if (hint > 0.0) {
     const double h4 = fmin(mu_max, hint * 4.0), l4 = hint * 0.25;
     const long long ch = cost_at(c, br, M, h4);
@@ -179,17 +195,42 @@ __device__ Price solve_price(const Ctx &c, Red &br, double M, double mu_max, int
     if (ch <= c.GT) { hi = h4; hib = (unsigned long long)__double_as_longlong(h4); chi = ch; }
     const long long cl = cost_at(c, br, M, l4);
     p.iters++;
-    if (cl > c.GT) { lo = l4; lob = (unsigned long long)__double_as_longlong(l4); }
+    if (cl > c.GT) { lo = l4; lob = (unsigned long long)__double_as_longlong(l4); clo = cl; }
     else if (chi >= 0 || l4 < hi) { hi = l4; hib = (unsigned long long)__double_as_longlong(l4); chi = cl; }
   }
   if (chi < 0) { chi = cost_at(c, br, M, hi); p.iters++; }
   const unsigned long long width = 1ull << (52 - prec);
+  // Regula falsi (Illinois variant) on the bit pattern, i.e. in log(price): the excess demand is a step function, but
+  // at the scale of the bracket it is close to linear in log(price), so interpolating between the two ends lands
+  // near the clearing price in a few evaluations; the Illinois halving of a stale end keeps the worst case
+  // logarithmic, and a plain bisection step is taken when the interpolation stops making progress.
+  double flo = clo >= 0 ? (double)(clo - c.GT) : -1.0, fhi = (double)(chi - c.GT);
+  int side = 0, stall = 0;
   while (hib - lob > width) {
-    const unsigned long long midb = lob + ((hib - lob) >> 1);
+    const unsigned long long span = hib - lob;
+    unsigned long long midb = lob + (span >> 1);
+    if (flo > 0.0 && fhi < 0.0 && stall < 2 && lob != 0ull) {
+      double frac = flo / (flo - fhi);
+      frac = fmin(0.95, fmax(0.05, frac));
+      midb = lob + (unsigned long long)((double)span * frac);
+      if (midb <= lob) midb = lob + 1;
+      if (midb >= hib) midb = hib - 1;
+    }
     const double mid = __longlong_as_double((long long)midb);
     const long long cm = cost_at(c, br, M, mid);
     p.iters++;
-    if (cm <= c.GT) { hib = midb; hi = mid; chi = cm; if (cm == c.GT) break; } else { lob = midb; lo = mid; }
+    const unsigned long long nspan = (cm <= c.GT) ? midb - lob : hib - midb;
+    stall = (nspan > span - (span >> 2)) ? stall + 1 : 0;      // shrank by less than a quarter
+    if (cm <= c.GT) {
+      hib = midb; hi = mid; chi = cm; fhi = (double)(cm - c.GT);
+      if (cm == c.GT) break;
+      if (side == 1 && flo > 0.0) flo *= 0.5;
+      side = 1;
+    } else {
+      lob = midb; lo = mid; flo = (double)(cm - c.GT);
+      if (side == -1) fhi *= 0.5;
+      side = -1;
+    }
   }
   p.hi = hi; p.lo = lo; p.cost_hi = chi;
   return p;

@@ -140,6 +140,30 @@ struct MarketLaunch {
 };
 cudaError_t launch_market_iter(const MarketLaunch &L, cudaStream_t st, bool dense);
 
+// Gavel's per-round priority -> selection -> worker assignment (gavel.cu).  Worker types appear in PROCESSING order
+// in type_order / nworkers / worker_ids; alloc etc. are [J][W] indexed by the caller's type index.
+struct GavelLaunch {
+  int J, W, flags, maxw;          // flags: bit0 Isolated_plus (strict order), bit1 FIFO (skip priority <= 0)
+  const int32_t *type_order;      // [W] type index processed ti-th
+  const int32_t *capacity;        // [W] by type index: cluster_spec
+  const double *alloc, *job_time, *deficit, *thr;   // [J][W]; alloc = NaN when the job is not in the allocation
+  const double *worker_time;      // [W]
+  const uint8_t *in_alloc;        // [J]
+  const int32_t *sf;              // [J] scale factors
+  const int32_t *nworkers;        // [W] by processing position
+  const int32_t *worker_ids;      // workers by processing position, server order
+  const int32_t *prev_type;       // [J] type index of last round's assignment, -1 = none
+  const int32_t *prev_off;        // [J+1]
+  const int32_t *prev_local;      // last round's workers as positions in their type's worker list
+  double *prio;                   // [J][W] out
+  int32_t *n_sel, *sel_jobs;      // [W], [W][J] out: selected jobs per processing position, selection order
+  int32_t *assign_job, *assign_cnt, *assign_off, *assign_workers;   // out: assignments in insertion order
+  int32_t *tmp_rank0, *tmp_free;  // scratch
+  uint8_t *sched;                 // [J] scratch
+  int32_t *out_scalars;           // [2]: number of assignments, error flag
+};
+cudaError_t launch_gavel_round(const GavelLaunch &L, cudaStream_t st);
+
 struct GbmLaunch {
   int J;
   long long P_local, path_offset;

@@ -308,6 +308,13 @@ class Engine:
     def stream_ptr(self):
         return int(self.lib.swb_stream(self.h) or 0)
 
+    def gbm_forecast_device(self, J, R0_ptr, H_ptr, mu_ptr, sigma_ptr, P_local, path_offset, seed, out_ptr):
+        """All-device variant: raw device pointers in, partial sums written to out_ptr ([2, J] float64)."""
+        vp = lambda v: C.c_void_p(int(v))
+        self._check(self.lib.swb_gbm_forecast(self.h, int(J), vp(R0_ptr), vp(H_ptr), vp(mu_ptr), vp(sigma_ptr),
+                                              int(P_local), int(path_offset), int(seed), vp(out_ptr), 3),
+                    "swb_gbm_forecast")
+
     def gbm_forecast(self, R0, H, mu, sigma, P_local, path_offset=0, seed=0, out_device_ptr=None):
         """Sums over the local sample paths: returns [2, J] (host) or writes them to `out_device_ptr`."""
         R0 = np.ascontiguousarray(R0, dtype=np.float64); mu = np.ascontiguousarray(mu, dtype=np.float64)
