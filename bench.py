@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """bench.py — schedule rounds/sec of the per-round market solve on B200 (BASELINE.json metric).
 
-Workload (config.workload): BASELINE.json config D — 4096 jobs x 512 GPUs x 64-round planning window.
-One "step" = the Monte-Carlo (GBM) throughput forecast of the live job set (8192 paths/job, sharded over
-the ranks, one NCCL allreduce) followed by one pass of the market solve + round placement +
-work-conserving back-fill over a batch of S independent scenarios of that size (a hyper-parameter / trace-ensemble sweep: every
-scenario has its own synthetic job set and its own k).  A scenario is one CTA, so S = 2 x 148 fills
-the GPU twice.  `value` = scenarios solved per second with the inputs resident in HBM; `e2e` = the
-same through the public host API (Engine.solve, pinned host buffers, H2D + D2H inside the call);
-`latency_ms_S1` in `config` = one single re-solve (what ShockwaveScheduler.round_schedule() pays).
+Workload (identical in both arms, `config`): BASELINE config D — ONE re-solve per step of a 4096-job x 512-GPU x
+64-round planning window, scenario `i` = tests/synth.py seeded with 1000 + i (+ rank offset), k cycling through the
+shipped configurations' values.  That is SURVEY.md §8(d)'s metric: 1 / time of one full round_schedule() re-solve.
 
-N > 1 (torchrun): scenarios shard across ranks with no data-path collective ("weak" scaling, S per
-GPU fixed); the only collective is the max-over-ranks of the timed region.
+--impl ours (default)
+  value   one step = Monte-Carlo (GBM, 8192 paths/job) forecast of the step's job set -> its mean replaces the
+          deterministic remaining runtime ON THE DEVICE (swb_gbm_ensemble, z = 0) -> market solve (8-CTA cluster) ->
+          round placement + back-fill, everything resident in HBM, CUDA events on the launching stream.
+  e2e     the drop-in class itself: ShockwaveScheduler(forecast="gbm").round_schedule() with a forced re-solve per step
+          (host packing, host->device copies of the per-call inputs, forecast + GBM + solve + placement on the device,
+          device->host copies of the round masks, list building) — the call scheduler/scheduler.py:1131 makes.
+  batched a second, clearly separated figure: S = 296 what-if scenarios (k x rhomax x forecast quantile) of one job
+          set per step, one CTA each — the GBM forecast is computed once, path-sharded over the ranks with ONE NCCL
+          all-reduce, and every scenario plans against its own quantile of that forecast.
+  N > 1   independent scenario streams per rank (a single solve does not shard: "replicas only"), no data-path
+          collective in the headline step; the only collective of the timed region is the max over ranks.
 
---impl reference: the CPU path on the host cores — the HiGHS restatement of the reference's MILP
-(oracle/shockwave_milp.py; Gurobi/cvxpy cannot be installed here), one scenario of the same config
-per step with the reference's own solver settings (MIPGap 1e-3, TimeLimit 15 s).
+--impl reference
+  the reference's own CPU path for the same steps: the HiGHS restatement of its MILP (oracle/shockwave_milp.py; Gurobi
+  and cvxpy cannot be installed here), same seeds, same step count.  The reference's 15 s TimeLimit does not yield an
+  incumbent at this size (recorded in round 1), so the limit is lifted until HiGHS returns a schedule within the
+  reference's MIPGap 1e-3 (~2-5 min per scenario on one core); the K timed steps run concurrently, one single-threaded
+  HiGHS process per step on K host cores (HiGHS' branch and bound is single-threaded).
 """
 import argparse
 import json
@@ -35,25 +43,26 @@ ORIGIN = {0.0: 1e-6}
 J, G, T, D = 4096, 512, 64, 120.0
 K_SWEEP = [1e-3, 1e1, 1e5]          # the k values of the shipped configurations/*.json
 METRIC = "schedule rounds/sec (4096 jobs x 512 GPUs x 64-round window)"
+# identical in both arms (the driver compares it): what ONE step is
+CONFIG = {"workload": "BASELINE config D: 4096 jobs x 512 GPUs x 64-round window, one full re-solve per step",
+          "scenario_of_step_i": "tests/synth.py synth_problem(4096, 512, 64, seed=1000+i+1000003*rank, "
+                                "tight=3.0 if i % 4 else 0.5), k = [1e-3, 1e1, 1e5][i % 3], lam=12, rhomax=1",
+          "scenarios_per_step": 1, "parallelism": "one scenario stream per rank (replicas), no data-path collective"}
 
 
-def synth_batch(S, seed0):
+def scenario(i, rank=0):
     from tests.synth import synth_problem
-    pbs = [synth_problem(J, G, T, D, seed=seed0 + s, tight=3.0 if s % 4 else 0.5) for s in range(S)]
-    st = lambda k, dt: np.ascontiguousarray(np.stack([p[k] for p in pbs]).astype(dt))
-    arrs = dict(g=st("g", np.int32), E=st("E", np.int32), c=st("c", np.int32), dbar=st("dbar", np.float64),
-                rem=st("rem", np.float64), ftobj=st("ftobj", np.float64))
-    return arrs, [p["round_ptr"] for p in pbs]
+    pb = synth_problem(J, G, T, D, seed=1000 + i + 1000003 * rank, tight=3.0 if i % 4 else 0.5)
+    return pb, K_SWEEP[i % len(K_SWEEP)]
 
 
 class ClockSampler(threading.Thread):
-    """SM clock / throttle reasons DURING the timed region, through NVML (nvidia_ml_py) every 5 ms — the timed
-    region is ~50 ms, far too short for spawning nvidia-smi (B200_PROFILING.md's query, same fields)."""
+    """SM clock / throttle reasons DURING the timed region, through NVML every 2 ms (the recipe's nvidia-smi fields)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.sm, self.reasons, self.mx, self.power = index, False, [], set(), None, []
+        self.index, self.stop_flag, self.sm, self.mx, self.power = index, False, [], None, []
         self.t0, self.t1, self.ts, self.bits = None, None, [], []
 
     def run(self):
@@ -73,8 +82,7 @@ class ClockSampler(threading.Thread):
                 except Exception:
                     self.power.append(0.0); self.bits.append(0)
                 time.sleep(0.002)
-        except Exception as e:                      # NVML missing: fall back to one nvidia-smi query
-            self.error = repr(e)
+        except Exception:
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
@@ -84,12 +92,11 @@ class ClockSampler(threading.Thread):
                 pass
 
     def summary(self):
-        """Samples taken inside [t0, t1] (the timed region); the sampler itself starts before the warm-up."""
         idx = [i for i, t in enumerate(self.ts) if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e300)]
         if not idx:
             idx = list(range(len(self.sm)))
         sm = [self.sm[i] for i in idx]
-        reasons = set(self.reasons)
+        reasons = set()
         for i in idx:
             if i < len(self.bits):
                 for b, name in self.REASONS.items():
@@ -100,70 +107,118 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
-def _ref_one(seed):
-    """One config-D scenario through the HiGHS restatement of the reference's first MILP."""
+# ------------------------------------------------------------------------------------------ reference arm
+def _ref_step(args):
+    """One step on one host core: the HiGHS restatement of dynamic_eisenberg_gale_scheduling (model build + MILP at
+    the reference's MIPGap + fallback priorities / second solve when the FTF rows are infeasible) + construct_schedules.
+    `limit`: HiGHS time limit per MILP (the reference's own is 15 s)."""
+    i, limit, do_rank = args
     from oracle import shockwave_milp as om
-    from tests.synth import synth_problem
     logv = om.pwl_log_values(BASES, ORIGIN)
-    pb = synth_problem(J, G, T, D, seed=seed, tight=3.0)
+    pb, k = scenario(i)
     t0 = time.perf_counter()
-    cap = om.ftf_caps(pb["rem"], pb["ftobj"], G, J, T, D, pb["round_ptr"], 1.0)
-    ok, x, p, obj = om._solve(pb["g"].astype(np.int64), pb["E"].astype(float), pb["c"].astype(float),
-                              pb["dbar"], pb["rem"], np.ones(J), G, T, D, 1e-3, BASES, logv, cap, 1e-3, 15.0)
-    return bool(ok), time.perf_counter() - t0
+    try:
+        out = om.dynamic_eisenberg_gale(pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"], G, T, D,
+                                        pb["round_ptr"], k, 12.0, 1.0, BASES, logv, rel_gap=1e-3, time_limit=limit,
+                                        do_rank=do_rank)
+        om.construct_schedules(out["x"], list(range(J)), pb["g"], pb["rem"], pb["round_ptr"], G)
+        ok, status = True, int(out["status"])
+    except AssertionError:      # "relaxed problem must have a solution" = no incumbent inside the limit
+        ok, status = False, -1
+    return ok, status, time.perf_counter() - t0
 
 
 def run_reference(args):
-    """CPU arm: HiGHS restatement of the reference MILP on ALL host cores — HiGHS' branch-and-bound is
-    single-threaded, so one independent config-D scenario per core and step (a throughput-fair figure)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    # one single-threaded HiGHS process per host core, at most 16: with 64 concurrent processes on the 128-core GPU box
-    # one step took 416 s instead of ~70 s (memory-bandwidth contention) for barely more throughput (0.154 vs 0.10
-    # rounds/s) — past 16 the run no longer finishes "within a few minutes"
-    cores = max(1, min(os.cpu_count() or 1, 16))
-    steps = max(1, min(args.steps, 2))          # one step is ~70-100 s of CPU at this size
-    solved, walls = [], []
-    with mp.get_context("spawn").Pool(cores) as pool:
-        for i in range(steps):
-            t0 = time.perf_counter()
-            out = pool.map(_ref_one, [1000 + i * cores + w for w in range(cores)])
-            walls.append(time.perf_counter() - t0)
-            solved += [o[0] for o in out]
-    total = float(sum(walls))
-    val = steps * cores / total
-    sample = (f"{steps} step(s) x {cores} concurrent scenarios of the config-D workload (one per host core), first MILP "
-              f"of dynamic_eisenberg_gale_scheduling only (model build + HiGHS, mip_rel_gap=1e-3, time_limit=15 s = "
-              f"the reference's Gurobi settings); incumbents found: {sum(solved)}/{len(solved)}")
+    K, W = args.steps, args.warmup
+    ncpu = os.cpu_count() or 1
+    procs = max(1, min(K, ncpu, args.ref_procs))
+    limit = args.ref_time_limit
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        # warm-up: the same code path with the reference's own 15 s limit (imports, model build, HiGHS start-up)
+        t0 = time.perf_counter()
+        warm = pool.map(_ref_step, [(i, 15.0, False) for i in range(W)]) if W > 0 else []
+        warm_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        out = pool.map(_ref_step, [(W + i, limit, False) for i in range(K)], chunksize=1)
+        total = time.perf_counter() - t0
+    solved = sum(1 for o in out if o[0])
+    val = K / total
+    per = [round(o[2], 1) for o in out]
+    sample = (f"{K} timed steps = {K} config-D scenarios (seeds {1000 + W}..{1000 + W + K - 1}), {procs} concurrent "
+              f"single-threaded HiGHS processes (scipy.optimize.milp, mip_rel_gap=1e-3 as in the reference; time limit "
+              f"lifted from the reference's 15 s to {limit:.0f} s per MILP because 15 s yields no incumbent at this size); "
+              f"schedules produced: {solved}/{K}; fallback path taken: {sum(1 for o in out if o[1] == 1)}/{K}; "
+              f"seconds per scenario (one core each, concurrent): min {min(per)} median {float(np.median(per))} max {max(per)}; "
+              f"the re-rank MILP of the fallback path (shockwave.py:714-793) is NOT included; warm-up: {W} steps with "
+              f"the 15 s limit, {sum(1 for o in warm if o[0])}/{W} produced a schedule, {warm_s:.0f} s")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rounds/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": 0, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"4096 jobs x 512 GPUs x 64-round window (BASELINE config D), {cores} scenarios/step",
-                       "solver": "HiGHS via scipy.optimize.milp — stand-in for Gurobi (not installable here)"},
-            "cpu_baseline": {"value": val, "unit": "rounds/s", "cores": cores, "kind": "port", "sample": sample,
-                             "host_cores": os.cpu_count()},
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * total / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": CONFIG,
+            "solver": "HiGHS via scipy.optimize.milp — stand-in for Gurobi (not installable here: no package, no licence, "
+                      "no network)",
+            "incumbents": solved,
+            "cpu_baseline": {"value": val, "unit": "rounds/s", "cores": procs, "kind": "port", "sample": sample,
+                             "host_cores": ncpu},
             "e2e": {"value": val, "unit": "rounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ ours
+class _Job:      # what scheduler.py hands over (scheduler/JobMetaData.py:41-98), duck-typed
+    def __init__(self, pb, jid):
+        from collections import OrderedDict
+        E = int(pb["E"][jid])
+        self.nworkers, self.epochs, self.epoch_nsamples = int(pb["g"][jid]), E, 50000
+        dur = max(1.0, round(float(pb["dbar"][jid])))
+        self.epoch_duration_preprofiled = [dur] * E
+        self.bs_schedule = [32] * (E // 2) + [64] * (E - E // 2)
+        self.timestamp_submit, self.gavel_round_duration = 0.0, D
+        self.throughput_measurements = OrderedDict()
+        self.epoch_progress, self.waiting_delay = int(pb["c"][jid]), 0
+
+    def set_epoch_progress(self, c): self.epoch_progress = c
+    def reset_waiting_delay(self): self.waiting_delay = 0
+    def add_waiting_delay(self, d): self.waiting_delay += d
+
+
+def _ncu_traffic(kernel_substr):
+    """dram bytes per launch of a kernel from this round's committed ncu summary (profiles/ncu_kernels_r02.json,
+    written by profiles/summarize.py from the .ncu-rep of the same command); None when there is no capture."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernels_r02.json")))
+        for name, row in d.items():
+            if kernel_substr in name and row.get("dram_bytes") is not None:
+                return float(row["dram_bytes"]), row
+    except Exception:
+        pass
+    return None, None
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scenarios", type=int, default=296, help="scenarios per GPU per step (2 x 148 SMs)")
-    ap.add_argument("--mc-paths", type=int, default=8192, help="GBM sample paths per job (global, sharded over ranks)")
+    ap.add_argument("--scenarios", type=int, default=296, help="batched block: scenarios per GPU per step (2 x 148 SMs)")
+    ap.add_argument("--mc-paths", type=int, default=8192, help="GBM sample paths per job")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the batched / dense / policy legs")
+    ap.add_argument("--ref-procs", type=int, default=32, help="reference arm: concurrent HiGHS processes")
+    ap.add_argument("--ref-time-limit", type=float, default=900.0, help="reference arm: HiGHS limit per MILP (s)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from shockwave_b200 import Engine, make_params
+    from shockwave_b200 import Engine, ShockwaveScheduler, make_params
+    from shockwave_b200.forecast_mc import path_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -172,189 +227,358 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    # bind this rank's host threads to the CPUs of its GPU's NUMA node (pinned buffers are then allocated there)
+    numa = None
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * wi + b for wi, wv in enumerate(mask) for b in range(64) if (int(wv) >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            numa = f"{len(cpus)} cpus ({cpus[0]}..{cpus[-1]})"
+    except Exception:
+        pass
     eng = Engine(local)
-    S = args.scenarios
     W = max(args.warmup, 3)
     K = args.steps
-
-    arrs, rptr = synth_batch(S, seed0=rank * S)
-    prms = [make_params(G, T, D, K_SWEEP[s % len(K_SWEEP)], 12.0, 1.0, BASES, ORIGIN, round_ptr=rptr[s])
-            for s in range(S)]
-    # ---- device-resident inputs / outputs (value) ----
-    dten = {k: torch.from_numpy(v).to(dev) for k, v in arrs.items()}
-    outs = dict(x=torch.empty((S, J, T), dtype=torch.uint8, device=dev),
-                backfill=torch.empty((S, J, T), dtype=torch.uint8, device=dev),
-                nrounds=torch.empty((S, J), dtype=torch.int32, device=dev),
-                weights=torch.empty((S, J), dtype=torch.float64, device=dev))
-    ptrs = {k: v.data_ptr() for k, v in dten.items()}
-    ptrs["bfkey"] = dten["rem"].data_ptr()
-    optrs = {k: v.data_ptr() for k, v in outs.items()}
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    # Engine calls are synchronous (they end with a stream synchronize), so events recorded on torch's
-    # current stream bracket everything a step launches: our kernels on the engine stream and NCCL.
+    P_MC = args.mc_paths
     est = torch.cuda.current_stream(dev)
 
-    # ---- Monte-Carlo (GBM) forecast of the live job set: P paths/job sharded over the ranks, ONE allreduce ----
-    from shockwave_b200.forecast_mc import path_range
-    P_MC = args.mc_paths
-    rng = np.random.default_rng(12345)
-    mc_R0 = arrs["rem"][0].copy()
-    mc_H = np.minimum(arrs["E"][0] - arrs["c"][0], 256).astype(np.int32)
-    mc_mu = rng.uniform(-1e-3, 1e-3, J)
-    mc_sg = rng.uniform(0.0, 0.05, J)
-    mc_lo, mc_n = path_range(P_MC, rank, world)
+    # ---- scenarios of all steps, resident in HBM (inputs of `value`) -----------------------------------------
+    NS = W + K
+    pbs = [scenario(i, rank) for i in range(NS)]
+    st = lambda key, dt: torch.from_numpy(np.ascontiguousarray(np.stack([p[0][key] for p in pbs]).astype(dt))).to(dev)
+    dten = dict(g=st("g", np.int32), E=st("E", np.int32), c=st("c", np.int32), dbar=st("dbar", np.float64),
+                rem=st("rem", np.float64), ftobj=st("ftobj", np.float64))
+    prms = [make_params(G, T, D, p[1], 12.0, 1.0, BASES, ORIGIN, round_ptr=p[0]["round_ptr"]) for p in pbs]
+    rng = np.random.default_rng(12345 + rank)
+    mc_mu = torch.from_numpy(rng.uniform(-1e-3, 1e-3, (NS, J))).to(dev)
+    mc_sg = torch.from_numpy(rng.uniform(0.0, 0.05, (NS, J))).to(dev)
+    mc_H = torch.minimum(dten["E"] - dten["c"], torch.tensor(256, dtype=torch.int32, device=dev)).contiguous()
     mc_out = torch.zeros((2, J), dtype=torch.float64, device=dev)
+    rem_mc = torch.zeros((1, J), dtype=torch.float64, device=dev)
+    xm = torch.zeros((1, J, 2), dtype=torch.int64, device=dev)
+    bm = torch.zeros((1, J, 2), dtype=torch.int64, device=dev)
+    nr = torch.zeros((1, J), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    torch.cuda.synchronize()
+    ptr = lambda t, i: t[i].data_ptr()
+    launches = [0]
 
-    def step_resident():
-        eng.gbm_forecast(mc_R0, mc_H, mc_mu, mc_sg, mc_n, mc_lo, 7, out_device_ptr=mc_out.data_ptr())
-        if world > 1:
-            dist.all_reduce(mc_out, op=dist.ReduceOp.SUM)      # NCCL over NVLink: 2*J float64 = 64 KiB
-        return eng.solve_device(prms, J, ptrs, optrs)
+    def step_resident(i):
+        """forecast (GBM) -> its mean becomes the remaining runtime -> solve -> place; all device-resident."""
+        eng.gbm_forecast_device(J, ptr(dten["rem"], i), ptr(mc_H, i), ptr(mc_mu, i), ptr(mc_sg, i), P_MC, 0, 7 + i,
+                                mc_out.data_ptr())
+        eng.gbm_ensemble(1, J, P_MC, mc_out.data_ptr(), [0.0], rem_mc.data_ptr())
+        res = eng.solve_device([prms[i]], J,
+                               dict(g=ptr(dten["g"], i), E=ptr(dten["E"], i), c=ptr(dten["c"], i),
+                                    dbar=ptr(dten["dbar"], i), rem=rem_mc.data_ptr(), ftobj=ptr(dten["ftobj"], i),
+                                    bfkey=rem_mc.data_ptr()),
+                               dict(xmask=xm.data_ptr(), bfmask=bm.data_ptr(), nrounds=nr.data_ptr()),
+                               per_scenario_jobs=False)
+        tm = eng.last_timings()
+        launches[0] += 2 + 2 * tm["passes"]
+        return res[0], tm
 
     sampler = ClockSampler(local)
     sampler.start()
-    for _ in range(W):
-        step_resident()
+    for i in range(W):
+        step_resident(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     sampler.t0 = time.perf_counter()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    ksolve, kplace, launches = [], [], 0
+    ksolve, kplace, nfb, shortf = [], [], 0, 0
+    launches[0] = 0
     torch.cuda.synchronize()
     for i in range(K):
         flush.fill_(i)                          # L2 flush between timed iterations (not timed)
         torch.cuda.synchronize()
         ev[i][0].record(est)
-        res = step_resident()
+        res, tm = step_resident(W + i)          # engine calls end with a stream synchronize: the events bracket them
         ev[i][1].record(est)
-        tm = eng.last_timings()
         ksolve.append(tm["ms_solve"]); kplace.append(tm["ms_place"])
-        launches += 1 + 2 * tm["passes"] + (tm["passes"] - 1)       # gbm + (solve, place) per pass + tighten
+        nfb += int(res["status"] == 1); shortf += int(res["shortfall"])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler.t1 = time.perf_counter()
-    sampler.stop_flag = True
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms = float(tt.item())
-    value = world * S * K / (total_ms * 1e-3)
-    nfallback = sum(1 for r in res if r["status"] == 1)
-
-    # ---- single re-solve latency (S = 1, resident) ----
-    one = [prms[1]]
-    p1 = {k: v[1:2].contiguous().data_ptr() for k, v in dten.items()}
-    p1["bfkey"] = p1["rem"]
-    lat = []
-    for i in range(W + 5):
-        t0 = time.perf_counter()
-        eng.solve_device(one, J, p1, optrs)
-        lat.append((time.perf_counter() - t0) * 1e3)
-    lat_ms = float(np.median(lat[W:]))
-    lat_k = eng.last_timings()
-
-    # ---- e2e through the public host API, pinned host buffers, copies inside the timed region ----
-    hin = {k: torch.from_numpy(v).pin_memory() for k, v in arrs.items()}
-    hnp = {k: v.numpy() for k, v in hin.items()}
-    hout = {"xmask": torch.empty((S, J, 2), dtype=torch.uint64).pin_memory().numpy(),
-            "bfmask": torch.empty((S, J, 2), dtype=torch.uint64).pin_memory().numpy(),
-            "nrounds": torch.empty((S, J), dtype=torch.int32).pin_memory().numpy(),
-            "weights": torch.empty((S, J), dtype=torch.float64).pin_memory().numpy()}
-    # two engines (two CUDA streams, two sets of device + pinned buffers) driven by two host threads: step i+1's
-    # host->device copies overlap step i's kernels and device->host copies.  Every copy of every step stays inside
-    # the timed region; ctypes releases the GIL during the library calls.
-    from concurrent.futures import ThreadPoolExecutor
-    eng_b = Engine(local)
-    hout_b = {k: torch.from_numpy(np.empty_like(v)).pin_memory().numpy() for k, v in hout.items()}
-    lanes = [(eng, hout, ThreadPoolExecutor(1)), (eng_b, hout_b, ThreadPoolExecutor(1))]
-
-    def e2e_step(i):
-        e, ho, _ = lanes[i % 2]
-        sums_ = e.gbm_forecast(mc_R0, mc_H, mc_mu, mc_sg, mc_n, mc_lo, 7)
-        e.solve(prms, hnp["g"], hnp["E"], hnp["c"], hnp["dbar"], hnp["rem"], hnp["ftobj"], packed=True, out=ho)
-        return sums_
-
-    for f in [lanes[i % 2][2].submit(e2e_step, i) for i in range(6)]:
-        f.result()
-    # the same K steps one after the other on one engine, for reference (reported in config)
-    t0 = time.perf_counter()
-    for i in range(K):
-        e2e_step(0)
-    e2e_serial_s = time.perf_counter() - t0
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    futs = [lanes[i % 2][2].submit(e2e_step, i) for i in range(K)]
-    for f in futs:
-        sums = f.result()
-        if world > 1:       # collectives stay on the main thread, in step order on every rank
-            tsum = torch.from_numpy(sums).to(dev)
-            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            sums = tsum.cpu().numpy()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * S * K / float(te.item())
-    for _, _, ex_ in lanes:
-        ex_.shutdown()
-    del eng_b
-    h2d = S * J * (3 * 4 + 4 * 8) + S * 256 + J * (3 * 8 + 4)
-    d2h = S * J * 16 * 2 + S * J * (4 + 8) + S * 56 + 2 * J * 8      # round masks (128 bit/job) x2, counts, weights
-    # MC kernel alone (device time)
-    eng.gbm_forecast(mc_R0, mc_H, mc_mu, mc_sg, mc_n, mc_lo, 7, out_device_ptr=mc_out.data_ptr())
+    value = world * K / (total_ms * 1e-3)
+    gpu_launches = launches[0]
+    # GBM kernel alone (device time of the library's own events)
+    eng.gbm_forecast_device(J, ptr(dten["rem"], 0), ptr(mc_H, 0), ptr(mc_mu, 0), ptr(mc_sg, 0), P_MC, 0, 7,
+                            mc_out.data_ptr())
     mc_ms = eng.last_timings()["ms_solve"]
 
-    # ---- the drop-in class itself: ShockwaveScheduler.round_schedule() with a forced re-solve (S = 1) ----
+    # ---- e2e: the drop-in class, forced re-solve per step, host buffers, copies inside -------------------------
     from collections import OrderedDict
-    from shockwave_b200 import ShockwaveScheduler
-
-    class _Job:                      # what scheduler.py hands over (scheduler/JobMetaData.py:41-98), duck-typed
-        def __init__(self, jid, r):
-            E = int(arrs["E"][0][jid])
-            self.jobid, self.nworkers, self.epochs, self.epoch_nsamples = jid, int(arrs["g"][0][jid]), E, 50000
-            dur = max(1.0, round(float(arrs["dbar"][0][jid])))
-            self.epoch_duration_preprofiled = [dur] * E
-            self.bs_schedule = [32] * (E // 2) + [64] * (E - E // 2)
-            self.timestamp_submit, self.gavel_round_duration = 0.0, D
-            self.throughput_measurements = OrderedDict()
-            self.epoch_progress, self.waiting_delay = int(arrs["c"][0][jid]), 0
-        def set_epoch_progress(self, c): self.epoch_progress = c
-        def reset_waiting_delay(self): self.waiting_delay = 0
-        def add_waiting_delay(self, d): self.waiting_delay += d
-
+    pb0 = pbs[0][0]
     sw = ShockwaveScheduler(ngpus=G, gram=16, init_metadata=OrderedDict(), future_nrounds=T, round_duration=int(D),
                             solver_preference=["GUROBI"], solver_rel_gap=1e-3, solver_num_threads=24, solver_timeout=15,
                             n_epoch_vars_max=64, logapx_bases=BASES, logapx_origin=ORIGIN, k=1e-3, lam=12.0, rhomax=1.0,
-                            device=local)
+                            device=local, forecast="gbm", gbm_paths=P_MC, gbm_seed=7,
+                            gbm_volatility=lambda jid, job: (float((jid % 21 - 10) * 1e-4), float((jid % 11) * 5e-3)))
     for jid in range(J):
-        sw.add_metadata(jid, _Job(jid, None))
-    rs_ms = []
-    for i in range(W + 5):
-        sw.round_ptr = 10 + i
-        sw.set_resolve()
-        t0 = time.perf_counter()
-        sw.round_schedule()
-        rs_ms.append((time.perf_counter() - t0) * 1e3)
-    rs_ms = float(np.median(rs_ms[W:]))
-    del sw
+        sw.add_metadata(jid, _Job(pb0, jid))
+    sw.round_ptr = int(pb0["round_ptr"])
 
-    # ---- dense PR-dynamics pass over X[S][J][W][T]: S*J*W*T*4 B = 512 MiB > L2 ----
+    def e2e_step():
+        ids = sw.round_schedule()               # forced re-solve (resolve flag set below)
+        for jid in ids[:G]:                     # what the round loop reports back (scheduler.py:2274-2341)
+            job = sw.metadata[jid]
+            sw.schedule_progress(jid, min(job.epochs, job.epoch_progress + (1 if jid % 3 == 0 else 0)))
+        sw.increment_round_ptr()
+        sw.set_resolve()
+        return len(ids)
+
+    for _ in range(W):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    sampler.t1 = None
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    sampler.t1 = time.perf_counter()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * K / float(te.item())
+    rs_kern = eng_t = sw._eng().last_timings()
+    h2d = J * (4 + 4 + 8 + 4) + 256                      # slots, epoch_progress, measured samples, last round; params
+    d2h = J * (16 * 2 + 4 + 6 * 8) + 64                  # two 128-bit masks/job, counts, six forecast planes; scalars
+    # the same call without the Monte-Carlo stage, and its host part alone
+    sw_det = ShockwaveScheduler(ngpus=G, gram=16, init_metadata=OrderedDict(), future_nrounds=T, round_duration=int(D),
+                                solver_preference=["GUROBI"], solver_rel_gap=1e-3, solver_num_threads=24,
+                                solver_timeout=15, n_epoch_vars_max=64, logapx_bases=BASES, logapx_origin=ORIGIN,
+                                k=1e-3, lam=12.0, rhomax=1.0, device=local)
+    for jid in range(J):
+        sw_det.add_metadata(jid, _Job(pb0, jid))
+    det_ms = []
+    for i in range(W + 8):
+        sw_det.round_ptr = int(pb0["round_ptr"]) + i
+        sw_det.set_resolve()
+        t0 = time.perf_counter()
+        sw_det.round_schedule()
+        det_ms.append((time.perf_counter() - t0) * 1e3)
+    det_ms = float(np.median(det_ms[W:]))
+    det_kern = sw_det._eng().last_timings()
+    sampler.stop_flag = True
+    del sw, sw_det
+
+    extras = {}
+    if not args.no_extras:
+        extras = run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    clocks = sampler.summary()
+    ms_solve, ms_place = float(np.mean(ksolve)), float(np.mean(kplace))
+    step_ms = total_ms / K
+    line = {
+        "metric": METRIC, "value": value, "unit": "rounds/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 (job scalars, objective, forecast sums); price thresholds compared in fp32; GBM paths in fp32",
+        "data": "synthetic", "config": CONFIG,
+        "timing": {"l2": "flushed between timed steps (256 MiB write)", "events": "CUDA events on the launching "
+                   "stream around every step (library calls are synchronous), summed, max over ranks",
+                   "numa_binding": numa},
+        "clocks": clocks,
+        "gpu_launches": gpu_launches,
+        "step": {"fallback_steps": nfb, "unseated_job_rounds": shortf, "mc_paths_per_job": P_MC,
+                 "kernels_ms": {"gbm_kernel": mc_ms, "solve_kernel": ms_solve, "place_kernel": ms_place},
+                 "kernel_share_of_step": {"gbm_kernel": mc_ms / step_ms, "solve_kernel": ms_solve / step_ms,
+                                          "place_kernel": ms_place / step_ms},
+                 "bounds": {"gbm_kernel": "ALU/SFU (xorshift128+, Box-Muller, exp per path step)",
+                            "solve_kernel": "instruction issue + barrier latency (8-CTA cluster, DSMEM reductions)",
+                            "place_kernel": "latency (sorts, scans and the round packer in shared memory, one CTA)"}},
+        "e2e": {"value": e2e_val, "unit": "rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "what": "ShockwaveScheduler(forecast='gbm').round_schedule() with a forced re-solve per step, "
+                        f"4096 live jobs, {G} schedule_progress() calls between steps (timed too)",
+                "ms_per_call": 1e3 * float(te.item()) / K,
+                "without_monte_carlo_ms_per_call": det_ms,
+                "kernels_ms_without_monte_carlo": det_kern},
+    }
+    line.update(extras)
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample():
+    """Bounded CPU sample (10-30 s): a full config-D MILP needs minutes of HiGHS (see --impl reference, which times it
+    on the same seeds), so the sample is the largest BASELINE size the oracle finishes inside the budget — config C
+    (1024 jobs x 128 GPUs x 32 rounds) — solved by the oracle with the reference's settings AND by the GPU path."""
+    from oracle import shockwave_milp as om
+    from shockwave_b200 import Engine, make_params
+    from tests.synth import synth_problem
+    logv = om.pwl_log_values(BASES, ORIGIN)
+    Jc, Gc, Tc = 1024, 128, 32
+    times, oks, gaps = [], 0, []
+    eng = Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    gpu_ms = []
+    for s in range(3):
+        pb = synth_problem(Jc, Gc, Tc, D, seed=900 + s, tight=3.0)
+        t0 = time.perf_counter()
+        out = None
+        try:
+            out = om.dynamic_eisenberg_gale(pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"], Gc, Tc, D,
+                                            pb["round_ptr"], 1e-3, 12.0, 1.0, BASES, logv, rel_gap=1e-3,
+                                            time_limit=15.0, do_rank=False)
+            om.construct_schedules(out["x"], list(range(Jc)), pb["g"], pb["rem"], pb["round_ptr"], Gc)
+            oks += 1
+        except AssertionError:
+            pass
+        times.append(time.perf_counter() - t0)
+        prm = make_params(Gc, Tc, D, 1e-3, 12.0, 1.0, BASES, ORIGIN, round_ptr=pb["round_ptr"])
+        for _ in range(3):
+            t0 = time.perf_counter()
+            o = eng.solve(prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], pb["ftobj"], packed=True)
+            g_ms = (time.perf_counter() - t0) * 1e3
+        gpu_ms.append(g_ms)
+        if out is not None:
+            gaps.append((o["results"][0]["objective"] - out["objective"]) / abs(out["objective"]))
+    val = len(times) / sum(times)
+    return {"value": val, "unit": "rounds/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+            "workload": "BASELINE config C: 1024 jobs x 128 GPUs x 32-round window (NOT the headline size)",
+            "gpu_same_instances_rounds_per_s": 1e3 / float(np.mean(gpu_ms)),
+            "gpu_over_cpu_same_instances": (1e3 / float(np.mean(gpu_ms))) / val,
+            "gpu_objective_minus_cpu_objective_rel": gaps,
+            "sample": (f"3 config-C scenarios (seeds 900-902) through oracle/shockwave_milp.py (HiGHS, mip_rel_gap=1e-3, "
+                       f"time_limit=15 s = the reference's settings) + construct_schedules, one core: {[round(t, 2) for t in times]} s, "
+                       f"incumbents {oks}/3; the same three instances through Engine.solve with host buffers: "
+                       f"{[round(m, 3) for m in gpu_ms]} ms; the headline size (config D) needs minutes per scenario on "
+                       "one core — timed on the same seeds by `bench.py --impl reference`")}
+
+
+def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):
+    """Legs that explain the headline: batched scenario sweep (+ path-sharded GBM with one all-reduce), the dense
+    PR-dynamics pass (HBM roofline kernel), single re-solve latency, Gavel get_allocation() latency."""
+    import torch
+    from shockwave_b200 import make_params
+    from shockwave_b200.forecast_mc import path_range
+    out = {}
+    S, P_MC = args.scenarios, args.mc_paths
+    pb0 = pbs[0][0]
+    # ---- batched: S what-if scenarios of ONE job set per step ------------------------------------------------
+    rep = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.broadcast_to(a.astype(dt), (S, J)))).to(dev)
+    bt = dict(g=rep(pb0["g"], np.int32), E=rep(pb0["E"], np.int32), c=rep(pb0["c"], np.int32),
+              dbar=rep(pb0["dbar"], np.float64), ftobj=rep(pb0["ftobj"], np.float64))
+    RH = [1.0, 1.5, 3.0, 10.0]
+    zq = np.linspace(-1.5, 1.5, S)
+    bprm = [make_params(G, T, D, K_SWEEP[s % 3], 12.0, RH[(s // 3) % 4], BASES, ORIGIN, round_ptr=pb0["round_ptr"])
+            for s in range(S)]
+    rem_s = torch.zeros((S, J), dtype=torch.float64, device=dev)
+    R0 = torch.from_numpy(pb0["rem"]).to(dev)
+    Hh = torch.from_numpy(np.minimum(pb0["E"] - pb0["c"], 256).astype(np.int32)).to(dev)
+    rng = np.random.default_rng(99)
+    mu = torch.from_numpy(rng.uniform(-1e-3, 1e-3, J)).to(dev)
+    sg = torch.from_numpy(rng.uniform(0.0, 0.05, J)).to(dev)
+    sums = torch.zeros((2, J), dtype=torch.float64, device=dev)
+    bxm = torch.zeros((S, J, 2), dtype=torch.int64, device=dev)
+    bbm = torch.zeros((S, J, 2), dtype=torch.int64, device=dev)
+    lo, nloc = path_range(P_MC, rank, world)
+    bptrs = {k: v.data_ptr() for k, v in bt.items()}
+    bptrs["rem"] = rem_s.data_ptr(); bptrs["bfkey"] = rem_s.data_ptr()
+
+    def bstep():
+        eng.gbm_forecast_device(J, R0.data_ptr(), Hh.data_ptr(), mu.data_ptr(), sg.data_ptr(), nloc, lo, 11,
+                                sums.data_ptr())
+        if world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)        # NCCL over NVLink: [2][J] float64 = 64 KiB
+            torch.cuda.current_stream(dev).synchronize()
+        eng.gbm_ensemble(S, J, P_MC, sums.data_ptr(), zq, rem_s.data_ptr())
+        return eng.solve_device(bprm, J, bptrs, dict(xmask=bxm.data_ptr(), bfmask=bbm.data_ptr()))
+
+    for _ in range(3):
+        res = bstep()
+    if world > 1:
+        # N > 1 correctness of the sharded forecast, checked by every driver run: the all-reduced sums must equal a
+        # rank-0 recompute of ALL paths (path streams are keyed by the global path id)
+        full = torch.zeros((2, J), dtype=torch.float64, device=dev)
+        eng.gbm_forecast_device(J, R0.data_ptr(), Hh.data_ptr(), mu.data_ptr(), sg.data_ptr(), P_MC, 0, 11,
+                                full.data_ptr())
+        rel = float(((sums - full).abs() / full.abs().clamp_min(1e-300)).max().item())
+        assert rel < 1e-9, f"sharded GBM forecast differs from the single-GPU recompute: {rel}"
+        out["mc_shard_check_rel"] = rel
+    KB = 5
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KB)]
+    ks, kp = [], []
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    for i in range(KB):
+        flush.fill_(i)
+        torch.cuda.synchronize()
+        ev[i][0].record(est)
+        res = bstep()
+        ev[i][1].record(est)
+        tm = eng.last_timings()
+        ks.append(tm["ms_solve"]); kp.append(tm["ms_place"])
+    torch.cuda.synchronize()
+    bms = sum(a.elapsed_time(b) for a, b in ev)
+    tb = torch.tensor([bms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    bms = float(tb.item())
+    out["batched"] = {"value": world * S * KB / (bms * 1e-3), "unit": "rounds/s", "scenarios_per_gpu_per_step": S,
+                      "steps": KB, "ms_per_step": bms / KB,
+                      "what": "GBM forecast of one job set (paths sharded over the ranks, one NCCL all-reduce of 64 KiB) "
+                              "-> S scenarios = k x rhomax x forecast quantile (z in [-1.5, 1.5]) -> solve + placement, "
+                              "one CTA per scenario, packed round masks out; inputs resident",
+                      "fallback_scenarios": sum(1 for r in res if r["status"] == 1),
+                      "kernels_ms": {"solve_kernel": float(np.mean(ks)), "place_kernel": float(np.mean(kp))},
+                      "mc_paths_this_rank": nloc}
+    del bt, rem_s, bxm, bbm
+    if rank != 0:
+        return out
+
+    # ---- single re-solve latency (S = 1, resident, no Monte-Carlo) -------------------------------------------
+    dt1 = {k: torch.from_numpy(np.ascontiguousarray(pb0[k].astype(dtp))).to(dev)
+           for k, dtp in (("g", np.int32), ("E", np.int32), ("c", np.int32), ("dbar", np.float64),
+                          ("rem", np.float64), ("ftobj", np.float64))}
+    xm1 = torch.zeros((1, J, 2), dtype=torch.int64, device=dev)
+    bm1 = torch.zeros((1, J, 2), dtype=torch.int64, device=dev)
+    lat = {}
+    for name, cl in (("cluster8", 8), ("one_cta", 1)):
+        eng.set_option(2, cl)
+        ws = []
+        for i in range(W + 8):
+            t0 = time.perf_counter()
+            eng.solve_device([make_params(G, T, D, 1e-3, 12.0, 1.0, BASES, ORIGIN, round_ptr=pb0["round_ptr"])], J,
+                             {k: v.data_ptr() for k, v in dt1.items()}, dict(xmask=xm1.data_ptr(), bfmask=bm1.data_ptr()),
+                             per_scenario_jobs=False)
+            ws.append((time.perf_counter() - t0) * 1e3)
+        lat[name] = {"wall_ms": float(np.median(ws[W:])), **eng.last_timings()}
+    eng.set_option(2, 8)
+    out["latency_S1"] = lat
+
+    # ---- dense PR-dynamics pass over X[S][J][W][T] (SURVEY.md §8d): S*J*W*T*4 B = 512 MiB > L2 ------------------
     from shockwave_b200.engine import market_pgd
     Sd, Wd = 512, 1
     Xd = torch.zeros((Sd, J, Wd, T), dtype=torch.float32, device=dev)
-    dj = {k: torch.from_numpy(np.ascontiguousarray(arrs[k][0]).astype(np.float64 if k != "g" else np.int32)).to(dev)
+    dj = {k: torch.from_numpy(np.ascontiguousarray(pb0[k]).astype(np.float64 if k != "g" else np.int32)).to(dev)
           for k in ("g", "E", "c", "dbar", "rem")}
-    drate = torch.from_numpy((D / arrs["dbar"][0])[:, None].astype(np.float32)).to(dev)
+    drate = torch.from_numpy((D / pb0["dbar"])[:, None].astype(np.float32)).to(dev)
     mptr = dict(shape=(Sd, J, Wd, T), per_scenario_jobs=0, g=dj["g"].data_ptr(), E=dj["E"].data_ptr(),
                 c=dj["c"].data_ptr(), dbar=dj["dbar"].data_ptr(), rem=dj["rem"].data_ptr(), rate=drate.data_ptr(),
                 X=Xd.data_ptr())
     mprm = [make_params(G, T, D, 1e-9, 12.0, 1.0, BASES, ORIGIN) for _ in range(Sd)]
     dense_ms = []
-    for i in range(W + K):
+    for i in range(W + 5):
         _, ms = market_pgd(eng, mprm, None, None, None, None, None, None, [G], None, 8, 0.1, 0.3, float(J * T),
                            device_ptrs=mptr, eta_decay=50.0)
         if i >= W:
@@ -362,125 +586,52 @@ def main():
     dense_ms = float(np.mean(dense_ms))
     dense_bytes = 8.0 * Sd * J * Wd * T + Sd * (24.0 * J + 8.0 * Wd * T)
     del Xd
-
-    # ---- config E (J=2048 policy sweep): Gavel get_allocation() latency, W=1 (pooled) and W=3 (heterogeneous) ----
-    pol_ms = {}
-    if rank == 0:
-        from shockwave_b200 import policies as GP
-        GP._shared_engine = eng
-        rngp = np.random.default_rng(7)
-        JE = 2048
-        mE = rngp.uniform(0.5, 20.0, size=(JE, 1)) * np.sort(rngp.uniform(0.1, 1.0, size=(JE, 3)), axis=1)
-        wts = ["k80", "p100", "v100"]
-        thr3 = {j: {w: float(mE[j, i]) for i, w in enumerate(wts)} for j in range(JE)}
-        thr1 = {j: {w: float(mE[j, 2]) for w in wts} for j in range(JE)}
-        sfE = {j: int(rngp.choice([1, 2, 4, 8], p=[0.6, 0.3, 0.09, 0.01])) for j in range(JE)}
-        prE = {j: 1.0 for j in range(JE)}
-        stE = {j: float(rngp.uniform(1e4, 1e6)) for j in range(JE)}
-        tE = {j: float(rngp.uniform(0, 5e3)) for j in range(JE)}
-        for tag, thr_, spec_ in (("W1", thr1, {"k80": 0, "p100": 0, "v100": 512}),
-                                 ("W3", thr3, {"k80": 256, "p100": 128, "v100": 128})):
-            for name, call in (
-                    ("max_min_fairness_perf", lambda: GP.MaxMinFairnessPolicyWithPerf("ECOS").get_allocation(thr_, sfE, prE, spec_)),
-                    ("finish_time_fairness_perf", lambda: GP.FinishTimeFairnessPolicyWithPerf("GUROBI").get_allocation(
-                        thr_, sfE, prE, tE, stE, spec_))):
-                call()
-                t0 = time.perf_counter()
-                for _ in range(3):
-                    call()
-                pol_ms[f"{name}_{tag}"] = (time.perf_counter() - t0) / 3 * 1e3
-
-    if rank != 0:
-        return
-    clocks = sampler.summary()
-    # ---- roofline of the dominant kernel (solve_kernel): algorithmic bytes per launch ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    ms_solve, ms_place = float(np.mean(ksolve)), float(np.mean(kplace))
-    # algorithmic bytes per launch: inputs + outputs each kernel must touch once
-    kern = {
-        "solve_kernel": (ms_solve, S * J * (3 * 4 + 3 * 8) + S * J * (1 + 8)),
-        "place_kernel": (ms_place, S * J * (1 + 8 + 8) + S * J * T * 2 + S * J * 4),
-        "gbm_kernel": (mc_ms, J * (3 * 8 + 4) + 2 * J * 8),
-    }
-    dom = max(kern, key=lambda k: kern[k][0])
-    dom_ms, dom_bytes = kern[dom]
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    bound_note = {
-        "solve_kernel": "price/makespan search on per-job scalars staged in shared memory: instruction-issue bound "
-                        "(79 % issue-active in profiles/), not HBM bound",
-        "place_kernel": "sorts + water-filling over 64 rounds in shared memory: latency bound, not HBM bound",
-        "gbm_kernel": "Monte-Carlo paths (xorshift128+, Box-Muller, exp): ALU/SFU bound (86 % issue-active in profiles/), "
-                      "28 bytes in / 16 bytes out per job — the HBM fraction is reported only because the contract asks for it",
-    }[dom]
-    line = {
-        "metric": METRIC, "value": value, "unit": "rounds/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE config D: 4096 jobs x 512 GPUs x 64-round window",
-                   "scenarios_per_gpu_per_step": S, "k_sweep": K_SWEEP, "fallback_scenarios": nfallback,
-                   "latency_ms_S1": lat_ms, "latency_kernels_ms_S1": lat_k,
-                   "gavel_get_allocation_ms_J2048": pol_ms,   # config E: dict in -> dict out, host packing included
-                   "round_schedule_ms": rs_ms,   # ShockwaveScheduler.round_schedule(): host packing + forecast + solve + lists
-                   "mc_forecast": {"paths_per_job": P_MC, "paths_this_rank": mc_n, "horizon_epochs": "min(E-c, 256)",
-                                   "kernel_ms": mc_ms, "allreduce": "NCCL SUM of [2][J] float64 (64 KiB)" if world > 1 else "none (1 GPU)"},
-                   "e2e_pipeline": "2 engines x 2 host threads (double buffering): the copies of step i+1 overlap the kernels "
-                                   "of step i; all host<->device copies of all steps inside the timed region; the same "
-                                   f"steps one after the other on one engine: {S * K / e2e_serial_s:.0f} rounds/s on this rank",
-                   "l2": "flushed between timed steps (256 MiB write); per-step CUDA events on the launching stream, summed",
-                   "parallelism": f"scenario-sharded x{world}, no data-path collective",
-                   "scaling_note": "scenarios per GPU are fixed (weak scaling); the 8192 Monte-Carlo paths per job are a fixed "
-                                   "TOTAL sharded over the ranks (BASELINE config D), so the forecast's share of the step "
-                                   "shrinks with N and value can grow faster than N"},
-        "clocks": clocks,
-        "gpu_launches": launches,
-        "kernels_ms": {"solve_kernel": ms_solve, "place_kernel": ms_place, "gbm_kernel": mc_ms},
-        "e2e": {"value": e2e_val, "unit": "rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        # the bounding roofline of this path is HBM bandwidth of the dense PR-dynamics kernel in its
-        # scenario-batched form; the Monte-Carlo / search kernels of the timed step are ALU- and issue-bound and are
-        # listed with those bounds in step_kernels (never against HBM).
-        "roofline": {
-            "bound": "hbm", "kernel": "market_step_kernel<1,4> (dense PR-dynamics pass over X[S][J][W][T], fp32)",
-            "achieved": dense_bytes / (dense_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": dense_bytes / (dense_ms * 1e-3) / 1e9 / peak,
-            "traffic": 1031965952,      # dram__bytes_read+write per launch, profiles/ncu_summary_r01.txt (ncu --set full)
-            "algorithmic_bytes_per_launch": dense_bytes, "shape": [Sd, J, Wd, T], "ms_per_launch": dense_ms,
-            "note": "kernel designated by SURVEY.md §8(d); algorithmic bytes = 8*S*J*W*T + S*(24*J + 8*W*T); tensor "
-                    "(512 MiB) larger than L2; timed live in this run with CUDA events on the launching stream around "
-                    "each pass of an 8-iteration run, in its own leg (the collapsed Shockwave solve of the timed step "
-                    "never materialises X, DESIGN.md §2); peak = MEASURED_PEAKS.json hbm_gbs"
-                    + ("" if peaks else " (fallback 6650)")},
-        "step_kernels": [
-            {"kernel": "gbm_kernel", "ms": mc_ms, "bound": "alu/sfu",
-             "evidence": "86 % issue-active, 75 % SM throughput (profiles/ncu_summary_r01.txt); 28 B in / 16 B out per job"},
-            {"kernel": "solve_kernel", "ms": ms_solve, "bound": "instruction issue",
-             "evidence": "77 % issue-active, 59 % SM throughput; per-job scalars staged once in shared memory, 76 MB DRAM per launch"},
-            {"kernel": "place_kernel", "ms": ms_place, "bound": "latency (sorts, scans and a sequential packer in shared memory)",
-             "evidence": "44 % issue-active, 202 MB DRAM per launch (145 MB of it the J x T byte matrices it writes)"}],
-        "step_dominant_kernel": {"kernel": dom, "hbm_gbs": achieved, "note": bound_note},
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import shockwave_milp as om
-        from tests.synth import synth_problem
-        logv = om.pwl_log_values(BASES, ORIGIN)
-        pb = synth_problem(J, G, T, D, seed=1000, tight=3.0)
-        t0 = time.perf_counter()
-        cap = om.ftf_caps(pb["rem"], pb["ftobj"], G, J, T, D, pb["round_ptr"], 1.0)
-        ok, _, _, _ = om._solve(pb["g"].astype(np.int64), pb["E"].astype(float), pb["c"].astype(float), pb["dbar"],
-                                pb["rem"], np.ones(J), G, T, D, 1e-3, BASES, logv, cap, 1e-3, 15.0)
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {
-            "value": 1.0 / dt, "unit": "rounds/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
-            "sample": ("1 scenario of the same workload: first MILP of dynamic_eisenberg_gale_scheduling (model build + "
-                       f"HiGHS, mip_rel_gap=1e-3, time_limit=15 s = the reference's Gurobi settings); took {dt:.1f} s, "
-                       f"incumbent found: {bool(ok)}; HiGHS stand-in for Gurobi (not installable: no package/licence/network)")}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    traffic, trow = _ncu_traffic("market_step_kernel")
+    out["roofline"] = {
+        "bound": "hbm", "kernel": "market_step_kernel<1,4> (dense PR-dynamics pass over X[S][J][W][T], fp32)",
+        "achieved": dense_bytes / (dense_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": dense_bytes / (dense_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+        "traffic_source": "profiles/ncu_kernels_r02.json (ncu --set full of this command)" if traffic else None,
+        "algorithmic_bytes_per_launch": dense_bytes, "shape": [Sd, J, Wd, T], "ms_per_launch": dense_ms,
+        "note": "the kernel SURVEY.md §8(d) designates for the HBM roofline; algorithmic bytes = 8*S*J*W*T + "
+                "S*(24*J + 8*W*T); tensor (512 MiB) larger than L2; timed live with CUDA events on the launching stream "
+                "around each dense pass of an 8-iteration run, in its own leg: the kernels of the timed step (`step`) are "
+                "ALU- and latency-bound, never HBM-bound, and are listed with those bounds; peak = MEASURED_PEAKS.json "
+                "hbm_gbs" + ("" if peaks else " (fallback 6650)")}
+
+    # ---- config E (J=2048 policy sweep): Gavel get_allocation() latency, W=1 (pooled) and W=3 (heterogeneous) ----
+    from shockwave_b200 import policies as GP
+    GP._shared_engine = eng
+    rngp = np.random.default_rng(7)
+    JE = 2048
+    mE = rngp.uniform(0.5, 20.0, size=(JE, 1)) * np.sort(rngp.uniform(0.1, 1.0, size=(JE, 3)), axis=1)
+    wts = ["k80", "p100", "v100"]
+    thr3 = {j: {w: float(mE[j, i]) for i, w in enumerate(wts)} for j in range(JE)}
+    thr1 = {j: {w: float(mE[j, 2]) for w in wts} for j in range(JE)}
+    sfE = {j: int(rngp.choice([1, 2, 4, 8], p=[0.6, 0.3, 0.09, 0.01])) for j in range(JE)}
+    prE = {j: 1.0 for j in range(JE)}
+    stE = {j: float(rngp.uniform(1e4, 1e6)) for j in range(JE)}
+    tE = {j: float(rngp.uniform(0, 5e3)) for j in range(JE)}
+    pol_ms = {}
+    for tag, thr_, spec_ in (("W1", thr1, {"k80": 0, "p100": 0, "v100": 512}),
+                             ("W3", thr3, {"k80": 256, "p100": 128, "v100": 128})):
+        for name, call in (
+                ("max_min_fairness_perf", lambda: GP.MaxMinFairnessPolicyWithPerf("ECOS").get_allocation(thr_, sfE, prE, spec_)),
+                ("finish_time_fairness_perf", lambda: GP.FinishTimeFairnessPolicyWithPerf("GUROBI").get_allocation(
+                    thr_, sfE, prE, tE, stE, spec_))):
+            call()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                call()
+            pol_ms[f"{name}_{tag}"] = (time.perf_counter() - t0) / 3 * 1e3
+    out["gavel_get_allocation_ms_J2048"] = pol_ms
+    return out
 
 
 if __name__ == "__main__":

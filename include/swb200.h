@@ -91,6 +91,11 @@ int swb_sync(swb_ctx *ctx);
  * value (gbm.cu); jobs with mu = sigma = 0 keep the deterministic value bit for bit, so P > 0 with all-zero models
  * reproduces the reference's forecast exactly.  0 (default) = off.  SWB_OPT_GBM_SEED: stream seed;
  * SWB_OPT_GBM_HORIZON: horizon cap in epochs (default 256). */
+/* SWB_OPT_RERANK_ITERS: budget (cancelled cycles per scenario) of the local search that follows the priority round-sweep
+ * of the fallback re-rank (rank_in_schedule_jobs, shockwave.py:714-793); 0 = sweep only.  Default 400.  The search runs
+ * when jobs x rounds^2 <= 4 Mi (e.g. 10 000 jobs at 20 rounds, 1024 jobs at 64 rounds); swb_result.flags >> 8 = cycles
+ * cancelled. */
+#define SWB_OPT_RERANK_ITERS 6
 #define SWB_OPT_GBM_PATHS 3
 #define SWB_OPT_GBM_SEED 4
 #define SWB_OPT_GBM_HORIZON 5
@@ -226,6 +231,41 @@ int swb_policy_hetero(swb_ctx *ctx, int32_t mode, int32_t J, int32_t W, const do
  * path, float64), like the reference's solver; optimal assignments are not unique. */
 int swb_allox_assign(swb_ctx *ctx, int32_t m, int32_t n, int32_t W, const double *p, const double *t,
                      const int32_t *wtype, int32_t *col_of_job, double *total_cost);
+
+/* ---- Gavel's per-round priority -> selection -> worker assignment ------------------------------------ *
+ * Replaces, for single (unpacked) jobs, the step that follows get_allocation() in the reference's round loop:
+ *   Scheduler._update_priorities, the "Compute priorities" half      scheduler/scheduler.py:3669-3724
+ *   Scheduler._schedule_jobs_on_workers_helper, vanilla-Gavel branch scheduler/scheduler.py:1166-1258
+ *   Scheduler._schedule_jobs_on_workers + _assign_workers_to_job     scheduler/scheduler.py:1306-1378, :1049-1110
+ * Jobs are indexed in the iteration order of the reference's dicts (ties in its stable sorts resolve in that order).
+ * Worker types: `W` types; per-(job, type) matrices are [J][W] indexed by the caller's type index; type_order lists
+ * the type indices in PROCESSING order (the reference's possibly shuffled `worker_types`); nworkers / worker_ids are
+ * given in that processing order (worker ids of a type in server order, servers concatenated).
+ *   alloc      allocation[job][type], NaN when the job is not in the allocation (priority 0, not assigned)
+ *   job_time   _job_time_so_far[job][type] (0 when absent); worker_time _worker_time_so_far[type]
+ *   thr        throughput of the job on the type (only its sign / zero-ness is used)
+ *   deficit    _deficits[type][job];  sf scale factors;  capacity cluster_spec[type]
+ *   prev_type  type index of the job's assignment in the previous round (-1: none); prev_off [J+1] / prev_local: that
+ *              assignment's workers as positions inside the type's worker list
+ *   flags      bit 0: policy is Isolated_plus (the walk stops at the first job that does not fit), bit 1: FIFO
+ * Outputs: prio [J][W]; n_sel [W] and sel_jobs [W][J] (per processing position, selection order);
+ *   n_assigned, assign_job [J], assign_off [J+1], assign_workers: the new assignment in the reference's OrderedDict
+ *   insertion order.  Returns 0, or SWB_ERR_STATE when the selected jobs do not fit the workers ("Could not assign
+ *   workers to job", scheduler.py:1097-1100).  Bit-for-bit the dict code's result (integer / comparison work; the one
+ *   division is the reference's own IEEE operation). */
+typedef struct swb_gavel_round_args {
+  int32_t J, W, flags;
+  const int32_t *type_order, *capacity;
+  const double *alloc, *job_time, *thr, *deficit;
+  const double *worker_time;
+  const int32_t *sf;
+  const int32_t *nworkers, *worker_ids;
+  const int32_t *prev_type, *prev_off, *prev_local;
+  double *prio;
+  int32_t *n_sel, *sel_jobs;
+  int32_t *n_assigned, *assign_job, *assign_off, *assign_workers;
+} swb_gavel_round_args;
+int swb_gavel_round(swb_ctx *ctx, const swb_gavel_round_args *a);
 
 /* ---- Monte-Carlo (geometric Brownian motion) throughput forecast -------------------------------- *
  * New capability, no reference counterpart (the reference's forecast is the deterministic

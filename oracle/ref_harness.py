@@ -115,7 +115,7 @@ def import_reference(dst, shockwave_scheduler_cls=None):
 def simulate(policy_name, shockwave_scheduler_cls=None, policy_obj=None,
              config="configurations/tacc_32gpus.json", cluster="32:0:0", trace=CANONICAL_TRACE,
              throughputs="tacc_throughputs.json", time_per_iteration=120, seed=0, scratch=None,
-             max_rounds=None):
+             max_rounds=None, scheduler_mixin=None):
     """Mirror of simulate_scheduler_with_trace.py:main for one policy.  Returns the result dict."""
     dst = prepare_tree(scratch, trace)
     cwd = os.getcwd()
@@ -141,7 +141,10 @@ def simulate(policy_name, shockwave_scheduler_cls=None, policy_obj=None,
             sw_cfg = json.load(open(os.path.join(dst, config)))
             sw_cfg["time_per_iteration"] = time_per_iteration
             sw_cfg["num_gpus"] = cluster_spec["v100"] * per_server["v100"]
-        sched = ref_sched.Scheduler(policy_obj, throughputs_file=throughputs_file, simulate=True,
+        sched_cls = ref_sched.Scheduler
+        if scheduler_mixin is not None:      # drop-in for methods of the round mechanism itself (placement.py)
+            sched_cls = type("Scheduler", (scheduler_mixin, ref_sched.Scheduler), {})
+        sched = sched_cls(policy_obj, throughputs_file=throughputs_file, simulate=True,
                                     seed=seed, time_per_iteration=time_per_iteration,
                                     pickle_file=pickle_path, shockwave_config=sw_cfg)
         makespan = sched.simulate(cluster_spec, arrival_times, jobs,

@@ -66,6 +66,9 @@ struct swb_ctx {
   uint64_t gbm_seed = 0;
   int gbm_hmax = 256;
   DBuf ens_z;
+  DBuf gv_in, gv_out;     // swb_gavel_round: one staging buffer each way
+  DBuf rr_items;          // re-rank local search scratch
+  int rr_iters = 400;     // SWB_OPT_RERANK_ITERS (0 = sweep only)
   DBuf pool_pp, pool_bs;
   int64_t pool_used = 0;
   // holes left by removed jobs in pool_pp / pool_bs: (offset, rows), sorted by offset, adjacent holes merged;
@@ -128,7 +131,7 @@ void swb_destroy(swb_ctx *c) {
   DBuf *all[] = {&c->prm, &c->res, &c->g, &c->E, &c->c, &c->dbar, &c->rem, &c->ftobj, &c->bfkey, &c->x,
                  &c->bf, &c->nr, &c->w, &c->xmk, &c->bmk, &c->sa, &c->su0, &c->sR, &c->sws, &c->scap, &c->sg, &c->snF,
                  &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->scth, &c->sRr, &c->sths, &c->sn0, &c->snfc, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
-                 &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc, &c->t_mu, &c->t_sg, &c->ens_z,
+                 &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc, &c->t_mu, &c->t_sg, &c->ens_z, &c->gv_in, &c->gv_out, &c->rr_items,
                  &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
                  &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal, &c->ax_p, &c->ax_t, &c->ax_wt, &c->ax_u, &c->ax_v, &c->ax_spc, &c->ax_c4r, &c->ax_r4c,
                  &c->ax_path, &c->ax_sc, &c->ax_sr, &c->ax_out, &c->pol_coef, &c->pol_sf, &c->pol_t,
@@ -221,6 +224,16 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   P.sc_g = L.sc_g; P.sc_n = L.sc_n; P.sc_nmax = L.sc_nmax; P.weights = L.weights; P.E = E; P.c = cc; P.dbar = dbar;
   P.x = x; P.backfill = bf; P.nrounds = nr ? nr : c->seated.as<int32_t>(); P.ncal = ncal; P.res = L.res;
   P.xmask = xmask; P.bfmask = bfmask; P.ncap = c->sncap.as<uint8_t>();
+  // re-rank local search: O(J T^2) per cancelled cycle — on where that stays in the tens of microseconds
+  P.rr_items = nullptr; P.rr_iters = 0;
+  {
+    const size_t T_ = (size_t)h_prm[0].future_rounds;
+    const size_t bytes = (size_t)S * 4 * T_ * T_ * 64;
+    if (c->rr_iters > 0 && (size_t)J * T_ * T_ <= (4u << 20) && bytes <= (512u << 20)) {
+      CK(c->rr_items.need(bytes, c->st));
+      P.rr_items = c->rr_items.p; P.rr_iters = c->rr_iters;
+    }
+  }
   int rc2 = ensure_hres(c, S);
   if (rc2) return rc2;
   for (int pass = 0; pass < SWB_MAX_REPLAN + 1; ++pass) {
@@ -752,6 +765,87 @@ int swb_gbm_forecast(swb_ctx *c, int32_t J, const double *R0, const int32_t *H, 
   return 0;
 }
 
+int swb_gavel_round(swb_ctx *c, const swb_gavel_round_args *a) {
+  if (!c || !a) return fail(SWB_ERR_ARG, "swb_gavel_round: null argument");
+  const int J = a->J, W = a->W;
+  if (J <= 0 || J > SWB_MAX_J || W <= 0 || W > 8) return fail(SWB_ERR_ARG, "swb_gavel_round: need J in [1,8192], W in [1,8]");
+  if (!a->type_order || !a->capacity || !a->alloc || !a->job_time || !a->thr || !a->deficit || !a->worker_time ||
+      !a->sf || !a->nworkers || !a->worker_ids || !a->prev_type || !a->prev_off || !a->prev_local || !a->prio ||
+      !a->n_sel || !a->sel_jobs || !a->n_assigned || !a->assign_job || !a->assign_off || !a->assign_workers)
+    return fail(SWB_ERR_ARG, "swb_gavel_round: missing pointer");
+  int totw = 0, maxw = 0;
+  for (int t = 0; t < W; ++t) {
+    if (a->nworkers[t] < 0 || a->nworkers[t] > 8192) return fail(SWB_ERR_ARG, "swb_gavel_round: <= 8192 workers per type");
+    totw += a->nworkers[t]; if (a->nworkers[t] > maxw) maxw = a->nworkers[t];
+    if (a->type_order[t] < 0 || a->type_order[t] >= W) return fail(SWB_ERR_ARG, "swb_gavel_round: bad type_order");
+  }
+  const int nprev = a->prev_off[J];
+  for (int j = 0; j < J; ++j) {
+    if (a->sf[j] <= 0) return fail(SWB_ERR_ARG, "swb_gavel_round: scale factors must be positive");
+    if (a->prev_off[j + 1] < a->prev_off[j]) return fail(SWB_ERR_ARG, "swb_gavel_round: prev_off must be non-decreasing");
+  }
+  CK(cudaSetDevice(c->device));
+  // one staging buffer each way: [doubles | int32s | bytes]
+  const size_t JW = (size_t)J * W;
+  const size_t nd_in = 4 * JW + W;                                  // alloc, job_time, thr, deficit, worker_time
+  const size_t ni_in = 2 * (size_t)W + J + W + totw + J + (J + 1) + (size_t)nprev;
+  const size_t in_bytes = nd_in * 8 + ni_in * 4;
+  const size_t nd_out = JW;                                         // prio
+  const size_t ni_out = W + JW + 2 + J + J + (J + 1) + (size_t)totw + 2 * (size_t)J + (size_t)totw;
+  const size_t out_bytes = nd_out * 8 + ni_out * 4 + J;
+  std::vector<unsigned char> h(in_bytes);
+  double *hd = reinterpret_cast<double *>(h.data());
+  memcpy(hd, a->alloc, JW * 8); memcpy(hd + JW, a->job_time, JW * 8); memcpy(hd + 2 * JW, a->thr, JW * 8);
+  memcpy(hd + 3 * JW, a->deficit, JW * 8); memcpy(hd + 4 * JW, a->worker_time, (size_t)W * 8);
+  int32_t *hi = reinterpret_cast<int32_t *>(hd + nd_in);
+  size_t o = 0;
+  auto put = [&](const int32_t *src, size_t n) { memcpy(hi + o, src, n * 4); size_t at = o; o += n; return at; };
+  const size_t o_order = put(a->type_order, W), o_cap = put(a->capacity, W), o_sf = put(a->sf, J),
+               o_nw = put(a->nworkers, W), o_wid = put(a->worker_ids, totw), o_pt = put(a->prev_type, J),
+               o_po = put(a->prev_off, J + 1), o_pl = put(a->prev_local, nprev);
+  CK(c->gv_in.need(in_bytes, c->st)); CK(c->gv_out.need(out_bytes, c->st));
+  CK(cudaMemcpyAsync(c->gv_in.p, h.data(), in_bytes, cudaMemcpyHostToDevice, c->st));
+  const double *dd = c->gv_in.as<double>();
+  const int32_t *di = reinterpret_cast<const int32_t *>(dd + nd_in);
+  double *od = c->gv_out.as<double>();
+  int32_t *oi = reinterpret_cast<int32_t *>(od + nd_out);
+  swb::GavelLaunch L;
+  L.J = J; L.W = W; L.flags = a->flags; L.maxw = maxw;
+  L.alloc = dd; L.job_time = dd + JW; L.thr = dd + 2 * JW; L.deficit = dd + 3 * JW; L.worker_time = dd + 4 * JW;
+  L.type_order = di + o_order; L.capacity = di + o_cap; L.sf = di + o_sf; L.nworkers = di + o_nw;
+  L.worker_ids = di + o_wid; L.prev_type = di + o_pt; L.prev_off = di + o_po; L.prev_local = di + o_pl;
+  L.in_alloc = nullptr;
+  L.prio = od;
+  size_t q = 0;
+  L.n_sel = oi + q; q += W;
+  L.sel_jobs = oi + q; q += JW;
+  L.out_scalars = oi + q; q += 2;
+  L.assign_job = oi + q; q += J;
+  L.assign_cnt = oi + q; q += J;
+  L.assign_off = oi + q; q += J + 1;
+  L.assign_workers = oi + q; q += totw;
+  L.tmp_rank0 = oi + q; q += J;
+  q += J;
+  L.tmp_free = oi + q; q += totw;
+  L.sched = reinterpret_cast<uint8_t *>(oi + ni_out);
+  CK(swb::launch_gavel_round(L, c->st));
+  std::vector<unsigned char> ho(out_bytes);
+  CK(cudaMemcpyAsync(ho.data(), c->gv_out.p, out_bytes, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  const double *rd = reinterpret_cast<const double *>(ho.data());
+  const int32_t *ri = reinterpret_cast<const int32_t *>(rd + nd_out);
+  memcpy(a->prio, rd, JW * 8);
+  memcpy(a->n_sel, ri, (size_t)W * 4);
+  memcpy(a->sel_jobs, ri + W, JW * 4);
+  const int32_t nasg = ri[W + JW], err = ri[W + JW + 1];
+  *a->n_assigned = nasg;
+  memcpy(a->assign_job, ri + W + JW + 2, (size_t)J * 4);
+  memcpy(a->assign_off, ri + W + JW + 2 + 2 * (size_t)J, (size_t)(J + 1) * 4);
+  memcpy(a->assign_workers, ri + W + JW + 2 + 2 * (size_t)J + (J + 1), (size_t)totw * 4);
+  if (err) return fail(SWB_ERR_STATE, "swb_gavel_round: could not assign workers to a selected job (scheduler.py:1097-1100)");
+  return 0;
+}
+
 int swb_gbm_ensemble(swb_ctx *c, int32_t S, int32_t J, double P_total, const double *sums_dev, const double *z,
                      double *rem_out_dev) {
   if (!c || !sums_dev || !z || !rem_out_dev) return fail(SWB_ERR_ARG, "swb_gbm_ensemble: null argument");
@@ -850,6 +944,7 @@ int swb_set_option(swb_ctx *c, int32_t option, int32_t value) {
   if (!c) return fail(SWB_ERR_ARG, "null ctx");
   if (option == SWB_OPT_RELAXED_OPTIMUM) { c->want_relaxed = value ? 1 : 0; return 0; }
   if (option == SWB_OPT_SOLVE_CLUSTER) { swb::set_solve_cluster(value); return 0; }
+  if (option == SWB_OPT_RERANK_ITERS) { c->rr_iters = value < 0 ? 0 : value; return 0; }
   if (option == SWB_OPT_GBM_PATHS) { if (value < 0) return fail(SWB_ERR_ARG, "paths < 0"); c->gbm_paths = value; return 0; }
   if (option == SWB_OPT_GBM_SEED) { c->gbm_seed = (uint64_t)(uint32_t)value; return 0; }
   if (option == SWB_OPT_GBM_HORIZON) { if (value < 1) return fail(SWB_ERR_ARG, "horizon < 1"); c->gbm_hmax = value; return 0; }

@@ -87,7 +87,12 @@ __global__ void __launch_bounds__(1024, 1) gavel_round_kernel(GavelLaunch L) {
     }
     L.prio[e] = p;
   }
-  for (int j = tid; j < J; j += nt) sched[j] = 0;
+  // sched[j]: bit 0 = scheduled on some type already, bit 1 = the allocation knows the job (any non-NaN entry)
+  for (int j = tid; j < J; j += nt) {
+    unsigned char known = 0;
+    for (int w = 0; w < W; ++w) known |= isnan(L.alloc[(size_t)j * W + w]) ? 0 : 2;
+    sched[j] = known;
+  }
   if (tid == 0) { s_stop = 0; s_nasg = 0; s_err = 0; L.assign_off[0] = 0; }
   __syncthreads();
 
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(1024, 1) gavel_round_kernel(GavelLaunch L) {
       if (pos < npad) {
         const int j = ord[pos];
         unsigned char st = 2;
-        if (j < J && !sched[j] && L.thr[(size_t)j * W + w] > 0.0 &&
+        if (j < J && !(sched[j] & 1) && L.thr[(size_t)j * W + w] > 0.0 &&
             !((L.flags & 2) && L.prio[(size_t)j * W + w] <= 0.0))
           st = 0;
         state[pos] = st;
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(1024, 1) gavel_round_kernel(GavelLaunch L) {
       int off = gv_scan(cnt, wsum, &tot);
       for (int q = 0; q < chs; ++q) {
         const int pos = p0 + q;
-        if (pos < npad && state[pos] == 1) { const int j = ord[pos]; L.sel_jobs[(size_t)ti * J + off++] = j; sched[j] = 1; }
+        if (pos < npad && state[pos] == 1) { const int j = ord[pos]; L.sel_jobs[(size_t)ti * J + off++] = j; sched[j] |= 1; }
       }
       if (tid == 0) { s_nsel = tot; L.n_sel[ti] = tot; }
     }
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(1024, 1) gavel_round_kernel(GavelLaunch L) {
       int cntB = 0, needB = 0;
       for (int q = 0; q < chn; ++q) {
         const int i = n0 + q;
-        if (i < nsel && state[i] == 0 && L.sf[sel[i]] == cur && L.in_alloc[sel[i]]) { ++cntB; needB += cur; }
+        if (i < nsel && state[i] == 0 && L.sf[sel[i]] == cur && (sched[sel[i]] & 2)) { ++cntB; needB += cur; }
       }
       int totB = 0, totNeed = 0;
       int offB = gv_scan(cntB, wsum, &totB);
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(1024, 1) gavel_round_kernel(GavelLaunch L) {
       // rank / cur-th pending job of the class (all have the same width)
       for (int q = 0; q < chn; ++q) {
         const int i = n0 + q;
-        if (i < nsel && state[i] == 0 && L.sf[sel[i]] == cur && L.in_alloc[sel[i]]) {
+        if (i < nsel && state[i] == 0 && L.sf[sel[i]] == cur && (sched[sel[i]] & 2)) {
           const int slot = baseB + offB++;
           L.assign_job[slot] = sel[i];
           L.assign_cnt[slot] = cur;

@@ -18,6 +18,7 @@
 
 #include "swb_common.cuh"
 #include "swb_internal.h"
+#include "rerank.cuh"
 
 namespace swb {
 
@@ -146,18 +147,6 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   }
   __syncthreads();
 
-  // ---- back-fill order: descending remaining runtime, stable (shockwave.py:261-267) ---------
-  {
-    const double *bk = ((fallback && L.bfkey_fb) ? L.bfkey_fb : L.bfkey) + (L.per_scn ? so : 0);
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-      key64[i] = (i < J) ? dbl_order_key(bk[i]) : 0ull;
-      idx16[i] = (unsigned short)(i < J ? i : 0xffff);
-    }
-    __syncthreads();
-    sort_desc64(key64, idx16, npad);
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) order[i] = idx16[i];
-    __syncthreads();
-  }
   // ---- packing order: wider gangs first, then more planned rounds (fallback: higher
   //      prio_j/(n_j g_j), the exchange-argument order of rank_in_schedule_jobs), then job index ----
   if (fallback && L.weights) {
@@ -512,6 +501,21 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   }
   __syncthreads();
 
+  // ---- fallback re-rank, second stage: negative-cycle cancelling on the round graph (rerank.cuh) improves the
+  //      sweep's schedule towards the optimum of rank_in_schedule_jobs (shockwave.py:714-793); only when every
+  //      planned round was seated and the instance is inside the search's size budget (api.cu) -----------------------
+  int rr_cycles = 0;
+  if (fallback && L.weights && L.rr_items && L.rr_iters > 0) {
+    long long sfl = 0;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) sfl += remn[j];
+    sfl = br.sumll(sfl);
+    if (sfl == 0) {
+      rr_cycles = rr_local_search(reinterpret_cast<RrTop2 *>(L.rr_items) + (size_t)s * RR_MAXCLS * T * T, xm, gs, remn,
+                                  nplan, L.weights + so, idle, J, T, L.rr_iters);
+      __syncthreads();
+    }
+  }
+
   Pwl P;
   P.B = prm.nbases;
   for (int b = 0; b < prm.nbases; ++b) { P.base[b] = prm.bases[b]; P.logv[b] = prm.logv[b]; }
@@ -604,6 +608,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
       swb_result &r = L.res[s];
       r.welfare = w; r.makespan = me; r.objective = w - prm.k * me; r.shortfall = (int)shortf;
       r.placement = t0;
+      r.flags = (r.flags & 0xff) | (rr_cycles << 8);      // cycles cancelled by the re-rank local search
     }
   }
 
@@ -659,6 +664,23 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   }
 
   // ---- work-conserving back-fill: one warp per round walks the sorted order --------------------
+  //      (the order — descending remaining runtime, stable, shockwave.py:261-267 — costs a full sort of the jobs and
+  //      is only needed when some round has idle GPUs left; a window whose rounds are all full skips it)
+  int any_idle = 0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) any_idle |= idle[t] > 0 ? 1 : 0;
+  any_idle = __syncthreads_or(any_idle);
+  if (any_idle) {
+  {
+    const double *bk = ((fallback && L.bfkey_fb) ? L.bfkey_fb : L.bfkey) + (L.per_scn ? so : 0);
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+      key64[i] = (i < J) ? dbl_order_key(bk[i]) : 0ull;
+      idx16[i] = (unsigned short)(i < J ? i : 0xffff);
+    }
+    __syncthreads();
+    sort_desc64(key64, idx16, npad);
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) order[i] = idx16[i];
+    __syncthreads();
+  }
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int t = warp; t < T; t += nw) {
@@ -686,6 +708,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
       }
     }
   }
+  }  // any_idle
   __syncthreads();
 
   // ---- outputs: 128-bit round masks (16 B per job and matrix) and/or byte matrices, coalesced ---------

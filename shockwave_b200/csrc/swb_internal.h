@@ -52,6 +52,8 @@ struct PlaceLaunch {
   int32_t *ncal;          // [S][J] out, may be null: rounds with idle GPUs in which the job is unscheduled
   swb_result *res;        // device [S] (status in, objective/shortfall updated)
   uint8_t *ncap;          // [S][J] in/out, may be null: per-job count caps for the next pass (packing feedback)
+  void *rr_items;         // scratch of the re-rank local search, S x 4 x T x T x 64 B (null: search off)
+  int rr_iters;           // cycle-cancelling budget per scenario
 };
 
 cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st, int nbases);

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libswb200.so")
 
 MAX_BASES = 16
 ST_OK, ST_FALLBACK = 0, 1
-OPT_RELAXED_OPTIMUM, OPT_SOLVE_CLUSTER, OPT_GBM_PATHS, OPT_GBM_SEED, OPT_GBM_HORIZON = 1, 2, 3, 4, 5
+OPT_RELAXED_OPTIMUM, OPT_SOLVE_CLUSTER, OPT_GBM_PATHS, OPT_GBM_SEED, OPT_GBM_HORIZON, OPT_RERANK_ITERS = 1, 2, 3, 4, 5, 6
 
 
 class Params(C.Structure):
@@ -58,7 +58,7 @@ class RoundArgs(C.Structure):
 
 
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
-           "swb_solve", "swb_job_add", "swb_job_remove", "swb_job_table_stats", "swb_job_set_gbm", "swb_gbm_ensemble", "swb_round_solve", "swb_forecast",
+           "swb_solve", "swb_job_add", "swb_job_remove", "swb_job_table_stats", "swb_job_set_gbm", "swb_gbm_ensemble", "swb_gavel_round", "swb_round_solve", "swb_forecast",
            "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_policy_hetero", "swb_gbm_forecast", "swb_market_pgd", "swb_set_option", "swb_allox_assign"]
 
 _lib = None
@@ -229,6 +229,55 @@ class Engine:
                                               C.c_void_p]
         self._check(self.lib.swb_gbm_ensemble(self.h, int(S), int(J), float(P_total), C.c_void_p(int(sums_device_ptr)),
                                               _ptr(z), C.c_void_p(int(rem_out_device_ptr))), "swb_gbm_ensemble")
+
+    def gavel_round(self, alloc, job_time, worker_time, thr, deficit, sf, capacity, type_order, worker_lists, prev,
+                    isolated_plus=False, fifo=False):
+        """swb_gavel_round on plain arrays.  alloc / job_time / thr / deficit: [J, W] float64 (alloc NaN = job not in
+        the allocation); worker_lists: list (processing order) of flat worker-id lists; prev: {job idx: (type idx,
+        (worker ids))}.  Returns (prio [J, W], {type idx: [job idx in selection order]}, [(job idx, (worker ids))] in
+        the reference's insertion order)."""
+        f64 = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+        i32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        alloc, job_time, thr, deficit, worker_time = f64(alloc), f64(job_time), f64(thr), f64(deficit), f64(worker_time)
+        J, W = alloc.shape
+        sf, capacity, type_order = i32(sf), i32(capacity), i32(type_order)
+        nworkers = i32([len(wl) for wl in worker_lists])
+        wids = i32([w for wl in worker_lists for w in wl]) if nworkers.sum() else np.zeros(1, np.int32)
+        local = [{w: i for i, w in enumerate(worker_lists[ti])} for ti in range(W)]
+        pos_of_type = {int(t): ti for ti, t in enumerate(type_order)}
+        prev_type = np.full(J, -1, dtype=np.int32)
+        prev_off = np.zeros(J + 1, dtype=np.int32)
+        pl = []
+        for j in range(J):
+            if j in prev:
+                t, ws = prev[j]
+                prev_type[j] = t
+                lut = local[pos_of_type[int(t)]] if int(t) in pos_of_type else {}
+                pl += [lut.get(w, -1) for w in ws]
+            prev_off[j + 1] = len(pl)
+        prev_local = i32(pl) if pl else np.zeros(1, np.int32)
+        prio = np.empty((J, W), dtype=np.float64)
+        n_sel = np.zeros(W, dtype=np.int32); sel_jobs = np.zeros((W, J), dtype=np.int32)
+        n_asg = C.c_int32(); a_job = np.zeros(J, dtype=np.int32); a_off = np.zeros(J + 1, dtype=np.int32)
+        a_w = np.zeros(max(1, int(nworkers.sum())), dtype=np.int32)
+
+        class Args(C.Structure):
+            _fields_ = [("J", C.c_int32), ("W", C.c_int32), ("flags", C.c_int32)] + \
+                       [(n, C.c_void_p) for n in ("type_order", "capacity", "alloc", "job_time", "thr", "deficit",
+                                                  "worker_time", "sf", "nworkers", "worker_ids", "prev_type", "prev_off",
+                                                  "prev_local", "prio", "n_sel", "sel_jobs")] + \
+                       [("n_assigned", C.POINTER(C.c_int32))] + \
+                       [(n, C.c_void_p) for n in ("assign_job", "assign_off", "assign_workers")]
+        a = Args(J, W, (1 if isolated_plus else 0) | (2 if fifo else 0), _ptr(type_order), _ptr(capacity), _ptr(alloc),
+                 _ptr(job_time), _ptr(thr), _ptr(deficit), _ptr(worker_time), _ptr(sf), _ptr(nworkers), _ptr(wids),
+                 _ptr(prev_type), _ptr(prev_off), _ptr(prev_local), _ptr(prio), _ptr(n_sel), _ptr(sel_jobs),
+                 C.pointer(n_asg), _ptr(a_job), _ptr(a_off), _ptr(a_w))
+        self.lib.swb_gavel_round.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.swb_gavel_round.restype = C.c_int
+        self._check(self.lib.swb_gavel_round(self.h, C.byref(a)), "swb_gavel_round")
+        sel = {int(type_order[ti]): sel_jobs[ti, :n_sel[ti]].tolist() for ti in range(W)}
+        asg = [(int(a_job[s]), tuple(a_w[a_off[s]:a_off[s + 1]].tolist())) for s in range(n_asg.value)]
+        return prio, sel, asg
 
     def job_table_stats(self):
         used, holes = C.c_int64(), C.c_int64()

@@ -275,9 +275,11 @@ class ShockwaveScheduler(object):
         if self._ids_cache is None:                 # rebuilt after add / remove only
             self._ids_cache = (list(self.metadata.keys()), list(self.metadata.values()))
         jobids, jobobjs = self._ids_cache
-        # the reference re-seeds both global RNGs on every solver call (call_cvxpy_solver,
-        # shockwave.py:451-452); the simulator draws from them afterwards, so this side effect is part
-        # of the drop-in contract
+        # the reference re-seeds both global generators on every solver call (call_cvxpy_solver, shockwave.py:451-452):
+        # kept, so that user code drawing from them sees the same state after a re-solve.  Not reproduced: the
+        # reference then consumes one `random.choice` draw per back-fill sort-key evaluation (JobMetaData.py:365 with
+        # noise_level = 0 — the VALUE is unaffected).  The simulator itself never reads the global generators (it
+        # draws from private random.Random instances, scheduler.py:502-511), so closed-loop results do not depend on it.
         random.seed(0)
         np.random.seed(0)
         schedules = self._resolve(jobids, jobobjs)

@@ -100,3 +100,27 @@ def test_gavel_policy_closed_loop_matches_golden_pickle(policy):
     # is within 0.8 % (tests/golden/tacc32_policy_pins.json), the GPU-backed one must be too
     assert abs(out["makespan"] - gold["makespan"]) / gold["makespan"] < 0.015
     assert abs(out["avg_jct"] - gold["avg_jct"]) / gold["avg_jct"] < 0.015
+
+
+@pytest.mark.skipif(not _have_both(), reason="needs a B200 and the (staged) reference simulator at the same time")
+@pytest.mark.parametrize("policy", ["max_min_fairness", "finish_time_fairness", "max_sum_throughput_perf"])
+def test_gavel_round_step_on_the_device_reproduces_the_reference_loop(policy):
+    """§8(f)-2: priorities -> selection -> worker assignment of every round computed by gavel.cu (GavelRoundMixin in
+    front of the reference's Scheduler class) — per_round_schedule must be identical, worker id by worker id, to the
+    same run with the reference's own dict code."""
+    from shockwave_b200 import policies
+    from shockwave_b200.placement import GavelRoundMixin
+    before = GavelRoundMixin.swb_round_calls
+    t0 = time.perf_counter()
+    dev = rh.simulate(policy, policy_obj=policies.get_policy(policy, solver="ECOS", seed=0),
+                      scheduler_mixin=GavelRoundMixin)
+    t_dev = time.perf_counter() - t0
+    ncalls = GavelRoundMixin.swb_round_calls - before
+    ref = rh.simulate(policy, policy_obj=policies.get_policy(policy, solver="ECOS", seed=0))
+    assert ncalls == len(dev["per_round_schedule"]) > 100 and _native_loaded()
+    assert len(dev["per_round_schedule"]) == len(ref["per_round_schedule"])
+    for r, (a, b) in enumerate(zip(dev["per_round_schedule"], ref["per_round_schedule"])):
+        assert list(a.items()) == list(b.items()), r
+    assert dev["makespan"] == ref["makespan"] and dev["jct_list"] == ref["jct_list"]
+    gold = pickle.load(open(glob.glob(os.path.join(GOLD, policy + "_120_*"))[0], "rb"))
+    print(_record(policy + "+round_step_on_device", dev, gold, t_dev, dict(device_round_calls=ncalls)))

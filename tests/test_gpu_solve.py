@@ -60,29 +60,41 @@ def test_recorded_canonical_solves(engine):
 
 
 def test_fallback_rerank_quality(engine):
-    """rank_in_schedule_jobs (shockwave.py:714-793) is a second MILP over the ORDER of the rounds with the
-    counts fixed.  The GPU replaces it by a priority round-sweep + water-filling; on every 3rd recorded
-    fallback solve its rank objective must stay within 10 % of the exact re-rank MILP of the same counts
-    (measured: median 0.2 %, p90 1.4 %, max 6.6 % over all 128)."""
+    """rank_in_schedule_jobs (shockwave.py:714-793) is a second MILP over the ORDER of the rounds with the counts fixed
+    (the reference solves it to MIPGap 1e-3).  The GPU replaces it by a priority round-sweep followed by negative-cycle
+    cancelling on the round graph (rerank.cuh).  On ALL 128 recorded fallback solves of the canonical run its rank
+    objective is compared with the exact re-rank MILP of the same counts (HiGHS, gap 1e-6)."""
     T, G, D = fx.TACC["T"], fx.TACC["G"], fx.TACC["D"]
-    worst, seen = 0.0, 0
+    exc, exc_sweep, cycles = [], [], []
     for i in range(fx.n_solves()):
         s = fx.solve(i)
         if s["status"] != om.STATUS_FALLBACK:
-            continue
-        seen += 1
-        if seen % 3:
             continue
         prm = make_params(G, T, D, fx.TACC["k"], fx.TACC["lam"], fx.TACC["rhomax"], fx.BASES, fx.ORIGIN,
                           round_ptr=s["round_ptr"])
         out = engine.solve(prm, s["g"], s["E"], s["c"], s["dbar"], s["rem"], s["ftobj"], bfkey=s["rem"])
         x, w = out["x"][0], out["weights"][0]
-        y = om.rank_in_schedule(x.astype(float), w, s["g"].astype(np.int64), G, 1e-6, 20.0)
+        assert out["results"][0]["shortfall"] == 0
+        assert np.all(x.T.astype(np.int64) @ s["g"].astype(np.int64) <= G)
+        y = om.rank_in_schedule(x.astype(float), w, s["g"].astype(np.int64), G, 1e-6, 30.0)
         ry, rg = om.rank_objective(y, w), om.rank_objective(x, w)
         assert np.array_equal(np.asarray(y).sum(axis=1).round().astype(int), x.sum(axis=1))
-        worst = max(worst, (rg - ry) / max(1e-12, abs(ry)))
-    print("fallback re-rank: worst excess over the exact re-rank MILP", worst)
-    assert worst <= 0.10
+        exc.append((rg - ry) / max(1e-12, abs(ry)))
+        cycles.append(out["results"][0]["flags"] >> 8)
+        engine.set_option(6, 0)                              # the sweep alone, same counts
+        x0 = engine.solve(prm, s["g"], s["E"], s["c"], s["dbar"], s["rem"], s["ftobj"], bfkey=s["rem"])["x"][0]
+        engine.set_option(6, 400)
+        assert np.array_equal(x0.sum(axis=1), x.sum(axis=1))
+        exc_sweep.append((om.rank_objective(x0, w) - ry) / max(1e-12, abs(ry)))
+    exc, exc_sweep = np.array(exc), np.array(exc_sweep)
+    print("fallback re-rank excess over the exact MILP: median %.2e p90 %.2e max %.2e, above 1e-3: %d of %d "
+          "(sweep alone: median %.2e p90 %.2e max %.2e, above 1e-3: %d); cycles cancelled: mean %.1f max %d"
+          % (np.median(exc), np.percentile(exc, 90), exc.max(), int((exc > 1e-3).sum()), len(exc),
+             np.median(exc_sweep), np.percentile(exc_sweep, 90), exc_sweep.max(), int((exc_sweep > 1e-3).sum()),
+             float(np.mean(cycles)), int(np.max(cycles))))
+    assert len(exc) >= 120
+    assert np.all(exc <= exc_sweep + 1e-12)                  # the search never makes the schedule worse
+    assert np.median(exc) <= 1e-4 and np.percentile(exc, 90) <= 2.5e-3 and exc.max() <= 1.5e-2
 
 def _oracle_obj(s, w):
     """Recorded oracle x re-scored with the weights the GPU used (identical to the recorded weights
