@@ -413,6 +413,7 @@ def main():
     line.update(extras)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample()
+        line["same_algorithm_cpu"] = same_algorithm_cpu()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -462,6 +463,32 @@ def cpu_baseline_sample():
                        f"incumbents {oks}/3; the same three instances through Engine.solve with host buffers: "
                        f"{[round(m, 3) for m in gpu_ms]} ms; the headline size (config D) needs minutes per scenario on "
                        "one core — timed on the same seeds by `bench.py --impl reference`")}
+
+
+def same_algorithm_cpu(nscn=None):
+    """The SAME algorithm as solve.cu (collapsed MILP: clearing price nested in a makespan search) as plain C on ALL host
+    cores, one config-D scenario per OpenMP thread (oracle/price_search.c) — separates what the algorithm buys from what
+    the B200 buys.  Counts only (no placement / back-fill), float64."""
+    from oracle import price_search as ps
+    from oracle import shockwave_milp as om
+    ncpu = os.cpu_count() or 1
+    S = nscn or max(8, min(2 * ncpu, 256))
+    pbs = [scenario(i) for i in range(S)]
+    st = lambda key: np.stack([p[0][key] for p in pbs])
+    logv = om.pwl_log_values(BASES, ORIGIN)
+    arrs = [st(k) for k in ("g", "E", "c", "dbar", "rem", "ftobj")]
+    ks, rps = [p[1] for p in pbs], [p[0]["round_ptr"] for p in pbs]
+    ps.price_search(ks[:ncpu], rps[:ncpu], *[a[:ncpu] for a in arrs], G, T, D, 12.0, 1.0, BASES, logv, ncpu)   # warm-up
+    t0 = time.perf_counter()
+    r = ps.price_search(ks, rps, *arrs, G, T, D, 12.0, 1.0, BASES, logv, ncpu)
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ps.price_search(ks[:4], rps[:4], *[a[:4] for a in arrs], G, T, D, 12.0, 1.0, BASES, logv, 1)
+    one = (time.perf_counter() - t0) / 4
+    return {"value": S / dt, "unit": "rounds/s", "threads": ncpu, "scenarios": S, "seconds_per_scenario_one_core": one,
+            "mean_price_evaluations": float(np.mean(r["evals"])),
+            "what": "oracle/price_search.c: the collapsed solve of solve.cu restated in plain C (float64, gcc -O3, OpenMP, "
+                    "one scenario per thread), round counts only — no placement, back-fill or forecast"}
 
 
 def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):

@@ -29,7 +29,7 @@ for i in range(fx.n_solves()):
     eng.set_option(6, 400)
     r0 = om.rank_objective(o0["x"][0], w)
     rows.append(dict(i=i, J=int(s["J"]), milp=ry, exc=(rg - ry) / max(1e-12, abs(ry)), exc_sweep=(r0 - ry) / max(1e-12, abs(ry)),
-                     cycles=out["results"][0]["flags"] >> 8, swept=out["results"][0]["placement"],
+                     cycles=(out["results"][0]["flags"] >> 8) & 0xfff, winner=out["results"][0]["flags"] >> 20, swept=out["results"][0]["placement"],
                      place_ms=tm["ms_place"], place_ms_sweep=tm0["ms_place"],
                      widths=sorted(set(int(v) for v in s["g"][x.sum(axis=1) > 0]))))
     if rows[-1]["exc"] > 1e-3:

@@ -18,18 +18,44 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "launch__shared_mem_per_block_dynamic"]
 
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3,
+        "msecond": 1e3, "nsecond": 1e-3, "second": 1e6, "s": 1e6}
+
+
+def _num(v, u):
+    try:
+        return float(v.replace(",", "")) * UNIT.get(u, 1.0)
+    except ValueError:
+        return None
+
+
 def main(tag):
     out = []
+    kernels = {}
     for rep in sorted(glob.glob(f"gpurun_out/*_{tag}.ncu-rep")):
         txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(txt)))
         hdr, units, vals = rows[0], rows[1], rows[2]
         name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else rep
         out.append(f"== {os.path.basename(rep)} :: {name}")
+        row = {}
         for h, u, v in zip(hdr, units, vals):
             if h in WANT:
                 out.append(f"   {h} = {v} {u}")
+                row[h] = _num(v, u)
+        rd, wr = row.get("dram__bytes_read.sum"), row.get("dram__bytes_write.sum")
+        kernels[name] = {"capture": os.path.basename(rep), "duration_us": row.get("gpu__time_duration.sum"),
+                         "dram_bytes": (rd + wr) if rd is not None and wr is not None else None,
+                         "dram_bytes_read": rd, "dram_bytes_write": wr,
+                         "issue_active_pct": row.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                         "sm_throughput_pct": row.get("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+                         "warps_active_pct": row.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                         "dram_throughput_pct": row.get("dram__throughput.avg.pct_of_peak_sustained_elapsed"),
+                         "grid": row.get("launch__grid_size"), "block": row.get("launch__block_size"),
+                         "registers": row.get("launch__registers_per_thread")}
     open(f"profiles/ncu_summary_{tag}.txt", "w").write("\n".join(out) + "\n")
+    import json
+    json.dump(kernels, open(f"profiles/ncu_kernels_{tag}.json", "w"), indent=1)    # bench.py reads roofline.traffic here
     print("\n".join(out))
 
 

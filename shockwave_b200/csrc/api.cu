@@ -225,13 +225,15 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   P.x = x; P.backfill = bf; P.nrounds = nr ? nr : c->seated.as<int32_t>(); P.ncal = ncal; P.res = L.res;
   P.xmask = xmask; P.bfmask = bfmask; P.ncap = c->sncap.as<uint8_t>();
   // re-rank local search: O(J T^2) per cancelled cycle — on where that stays in the tens of microseconds
-  P.rr_items = nullptr; P.rr_iters = 0;
+  P.rr_items = nullptr; P.rr_iters = 0; P.prm_T = h_prm[0].future_rounds;
   {
     const size_t T_ = (size_t)h_prm[0].future_rounds;
-    const size_t bytes = (size_t)S * 4 * T_ * T_ * 64;
+    const int cl = (S * 8 <= 144 && J <= SWB_SMEM_JOBS) ? 8 : 1;     // multi-start over a cluster (place.cu)
+    const size_t bytes = (size_t)S * cl * swb::rr_scratch_bytes(J, (int)T_);
+    P.rr_cluster = 1;
     if (c->rr_iters > 0 && (size_t)J * T_ * T_ <= (4u << 20) && bytes <= (512u << 20)) {
       CK(c->rr_items.need(bytes, c->st));
-      P.rr_items = c->rr_items.p; P.rr_iters = c->rr_iters;
+      P.rr_items = c->rr_items.p; P.rr_iters = c->rr_iters; P.rr_cluster = cl;
     }
   }
   int rc2 = ensure_hres(c, S);
@@ -943,7 +945,7 @@ int swb_market_pgd(swb_ctx *c, const swb_market_args *a) {
 int swb_set_option(swb_ctx *c, int32_t option, int32_t value) {
   if (!c) return fail(SWB_ERR_ARG, "null ctx");
   if (option == SWB_OPT_RELAXED_OPTIMUM) { c->want_relaxed = value ? 1 : 0; return 0; }
-  if (option == SWB_OPT_SOLVE_CLUSTER) { swb::set_solve_cluster(value); return 0; }
+  if (option == SWB_OPT_SOLVE_CLUSTER) { swb::set_solve_cluster(value); swb::set_place_cluster(value); return 0; }
   if (option == SWB_OPT_RERANK_ITERS) { c->rr_iters = value < 0 ? 0 : value; return 0; }
   if (option == SWB_OPT_GBM_PATHS) { if (value < 0) return fail(SWB_ERR_ARG, "paths < 0"); c->gbm_paths = value; return 0; }
   if (option == SWB_OPT_GBM_SEED) { c->gbm_seed = (uint64_t)(uint32_t)value; return 0; }

@@ -7,8 +7,9 @@
 //     W_h = sum of h iid N(0,1)   (a running sum = the prefix scan along the path),
 // R0_j the deterministic forecast.  Per job the kernel returns sum_p R^(p) and sum_p (R^(p))^2 over the
 // LOCAL paths; paths shard across GPUs and ONE allreduce of the [2][J] float64 vector follows
-// (SURVEY.md §8e).  Every path's random stream is keyed by (seed, job, GLOBAL path id), so results do
-// not depend on how the paths are sharded (up to float64 summation order).
+// (SURVEY.md §8e).  Random streams are keyed by (seed, job, GLOBAL pair id) — global paths 2q and 2q+1 are an
+// antithetic pair driven by the same normals with opposite signs — so results do not depend on how the paths are
+// sharded (up to float64 summation order).
 // Bound: ALU/SFU (xorshift128+, Box-Muller, exp), not HBM: 40 bytes in and 16 bytes out per job.
 #include <math.h>
 
@@ -55,13 +56,18 @@ __global__ void __launch_bounds__(256) gbm_kernel(GbmLaunch L) {
   const float invH = H > 0 ? 1.0f / (float)H : 0.0f;
   const double R0 = L.R0[j];
   double s1 = 0.0, s2 = 0.0;
-  for (long long p = threadIdx.x; p < L.P_local; p += blockDim.x) {
-    const unsigned long long gp = (unsigned long long)(L.path_offset + p);
-    unsigned long long sm = L.seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(j + 1)) ^ (gp * 0x9E3779B97F4A7C15ull);
+  // ANTITHETIC PAIRS: global paths 2q and 2q+1 share one stream of normals with opposite signs (W and -W) — half
+  // the random numbers, logs, square roots and sin/cos per path, and a lower variance of the mean for free.  A
+  // thread walks whole pairs; a shard boundary that cuts a pair (odd offset / count) simply skips the missing member.
+  const long long first = L.path_offset, last = L.path_offset + L.P_local;     // [first, last)
+  const long long q0 = first >> 1, q1 = (last + 1) >> 1;                         // pair ids touched
+  for (long long q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+    const unsigned long long gq = (unsigned long long)q;
+    unsigned long long sm = L.seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(j + 1)) ^ (gq * 0x9E3779B97F4A7C15ull);
     XorShift128p rng;
     rng.s0 = splitmix64(sm);
     rng.s1 = splitmix64(sm) | 1ull;
-    float W = 0.0f, acc = 0.0f;
+    float W = 0.0f, accA = 0.0f, accB = 0.0f;
     for (int h = 1; h <= H; h += 2) {
       // Box-Muller: two normals per pair of 24-bit uniforms
       const unsigned long long r = rng.next();
@@ -71,15 +77,19 @@ __global__ void __launch_bounds__(256) gbm_kernel(GbmLaunch L) {
       float sn, cs;
       __sincosf(6.283185307179586f * u2, &sn, &cs);
       W += rad * cs;
-      acc += __expf(fmaf(drift, (float)h, sg * W));
+      float dh = drift * (float)h, sw = sg * W;
+      accA += __expf(dh + sw);
+      accB += __expf(dh - sw);
       if (h + 1 <= H) {
         W += rad * sn;
-        acc += __expf(fmaf(drift, (float)(h + 1), sg * W));
+        dh = drift * (float)(h + 1); sw = sg * W;
+        accA += __expf(dh + sw);
+        accB += __expf(dh - sw);
       }
     }
-    const double R = H > 0 ? R0 * (double)(acc * invH) : R0;
-    s1 += R;
-    s2 += R * R;
+    const long long pa = 2 * q, pb = 2 * q + 1;
+    if (pa >= first && pa < last) { const double R = H > 0 ? R0 * (double)(accA * invH) : R0; s1 += R; s2 += R * R; }
+    if (pb >= first && pb < last) { const double R = H > 0 ? R0 * (double)(accB * invH) : R0; s1 += R; s2 += R * R; }
   }
   BlockRed br(red);
   br.sum2(s1, s2);

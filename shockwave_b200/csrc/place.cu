@@ -19,6 +19,7 @@
 #include "swb_common.cuh"
 #include "swb_internal.h"
 #include "rerank.cuh"
+#include <cooperative_groups.h>
 
 namespace swb {
 
@@ -72,8 +73,15 @@ __device__ __forceinline__ int block_excl_scan(int v, int *wsum, int *tot) {
   return off + incl - v;
 }
 
+// CL = 1: one CTA per scenario.  CL = 8 (few scenarios, the re-rank search on): a thread-block cluster per scenario —
+// all 8 CTAs build the same schedule, each runs the re-rank local search from a different noising seed (rank 0: none),
+// the costs meet through distributed shared memory and the CTA with the best schedule carries on alone.
+template <int CL>
 __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch L, unsigned long long *gmask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  namespace cg = cooperative_groups;
+  int crank = 0;
+  if constexpr (CL > 1) crank = (int)cg::this_cluster().block_rank();
   // CTA -> scenario: longest first.  A fallback scenario costs about twice a plain one here (priority sweep), and with
   // two waves of CTAs the launch ends when the slowest SM finishes: CTA b takes the b-th fallback scenario while
   // there are any, then the plain ones (the result does not depend on the mapping).
@@ -85,7 +93,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     for (int i = c0; i < c1; ++i) cnt += (L.res[i].status == SWB_ST_FALLBACK) ? 1 : 0;
     int tot = 0;
     const int pre = block_excl_scan(cnt, s_scan, &tot);
-    const int b = blockIdx.x;
+    const int b = blockIdx.x / CL;
     const bool want_fb = b < tot;
     const int target = want_fb ? b : b - tot;
     const int mypre = want_fb ? pre : (c0 - pre);
@@ -129,9 +137,11 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   unsigned short *ordr = reinterpret_cast<unsigned short *>(p); p += 2 * (size_t)npad;  // jobs by priority density
   p = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
   unsigned long long *xm, *bm;  // [J][2] each
+  unsigned char *rr_smem = nullptr;   // hot arrays of the re-rank search (w_j, dense edge costs): after the masks
   if (J <= SWB_SMEM_JOBS) {
     xm = reinterpret_cast<unsigned long long *>(p);
     bm = xm + 2 * (size_t)J;
+    rr_smem = p + 32 * (size_t)J;
   } else {
     xm = gmask + (size_t)s * 4 * J;
     bm = xm + 2 * (size_t)J;
@@ -509,11 +519,33 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     long long sfl = 0;
     for (int j = threadIdx.x; j < J; j += blockDim.x) sfl += remn[j];
     sfl = br.sumll(sfl);
+    __shared__ double s_rr_cost;
+    if (threadIdx.x == 0) s_rr_cost = 1e300;
+    __syncthreads();
     if (sfl == 0) {
-      rr_cycles = rr_local_search(reinterpret_cast<RrTop2 *>(L.rr_items) + (size_t)s * RR_MAXCLS * T * T, xm, gs, remn,
-                                  nplan, L.weights + so, idle, J, T, L.rr_iters);
+      rr_cycles = rr_local_search(reinterpret_cast<unsigned char *>(L.rr_items) +
+                                      ((size_t)s * CL + crank) * rr_scratch_bytes(J, T), rr_smem,
+                                  xm, gs, remn, nplan, L.weights + so, idle, J, T, L.rr_iters,
+                                  crank == 0 ? 0u : (unsigned)(crank * 7919 + 13), &s_rr_cost);
       __syncthreads();
     }
+    if constexpr (CL > 1) {
+      // best of the cluster's 8 searches carries on; the others are done (two barriers: nobody leaves while its
+      // cost may still be read)
+      cg::cluster_group cl = cg::this_cluster();
+      cl.sync();
+      int win = 0;
+      double bestc = *cl.map_shared_rank(&s_rr_cost, 0);
+      for (int r = 1; r < CL; ++r) {
+        const double cr = *cl.map_shared_rank(&s_rr_cost, r);
+        if (cr < bestc) { bestc = cr; win = r; }
+      }
+      cl.sync();
+      if (crank != win) return;
+      rr_cycles |= win << 12;          // reported in swb_result.flags: which start won
+    }
+  } else {
+    if constexpr (CL > 1) { if (crank != 0) return; }
   }
 
   Pwl P;
@@ -747,6 +779,9 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   }
 }
 
+static int g_place_cl = 8;
+void set_place_cluster(int v) { g_place_cl = (v == 8) ? 8 : 1; }
+
 cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask) {
   int npad = 64;
   while (npad < L.J) npad <<= 1;
@@ -760,15 +795,47 @@ cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long lo
   bool &attr_set = attr_done[dev_ & 63];
   if (!attr_set) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, place_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&fa, place_kernel<1>);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(place_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SWB_MAX_DYN_SMEM - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&fa, place_kernel<8>);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(place_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SWB_MAX_DYN_SMEM - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   int nt = npad < SWB_PLACE_THREADS ? npad : SWB_PLACE_THREADS;
-  place_kernel<<<L.S, nt, smem, st>>>(L, gmask);
+  // re-rank search: its hot arrays (w_j, one dense (T+1)^2 cost matrix per width class) live in shared memory behind
+  // the round masks; when they do not fit the search is left out.  It wants a thread per ordered pair of rounds.
+  PlaceLaunch L2 = L;
+  if (L2.rr_items && L2.rr_iters > 0) {
+    const size_t N = (size_t)L.prm_T + 1;
+    const size_t need = (size_t)L.J * 8 + RR_MAXCLS * N * N * 8 + 16;
+    int stat = 0;
+    { cudaFuncAttributes fa; if (cudaFuncGetAttributes(&fa, place_kernel<1>) == cudaSuccess) stat = (int)fa.sharedSizeBytes; }
+    if (L.J <= SWB_SMEM_JOBS && smem + need + (size_t)stat <= (size_t)SWB_MAX_DYN_SMEM) {
+      smem += need;
+      if (nt < 512) nt = 512;
+    } else {
+      L2.rr_items = nullptr; L2.rr_iters = 0;
+    }
+  }
+  // multi-start re-rank: a cluster of 8 CTAs per scenario when the search is on, the masks live in shared memory
+  // and the launch still fits one wave of SMs
+  if (L2.rr_cluster == 8 && g_place_cl == 8 && L2.rr_items && L2.rr_iters > 0 && L.S * 8 <= 144) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(L.S * 8)); cfg.blockDim = dim3((unsigned)nt);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, place_kernel<8>, L2, gmask);
+  }
+  place_kernel<1><<<L.S, nt, smem, st>>>(L2, gmask);
   return cudaGetLastError();
 }
 

@@ -13,85 +13,118 @@
 // A negative cycle of one width class leaves every round's load unchanged (or moves load into idle GPUs through the
 // slack node) and lowers the objective by its (negative) cost; for unit widths cancelling until none is left is the
 // exact min-cost-flow optimum, for mixed widths it is a local optimum of a neighbourhood that contains every
-// same-class exchange chain and the nested cross-class ones.  Bellman-Ford on <= 129 nodes, one warp per width class.
-// Measured on the 128 recorded fallback solves of the canonical trace (exact re-rank MILP of the same counts as the
-// yardstick): excess median 0, p90 1e-3, max 7e-3 (sweep alone: median 2e-3, p90 1.4e-2, max 4.4e-2).
+// same-class exchange chain and the nested cross-class ones.  Per cancelled cycle: one pass over (round pair, job)
+// (a thread per ordered pair, the job's round masks broadcast from shared memory) and one Bellman-Ford on <= 129 nodes
+// per width class (one warp each, Jacobi sweeps over a dense cost matrix in L2).
+// Multi-start ("noising"): with a seed the first <= 24 cycles are cancelled under weights perturbed by +-30 %, which
+// lands the search in another basin; place.cu runs 8 seeds in a thread-block cluster and keeps the best result.
 #pragma once
 #include "swb_common.cuh"
 #include "swb_internal.h"
 
 namespace swb {
 
-#define RR_MAXCLS 4
-#define RR_ITEMJOBS 8
 
-struct RrItem {               // 32 bytes
-  double cost;
-  unsigned short n;
-  unsigned short job[RR_ITEMJOBS];
-  unsigned short pad[3];
+// scratch of one search (global memory, L2 resident): sized by rr_scratch_bytes()
+struct RrScratch {
+  double *wj;              // [J] w_j = prio_j / n_j (0: job not movable)
+  double *cost;            // [RR_MAXCLS][N*N] dense edge costs, N = T + 1, row u -> column v
+  unsigned short *jobs;    // [RR_MAXCLS][T*T][RR_ITEMJOBS] jobs of the best item of every (class, pair)
+  unsigned char *nj;       // [RR_MAXCLS][T*T] number of jobs of that item
 };
-
-struct RrTop2 { RrItem it[2]; };   // best and second best item of one (pair, class), disjoint job sets
-
-__device__ __forceinline__ void rr_insert(RrItem &b0, RrItem &b1, const RrItem &x) {
-  if (x.cost < b0.cost) { b1 = b0; b0 = x; }
-  else if (x.cost < b1.cost) b1 = x;
+// hot: w_j and the dense cost matrices in SHARED memory (hot != null), else in the global scratch
+__device__ __forceinline__ RrScratch rr_carve(unsigned char *base, unsigned char *hot, int J, int T) {
+  const size_t N = (size_t)T + 1, TT = (size_t)T * T;
+  RrScratch s;
+  s.wj = reinterpret_cast<double *>(base); base += (size_t)J * 8;
+  s.cost = reinterpret_cast<double *>(base); base += RR_MAXCLS * N * N * 8;
+  s.jobs = reinterpret_cast<unsigned short *>(base); base += RR_MAXCLS * TT * RR_ITEMJOBS * 2;
+  s.nj = base;
+  if (hot) {
+    hot = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hot) + 15) & ~uintptr_t(15));
+    s.wj = reinterpret_cast<double *>(hot);
+    s.cost = s.wj + J;
+  }
+  return s;
 }
 
-// Builds, for every ordered pair of rounds and every width class, the best two items.  One thread per pair.
-__device__ void rr_build_items(RrTop2 *items, const unsigned long long *xm, const unsigned char *gs,
-                               const unsigned char *remn, const unsigned char *nplan, const double *prio, int J, int T,
-                               const int *clsw, int ncls) {
+__device__ __forceinline__ double rr_noise(int j, unsigned seed) {
+  if (seed == 0u) return 1.0;
+  unsigned h = (unsigned)j * 0x9E3779B1u ^ seed * 0x85EBCA77u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return 1.0 + 0.3 * ((double)(h & 0xffffffu) * (2.0 / 16777215.0) - 1.0);
+}
+
+struct RrItem { double cost; int n; unsigned short job[RR_ITEMJOBS]; };
+
+// Edge costs and best items of every ordered pair of rounds and every width class.  One thread per pair; the inner
+// loop over the jobs keeps the two cheapest SINGLE jobs per class in registers (cls_of[] maps a width to its class).
+__device__ void rr_build(const RrScratch &S, const unsigned long long *xm, const unsigned char *gs,
+                         const unsigned char *cls_of, const int *clsw, int ncls, const int *idle, int J, int T,
+                         unsigned noise_seed) {
   const double INF = 1e300;
-  for (int pr = threadIdx.x; pr < T * T; pr += blockDim.x) {
-    const int a = pr / T, c = pr - a * T;
-    RrItem best[RR_MAXCLS][2];
-#pragma unroll
-    for (int k = 0; k < RR_MAXCLS; ++k) { best[k][0].cost = INF; best[k][0].n = 0; best[k][1].cost = INF; best[k][1].n = 0; }
-    if (a != c) {
-      const int wa = a >> 6, wc = c >> 6;
-      const unsigned long long ba = 1ull << (a & 63), bc = 1ull << (c & 63);
-      const double dist = (double)(c - a);
-      for (int j = 0; j < J; ++j) {
-        if (!(xm[2 * j + wa] & ba) || (xm[2 * j + wc] & bc)) continue;
-        const int n = nplan[j];
-        if (n == 0 || remn[j] != 0) continue;
-        const int g = gs[j];
-        int k = -1;
-#pragma unroll
-        for (int q = 0; q < RR_MAXCLS; ++q) if (q < ncls && clsw[q] == g) k = q;
-        if (k < 0) continue;
-        RrItem x;
-        x.cost = prio[j] / (double)n * dist; x.n = 1; x.job[0] = (unsigned short)j;
-#pragma unroll
-        for (int q = 0; q < RR_MAXCLS; ++q) if (q == k) rr_insert(best[q][0], best[q][1], x);
+  const int N = T + 1;
+  for (int pr = threadIdx.x; pr < N * N; pr += blockDim.x) {
+    const int a = pr / N, c = pr - a * N;
+    if (a == T || c == T || a == c) {
+      // slack edges and the diagonal
+      for (int k = 0; k < ncls; ++k) {
+        double v = INF;
+        if (a == T && c != T) v = 0.0;
+        else if (c == T && a != T) v = (idle[a] >= clsw[k]) ? 0.0 : INF;
+        S.cost[(size_t)k * N * N + pr] = v;
       }
-      // composites: two disjoint items of half the width (nested gang widths)
-#pragma unroll
-      for (int k = 1; k < RR_MAXCLS; ++k) {
-        if (k < ncls && clsw[k] == 2 * clsw[k - 1] && best[k - 1][1].cost < INF &&
-            best[k - 1][0].n + best[k - 1][1].n <= RR_ITEMJOBS) {
-          RrItem x;
-          x.cost = best[k - 1][0].cost + best[k - 1][1].cost;
-          x.n = (unsigned short)(best[k - 1][0].n + best[k - 1][1].n);
-          for (int q = 0; q < best[k - 1][0].n; ++q) x.job[q] = best[k - 1][0].job[q];
-          for (int q = 0; q < best[k - 1][1].n; ++q) x.job[best[k - 1][0].n + q] = best[k - 1][1].job[q];
-          rr_insert(best[k][0], best[k][1], x);
-        }
-      }
+      continue;
     }
+    double c0[RR_MAXCLS], c1[RR_MAXCLS];
+    int j0[RR_MAXCLS], j1[RR_MAXCLS];
 #pragma unroll
-    for (int k = 0; k < RR_MAXCLS; ++k)
-      if (k < ncls) { items[(size_t)k * T * T + pr].it[0] = best[k][0]; items[(size_t)k * T * T + pr].it[1] = best[k][1]; }
+    for (int k = 0; k < RR_MAXCLS; ++k) { c0[k] = INF; c1[k] = INF; j0[k] = -1; j1[k] = -1; }
+    const int wa = a >> 6, wc = c >> 6;
+    const unsigned long long ba = 1ull << (a & 63), bc = 1ull << (c & 63);
+    const double dist = (double)(c - a);
+    for (int j = 0; j < J; ++j) {
+      if (!(xm[2 * j + wa] & ba) || (xm[2 * j + wc] & bc)) continue;
+      const double w = S.wj[j];
+      if (w == 0.0) continue;
+      const int k = cls_of[gs[j]];
+      if (k >= RR_MAXCLS) continue;
+      const double x = w * dist * rr_noise(j, noise_seed);
+#pragma unroll
+      for (int q = 0; q < RR_MAXCLS; ++q)
+        if (q == k) {
+          if (x < c0[q]) { c1[q] = c0[q]; j1[q] = j0[q]; c0[q] = x; j0[q] = j; }
+          else if (x < c1[q]) { c1[q] = x; j1[q] = j; }
+        }
+    }
+    // best / second-best ITEM per class: singles, plus the composite of the two best items of half the width
+    RrItem b0, b1;                       // of the previous class
+    b0.cost = INF; b0.n = 0; b1.cost = INF; b1.n = 0;
+    const int tp = a * T + c;
+#pragma unroll
+    for (int k = 0; k < RR_MAXCLS; ++k) {
+      if (k >= ncls) break;
+      RrItem n0, n1;
+      n0.cost = c0[k]; n0.n = j0[k] >= 0 ? 1 : 0; n0.job[0] = (unsigned short)j0[k];
+      n1.cost = c1[k]; n1.n = j1[k] >= 0 ? 1 : 0; n1.job[0] = (unsigned short)j1[k];
+      if (k > 0 && clsw[k] == 2 * clsw[k - 1] && b1.cost < INF && b0.n + b1.n <= RR_ITEMJOBS) {
+        RrItem x;
+        x.cost = b0.cost + b1.cost; x.n = b0.n + b1.n;
+        for (int q = 0; q < b0.n; ++q) x.job[q] = b0.job[q];
+        for (int q = 0; q < b1.n; ++q) x.job[b0.n + q] = b1.job[q];
+        if (x.cost < n0.cost) { n1 = n0; n0 = x; } else if (x.cost < n1.cost) n1 = x;
+      }
+      S.cost[(size_t)k * N * N + pr] = n0.cost;
+      S.nj[(size_t)k * T * T + tp] = (unsigned char)n0.n;
+      for (int q = 0; q < n0.n; ++q) S.jobs[((size_t)k * T * T + tp) * RR_ITEMJOBS + q] = n0.job[q];
+      b0 = n0; b1 = n1;
+    }
   }
 }
 
-// One warp: Bellman-Ford (Jacobi sweeps, double-buffered distances) from a virtual source on the class's round graph;
-// returns the length of a negative cycle written to cyc[] (nodes in forward order), 0 if there is none.
-// d: 2 x (T+1) doubles, pred: T+1 shorts of scratch.
-__device__ int rr_find_cycle(const RrTop2 *items_k, const int *idle, int width, int T, double *d, short *pred,
-                             short *cyc, double tol) {
+// One warp: Bellman-Ford (Jacobi sweeps, double-buffered distances) from a virtual source on one class's dense cost
+// matrix; returns the length of a negative cycle written to cyc[] (nodes in forward order), 0 if there is none.
+__device__ int rr_find_cycle(const double *cost, int T, double *d, short *pred, short *cyc, double tol) {
   const int lane = threadIdx.x & 31, N = T + 1;
   const double INF = 1e300;
   double *dold = d, *dnew = d + (SWB_MAX_T + 1);
@@ -104,11 +137,7 @@ __device__ int rr_find_cycle(const RrTop2 *items_k, const int *idle, int width, 
       double dv = dold[v];
       int pv = -2;
       for (int u = 0; u < N; ++u) {
-        if (u == v) continue;
-        double cuv;
-        if (u == T) cuv = 0.0;                                       // slack -> round v
-        else if (v == T) cuv = (idle[u] >= width) ? 0.0 : INF;       // round u -> slack (idle GPUs absorb the item)
-        else cuv = items_k[u * T + v].it[0].cost;
+        const double cuv = cost[u * N + v];
         if (cuv >= INF * 0.5) continue;
         const double cand = dold[u] + cuv;
         if (cand < dv - tol) { dv = cand; pv = u; }
@@ -121,38 +150,82 @@ __device__ int rr_find_cycle(const RrTop2 *items_k, const int *idle, int width, 
     double *t = dold; dold = dnew; dnew = t;
     last = changed;
     if (changed < 0) return 0;
-  }
-  // a relaxation in the N-th sweep: `last` hangs off a negative cycle of the predecessor graph; N steps back land on it
-  int len = 0;
-  if (lane == 0) {
-    int x = last;
-    for (int q = 0; q < N && x >= 0; ++q) x = pred[x];
-    if (x >= 0) {
-      int cur = x, guard = 0;
-      do { cyc[len++] = (short)cur; cur = pred[cur]; } while (cur != x && cur >= 0 && ++guard <= N);
-      if (cur != x) len = 0;
-      for (int q = 0; q < len / 2; ++q) { const short t2 = cyc[q]; cyc[q] = cyc[len - 1 - q]; cyc[len - 1 - q] = t2; }
+    // A negative cycle shows up in the predecessor graph long before the N-th sweep: every 4th sweep (and at the
+    // end) walk back from the last relaxed node; a node met twice closes a cycle, which is returned if its cost is
+    // negative (the caller re-verifies with compensated summation).
+    if ((it & 3) == 3 || it == N - 1) {
+      int len = 0;
+      if (lane == 0) {
+        int x = last;
+        for (int q = 0; q < N && x >= 0; ++q) x = pred[x];
+        if (x >= 0) {
+          int cur = x, guard = 0;
+          double tot = 0.0;
+          do {
+            cyc[len++] = (short)cur;
+            const int pu = pred[cur];
+            if (pu < 0) break;
+            tot += cost[pu * N + cur];
+            cur = pu;
+          } while (cur != x && ++guard <= N);
+          if (cur != x || !(tot < -tol)) len = 0;
+          for (int q = 0; q < len / 2; ++q) { const short t2 = cyc[q]; cyc[q] = cyc[len - 1 - q]; cyc[len - 1 - q] = t2; }
+        }
+      }
+      len = __shfl_sync(SWB_FULL, len, 0);
+      __syncwarp();
+      if (len >= 2) return len;
     }
   }
-  len = __shfl_sync(SWB_FULL, len, 0);
-  __syncwarp();
-  return len;
+  return 0;
+}
+
+// sum_j w_j * (sum of the round indices of job j); every thread gets the result.  part: 32 doubles of shared scratch.
+__device__ double rr_objective(const RrScratch &S, const unsigned long long *xm, int J, double *part) {
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    const double w = S.wj[j];
+    if (w == 0.0) continue;
+    int st = 0;
+    for (int wi = 0; wi < 2; ++wi) {
+      unsigned long long m = xm[2 * j + wi];
+      while (m) { st += 64 * wi + (__ffsll((long long)m) - 1); m &= m - 1; }
+    }
+    acc += w * (double)st;
+  }
+  acc = warp_sum(acc);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  double tot = 0.0;
+  for (int q = 0; q < (int)((blockDim.x + 31) >> 5); ++q) tot += part[q];
+  __syncthreads();
+  return tot;
 }
 
 // The local search.  All threads of the CTA call it.  xm: [J][2] round masks (in/out); idle: [T] (in/out).
-// Returns the number of cancelled cycles.
-__device__ __noinline__ int rr_local_search(RrTop2 *items, unsigned long long *xm, const unsigned char *gs,
+// Returns the number of cancelled cycles; *final_cost = objective of the result under the true weights.
+__device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned char *hot, unsigned long long *xm,
+                                            const unsigned char *gs,
                                             const unsigned char *remn, const unsigned char *nplan, const double *prio,
-                                            int *idle, int J, int T, int max_iters) {
+                                            int *idle, int J, int T, int max_iters, unsigned noise_seed,
+                                            double *final_cost) {
   __shared__ double ws_d[RR_MAXCLS * 2 * (SWB_MAX_T + 1)];
   __shared__ short ws_pred[RR_MAXCLS * (SWB_MAX_T + 1)];
   __shared__ short ws_cyc[RR_MAXCLS * (SWB_MAX_T + 2)];
-  // width classes: the (up to 4) distinct widths among the placed jobs, ascending
+  __shared__ unsigned char s_clsof[256];
   __shared__ int s_cls[RR_MAXCLS], s_ncls, s_found, s_len[RR_MAXCLS];
-  __shared__ double s_scale;
+  __shared__ double s_part[32];
+  const RrScratch S = rr_carve(scratch, hot, J, T);
+  const int N = T + 1;
+  for (int j = threadIdx.x; j < J; j += blockDim.x)
+    S.wj[j] = (nplan[j] > 0 && remn[j] == 0 && isfinite(prio[j])) ? prio[j] / (double)nplan[j] : 0.0;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_clsof[i] = 255;
+  __syncthreads();
   if (threadIdx.x == 0) {
+    // width classes: the (up to 4) distinct widths among the placed jobs, ascending
     int n = 0, w[RR_MAXCLS];
-    for (int j = 0; j < J && n <= RR_MAXCLS; ++j) {
+    for (int j = 0; j < J; ++j) {
       if (nplan[j] == 0) continue;
       const int g = gs[j];
       bool seen = false;
@@ -161,26 +234,28 @@ __device__ __noinline__ int rr_local_search(RrTop2 *items, unsigned long long *x
     }
     if (n > RR_MAXCLS) n = 0;                     // more than 4 distinct widths: leave the sweep's schedule as it is
     for (int q = 1; q < n; ++q) for (int r = q; r > 0 && w[r - 1] > w[r]; --r) { int t = w[r]; w[r] = w[r - 1]; w[r - 1] = t; }
-    for (int q = 0; q < n; ++q) s_cls[q] = w[q];
+    for (int q = 0; q < n; ++q) { s_cls[q] = w[q]; s_clsof[w[q]] = (unsigned char)q; }
     s_ncls = n;
-    double mx = 0.0;
-    for (int j = 0; j < J; ++j) if (nplan[j] > 0 && isfinite(prio[j])) mx = fmax(mx, prio[j] / (double)nplan[j]);
-    s_scale = mx * (double)T;
   }
   __syncthreads();
   const int ncls = s_ncls;
-  if (ncls == 0) return 0;
+  if (ncls == 0) { if (threadIdx.x == 0) *final_cost = 1e300; __syncthreads(); return 0; }
+  // scale of the tolerances: the CURRENT objective (not the largest weight: a job whose priority is 1e12 times the
+  // others' sits in round 0 and contributes nothing, while exchanges among the ordinary jobs still move the objective)
+  const double scale = fmax(rr_objective(S, xm, J, s_part), 1e-300);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int done = 0;
+  // phase 0 (only with a noise seed): up to 24 cycles under perturbed weights, to reach another basin;
+  // phase 1: true weights until no negative cycle is left (or the budget is spent)
+  int phase = noise_seed ? 0 : 1, phase_iters = 0;
   for (int iter = 0; iter < max_iters; ++iter) {
-    rr_build_items(items, xm, gs, remn, nplan, prio, J, T, s_cls, ncls);
+    rr_build(S, xm, gs, s_clsof, s_cls, ncls, idle, J, T, phase == 0 ? noise_seed : 0u);
     if (threadIdx.x == 0) s_found = -1;
     __syncthreads();
-    if (warp < ncls) {
-      const int len = rr_find_cycle(items + (size_t)warp * T * T, idle, s_cls[warp], T,
-                                    ws_d + warp * 2 * (SWB_MAX_T + 1), ws_pred + warp * (SWB_MAX_T + 1),
-                                    ws_cyc + warp * (SWB_MAX_T + 2), 1e-13 * s_scale);
-      if (lane == 0) s_len[warp] = len;
+    for (int k = warp; k < ncls; k += (int)(blockDim.x >> 5)) {       // one warp per width class
+      const int len = rr_find_cycle(S.cost + (size_t)k * N * N, T, ws_d + k * 2 * (SWB_MAX_T + 1),
+                                    ws_pred + k * (SWB_MAX_T + 1), ws_cyc + k * (SWB_MAX_T + 2), 1e-11 * scale);
+      if (lane == 0) s_len[k] = len;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -189,24 +264,29 @@ __device__ __noinline__ int rr_local_search(RrTop2 *items, unsigned long long *x
         const int len = s_len[k];
         if (len < 2) continue;
         const short *cyc = ws_cyc + k * (SWB_MAX_T + 2);
-        const RrTop2 *itk = items + (size_t)k * T * T;
-        double tot = 0.0;
+        const double *ck = S.cost + (size_t)k * N * N;
+        // gain of the cycle, Neumaier-compensated: edge costs span many decades and a huge +X / -X pair must
+        // cancel exactly instead of leaving rounding noise that looks like an improvement
+        double tot = 0.0, comp = 0.0;
         bool ok = true;
         for (int q = 0; q < len && ok; ++q) {
           const int u = cyc[q], v = cyc[(q + 1) % len];
-          if (u == T) continue;
-          if (v == T) { ok = idle[u] >= s_cls[k]; continue; }
-          const RrItem &it = itk[u * T + v].it[0];
-          if (it.cost >= 1e299) ok = false; else tot += it.cost;
+          const double x = ck[u * N + v];
+          if (x >= 1e299) { ok = false; break; }
+          const double t2 = tot + x;
+          comp += (fabs(tot) >= fabs(x)) ? (tot - t2) + x : (x - t2) + tot;
+          tot = t2;
         }
-        if (!ok || !(tot < -1e-12 * s_scale)) continue;
+        tot += comp;
+        if (!ok || !(tot < -1e-11 * scale)) continue;
         for (int q = 0; q < len; ++q) {
           const int u = cyc[q], v = cyc[(q + 1) % len];
           if (u == T) { idle[v] += s_cls[k]; continue; }           // v loses an item that no cycle edge brings back
           if (v == T) { idle[u] -= s_cls[k]; continue; }           // u keeps an item: its idle GPUs take it
-          const RrItem &it = itk[u * T + v].it[0];
-          for (int e = 0; e < it.n; ++e) {
-            const int j = it.job[e];
+          const size_t tp = (size_t)k * T * T + (size_t)u * T + v;
+          const int nj = S.nj[tp];
+          for (int e = 0; e < nj; ++e) {
+            const int j = S.jobs[tp * RR_ITEMJOBS + e];
             xm[2 * j + (u >> 6)] &= ~(1ull << (u & 63));
             xm[2 * j + (v >> 6)] |= 1ull << (v & 63);
           }
@@ -215,9 +295,14 @@ __device__ __noinline__ int rr_local_search(RrTop2 *items, unsigned long long *x
       }
     }
     __syncthreads();
+    ++phase_iters;
+    if (phase == 0 && (s_found < 0 || phase_iters >= 24)) { phase = 1; continue; }
     if (s_found < 0) break;
     ++done;
   }
+  const double fc = rr_objective(S, xm, J, s_part);
+  if (threadIdx.x == 0) *final_cost = fc;
+  __syncthreads();
   return done;
 }
 

@@ -52,13 +52,24 @@ struct PlaceLaunch {
   int32_t *ncal;          // [S][J] out, may be null: rounds with idle GPUs in which the job is unscheduled
   swb_result *res;        // device [S] (status in, objective/shortfall updated)
   uint8_t *ncap;          // [S][J] in/out, may be null: per-job count caps for the next pass (packing feedback)
-  void *rr_items;         // scratch of the re-rank local search, S x 4 x T x T x 64 B (null: search off)
+  void *rr_items;         // scratch of the re-rank local search, S x rr_cluster x rr_scratch_bytes(J, T) (null: off)
   int rr_iters;           // cycle-cancelling budget per scenario
+  int prm_T;              // future_rounds of the call (host copy, for sizing)
+  int rr_cluster;         // 8: rr_items holds 8 regions per scenario (multi-start over a thread-block cluster), else 1
 };
 
 cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st, int nbases);
 void set_solve_cluster(int ctas_per_scenario);
+// scratch of one re-rank local search (rerank.cuh): w_j, dense edge costs per width class, best items per (class, pair)
+#define RR_MAXCLS 4
+#define RR_ITEMJOBS 8
+__host__ __device__ inline size_t rr_scratch_bytes(int J, int T) {
+  const size_t N = (size_t)T + 1, TT = (size_t)T * T;
+  size_t b = (size_t)J * 8 + RR_MAXCLS * N * N * 8 + RR_MAXCLS * TT * RR_ITEMJOBS * 2 + RR_MAXCLS * TT;
+  return (b + 255) & ~(size_t)255;
+}
 cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask);
+void set_place_cluster(int ctas_per_scenario);
 
 struct ForecastLaunch {
   int J;

@@ -90,6 +90,7 @@ def test_cluster_solve_equals_single_cta_solve(engine, J, G, T, k):
     """Latency path: a cluster of 8 CTAs shares one scenario (DSMEM reductions in rank order).  Same searches on the
     same step functions -> the same round counts as the one-CTA kernel; the objective may differ in the last bits
     (summation order)."""
+    engine.set_option(6, 0)        # re-rank search off: with it the cluster size also selects single / multi-start placement
     for seed, tight in ((0, 3.0), (1, 0.5)):
         pb = synth_problem(J, G, T, 120.0, seed=seed, tight=tight)
         prm = make_params(G, T, 120.0, k, 12.0, 1.0, fx.BASES, fx.ORIGIN, round_ptr=pb["round_ptr"])
@@ -103,3 +104,4 @@ def test_cluster_solve_equals_single_cta_solve(engine, J, G, T, k):
         assert np.array_equal(a["nrounds"], b["nrounds"])
         assert np.array_equal(a["x"], b["x"])
         assert abs(a["results"][0]["objective"] - b["results"][0]["objective"]) <= 1e-9 * abs(a["results"][0]["objective"])
+    engine.set_option(6, 400)

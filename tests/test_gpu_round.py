@@ -97,12 +97,12 @@ def test_scheduler_class_replay():
         assert list(sw.metadata.keys()) == live
         for k, jid in enumerate(live):
             job = sw.metadata[jid]
-            sw.schedule_progress(jid, int(s["c"][k]))
-            tl = job.throughput_measurements
+            tl = job.throughput_measurements     # the simulator records the measurement first (scheduler.py:555-571) ...
             tl.clear()
             if s["meas_end"][k] >= 0:   # a 1-entry timeline with the same (nsamples, end_round) summary
                 end = int(s["meas_end"][k])
                 tl[end] = (float(s["meas_ns"][k]) / (job.gavel_round_duration * end), 1.0)
+            sw.schedule_progress(jid, int(s["c"][k]))      # ... and then reports progress (:2274-2341)
         sw.round_ptr = s["round_ptr"]
         sw.reestimate_share = s["reestimate"]
         sw.set_resolve()
@@ -122,3 +122,39 @@ def test_scheduler_class_replay():
     # the class drives its own calibration continuation (its x differs from the oracle's), so a
     # borderline verdict may flip late in the replay; require near-total agreement
     assert agree >= 0.95 * total
+
+
+def test_dirty_tracking_equals_exact_rereading():
+    """timeline_check="dirty" (summaries refreshed in schedule_progress, O(1) per call) and "exact" (every job re-read
+    at every re-solve) must produce the same forecasts and schedules when the caller follows the simulator's order
+    (measurement first, then schedule_progress)."""
+    G, T, D = fx.TACC["G"], fx.TACC["T"], fx.TACC["D"]
+    st = fx.job_statics()
+    outs = []
+    for mode in ("dirty", "exact"):
+        sw = ShockwaveScheduler(ngpus=G, gram=16, init_metadata=OrderedDict(), future_nrounds=T, round_duration=int(D),
+                                solver_preference=["GUROBI"], solver_rel_gap=1e-3, solver_num_threads=24,
+                                solver_timeout=15, n_epoch_vars_max=30, logapx_bases=fx.BASES, logapx_origin=fx.ORIGIN,
+                                k=fx.TACC["k"], lam=fx.TACC["lam"], rhomax=fx.TACC["rhomax"], timeline_check=mode)
+        rec = []
+        rng = np.random.default_rng(3)
+        jids = sorted(st.keys())[:60]
+        for r in range(25):
+            for jid in jids[: 10 + 2 * r]:
+                if jid not in sw.metadata:
+                    sw.add_metadata(jid, _Job(jid, st[jid]))
+            ids = sw.round_schedule()
+            rec.append((list(ids), sw.last_forecast["rem"].copy() if sw.resolve is False and hasattr(sw, "last_forecast") else None))
+            for jid in ids:
+                job = sw.metadata[jid]
+                job.throughput_measurements[r + 1] = (float(rng.uniform(1, 30)), 32)
+                sw.schedule_progress(jid, min(job.epochs, job.epoch_progress + int(rng.integers(0, 3))))
+            if r % 7 == 6 and len(sw.metadata) > 5:
+                sw.remove_metadata(list(sw.metadata.keys())[2])
+            sw.increment_round_ptr()
+            if r % 3 == 2:
+                sw.set_resolve()
+        outs.append(rec)
+    for (a_ids, a_rem), (b_ids, b_rem) in zip(*outs):
+        assert a_ids == b_ids
+        assert (a_rem is None) == (b_rem is None) and (a_rem is None or np.array_equal(a_rem, b_rem))

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 LOGV = om.pwl_log_values(fx.BASES, fx.ORIGIN)
 
 
-def check_against(out, s, pb, G, T, D, k, ora_obj, ora_status, tol=1e-3):
+def check_against(out, s, pb, G, T, D, k, ora_obj, ora_status, tol=1e-3, ora_x=None, ora_w=None):
     res = out["results"][s]
     x = out["x"][s]
     w = out["weights"][s]
@@ -29,6 +29,13 @@ def check_against(out, s, pb, G, T, D, k, ora_obj, ora_status, tol=1e-3):
     assert np.array_equal(n.astype(np.int32), out["nrounds"][s])
     assert abs(obj - res["objective"]) <= 1e-9 * max(1.0, abs(obj)), (obj, res["objective"])
     assert obj >= ora_obj - tol * abs(ora_obj) - 1e-12, (obj, ora_obj, res)
+    if ora_x is not None:
+        # at k >= 10 the objective is ~ -k * makespan (1e6) and the relative gate above says nothing about the welfare
+        # term (~ -250): whenever the makespans agree, the welfare itself must be within the reference's gap too
+        _, o_welf, o_M, _, _ = om.evaluate(ora_x, pb["g"], pb["E"].astype(float), pb["c"].astype(float), pb["dbar"],
+                                           pb["rem"], w if ora_w is None else ora_w, G, T, D, k, fx.BASES, LOGV)
+        if abs(M - o_M) <= 1e-9 * max(1.0, o_M):
+            assert welfare >= o_welf - tol * abs(o_welf) - 1e-12, (welfare, o_welf, M, o_M)
     # back-fill never overlaps the solver's schedule and never exceeds capacity
     bf = out["backfill"][s]
     assert not np.any(bf & x)
@@ -80,7 +87,7 @@ def test_fallback_rerank_quality(engine):
         ry, rg = om.rank_objective(y, w), om.rank_objective(x, w)
         assert np.array_equal(np.asarray(y).sum(axis=1).round().astype(int), x.sum(axis=1))
         exc.append((rg - ry) / max(1e-12, abs(ry)))
-        cycles.append(out["results"][0]["flags"] >> 8)
+        cycles.append((out["results"][0]["flags"] >> 8) & 0xfff)
         engine.set_option(6, 0)                              # the sweep alone, same counts
         x0 = engine.solve(prm, s["g"], s["E"], s["c"], s["dbar"], s["rem"], s["ftobj"], bfkey=s["rem"])["x"][0]
         engine.set_option(6, 400)
@@ -119,7 +126,8 @@ def test_synthetic_vs_live_oracle(engine, J, G, T, k, tight):
                                         time_limit=60.0, do_rank=False)
         # J=8 on 8 GPUs with gangs as wide as the cluster is a pure integer knapsack: the exact MILP
         # beats the price-based counts by a few 1e-3 there; every realistic size holds the 1e-3 gap
-        check_against(out, 0, pb, G, T, D, k, ora["objective"], ora["status"], tol=5e-3 if J <= 8 else 1e-3)
+        check_against(out, 0, pb, G, T, D, k, ora["objective"], ora["status"], tol=5e-3 if J <= 8 else 1e-3,
+                      ora_x=ora["x"], ora_w=ora["weights"])
 
 
 def test_relaxation_optimum_matches_highs_lp(engine):
