@@ -471,7 +471,7 @@ def same_algorithm_cpu(nscn=None):
     the B200 buys.  Counts only (no placement / back-fill), float64."""
     from oracle import price_search as ps
     from oracle import shockwave_milp as om
-    ncpu = os.cpu_count() or 1
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     S = nscn or max(8, min(2 * ncpu, 256))
     pbs = [scenario(i) for i in range(S)]
     st = lambda key: np.stack([p[0][key] for p in pbs])

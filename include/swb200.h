@@ -93,7 +93,7 @@ int swb_sync(swb_ctx *ctx);
  * SWB_OPT_GBM_HORIZON: horizon cap in epochs (default 256). */
 /* SWB_OPT_RERANK_ITERS: budget (cancelled cycles per scenario) of the local search that follows the priority round-sweep
  * of the fallback re-rank (rank_in_schedule_jobs, shockwave.py:714-793); 0 = sweep only.  Default 400.  The search runs
- * when jobs x rounds^2 <= 4 Mi (e.g. 10 000 jobs at 20 rounds, 1024 jobs at 64 rounds); swb_result.flags >> 8 = cycles
+ * when jobs x rounds^2 <= 256 Ki (e.g. 640 jobs at 20 rounds, 250 at 32); swb_result.flags >> 8 = cycles
  * cancelled (bits 8-19), >> 20 = which of the 8 starts of the multi-start search won (0 = the un-noised one; the search
  * runs 8 starts in a thread-block cluster when at most 18 scenarios of <= 4096 jobs are placed per call). */
 #define SWB_OPT_RERANK_ITERS 6

@@ -44,7 +44,7 @@ def main(tag):
                 out.append(f"   {h} = {v} {u}")
                 row[h] = _num(v, u)
         rd, wr = row.get("dram__bytes_read.sum"), row.get("dram__bytes_write.sum")
-        kernels[name] = {"capture": os.path.basename(rep), "duration_us": row.get("gpu__time_duration.sum"),
+        kernels[os.path.basename(rep).replace(f"_{tag}.ncu-rep", "") + " :: " + name] = {"capture": os.path.basename(rep), "duration_us": row.get("gpu__time_duration.sum"),
                          "dram_bytes": (rd + wr) if rd is not None and wr is not None else None,
                          "dram_bytes_read": rd, "dram_bytes_write": wr,
                          "issue_active_pct": row.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
@@ -62,37 +62,36 @@ def main(tag):
 
 
 def shares(tag, csv_path=None):
-    """Per-kernel totals of the ncu launch list (gpu__time_duration.sum per launch), and the shares of the three
-    kernels of the TIMED STEP (their batched launches: grid > 1) — the other kernels belong to the bench's side legs
-    (S=1 latency probes, dense-market roofline leg, Gavel-policy latency)."""
+    """Per (kernel, grid size) totals of the ncu launch list (gpu__time_duration.sum per launch) of the bench command.
+    The headline step launches gbm_kernel (grid 4096), gbm_ensemble_kernel, solve_kernel<1,512,8> (grid 8: the 8-CTA
+    cluster) and place_kernel (grid 1 or 8); the batched leg launches solve / place with grid 296; the other kernels
+    belong to the side legs (dense-market roofline leg, Gavel-policy latency, plug-in calls)."""
     csv_path = csv_path or f"gpurun_out/launches_{tag}.csv"
     rows = [r for r in csv.reader(open(csv_path)) if len(r) > 5]
     hdr = next(r for r in rows if "Kernel Name" in r)
     ki, vi, mi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name"), hdr.index("Grid Size")
-    tot, step = {}, {}
+    tot = {}
     for r in rows:
         if r is hdr or len(r) <= vi or r[mi] != "gpu__time_duration.sum":
             continue
-        name = r[ki].split("(")[0]
+        name = r[ki].split("(swb::")[0].split("(")[0] if "<" not in r[ki] else r[ki].split(">(")[0] + ">"
+        grid = int(r[gi].strip("()").split(",")[0])
         ms = float(r[vi].replace(",", "")) / 1e6          # ns -> ms
-        t = tot.setdefault(name, [0, 0.0])
+        t = tot.setdefault((name, grid), [0, 0.0])
         t[0] += 1
         t[1] += ms
-        grid = int(r[gi].strip("()").split(",")[0])
-        if grid > 1 and any(k in name for k in ("solve_kernel", "place_kernel", "gbm_kernel")):
-            u = step.setdefault(name, [0, 0.0])
-            u[0] += 1
-            u[1] += ms
     total = sum(v[1] for v in tot.values())
-    lines = ["ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (cold-cache, serialised: compare SHARES)",
-             "", "-- kernels of the timed step (batched launches, mean per launch; share of the step) --"]
-    smean = {k: v[1] / v[0] for k, v in step.items()}
-    ssum = sum(smean.values())
-    for name, ms in sorted(smean.items(), key=lambda kv: -kv[1]):
-        lines.append(f"{name:<70s} n={step[name][0]:3d} mean_ms={ms:9.3f} share={ms / ssum:6.3f}")
-    lines += ["", "-- every launch of the command (side legs included) --"]
-    for name, (n, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
-        lines.append(f"{name:<70s} n={n:3d} total_ms={ms:9.3f} share={ms / total:6.3f}")
+    lines = ["ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (cold-cache, serialised: compare SHARES)", "",
+             f"{'kernel':<64s} {'grid':>6s} {'n':>4s} {'mean_ms':>9s} {'total_ms':>9s} {'share':>6s}"]
+    for (name, grid), (n, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"{name:<64s} {grid:6d} {n:4d} {ms / n:9.3f} {ms:9.3f} {ms / total:6.3f}")
+    # the headline step: gbm (grid 4096) + cluster solve (grid 8) + place launched right after it
+    step = {k: v for k, v in tot.items() if ("gbm_kernel" in k[0] and k[1] >= 1024) or ("solve_kernel" in k[0] and k[1] == 8)
+            or ("place_kernel" in k[0] and k[1] in (1, 8)) or "gbm_ensemble" in k[0]}
+    ssum = sum(v[1] / v[0] for v in step.values())
+    lines += ["", "-- kernels of the headline step (one re-solve): mean per launch, share of their sum --"]
+    for (name, grid), (n, ms) in sorted(step.items(), key=lambda kv: -kv[1][1] / kv[1][0]):
+        lines.append(f"{name:<64s} {grid:6d} {n:4d} {ms / n:9.3f} share={ms / n / ssum:6.3f}")
     open(f"profiles/launch_shares_{tag}.txt", "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
 

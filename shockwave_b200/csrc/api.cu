@@ -225,13 +225,15 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   P.x = x; P.backfill = bf; P.nrounds = nr ? nr : c->seated.as<int32_t>(); P.ncal = ncal; P.res = L.res;
   P.xmask = xmask; P.bfmask = bfmask; P.ncap = c->sncap.as<uint8_t>();
   // re-rank local search: O(J T^2) per cancelled cycle — on where that stays in the tens of microseconds
+  // (jobs x rounds^2 <= 256 Ki: 640 jobs at 20 rounds, 250 at 32, 64 at 64 — the reference's deployments; beyond that
+  // the priority sweep alone places the fallback schedule)
   P.rr_items = nullptr; P.rr_iters = 0; P.prm_T = h_prm[0].future_rounds;
   {
     const size_t T_ = (size_t)h_prm[0].future_rounds;
     const int cl = (S * 8 <= 144 && J <= SWB_SMEM_JOBS) ? 8 : 1;     // multi-start over a cluster (place.cu)
     const size_t bytes = (size_t)S * cl * swb::rr_scratch_bytes(J, (int)T_);
     P.rr_cluster = 1;
-    if (c->rr_iters > 0 && (size_t)J * T_ * T_ <= (4u << 20) && bytes <= (512u << 20)) {
+    if (c->rr_iters > 0 && (size_t)J * T_ * T_ <= (256u << 10) && bytes <= (512u << 20)) {
       CK(c->rr_items.need(bytes, c->st));
       P.rr_items = c->rr_items.p; P.rr_iters = c->rr_iters; P.rr_cluster = cl;
     }
