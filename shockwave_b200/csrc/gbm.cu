@@ -37,6 +37,10 @@ struct XorShift128p {
   }
 };
 
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 __global__ void __launch_bounds__(256) gbm_kernel(GbmLaunch L) {
   __shared__ double red[2 * 64];
   const int j = blockIdx.x;
@@ -53,6 +57,7 @@ __global__ void __launch_bounds__(256) gbm_kernel(GbmLaunch L) {
     mu = (float)L.mu[j]; sg = (float)L.sigma[j];
   }
   const float drift = mu - 0.5f * sg * sg;
+  const float drift2 = drift * 1.4426950408889634f, sg2 = sg * 1.4426950408889634f;   // exponents in base 2
   const float invH = H > 0 ? 1.0f / (float)H : 0.0f;
   const double R0 = L.R0[j];
   double s1 = 0.0, s2 = 0.0;
@@ -67,24 +72,26 @@ __global__ void __launch_bounds__(256) gbm_kernel(GbmLaunch L) {
     XorShift128p rng;
     rng.s0 = splitmix64(sm);
     rng.s1 = splitmix64(sm) | 1ull;
-    float W = 0.0f, accA = 0.0f, accB = 0.0f;
-    for (int h = 1; h <= H; h += 2) {
-      // Box-Muller: two normals per pair of 24-bit uniforms
+    float W = 0.0f, accA = 0.0f, accB = 0.0f, hf = 1.0f;
+    for (int h = 1; h <= H; h += 2, hf += 2.0f) {
+      // Box-Muller: two normals per pair of 24-bit uniforms.  Every transcendental is ONE MUFU instruction (the
+      // kernel is bound by instruction issue and the MUFU pipe, ncu r02): exponents are kept in base 2 (drift and
+      // sigma pre-scaled by log2 e), the radius is sqrt(-2 ln2 * lg2 u1).
       const unsigned long long r = rng.next();
       const float u1 = ((float)((unsigned)(r >> 40)) + 1.0f) * (1.0f / 16777217.0f);  // (0,1)
       const float u2 = (float)((unsigned)(r >> 8) & 0xffffffu) * (1.0f / 16777216.0f);
-      const float rad = sqrtf(-2.0f * __logf(u1));
-      float sn, cs;
-      __sincosf(6.283185307179586f * u2, &sn, &cs);
-      W += rad * cs;
-      float dh = drift * (float)h, sw = sg * W;
-      accA += __expf(dh + sw);
-      accB += __expf(dh - sw);
+      const float rad = sqrt_approx(-1.3862943611198906f * lg2_approx(u1));
+      const float ang = 6.283185307179586f * u2;
+      const float cs = __cosf(ang), sn = __sinf(ang);
+      W = fmaf(rad, cs, W);
+      float dh = drift2 * hf, sw = sg2 * W;
+      accA += ex2_approx(dh + sw);
+      accB += ex2_approx(dh - sw);
       if (h + 1 <= H) {
-        W += rad * sn;
-        dh = drift * (float)(h + 1); sw = sg * W;
-        accA += __expf(dh + sw);
-        accB += __expf(dh - sw);
+        W = fmaf(rad, sn, W);
+        dh += drift2; sw = sg2 * W;
+        accA += ex2_approx(dh + sw);
+        accB += ex2_approx(dh - sw);
       }
     }
     const long long pa = 2 * q, pb = 2 * q + 1;

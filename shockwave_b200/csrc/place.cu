@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   unsigned int *binB = reinterpret_cast<unsigned int *>(p); p += SWB_MAX_T * sizeof(int);
   double *score = reinterpret_cast<double *>(p); p += SWB_MAX_T * sizeof(double);
   unsigned char *newpos = p;                   p += SWB_MAX_T;
+  // prefix OR of the bin bits behind the ring's physical positions [0, q) (water-filling packer, chunk path)
+  ulonglong2 *pmask = reinterpret_cast<ulonglong2 *>(p); p += (SWB_MAX_T + 1) * sizeof(ulonglong2);
   // sort scratch: key64[npad] + idx16[npad]
   unsigned long long *key64 = reinterpret_cast<unsigned long long *>(p);
   unsigned short *idx16 = reinterpret_cast<unsigned short *>(p + 8 * (size_t)npad);
@@ -306,6 +308,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     for (int p = lane; p < Tw; p += 32) A[p] = (unsigned)p;  // load 0, bin p
     __syncwarp();
     int head = 0;   // the sorted bins are a RING: logical position p lives in A[(head + p) mod Tw]
+    bool pm_ok = false;   // pmask[] matches the current physical order of A
     for (int pos = 0; pos < J; ++pos) {
       if (key64[pos] == 0ull) break;
       // ---- chunk-parallel path: 32 consecutive jobs of the SAME width on a balanced ring -------------
@@ -333,14 +336,48 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
         const int cfull = Ptot / Tw, rpart = Ptot - cfull * Tw;
         int hr = head + rpart - 1; if (hr >= Tw) hr -= Tw; if (hr < 0) hr += Tw;
         const int top = max(rpart > 0 ? (int)(A[hr] >> 8) + g0 * (cfull + 1) : 0, lmax + g0 * cfull);
-        if (cnt >= 4 && same && lmax - lmin <= g0 && top <= G) {
+        const bool short_ok = __all_sync(SWB_FULL, nn <= Tw);
+        if (cnt >= 4 && same && short_ok && lmax - lmin <= g0 && top <= G) {
+          if (!pm_ok) {
+            // the bins behind a ring range [a, b) as a mask = pmask[b] ^ pmask[a] (every bin appears once): one warp
+            // scan here replaces a dependent walk over up to T shared-memory reads per job
+            unsigned long long c0 = 0ull, c1 = 0ull, l0[4], l1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int pq = 4 * lane + e;
+              if (pq < Tw) {
+                const unsigned int b = A[pq] & 0xffu;
+                if (b < 64) c0 |= 1ull << b; else c1 |= 1ull << (b - 64);
+              }
+              l0[e] = c0; l1[e] = c1;
+            }
+            unsigned long long i0 = c0, i1 = c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const unsigned long long t0_ = __shfl_up_sync(SWB_FULL, i0, o), t1_ = __shfl_up_sync(SWB_FULL, i1, o);
+              if (lane >= o) { i0 |= t0_; i1 |= t1_; }
+            }
+            unsigned long long e0 = __shfl_up_sync(SWB_FULL, i0, 1), e1 = __shfl_up_sync(SWB_FULL, i1, 1);
+            if (lane == 0) { e0 = 0ull; e1 = 0ull; pmask[0] = make_ulonglong2(0ull, 0ull); }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int pq = 4 * lane + e;
+              if (pq < Tw) pmask[pq + 1] = make_ulonglong2(e0 | l0[e], e1 | l1[e]);
+            }
+            pm_ok = true;
+            __syncwarp();
+          }
           if (valid) {
             int st = head + (incl - nn) % Tw; if (st >= Tw) st -= Tw;
-            unsigned long long m0 = 0ull, m1 = 0ull;
-            for (int q = 0; q < nn; ++q) {
-              int ix = st + q; if (ix >= Tw) ix -= Tw;
-              const unsigned int b = A[ix] & 0xffu;
-              if (b < 64) m0 |= 1ull << b; else m1 |= 1ull << (b - 64);
+            const int en = st + nn;
+            const ulonglong2 pa = pmask[st];
+            unsigned long long m0, m1;
+            if (en <= Tw) {
+              const ulonglong2 pb = pmask[en];
+              m0 = pb.x ^ pa.x; m1 = pb.y ^ pa.y;
+            } else {
+              const ulonglong2 pe = pmask[Tw], pb = pmask[en - Tw];
+              m0 = (pe.x ^ pa.x) | pb.x; m1 = (pe.y ^ pa.y) | pb.y;
             }
             xm[2 * jj] = m0; xm[2 * jj + 1] = m1; remn[jj] = 0;
           }
@@ -391,6 +428,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
         continue;
       }
       // General path: linearise the ring, then take the usable prefix and re-merge.
+      pm_ok = false;
       if (head != 0) {
         for (int p = lane; p < Tw; p += 32) { int ix = head + p; if (ix >= Tw) ix -= Tw; B[p] = A[ix]; }
         unsigned int *tmp0 = A; A = B; B = tmp0;
@@ -786,6 +824,7 @@ cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long lo
   int npad = 64;
   while (npad < L.J) npad <<= 1;
   size_t smem = 2 * 64 * sizeof(double) + 32 * sizeof(int) + SWB_MAX_T * (4 * sizeof(int) + sizeof(double) + 1) +
+                (SWB_MAX_T + 1) * 16 +
                 10 * (size_t)npad + 4 * (size_t)npad + 6 * (size_t)npad + 16;
   if (L.J <= SWB_SMEM_JOBS) smem += 32 * (size_t)L.J;
   // function attributes are per device: one flag per device ordinal (one process may drive several GPUs)
