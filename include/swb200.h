@@ -223,6 +223,28 @@ int swb_policy_hetero(swb_ctx *ctx, int32_t mode, int32_t J, int32_t W, const do
                       const double *sf, const double *t, const double *n, const double *den, double *x,
                       double *objective, int32_t *stats);
 
+/* ---- water-filling max-min fairness: one iteration of WaterFillingAlgorithm ------------------------ *
+ * Replaces the two solver calls inside the loop of _run_get_allocation_iterations
+ * (scheduler/policies/max_min_fairness_water_filling.py:307-413):
+ *   _get_allocation      :81-189   (cvxpy -> ECOS)     max c <= M :  net_j >= lower_j + c / mult_j  for mult_j > 0,
+ *                                                       net_j >= lower_j otherwise,  net_j = thr_j.x_j / prop_j,
+ *                                                       base constraints of policy.py:58-65
+ *   _get_bottleneck_jobs :191-305  (cvxpy -> GLPK_MI)  max sum_j z_j :  every job keeps net_j >= so_far_j
+ *                                                       (= lower_j + c / mult_j), z_j = 1 needs net_j >= so_far_j * slack
+ * thr is the J x W throughput matrix (W <= 3 worker types, each with N[w] > 0), prop the proportional throughputs,
+ * lower the normalised lower bounds (final value of a saturated job, so_far of the others), mult the reference's
+ * multiplicative terms priority_j * scale_factor_j (0 for saturated / weightless jobs), M its big-M objective cap.
+ * Out: x (J x W) = the LP's allocation, *c = its objective, z[J] = relaxed bottleneck indicator in [0, 1]
+ * (the integer z of the reference rounds it; the caller treats z_j < 0.5 as "job j is a bottleneck").
+ * Both programs run on the device (hetero.cu: bisection on the scalar, Dantzig-Wolfe on the coupling rows, every
+ * feasibility claim certified).  stats (optional, int32[4]): pricing passes / feasibility checks of the two programs.
+ * Returns 0, or 1 when the LP has no feasible point (x, c, z untouched). */
+#define SWB_POL_WFILL 6
+#define SWB_POL_WFZ 7
+int swb_policy_waterfill_step(swb_ctx *ctx, int32_t J, int32_t W, const double *N, const double *thr, const double *sf,
+                              const double *prop, const double *lower, const double *mult, double M, double slack,
+                              double *x, double *c, double *z, int32_t *stats);
+
 /* ---- AlloX min-cost assignment --------------------------------------------------------------- *
  * Replaces scipy.optimize.linear_sum_assignment(q) in AlloXPolicy.get_allocation
  * (scheduler/policies/allox.py:108-144).  q is implicit: for job i and column col = k*n + j,

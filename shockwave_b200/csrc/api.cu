@@ -56,6 +56,7 @@ struct swb_ctx {
   cudaStream_t st = nullptr;
   // ---- work buffers of a solve
   DBuf prm, res, g, E, c, dbar, rem, ftobj, bfkey, x, bf, nr, w, xmk, bmk;
+  DBuf wf_z, wf_x2;
   DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask, sncap, seated, scth, sths, sn0, snfc, sRr;
   int want_relaxed = 0;
   // ---- resident job table (by slot)
@@ -137,7 +138,8 @@ void swb_destroy(swb_ctx *c) {
                  &c->ax_path, &c->ax_sc, &c->ax_sr, &c->ax_out, &c->pol_coef, &c->pol_sf, &c->pol_t,
                  &c->pol_n, &c->pol_den, &c->pol_x, &c->pol_out, &c->mc_R0, &c->mc_mu, &c->mc_sigma, &c->mc_H, &c->mc_out,
                  &c->m_theta, &c->m_rowp, &c->m_colload,
-                 &c->m_colscale, &c->m_price, &c->m_obj, &c->m_X, &c->m_rate, &c->m_E, &c->m_c, &c->m_Gw};
+                 &c->m_colscale, &c->m_price, &c->m_obj, &c->m_X, &c->m_rate, &c->m_E, &c->m_c, &c->m_Gw,
+                 &c->het_a, &c->het_N, &c->het_x, &c->wf_z, &c->wf_x2};
   for (DBuf *b : all) b->release();
   if (c->h_res) cudaFreeHost(c->h_res);
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -732,6 +734,56 @@ int swb_policy_hetero(swb_ctx *c, int32_t mode, int32_t J, int32_t W, const doub
     fprintf(stderr, "\n");
   }
   return out[1] != 0.0 ? 1 : 0;
+}
+
+int swb_policy_waterfill_step(swb_ctx *c, int32_t J, int32_t W, const double *N, const double *thr, const double *sf,
+                              const double *prop, const double *lower, const double *mult, double M, double slack,
+                              double *x, double *cobj, double *z, int32_t *stats) {
+  if (!c || !N || !thr || !sf || !prop || !lower || !mult || !x || !cobj || !z)
+    return fail(SWB_ERR_ARG, "swb_policy_waterfill_step: null argument");
+  if (J <= 0 || J > SWB_MAX_J) return fail(SWB_ERR_ARG, "swb_policy_waterfill_step: J must be in [1, 8192]");
+  if (W <= 0 || W > 3) return fail(SWB_ERR_ARG, "swb_policy_waterfill_step: W must be in [1, 3]");
+  if (!(slack >= 1.0)) return fail(SWB_ERR_ARG, "swb_policy_waterfill_step: slack must be >= 1");
+  for (int w = 0; w < W; ++w)
+    if (!(N[w] > 0.0)) return fail(SWB_ERR_ARG, "swb_policy_waterfill_step: every worker type needs capacity > 0 (drop empty types)");
+  for (int j = 0; j < J; ++j)
+    if (!(prop[j] > 0.0) || !(mult[j] >= 0.0) || !(sf[j] > 0.0))
+      return fail(SWB_ERR_ARG, "swb_policy_waterfill_step: prop and sf must be positive, mult non-negative");
+  CK(cudaSetDevice(c->device));
+  const size_t b = (size_t)J * 8, bw = b * (size_t)W;
+  CK(c->het_a.need(bw, c->st)); CK(c->het_x.need(bw, c->st)); CK(c->het_N.need(32, c->st));
+  CK(c->pol_sf.need(b, c->st)); CK(c->pol_t.need(b, c->st));
+  CK(c->pol_n.need(b, c->st)); CK(c->pol_den.need(b, c->st));
+  CK(c->pol_out.need(256, c->st)); CK(c->wf_z.need(b, c->st)); CK(c->wf_x2.need(bw, c->st));
+  CK(cudaMemcpyAsync(c->het_a.p, thr, bw, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->het_N.p, N, (size_t)W * 8, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->pol_sf.p, sf, b, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->pol_t.p, lower, b, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->pol_n.p, mult, b, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->pol_den.p, prop, b, cudaMemcpyHostToDevice, c->st));
+  swb::HeteroLaunch L;
+  L.mode = SWB_POL_WFILL; L.J = J; L.W = W;
+  L.N = c->het_N.as<double>(); L.a = c->het_a.as<double>(); L.sf = c->pol_sf.as<double>();
+  L.t = c->pol_t.as<double>(); L.n = c->pol_n.as<double>(); L.den = c->pol_den.as<double>();
+  L.x = c->het_x.as<double>(); L.out = c->pol_out.as<double>();
+  L.wf_M = M; L.wf_slack = slack;
+  CK(swb::launch_hetero(L, c->st));
+  // second program on the same stream: the LP's objective stays on the device (out[0]) and moves the lower bounds
+  swb::HeteroLaunch Z = L;
+  Z.mode = SWB_POL_WFZ; Z.wf_c = c->pol_out.as<double>(); Z.out = c->pol_out.as<double>() + 16;
+  Z.x = c->wf_x2.as<double>(); Z.zout = c->wf_z.as<double>();
+  CK(swb::launch_hetero(Z, c->st));
+  double out[32] = {0.0};
+  CK(cudaMemcpyAsync(out, c->pol_out.p, 256, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  if (stats) { stats[0] = (int32_t)out[2]; stats[1] = (int32_t)out[3]; stats[2] = (int32_t)out[18]; stats[3] = (int32_t)out[19]; }
+  if (out[1] != 0.0) return 1;
+  CK(cudaMemcpyAsync(x, c->het_x.p, bw, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(z, c->wf_z.p, b, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  *cobj = out[0];
+  if (out[17] != 0.0) for (int j = 0; j < J; ++j) z[j] = 0.0;     // the bottleneck program found no point: nobody moves
+  return 0;
 }
 
 int swb_gbm_forecast(swb_ctx *c, int32_t J, const double *R0, const int32_t *H, const double *mu,

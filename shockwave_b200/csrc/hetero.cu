@@ -76,7 +76,36 @@ __device__ __forceinline__ bool ht_requirement(const HeteroLaunch &L, int j, dou
     return true;
   }
   if (L.mode == SWB_POL_MTD) { r = L.n[j] / theta; return true; }
+  if (L.mode == SWB_POL_WFILL) {   // net_j = a_j.x_j / prop_j >= lower_j + theta / mult_j  (water_filling.py:127-171)
+    const double m = L.n[j];
+    r = L.den[j] * (L.t[j] + (m > 0.0 ? theta / m : 0.0));
+    return true;
+  }
   r = 0.0;
+  return true;
+}
+
+__device__ __forceinline__ bool ht_response(const double *a, int W, double r, const double *q, double *x);
+__device__ __forceinline__ bool ht_sum_mode(int mode) { return mode == SWB_POL_MAXSUM || mode == SWB_POL_WFZ; }
+
+// Bottleneck detection of the water-filling iteration (max_min_fairness_water_filling.py:191-305): every job keeps
+// net_j >= so_far_j; an active job may additionally rise to so_far_j * slack and then counts 1 (the z_j of the
+// reference's MILP, relaxed to [0, 1] by mixing the two vertices).  Returns the job's level at the prices (p0, q).
+__device__ __forceinline__ bool ht_response_wfz(const HeteroLaunch &L, int j, const double *a, int W, double sf, double p0,
+                                                const double *q, double *x, double &level) {
+  const double m = L.n[j];
+  const double cprev = L.wf_c ? *L.wf_c : 0.0;
+  const double r0 = L.den[j] * (L.t[j] + (m > 0.0 ? cprev / m : 0.0));
+  level = 0.0;
+  if (!ht_response(a, W, r0, q, x)) return false;
+  if (m > 0.0) {
+    double x1[HT_MAXR];
+    if (ht_response(a, W, r0 * L.wf_slack, q, x1)) {
+      double c0 = 0.0, c1 = 0.0;
+      for (int w = 0; w < W; ++w) { c0 += q[w] * x[w]; c1 += q[w] * x1[w]; }
+      if (p0 - sf * c1 > -sf * c0) { level = 1.0; for (int w = 0; w < W; ++w) x[w] = x1[w]; }
+    }
+  }
   return true;
 }
 
@@ -170,7 +199,7 @@ template <int W, int R>
 __device__ __noinline__ void ht_price(HtCtx &C, double theta) {
   const HeteroLaunch &L = C.L;
   double q[HT_MAXR], acc[HT_MAXR + 2];
-  const bool sum_mode = (L.mode == SWB_POL_MAXSUM);
+  const bool sum_mode = ht_sum_mode(L.mode);
   for (int w = 0; w < W; ++w) q[w] = C.S.pi[sum_mode ? w + 1 : w] / L.N[w];
   const double p0 = sum_mode ? C.S.pi[0] / C.vscale : 0.0;
   for (int i = 0; i < HT_MAXR + 2; ++i) acc[i] = 0.0;
@@ -178,7 +207,11 @@ __device__ __noinline__ void ht_price(HtCtx &C, double theta) {
     double a[HT_MAXR], x[HT_MAXR];
     for (int w = 0; w < W; ++w) a[w] = L.a[(size_t)j * W + w];
     const double sf = L.sf[j];
-    if (sum_mode) {
+    if (L.mode == SWB_POL_WFZ) {
+      double level;
+      if (!ht_response_wfz(L, j, a, W, sf, p0, q, x, level)) acc[HT_MAXR] += 1.0;
+      else { acc[0] += level; for (int w = 0; w < W; ++w) acc[w + 1] += sf * x[w]; }
+    } else if (sum_mode) {
       bool okj = true;
       if (L.t) {      // SLO floors: t = needed throughput, den = instance cost per type (thr = a * cost)
         double thr[HT_MAXR];
@@ -557,6 +590,54 @@ __global__ void __launch_bounds__(1024, 1) hetero_kernel(HeteroLaunch L) {
     }
     if (best < 0.0) { status = 1; best = max_T; }
     obj = best;
+  } else if (L.mode == SWB_POL_WFILL) {
+    // max theta <= M with net_j >= lower_j + theta / mult_j for the active jobs: theta cannot pass the point where an
+    // active job would need more than its best type at full time
+    double m = L.wf_M;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      const double mj = L.n[j];
+      if (mj > 0.0) {
+        double b = 0.0;
+        for (int w = 0; w < W; ++w) b = fmax(b, L.a[(size_t)j * W + w]);
+        m = fmin(m, (b / L.den[j] - L.t[j]) * mj);
+      }
+    }
+    { BlockRed br(&S.red[0][0][0]); m = br.min(m); __syncthreads(); }
+    double lo = 0.0, hi = fmax(m, 0.0);
+    ++checks;
+    if (!ht_feasible<W, R>(C, 0.0, rounds)) {
+      status = 1;
+    } else {
+      ht_accept(C, 0.0);
+      ++checks;
+      if (hi > 0.0 && ht_feasible<W, R>(C, hi, rounds)) { ht_accept(C, hi); lo = hi; }
+      for (int it = 0; it < 200 && hi - lo > 1e-12 * hi; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        ++checks;
+        if (ht_feasible<W, R>(C, mid, rounds)) { ht_accept(C, mid); lo = mid; } else hi = mid;
+      }
+    }
+    obj = lo;
+  } else if (L.mode == SWB_POL_WFZ) {
+    double na = 0.0;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) na += (L.n[j] > 0.0) ? 1.0 : 0.0;
+    { BlockRed br(&S.red[0][0][0]); na = br.sum(na); __syncthreads(); }
+    C.vscale = na > 0.0 ? na : 1.0;
+    double lo = 0.0, hi = na;
+    ++checks;
+    if (!ht_feasible<W, R>(C, 0.0, rounds)) {
+      status = 1;
+    } else {
+      ht_accept(C, 0.0);
+      ++checks;
+      if (hi > 0.0 && ht_feasible<W, R>(C, hi, rounds)) { ht_accept(C, hi); lo = hi; }
+      for (int it = 0; it < 200 && hi - lo > 1e-7 * fmax(hi, 1.0); ++it) {
+        const double mid = 0.5 * (lo + hi);
+        ++checks;
+        if (ht_feasible<W, R>(C, mid, rounds)) { ht_accept(C, mid); lo = mid; } else hi = mid;
+      }
+    }
+    obj = lo;
   } else {  // MAXSUM
     double ub = 0.0;
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
@@ -589,15 +670,20 @@ __global__ void __launch_bounds__(1024, 1) hetero_kernel(HeteroLaunch L) {
   __syncthreads();
   const int K = S.bK;
   const double theta = S.bTheta;
-  const bool sum_mode = (L.mode == SWB_POL_MAXSUM);
+  const bool sum_mode = ht_sum_mode(L.mode);
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
     double a[HT_MAXR], out[HT_MAXR];
     for (int w = 0; w < W; ++w) { a[w] = L.a[(size_t)j * W + w]; out[w] = 0.0; }
     const double sf = L.sf[j];
+    double zj = 0.0;
     for (int i = 0; i < K; ++i) {
       double q[HT_MAXR], x[HT_MAXR];
       for (int w = 0; w < W; ++w) q[w] = S.bPI[i][sum_mode ? w + 1 : w] / L.N[w];
-      if (sum_mode) {
+      if (L.mode == SWB_POL_WFZ) {
+        double level = 0.0;
+        ht_response_wfz(L, j, a, W, sf, S.bPI[i][0] / C.vscale, q, x, level);
+        zj += S.bMU[i] * level;
+      } else if (sum_mode) {
         if (L.t) {
           double thr[HT_MAXR];
           for (int w = 0; w < W; ++w) thr[w] = a[w] * L.den[w];
@@ -613,13 +699,14 @@ __global__ void __launch_bounds__(1024, 1) hetero_kernel(HeteroLaunch L) {
       for (int w = 0; w < W; ++w) out[w] += S.bMU[i] * x[w];
     }
     for (int w = 0; w < W; ++w) L.x[(size_t)j * W + w] = out[w];
+    if (L.mode == SWB_POL_WFZ && L.zout) L.zout[j] = zj;
   }
   if (threadIdx.x == 0) { L.out[0] = obj; L.out[1] = (double)status; L.out[2] = (double)rounds; L.out[3] = (double)checks;
     for (int i = 0; i < 12; ++i) L.out[4 + i] = S.dbg[i]; }
 }
 
 cudaError_t launch_hetero(const HeteroLaunch &L, cudaStream_t st) {
-  const bool sum = (L.mode == SWB_POL_MAXSUM);
+  const bool sum = (L.mode == SWB_POL_MAXSUM || L.mode == SWB_POL_WFZ);
   switch (L.W) {
     case 1: if (sum) hetero_kernel<1, 2><<<1, 1024, 0, st>>>(L); else hetero_kernel<1, 1><<<1, 1024, 0, st>>>(L); break;
     case 2: if (sum) hetero_kernel<2, 3><<<1, 1024, 0, st>>>(L); else hetero_kernel<2, 2><<<1, 1024, 0, st>>>(L); break;

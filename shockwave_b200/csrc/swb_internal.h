@@ -120,6 +120,11 @@ struct HeteroLaunch {
   const double *t, *n, *den;// as in PolicyLaunch
   double *x;                // [J][W] out
   double *out;              // [4] out: objective, status, pricing passes, feasibility checks
+  // water-filling iteration (SWB_POL_WFILL / SWB_POL_WFZ): t = normalised lower bounds, n = multiplicative terms
+  // (0: the job takes no part), den = proportional throughputs
+  double wf_M = 0.0, wf_slack = 1.0;   // cap of the LP objective; slack factor of the bottleneck test
+  const double *wf_c = nullptr;        // WFZ: device pointer to the LP step's objective (lower_j += c / mult_j)
+  double *zout = nullptr;              // WFZ: [J] relaxed z_j
 };
 cudaError_t launch_hetero(const HeteroLaunch &L, cudaStream_t st);
 

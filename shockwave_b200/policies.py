@@ -242,6 +242,203 @@ class MaxMinFairnessPolicy(Policy):
         return self._max_min_fairness_perf_policy.get_allocation(ones, scale_factors, priority_weights, cluster_spec)
 
 
+def _waterfill_step(N, thr, sf, prop, lower, mult, M, slack=1.0001):
+    """swb_policy_waterfill_step: the LP and the bottleneck program of one water-filling iteration on the device.
+    Returns (x[J,W], c, z[J]) or (None, None, None) when the LP has no feasible point."""
+    eng = _engine()
+    lib = eng.lib
+    if not getattr(lib, "_wf_bound", False):
+        lib.swb_policy_waterfill_step.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 6 + \
+                                                 [C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_double),
+                                                  C.c_void_p, C.c_void_p]
+        lib.swb_policy_waterfill_step.restype = C.c_int
+        lib._wf_bound = True
+    arr = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+    N, thr, sf, prop, lower, mult = arr(N), arr(thr), arr(sf), arr(prop), arr(lower), arr(mult)
+    J, W = thr.shape
+    if W > 3:
+        raise NotImplementedError("water-filling with more than 3 worker types with capacity: not solved on the GPU in this release")
+    x = np.zeros((J, W), dtype=np.float64)
+    z = np.zeros(J, dtype=np.float64)
+    c = C.c_double()
+    stats = np.zeros(4, dtype=np.int32)
+    p = lambda v: C.c_void_p(v.ctypes.data)
+    rc = lib.swb_policy_waterfill_step(eng.h, J, W, p(N), p(thr), p(sf), p(prop), p(lower), p(mult), float(M),
+                                       float(slack), p(x), C.byref(c), p(z), p(stats))
+    if rc < 0:
+        raise RuntimeError(f"swb_policy_waterfill_step failed ({rc}): {lib.swb_last_error().decode()}")
+    _waterfill_step.last_stats = tuple(int(v) for v in stats)
+    if rc == 1:
+        return None, None, None
+    return x, c.value, z
+
+
+class WaterFillingAlgorithm:
+    """max_min_fairness_water_filling.py:13-413: the iteration loop and the entity re-weighting stay on the host (dict
+    bookkeeping, a handful of iterations); `_get_allocation` (ECOS LP) and `_get_bottleneck_jobs` (GLPK_MI MILP) are
+    one device call per iteration (swb_policy_waterfill_step)."""
+    SLACK, EPSILON = 1.0001, 1e-5      # water_filling.py:200-203
+
+    def __init__(self, priority_reweighting_policies):
+        self._previous_priority_weights = None
+        self._priority_reweighting_policies = priority_reweighting_policies
+
+    def _compute_priority_weights(self, entity_weights, priority_weights, entity_to_job_mapping,
+                                  final_normalized_effective_throughputs, job_ids):
+        # water_filling.py:16-79
+        returned_priority_weights = {}
+        if self._priority_reweighting_policies is None:
+            return priority_weights
+        if entity_to_job_mapping is None:
+            raise ValueError("entity_to_job_mapping cannot be None when priority_reweighting_policies is not None!")
+        final = final_normalized_effective_throughputs
+        for entity_id in entity_to_job_mapping:
+            pol = self._priority_reweighting_policies[entity_id]
+            entity_weight = entity_weights[entity_id]
+            jobs = entity_to_job_mapping[entity_id]
+            if pol == "fairness":
+                total = 0.0
+                for job_id in jobs:
+                    if job_id not in final:
+                        total += float(priority_weights[job_id])
+                for job_id in jobs:
+                    returned_priority_weights[job_id] = 0.0 if job_id in final else \
+                        entity_weight * (float(priority_weights[job_id]) / total)
+            elif pol == "fifo":
+                jobs.sort()
+                done = False
+                for job_id in jobs:
+                    if job_id in final or done:
+                        returned_priority_weights[job_id] = 0.0
+                    else:
+                        returned_priority_weights[job_id] = entity_weight
+                        done = True
+            else:
+                raise ValueError("Unknown priority reweighting policy!")
+        return returned_priority_weights
+
+    def _run_get_allocation_iterations(self, job_ids, thr, sf, N, prop, M, entity_weights,
+                                       unflattened_priority_weights, entity_to_job_mapping, verbose=False):
+        """water_filling.py:307-413 on arrays (thr: J x W over the LIVE worker types).  Returns x of the last LP."""
+        J = len(job_ids)
+        final = {}
+        so_far = np.zeros(J)
+        x = None
+        done = False
+        self.last_iterations = 0
+        while not done:
+            pw_d = self._compute_priority_weights(entity_weights, unflattened_priority_weights, entity_to_job_mapping,
+                                                  final, job_ids)
+            self._previous_priority_weights = copy.copy(pw_d)
+            pw = np.array([1.0 / pw_d[j] if pw_d[j] > 0 else 0.0 for j in job_ids])
+            is_final = np.fromiter((j in final for j in job_ids), dtype=bool, count=J)
+            active = (~is_final) & (pw > 0.0)
+            mult = np.where(active, pw * sf, 0.0)
+            lower = np.where(is_final, np.array([final.get(j, 0.0) for j in job_ids]), so_far)
+            xs, c, z = _waterfill_step(N, thr, sf, prop, lower, mult, M, self.SLACK)
+            if xs is None:                       # "x is None" / solver exception: keep the previous iterate, stop
+                done = True
+                z = np.zeros(J)
+            else:
+                x = xs
+                so_far = so_far + np.where(active, c / np.where(active, mult, 1.0), 0.0)
+                # the reference's MILP also bounds every z = 0 job from above by so_far * slack - epsilon, which no
+                # point satisfies for so_far < 0.1: GLPK reports infeasible, the except branch returns z = 0 for all
+                lim = so_far * self.SLACK - self.EPSILON
+                base = np.where(is_final, lower, so_far)
+                if np.any(((~active) | (z < 0.5)) & (lim < base)):
+                    z = np.zeros(J)
+            before = len(final)
+            for i in np.flatnonzero(active & (z < 0.5)).tolist():
+                final[job_ids[i]] = so_far[i]
+            if verbose:
+                print("water-filling iteration %d: c = %.6f, %d saturated" % (self.last_iterations, c or 0.0, len(final)))
+            if before == len(final):
+                done = True
+            self.last_iterations += 1
+            if len(final) == J:
+                done = True
+        self.last_so_far = so_far
+        return x
+
+
+class MaxMinFairnessWaterFillingPolicyWithPerf(Policy, WaterFillingAlgorithm):
+    """max_min_fairness_water_filling.py:476-576."""
+    def __init__(self, priority_reweighting_policies=None):
+        WaterFillingAlgorithm.__init__(self, priority_reweighting_policies)
+        Policy.__init__(self, solver=None)
+        self._name = "MaxMinFairnessWaterFilling_Perf"
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, unflattened_priority_weights, cluster_spec,
+                       entity_weights=None, entity_to_job_mapping=None, verbose=False,
+                       return_effective_throughputs=False):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        job_ids, _ = index
+        sf = np.array([scale_factors[j] for j in job_ids], dtype=np.float64)
+        Nall = np.asarray(self._num_workers, dtype=np.float64)
+        share = Nall / Nall.sum()
+        prop = throughputs @ share                                    # proportional.py:20-43
+        self._M = float(np.max(throughputs / prop[:, None] * sf[:, None]))     # water_filling.py:507-512
+        live = Nall > 0
+        thr, Npool, _ = self._pool(throughputs)
+        if thr is not None:       # every live type gives a job the same throughput: one pooled type, split by capacity
+            xs = self._run_get_allocation_iterations(job_ids, thr[:, None], sf, np.array([Npool]), prop, self._M,
+                                                     entity_weights, unflattened_priority_weights,
+                                                     entity_to_job_mapping, verbose)
+            x = self._split(xs[:, 0], share)
+        else:
+            xs = self._run_get_allocation_iterations(job_ids, throughputs[:, live], sf, Nall[live], prop, self._M,
+                                                     entity_weights, unflattened_priority_weights,
+                                                     entity_to_job_mapping, verbose)
+            x = np.zeros_like(throughputs)
+            x[:, live] = xs
+        x = np.clip(x, 0.0, 1.0)
+        if return_effective_throughputs:
+            return (throughputs * x).sum(axis=1) / prop, job_ids
+        return super().unflatten(x, index)
+
+
+class MaxMinFairnessWaterFillingPolicy(Policy, WaterFillingAlgorithm):
+    """max_min_fairness_water_filling.py:416-473: the same algorithm with every throughput set to 1.0."""
+    def __init__(self, priority_reweighting_policies=None):
+        self._name = "MaxMinFairnessWaterFilling"
+        self._max_min_fairness_perf_policy = MaxMinFairnessWaterFillingPolicyWithPerf(priority_reweighting_policies)
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, unflattened_priority_weights, cluster_spec,
+                       entity_weights=None, entity_to_job_mapping=None, verbose=False,
+                       return_effective_throughputs=False):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        job_ids, worker_types = index
+        ones = {j: {w: 1.0 for w in unflattened_throughputs[j]} for j in unflattened_throughputs}
+        unflattened_x = self._max_min_fairness_perf_policy.get_allocation(
+            ones, scale_factors, unflattened_priority_weights, cluster_spec, entity_weights=entity_weights,
+            entity_to_job_mapping=entity_to_job_mapping, verbose=verbose, return_effective_throughputs=False)
+        if return_effective_throughputs:
+            x = np.array([[unflattened_x[j][w] for w in worker_types] for j in job_ids])
+            Nall = np.asarray(self._num_workers, dtype=np.float64)
+            prop = throughputs @ (Nall / Nall.sum())
+            return (throughputs * x).sum(axis=1) / prop, job_ids
+        return unflattened_x
+
+
+class MaxMinFairnessStrategyProofPolicy(Policy):
+    """max_min_fairness_strategy_proof.py:13-44: max-min fairness with every throughput set to 1.0."""
+    def __init__(self, solver):
+        self._name = "MaxMinFairness"
+        self._max_min_fairness_perf_policy = MaxMinFairnessPolicyWithPerf(solver)
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, priority_weights, cluster_spec):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        ones = {j: {w: 1.0 for w in unflattened_throughputs[j]} for j in unflattened_throughputs}
+        return self._max_min_fairness_perf_policy.get_allocation(ones, scale_factors, priority_weights, cluster_spec)
+
+
 class FinishTimeFairnessPolicyWithPerf(Policy):
     def __init__(self, solver):
         Policy.__init__(self, solver)
@@ -473,7 +670,7 @@ class ShockwavePolicy(Policy):
         self._name = "shockwave"
 
 
-def get_policy(policy_name, solver=None, seed=None):
+def get_policy(policy_name, solver=None, seed=None, priority_reweighting_policies=None):
     """The GPU-backed subset of utils.get_policy (scheduler/utils.py:603-685)."""
     table = {
         "finish_time_fairness": lambda: FinishTimeFairnessPolicy(solver="GUROBI"),
@@ -481,6 +678,10 @@ def get_policy(policy_name, solver=None, seed=None):
         "gandiva_fair": GandivProportionalPolicy, "isolated": IsolatedPolicy, "isolated_plus": IsolatedPlusPolicy,
         "max_min_fairness": lambda: MaxMinFairnessPolicy(solver=solver),
         "max_min_fairness_perf": lambda: MaxMinFairnessPolicyWithPerf(solver=solver),
+        "max_min_fairness_water_filling": lambda: MaxMinFairnessWaterFillingPolicy(
+            priority_reweighting_policies=priority_reweighting_policies),
+        "max_min_fairness_water_filling_perf": lambda: MaxMinFairnessWaterFillingPolicyWithPerf(
+            priority_reweighting_policies=priority_reweighting_policies),
         "max_sum_throughput_perf": lambda: ThroughputSumWithPerf(solver=solver),
         "max_sum_throughput_normalized_by_cost_perf": lambda: ThroughputNormalizedByCostSumWithPerf(solver=solver),
         "max_sum_throughput_normalized_by_cost_perf_SLOs": lambda: ThroughputNormalizedByCostSumWithPerfSLOs(solver=solver),
