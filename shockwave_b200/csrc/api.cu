@@ -93,6 +93,9 @@ struct swb_ctx {
   int last_passes = 0;
   // pinned staging for the scalar results
   swb_result *h_res = nullptr;
+  unsigned char *h_stage = nullptr;   // pinned staging of the per-call inputs / outputs of swb_round_solve / swb_forecast
+  size_t h_stage_cap = 0;
+  DBuf f_in;                          // device arena of the per-call forecast inputs (one H2D copy)
   size_t h_res_cap = 0;
 };
 
@@ -142,6 +145,8 @@ void swb_destroy(swb_ctx *c) {
                  &c->het_a, &c->het_N, &c->het_x, &c->wf_z, &c->wf_x2};
   for (DBuf *b : all) b->release();
   if (c->h_res) cudaFreeHost(c->h_res);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  c->f_in.release();
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 2; ++i) if (c->mev[i]) cudaEventDestroy(c->mev[i]);
   if (c->st) cudaStreamDestroy(c->st);
@@ -184,6 +189,18 @@ static int ensure_hres(swb_ctx *c, size_t S) {
     c->h_res = nullptr;
     CK(cudaMallocHost((void **)&c->h_res, S * sizeof(swb_result)));
     c->h_res_cap = S;
+  }
+  return 0;
+}
+
+static int ensure_hstage(swb_ctx *c, size_t bytes) {
+  if (bytes > c->h_stage_cap) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->h_stage_cap = 0;
+    size_t cap = 1 << 16;
+    while (cap < bytes) cap *= 2;
+    CK(cudaMallocHost((void **)&c->h_stage, cap));
+    c->h_stage_cap = cap;
   }
   return 0;
 }
@@ -541,21 +558,27 @@ static int run_forecast(swb_ctx *c, const swb_params *prm, const swb_round_args 
     if (a->epoch_progress[j] < 0 || a->epoch_progress[j] > c->h_E[s])
       return fail(SWB_ERR_ARG, "epoch_progress out of range (JobMetaData.py:164)");
   }
-  CK(c->f_slots.need(J * 4, c->st)); CK(c->f_prog.need(J * 4, c->st)); CK(c->f_mend.need(J * 4, c->st));
-  CK(c->f_mns.need(J * 8, c->st));
   CK(c->g.need(J * 4, c->st)); CK(c->E.need(J * 4, c->st)); CK(c->c.need(J * 4, c->st));
   CK(c->dbar.need(J * 8, c->st)); CK(c->rem.need(J * 8, c->st)); CK(c->ftobj.need(J * 8, c->st));
   CK(c->bfkey.need(J * 8, c->st)); CK(c->f_remfb.need(J * 8, c->st)); CK(c->f_bffb.need(J * 8, c->st));
   CK(c->f_ampok.need(J * 8, c->st)); CK(c->f_ampfb.need(J * 8, c->st)); CK(c->f_ftest.need(J * 8, c->st));
-  CK(cudaMemcpyAsync(c->f_slots.p, a->slots, J * 4, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->f_prog.p, a->epoch_progress, J * 4, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->f_mend.p, a->meas_end_round, J * 4, cudaMemcpyHostToDevice, c->st));
-  CK(cudaMemcpyAsync(c->f_mns.p, a->meas_nsamples, J * 8, cudaMemcpyHostToDevice, c->st));
+  // the four per-call input arrays (20 bytes per job) travel as ONE copy from pinned staging: a cudaMemcpyAsync from
+  // pageable memory is a staged, synchronous copy of its own (every API call ends with a stream sync, so the staging
+  // buffer is free again when the next call starts)
+  const size_t Jz = (size_t)J;
+  { int rcs = ensure_hstage(c, 84 * Jz + 64); if (rcs) return rcs; }
+  CK(c->f_in.need(20 * Jz, c->st));
+  memcpy(c->h_stage, a->meas_nsamples, 8 * Jz);
+  memcpy(c->h_stage + 8 * Jz, a->slots, 4 * Jz);
+  memcpy(c->h_stage + 12 * Jz, a->epoch_progress, 4 * Jz);
+  memcpy(c->h_stage + 16 * Jz, a->meas_end_round, 4 * Jz);
+  CK(cudaMemcpyAsync(c->f_in.p, c->h_stage, 20 * Jz, cudaMemcpyHostToDevice, c->st));
+  unsigned char *din = reinterpret_cast<unsigned char *>(c->f_in.p);
   swb::ForecastLaunch F;
   F.J = J; F.reestimate_share = a->reestimate_share; F.round_ptr = prm->round_ptr; F.ngpus = prm->ngpus;
   F.gavel_round_duration = a->gavel_round_duration;
-  F.slots = c->f_slots.as<int32_t>(); F.progress = c->f_prog.as<int32_t>();
-  F.meas_end = c->f_mend.as<int32_t>(); F.meas_ns = c->f_mns.as<double>();
+  F.meas_ns = reinterpret_cast<double *>(din); F.slots = reinterpret_cast<int32_t *>(din + 8 * Jz);
+  F.progress = reinterpret_cast<int32_t *>(din + 12 * Jz); F.meas_end = reinterpret_cast<int32_t *>(din + 16 * Jz);
   F.tab_off = c->t_off.as<int64_t>(); F.tab_E = c->t_E.as<int32_t>(); F.tab_nmodes = c->t_nm.as<int32_t>();
   F.tab_g = c->t_g.as<int32_t>(); F.tab_nsamples = c->t_ns.as<double>(); F.tab_tsubmit = c->t_ts.as<double>();
   F.tab_modes = c->t_modes.as<int32_t>(); F.tab_modemean = c->t_mm.as<double>(); F.tab_amp = c->t_amp.as<double>();
@@ -591,7 +614,7 @@ int swb_round_solve(swb_ctx *c, const swb_params *prm, const swb_round_args *a) 
     Gm.J = J; Gm.P_local = c->gbm_paths; Gm.path_offset = 0; Gm.seed = c->gbm_seed ^ (uint64_t)prm->round_ptr * 0x9E3779B97F4A7C15ull;
     Gm.R0 = c->rem.as<double>(); Gm.mu = nullptr; Gm.sigma = nullptr; Gm.H = nullptr;
     Gm.out = c->mc_out.as<double>();
-    Gm.slots = c->f_slots.as<int32_t>(); Gm.Eo = c->E.as<int32_t>(); Gm.co = c->c.as<int32_t>();
+    Gm.slots = c->last_fc.slots; Gm.Eo = c->E.as<int32_t>(); Gm.co = c->c.as<int32_t>();
     Gm.tab_mu = c->t_mu.as<double>(); Gm.tab_sigma = c->t_sg.as<double>(); Gm.Hmax = c->gbm_hmax;
     CK(swb::launch_gbm(Gm, c->st));
     swb::GbmApplyLaunch Ga;
@@ -621,19 +644,27 @@ int swb_round_solve(swb_ctx *c, const swb_params *prm, const swb_round_args *a) 
   CK(cudaMemcpyAsync(c->h_res, c->res.p, sizeof(swb_result), cudaMemcpyDeviceToHost, c->st));
   if (a->x) CK(cudaMemcpyAsync(a->x, c->x.p, nx, cudaMemcpyDeviceToHost, c->st));
   if (a->backfill) CK(cudaMemcpyAsync(a->backfill, c->bf.p, nx, cudaMemcpyDeviceToHost, c->st));
-  if (a->xmask) CK(cudaMemcpyAsync(a->xmask, dxm, (size_t)J * 16, cudaMemcpyDeviceToHost, c->st));
-  if (a->bfmask) CK(cudaMemcpyAsync(a->bfmask, dbm, (size_t)J * 16, cudaMemcpyDeviceToHost, c->st));
-  if (a->nrounds) CK(cudaMemcpyAsync(a->nrounds, c->nr.p, (size_t)J * 4, cudaMemcpyDeviceToHost, c->st));
-  if (a->forecast_out) {
-    double *fo = a->forecast_out;  // [6][J] planes: dbar, rem, ftobj, bfkey, rem_fb, bfkey_fb
-    CK(cudaMemcpyAsync(fo, c->dbar.p, J * 8, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(fo + J, c->rem.p, J * 8, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(fo + 2 * (size_t)J, c->ftobj.p, J * 8, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(fo + 3 * (size_t)J, c->bfkey.p, J * 8, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(fo + 4 * (size_t)J, c->f_remfb.p, J * 8, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(fo + 5 * (size_t)J, c->f_bffb.p, J * 8, cudaMemcpyDeviceToHost, c->st));
+  // the packed outputs (84 bytes per job) come back through the pinned staging buffer — truly asynchronous copies and
+  // one sync — and are handed to the caller's (pageable) arrays by memcpy
+  unsigned char *hs = c->h_stage;
+  const size_t Jz = (size_t)J;
+  if (a->xmask) CK(cudaMemcpyAsync(hs, dxm, 16 * Jz, cudaMemcpyDeviceToHost, c->st));
+  if (a->bfmask) CK(cudaMemcpyAsync(hs + 16 * Jz, dbm, 16 * Jz, cudaMemcpyDeviceToHost, c->st));
+  if (a->nrounds) CK(cudaMemcpyAsync(hs + 32 * Jz, c->nr.p, 4 * Jz, cudaMemcpyDeviceToHost, c->st));
+  if (a->forecast_out) {   // [6][J] planes: dbar, rem, ftobj, bfkey, rem_fb, bfkey_fb
+    unsigned char *fo = hs + 36 * Jz;
+    CK(cudaMemcpyAsync(fo, c->dbar.p, 8 * Jz, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fo + 8 * Jz, c->rem.p, 8 * Jz, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fo + 16 * Jz, c->ftobj.p, 8 * Jz, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fo + 24 * Jz, c->bfkey.p, 8 * Jz, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fo + 32 * Jz, c->f_remfb.p, 8 * Jz, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fo + 40 * Jz, c->f_bffb.p, 8 * Jz, cudaMemcpyDeviceToHost, c->st));
   }
   CK(cudaStreamSynchronize(c->st));
+  if (a->xmask) memcpy(a->xmask, hs, 16 * Jz);
+  if (a->bfmask) memcpy(a->bfmask, hs + 16 * Jz, 16 * Jz);
+  if (a->nrounds) memcpy(a->nrounds, hs + 32 * Jz, 4 * Jz);
+  if (a->forecast_out) memcpy(a->forecast_out, hs + 36 * Jz, 48 * Jz);
   *a->res = *c->h_res;
   return a->res->status == SWB_ST_FALLBACK ? SWB_ST_FALLBACK : SWB_ST_OK;
 }

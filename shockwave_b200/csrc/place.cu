@@ -28,10 +28,16 @@ __device__ __forceinline__ unsigned long long dbl_order_key(double v) {
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);  // ascending order-preserving
 }
 
-// bitonic sort, DESCENDING by (key, then ascending idx) over n = power of two entries
+// bitonic sort, DESCENDING by (key, then ascending idx) over n = power of two entries (n >= 64, blockDim a multiple of
+// 32).  Strides >= 32 go through shared memory (one barrier each); the strides 16..1 that end every merge level stay in
+// registers: element i lives in lane i % 32 of its warp, its partner i ^ j in lane (i % 32) ^ j, so the five
+// compare-exchanges are shuffles with one barrier for all of them (36 barriers instead of 78 at n = 4096).
 __device__ void sort_desc64(unsigned long long *key, unsigned short *idx, int n) {
   for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
+    // all levels k <= 32 run inside one register pass (k = 32 carries them)
+    if (k < 32) continue;
+    int j = k >> 1;
+    for (; j >= 32; j >>= 1) {
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int p = i ^ j;
         if (p > i) {
@@ -44,6 +50,23 @@ __device__ void sort_desc64(unsigned long long *key, unsigned short *idx, int n)
       }
       __syncthreads();
     }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      unsigned long long a = key[i];
+      int ia = idx[i];
+      for (int kk = (k == 32 ? 2 : k); kk <= k; kk <<= 1) {
+        const bool up = (i & kk) == 0;
+        for (int jj = (kk >> 1) > 16 ? 16 : (kk >> 1); jj > 0; jj >>= 1) {
+          const unsigned long long b = __shfl_xor_sync(SWB_FULL, a, jj);
+          const int ib = __shfl_xor_sync(SWB_FULL, ia, jj);
+          const bool mine_first = (a > b) || (a == b && ia < ib);
+          const bool keep_first = (((i & jj) == 0) == up);
+          if (keep_first != mine_first) { a = b; ia = ib; }
+        }
+      }
+      key[i] = a;
+      idx[i] = (unsigned short)ia;
+    }
+    __syncthreads();
   }
 }
 
@@ -117,7 +140,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
   // ---- shared-memory carve-up -------------------------------------------------------------
   unsigned char *p = smem_raw;
   double *red = reinterpret_cast<double *>(p); p += 2 * 64 * sizeof(double);
-  int *wsum = reinterpret_cast<int *>(p);      p += 32 * sizeof(int);
+  p += 32 * sizeof(int);                       // (scan scratch of the former block-wide sweep)
   int *idle = reinterpret_cast<int *>(p);      p += SWB_MAX_T * sizeof(int);
   int *load_of = reinterpret_cast<int *>(p);   p += SWB_MAX_T * sizeof(int);
   unsigned int *binA = reinterpret_cast<unsigned int *>(p); p += SWB_MAX_T * sizeof(int);
@@ -197,60 +220,76 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     for (int j = threadIdx.x; j < npad; j += blockDim.x) remr[j] = j < J ? nplan[j] : 0;
     __syncthreads();
     t0 = T;
+    // One round = (a) the CRITICAL jobs (remaining count == rounds left; all of them must fit) seated by the whole block
+    // with one reduction, then (b) a SEQUENTIAL greedy in priority order — a job is seated if it still fits — walked by
+    // warp 0 alone over 32 jobs at a time: no block barrier inside the walk (the block-wide version of this loop spent
+    // ~16 barriers per round and dominated the fallback placement at 4096 jobs).  The greedy is the fixed point of
+    // "take the longest prefix of the eligible jobs that fits, repeat", i.e. exactly what the multi-pass form computed.
+    __shared__ int s_sw_cap, s_sw_first;
+    if (threadIdx.x == 0) s_sw_first = 0;
     for (int t = 0; t < T; ++t) {
       const int tau = T - t;
       int capleft = G;
-      int has_crit = 0;
+      int fail = 0;
+      const int wt = t >> 6;
+      const unsigned long long bt = 1ull << (t & 63);
+      // (a) critical jobs
+      int csum = 0;
       for (int q = 0; q < chs; ++q) {
         const int pos = p0 + q;
         if (pos < npad) {
           const int j = ordr[pos];
-          if (j != 0xffff && remr[j] >= tau) has_crit = 1;
+          if (j != 0xffff && remr[j] > 0 && remr[j] >= tau) csum += gs[j];
         }
       }
-      has_crit = __syncthreads_or(has_crit);
-      // stage 0: critical jobs (all of them must fit); stage 1: best priority density first, as they fit;
-      // every pass takes a strict prefix of the eligible jobs in priority order
-      int stage = has_crit ? 0 : 1;
-      int fail = 0;
-      for (int pass = 0; pass < 80; ++pass) {
-        int lsum = 0;
-        for (int q = 0; q < chs; ++q) {
-          const int pos = p0 + q;
-          if (pos < npad) {
-            const int j = ordr[pos];
-            if (j != 0xffff && remr[j] > 0 && !((bm[2 * j + (t >> 6)] >> (t & 63)) & 1ull)) {
-              const bool el = stage == 0 ? (remr[j] >= tau) : ((int)gs[j] <= capleft);
-              if (el) lsum += gs[j];
-            }
-          }
-        }
-        int tot = 0;
-        int run = block_excl_scan(lsum, wsum, &tot);
-        if (stage == 0 && tot > capleft) { fail = 1; break; }       // the critical jobs alone do not fit
-        int took = 0;
-        if (tot > 0) {
+      const int ctot = (int)br.sumll((long long)csum);
+      if (ctot > capleft) {
+        fail = 1;                                  // the critical jobs alone do not fit
+      } else {
+        if (csum > 0)
           for (int q = 0; q < chs; ++q) {
             const int pos = p0 + q;
             if (pos < npad) {
               const int j = ordr[pos];
-              if (j != 0xffff && remr[j] > 0 && !((bm[2 * j + (t >> 6)] >> (t & 63)) & 1ull)) {
-                const bool el = stage == 0 ? (remr[j] >= tau) : ((int)gs[j] <= capleft);
-                if (el) {
-                  run += gs[j];
-                  if (run <= capleft) { bm[2 * j + (t >> 6)] |= 1ull << (t & 63); remr[j] = (unsigned char)(remr[j] - 1); took += gs[j]; }
-                }
-              }
+              if (j != 0xffff && remr[j] > 0 && remr[j] >= tau) { bm[2 * j + wt] |= bt; remr[j] = (unsigned char)(remr[j] - 1); }
             }
           }
-        }
-        const int taken = (int)br.sumll((long long)took);
-        capleft -= taken;
-        dem -= taken;
+        capleft -= ctot;
         __syncthreads();
-        if (capleft <= 0) break;
-        if (stage == 0) { stage = 1; continue; }
-        if (tot == 0 || taken == tot) break;     // nobody else fits
+        // (b) greedy walk by warp 0
+        if (threadIdx.x < 32) {
+          const int lane = threadIdx.x;
+          int cap = capleft, first = s_sw_first;
+          bool lead = true;                        // still inside the finished prefix of the priority order
+          for (int base = first; base < npad && cap > 0; base += 32) {
+            const int j = ordr[base + lane];
+            const bool live = (j != 0xffff) && remr[j] > 0;
+            if (lead) { if (!__any_sync(SWB_FULL, live)) { first = base + 32; continue; } lead = false; }
+            const int g = live ? (int)gs[j] : 0;
+            bool el = live && !(bm[2 * j + wt] & bt) && g <= cap;
+            while (true) {
+              const unsigned int em = __ballot_sync(SWB_FULL, el);
+              if (em == 0u) break;
+              int incl = el ? g : 0;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(SWB_FULL, incl, o); if (lane >= o) incl += v; }
+              const bool take = el && incl <= cap;
+              const unsigned int tm = __ballot_sync(SWB_FULL, take);
+              const unsigned int viol = em & ~tm;                    // eligible lanes that no longer fit
+              if (take) { bm[2 * j + wt] |= bt; remr[j] = (unsigned char)(remr[j] - 1); }
+              const int got = __reduce_add_sync(SWB_FULL, take ? g : 0);
+              cap -= got;
+              if (viol == 0u) break;
+              const int vb = __ffs(viol) - 1;                        // first job that did not fit: skipped for good
+              el = el && !take && lane > vb && g <= cap;
+            }
+          }
+          if (lane == 0) { s_sw_cap = cap; s_sw_first = first; }
+        }
+        __syncthreads();
+        const int ncap = s_sw_cap;
+        dem -= (long long)(G - ncap);
+        capleft = ncap;
       }
       if (!fail) {
         if (threadIdx.x == 0) idle[t] = capleft;

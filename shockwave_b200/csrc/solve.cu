@@ -85,6 +85,23 @@ struct ClusterRed {
     }
     return a;
   }
+  __device__ __forceinline__ void sumi3(int &a, int &b, int &c) {
+    br.sumi3(a, b, c);
+    if constexpr (CL > 1) {
+      cg::cluster_group cl = cg::this_cluster();
+      int *xi = reinterpret_cast<int *>(xs);                    // a slot is 16 bytes: three ints fit
+      if (threadIdx.x == 0) { xi[xphase * 4] = a; xi[xphase * 4 + 1] = b; xi[xphase * 4 + 2] = c; }
+      cl.sync();
+      int ra = 0, rb = 0, rc = 0;
+#pragma unroll
+      for (int q = 0; q < CL; ++q) {
+        const int *rem = reinterpret_cast<const int *>(cl.map_shared_rank(xs, q)) + xphase * 4;
+        ra += rem[0]; rb += rem[1]; rc += rem[2];
+      }
+      a = ra; b = rb; c = rc;
+      xphase ^= 1;
+    }
+  }
   __device__ __forceinline__ double max(double a) { a = br.max(a); double b = 0.0; exchange2(a, b, 1); return a; }
   __device__ __forceinline__ double min(double a) { return -max(-a); }
   // all-gather of one value per CTA (rank order) — used for the prefix of the tie-fill
@@ -169,68 +186,87 @@ __device__ long long cost_at(const Ctx &c, Red &br, double M, double mu) {
   return (long long)br.sumi(s);
 }
 
+// demand at three prices in one pass over the jobs and ONE reduction: an evaluation costs a block (cluster) barrier,
+// not arithmetic, so three candidates per barrier shorten the search by the number of passes it saves
+template <class Red>
+__device__ void cost_at3(const Ctx &c, Red &br, double M, double mu0, double mu1, double mu2, long long &c0,
+                         long long &c1, long long &c2) {
+  const double Md = M * c.invD;
+  int s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll 2
+  for (int j = c.j0 + threadIdx.x; j < c.j1; j += blockDim.x) {
+    const int L = lower_n(c, j, Md), g = (int)c.t.g[j];
+    s0 += g * max(L, pref_n(c, j, mu0));
+    s1 += g * max(L, pref_n(c, j, mu1));
+    s2 += g * max(L, pref_n(c, j, mu2));
+  }
+  br.sumi3(s0, s1, s2);
+  c0 = s0; c1 = s1; c2 = s2;
+}
+
 struct Price { double hi, lo; long long cost_hi; int iters; };
 
 // smallest price at which demand fits: cost(M, hi) <= GT < cost(M, lo).
-// Bisection on the BIT PATTERN of the (positive) price: the fallback priorities span 20+ orders of
+// Search on the BIT PATTERN of the (positive) price: the fallback priorities span 20+ orders of
 // magnitude (ratio^lam, shockwave.py:899-903), so an arithmetic midpoint would stop far above the real
 // clearing price and lump every cheaper item into one "tie".  Positive doubles are ordered like their bit
 // patterns.  The loop ends when hi/lo - 1 < 2^-prec; everything priced inside such an interval is treated
 // as a tie and filled in job order (prec = 12 while searching the makespan threshold, 22 for the final
 // allocation; the response function itself has fp32 resolution).  `hint` (> 0) is the clearing price of a
 // neighbouring threshold: the search then starts from [hint/4, 4 hint] when that bracket holds.
+// Every pass evaluates THREE prices (cost_at3): the first one the free price 0 and both ends of the hint bracket, the
+// later ones the regula-falsi point of the bracket (the excess demand is a step function, but close to linear in
+// log(price) at the scale of the bracket) flanked at +-1/8 of the bracket; a pass that shrinks the bracket by less
+// than half is followed by a pass at the quarter points (guaranteed factor 4), so the worst case stays logarithmic.
 template <class Red>
 __device__ Price solve_price(const Ctx &c, Red &br, double M, double mu_max, int prec, double hint) {
   Price p;
   p.iters = 1;
-  long long c0 = cost_at(c, br, M, 0.0);
+  const double h4 = hint > 0.0 ? fmin(mu_max, hint * 4.0) : mu_max, l4 = hint > 0.0 ? hint * 0.25 : mu_max;
+  long long c0, ch, cl;
+  cost_at3(c, br, M, 0.0, h4, l4, c0, ch, cl);
   if (c0 <= c.GT) { p.hi = p.lo = 0.0; p.cost_hi = c0; return p; }
   unsigned long long lob = 0ull, hib = (unsigned long long)__double_as_longlong(mu_max);
   double lo = 0.0, hi = mu_max;
   long long chi = -1, clo = -1;     // demand at hi / at lo (-1: not evaluated; lo = 0 has no log-scale position)
   if (hint > 0.0) {
-    const double h4 = fmin(mu_max, hint * 4.0), l4 = hint * 0.25;
-    const long long ch = cost_at(c, br, M, h4);
-    p.iters++;
     if (ch <= c.GT) { hi = h4; hib = (unsigned long long)__double_as_longlong(h4); chi = ch; }
-    const long long cl = cost_at(c, br, M, l4);
-    p.iters++;
     if (cl > c.GT) { lo = l4; lob = (unsigned long long)__double_as_longlong(l4); clo = cl; }
     else if (chi >= 0 || l4 < hi) { hi = l4; hib = (unsigned long long)__double_as_longlong(l4); chi = cl; }
+  } else {
+    chi = ch;                       // h4 = mu_max
   }
   if (chi < 0) { chi = cost_at(c, br, M, hi); p.iters++; }
   const unsigned long long width = 1ull << (52 - prec);
-  // Regula falsi (Illinois variant) on the bit pattern, i.e. in log(price): the excess demand is a step function, but
-  // at the scale of the bracket it is close to linear in log(price), so interpolating between the two ends lands
-  // near the clearing price in a few evaluations; the Illinois halving of a stale end keeps the worst case
-  // logarithmic, and a plain bisection step is taken when the interpolation stops making progress.
   double flo = clo >= 0 ? (double)(clo - c.GT) : -1.0, fhi = (double)(chi - c.GT);
-  int side = 0, stall = 0;
-  while (hib - lob > width) {
+  bool quarters = false;
+  while (hib - lob > width && fhi != 0.0) {
     const unsigned long long span = hib - lob;
-    unsigned long long midb = lob + (span >> 1);
-    if (flo > 0.0 && fhi < 0.0 && stall < 2 && lob != 0ull) {
-      double frac = flo / (flo - fhi);
-      frac = fmin(0.95, fmax(0.05, frac));
-      midb = lob + (unsigned long long)((double)span * frac);
-      if (midb <= lob) midb = lob + 1;
-      if (midb >= hib) midb = hib - 1;
+    double f1 = 0.25, f2 = 0.5, f3 = 0.75;
+    if (!quarters && flo > 0.0 && fhi < 0.0 && lob != 0ull) {
+      f2 = fmin(0.85, fmax(0.15, flo / (flo - fhi)));
+      f1 = f2 - 0.125; f3 = f2 + 0.125;
     }
-    const double mid = __longlong_as_double((long long)midb);
-    const long long cm = cost_at(c, br, M, mid);
+    unsigned long long b1 = lob + (unsigned long long)((double)span * f1);
+    unsigned long long b2 = lob + (unsigned long long)((double)span * f2);
+    unsigned long long b3 = lob + (unsigned long long)((double)span * f3);
+    if (b1 <= lob) b1 = lob + 1;
+    if (b2 <= b1) b2 = b1 + 1;
+    if (b3 <= b2) b3 = b2 + 1;
+    if (b3 >= hib) b3 = hib - 1;              // span > width >= 2^30: the three points stay distinct and interior
+    const double m1 = __longlong_as_double((long long)b1), m2 = __longlong_as_double((long long)b2),
+                 m3 = __longlong_as_double((long long)b3);
+    long long k1, k2, k3;
+    cost_at3(c, br, M, m1, m2, m3, k1, k2, k3);
     p.iters++;
-    const unsigned long long nspan = (cm <= c.GT) ? midb - lob : hib - midb;
-    stall = (nspan > span - (span >> 2)) ? stall + 1 : 0;      // shrank by less than a quarter
-    if (cm <= c.GT) {
-      hib = midb; hi = mid; chi = cm; fhi = (double)(cm - c.GT);
-      if (cm == c.GT) break;
-      if (side == 1 && flo > 0.0) flo *= 0.5;
-      side = 1;
-    } else {
-      lob = midb; lo = mid; flo = (double)(cm - c.GT);
-      if (side == -1) fhi *= 0.5;
-      side = -1;
-    }
+    // demand is non-increasing in the price: the new bracket is the sub-interval where it crosses GT
+    if (k1 <= c.GT) { hib = b1; hi = m1; chi = k1; }
+    else if (k2 <= c.GT) { lob = b1; lo = m1; clo = k1; hib = b2; hi = m2; chi = k2; }
+    else if (k3 <= c.GT) { lob = b2; lo = m2; clo = k2; hib = b3; hi = m3; chi = k3; }
+    else { lob = b3; lo = m3; clo = k3; }
+    flo = clo >= 0 ? (double)(clo - c.GT) : -1.0;
+    fhi = (double)(chi - c.GT);
+    quarters = (hib - lob) > (span >> 1);
   }
   p.hi = hi; p.lo = lo; p.cost_hi = chi;
   return p;

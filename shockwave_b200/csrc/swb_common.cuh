@@ -103,6 +103,18 @@ struct BlockRed {
     phase ^= 1;
     return a;
   }
+  // three int32 sums with ONE barrier (the price search evaluates three candidate prices per pass)
+  __device__ __forceinline__ void sumi3(int &a, int &b, int &c) {
+    a = __reduce_add_sync(SWB_FULL, a); b = __reduce_add_sync(SWB_FULL, b); c = __reduce_add_sync(SWB_FULL, c);
+    int *row = reinterpret_cast<int *>(s + phase * 64);       // 128 ints per row: [32 warps][3]
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (l == 0) { row[3 * w] = a; row[3 * w + 1] = b; row[3 * w + 2] = c; }
+    __syncthreads();
+    a = __reduce_add_sync(SWB_FULL, (l < nw) ? row[3 * l] : 0);
+    b = __reduce_add_sync(SWB_FULL, (l < nw) ? row[3 * l + 1] : 0);
+    c = __reduce_add_sync(SWB_FULL, (l < nw) ? row[3 * l + 2] : 0);
+    phase ^= 1;
+  }
   __device__ __forceinline__ double max(double a) {
     a = warp_max(a);
     double *row = s + phase * 64;
