@@ -651,7 +651,9 @@ def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):
         for name, call in (
                 ("max_min_fairness_perf", lambda: GP.MaxMinFairnessPolicyWithPerf("ECOS").get_allocation(thr_, sfE, prE, spec_)),
                 ("finish_time_fairness_perf", lambda: GP.FinishTimeFairnessPolicyWithPerf("GUROBI").get_allocation(
-                    thr_, sfE, prE, tE, stE, spec_))):
+                    thr_, sfE, prE, tE, stE, spec_)),
+                ("max_min_fairness_water_filling_perf", lambda: GP.MaxMinFairnessWaterFillingPolicyWithPerf().get_allocation(
+                    thr_, sfE, prE, spec_))):
             call()
             t0 = time.perf_counter()
             for _ in range(3):

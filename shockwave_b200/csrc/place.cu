@@ -217,30 +217,35 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     long long dem = 0;     // GPU-rounds still to seat; they must fit the rounds that remain
     for (int j = threadIdx.x; j < J; j += blockDim.x) dem += (long long)gs[j] * nplan[j];
     dem = br.sumll(dem);
-    for (int j = threadIdx.x; j < npad; j += blockDim.x) remr[j] = j < J ? nplan[j] : 0;
+    // the sweep works on arrays IN PRIORITY ORDER (contiguous, one 32-bit word = 4 consecutive jobs; the sort scratch is
+    // free here): width, remaining count, "seated in round t" marker (t + 1)
+    unsigned char *g_o = reinterpret_cast<unsigned char *>(key64), *rem_o = g_o + npad, *flag_o = g_o + 2 * (size_t)npad;
+    for (int pos = threadIdx.x; pos < npad; pos += blockDim.x) {
+      const int j = ordr[pos];
+      const bool v = (j != 0xffff);
+      g_o[pos] = v ? gs[j] : 0; rem_o[pos] = v ? nplan[j] : 0; flag_o[pos] = 0;
+    }
     __syncthreads();
     t0 = T;
     // One round = (a) the CRITICAL jobs (remaining count == rounds left; all of them must fit) seated by the whole block
     // with one reduction, then (b) a SEQUENTIAL greedy in priority order — a job is seated if it still fits — walked by
-    // warp 0 alone over 32 jobs at a time: no block barrier inside the walk (the block-wide version of this loop spent
-    // ~16 barriers per round and dominated the fallback placement at 4096 jobs).  The greedy is the fixed point of
-    // "take the longest prefix of the eligible jobs that fits, repeat", i.e. exactly what the multi-pass form computed.
+    // warp 0 alone, 128 jobs per step (4 per lane): no block barrier inside the walk (the block-wide multi-pass form of
+    // this loop spent ~16 barriers per round and dominated the fallback placement at 4096 jobs).  The greedy is the fixed
+    // point of "take the longest prefix of the eligible jobs that fits, repeat", i.e. exactly what that form computed.
     __shared__ int s_sw_cap, s_sw_first;
     if (threadIdx.x == 0) s_sw_first = 0;
+    int fail = 0, tfail = 0;
     for (int t = 0; t < T; ++t) {
       const int tau = T - t;
       int capleft = G;
-      int fail = 0;
       const int wt = t >> 6;
       const unsigned long long bt = 1ull << (t & 63);
+      const unsigned char mark = (unsigned char)(t + 1);
       // (a) critical jobs
       int csum = 0;
       for (int q = 0; q < chs; ++q) {
         const int pos = p0 + q;
-        if (pos < npad) {
-          const int j = ordr[pos];
-          if (j != 0xffff && remr[j] > 0 && remr[j] >= tau) csum += gs[j];
-        }
+        if (pos < npad && rem_o[pos] > 0 && rem_o[pos] >= tau) csum += g_o[pos];
       }
       const int ctot = (int)br.sumll((long long)csum);
       if (ctot > capleft) {
@@ -249,9 +254,8 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
         if (csum > 0)
           for (int q = 0; q < chs; ++q) {
             const int pos = p0 + q;
-            if (pos < npad) {
-              const int j = ordr[pos];
-              if (j != 0xffff && remr[j] > 0 && remr[j] >= tau) { bm[2 * j + wt] |= bt; remr[j] = (unsigned char)(remr[j] - 1); }
+            if (pos < npad && rem_o[pos] > 0 && rem_o[pos] >= tau) {
+              bm[2 * ordr[pos] + wt] |= bt; rem_o[pos] = (unsigned char)(rem_o[pos] - 1); flag_o[pos] = mark;
             }
           }
         capleft -= ctot;
@@ -261,27 +265,48 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
           const int lane = threadIdx.x;
           int cap = capleft, first = s_sw_first;
           bool lead = true;                        // still inside the finished prefix of the priority order
-          for (int base = first; base < npad && cap > 0; base += 32) {
-            const int j = ordr[base + lane];
-            const bool live = (j != 0xffff) && remr[j] > 0;
-            if (lead) { if (!__any_sync(SWB_FULL, live)) { first = base + 32; continue; } lead = false; }
-            const int g = live ? (int)gs[j] : 0;
-            bool el = live && !(bm[2 * j + wt] & bt) && g <= cap;
+          for (int base = first; base < npad && cap > 0; base += 128) {
+            const int q0 = base + 4 * lane;        // npad is a multiple of 128 whenever it exceeds 64
+            int g[4], rem[4];
+            bool el[4];
+            bool live = false;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool in = q0 + e < npad;
+              g[e] = in ? (int)g_o[q0 + e] : 0; rem[e] = in ? (int)rem_o[q0 + e] : 0;
+              live |= rem[e] > 0;
+              el[e] = rem[e] > 0 && flag_o[in ? q0 + e : 0] != mark && g[e] <= cap;
+            }
+            if (lead) { if (!__any_sync(SWB_FULL, live)) { first = base + 128; continue; } lead = false; }
             while (true) {
-              const unsigned int em = __ballot_sync(SWB_FULL, el);
-              if (em == 0u) break;
-              int incl = el ? g : 0;
+              int inc[4], sloc = 0;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { if (el[e]) sloc += g[e]; inc[e] = sloc; }
+              if (!__any_sync(SWB_FULL, sloc > 0)) break;
+              int incl = sloc;
 #pragma unroll
               for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(SWB_FULL, incl, o); if (lane >= o) incl += v; }
-              const bool take = el && incl <= cap;
-              const unsigned int tm = __ballot_sync(SWB_FULL, take);
-              const unsigned int viol = em & ~tm;                    // eligible lanes that no longer fit
-              if (take) { bm[2 * j + wt] |= bt; remr[j] = (unsigned char)(remr[j] - 1); }
-              const int got = __reduce_add_sync(SWB_FULL, take ? g : 0);
+              const int excl = incl - sloc;
+              int got = 0, vpos = 128;
+#pragma unroll
+              for (int e = 3; e >= 0; --e) {
+                if (el[e]) {
+                  if (excl + inc[e] <= cap) {
+                    got += g[e];
+                    rem[e] -= 1; rem_o[q0 + e] = (unsigned char)rem[e];
+                    bm[2 * ordr[q0 + e] + wt] |= bt;
+                    el[e] = false;
+                  } else {
+                    vpos = 4 * lane + e;           // ends as this lane's FIRST job that did not fit
+                  }
+                }
+              }
+              got = __reduce_add_sync(SWB_FULL, got);
+              vpos = __reduce_min_sync(SWB_FULL, vpos);
               cap -= got;
-              if (viol == 0u) break;
-              const int vb = __ffs(viol) - 1;                        // first job that did not fit: skipped for good
-              el = el && !take && lane > vb && g <= cap;
+              if (vpos == 128) break;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) el[e] = el[e] && (4 * lane + e) > vpos && g[e] <= cap;
             }
           }
           if (lane == 0) { s_sw_cap = cap; s_sw_first = first; }
@@ -295,16 +320,22 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
         if (threadIdx.x == 0) idle[t] = capleft;
         if (dem > (long long)G * (tau - 1)) fail = 2;   // what is left no longer fits the rounds that remain
       }
-      if (fail) {
-        // fail 1 is detected before round t seats anybody: the culprit is round t-1; fail 2: round t itself
-        const int tr = (fail == 1 && t > 0) ? t - 1 : t;
-        for (int j = threadIdx.x; j < J; j += blockDim.x) {
-          const unsigned long long bit = 1ull << (tr & 63);
-          if (bm[2 * j + (tr >> 6)] & bit) { bm[2 * j + (tr >> 6)] &= ~bit; remr[j] = (unsigned char)(remr[j] + 1); }
-        }
-        t0 = tr;
-        break;
+      if (fail) { tfail = t; break; }
+    }
+    __syncthreads();
+    for (int pos = threadIdx.x; pos < npad; pos += blockDim.x) {
+      const int j = ordr[pos];
+      if (j != 0xffff) remr[j] = rem_o[pos];
+    }
+    __syncthreads();
+    if (fail) {
+      // fail 1 is detected before round t seats anybody: the culprit is round t-1; fail 2: round t itself
+      const int tr = (fail == 1 && tfail > 0) ? tfail - 1 : tfail;
+      for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        const unsigned long long bit = 1ull << (tr & 63);
+        if (bm[2 * j + (tr >> 6)] & bit) { bm[2 * j + (tr >> 6)] &= ~bit; remr[j] = (unsigned char)(remr[j] + 1); }
       }
+      t0 = tr;
     }
     __syncthreads();
     for (int j = threadIdx.x; j < J; j += blockDim.x) remn[j] = remr[j];

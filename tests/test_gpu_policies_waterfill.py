@@ -45,29 +45,38 @@ def test_waterfill_iterations_match_the_oracle(J, N, seed):
     thr, sf, prio, N = _instance(J, N, seed)
     prop = gl.proportional_throughputs(thr, N)
     M = float(np.max(thr / prop[:, None] * sf[:, None]))
-    seen = []
+    seen, errs = [], []      # (run_iterations swallows exceptions of its solver hooks like the reference does: collect)
 
     def lp(thr_, sf_, N_, prop_, lower, mult, add, so_far):
         x, c = wf.lp_step(thr_, sf_, N_, prop_, lower, mult, add, so_far)
         xg, cg, zg = P._waterfill_step(N_, thr_, sf_, prop_, lower, mult, M)
-        assert xg is not None
-        assert abs(cg - c) <= 1e-9 * max(1.0, abs(c)), (cg, c)
+        seen.append(zg)
+        if (xg is None) != (x is None):
+            errs.append(("feasibility", xg is None, x is None))
+            return x, c
+        if x is None:
+            return x, c
+        if not abs(cg - c) <= 1e-9 * max(1.0, abs(c)):
+            errs.append(("objective", len(seen), cg, c))
         net = (thr_ * xg).sum(axis=1) / prop_
         need = lower + np.where(mult > 0, cg / np.where(mult > 0, mult, 1.0), 0.0)
-        assert np.all(net >= need - 1e-9 * np.maximum(1.0, need))
-        assert np.all(xg >= -1e-12) and np.all(xg.sum(axis=1) <= 1 + 1e-9)
-        assert np.all((xg * sf_[:, None]).sum(axis=0) <= N_ * (1 + 1e-9))
-        seen.append(zg)
+        if not np.all(net >= need - 1e-9 * np.maximum(1.0, need)):
+            errs.append(("requirement", len(seen), float((need - net).max())))
+        if not (np.all(xg >= -1e-12) and np.all(xg.sum(axis=1) <= 1 + 1e-9)
+                and np.all((xg * sf_[:, None]).sum(axis=0) <= N_ * (1 + 1e-9))):
+            errs.append(("base constraints", len(seen)))
         return x, c
 
     def bottleneck(thr_, sf_, N_, prop_, lower, so_far, zmask, M_):
         z = wf.bottleneck_milp(thr_, sf_, N_, prop_, lower, so_far, zmask, M_)
         zg = seen[-1]
-        assert np.array_equal(zg >= 0.5, z >= 0.5), (np.round(zg, 3), z)
+        if zg is not None and not np.array_equal(zg >= 0.5, z >= 0.5):
+            errs.append(("bottleneck set", len(seen), np.round(zg, 3).tolist(), z.tolist()))
         return z
 
     x, so_far, final, it = wf.run_iterations(list(range(J)), thr, sf, N, prop, dict(enumerate(prio)), M, lp=lp,
                                              bottleneck=bottleneck)
+    assert not errs, errs
     assert it >= 1 and len(seen) == it
 
 
