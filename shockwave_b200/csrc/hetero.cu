@@ -36,6 +36,7 @@ namespace swb {
 #define HT_MAXR 4
 #define HT_MAXC 40
 #define HT_TOL 1e-12
+#define HT_WF_LOWER (1.0 - 1e-9)
 
 struct HtShared {
   double E[HT_MAXC][HT_MAXR];    // columns: relative excess per row
@@ -77,8 +78,10 @@ __device__ __forceinline__ bool ht_requirement(const HeteroLaunch &L, int j, dou
   }
   if (L.mode == SWB_POL_MTD) { r = L.n[j] / theta; return true; }
   if (L.mode == SWB_POL_WFILL) {   // net_j = a_j.x_j / prop_j >= lower_j + theta / mult_j  (water_filling.py:127-171)
+    // the lower bounds carry a relative slack of 1e-9 (the reference's ECOS works to ~1e-8): they are the previous
+    // iteration's optimum, i.e. exactly tight against capacity, and must stay feasible under one ulp of re-association
     const double m = L.n[j];
-    r = L.den[j] * (L.t[j] + (m > 0.0 ? theta / m : 0.0));
+    r = L.den[j] * (L.t[j] * HT_WF_LOWER + (m > 0.0 ? theta / m : 0.0));
     return true;
   }
   r = 0.0;
@@ -95,7 +98,7 @@ __device__ __forceinline__ bool ht_response_wfz(const HeteroLaunch &L, int j, co
                                                 const double *q, double *x, double &level) {
   const double m = L.n[j];
   const double cprev = L.wf_c ? *L.wf_c : 0.0;
-  const double r0 = L.den[j] * (L.t[j] + (m > 0.0 ? cprev / m : 0.0));
+  const double r0 = L.den[j] * (L.t[j] * HT_WF_LOWER + (m > 0.0 ? cprev / m : 0.0));
   level = 0.0;
   if (!ht_response(a, W, r0, q, x)) return false;
   if (m > 0.0) {

@@ -38,8 +38,10 @@ template <int CL>
 struct ClusterRed {
   BlockRed br;
   double *xs;        // this CTA's published partials: [2 slots][2 values]
-  int xphase;
-  __device__ __forceinline__ ClusterRed(double *scratch, double *xslots) : br(scratch), xs(xslots), xphase(0) {}
+  int *xw;           // [2 slots][32 warps][3]: per-WARP partials of sumi3, read by every CTA of the cluster
+  int xphase, wphase;
+  __device__ __forceinline__ ClusterRed(double *scratch, double *xslots)
+      : br(scratch), xs(xslots), xw(reinterpret_cast<int *>(xslots + 4)), xphase(0), wphase(0) {}
 
   __device__ __forceinline__ void exchange2(double &a, double &b, int op) {   // op 0: sum, 1: max
     if constexpr (CL > 1) {
@@ -85,21 +87,29 @@ struct ClusterRed {
     }
     return a;
   }
+  // three demand sums per pass.  Cluster: the warp partials go straight to a cluster-visible slot and the CLUSTER barrier
+  // is the only barrier of the reduction (it also orders the CTA's own warps); lane l then adds up warp l of every CTA
+  // in rank order and a second REDUX finishes — integer sums, so every thread of every CTA holds the same totals.
   __device__ __forceinline__ void sumi3(int &a, int &b, int &c) {
-    br.sumi3(a, b, c);
     if constexpr (CL > 1) {
       cg::cluster_group cl = cg::this_cluster();
-      int *xi = reinterpret_cast<int *>(xs);                    // a slot is 16 bytes: three ints fit
-      if (threadIdx.x == 0) { xi[xphase * 4] = a; xi[xphase * 4 + 1] = b; xi[xphase * 4 + 2] = c; }
+      a = __reduce_add_sync(SWB_FULL, a); b = __reduce_add_sync(SWB_FULL, b); c = __reduce_add_sync(SWB_FULL, c);
+      const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+      int *row = xw + wphase * 96;
+      if (l == 0) { row[3 * w] = a; row[3 * w + 1] = b; row[3 * w + 2] = c; }
       cl.sync();
       int ra = 0, rb = 0, rc = 0;
+      if (l < nw) {
 #pragma unroll
-      for (int q = 0; q < CL; ++q) {
-        const int *rem = reinterpret_cast<const int *>(cl.map_shared_rank(xs, q)) + xphase * 4;
-        ra += rem[0]; rb += rem[1]; rc += rem[2];
+        for (int q = 0; q < CL; ++q) {
+          const int *rem = cl.map_shared_rank(xw, q) + wphase * 96 + 3 * l;
+          ra += rem[0]; rb += rem[1]; rc += rem[2];
+        }
       }
-      a = ra; b = rb; c = rc;
-      xphase ^= 1;
+      a = __reduce_add_sync(SWB_FULL, ra); b = __reduce_add_sync(SWB_FULL, rb); c = __reduce_add_sync(SWB_FULL, rc);
+      wphase ^= 1;
+    } else {
+      br.sumi3(a, b, c);
     }
   }
   __device__ __forceinline__ double max(double a) { a = br.max(a); double b = 0.0; exchange2(a, b, 1); return a; }
@@ -412,7 +422,7 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(SolveLaunch L) {
   Pwl *P = reinterpret_cast<Pwl *>(smem_raw);
   double *red = reinterpret_cast<double *>(smem_raw + SWB_PWL_BYTES);  // 2*64 doubles
   double *xslots = red + 2 * 64;                                       // 4 doubles: cluster exchange slots
-  unsigned char *p = smem_raw + SWB_PWL_BYTES + (2 * 64 + 4) * sizeof(double);
+  unsigned char *p = smem_raw + SWB_PWL_BYTES + (2 * 64 + 4) * sizeof(double) + 2 * 96 * sizeof(int);   // + xw
   Ctx c;
   c.j0 = jbeg; c.j1 = jend;
   const size_t so = (size_t)s * J;
@@ -717,7 +727,7 @@ static cudaError_t set_smem_attr(K kern, int static_bytes) {
 }
 
 cudaError_t launch_solve(const SolveLaunch &L, cudaStream_t st, int nbases) {
-  const size_t smem_fixed = SWB_PWL_BYTES + (2 * 64 + 4) * sizeof(double);
+  const size_t smem_fixed = SWB_PWL_BYTES + (2 * 64 + 4) * sizeof(double) + 2 * 96 * sizeof(int);
   // function attributes are per device: one flag per device ordinal (one process may drive several GPUs)
   static bool attr_done[64] = {false};
   int dev_ = 0;
