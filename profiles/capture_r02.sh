@@ -4,13 +4,14 @@
 set -x
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_r02.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-cap() {  # name regex driver-section
-  ncu --set full --clock-control none --import-source on -k "regex:$2" -s 2 -c 1 -f -o gpurun_out/$1_r02 \
+cap() {  # name regex driver-section [launches to skip]
+  ncu --set full --clock-control none --import-source on -k "regex:$2" -s ${4:-2} -c 1 -f -o gpurun_out/$1_r02 \
       python profiles/run_kernels.py $3 > gpurun_out/ncu_$1.log 2>&1
 }
 cap solve_cluster 'solve_kernel' single
 cap solve_batched 'solve_kernel' batched
 cap place_single 'place_kernel' single
+cap place_single_fb 'place_kernel' single 6      # the fallback instance (priority sweep) of the same section
 cap place_batched 'place_kernel' batched
 cap gbm 'gbm_kernel' gbm
 cap market 'market_step_kernel' market

@@ -986,7 +986,7 @@ int swb_market_pgd(swb_ctx *c, const swb_market_args *a) {
   L.obj = c->m_obj.as<double>();
   L.sigma = a->sigma; L.theta_scale = a->theta_scale;
   // jobs per CTA: enough CTAs to fill the GPU a few times, but long sweeps so the column accumulators pay
-  int split = 16;                      // CTAs per scenario
+  int split = 8;                       // CTAs per scenario (8 sweeps per thread at 4096 jobs x 64 rounds)
   if (const char *e = getenv("SWB_MK_SPLIT")) { const int v = atoi(e); if (v > 0) split = v; }
   int per = (J + split - 1) / split;
   const int sweep = 256 / (T / 4) > 0 ? 256 / (T / 4) : 1;

@@ -87,29 +87,24 @@ struct ClusterRed {
     }
     return a;
   }
-  // three demand sums per pass.  Cluster: the warp partials go straight to a cluster-visible slot and the CLUSTER barrier
-  // is the only barrier of the reduction (it also orders the CTA's own warps); lane l then adds up warp l of every CTA
-  // in rank order and a second REDUX finishes — integer sums, so every thread of every CTA holds the same totals.
+  // three demand sums per pass: block reduction first, then ONE 16-byte slot per CTA through distributed shared memory.
+  // (Publishing the per-warp partials instead and letting the cluster barrier double as the block barrier was measured
+  // twice as slow: 16 lanes x 8 CTAs x 3 remote loads per warp saturate the ~17 B/clk DSMEM port.)
   __device__ __forceinline__ void sumi3(int &a, int &b, int &c) {
+    br.sumi3(a, b, c);
     if constexpr (CL > 1) {
       cg::cluster_group cl = cg::this_cluster();
-      a = __reduce_add_sync(SWB_FULL, a); b = __reduce_add_sync(SWB_FULL, b); c = __reduce_add_sync(SWB_FULL, c);
-      const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-      int *row = xw + wphase * 96;
-      if (l == 0) { row[3 * w] = a; row[3 * w + 1] = b; row[3 * w + 2] = c; }
+      int *xi = reinterpret_cast<int *>(xs);                    // a slot is 16 bytes: three ints fit
+      if (threadIdx.x == 0) { xi[xphase * 4] = a; xi[xphase * 4 + 1] = b; xi[xphase * 4 + 2] = c; }
       cl.sync();
       int ra = 0, rb = 0, rc = 0;
-      if (l < nw) {
 #pragma unroll
-        for (int q = 0; q < CL; ++q) {
-          const int *rem = cl.map_shared_rank(xw, q) + wphase * 96 + 3 * l;
-          ra += rem[0]; rb += rem[1]; rc += rem[2];
-        }
+      for (int q = 0; q < CL; ++q) {
+        const int *rem = reinterpret_cast<const int *>(cl.map_shared_rank(xs, q)) + xphase * 4;
+        ra += rem[0]; rb += rem[1]; rc += rem[2];
       }
-      a = __reduce_add_sync(SWB_FULL, ra); b = __reduce_add_sync(SWB_FULL, rb); c = __reduce_add_sync(SWB_FULL, rc);
-      wphase ^= 1;
-    } else {
-      br.sumi3(a, b, c);
+      a = ra; b = rb; c = rc;
+      xphase ^= 1;
     }
   }
   __device__ __forceinline__ double max(double a) { a = br.max(a); double b = 0.0; exchange2(a, b, 1); return a; }

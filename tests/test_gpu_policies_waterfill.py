@@ -129,4 +129,4 @@ def test_waterfill_non_perf_and_entities():
                                                entity_to_job_mapping={k: list(v) for k, v in ent.items()},
                                                policies={"a": "fairness", "b": "fifo"})
     assert pol.last_iterations == ito
-    assert np.allclose(pol.last_so_far, so_far, rtol=2e-4, atol=1e-9)
+    assert np.allclose(pol.last_so_far, so_far, rtol=2e-4, atol=1e-7)    # (1e-9 slack on the lower bounds frees ~1e-8)
