@@ -390,13 +390,17 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
       // The result is identical to seating the 32 jobs one after the other below.
       {
         const int pp = pos + lane;
-        const bool valid = pp < J && key64[pp] != 0ull;
-        const int jj = valid ? (int)idx16[pp] : 0;
-        const int gg = valid ? (int)gs[jj] : 0, nn = valid ? (int)remn[jj] : 0;
-        const unsigned int vmask = __ballot_sync(SWB_FULL, valid);
-        const int cnt = __popc(vmask);
-        const int g0 = __shfl_sync(SWB_FULL, gg, 0);
-        const bool same = __all_sync(SWB_FULL, !valid || gg == g0);
+        const bool valid0 = pp < J && key64[pp] != 0ull;
+        const int jj = valid0 ? (int)idx16[pp] : 0;
+        const int gg0 = valid0 ? (int)gs[jj] : 0;
+        const int g0 = __shfl_sync(SWB_FULL, gg0, 0);
+        // the chunk = the leading run of jobs of the first job's width (at a boundary between two width classes the
+        // run is shorter than 32; the next iteration starts on the new width)
+        const unsigned int okm = __ballot_sync(SWB_FULL, valid0 && gg0 == g0);
+        const int cnt = (okm == 0xffffffffu) ? 32 : (__ffs((int)~okm) - 1);
+        const bool valid = lane < cnt;
+        const int nn = valid ? (int)remn[jj] : 0;
+        const bool same = true;
         int hl0 = head + Tw - 1; if (hl0 >= Tw) hl0 -= Tw;
         const int lmin = (int)(A[head] >> 8), lmax = (int)(A[hl0] >> 8);
         int incl = nn;
