@@ -97,11 +97,31 @@ def pooled_cpu(mode, N, coef, sf, t=None, n=None, den=None, select="centre"):
     return x, obj, rc
 
 
+def waterfill_step_cpu(N, thr, sf, prop, lower, mult, M, slack=1.0001):
+    """policies._waterfill_step on the HiGHS restatement (oracle/gavel_waterfill.py): the LP and the bottleneck MILP of
+    one water-filling iteration; returns (x, c, z) or (None, None, None)."""
+    from oracle import gavel_waterfill as wf
+    thr, sf, prop = np.asarray(thr, float), np.asarray(sf, float), np.asarray(prop, float)
+    lower, mult, N = np.asarray(lower, float), np.asarray(mult, float), np.asarray(N, float)
+    add = np.where(mult > 0, 0.0, M)
+    x, c = wf.lp_step(thr, sf, N, prop, lower, mult, add, lower)      # objective terms (net - lower) * mult
+    if x is None:
+        return None, None, None
+    so_far = lower + np.where(mult > 0, c / np.where(mult > 0, mult, 1.0), 0.0)
+    try:
+        z = wf.bottleneck_milp(thr, sf, N, prop, so_far, so_far, (mult <= 0).astype(float), M, slack, wf.EPSILON)
+    except RuntimeError:
+        z = np.zeros(len(sf))
+    return x, c, z
+
+
 @contextlib.contextmanager
 def cpu_backend():
     """Route shockwave_b200.policies through the HiGHS oracle for the duration of the block."""
     from shockwave_b200 import policies as P
     saved = (P._pooled, P._hetero)
+    saved_wf = P._waterfill_step
+    P._waterfill_step = waterfill_step_cpu
     def _het(mode, N, a, sf, t=None, n=None, den=None):
         out = hetero_cpu(mode, N, a, sf, t, n, den)
         _het.last_stats = (0, 0)
@@ -116,4 +136,5 @@ def cpu_backend():
         yield P
     finally:
         P._pooled, P._hetero = saved
+        P._waterfill_step = saved_wf
         P._engine = saved_engine

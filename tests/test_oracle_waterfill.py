@@ -44,3 +44,39 @@ def test_entity_reweighting_follows_the_reference_rules():
     pw = wf.compute_priority_weights({"a": 3.0, "b": 2.0}, {0: 1.0, 1: 3.0, 2: 5.0, 3: 1.0, 4: 1.0},
                                      {"a": [0, 1, 2], "b": [4, 3]}, final, [0, 1, 2, 3, 4], {"a": "fairness", "b": "fifo"})
     assert pw == {0: 3.0 * 0.25, 1: 3.0 * 0.75, 2: 0.0, 3: 2.0, 4: 0.0}
+
+
+def test_policy_host_loop_with_the_oracle_backend():
+    """shockwave_b200.policies' water-filling classes (host loop, pooling, entity re-weighting, return values) driven by
+    the HiGHS backend instead of the CUDA library: same water levels and iteration counts as the restatement of the
+    reference's own loop."""
+    from oracle import gavel_backend as gb
+    WT = ["k80", "p100", "v100"]
+    for J, N, seed in ((8, [6, 4, 2], 2), (10, [4, 3, 6], 3), (24, [6, 4, 3], 6)):
+        thr, sf, prio = _inst(J, seed)
+        N = np.asarray(N, float)
+        d = {j: {w: float(thr[j, i]) for i, w in enumerate(WT)} for j in range(J)}
+        spec = dict(zip(WT, [int(v) for v in N]))
+        with gb.cpu_backend() as P:
+            pol = P.get_policy("max_min_fairness_water_filling_perf")
+            alloc = pol.get_allocation(d, dict(enumerate(sf)), dict(enumerate(prio)), spec)
+            net2, ids = pol.get_allocation(d, dict(enumerate(sf)), dict(enumerate(prio)), spec,
+                                           return_effective_throughputs=True)
+        x = np.array([[alloc[j][w] for w in WT] for j in range(J)])
+        xo, neto, ito = wf.water_filling_perf(thr, sf, prio, N)
+        assert pol.last_iterations == ito
+        prop = gl.proportional_throughputs(thr, N)
+        assert np.allclose((thr * x).sum(axis=1) / prop, neto, rtol=1e-6, atol=1e-9)
+        assert ids == list(range(J)) and np.allclose(net2, neto, rtol=1e-6, atol=1e-9)
+    # pooled: every live type gives the job the same throughput -> one pooled type, split by capacity
+    thr, sf, prio = _inst(12, 9)
+    thr = np.repeat(thr[:, :1], 3, axis=1)
+    N = np.array([4.0, 2.0, 2.0])
+    d = {j: {w: float(thr[j, i]) for i, w in enumerate(WT)} for j in range(12)}
+    with gb.cpu_backend() as P:
+        pol = P.get_policy("max_min_fairness_water_filling")          # non-Perf: throughputs replaced by 1.0
+        alloc = pol.get_allocation(d, dict(enumerate(sf)), dict(enumerate(prio)), dict(zip(WT, [4, 2, 2])))
+    x = np.array([[alloc[j][w] for w in WT] for j in range(12)])
+    xo, neto, ito = wf.water_filling_perf(np.ones_like(thr), sf, prio, N)
+    assert np.allclose(x.sum(axis=1), neto, rtol=1e-6, atol=1e-9)
+    assert np.all((x * sf[:, None]).sum(axis=0) <= N * (1 + 1e-9))
