@@ -619,9 +619,9 @@ def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic, trow = _ncu_traffic("market_step_kernel")
+    traffic, trow = _ncu_traffic("market_step")
     out["roofline"] = {
-        "bound": "hbm", "kernel": "market_step_kernel<1,4> (dense PR-dynamics pass over X[S][J][W][T], fp32)",
+        "bound": "hbm", "kernel": "market_step_fast<1,4,16> (dense PR-dynamics pass over X[S][J][W][T], fp32)",
         "achieved": dense_bytes / (dense_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": dense_bytes / (dense_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
         "traffic_source": "profiles/ncu_kernels_r02.json (ncu --set full of this command)" if traffic else None,

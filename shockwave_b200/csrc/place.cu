@@ -232,8 +232,9 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
     // warp 0 alone, 128 jobs per step (4 per lane): no block barrier inside the walk (the block-wide multi-pass form of
     // this loop spent ~16 barriers per round and dominated the fallback placement at 4096 jobs).  The greedy is the fixed
     // point of "take the longest prefix of the eligible jobs that fits, repeat", i.e. exactly what that form computed.
-    __shared__ int s_sw_cap, s_sw_first;
-    if (threadIdx.x == 0) s_sw_first = 0;
+    __shared__ int s_sw_cap;
+    __shared__ unsigned short blk_min[64];              // 0xffff: nobody in the block needs rounds any more
+    if (threadIdx.x < 64) blk_min[threadIdx.x] = 0;     // 0 = unknown: visit
     int fail = 0, tfail = 0;
     for (int t = 0; t < T; ++t) {
       const int tau = T - t;
@@ -260,24 +261,32 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
           }
         capleft -= ctot;
         __syncthreads();
-        // (b) greedy walk by warp 0
+        // (b) greedy walk by warp 0.  blk_min[b] = a lower bound of the narrowest job of block b (128 consecutive
+        // jobs of the priority order) that still needs rounds — refreshed whenever the walk visits the block, stale only
+        // on the low side (jobs finish, they never come back) — so a block whose bound exceeds the capacity left is
+        // skipped without being read; a round that ends with a few idle GPUs nobody fits costs two ballots, not a scan
         if (threadIdx.x < 32) {
           const int lane = threadIdx.x;
-          int cap = capleft, first = s_sw_first;
-          bool lead = true;                        // still inside the finished prefix of the priority order
-          for (int base = first; base < npad && cap > 0; base += 128) {
-            const int q0 = base + 4 * lane;        // npad is a multiple of 128 whenever it exceeds 64
+          int cap = capleft;
+          const int nblk = (npad + 127) >> 7;     // <= 64
+          int nextb = 0;
+          while (cap > 0) {
+            const unsigned int m0 = __ballot_sync(SWB_FULL, lane < nblk && (int)blk_min[lane] <= cap);
+            const unsigned int m1 = __ballot_sync(SWB_FULL, lane + 32 < nblk && (int)blk_min[lane + 32] <= cap);
+            unsigned long long mm = ((unsigned long long)m1 << 32) | m0;
+            mm &= (nextb >= 64) ? 0ull : (~0ull << nextb);
+            if (mm == 0ull) break;
+            const int blk = __ffsll((long long)mm) - 1;
+            nextb = blk + 1;
+            const int q0 = (blk << 7) + 4 * lane;
             int g[4], rem[4];
             bool el[4];
-            bool live = false;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const bool in = q0 + e < npad;
               g[e] = in ? (int)g_o[q0 + e] : 0; rem[e] = in ? (int)rem_o[q0 + e] : 0;
-              live |= rem[e] > 0;
               el[e] = rem[e] > 0 && flag_o[in ? q0 + e : 0] != mark && g[e] <= cap;
             }
-            if (lead) { if (!__any_sync(SWB_FULL, live)) { first = base + 128; continue; } lead = false; }
             while (true) {
               int inc[4], sloc = 0;
 #pragma unroll
@@ -308,8 +317,14 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
 #pragma unroll
               for (int e = 0; e < 4; ++e) el[e] = el[e] && (4 * lane + e) > vpos && g[e] <= cap;
             }
+            int lm = 0xffff;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (rem[e] > 0) lm = min(lm, g[e]);
+            lm = __reduce_min_sync(SWB_FULL, lm);
+            if (lane == 0) blk_min[blk] = (unsigned short)lm;
+            __syncwarp();
           }
-          if (lane == 0) { s_sw_cap = cap; s_sw_first = first; }
+          if (lane == 0) s_sw_cap = cap;
         }
         __syncthreads();
         const int ncap = s_sw_cap;

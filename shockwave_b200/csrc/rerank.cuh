@@ -9,6 +9,9 @@
 //             = the job of width g present in a and absent from c with the smallest w_j (c - a), OR (nested widths, the
 //             reference's {1,2,4,8} gangs) a composite of two disjoint items of width g/2 — so one 4-gang can trade places
 //             with two 2-gangs or a 2-gang and two singles
+//             OR a SWAP across two classes: a job of width 2g moves a -> c while a job of width g moves c -> a — a net
+//             transfer of g GPUs, which is what lets a wide gang move up into a round that has fewer idle GPUs than
+//             its width
 //   edge slack->a  cost 0 (a round may simply lose a job);  edge c->slack cost 0 if round c has >= g idle GPUs
 // A negative cycle of one width class leaves every round's load unchanged (or moves load into idle GPUs through the
 // slack node) and lowers the objective by its (negative) cost; for unit widths cancelling until none is left is the
@@ -31,7 +34,10 @@ struct RrScratch {
   double *cost;            // [RR_MAXCLS][N*N] dense edge costs, N = T + 1, row u -> column v
   unsigned short *jobs;    // [RR_MAXCLS][T*T][RR_ITEMJOBS] jobs of the best item of every (class, pair)
   unsigned char *nj;       // [RR_MAXCLS][T*T] number of jobs of that item
+  int *log;                // [(T+1) * RR_ITEMJOBS][2] moves of the cycle being applied: job | from << 16, to
 };
+#define RR_MAXBAN 16
+#define RR_REV 0x8000u     // job entry of an item: this job moves AGAINST the edge (v -> u)
 // hot: w_j and the dense cost matrices in SHARED memory (hot != null), else in the global scratch
 __device__ __forceinline__ RrScratch rr_carve(unsigned char *base, unsigned char *hot, int J, int T) {
   const size_t N = (size_t)T + 1, TT = (size_t)T * T;
@@ -39,7 +45,9 @@ __device__ __forceinline__ RrScratch rr_carve(unsigned char *base, unsigned char
   s.wj = reinterpret_cast<double *>(base); base += (size_t)J * 8;
   s.cost = reinterpret_cast<double *>(base); base += RR_MAXCLS * N * N * 8;
   s.jobs = reinterpret_cast<unsigned short *>(base); base += RR_MAXCLS * TT * RR_ITEMJOBS * 2;
-  s.nj = base;
+  s.nj = base; base += RR_MAXCLS * TT;
+  base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(base) + 15) & ~uintptr_t(15));
+  s.log = reinterpret_cast<int *>(base);
   if (hot) {
     hot = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hot) + 15) & ~uintptr_t(15));
     s.wj = reinterpret_cast<double *>(hot);
@@ -76,26 +84,34 @@ __device__ void rr_build(const RrScratch &S, const unsigned long long *xm, const
       }
       continue;
     }
-    double c0[RR_MAXCLS], c1[RR_MAXCLS];
-    int j0[RR_MAXCLS], j1[RR_MAXCLS];
+    double c0[RR_MAXCLS], c1[RR_MAXCLS], cr[RR_MAXCLS];      // cr / jr: cheapest single job moving c -> a (against the edge)
+    int j0[RR_MAXCLS], j1[RR_MAXCLS], jr[RR_MAXCLS];
 #pragma unroll
-    for (int k = 0; k < RR_MAXCLS; ++k) { c0[k] = INF; c1[k] = INF; j0[k] = -1; j1[k] = -1; }
+    for (int k = 0; k < RR_MAXCLS; ++k) { c0[k] = INF; c1[k] = INF; cr[k] = INF; j0[k] = -1; j1[k] = -1; jr[k] = -1; }
     const int wa = a >> 6, wc = c >> 6;
     const unsigned long long ba = 1ull << (a & 63), bc = 1ull << (c & 63);
     const double dist = (double)(c - a);
     for (int j = 0; j < J; ++j) {
-      if (!(xm[2 * j + wa] & ba) || (xm[2 * j + wc] & bc)) continue;
+      const bool ina = (xm[2 * j + wa] & ba) != 0ull, inc = (xm[2 * j + wc] & bc) != 0ull;
+      if (ina == inc) continue;
       const double w = S.wj[j];
       if (w == 0.0) continue;
       const int k = cls_of[gs[j]];
       if (k >= RR_MAXCLS) continue;
-      const double x = w * dist * rr_noise(j, noise_seed);
+      if (ina) {
+        const double x = w * dist * rr_noise(j, noise_seed);
 #pragma unroll
-      for (int q = 0; q < RR_MAXCLS; ++q)
-        if (q == k) {
-          if (x < c0[q]) { c1[q] = c0[q]; j1[q] = j0[q]; c0[q] = x; j0[q] = j; }
-          else if (x < c1[q]) { c1[q] = x; j1[q] = j; }
-        }
+        for (int q = 0; q < RR_MAXCLS; ++q)
+          if (q == k) {
+            if (x < c0[q]) { c1[q] = c0[q]; j1[q] = j0[q]; c0[q] = x; j0[q] = j; }
+            else if (x < c1[q]) { c1[q] = x; j1[q] = j; }
+          }
+      } else {
+        const double x = -w * dist * rr_noise(j, noise_seed);
+#pragma unroll
+        for (int q = 0; q < RR_MAXCLS; ++q)
+          if (q == k && x < cr[q]) { cr[q] = x; jr[q] = j; }
+      }
     }
     // best / second-best ITEM per class: singles, plus the composite of the two best items of half the width
     RrItem b0, b1;                       // of the previous class
@@ -112,6 +128,13 @@ __device__ void rr_build(const RrScratch &S, const unsigned long long *xm, const
         x.cost = b0.cost + b1.cost; x.n = b0.n + b1.n;
         for (int q = 0; q < b0.n; ++q) x.job[q] = b0.job[q];
         for (int q = 0; q < b1.n; ++q) x.job[b0.n + q] = b1.job[q];
+        if (x.cost < n0.cost) { n1 = n0; n0 = x; } else if (x.cost < n1.cost) n1 = x;
+      }
+      // swap across classes: one job of the next class (twice the width) with the edge, one of this class against it
+      if (k + 1 < ncls && k + 1 < RR_MAXCLS && clsw[k + 1] == 2 * clsw[k] && j0[k + 1] >= 0 && jr[k] >= 0) {
+        RrItem x;
+        x.cost = c0[k + 1] + cr[k]; x.n = 2;
+        x.job[0] = (unsigned short)j0[k + 1]; x.job[1] = (unsigned short)(jr[k] | RR_REV);
         if (x.cost < n0.cost) { n1 = n0; n0 = x; } else if (x.cost < n1.cost) n1 = x;
       }
       S.cost[(size_t)k * N * N + pr] = n0.cost;
@@ -214,7 +237,7 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
   __shared__ short ws_pred[RR_MAXCLS * (SWB_MAX_T + 1)];
   __shared__ short ws_cyc[RR_MAXCLS * (SWB_MAX_T + 2)];
   __shared__ unsigned char s_clsof[256];
-  __shared__ int s_cls[RR_MAXCLS], s_ncls, s_found, s_len[RR_MAXCLS];
+  __shared__ int s_cls[RR_MAXCLS], s_ncls, s_found, s_len[RR_MAXCLS], s_ban[RR_MAXBAN], s_nban;
   __shared__ double s_part[32];
   const RrScratch S = rr_carve(scratch, hot, J, T);
   const int N = T + 1;
@@ -236,6 +259,7 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
     for (int q = 1; q < n; ++q) for (int r = q; r > 0 && w[r - 1] > w[r]; --r) { int t = w[r]; w[r] = w[r - 1]; w[r - 1] = t; }
     for (int q = 0; q < n; ++q) { s_cls[q] = w[q]; s_clsof[w[q]] = (unsigned char)q; }
     s_ncls = n;
+    s_nban = 0;
   }
   __syncthreads();
   const int ncls = s_ncls;
@@ -251,6 +275,8 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
   for (int iter = 0; iter < max_iters; ++iter) {
     rr_build(S, xm, gs, s_clsof, s_cls, ncls, idle, J, T, phase == 0 ? noise_seed : 0u);
     if (threadIdx.x == 0) s_found = -1;
+    __syncthreads();
+    if ((int)threadIdx.x < s_nban) S.cost[(size_t)(s_ban[threadIdx.x] >> 28) * N * N + (s_ban[threadIdx.x] & 0xfffffff)] = 1e300;
     __syncthreads();
     for (int k = warp; k < ncls; k += (int)(blockDim.x >> 5)) {       // one warp per width class
       const int len = rr_find_cycle(S.cost + (size_t)k * N * N, T, ws_d + k * 2 * (SWB_MAX_T + 1),
@@ -279,23 +305,46 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
         }
         tot += comp;
         if (!ok || !(tot < -1e-11 * scale)) continue;
-        for (int q = 0; q < len; ++q) {
+        // apply the cycle job by job with its precondition (present in the source round, absent from the target):
+        // items that mix classes can name the same job on two edges of one cycle; such a cycle is rolled back and its
+        // first offending edge is banned for the rest of the search (s_ban)
+        int nlog = 0, bad_edge = -1;
+        for (int q = 0; q < len && bad_edge < 0; ++q) {
           const int u = cyc[q], v = cyc[(q + 1) % len];
-          if (u == T) { idle[v] += s_cls[k]; continue; }           // v loses an item that no cycle edge brings back
-          if (v == T) { idle[u] -= s_cls[k]; continue; }           // u keeps an item: its idle GPUs take it
+          if (u == T || v == T) continue;
           const size_t tp = (size_t)k * T * T + (size_t)u * T + v;
           const int nj = S.nj[tp];
           for (int e = 0; e < nj; ++e) {
-            const int j = S.jobs[tp * RR_ITEMJOBS + e];
-            xm[2 * j + (u >> 6)] &= ~(1ull << (u & 63));
-            xm[2 * j + (v >> 6)] |= 1ull << (v & 63);
+            const unsigned int raw = S.jobs[tp * RR_ITEMJOBS + e];
+            const int j = (int)(raw & 0x7fffu);
+            const int from = (raw & RR_REV) ? v : u, to = (raw & RR_REV) ? u : v;
+            const unsigned long long bf = 1ull << (from & 63), bt2 = 1ull << (to & 63);
+            if (!(xm[2 * j + (from >> 6)] & bf) || (xm[2 * j + (to >> 6)] & bt2)) { bad_edge = u * N + v; break; }
+            xm[2 * j + (from >> 6)] &= ~bf;
+            xm[2 * j + (to >> 6)] |= bt2;
+            S.log[2 * nlog] = j | (from << 16); S.log[2 * nlog + 1] = to; ++nlog;
           }
+        }
+        if (bad_edge >= 0) {
+          for (int q = nlog - 1; q >= 0; --q) {
+            const int j = S.log[2 * q] & 0xffff, from = S.log[2 * q] >> 16, to = S.log[2 * q + 1];
+            xm[2 * j + (to >> 6)] &= ~(1ull << (to & 63));
+            xm[2 * j + (from >> 6)] |= 1ull << (from & 63);
+          }
+          if (s_nban < RR_MAXBAN) { s_ban[s_nban] = (k << 28) | bad_edge; s_nban = s_nban + 1; s_found = -2; }
+          continue;
+        }
+        for (int q = 0; q < len; ++q) {
+          const int u = cyc[q], v = cyc[(q + 1) % len];
+          if (u == T) idle[v] += s_cls[k];                          // v loses an item that no cycle edge brings back
+          else if (v == T) idle[u] -= s_cls[k];                     // u keeps an item: its idle GPUs take it
         }
         s_found = k;
       }
     }
     __syncthreads();
     ++phase_iters;
+    if (s_found == -2) continue;                 // a cycle was rolled back and its edge banned: search again
     if (phase == 0 && (s_found < 0 || phase_iters >= 24)) { phase = 1; continue; }
     if (s_found < 0) break;
     ++done;
