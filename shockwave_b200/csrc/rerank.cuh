@@ -9,9 +9,6 @@
 //             = the job of width g present in a and absent from c with the smallest w_j (c - a), OR (nested widths, the
 //             reference's {1,2,4,8} gangs) a composite of two disjoint items of width g/2 — so one 4-gang can trade places
 //             with two 2-gangs or a 2-gang and two singles
-//             OR a SWAP across two classes: a job of width 2g moves a -> c while a job of width g moves c -> a — a net
-//             transfer of g GPUs, which is what lets a wide gang move up into a round that has fewer idle GPUs than
-//             its width
 //   edge slack->a  cost 0 (a round may simply lose a job);  edge c->slack cost 0 if round c has >= g idle GPUs
 // A negative cycle of one width class leaves every round's load unchanged (or moves load into idle GPUs through the
 // slack node) and lowers the objective by its (negative) cost; for unit widths cancelling until none is left is the
@@ -19,6 +16,9 @@
 // same-class exchange chain and the nested cross-class ones.  Per cancelled cycle: one pass over (round pair, job)
 // (a thread per ordered pair, the job's round masks broadcast from shared memory) and one Bellman-Ford on <= 129 nodes
 // per width class (one warp each, Jacobi sweeps over a dense cost matrix in L2).
+// SWAP INTO IDLE GPUs (tried when no negative cycle is left): a job of width 2g moves a -> c while a job of width g moves
+// c -> a and round c absorbs the net g GPUs in its idle capacity — the move that lets a wide gang step up into a round
+// with fewer idle GPUs than its width (it mixes two width classes AND idle GPUs, so no single-class cycle contains it).
 // Multi-start ("noising"): with a seed the first <= 24 cycles are cancelled under weights perturbed by +-30 %, which
 // lands the search in another basin; place.cu runs 8 seeds in a thread-block cluster and keeps the best result.
 #pragma once
@@ -35,8 +35,10 @@ struct RrScratch {
   unsigned short *jobs;    // [RR_MAXCLS][T*T][RR_ITEMJOBS] jobs of the best item of every (class, pair)
   unsigned char *nj;       // [RR_MAXCLS][T*T] number of jobs of that item
   int *log;                // [(T+1) * RR_ITEMJOBS][2] moves of the cycle being applied: job | from << 16, to
+  double *swc;             // [N*N] cost of the best swap-into-idle move of the pair a -> c (1e300: none)
+  unsigned short *swj;     // [N*N][4] its jobs (with the edge, against it) and its class
 };
-#define RR_MAXBAN 16
+#define RR_MAXBAN 64
 #define RR_REV 0x8000u     // job entry of an item: this job moves AGAINST the edge (v -> u)
 // hot: w_j and the dense cost matrices in SHARED memory (hot != null), else in the global scratch
 __device__ __forceinline__ RrScratch rr_carve(unsigned char *base, unsigned char *hot, int J, int T) {
@@ -47,7 +49,9 @@ __device__ __forceinline__ RrScratch rr_carve(unsigned char *base, unsigned char
   s.jobs = reinterpret_cast<unsigned short *>(base); base += RR_MAXCLS * TT * RR_ITEMJOBS * 2;
   s.nj = base; base += RR_MAXCLS * TT;
   base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(base) + 15) & ~uintptr_t(15));
-  s.log = reinterpret_cast<int *>(base);
+  s.log = reinterpret_cast<int *>(base); base += N * RR_ITEMJOBS * 8;
+  s.swc = reinterpret_cast<double *>(base); base += N * N * 8;
+  s.swj = reinterpret_cast<unsigned short *>(base);
   if (hot) {
     hot = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hot) + 15) & ~uintptr_t(15));
     s.wj = reinterpret_cast<double *>(hot);
@@ -82,6 +86,7 @@ __device__ void rr_build(const RrScratch &S, const unsigned long long *xm, const
         else if (c == T && a != T) v = (idle[a] >= clsw[k]) ? 0.0 : INF;
         S.cost[(size_t)k * N * N + pr] = v;
       }
+      S.swc[pr] = INF;
       continue;
     }
     double c0[RR_MAXCLS], c1[RR_MAXCLS], cr[RR_MAXCLS];      // cr / jr: cheapest single job moving c -> a (against the edge)
@@ -128,20 +133,29 @@ __device__ void rr_build(const RrScratch &S, const unsigned long long *xm, const
         x.cost = b0.cost + b1.cost; x.n = b0.n + b1.n;
         for (int q = 0; q < b0.n; ++q) x.job[q] = b0.job[q];
         for (int q = 0; q < b1.n; ++q) x.job[b0.n + q] = b1.job[q];
-        if (x.cost < n0.cost) { n1 = n0; n0 = x; } else if (x.cost < n1.cost) n1 = x;
-      }
-      // swap across classes: one job of the next class (twice the width) with the edge, one of this class against it
-      if (k + 1 < ncls && k + 1 < RR_MAXCLS && clsw[k + 1] == 2 * clsw[k] && j0[k + 1] >= 0 && jr[k] >= 0) {
-        RrItem x;
-        x.cost = c0[k + 1] + cr[k]; x.n = 2;
-        x.job[0] = (unsigned short)j0[k + 1]; x.job[1] = (unsigned short)(jr[k] | RR_REV);
-        if (x.cost < n0.cost) { n1 = n0; n0 = x; } else if (x.cost < n1.cost) n1 = x;
+        bool dup = false;                  // items that contain a swap can share a job: not a valid composite
+        for (int q = 0; q < b0.n; ++q)
+          for (int r = 0; r < b1.n; ++r) dup |= ((b0.job[q] ^ b1.job[r]) & 0x7fffu) == 0u;
+        if (!dup) { if (x.cost < n0.cost) { n1 = n0; n0 = x; } else if (x.cost < n1.cost) n1 = x; }
       }
       S.cost[(size_t)k * N * N + pr] = n0.cost;
       S.nj[(size_t)k * T * T + tp] = (unsigned char)n0.n;
       for (int q = 0; q < n0.n; ++q) S.jobs[((size_t)k * T * T + tp) * RR_ITEMJOBS + q] = n0.job[q];
       b0 = n0; b1 = n1;
     }
+    // swap into idle GPUs: a job of class k+1 (twice the width) a -> c, a job of class k c -> a, round c takes the net
+    // width of class k out of its idle GPUs
+    double sb = INF;
+    int sk = 0, sA = 0, sB = 0;
+#pragma unroll
+    for (int k = 0; k + 1 < RR_MAXCLS; ++k) {
+      if (k + 1 >= ncls) break;
+      if (clsw[k + 1] != 2 * clsw[k] || j0[k + 1] < 0 || jr[k] < 0 || idle[c] < clsw[k]) continue;
+      const double x = c0[k + 1] + cr[k];
+      if (x < sb) { sb = x; sk = k; sA = j0[k + 1]; sB = jr[k]; }
+    }
+    S.swc[pr] = sb;
+    S.swj[4 * pr] = (unsigned short)sA; S.swj[4 * pr + 1] = (unsigned short)sB; S.swj[4 * pr + 2] = (unsigned short)sk;
   }
 }
 
@@ -239,6 +253,7 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
   __shared__ unsigned char s_clsof[256];
   __shared__ int s_cls[RR_MAXCLS], s_ncls, s_found, s_len[RR_MAXCLS], s_ban[RR_MAXBAN], s_nban;
   __shared__ double s_part[32];
+  __shared__ int s_parti[32];
   const RrScratch S = rr_carve(scratch, hot, J, T);
   const int N = T + 1;
   for (int j = threadIdx.x; j < J; j += blockDim.x)
@@ -343,6 +358,45 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
       }
     }
     __syncthreads();
+    if (s_found == -1) {
+      // no negative cycle: the best swap-into-idle move of any ordered pair of rounds (block arg-min, lowest pair wins ties)
+      double bv = -1e-11 * scale;
+      int bi = -1;
+      for (int pr = threadIdx.x; pr < N * N; pr += blockDim.x) {
+        const double v = S.swc[pr];
+        if (v < bv) { bv = v; bi = pr; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(SWB_FULL, bv, o);
+        const int oi = __shfl_xor_sync(SWB_FULL, bi, o);
+        if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { s_part[warp] = bv; s_parti[warp] = bi; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double gv = 0.0;
+        int gi = -1;
+        for (int q = 0; q < (int)((blockDim.x + 31) >> 5); ++q) {
+          const int oi = s_parti[q];
+          if (oi >= 0 && (gi < 0 || s_part[q] < gv || (s_part[q] == gv && oi < gi))) { gv = s_part[q]; gi = oi; }
+        }
+        if (gi >= 0) {
+          const int a = gi / N, c2 = gi - a * N;
+          const int A = S.swj[4 * gi], B = S.swj[4 * gi + 1], k = S.swj[4 * gi + 2];
+          const unsigned long long ba = 1ull << (a & 63), bc = 1ull << (c2 & 63);
+          const bool okA = (xm[2 * A + (a >> 6)] & ba) && !(xm[2 * A + (c2 >> 6)] & bc);
+          const bool okB = (xm[2 * B + (c2 >> 6)] & bc) && !(xm[2 * B + (a >> 6)] & ba);
+          if (okA && okB && idle[c2] >= s_cls[k]) {
+            xm[2 * A + (a >> 6)] &= ~ba; xm[2 * A + (c2 >> 6)] |= bc;
+            xm[2 * B + (c2 >> 6)] &= ~bc; xm[2 * B + (a >> 6)] |= ba;
+            idle[c2] -= s_cls[k]; idle[a] += s_cls[k];
+            s_found = RR_MAXCLS;                   // "a move was applied"
+          }
+        }
+      }
+      __syncthreads();
+    }
     ++phase_iters;
     if (s_found == -2) continue;                 // a cycle was rolled back and its edge banned: search again
     if (phase == 0 && (s_found < 0 || phase_iters >= 24)) { phase = 1; continue; }

@@ -68,6 +68,7 @@ __host__ __device__ inline size_t rr_scratch_bytes(int J, int T) {
   size_t b = (size_t)J * 8 + RR_MAXCLS * N * N * 8 + RR_MAXCLS * TT * RR_ITEMJOBS * 2 + RR_MAXCLS * TT;
   b = (b + 15) & ~(size_t)15;
   b += N * RR_ITEMJOBS * 8;          // move log of the cycle being applied (job, from, to)
+  b += N * N * 16;                   // best swap-into-idle move of every ordered pair of rounds (cost, jobs, class)
   return (b + 255) & ~(size_t)255;
 }
 cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask);
