@@ -97,6 +97,9 @@ int swb_sync(swb_ctx *ctx);
  * cancelled (bits 8-19), >> 20 = which of the 8 starts of the multi-start search won (0 = the un-noised one; the search
  * runs 8 starts in a thread-block cluster when at most 18 scenarios of <= 4096 jobs are placed per call). */
 #define SWB_OPT_RERANK_ITERS 6
+/* SWB_OPT_RERANK_RESTARTS: rounds of perturb-and-continue (iterated local search) after the first local optimum of
+ * every start; a round that does not improve is undone.  Default 3, at most 16, 0 = off. */
+#define SWB_OPT_RERANK_RESTARTS 7
 #define SWB_OPT_GBM_PATHS 3
 #define SWB_OPT_GBM_SEED 4
 #define SWB_OPT_GBM_HORIZON 5
@@ -309,26 +312,29 @@ int swb_gbm_ensemble(swb_ctx *ctx, int32_t S, int32_t J, double P_total, const d
                      double *rem_out_dev);
 
 /* ---- dense market iteration over X[S][J][W][T] ------------------------------------------------ *
- * Projected-gradient / price-response iterations on the dense allocation tensor (fp32, t innermost) of
- * the general volatile-Fisher-market relaxation: per-(job, type) progress rates, one capacity price per
+ * Primal-dual price-response iterations (preconditioned PDHG) on the dense allocation tensor (fp32, t innermost) of
+ * the general volatile-Fisher-market relaxation: per-(job, type) progress rates, one capacity and one price per
  * (type, round).  Objective pieces as in scheduler/shockwave.py:565-568; base constraints as in
- * scheduler/policies/policy.py:58-65 applied per round.  `iters` iterations of (small dual pass + dense
- * pass); the dense pass reads X once and writes X once.  obj = [S][3]: relaxed objective, makespan,
- * worst relative capacity violation of the final X.  dense_ms (may be NULL) = device time of the last
- * dense pass (CUDA events). */
+ * scheduler/policies/policy.py:58-65 applied per round.  `coarse_iters` iterations on the tensor coarsened to 4
+ * super-rounds (prolongated afterwards; skipped when T < 16), then `iters` iterations of (dense pass + small dual
+ * pass) on the full tensor; a dense pass reads X once and writes X once.  The returned X is feasible (a final pass
+ * scales over-subscribed columns).  obj = [S][3]: relaxed objective, makespan and worst relative capacity violation
+ * of the returned X.  dense_ms (may be NULL) = device time of the last full dense pass (CUDA events). */
 typedef struct swb_market_args {
   int32_t S, J, W, T;
   int32_t per_scenario_jobs;    /* job arrays are [S][J] (else shared [J]) */
   int32_t on_device;            /* g,E,c,dbar,rem,rate,X are device pointers */
-  int32_t iters;
-  float eta, sigma;             /* primal step (on the relative surplus), multiplicative price step */
-  float eta_decay;              /* step of iteration i is eta / (1 + i/eta_decay); 0 = constant */
-  double theta_scale;           /* multiplies the marginal utilities (gradient normalisation) */
+  int32_t iters;                /* dense passes on the full tensor */
+  int32_t coarse_iters;         /* passes on the time-coarsened tensor X_c[S][J][W][4], run first */
+  int32_t warm_start;           /* 1: X holds the starting point, 0: start from X = 0 */
+  float primal_weight;          /* PDHG step balance for the objective scaled by J T (tau = tau0/pw, sigma = sigma0 pw);
+                                   0 = default (60) */
   const swb_params *prm;        /* [S] host: k, bases/logv, round_duration are used */
   const int32_t *g;
   const double *E, *c, *dbar, *rem;
   const float *rate;            /* [J][W] epochs of progress per round on worker type w */
-  const double *Gw;             /* [W] host: workers per type */
+  const double *Gw;             /* [W] host: workers per type (used when cap is NULL) */
+  const double *cap;            /* [W][T] host: workers of type w available in round t; may be NULL */
   float *X;                     /* [S][J][W][T] in/out */
   double *obj;                  /* [S][3] host out, may be NULL */
   float *dense_ms;              /* host out, may be NULL */

@@ -14,7 +14,7 @@ cap place_single 'place_kernel' single
 cap place_single_fb 'place_kernel' single 6      # the fallback instance (priority sweep) of the same section
 cap place_batched 'place_kernel' batched
 cap gbm 'gbm_kernel' gbm
-cap market 'market_step' market
+cap market 'market_step_fast' market
 cap gavel 'gavel_round_kernel' gavel
 cap place_rerank 'place_kernel' canonical
 ls -la gpurun_out/*_r02.ncu-rep

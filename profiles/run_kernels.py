@@ -54,7 +54,7 @@ if which in ("all", "market"):
     mptr = dict(shape=(Sd, J, 1, T), per_scenario_jobs=0, g=dj["g"].data_ptr(), E=dj["E"].data_ptr(), c=dj["c"].data_ptr(),
                 dbar=dj["dbar"].data_ptr(), rem=dj["rem"].data_ptr(), rate=drate.data_ptr(), X=Xd.data_ptr())
     mprm = [make_params(G, T, D, 1e-9, 12.0, 1.0, BASES, ORIGIN) for _ in range(Sd)]
-    market_pgd(eng, mprm, None, None, None, None, None, None, [G], None, 6, 0.1, 0.3, float(J * T), device_ptrs=mptr, eta_decay=50.0)
+    market_pgd(eng, mprm, None, None, None, None, None, None, [G], None, 6, coarse_iters=100, device_ptrs=mptr)
 if which in ("all", "gavel"):           # config E: 2048 jobs, 3 worker types
     rng = np.random.default_rng(3)
     JE, W = 2048, 3

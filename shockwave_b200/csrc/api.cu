@@ -70,6 +70,7 @@ struct swb_ctx {
   DBuf gv_in, gv_out;     // swb_gavel_round: one staging buffer each way
   DBuf rr_items;          // re-rank local search scratch
   int rr_iters = 400;     // SWB_OPT_RERANK_ITERS (0 = sweep only)
+  int rr_restarts = 3;    // SWB_OPT_RERANK_RESTARTS
   DBuf pool_pp, pool_bs;
   int64_t pool_used = 0;
   // holes left by removed jobs in pool_pp / pool_bs: (offset, rows), sorted by offset, adjacent holes merged;
@@ -86,6 +87,7 @@ struct swb_ctx {
   DBuf het_a, het_N, het_x;                                                 // swb_policy_hetero
   DBuf mc_R0, mc_mu, mc_sigma, mc_H, mc_out;                                 // swb_gbm_forecast
   DBuf m_theta, m_rowp, m_colload, m_colscale, m_price, m_obj, m_X, m_rate, m_E, m_c, m_Gw;
+  DBuf m_beta, m_rowprev, m_mj, m_om, m_colprev, m_pi, m_Xc, m_cc, m_pws;   // PDHG state; m_cc = the coarse level's column arrays
   cudaEvent_t mev[2] = {nullptr, nullptr};
   double last_market_ms = 0.0;
   // CUDA events around the two kernels of the latest solve pass (bench.py's roofline)
@@ -142,6 +144,7 @@ void swb_destroy(swb_ctx *c) {
                  &c->pol_n, &c->pol_den, &c->pol_x, &c->pol_out, &c->mc_R0, &c->mc_mu, &c->mc_sigma, &c->mc_H, &c->mc_out,
                  &c->m_theta, &c->m_rowp, &c->m_colload,
                  &c->m_colscale, &c->m_price, &c->m_obj, &c->m_X, &c->m_rate, &c->m_E, &c->m_c, &c->m_Gw,
+                 &c->m_beta, &c->m_rowprev, &c->m_mj, &c->m_om, &c->m_colprev, &c->m_pi, &c->m_Xc, &c->m_cc, &c->m_pws,
                  &c->het_a, &c->het_N, &c->het_x, &c->wf_z, &c->wf_x2};
   for (DBuf *b : all) b->release();
   if (c->h_res) cudaFreeHost(c->h_res);
@@ -246,7 +249,7 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
   // re-rank local search: O(J T^2) per cancelled cycle — on where that stays in the tens of microseconds
   // (jobs x rounds^2 <= 256 Ki: 640 jobs at 20 rounds, 250 at 32, 64 at 64 — the reference's deployments; beyond that
   // the priority sweep alone places the fallback schedule)
-  P.rr_items = nullptr; P.rr_iters = 0; P.prm_T = h_prm[0].future_rounds;
+  P.rr_items = nullptr; P.rr_iters = 0; P.rr_restarts = 0; P.prm_T = h_prm[0].future_rounds;
   {
     const size_t T_ = (size_t)h_prm[0].future_rounds;
     const int cl = (S * 8 <= 144 && J <= SWB_SMEM_JOBS) ? 8 : 1;     // multi-start over a cluster (place.cu)
@@ -254,7 +257,7 @@ static int run_solve(swb_ctx *c, int S, int J, int per_scn, const swb_params *h_
     P.rr_cluster = 1;
     if (c->rr_iters > 0 && (size_t)J * T_ * T_ <= (256u << 10) && bytes <= (512u << 20)) {
       CK(c->rr_items.need(bytes, c->st));
-      P.rr_items = c->rr_items.p; P.rr_iters = c->rr_iters; P.rr_cluster = cl;
+      P.rr_items = c->rr_items.p; P.rr_iters = c->rr_iters; P.rr_restarts = c->rr_restarts; P.rr_cluster = cl;
     }
   }
   int rc2 = ensure_hres(c, S);
@@ -945,25 +948,68 @@ int swb_gbm_ensemble(swb_ctx *c, int32_t S, int32_t J, double P_total, const dou
   return 0;
 }
 
+// One level of the market iteration: measurement pass, start pass, `iters` x (dense step + dual step).  Events around
+// the last dense step when `timed`.
+static int market_level(swb_ctx *c, swb::MarketLaunch &L, int iters, bool timed) {
+  const size_t nwt = (size_t)L.S * L.W * L.T;
+  CK(swb::launch_market_fill(L.colscale, nwt, 1.0f, c->st));
+  CK(swb::launch_market_fill(L.pws, (size_t)L.S, L.pw, c->st));
+  CK(cudaMemsetAsync(L.colload, 0, nwt * 4, c->st));
+  CK(cudaMemsetAsync(L.rowp, 0, (size_t)L.S * L.J * 4, c->st));
+  L.mode = 1;                                            // measurement: X clamped to [0,1], reductions filled
+  CK(swb::launch_market_iter(L, c->st, true));
+  L.phase = 0;
+  CK(swb::launch_market_iter(L, c->st, false));
+  L.mode = 0; L.phase = 1;
+  for (int it = 0; it < iters; ++it) {
+    if (timed && it == iters - 1) CK(cudaEventRecord(c->mev[0], c->st));
+    CK(swb::launch_market_iter(L, c->st, true));
+    if (timed && it == iters - 1) CK(cudaEventRecord(c->mev[1], c->st));
+    CK(swb::launch_market_iter(L, c->st, false));
+  }
+  return 0;
+}
+
 int swb_market_pgd(swb_ctx *c, const swb_market_args *a) {
-  if (!c || !a || !a->prm || !a->g || !a->E || !a->c || !a->dbar || !a->rem || !a->rate || !a->Gw || !a->X)
+  if (!c || !a || !a->prm || !a->g || !a->E || !a->c || !a->dbar || !a->rem || !a->rate || (!a->Gw && !a->cap) || !a->X)
     return fail(SWB_ERR_ARG, "swb_market_pgd: null argument");
   const int S = a->S, J = a->J, W = a->W, T = a->T;
   if (S <= 0 || J <= 0 || W <= 0 || W > SWB_MK_MAXW || T <= 0 || (T & 3) || T > 1024)
     return fail(SWB_ERR_ARG, "swb_market_pgd: need W in [1,4], T a multiple of 4, T <= 1024");
   if (MK_CHECK_Q(T)) return fail(SWB_ERR_ARG, "swb_market_pgd: T/4 must not exceed 256");
+  if (a->iters < 0 || a->coarse_iters < 0 || a->primal_weight < 0.f)
+    return fail(SWB_ERR_ARG, "swb_market_pgd: negative iteration count or primal weight");
+  const int TC = 4, grp = T / TC;
+  const bool coarse = a->coarse_iters > 0 && T >= 16;
+  // 1 / capacity per (type, round), fine and coarse (mean over the group of rounds), host side: W T numbers
+  std::vector<float> icap((size_t)W * T + (size_t)W * TC);
+  for (int w = 0; w < W; ++w) {
+    for (int t = 0; t < T; ++t) {
+      const double cv = a->cap ? a->cap[(size_t)w * T + t] : a->Gw[w];
+      if (!(cv > 0.0)) return fail(SWB_ERR_ARG, "swb_market_pgd: capacities must be positive");
+      icap[(size_t)w * T + t] = (float)(1.0 / cv);
+    }
+    for (int tc = 0; tc < TC; ++tc) {
+      double m = 0.0;
+      for (int t = tc * grp; t < (tc + 1) * grp; ++t) m += a->cap ? a->cap[(size_t)w * T + t] : a->Gw[w];
+      icap[(size_t)W * T + (size_t)w * TC + tc] = (float)((double)grp / m);
+    }
+  }
   CK(cudaSetDevice(c->device));
   const size_t nj = a->per_scenario_jobs ? (size_t)S * J : (size_t)J, sj = (size_t)S * J;
-  const size_t nx = sj * W * T, nwt = (size_t)S * W * T;
+  const size_t nx = sj * W * T, nwt = (size_t)S * W * T, nwc = (size_t)S * W * TC;
   CK(c->prm.need(sizeof(swb_params) * S, c->st));
   CK(cudaMemcpyAsync(c->prm.p, a->prm, sizeof(swb_params) * S, cudaMemcpyHostToDevice, c->st));
-  CK(c->m_theta.need(sj * 4, c->st)); CK(c->m_rowp.need(sj * 4, c->st));
+  CK(c->m_theta.need(sj * 4, c->st)); CK(c->m_rowp.need(sj * 4, c->st)); CK(c->m_beta.need(sj * 4, c->st));
+  CK(c->m_rowprev.need(sj * 4, c->st)); CK(c->m_mj.need(sj * 8, c->st)); CK(c->m_om.need(sj * 8, c->st));
   CK(c->m_colload.need(nwt * 4, c->st)); CK(c->m_colscale.need(nwt * 4, c->st)); CK(c->m_price.need(nwt * 4, c->st));
-  CK(c->m_obj.need((size_t)S * 3 * 8, c->st)); CK(c->m_Gw.need((size_t)W * 8, c->st));
-  CK(cudaMemcpyAsync(c->m_Gw.p, a->Gw, (size_t)W * 8, cudaMemcpyHostToDevice, c->st));
+  CK(c->m_colprev.need(nwt * 4, c->st)); CK(c->m_pi.need(nwt * 8, c->st));
+  CK(c->m_obj.need((size_t)S * 3 * 8, c->st)); CK(c->m_Gw.need(icap.size() * 4, c->st));
+  CK(cudaMemcpyAsync(c->m_Gw.p, icap.data(), icap.size() * 4, cudaMemcpyHostToDevice, c->st));
   swb::MarketLaunch L;
   L.S = S; L.J = J; L.W = W; L.T = T; L.per_scn = a->per_scenario_jobs;
-  L.prm = c->prm.as<swb_params>(); L.Gw = c->m_Gw.as<double>();
+  L.Tfull = T; L.rscale = 1.f;
+  L.prm = c->prm.as<swb_params>(); L.icap = c->m_Gw.as<float>();
   if (a->on_device) {
     L.g = a->g; L.E = a->E; L.c = a->c; L.dbar = a->dbar; L.rem = a->rem; L.rate = a->rate; L.X = a->X;
   } else {
@@ -976,47 +1022,59 @@ int swb_market_pgd(swb_ctx *c, const swb_market_args *a) {
     CK(cudaMemcpyAsync(c->dbar.p, a->dbar, nj * 8, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(c->rem.p, a->rem, nj * 8, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(c->m_rate.p, a->rate, nj * W * 4, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(c->m_X.p, a->X, nx * 4, cudaMemcpyHostToDevice, c->st));
+    if (a->warm_start) CK(cudaMemcpyAsync(c->m_X.p, a->X, nx * 4, cudaMemcpyHostToDevice, c->st));
     L.g = c->g.as<int32_t>(); L.E = c->m_E.as<double>(); L.c = c->m_c.as<double>();
     L.dbar = c->dbar.as<double>(); L.rem = c->rem.as<double>(); L.rate = c->m_rate.as<float>();
     L.X = c->m_X.as<float>();
   }
-  L.theta = c->m_theta.as<float>(); L.rowp = c->m_rowp.as<float>();
-  L.colload = c->m_colload.as<float>(); L.colscale = c->m_colscale.as<float>(); L.price = c->m_price.as<float>();
+  if (!a->warm_start) CK(cudaMemsetAsync(L.X, 0, nx * 4, c->st));
+  L.theta = c->m_theta.as<float>(); L.beta = c->m_beta.as<float>();
+  L.rowp = c->m_rowp.as<float>(); L.rowprev = c->m_rowprev.as<float>();
+  L.mj = c->m_mj.as<double>(); L.om = c->m_om.as<double>();
+  L.colload = c->m_colload.as<float>(); L.colprev = c->m_colprev.as<float>();
+  L.colscale = c->m_colscale.as<float>(); L.price = c->m_price.as<float>(); L.pi = c->m_pi.as<double>();
   L.obj = c->m_obj.as<double>();
-  L.sigma = a->sigma; L.theta_scale = a->theta_scale;
-  // jobs per CTA: enough CTAs to fill the GPU a few times, but long sweeps so the column accumulators pay
+  const double pwrel = a->primal_weight > 0.f ? (double)a->primal_weight : 60.0;
+  L.pw = (float)(pwrel / ((double)J * (double)T));
+  CK(c->m_pws.need((size_t)S * 4, c->st));
+  L.pws = c->m_pws.as<float>();
+  L.phase = 0; L.mode = 0;
   int split = 8;                       // CTAs per scenario (8 sweeps per thread at 4096 jobs x 64 rounds)
   if (const char *e = getenv("SWB_MK_SPLIT")) { const int v = atoi(e); if (v > 0) split = v; }
-  int per = (J + split - 1) / split;
-  const int sweep = 256 / (T / 4) > 0 ? 256 / (T / 4) : 1;
-  per = ((per + sweep - 1) / sweep) * sweep;
-  L.jobs_per_cta = per < sweep ? sweep : per;
-  // state: theta = 0, rowp = colload = 0, colscale = 1, prices = caller's or 0
-  CK(cudaMemsetAsync(L.theta, 0, sj * 4, c->st)); CK(cudaMemsetAsync(L.rowp, 0, sj * 4, c->st));
-  CK(cudaMemsetAsync(L.colload, 0, nwt * 4, c->st)); CK(cudaMemsetAsync(L.price, 0, nwt * 4, c->st));
-  {
-    std::vector<float> ones(nwt, 1.0f);
-    CK(cudaMemcpyAsync(L.colscale, ones.data(), nwt * 4, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+  auto tile = [&](int Tl) {            // jobs per CTA: enough CTAs to fill the GPU, long sweeps so the column accumulators pay
+    int per = (J + split - 1) / split;
+    const int sweep = 256 / (Tl / 4) > 0 ? 256 / (Tl / 4) : 1;
+    per = ((per + sweep - 1) / sweep) * sweep;
+    return per < sweep ? sweep : per;
+  };
+  // duals start at zero: marginal utilities, makespan multipliers, prices
+  CK(cudaMemsetAsync(L.mj, 0, sj * 8, c->st)); CK(cudaMemsetAsync(L.om, 0, sj * 8, c->st));
+  CK(cudaMemsetAsync(L.pi, 0, nwt * 8, c->st));
+  if (coarse) {
+    // level 1: the same iteration on X_c[S][J][W][4] — one entry stands for T/4 rounds (rate x T/4, mean capacity)
+    CK(c->m_Xc.need(sj * W * TC * 4, c->st));
+    CK(c->m_cc.need(nwc * (4 * 4 + 8), c->st));
+    swb::MarketLaunch Lc = L;
+    Lc.T = TC; Lc.rscale = (float)grp; Lc.X = c->m_Xc.as<float>(); Lc.icap = L.icap + (size_t)W * T;
+    float *cc = c->m_cc.as<float>();
+    Lc.colload = cc; Lc.colprev = cc + nwc; Lc.colscale = cc + 2 * nwc; Lc.price = cc + 3 * nwc;
+    Lc.pi = reinterpret_cast<double *>(cc + 4 * nwc);
+    Lc.jobs_per_cta = tile(TC);
+    CK(cudaMemsetAsync(Lc.pi, 0, nwc * 8, c->st));
+    if (a->warm_start) CK(swb::launch_market_restrict(L.X, Lc.X, sj * W, T, grp, c->st));
+    else CK(cudaMemsetAsync(Lc.X, 0, sj * W * TC * 4, c->st));
+    if (int rc = market_level(c, Lc, a->coarse_iters, false)) return rc;
+    CK(swb::launch_market_prolong(Lc.X, L.X, Lc.pi, L.pi, sj * W, S, W, T, grp, c->st));
   }
-  L.init_price = 0;
-  L.eta = 0.f;                                           // measurement pass: X unchanged, reductions filled
-  CK(swb::launch_market_iter(L, c->st, true));
+  L.jobs_per_cta = tile(T);
+  if (int rc = market_level(c, L, a->iters, true)) return rc;
+  // objective and violation of the last iterate, then make it feasible (column scaling) and score that
   float dense_ms = 0.f;
-  L.init_price = 1;
-  for (int it = 0; it < a->iters; ++it) {
-    CK(swb::launch_market_iter(L, c->st, false));
-    L.init_price = 0;
-    L.eta = a->eta_decay > 0.f ? a->eta / (1.0f + (float)it / a->eta_decay) : a->eta;
-    if (it == a->iters - 1) CK(cudaEventRecord(c->mev[0], c->st));
-    CK(swb::launch_market_iter(L, c->st, true));
-    if (it == a->iters - 1) CK(cudaEventRecord(c->mev[1], c->st));
-  }
-  // make the final X feasible (apply the last capacity scaling without a gradient step), then score it
+  L.phase = 2;
   CK(swb::launch_market_iter(L, c->st, false));
-  L.eta = 0.f;
+  L.mode = 1;
   CK(swb::launch_market_iter(L, c->st, true));
+  L.phase = 3;
   CK(swb::launch_market_iter(L, c->st, false));
   if (a->obj) CK(cudaMemcpyAsync(a->obj, L.obj, (size_t)S * 3 * 8, cudaMemcpyDeviceToHost, c->st));
   if (!a->on_device) CK(cudaMemcpyAsync(a->X, L.X, nx * 4, cudaMemcpyDeviceToHost, c->st));
@@ -1032,6 +1090,7 @@ int swb_set_option(swb_ctx *c, int32_t option, int32_t value) {
   if (option == SWB_OPT_RELAXED_OPTIMUM) { c->want_relaxed = value ? 1 : 0; return 0; }
   if (option == SWB_OPT_SOLVE_CLUSTER) { swb::set_solve_cluster(value); swb::set_place_cluster(value); return 0; }
   if (option == SWB_OPT_RERANK_ITERS) { c->rr_iters = value < 0 ? 0 : value; return 0; }
+  if (option == SWB_OPT_RERANK_RESTARTS) { c->rr_restarts = value < 0 ? 0 : (value > 16 ? 16 : value); return 0; }
   if (option == SWB_OPT_GBM_PATHS) { if (value < 0) return fail(SWB_ERR_ARG, "paths < 0"); c->gbm_paths = value; return 0; }
   if (option == SWB_OPT_GBM_SEED) { c->gbm_seed = (uint64_t)(uint32_t)value; return 0; }
   if (option == SWB_OPT_GBM_HORIZON) { if (value < 1) return fail(SWB_ERR_ARG, "horizon < 1"); c->gbm_hmax = value; return 0; }

@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(SWB_PLACE_THREADS, 1) place_kernel(PlaceLaunch
       rr_cycles = rr_local_search(reinterpret_cast<unsigned char *>(L.rr_items) +
                                       ((size_t)s * CL + crank) * rr_scratch_bytes(J, T), rr_smem,
                                   xm, gs, remn, nplan, L.weights + so, idle, J, T, L.rr_iters,
-                                  crank == 0 ? 0u : (unsigned)(crank * 7919 + 13), &s_rr_cost);
+                                  crank == 0 ? 0u : (unsigned)(crank * 7919 + 13), L.rr_restarts, &s_rr_cost);
       __syncthreads();
     }
     if constexpr (CL > 1) {

@@ -37,6 +37,8 @@ struct RrScratch {
   int *log;                // [(T+1) * RR_ITEMJOBS][2] moves of the cycle being applied: job | from << 16, to
   double *swc;             // [N*N] cost of the best swap-into-idle move of the pair a -> c (1e300: none)
   unsigned short *swj;     // [N*N][4] its jobs (with the edge, against it) and its class
+  unsigned long long *bkx; // [J][2] round masks of the best schedule so far (iterated search)
+  int *bki;                // [T] its idle GPUs
 };
 #define RR_MAXBAN 64
 #define RR_REV 0x8000u     // job entry of an item: this job moves AGAINST the edge (v -> u)
@@ -51,7 +53,10 @@ __device__ __forceinline__ RrScratch rr_carve(unsigned char *base, unsigned char
   base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(base) + 15) & ~uintptr_t(15));
   s.log = reinterpret_cast<int *>(base); base += N * RR_ITEMJOBS * 8;
   s.swc = reinterpret_cast<double *>(base); base += N * N * 8;
-  s.swj = reinterpret_cast<unsigned short *>(base);
+  s.swj = reinterpret_cast<unsigned short *>(base); base += N * N * 8;
+  base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(base) + 15) & ~uintptr_t(15));
+  s.bkx = reinterpret_cast<unsigned long long *>(base); base += (size_t)J * 16;
+  s.bki = reinterpret_cast<int *>(base);
   if (hot) {
     hot = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hot) + 15) & ~uintptr_t(15));
     s.wj = reinterpret_cast<double *>(hot);
@@ -246,7 +251,7 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
                                             const unsigned char *gs,
                                             const unsigned char *remn, const unsigned char *nplan, const double *prio,
                                             int *idle, int J, int T, int max_iters, unsigned noise_seed,
-                                            double *final_cost) {
+                                            int restarts, double *final_cost) {
   __shared__ double ws_d[RR_MAXCLS * 2 * (SWB_MAX_T + 1)];
   __shared__ short ws_pred[RR_MAXCLS * (SWB_MAX_T + 1)];
   __shared__ short ws_cyc[RR_MAXCLS * (SWB_MAX_T + 2)];
@@ -284,11 +289,18 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
   const double scale = fmax(rr_objective(S, xm, J, s_part), 1e-300);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int done = 0;
+  // ITERATED local search: after the first local optimum the search is perturbed again (a fresh noise seed, from the
+  // best schedule so far) `restarts` times; a round that does not improve is undone.
+  double best_cost = 1e300;
+  for (int rs = 0; rs <= restarts; ++rs) {
+  const unsigned seed_rs = rs == 0 ? noise_seed : (noise_seed * 2654435761u + (unsigned)rs * 40503u + 977u) | 1u;
+  if (threadIdx.x == 0) s_nban = 0;
+  __syncthreads();
   // phase 0 (only with a noise seed): up to 24 cycles under perturbed weights, to reach another basin;
   // phase 1: true weights until no negative cycle is left (or the budget is spent)
-  int phase = noise_seed ? 0 : 1, phase_iters = 0;
+  int phase = seed_rs ? 0 : 1, phase_iters = 0;
   for (int iter = 0; iter < max_iters; ++iter) {
-    rr_build(S, xm, gs, s_clsof, s_cls, ncls, idle, J, T, phase == 0 ? noise_seed : 0u);
+    rr_build(S, xm, gs, s_clsof, s_cls, ncls, idle, J, T, phase == 0 ? seed_rs : 0u);
     if (threadIdx.x == 0) s_found = -1;
     __syncthreads();
     if ((int)threadIdx.x < s_nban) S.cost[(size_t)(s_ban[threadIdx.x] >> 28) * N * N + (s_ban[threadIdx.x] & 0xfffffff)] = 1e300;
@@ -402,6 +414,19 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
     if (phase == 0 && (s_found < 0 || phase_iters >= 24)) { phase = 1; continue; }
     if (s_found < 0) break;
     ++done;
+  }
+  const double fc_rs = rr_objective(S, xm, J, s_part);
+  if (restarts > 0) {
+    if (fc_rs < best_cost) {                     // keep
+      best_cost = fc_rs;
+      for (int i = threadIdx.x; i < 2 * J; i += blockDim.x) S.bkx[i] = xm[i];
+      for (int i = threadIdx.x; i < T; i += blockDim.x) S.bki[i] = idle[i];
+    } else {                                     // undo this round
+      for (int i = threadIdx.x; i < 2 * J; i += blockDim.x) xm[i] = S.bkx[i];
+      for (int i = threadIdx.x; i < T; i += blockDim.x) idle[i] = S.bki[i];
+    }
+    __syncthreads();
+  }
   }
   const double fc = rr_objective(S, xm, J, s_part);
   if (threadIdx.x == 0) *final_cost = fc;

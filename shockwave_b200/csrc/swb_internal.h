@@ -54,6 +54,7 @@ struct PlaceLaunch {
   uint8_t *ncap;          // [S][J] in/out, may be null: per-job count caps for the next pass (packing feedback)
   void *rr_items;         // scratch of the re-rank local search, S x rr_cluster x rr_scratch_bytes(J, T) (null: off)
   int rr_iters;           // cycle-cancelling budget per scenario
+  int rr_restarts;        // perturb-and-continue rounds after the first local optimum (iterated local search)
   int prm_T;              // future_rounds of the call (host copy, for sizing)
   int rr_cluster;         // 8: rr_items holds 8 regions per scenario (multi-start over a thread-block cluster), else 1
 };
@@ -69,6 +70,7 @@ __host__ __device__ inline size_t rr_scratch_bytes(int J, int T) {
   b = (b + 15) & ~(size_t)15;
   b += N * RR_ITEMJOBS * 8;          // move log of the cycle being applied (job, from, to)
   b += N * N * 16;                   // best swap-into-idle move of every ordered pair of rounds (cost, jobs, class)
+  b += (size_t)J * 16 + N * 4 + 16;  // best schedule so far of the iterated search (round masks, idle GPUs)
   return (b + 255) & ~(size_t)255;
 }
 cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask);
@@ -146,19 +148,28 @@ cudaError_t launch_assign(const AssignLaunch &L, cudaStream_t st);
 #define SWB_MK_MAXW 4
 struct MarketLaunch {
   int S, J, W, T, per_scn, jobs_per_cta;
+  int Tfull;                      // planning rounds of the full problem: objective 1/(J Tfull), makespan in units of D Tfull
+  float rscale;                   // progress of one tensor entry = rscale * rate (Tfull/T on the time-coarsened level)
   const swb_params *prm;          // device [S]
   const int32_t *g;               // [J] or [S][J]
   const double *E, *c, *dbar, *rem;
   const float *rate;              // [J][W] or [S][J][W]: epochs of progress per round on worker type w
-  const double *Gw;               // [W] capacities
+  const float *icap;              // [W][T] 1 / workers of type w in round t (shared by the scenarios)
   float *X;                       // [S][J][W][T]
-  float *theta, *rowp;            // [S][J]
-  float *colload, *colscale, *price;  // [S][W][T]
+  float *theta, *beta, *rowp, *rowprev;   // [S][J]: gain per unit rate, step-size term, row reductions of x^{k+1} / x^k
+  double *mj, *om;                // [S][J] duals: marginal utility, makespan multipliers
+  float *colload, *colprev, *colscale, *price;  // [S][W][T]; price = pi * icap
+  double *pi;                     // [S][W][T] capacity prices (normalised rows)
   double *obj;                    // [S][3]: objective, makespan, worst relative capacity violation
-  float eta, sigma;
-  double theta_scale;
-  int init_price;
+  float pw;                       // primal weight asked for (tau = tau0 / pw, sigma = sigma0 * pw)
+  float *pws;                     // [S] primal weight in use (market_dual_kernel phase 0: pw raised with k)
+  int phase;                      // dual pass: 0 start, 1 PDHG dual step, 2 repair factors, 3 score only
+  int mode;                       // dense pass: 0 primal step, 1 column scaling
 };
+cudaError_t launch_market_prolong(const float *Xc, float *X, const double *pic, double *pi, size_t rows, int S, int W,
+                                  int T, int grp, cudaStream_t st);
+cudaError_t launch_market_restrict(const float *X, float *Xc, size_t rows, int T, int grp, cudaStream_t st);
+cudaError_t launch_market_fill(float *p, size_t n, float v, cudaStream_t st);
 cudaError_t launch_market_iter(const MarketLaunch &L, cudaStream_t st, bool dense);
 
 // Gavel's per-round priority -> selection -> worker assignment (gavel.cu).  Worker types appear in PROCESSING order

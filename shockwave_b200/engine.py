@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libswb200.so")
 
 MAX_BASES = 16
 ST_OK, ST_FALLBACK = 0, 1
-OPT_RELAXED_OPTIMUM, OPT_SOLVE_CLUSTER, OPT_GBM_PATHS, OPT_GBM_SEED, OPT_GBM_HORIZON, OPT_RERANK_ITERS = 1, 2, 3, 4, 5, 6
+OPT_RELAXED_OPTIMUM, OPT_SOLVE_CLUSTER, OPT_GBM_PATHS, OPT_GBM_SEED, OPT_GBM_HORIZON, OPT_RERANK_ITERS, OPT_RERANK_RESTARTS = 1, 2, 3, 4, 5, 6, 7
 
 
 class Params(C.Structure):
@@ -384,17 +384,19 @@ class MarketArgs(C.Structure):
     """swb_market_args (include/swb200.h)."""
     _fields_ = [("S", C.c_int32), ("J", C.c_int32), ("W", C.c_int32), ("T", C.c_int32),
                 ("per_scenario_jobs", C.c_int32), ("on_device", C.c_int32), ("iters", C.c_int32),
-                ("eta", C.c_float), ("sigma", C.c_float), ("eta_decay", C.c_float), ("theta_scale", C.c_double),
+                ("coarse_iters", C.c_int32), ("warm_start", C.c_int32), ("primal_weight", C.c_float),
                 ("prm", C.POINTER(Params)), ("g", C.c_void_p), ("E", C.c_void_p), ("c", C.c_void_p),
                 ("dbar", C.c_void_p), ("rem", C.c_void_p), ("rate", C.c_void_p), ("Gw", C.c_void_p),
-                ("X", C.c_void_p), ("obj", C.c_void_p), ("dense_ms", C.POINTER(C.c_float))]
+                ("cap", C.c_void_p), ("X", C.c_void_p), ("obj", C.c_void_p), ("dense_ms", C.POINTER(C.c_float))]
 
 
-def market_pgd(eng, params, g, E, c, dbar, rem, rate, Gw, X, iters, eta, sigma, theta_scale=1.0,
-               device_ptrs=None, eta_decay=0.0):
-    """Dense projected-gradient iterations on X[S,J,W,T] (fp32).  Host arrays by default (X is updated in
-    place); `device_ptrs` = dict(g,E,c,dbar,rem,rate,X) of raw device pointers for resident data.
-    Returns (obj[S,3] = objective, makespan, capacity violation ; ms of the last dense pass)."""
+def market_pgd(eng, params, g, E, c, dbar, rem, rate, Gw, X, iters, coarse_iters=0, primal_weight=0.0, cap=None,
+               warm_start=False, device_ptrs=None):
+    """Dense primal-dual price-response iterations on X[S,J,W,T] (fp32): `coarse_iters` on the time-coarsened tensor,
+    then `iters` on the full one.  Host arrays by default (X is overwritten with the feasible result; its content is
+    the starting point only with warm_start); `device_ptrs` = dict(g,E,c,dbar,rem,rate,X) of raw device pointers for
+    resident data.  Gw [W] workers per type, or cap [W,T] workers per type and round.
+    Returns (obj[S,3] = objective, makespan, capacity violation before the final repair ; ms of the last dense pass)."""
     lib = eng.lib
     if not getattr(lib, "_mk_bound", False):
         lib.swb_market_pgd.argtypes = [C.c_void_p, C.POINTER(MarketArgs)]
@@ -403,13 +405,18 @@ def market_pgd(eng, params, g, E, c, dbar, rem, rate, Gw, X, iters, eta, sigma, 
     plist = params if isinstance(params, (list, tuple)) else [params]
     S = len(plist)
     a = MarketArgs()
-    Gw = np.ascontiguousarray(Gw, dtype=np.float64)
     obj = np.zeros((S, 3), dtype=np.float64)
     ms = C.c_float()
-    a.iters, a.eta, a.sigma, a.theta_scale = int(iters), float(eta), float(sigma), float(theta_scale)
-    a.eta_decay = float(eta_decay)
+    a.iters, a.coarse_iters, a.warm_start = int(iters), int(coarse_iters), int(bool(warm_start))
+    a.primal_weight = float(primal_weight)
     a.prm = (Params * S)(*plist)
-    a.Gw, a.obj, a.dense_ms = _ptr(Gw), _ptr(obj), C.pointer(ms)
+    if cap is not None:
+        cap = np.ascontiguousarray(cap, dtype=np.float64)
+        a.cap = _ptr(cap)
+    if Gw is not None:
+        Gw = np.ascontiguousarray(Gw, dtype=np.float64)
+        a.Gw = _ptr(Gw)
+    a.obj, a.dense_ms = _ptr(obj), C.pointer(ms)
     if device_ptrs is None:
         g = np.ascontiguousarray(g, dtype=np.int32)
         f64 = lambda v: np.ascontiguousarray(v, dtype=np.float64)
@@ -425,6 +432,8 @@ def market_pgd(eng, params, g, E, c, dbar, rem, rate, Gw, X, iters, eta, sigma, 
         a.per_scenario_jobs, a.on_device = int(device_ptrs.get("per_scenario_jobs", 0)), 1
         vp = lambda k: C.c_void_p(int(device_ptrs[k]))
         a.g, a.E, a.c, a.dbar, a.rem, a.rate, a.X = vp("g"), vp("E"), vp("c"), vp("dbar"), vp("rem"), vp("rate"), vp("X")
+    if cap is not None:
+        assert cap.shape == (a.W, a.T)
     rc = lib.swb_market_pgd(eng.h, C.byref(a))
     if rc < 0:
         raise RuntimeError(f"swb_market_pgd failed ({rc}): {lib.swb_last_error().decode()}")

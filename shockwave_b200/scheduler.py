@@ -91,6 +91,7 @@ class ShockwaveScheduler(object):
         self._slot_arr = None     # slots in metadata order, rebuilt after add / remove
         self._ids_cache = None    # (job ids, job objects) in metadata order, rebuilt after add / remove
         self.last_result = None   # scalars of the latest solve (objective, status, ...)
+        self.last_forecast = None
 
         assert type(init_metadata) == OrderedDict
         self.metadata = OrderedDict()
@@ -265,6 +266,30 @@ class ShockwaveScheduler(object):
         self.last_forecast = {k: out[k] for k in ("dbar", "rem", "ftobj", "bfkey")}
         return LazySchedules(None, None, out["bfkey"], jobids, self.round_ptr, xmask=out["xmask"],
                              bfmask=out["bfmask"], T=self.future_nrounds)
+
+    # ---- extension: planning on several worker types / capacities that change inside the window ---------------
+    def heterogeneous_plan(self, type_speed, capacity, full_iters=400, coarse_iters=1000):
+        """Fractional plan x[job][worker type][round] of the live jobs on W worker types (market.py: the dense
+        price-response solve on the device).  type_speed [W]: progress relative to the type the epoch durations were
+        profiled on; capacity [W][T]: workers of type w available in round round_ptr + t.  Uses the forecast of the
+        latest re-solve (mean epoch duration, remaining runtime: shockwave.py:322-324, JobMetaData.py:315-370), so
+        call it after round_schedule().  Not part of the reference's surface (it plans on one type only).
+        Returns (job ids, dict of market.solve_relaxation)."""
+        from . import market
+        if self.last_forecast is None:
+            raise RuntimeError("heterogeneous_plan() needs the forecast of a re-solve: call round_schedule() first")
+        jobids = list(self.metadata.keys())
+        if len(jobids) != len(self.last_forecast["dbar"]):
+            raise RuntimeError("jobs were added or removed since the latest re-solve: call round_schedule() first")
+        jobs = [self.metadata[j] for j in jobids]
+        g = np.array([j.nworkers for j in jobs], dtype=np.int32)
+        E = np.array([j.epochs for j in jobs], dtype=np.float64)
+        c = np.array([j.epoch_progress for j in jobs], dtype=np.float64)
+        prm = _eng.make_params(self.ngpus, self.future_nrounds, self.round_duration, self.k, self.lam,
+                               self.rhomax, self.logapx_bases, self.logapx_origin, self.round_ptr)
+        plan = market.solve_relaxation(self._eng(), prm, g, E, c, self.last_forecast["dbar"], self.last_forecast["rem"],
+                                       type_speed, capacity, full_iters=full_iters, coarse_iters=coarse_iters)
+        return jobids, plan
 
     # ---- reference surface ------------------------------------------------------------------------
     def round_schedule(self):

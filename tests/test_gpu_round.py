@@ -124,6 +124,46 @@ def test_scheduler_class_replay():
     assert agree >= 0.95 * total
 
 
+def test_heterogeneous_plan_from_live_state():
+    """ShockwaveScheduler.heterogeneous_plan(): the dense relaxation fed from the drop-in class' own state.  With ONE
+    type at the cluster's capacity it must reproduce the relaxation of the problem the class just solved (HiGHS LP of the
+    same forecast); a second, slower type with per-round capacities can only improve it."""
+    from oracle import market_lp as ml
+    G, T, D = fx.TACC["G"], fx.TACC["T"], fx.TACC["D"]
+    sw = ShockwaveScheduler(ngpus=G, gram=16, init_metadata=OrderedDict(), future_nrounds=T, round_duration=int(D),
+                            solver_preference=["GUROBI"], solver_rel_gap=1e-3, solver_num_threads=24,
+                            solver_timeout=15, n_epoch_vars_max=30, logapx_bases=fx.BASES,
+                            logapx_origin=fx.ORIGIN, k=fx.TACC["k"], lam=fx.TACC["lam"], rhomax=fx.TACC["rhomax"])
+    st = fx.job_statics()
+    s = fx.solve(40)
+    live = [int(j) for j in s["jobids"]]
+    for k, jid in enumerate(live):
+        sw.add_metadata(jid, _Job(jid, st[jid]))
+        sw.schedule_progress(jid, int(s["c"][k]))
+    sw.round_ptr = s["round_ptr"]
+    with pytest.raises(RuntimeError):
+        sw.heterogeneous_plan([1.0], np.full((1, T), float(G)))
+    sw.set_resolve()
+    sw.round_schedule()
+    fc = sw.last_forecast
+    g = np.array([st[j]["nworkers"] for j in live]); E = np.array([float(st[j]["epochs"]) for j in live])
+    c = s["c"].astype(float)
+    logv = om.pwl_log_values(fx.BASES, fx.ORIGIN)
+    cap1 = np.full((1, T), float(G))
+    ids, plan = sw.heterogeneous_plan([1.0], cap1, full_iters=600, coarse_iters=1500)
+    assert ids == live
+    lp1 = ml.solve(g, E, c, fc["dbar"], fc["rem"], (D / fc["dbar"])[:, None], cap1, fx.TACC["k"], fx.BASES, logv)
+    assert 0 <= (lp1["objective"] - plan["objective"]) / abs(lp1["objective"]) + 1e-6 < 1e-3
+    assert np.all((g[:, None, None] * plan["x"]).sum(axis=0) <= cap1 * (1 + 1e-4))
+    cap2 = np.stack([np.full(T, float(G)), np.where(np.arange(T) % 2 == 0, 16.0, 4.0)])
+    _, plan2 = sw.heterogeneous_plan([1.0, 0.5], cap2, full_iters=600, coarse_iters=1500)
+    lp2 = ml.solve(g, E, c, fc["dbar"], fc["rem"], (D / fc["dbar"])[:, None] * np.array([1.0, 0.5]), cap2, fx.TACC["k"],
+                   fx.BASES, logv)
+    assert 0 <= (lp2["objective"] - plan2["objective"]) / abs(lp2["objective"]) + 1e-6 < 1e-3
+    assert plan2["objective"] >= plan["objective"] - 1e-4 * abs(plan["objective"])
+    assert plan2["x"].sum(axis=1).max() <= 1 + 1e-5 and np.all((g[:, None, None] * plan2["x"]).sum(axis=0) <= cap2 * (1 + 1e-4))
+
+
 def test_dirty_tracking_equals_exact_rereading():
     """timeline_check="dirty" (summaries refreshed in schedule_progress, O(1) per call) and "exact" (every job re-read
     at every re-solve) must produce the same forecasts and schedules when the caller follows the simulator's order

@@ -71,8 +71,8 @@ def test_recorded_canonical_solves(engine):
 
 def test_fallback_rerank_quality(engine):
     """rank_in_schedule_jobs (shockwave.py:714-793) is a second MILP over the ORDER of the rounds with the counts fixed
-    (the reference solves it to MIPGap 1e-3).  The GPU replaces it by a priority round-sweep followed by negative-cycle
-    cancelling on the round graph (rerank.cuh).  On ALL 128 recorded fallback solves of the canonical run its rank
+    (the reference solves it to MIPGap 1e-3).  The GPU replaces it by a priority round-sweep followed by an iterated
+    local search (negative-cycle cancelling on the round graph, rerank.cuh).  On ALL 128 recorded fallback solves of the canonical run its rank
     objective is compared with the exact re-rank MILP of the same counts (HiGHS, gap 1e-6)."""
     T, G, D = fx.TACC["T"], fx.TACC["G"], fx.TACC["D"]
     exc, exc_sweep, cycles = [], [], []
@@ -104,10 +104,10 @@ def test_fallback_rerank_quality(engine):
              float(np.mean(cycles)), int(np.max(cycles))))
     assert len(exc) >= 120
     assert np.all(exc <= exc_sweep + 1e-12)                  # the search never makes the schedule worse
-    # measured on the B200: median 0, p90 2e-4, max 4.1e-3, 2 of 128 above the reference's 1e-3 (both need an exchange
-    # that mixes two width classes AND idle GPUs, outside the search's neighbourhood)
-    assert np.median(exc) <= 1e-5 and np.percentile(exc, 90) <= 1e-3 and exc.max() <= 1e-2
-    assert int((exc > 1e-3).sum()) <= 6
+    # measured on the B200 (8 noised starts x 4 perturb-and-continue rounds each): median 0, p90 1.1e-4, max 7.0e-4 — every
+    # one of the 128 recorded fallback solves inside the reference's own MIPGap of 1e-3
+    assert np.median(exc) <= 1e-5 and np.percentile(exc, 90) <= 5e-4
+    assert exc.max() <= 1e-3
 
 def _oracle_obj(s, w):
     """Recorded oracle x re-scored with the weights the GPU used (identical to the recorded weights
