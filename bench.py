@@ -613,6 +613,19 @@ def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):
         if i >= W:
             dense_ms.append(ms)
     dense_ms = float(np.mean(dense_ms))
+    # the same iteration as a SOLVER on one config-D scenario: objective of its feasible tensor against the exact optimum of
+    # the same relaxation from the collapsed price search (solve.cu, itself pinned on the HiGHS LP in the tests)
+    eng.set_option(1, 1)
+    ex = eng.solve(make_params(G, T, D, 1e-9, 12.0, 1.0, BASES, ORIGIN, round_ptr=pb0["round_ptr"]), pb0["g"], pb0["E"],
+                   pb0["c"], pb0["dbar"], pb0["rem"], 1e30 * np.ones(J))["results"][0]["relaxed_objective"]
+    eng.set_option(1, 0)
+    X1 = np.zeros((1, J, 1, T), dtype=np.float32)
+    t0 = time.perf_counter()
+    o1, _ = market_pgd(eng, mprm[0], pb0["g"], pb0["E"], pb0["c"], pb0["dbar"], pb0["rem"],
+                       (D / pb0["dbar"])[:, None].astype(np.float32), [G], X1, 300, coarse_iters=1000)
+    dense_solver = {"passes_full": 300, "passes_coarse": 1000, "objective": float(o1[0, 0]), "exact_relaxation": float(ex),
+                    "relative_gap": float((ex - o1[0, 0]) / abs(ex)), "wall_ms_incl_copies": (time.perf_counter() - t0) * 1e3,
+                    "what": "config D, W = 1, k = 1e-9 (welfare only): two-level PDHG from X = 0 vs the exact relaxed optimum"}
     dense_bytes = 8.0 * Sd * J * Wd * T + Sd * (24.0 * J + 8.0 * Wd * T)
     del Xd
     peaks = {}
@@ -628,6 +641,7 @@ def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):
         "frac": dense_bytes / (dense_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
         "traffic_source": "profiles/ncu_kernels_r02.json (ncu --set full of this command)" if traffic else None,
         "algorithmic_bytes_per_launch": dense_bytes, "shape": [Sd, J, Wd, T], "ms_per_launch": dense_ms,
+        "as_solver": dense_solver,
         "note": "the kernel SURVEY.md §8(d) designates for the HBM roofline; algorithmic bytes = 8*S*J*W*T + "
                 "S*(24*J + 8*W*T); tensor (512 MiB) larger than L2; timed live with CUDA events on the launching stream "
                 "around the last dense pass of a run of 150 coarse + 8 full PDHG iterations, in its own leg: the kernels of the timed step (`step`) are "

@@ -87,7 +87,7 @@ struct swb_ctx {
   DBuf het_a, het_N, het_x;                                                 // swb_policy_hetero
   DBuf mc_R0, mc_mu, mc_sigma, mc_H, mc_out;                                 // swb_gbm_forecast
   DBuf m_theta, m_rowp, m_colload, m_colscale, m_price, m_obj, m_X, m_rate, m_E, m_c, m_Gw;
-  DBuf m_beta, m_rowprev, m_mj, m_om, m_colprev, m_pi, m_Xc, m_cc, m_pws;   // PDHG state; m_cc = the coarse level's column arrays
+  DBuf m_rowprev, m_mj, m_om, m_colprev, m_pi, m_Xc, m_cc, m_pws;   // PDHG state; m_cc = the coarse level's column arrays
   cudaEvent_t mev[2] = {nullptr, nullptr};
   double last_market_ms = 0.0;
   // CUDA events around the two kernels of the latest solve pass (bench.py's roofline)
@@ -144,7 +144,7 @@ void swb_destroy(swb_ctx *c) {
                  &c->pol_n, &c->pol_den, &c->pol_x, &c->pol_out, &c->mc_R0, &c->mc_mu, &c->mc_sigma, &c->mc_H, &c->mc_out,
                  &c->m_theta, &c->m_rowp, &c->m_colload,
                  &c->m_colscale, &c->m_price, &c->m_obj, &c->m_X, &c->m_rate, &c->m_E, &c->m_c, &c->m_Gw,
-                 &c->m_beta, &c->m_rowprev, &c->m_mj, &c->m_om, &c->m_colprev, &c->m_pi, &c->m_Xc, &c->m_cc, &c->m_pws,
+                 &c->m_rowprev, &c->m_mj, &c->m_om, &c->m_colprev, &c->m_pi, &c->m_Xc, &c->m_cc, &c->m_pws,
                  &c->het_a, &c->het_N, &c->het_x, &c->wf_z, &c->wf_x2};
   for (DBuf *b : all) b->release();
   if (c->h_res) cudaFreeHost(c->h_res);
@@ -956,10 +956,11 @@ static int market_level(swb_ctx *c, swb::MarketLaunch &L, int iters, bool timed)
   CK(swb::launch_market_fill(L.pws, (size_t)L.S, L.pw, c->st));
   CK(cudaMemsetAsync(L.colload, 0, nwt * 4, c->st));
   CK(cudaMemsetAsync(L.rowp, 0, (size_t)L.S * L.J * 4, c->st));
+  L.phase = 0;                                           // per-job constants (jobpack) for the measurement pass
+  CK(swb::launch_market_iter(L, c->st, false));
   L.mode = 1;                                            // measurement: X clamped to [0,1], reductions filled
   CK(swb::launch_market_iter(L, c->st, true));
-  L.phase = 0;
-  CK(swb::launch_market_iter(L, c->st, false));
+  CK(swb::launch_market_iter(L, c->st, false));          // start: reductions of x^0 remembered, theta / prices from the duals
   L.mode = 0; L.phase = 1;
   for (int it = 0; it < iters; ++it) {
     if (timed && it == iters - 1) CK(cudaEventRecord(c->mev[0], c->st));
@@ -1000,7 +1001,7 @@ int swb_market_pgd(swb_ctx *c, const swb_market_args *a) {
   const size_t nx = sj * W * T, nwt = (size_t)S * W * T, nwc = (size_t)S * W * TC;
   CK(c->prm.need(sizeof(swb_params) * S, c->st));
   CK(cudaMemcpyAsync(c->prm.p, a->prm, sizeof(swb_params) * S, cudaMemcpyHostToDevice, c->st));
-  CK(c->m_theta.need(sj * 4, c->st)); CK(c->m_rowp.need(sj * 4, c->st)); CK(c->m_beta.need(sj * 4, c->st));
+  CK(c->m_theta.need(sj * 16, c->st)); CK(c->m_rowp.need(sj * 4, c->st));
   CK(c->m_rowprev.need(sj * 4, c->st)); CK(c->m_mj.need(sj * 8, c->st)); CK(c->m_om.need(sj * 8, c->st));
   CK(c->m_colload.need(nwt * 4, c->st)); CK(c->m_colscale.need(nwt * 4, c->st)); CK(c->m_price.need(nwt * 4, c->st));
   CK(c->m_colprev.need(nwt * 4, c->st)); CK(c->m_pi.need(nwt * 8, c->st));
@@ -1028,7 +1029,7 @@ int swb_market_pgd(swb_ctx *c, const swb_market_args *a) {
     L.X = c->m_X.as<float>();
   }
   if (!a->warm_start) CK(cudaMemsetAsync(L.X, 0, nx * 4, c->st));
-  L.theta = c->m_theta.as<float>(); L.beta = c->m_beta.as<float>();
+  L.jobpack = c->m_theta.as<float4>();
   L.rowp = c->m_rowp.as<float>(); L.rowprev = c->m_rowprev.as<float>();
   L.mj = c->m_mj.as<double>(); L.om = c->m_om.as<double>();
   L.colload = c->m_colload.as<float>(); L.colprev = c->m_colprev.as<float>();

@@ -150,11 +150,10 @@ __global__ void __launch_bounds__(MK_THREADS) market_step_kernel(MarketLaunch L)
         const float4 *xrow = reinterpret_cast<const float4 *>(L.X + sj * WT);
 #pragma unroll
         for (int w = 0; w < W; ++w) x[u][w] = ld_stream(xrow + w * Q + q);
-        theta[u] = L.theta[sj];
-        beta[u] = L.beta[sj];
-        gj[u] = (float)L.g[L.per_scn ? sj : j];
+        const float4 jp = L.jobpack[sj];
+        theta[u] = jp.x; beta[u] = jp.y; gj[u] = jp.z; r[u][0] = jp.w;
 #pragma unroll
-        for (int w = 0; w < W; ++w) r[u][w] = L.rate[(L.per_scn ? sj : (size_t)j) * W + w];
+        for (int w = 1; w < W; ++w) r[u][w] = L.rate[(L.per_scn ? sj : (size_t)j) * W + w];
       }
     }
 #pragma unroll
@@ -228,9 +227,8 @@ __global__ void __launch_bounds__(MK_THREADS) market_step_fast(MarketLaunch L) {
   __syncthreads();
   const size_t sJ = (size_t)s * J;
   float4 *xs = reinterpret_cast<float4 *>(L.X + sJ * WT) + q;          // + (j W + w) Q : 32-bit offsets below
-  const float *th = L.theta + sJ, *bt = L.beta + sJ;
+  const float4 *jpk = L.jobpack + sJ;
   float *rp = L.rowp + sJ;
-  const int32_t *gp = L.g + (L.per_scn ? sJ : 0);
   const float *rt = L.rate + (L.per_scn ? sJ * W : 0);
   for (int jb = j0 + jl; jb < j1; jb += U * JPS) {
     float4 x[U][W];
@@ -241,11 +239,10 @@ __global__ void __launch_bounds__(MK_THREADS) market_step_fast(MarketLaunch L) {
       if (j < j1) {
 #pragma unroll
         for (int w = 0; w < W; ++w) x[u][w] = ld_stream(xs + (j * W + w) * Q);
-        theta[u] = th[j];
-        beta[u] = bt[j];
-        gj[u] = (float)gp[j];
+        const float4 jp = jpk[j];                  // (theta, beta, g, rate on type 0): one 16-byte load per job
+        theta[u] = jp.x; beta[u] = jp.y; gj[u] = jp.z; r[u][0] = jp.w;
 #pragma unroll
-        for (int w = 0; w < W; ++w) r[u][w] = rt[j * W + w];
+        for (int w = 1; w < W; ++w) r[u][w] = rt[j * W + w];
       }
     }
 #pragma unroll
@@ -344,9 +341,7 @@ __global__ void __launch_bounds__(1024) market_dual_kernel(MarketLaunch L) {
       const size_t sj = (size_t)s * J + j, ji = L.per_scn ? sj : j;
       const double Ef = L.E[ji], cf = L.c[ji];
       const double aE = rs / Ef, fD = rs * L.dbar[ji] / DT;
-      if (L.phase == 0) {
-        L.beta[sj] = (float)(aE + fD);
-      } else {
+      if (L.phase == 1) {
         double sumr = 0.0;
         for (int w = 0; w < W; ++w) sumr += (double)L.rate[ji * W + w];
         const double Pbar = 2.0 * (double)L.rowp[sj] - (double)L.rowprev[sj];      // extrapolated, in rate units
@@ -397,7 +392,8 @@ __global__ void __launch_bounds__(1024) market_dual_kernel(MarketLaunch L) {
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
       const size_t sj = (size_t)s * J + j, ji = L.per_scn ? sj : j;
       const double aE = rs / L.E[ji], fD = rs * L.dbar[ji] / DT;
-      L.theta[sj] = (float)(L.mj[sj] * aE + L.om[sj] * fD);
+      L.jobpack[sj] = make_float4((float)(L.mj[sj] * aE + L.om[sj] * fD), (float)(aE + fD), (float)L.g[ji],
+                                  L.rate[ji * W]);
       if (Q_ROW_ATOMICS(T)) L.rowp[sj] = 0.f;
     }
   } else if (Q_ROW_ATOMICS(T) && L.phase == 2) {

@@ -156,7 +156,8 @@ struct MarketLaunch {
   const float *rate;              // [J][W] or [S][J][W]: epochs of progress per round on worker type w
   const float *icap;              // [W][T] 1 / workers of type w in round t (shared by the scenarios)
   float *X;                       // [S][J][W][T]
-  float *theta, *beta, *rowp, *rowprev;   // [S][J]: gain per unit rate, step-size term, row reductions of x^{k+1} / x^k
+  float4 *jobpack;                // [S][J] (theta = gain per unit rate, beta = step-size term, g, rate on type 0)
+  float *rowp, *rowprev;          // [S][J]: row reductions of x^{k+1} / x^k
   double *mj, *om;                // [S][J] duals: marginal utility, makespan multipliers
   float *colload, *colprev, *colscale, *price;  // [S][W][T]; price = pi * icap
   double *pi;                     // [S][W][T] capacity prices (normalised rows)
