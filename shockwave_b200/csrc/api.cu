@@ -70,7 +70,7 @@ struct swb_ctx {
   DBuf gv_in, gv_out;     // swb_gavel_round: one staging buffer each way
   DBuf rr_items;          // re-rank local search scratch
   int rr_iters = 400;     // SWB_OPT_RERANK_ITERS (0 = sweep only)
-  int rr_restarts = 3;    // SWB_OPT_RERANK_RESTARTS
+  int rr_restarts = 2;    // SWB_OPT_RERANK_RESTARTS
   DBuf pool_pp, pool_bs;
   int64_t pool_used = 0;
   // holes left by removed jobs in pool_pp / pool_bs: (offset, rows), sorted by offset, adjacent holes merged;

@@ -104,7 +104,7 @@ def test_fallback_rerank_quality(engine):
              float(np.mean(cycles)), int(np.max(cycles))))
     assert len(exc) >= 120
     assert np.all(exc <= exc_sweep + 1e-12)                  # the search never makes the schedule worse
-    # measured on the B200 (8 noised starts x 4 perturb-and-continue rounds each): median 0, p90 1.1e-4, max 7.0e-4 — every
+    # measured on the B200 (8 noised starts, 2 perturb-and-continue rounds each): median 0, p90 1.6e-4, max 8.4e-4 — every
     # one of the 128 recorded fallback solves inside the reference's own MIPGap of 1e-3
     assert np.median(exc) <= 1e-5 and np.percentile(exc, 90) <= 5e-4
     assert exc.max() <= 1e-3
