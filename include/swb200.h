@@ -100,7 +100,7 @@ int swb_sync(swb_ctx *ctx);
 /* SWB_OPT_RERANK_RESTARTS: rounds of perturb-and-continue (iterated local search) after the first local optimum of
  * every start; a round that does not improve is undone.  Default 2 (measured on the 128 recorded fallback solves of the
  * canonical run, profiles/rerank_restarts_r02.json: 0 rounds leave 3 solves above the reference's MIPGap of 1e-3, 1 round 1,
- * 2 rounds none, at +1.6 ms per round), at most 16, 0 = off. */
+ * 2 rounds none, at +0.8 ms per round), at most 16, 0 = off. */
 #define SWB_OPT_RERANK_RESTARTS 7
 #define SWB_OPT_GBM_PATHS 3
 #define SWB_OPT_GBM_SEED 4

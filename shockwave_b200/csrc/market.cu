@@ -44,6 +44,12 @@ __device__ __forceinline__ void st_stream(float4 *p, const float4 &v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // One job's W x 4 block of the tensor (all worker types of four consecutive rounds) through one primal step.
 //   MODE 0: x <- proj( x + tau (theta r_w - price_wt g) ),  tau = ipw / max_w (g icap_wt + r_w beta); the projection is
 //           the Euclidean one on {x >= 0, sum_w x <= 1} (x <= 1 is implied), exact for W <= 4 by active-set pruning —
@@ -70,7 +76,7 @@ __device__ __forceinline__ void respond(float4 (&x)[W], const float (&ca)[W][4],
       float den = fmaf(gj, ca[0][e], rb[0]);
 #pragma unroll
       for (int w = 1; w < W; ++w) den = fmaxf(den, fmaf(gj, ca[w][e], rb[w]));
-      const float tau = __fdividef(ipw, den);
+      const float tau = ipw * rcp_ftz(den);      // den >= r beta > 0, never denormal: bare MUFU.RCP (no range fix-up)
       float y[W], pos = 0.f;
 #pragma unroll
       for (int w = 0; w < W; ++w) {

@@ -39,6 +39,8 @@ struct RrScratch {
   unsigned short *swj;     // [N*N][4] its jobs (with the edge, against it) and its class
   unsigned long long *bkx; // [J][2] round masks of the best schedule so far (iterated search)
   int *bki;                // [T] its idle GPUs
+  double *wn;              // [J] w_j x noise of the current phase (what the edge costs are built from)
+  unsigned short *ord;     // [J] movable jobs grouped by width class, ascending job index inside a class
 };
 #define RR_MAXBAN 64
 #define RR_REV 0x8000u     // job entry of an item: this job moves AGAINST the edge (v -> u)
@@ -56,7 +58,10 @@ __device__ __forceinline__ RrScratch rr_carve(unsigned char *base, unsigned char
   s.swj = reinterpret_cast<unsigned short *>(base); base += N * N * 8;
   base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(base) + 15) & ~uintptr_t(15));
   s.bkx = reinterpret_cast<unsigned long long *>(base); base += (size_t)J * 16;
-  s.bki = reinterpret_cast<int *>(base);
+  s.bki = reinterpret_cast<int *>(base); base += N * 4;
+  base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(base) + 15) & ~uintptr_t(15));
+  s.wn = reinterpret_cast<double *>(base); base += (size_t)J * 8;
+  s.ord = reinterpret_cast<unsigned short *>(base);
   if (hot) {
     hot = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hot) + 15) & ~uintptr_t(15));
     s.wj = reinterpret_cast<double *>(hot);
@@ -76,9 +81,8 @@ struct RrItem { double cost; int n; unsigned short job[RR_ITEMJOBS]; };
 
 // Edge costs and best items of every ordered pair of rounds and every width class.  One thread per pair; the inner
 // loop over the jobs keeps the two cheapest SINGLE jobs per class in registers (cls_of[] maps a width to its class).
-__device__ void rr_build(const RrScratch &S, const unsigned long long *xm, const unsigned char *gs,
-                         const unsigned char *cls_of, const int *clsw, int ncls, const int *idle, int J, int T,
-                         unsigned noise_seed) {
+__device__ void rr_build(const RrScratch &S, const unsigned long long *xm, const int *off,
+                         const int *clsw, int ncls, const int *idle, int J, int T) {
   const double INF = 1e300;
   const int N = T + 1;
   for (int pr = threadIdx.x; pr < N * N; pr += blockDim.x) {
@@ -96,32 +100,30 @@ __device__ void rr_build(const RrScratch &S, const unsigned long long *xm, const
     }
     double c0[RR_MAXCLS], c1[RR_MAXCLS], cr[RR_MAXCLS];      // cr / jr: cheapest single job moving c -> a (against the edge)
     int j0[RR_MAXCLS], j1[RR_MAXCLS], jr[RR_MAXCLS];
-#pragma unroll
-    for (int k = 0; k < RR_MAXCLS; ++k) { c0[k] = INF; c1[k] = INF; cr[k] = INF; j0[k] = -1; j1[k] = -1; jr[k] = -1; }
     const int wa = a >> 6, wc = c >> 6;
     const unsigned long long ba = 1ull << (a & 63), bc = 1ull << (c & 63);
     const double dist = (double)(c - a);
-    for (int j = 0; j < J; ++j) {
-      const bool ina = (xm[2 * j + wa] & ba) != 0ull, inc = (xm[2 * j + wc] & bc) != 0ull;
-      if (ina == inc) continue;
-      const double w = S.wj[j];
-      if (w == 0.0) continue;
-      const int k = cls_of[gs[j]];
-      if (k >= RR_MAXCLS) continue;
-      if (ina) {
-        const double x = w * dist * rr_noise(j, noise_seed);
+    // one pass per width class over THAT class's jobs (S.ord, ascending job index = the order of the plain loop, so
+    // ties break the same way): the class is a compile-time index, the running best / second best are scalars —
+    // ncu r02: the one-loop form with a 4-way class select spent ~60 instructions per (pair, job) and the per-thread
+    // chain of the rebuild was the critical path of every search iteration
 #pragma unroll
-        for (int q = 0; q < RR_MAXCLS; ++q)
-          if (q == k) {
-            if (x < c0[q]) { c1[q] = c0[q]; j1[q] = j0[q]; c0[q] = x; j0[q] = j; }
-            else if (x < c1[q]) { c1[q] = x; j1[q] = j; }
-          }
-      } else {
-        const double x = -w * dist * rr_noise(j, noise_seed);
-#pragma unroll
-        for (int q = 0; q < RR_MAXCLS; ++q)
-          if (q == k && x < cr[q]) { cr[q] = x; jr[q] = j; }
+    for (int k = 0; k < RR_MAXCLS; ++k) {
+      double b0 = INF, b1 = INF, br = INF;
+      int i0 = -1, i1 = -1, ir = -1;
+      if (k < ncls) {
+        for (int i = off[k]; i < off[k + 1]; ++i) {
+          const int j = S.ord[i];
+          const bool ina = (xm[2 * j + wa] & ba) != 0ull, inc = (xm[2 * j + wc] & bc) != 0ull;
+          if (ina == inc) continue;
+          const double x = S.wn[j] * dist;
+          if (ina) {
+            if (x < b0) { b1 = b0; i1 = i0; b0 = x; i0 = j; }
+            else if (x < b1) { b1 = x; i1 = j; }
+          } else if (-x < br) { br = -x; ir = j; }
+        }
       }
+      c0[k] = b0; c1[k] = b1; cr[k] = br; j0[k] = i0; j1[k] = i1; jr[k] = ir;
     }
     // best / second-best ITEM per class: singles, plus the composite of the two best items of half the width
     RrItem b0, b1;                       // of the previous class
@@ -256,7 +258,7 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
   __shared__ short ws_pred[RR_MAXCLS * (SWB_MAX_T + 1)];
   __shared__ short ws_cyc[RR_MAXCLS * (SWB_MAX_T + 2)];
   __shared__ unsigned char s_clsof[256];
-  __shared__ int s_cls[RR_MAXCLS], s_ncls, s_found, s_len[RR_MAXCLS], s_ban[RR_MAXBAN], s_nban;
+  __shared__ int s_cls[RR_MAXCLS], s_ncls, s_found, s_len[RR_MAXCLS], s_ban[RR_MAXBAN], s_nban, s_off[RR_MAXCLS + 1];
   __shared__ double s_part[32];
   __shared__ int s_parti[32];
   const RrScratch S = rr_carve(scratch, hot, J, T);
@@ -280,6 +282,14 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
     for (int q = 0; q < n; ++q) { s_cls[q] = w[q]; s_clsof[w[q]] = (unsigned char)q; }
     s_ncls = n;
     s_nban = 0;
+    // movable jobs grouped by class (counting sort, ascending job index inside a class)
+    int cnt[RR_MAXCLS + 1];
+    for (int q = 0; q <= RR_MAXCLS; ++q) cnt[q] = 0;
+    for (int j = 0; j < J; ++j) if (n > 0 && S.wj[j] != 0.0 && s_clsof[gs[j]] < RR_MAXCLS) ++cnt[s_clsof[gs[j]] + 1];
+    for (int q = 0; q < RR_MAXCLS; ++q) cnt[q + 1] += cnt[q];
+    for (int q = 0; q <= RR_MAXCLS; ++q) s_off[q] = cnt[q];
+    for (int j = 0; j < J; ++j)
+      if (n > 0 && S.wj[j] != 0.0 && s_clsof[gs[j]] < RR_MAXCLS) S.ord[cnt[s_clsof[gs[j]]]++] = (unsigned short)j;
   }
   __syncthreads();
   const int ncls = s_ncls;
@@ -298,9 +308,15 @@ __device__ __noinline__ int rr_local_search(unsigned char *scratch, unsigned cha
   __syncthreads();
   // phase 0 (only with a noise seed): up to 24 cycles under perturbed weights, to reach another basin;
   // phase 1: true weights until no negative cycle is left (or the budget is spent)
-  int phase = seed_rs ? 0 : 1, phase_iters = 0;
+  int phase = seed_rs ? 0 : 1, phase_iters = 0, wn_phase = -1;
   for (int iter = 0; iter < max_iters; ++iter) {
-    rr_build(S, xm, gs, s_clsof, s_cls, ncls, idle, J, T, phase == 0 ? seed_rs : 0u);
+    if (phase != wn_phase) {                   // edge costs use w_j x noise(phase): once per phase, not per (pair, job)
+      const unsigned sd = phase == 0 ? seed_rs : 0u;
+      for (int j = threadIdx.x; j < J; j += blockDim.x) S.wn[j] = S.wj[j] * rr_noise(j, sd);
+      wn_phase = phase;
+      __syncthreads();
+    }
+    rr_build(S, xm, s_off, s_cls, ncls, idle, J, T);
     if (threadIdx.x == 0) s_found = -1;
     __syncthreads();
     if ((int)threadIdx.x < s_nban) S.cost[(size_t)(s_ban[threadIdx.x] >> 28) * N * N + (s_ban[threadIdx.x] & 0xfffffff)] = 1e300;

@@ -71,6 +71,7 @@ __host__ __device__ inline size_t rr_scratch_bytes(int J, int T) {
   b += N * RR_ITEMJOBS * 8;          // move log of the cycle being applied (job, from, to)
   b += N * N * 16;                   // best swap-into-idle move of every ordered pair of rounds (cost, jobs, class)
   b += (size_t)J * 16 + N * 4 + 16;  // best schedule so far of the iterated search (round masks, idle GPUs)
+  b += (size_t)J * 8 + (size_t)J * 2 + 32;   // noised weights of the current phase, job order by width class
   return (b + 255) & ~(size_t)255;
 }
 cudaError_t launch_place(const PlaceLaunch &L, cudaStream_t st, unsigned long long *gmask);
