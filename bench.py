@@ -499,7 +499,9 @@ def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):
     from shockwave_b200.forecast_mc import path_range
     out = {}
     S, P_MC = args.scenarios, args.mc_paths
-    pb0 = pbs[0][0]
+    # ONE job set shared by all ranks (the sweep forecasts it with paths sharded over the ranks): rank 0's scenario 0 —
+    # `pbs` holds a different scenario stream per rank
+    pb0 = scenario(0, 0)[0]
     # ---- batched: S what-if scenarios of ONE job set per step ------------------------------------------------
     rep = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.broadcast_to(a.astype(dt), (S, J)))).to(dev)
     bt = dict(g=rep(pb0["g"], np.int32), E=rep(pb0["E"], np.int32), c=rep(pb0["c"], np.int32),
