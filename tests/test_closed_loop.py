@@ -86,6 +86,55 @@ def test_shockwave_closed_loop_matches_golden_pickle():
     assert abs((ftf > 1.05).mean() - (gftf > 1.05).mean()) < 0.03
 
 
+def _pin(G):
+    return os.path.join(ROOT, "tests", "golden", f"scale{G}_oracle_pin.json")
+
+
+@pytest.mark.skipif(not _have_both(), reason="needs a B200 and the (staged) reference simulator at the same time")
+@pytest.mark.parametrize("G", [64, 128, 256])
+def test_shockwave_closed_loop_scale_runs_match_oracle_pins(G):
+    """Closed-loop cases at the reference's scale-out sizes: the traces of reproduce/scale_{64,128,256}gpus.sh (220 / 460 /
+    900 jobs; configurations/scale_*gpus.json: k = 10 / 1e-3 / 1e5, lambda = 5 / 15 / 5; wisr_throughputs.json).  The
+    reference ships no golden pickles for them; the yardstick is the same unmodified simulator with the HiGHS oracle in
+    place of Gurobi (tests/golden/make_scale_pins.py).  Same 3 % tolerance as the canonical case."""
+    from shockwave_b200 import ShockwaveScheduler
+    if not os.path.exists(_pin(G)):
+        pytest.skip(f"no oracle pin recorded for the {G}-GPU run (tests/golden/make_scale_pins.py {G})")
+    pin = json.load(open(_pin(G)))
+    if not os.path.exists(os.path.join(rh.REF, pin["trace"])):
+        pytest.skip("trace not staged")
+    stats = dict(solves=0, fallback=0, ms=0.0, jmax=0)
+
+    class Counting(ShockwaveScheduler):
+        def _resolve(self, jobids, jobobjs):
+            t0 = time.perf_counter()
+            out = super()._resolve(jobids, jobobjs)
+            stats["ms"] += (time.perf_counter() - t0) * 1e3
+            stats["solves"] += 1
+            stats["fallback"] += int(self.last_result["status"] != 0)
+            stats["jmax"] = max(stats["jmax"], len(jobids))
+            return out
+
+    t0 = time.perf_counter()
+    out = rh.simulate("shockwave", shockwave_scheduler_cls=Counting, config=pin["config"], cluster=pin["cluster"],
+                      trace=pin["trace"], throughputs=pin["throughputs"])
+    assert _native_loaded() and stats["solves"] > 50
+    ftf = np.array(out["finish_time_fairness_list"])
+    gold = dict(makespan=pin["makespan"], avg_jct=pin["avg_jct"], cluster_util=pin["cluster_util"],
+                finish_time_fairness_list=[pin["worst_ftf"]] + [0.0] * (len(ftf) - 1),
+                per_round_schedule=[None] * pin["rounds"])
+    row = _record(f"shockwave@{G}gpus(vs oracle pin)", out, gold, time.perf_counter() - t0,
+                  dict(resolves=stats["solves"], fallback_resolves=stats["fallback"], max_live_jobs=stats["jmax"],
+                       mean_resolve_ms=stats["ms"] / max(1, stats["solves"]),
+                       golden_unfair_fraction=pin["unfair_fraction"]))
+    print(row)
+    assert abs(out["makespan"] - pin["makespan"]) / pin["makespan"] < 0.03
+    assert abs(out["avg_jct"] - pin["avg_jct"]) / pin["avg_jct"] < 0.03
+    assert abs(out["cluster_util"] - pin["cluster_util"]) / pin["cluster_util"] < 0.03
+    assert ftf.max() <= pin["worst_ftf"] * 1.10
+    assert (ftf > 1.05).mean() <= pin["unfair_fraction"] + 0.03
+
+
 @pytest.mark.skipif(not _have_both(), reason="needs a B200 and the (staged) reference simulator at the same time")
 @pytest.mark.parametrize("policy", ["max_min_fairness", "finish_time_fairness", "min_total_duration",
                                     "max_sum_throughput_perf", "allox", "gandiva_fair"])
