@@ -608,9 +608,9 @@ def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):
     mprm = [make_params(G, T, D, 1e-9, 12.0, 1.0, BASES, ORIGIN) for _ in range(Sd)]
     dense_ms = []
     for i in range(W + 5):
-        # 150 passes on the time-coarsened tensor, then 8 full passes: the timed pass (the last one) works on a
-        # converged, non-trivial allocation, not on zeros
-        mobj, ms = market_pgd(eng, mprm, None, None, None, None, None, None, [G], None, 8, coarse_iters=150,
+        # 150 passes on the time-coarsened tensor, then 16 full passes, each timed with its own event pair (ms = their
+        # mean): the timed passes work on a converged, non-trivial allocation, not on zeros
+        mobj, ms = market_pgd(eng, mprm, None, None, None, None, None, None, [G], None, 16, coarse_iters=150,
                               device_ptrs=mptr)
         if i >= W:
             dense_ms.append(ms)
@@ -646,7 +646,7 @@ def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):
         "as_solver": dense_solver,
         "note": "the kernel SURVEY.md §8(d) designates for the HBM roofline; algorithmic bytes = 8*S*J*W*T + "
                 "S*(24*J + 8*W*T); tensor (512 MiB) larger than L2; timed live with CUDA events on the launching stream "
-                "around the last dense pass of a run of 150 coarse + 8 full PDHG iterations, in its own leg: the kernels of the timed step (`step`) are "
+                "around each of the 16 full dense passes of a run of 150 coarse + 16 full PDHG iterations (mean of 16 x 5 launches), in its own leg: the kernels of the timed step (`step`) are "
                 "ALU- and latency-bound, never HBM-bound, and are listed with those bounds; peak = MEASURED_PEAKS.json "
                 "hbm_gbs" + ("" if peaks else " (fallback 6650)")}
 

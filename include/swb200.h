@@ -321,7 +321,8 @@ int swb_gbm_ensemble(swb_ctx *ctx, int32_t S, int32_t J, double P_total, const d
  * super-rounds (prolongated afterwards; skipped when T < 16), then `iters` iterations of (dense pass + small dual
  * pass) on the full tensor; a dense pass reads X once and writes X once.  The returned X is feasible (a final pass
  * scales over-subscribed columns).  obj = [S][3]: relaxed objective, makespan and worst relative capacity violation
- * of the returned X.  dense_ms (may be NULL) = device time of the last full dense pass (CUDA events). */
+ * of the returned X.  dense_ms (may be NULL) = mean device time of the last (up to 16) full dense passes, one CUDA
+ * event pair per pass. */
 typedef struct swb_market_args {
   int32_t S, J, W, T;
   int32_t per_scenario_jobs;    /* job arrays are [S][J] (else shared [J]) */
