@@ -102,6 +102,11 @@ int swb_sync(swb_ctx *ctx);
  * canonical run, profiles/rerank_restarts_r02.json: 0 rounds leave 3 solves above the reference's MIPGap of 1e-3, 1 round 1,
  * 2 rounds none, at +0.8 ms per round), at most 16, 0 = off. */
 #define SWB_OPT_RERANK_RESTARTS 7
+/* SWB_OPT_ASYNC_AUX: 1 = swb_gbm_forecast with device inputs AND device output, and swb_gbm_ensemble, return right after
+ * their launches instead of synchronising the context's stream: a chain forecast -> ensemble -> swb_solve (device
+ * pointers) then runs back to back on the device with ONE synchronisation, at the end of swb_solve.  The caller must
+ * not read their outputs from another stream before a synchronising call (swb_sync, swb_solve, ...).  Default 0. */
+#define SWB_OPT_ASYNC_AUX 8
 #define SWB_OPT_GBM_PATHS 3
 #define SWB_OPT_GBM_SEED 4
 #define SWB_OPT_GBM_HORIZON 5

@@ -59,6 +59,7 @@ struct swb_ctx {
   DBuf wf_z, wf_x2;
   DBuf sa, su0, sR, sws, scap, sg, snF, snmax, sn, gmask, sncap, seated, scth, sths, sn0, snfc, sRr;
   int want_relaxed = 0;
+  int aux_async = 0;      // SWB_OPT_ASYNC_AUX: device-output forecast / ensemble calls return without synchronising
   // ---- resident job table (by slot)
   int nslots = 0;
   DBuf t_off, t_E, t_nm, t_g, t_ns, t_ts, t_modes, t_mm, t_amp, s_r0, s_rl, s_cnt, s_vl, s_acc, t_mu, t_sg;
@@ -852,7 +853,7 @@ int swb_gbm_forecast(swb_ctx *c, int32_t J, const double *R0, const int32_t *H, 
   CK(cudaEventRecord(c->ev[1], c->st));
   CK(cudaEventRecord(c->ev[2], c->st));
   if (!out_on_device) CK(cudaMemcpyAsync(out, c->mc_out.p, 2 * b, cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st));
+  if (!(c->aux_async && out_on_device && in_dev)) CK(cudaStreamSynchronize(c->st));
   return 0;
 }
 
@@ -945,7 +946,7 @@ int swb_gbm_ensemble(swb_ctx *c, int32_t S, int32_t J, double P_total, const dou
   CK(c->ens_z.need((size_t)S * 8, c->st));
   CK(cudaMemcpyAsync(c->ens_z.p, z, (size_t)S * 8, cudaMemcpyHostToDevice, c->st));
   CK(swb::launch_gbm_ensemble(S, J, P_total, sums_dev, c->ens_z.as<double>(), rem_out_dev, c->st));
-  CK(cudaStreamSynchronize(c->st));
+  if (!c->aux_async) CK(cudaStreamSynchronize(c->st));
   return 0;
 }
 
@@ -1104,6 +1105,7 @@ int swb_set_option(swb_ctx *c, int32_t option, int32_t value) {
   if (!c) return fail(SWB_ERR_ARG, "null ctx");
   if (option == SWB_OPT_RELAXED_OPTIMUM) { c->want_relaxed = value ? 1 : 0; return 0; }
   if (option == SWB_OPT_SOLVE_CLUSTER) { swb::set_solve_cluster(value); swb::set_place_cluster(value); return 0; }
+  if (option == SWB_OPT_ASYNC_AUX) { c->aux_async = value ? 1 : 0; return 0; }
   if (option == SWB_OPT_RERANK_ITERS) { c->rr_iters = value < 0 ? 0 : value; return 0; }
   if (option == SWB_OPT_RERANK_RESTARTS) { c->rr_restarts = value < 0 ? 0 : (value > 16 ? 16 : value); return 0; }
   if (option == SWB_OPT_GBM_PATHS) { if (value < 0) return fail(SWB_ERR_ARG, "paths < 0"); c->gbm_paths = value; return 0; }

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libswb200.so")
 
 MAX_BASES = 16
 ST_OK, ST_FALLBACK = 0, 1
-OPT_RELAXED_OPTIMUM, OPT_SOLVE_CLUSTER, OPT_GBM_PATHS, OPT_GBM_SEED, OPT_GBM_HORIZON, OPT_RERANK_ITERS, OPT_RERANK_RESTARTS = 1, 2, 3, 4, 5, 6, 7
+OPT_RELAXED_OPTIMUM, OPT_SOLVE_CLUSTER, OPT_GBM_PATHS, OPT_GBM_SEED, OPT_GBM_HORIZON, OPT_RERANK_ITERS, OPT_RERANK_RESTARTS, OPT_ASYNC_AUX = 1, 2, 3, 4, 5, 6, 7, 8
 
 
 class Params(C.Structure):
@@ -329,6 +329,10 @@ class Engine:
         ncal = np.ascontiguousarray(ncal, dtype=np.int32)
         self._check(self.lib.swb_forecast_commit(self.h, len(ncal), int(bool(fallback)), _ptr(ncal)),
                     "swb_forecast_commit")
+
+    def sync(self):
+        """Wait for everything queued on the context's stream (needed after calls made under OPT_ASYNC_AUX)."""
+        self._check(self.lib.swb_sync(self.h), "swb_sync")
 
     def set_option(self, option, value):
         self.lib.swb_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
