@@ -135,3 +135,21 @@ def test_warm_start_and_batched_scenarios(engine):
     obj1, _ = market_pgd(engine, prms[0], pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], rate, Gw, X1, 0, warm_start=True)
     assert abs(obj1[0, 0] - obj[0, 0]) <= 1e-6 * abs(obj[0, 0])           # zero passes: the same tensor scored again
     assert np.allclose(X1[0], X[0], atol=1e-6)
+
+
+def test_per_scenario_job_sets_equal_single_calls(engine):
+    """S scenarios with their OWN job arrays ([S][J] layout) in one launch == S single launches."""
+    J, G, T, W = 200, 64, 32, 2
+    sets = [_setup(J, G, T, W, seed=40 + s, k=1e-3) for s in range(3)]
+    stack = lambda key: np.stack([st[0][key] for st in sets])
+    rate = np.stack([st[1] for st in sets]).astype(np.float32)
+    prms = [st[4] for st in sets]
+    X = np.zeros((3, J, W, T), dtype=np.float32)
+    obj, _ = market_pgd(engine, prms, stack("g"), stack("E"), stack("c"), stack("dbar"), stack("rem"), rate, sets[0][2], X,
+                        60, coarse_iters=200)
+    for s, (pb, r, Gw, cap, prm, D) in enumerate(sets):
+        X1 = np.zeros((1, J, W, T), dtype=np.float32)
+        o1, _ = market_pgd(engine, prm, pb["g"], pb["E"], pb["c"], pb["dbar"], pb["rem"], r, Gw, X1, 60, coarse_iters=200)
+        assert np.abs(X[s] - X1[0]).mean() < 1e-4            # same trajectory up to atomics rounding
+        assert abs(obj[s, 0] - o1[0, 0]) <= 1e-6 * abs(o1[0, 0])       # column sums go through float atomics
+        _check_feasible(X[s], pb, cap)
