@@ -152,6 +152,32 @@ def test_gavel_policy_closed_loop_matches_golden_pickle(policy):
 
 
 @pytest.mark.skipif(not _have_both(), reason="needs a B200 and the (staged) reference simulator at the same time")
+@pytest.mark.parametrize("G", [64, 128, 256])
+@pytest.mark.parametrize("policy", ["max_min_fairness", "finish_time_fairness", "min_total_duration"])
+def test_gavel_policy_closed_loop_scale_runs_match_oracle_pins(policy, G):
+    """The Gavel policies of BASELINE config E closed loop at the reference's scale-out sizes (220 / 460 / 900 jobs on
+    64 / 128 / 256 GPUs, up to ~840 live jobs per get_allocation()): same host code, device kernels vs the HiGHS backend
+    (tests/golden/make_scale_policy_pins.py), same tolerance as the canonical case."""
+    from shockwave_b200 import policies
+    pins = json.load(open(os.path.join(ROOT, "tests", "golden", "scale_policy_pins.json")))
+    pin = pins.get(f"{policy}@{G}")
+    if pin is None or not os.path.exists(os.path.join(rh.REF, pin["trace"])):
+        pytest.skip("no pin / trace not staged")
+    t0 = time.perf_counter()
+    out = rh.simulate(policy, policy_obj=policies.get_policy(policy, solver="ECOS", seed=0), cluster=pin["cluster"],
+                      trace=pin["trace"], throughputs=pin["throughputs"])
+    assert _native_loaded()
+    ftf = np.array(out["finish_time_fairness_list"])
+    gold = dict(makespan=pin["makespan"], avg_jct=pin["avg_jct"], cluster_util=pin["cluster_util"],
+                finish_time_fairness_list=[pin["worst_ftf"]] + [0.0] * (len(ftf) - 1),
+                per_round_schedule=[None] * pin["rounds"])
+    print(_record(f"{policy}@{G}gpus(vs oracle pin)", out, gold, time.perf_counter() - t0,
+                  dict(golden_unfair_fraction=pin["unfair_frac"])))
+    assert abs(out["makespan"] - pin["makespan"]) / pin["makespan"] < 0.015
+    assert abs(out["avg_jct"] - pin["avg_jct"]) / pin["avg_jct"] < 0.015
+
+
+@pytest.mark.skipif(not _have_both(), reason="needs a B200 and the (staged) reference simulator at the same time")
 @pytest.mark.parametrize("policy", ["max_min_fairness", "finish_time_fairness", "max_sum_throughput_perf"])
 def test_gavel_round_step_on_the_device_reproduces_the_reference_loop(policy):
     """§8(f)-2: priorities -> selection -> worker assignment of every round computed by gavel.cu (GavelRoundMixin in
