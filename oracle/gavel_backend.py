@@ -122,6 +122,8 @@ def cpu_backend():
     saved = (P._pooled, P._hetero)
     saved_wf = P._waterfill_step
     P._waterfill_step = waterfill_step_cpu
+    saved_eg = P._eisenberg_gale
+    P._eisenberg_gale = lambda N, coef, sf, present, iters=0: gl.eisenberg_gale_batch(N, coef, sf, present)
     def _het(mode, N, a, sf, t=None, n=None, den=None):
         out = hetero_cpu(mode, N, a, sf, t, n, den)
         _het.last_stats = (0, 0)
@@ -137,4 +139,5 @@ def cpu_backend():
     finally:
         P._pooled, P._hetero = saved
         P._waterfill_step = saved_wf
+        P._eisenberg_gale = saved_eg
         P._engine = saved_engine

@@ -294,3 +294,37 @@ def allox_allocation(job_ids, worker_types, unflattened_throughputs, scale_facto
             if lst:
                 allocation[lst[0][0]][w_of[wid]] = 1.0 / scale_factors[lst[0][0]]
     return allocation
+
+
+def eisenberg_gale(coef, sf, N):
+    """The cvxpy program of policies/max_min_fairness_strategy_proof.py:102-123 — maximise geo_mean_j(sum_w coef_jw x_jw)
+    s.t. x >= 0, sum_j sf_j x_jw <= N_w, sum_w x_jw <= 1 (policy.py:58-65) — restated as max sum_j log(.) (same argmax)
+    on scipy's trust-constr (cvxpy is not installable here).  Per-job utilities are unique at the optimum (strictly
+    concave in them); x need not be.  Returns (x [J][W], utilities [J])."""
+    import numpy as np
+    from scipy.optimize import Bounds, LinearConstraint, minimize
+    coef, sf, N = np.asarray(coef, float), np.asarray(sf, float), np.asarray(N, float)
+    J, W = coef.shape
+    f = lambda z: -np.log(np.maximum((coef * z.reshape(J, W)).sum(axis=1), 1e-300)).sum()
+    g = lambda z: -(coef / np.maximum((coef * z.reshape(J, W)).sum(axis=1), 1e-300)[:, None]).ravel()
+    A1 = np.kron(np.eye(J), np.ones((1, W)))
+    A2 = np.kron(sf[None, :], np.eye(W)).reshape(W, J * W)
+    x0 = np.full(J * W, 0.5 * min(1.0 / W, float((N / sf.sum()).min())))
+    r = minimize(f, x0, jac=g, method="trust-constr", bounds=Bounds(0.0, 1.0),
+                 constraints=[LinearConstraint(A1, -np.inf, 1.0), LinearConstraint(A2, -np.inf, N)],
+                 options=dict(gtol=1e-12, xtol=1e-14, maxiter=20000))
+    x = np.clip(r.x.reshape(J, W), 0.0, 1.0)
+    return x, (coef * x).sum(axis=1)
+
+
+def eisenberg_gale_batch(N, coef, sf, present):
+    """present [S][J]: one program per scenario over the jobs present in it; x [S][J][W] (absent jobs: 0)."""
+    import numpy as np
+    present = np.asarray(present, bool)
+    S, J = present.shape
+    x = np.zeros((S, J, len(N)))
+    for s in range(S):
+        idx = np.flatnonzero(present[s])
+        if len(idx):
+            x[s, idx] = eisenberg_gale(np.asarray(coef)[idx], np.asarray(sf)[idx], N)[0]
+    return x

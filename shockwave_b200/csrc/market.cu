@@ -316,13 +316,18 @@ __global__ void __launch_bounds__(1024) market_dual_kernel(MarketLaunch L) {
   const double invJT = 1.0 / ((double)J * Tf);
   const double DT = prm.round_duration * Tf, kk = prm.k * DT;
   double welfare = 0.0, mx = 0.0, sumg = 0.0, maxKm = 0.0, mkmax = 0.0;
+  const bool eg = L.utility == 1;      // Eisenberg-Gale: sum_j log(U_j) over the jobs with E_j > 0, no makespan term
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
     const size_t sj = (size_t)s * J + j, ji = L.per_scn ? sj : j;
     const double Ef = L.E[ji], cf = L.c[ji];
+    sumg += (double)L.g[ji];
+    if (eg) {
+      if (Ef > 0.0) welfare += log(fmax(rs * (double)L.rowp[sj], 1e-300));
+      continue;
+    }
     const double Pj = fmin(rs * (double)L.rowp[sj], Ef - cf);
     welfare += plog(P, (cf + Pj) / Ef);
     mx = fmax(mx, fmax(0.0, L.rem[ji] - L.dbar[ji] * Pj));
-    sumg += (double)L.g[ji];
     double sumr = 0.0;
     for (int w = 0; w < W; ++w) sumr += (double)L.rate[ji * W + w];
     maxKm = fmax(maxKm, (double)T * rs * L.dbar[ji] / DT * sumr);
@@ -346,6 +351,26 @@ __global__ void __launch_bounds__(1024) market_dual_kernel(MarketLaunch L) {
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
       const size_t sj = (size_t)s * J + j, ji = L.per_scn ? sj : j;
       const double Ef = L.E[ji], cf = L.c[ji];
+      if (eg) {
+        // utility log(U_j)/(J T), U_j = rs * row sum: prox of the conjugate of -w log(u) in closed form; a job with
+        // E_j <= 0 is not part of this scenario (theta stays 0, its row stays at x = 0)
+        if (L.phase == 1) {
+          double sumr = 0.0;
+          for (int w = 0; w < W; ++w) sumr += (double)L.rate[ji * W + w];
+          double m = 0.0;
+          if (Ef > 0.0 && sumr > 0.0) {
+            const double du = rs * (2.0 * (double)L.rowp[sj] - (double)L.rowprev[sj]);
+            const double sig_u = pw / ((double)T * rs * sumr);
+            const double v = du - L.mj[sj] / sig_u;
+            const double ps = 0.5 * (v + sqrt(v * v + 4.0 * invJT / sig_u));
+            m = L.mj[sj] - sig_u * (du - ps);
+          }
+          L.mj[sj] = m;
+          L.om[sj] = 0.0;
+        }
+        L.rowprev[sj] = L.rowp[sj];
+        continue;
+      }
       const double aE = rs / Ef, fD = rs * L.dbar[ji] / DT;
       if (L.phase == 1) {
         double sumr = 0.0;
@@ -369,7 +394,7 @@ __global__ void __launch_bounds__(1024) market_dual_kernel(MarketLaunch L) {
       }
       L.rowprev[sj] = L.rowp[sj];
     }
-    if (L.phase == 1) {
+    if (L.phase == 1 && !eg) {
       // projection of the makespan multipliers on {omega >= 0, sum omega <= k D T}: threshold by active-set pruning
       zsum = br.sum(zsum);
       double th = 0.0;
@@ -397,7 +422,7 @@ __global__ void __launch_bounds__(1024) market_dual_kernel(MarketLaunch L) {
     }
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
       const size_t sj = (size_t)s * J + j, ji = L.per_scn ? sj : j;
-      const double aE = rs / L.E[ji], fD = rs * L.dbar[ji] / DT;
+      const double aE = eg ? rs : rs / L.E[ji], fD = eg ? 0.0 : rs * L.dbar[ji] / DT;
       L.jobpack[sj] = make_float4((float)(L.mj[sj] * aE + L.om[sj] * fD), (float)(aE + fD), (float)L.g[ji],
                                   L.rate[ji * W]);
       if (Q_ROW_ATOMICS(T)) L.rowp[sj] = 0.f;

@@ -167,6 +167,7 @@ struct MarketLaunch {
   float *pws;                     // [S] primal weight in use (market_dual_kernel phase 0: pw raised with k)
   int phase;                      // dual pass: 0 start, 1 PDHG dual step, 2 repair factors, 3 score only
   int mode;                       // dense pass: 0 primal step, 1 column scaling
+  int utility;                    // 0: Shockwave's PWL log + makespan term, 1: Eisenberg-Gale sum_j log(U_j)
 };
 cudaError_t launch_market_prolong(const float *Xc, float *X, const double *pic, double *pi, size_t rows, int S, int W,
                                   int T, int grp, cudaStream_t st);

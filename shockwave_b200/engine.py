@@ -388,14 +388,14 @@ class MarketArgs(C.Structure):
     """swb_market_args (include/swb200.h)."""
     _fields_ = [("S", C.c_int32), ("J", C.c_int32), ("W", C.c_int32), ("T", C.c_int32),
                 ("per_scenario_jobs", C.c_int32), ("on_device", C.c_int32), ("iters", C.c_int32),
-                ("coarse_iters", C.c_int32), ("warm_start", C.c_int32), ("primal_weight", C.c_float),
+                ("coarse_iters", C.c_int32), ("warm_start", C.c_int32), ("primal_weight", C.c_float), ("utility", C.c_int32),
                 ("prm", C.POINTER(Params)), ("g", C.c_void_p), ("E", C.c_void_p), ("c", C.c_void_p),
                 ("dbar", C.c_void_p), ("rem", C.c_void_p), ("rate", C.c_void_p), ("Gw", C.c_void_p),
                 ("cap", C.c_void_p), ("X", C.c_void_p), ("obj", C.c_void_p), ("dense_ms", C.POINTER(C.c_float))]
 
 
 def market_pgd(eng, params, g, E, c, dbar, rem, rate, Gw, X, iters, coarse_iters=0, primal_weight=0.0, cap=None,
-               warm_start=False, device_ptrs=None):
+               warm_start=False, device_ptrs=None, utility=0):
     """Dense primal-dual price-response iterations on X[S,J,W,T] (fp32): `coarse_iters` on the time-coarsened tensor,
     then `iters` on the full one.  Host arrays by default (X is overwritten with the feasible result; its content is
     the starting point only with warm_start); `device_ptrs` = dict(g,E,c,dbar,rem,rate,X) of raw device pointers for
@@ -413,6 +413,7 @@ def market_pgd(eng, params, g, E, c, dbar, rem, rate, Gw, X, iters, coarse_iters
     ms = C.c_float()
     a.iters, a.coarse_iters, a.warm_start = int(iters), int(coarse_iters), int(bool(warm_start))
     a.primal_weight = float(primal_weight)
+    a.utility = int(utility)
     a.prm = (Params * S)(*plist)
     if cap is not None:
         cap = np.ascontiguousarray(cap, dtype=np.float64)

@@ -439,6 +439,64 @@ class MaxMinFairnessStrategyProofPolicy(Policy):
         return self._max_min_fairness_perf_policy.get_allocation(ones, scale_factors, priority_weights, cluster_spec)
 
 
+def _eisenberg_gale(N, coef, sf, present, iters=1500):
+    """S Eisenberg-Gale programs in one batch on the device:  max sum_{j present in s} log(sum_w coef_jw x_jw)
+    s.t. x >= 0, sum_w x_jw <= 1, sum_j sf_j x_jw <= N_w — the cvxpy geo_mean program of
+    max_min_fairness_strategy_proof.py:102-123.  present [S][J] bool.  Solved by the dense price-response kernel
+    (market.cu, log utility) on a 4-round tensor with constant capacities; returns x [S][J][W]."""
+    S, J = present.shape
+    W, T = len(N), 4
+    eng = _engine()
+    prm = [_eng.make_params(int(max(1, round(float(np.sum(N))))), T, 1.0, 0.0, 1.0, 1.0, [0.0, 1.0], {0.0: 1e-6})] * S
+    rate = np.ascontiguousarray(np.broadcast_to((coef / T)[None], (S, J, W)), dtype=np.float32)
+    g = np.ascontiguousarray(np.broadcast_to(np.asarray(sf, np.int32)[None], (S, J)))
+    E = np.ascontiguousarray(present, dtype=np.float64)
+    zeros, ones = np.zeros((S, J)), np.ones((S, J))
+    X = np.zeros((S, J, W, T), dtype=np.float32)
+    _eng.market_pgd(eng, prm, g, E, zeros, ones, zeros, rate, np.asarray(N, np.float64), X, iters, utility=1)
+    return X.mean(axis=3, dtype=np.float64) * present[:, :, None]
+
+
+class MaxMinFairnessStrategyProofPolicyWithPerf(Policy):
+    """max_min_fairness_strategy_proof.py:47-155: the Nash-welfare (geo_mean) allocation, discounted per job by the
+    product over the OTHER jobs of (their throughput with the job) / (their throughput without it) — J + 1
+    Eisenberg-Gale programs, solved here as ONE batch of J + 1 scenarios by the dense price-response kernel."""
+    def __init__(self, solver):
+        Policy.__init__(self, solver)
+        self._name = "MaxMinFairness_Perf"
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, unflattened_priority_weights, cluster_spec,
+                       recurse_deeper=True):
+        throughputs, index = super().flatten(unflattened_throughputs, cluster_spec)
+        if throughputs is None:
+            return None
+        m, n = throughputs.shape
+        job_ids, _ = index
+        N = np.asarray(self._num_workers, dtype=np.float64)
+        live = N > 0
+        if not live.any():
+            raise ValueError("cluster has no workers")
+        sf = np.array([scale_factors[j] for j in job_ids], dtype=np.float64)
+        pw = np.array([1.0 / unflattened_priority_weights[j] for j in job_ids], dtype=np.float64)
+        prop = throughputs @ (N / N.sum())                          # proportional.py:20-43
+        coef = throughputs * (pw / prop * sf)[:, None]              # :87-116
+        present = np.ones((m + 1 if recurse_deeper else 1, m), dtype=bool)
+        for i in range(m if recurse_deeper else 0):
+            present[i + 1, i] = False                               # scenario i + 1: the market without job i (:68-84)
+        x_live = _eisenberg_gale(N[live], coef[:, live], sf, present)
+        x = np.zeros((present.shape[0], m, n))
+        x[:, :, live] = x_live
+        thr = (throughputs[None] * x).sum(axis=2)                   # :130-133, per scenario
+        if not recurse_deeper:
+            return {job_ids[i]: thr[0, i] for i in range(m)}
+        discount = np.ones(m)
+        for i in range(m):                                          # :137-145
+            others = present[i + 1]
+            discount[i] = float(np.prod(thr[0, others] / thr[i + 1, others])) if others.any() else 1.0
+        alloc = (x[0].T * discount).T
+        return super().unflatten(alloc.clip(min=0.0).clip(max=1.0), index), discount
+
+
 class FinishTimeFairnessPolicyWithPerf(Policy):
     def __init__(self, solver):
         Policy.__init__(self, solver)
@@ -688,6 +746,9 @@ def get_policy(policy_name, solver=None, seed=None, priority_reweighting_policie
         "min_total_duration": lambda: MinTotalDurationPolicy(solver=solver),
         "min_total_duration_perf": lambda: MinTotalDurationPolicyWithPerf(solver=solver),
         "shockwave": ShockwavePolicy,
+        # not in the reference's table (its strategy-proof classes are reachable by import only): names added here
+        "max_min_fairness_strategy_proof": lambda: MaxMinFairnessStrategyProofPolicy(solver=solver),
+        "max_min_fairness_strategy_proof_perf": lambda: MaxMinFairnessStrategyProofPolicyWithPerf(solver=solver),
     }
     if policy_name.startswith("allox"):
         return AlloXPolicy(alpha=0.2 if policy_name == "allox" else float(policy_name.split("allox_alpha=")[1]))
