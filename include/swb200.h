@@ -336,7 +336,7 @@ typedef struct swb_market_args {
   int32_t coarse_iters;         /* passes on the time-coarsened tensor X_c[S][J][W][4], run first */
   int32_t warm_start;           /* 1: X holds the starting point, 0: start from X = 0 */
   float primal_weight;          /* PDHG step balance for the objective scaled by J T (tau = tau0/pw, sigma = sigma0 pw);
-                                   0 = default (60; 3 with utility = 1) */
+                                   0 = default (60; 1 with utility = 1) */
   int32_t utility;              /* 0: Shockwave's objective (PWL log + makespan term).  1: Eisenberg-Gale program
                                    max sum_j log(U_j), U_j = sum_wt rate_jw x_jwt over the jobs with E_j > 0 (E_j <= 0:
                                    job absent from the scenario) — the program of

@@ -305,14 +305,35 @@ def eisenberg_gale(coef, sf, N):
     from scipy.optimize import Bounds, LinearConstraint, minimize
     coef, sf, N = np.asarray(coef, float), np.asarray(sf, float), np.asarray(N, float)
     J, W = coef.shape
-    f = lambda z: -np.log(np.maximum((coef * z.reshape(J, W)).sum(axis=1), 1e-300)).sum()
-    g = lambda z: -(coef / np.maximum((coef * z.reshape(J, W)).sum(axis=1), 1e-300)[:, None]).ravel()
+    # utilities floored at 1e-9 inside the solver only (finite derivatives when a trial point starves a job); exact
+    # block-diagonal Hessian and a start that already uses 90 % of every capacity — with the quasi-Newton default and a
+    # timid start trust-constr stops far from the optimum on some instances (capacities 15-60 % used)
+    U = lambda z: np.maximum((coef * z.reshape(J, W)).sum(axis=1), 1e-9)
+    f = lambda z: -np.log(U(z)).sum()
+    g = lambda z: -(coef / U(z)[:, None]).ravel()
+
+    def h(z):
+        u = U(z)
+        H = np.zeros((J * W, J * W))
+        for j in range(J):
+            H[j * W:(j + 1) * W, j * W:(j + 1) * W] = np.outer(coef[j], coef[j]) / u[j] ** 2
+        return H
     A1 = np.kron(np.eye(J), np.ones((1, W)))
     A2 = np.kron(sf[None, :], np.eye(W)).reshape(W, J * W)
-    x0 = np.full(J * W, 0.5 * min(1.0 / W, float((N / sf.sum()).min())))
-    r = minimize(f, x0, jac=g, method="trust-constr", bounds=Bounds(0.0, 1.0),
+    x0 = np.tile(np.minimum(1.0 / W, N / sf.sum()) * 0.9, J)
+    r = minimize(f, x0, jac=g, hess=h, method="trust-constr", bounds=Bounds(0.0, 1.0),
                  constraints=[LinearConstraint(A1, -np.inf, 1.0), LinearConstraint(A2, -np.inf, N)],
-                 options=dict(gtol=1e-12, xtol=1e-14, maxiter=20000))
+                 options=dict(gtol=1e-10, xtol=1e-12, maxiter=5000, barrier_tol=1e-12))
+    if r.status not in (1, 2):
+        raise RuntimeError(f"trust-constr: {r.message}")
+    # polish: the interior-point iterate stays ~1e-3 inside constraints that are exactly tight at the optimum (a job at
+    # its full time share); an active-set pass from there lands on them
+    cons = [dict(type="ineq", fun=lambda z: 1.0 - A1 @ z, jac=lambda z: -A1),
+            dict(type="ineq", fun=lambda z: N - A2 @ z, jac=lambda z: -A2)]
+    r2 = minimize(f, np.clip(r.x, 0.0, 1.0), jac=g, bounds=[(0.0, 1.0)] * (J * W), constraints=cons, method="SLSQP",
+                  options=dict(maxiter=500, ftol=1e-15))
+    if np.isfinite(r2.fun) and r2.fun <= r.fun + 1e-12 and (A1 @ r2.x).max() <= 1 + 1e-9 and np.all(A2 @ r2.x <= N * (1 + 1e-9)):
+        r = r2
     x = np.clip(r.x.reshape(J, W), 0.0, 1.0)
     return x, (coef * x).sum(axis=1)
 

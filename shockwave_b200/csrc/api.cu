@@ -1040,7 +1040,7 @@ int swb_market_pgd(swb_ctx *c, const swb_market_args *a) {
   L.obj = c->m_obj.as<double>();
   if (a->utility != 0 && a->utility != 1) return fail(SWB_ERR_ARG, "swb_market_pgd: utility must be 0 or 1");
   L.utility = a->utility;
-  const double pwrel = a->primal_weight > 0.f ? (double)a->primal_weight : (a->utility == 1 ? 3.0 : 60.0);
+  const double pwrel = a->primal_weight > 0.f ? (double)a->primal_weight : (a->utility == 1 ? 1.0 : 60.0);
   L.pw = (float)(pwrel / ((double)J * (double)T));
   CK(c->m_pws.need((size_t)S * 4, c->st));
   L.pws = c->m_pws.as<float>();

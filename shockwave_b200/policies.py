@@ -439,11 +439,13 @@ class MaxMinFairnessStrategyProofPolicy(Policy):
         return self._max_min_fairness_perf_policy.get_allocation(ones, scale_factors, priority_weights, cluster_spec)
 
 
-def _eisenberg_gale(N, coef, sf, present, iters=1500):
+def _eisenberg_gale(N, coef, sf, present, iters=4000):
     """S Eisenberg-Gale programs in one batch on the device:  max sum_{j present in s} log(sum_w coef_jw x_jw)
     s.t. x >= 0, sum_w x_jw <= 1, sum_j sf_j x_jw <= N_w — the cvxpy geo_mean program of
     max_min_fairness_strategy_proof.py:102-123.  present [S][J] bool.  Solved by the dense price-response kernel
-    (market.cu, log utility) on a 4-round tensor with constant capacities; returns x [S][J][W]."""
+    (market.cu, log utility) on a 4-round tensor with constant capacities; returns x [S][J][W].  4000 passes: the
+    iteration converges linearly once the active set is found, which takes a few hundred to ~2500 passes on the test
+    instances (numpy restatement: utilities within 1e-5 of the oracle's after 3000)."""
     S, J = present.shape
     W, T = len(N), 4
     eng = _engine()
