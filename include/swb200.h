@@ -255,6 +255,24 @@ int swb_policy_waterfill_step(swb_ctx *ctx, int32_t J, int32_t W, const double *
                               const double *prop, const double *lower, const double *mult, double M, double slack,
                               double *x, double *c, double *z, int32_t *stats);
 
+/* ---- Batch of sparse linear programs (the packing policies' LPs) ------------------------------ *
+ * Replaces `cvxprob.solve(solver=self._solver)` in the *WithPacking policies
+ * (scheduler/policies/max_min_fairness.py:317-410, finish_time_fairness.py:160-290, min_total_duration.py:138-234,
+ *  max_sum_throughput.py:111-200; columns and rows from policy.py:68-193 `PolicyWithPacking`): one variable per
+ * (job combination, worker type) — single jobs AND co-located pairs — so the per-job sub-problems the other policy
+ * kernels decompose over are coupled and a general LP method is needed.
+ *     maximise c'x   subject to   A x <= b,  x >= 0        (b may be negative; >= rows are passed negated)
+ * S programs per call, one CTA each, sharing the CSC pattern (colp[n+1], rowi[nnz]) with per-program values
+ * val[S][nnz], c[S][n], b[S][m].  Method: revised simplex with a dense fp64 basis inverse in HBM/L2 (rank-one
+ * updates, Gauss-Jordan refactorisation every 96 pivots, Dantzig pricing with Bland's rule after 40 stalled
+ * pivots, single-artificial phase I).  Exact to roundoff like the reference's solvers; optimal x is not unique.
+ * Out: x[S][n], objective[S], status[S] (0 optimal, 1 infeasible, 2 unbounded, 3 pivot limit, 4 singular basis),
+ * stats[S][4] (optional): pivots, phase-I pivots, refactorisations, Bland pivots.
+ * Limits: m <= 2048, S <= 4096, S * m^2 * 16 B <= 8 GiB.  Returns 0, or SWB_ERR_STATE when any status >= 3. */
+int swb_lp_solve(swb_ctx *ctx, int32_t S, int32_t m, int32_t n, int32_t nnz, const int32_t *colp, const int32_t *rowi,
+                 const double *val, const double *c, const double *b, int32_t max_iter, double *x,
+                 double *objective, int32_t *status, int32_t *stats);
+
 /* ---- AlloX min-cost assignment --------------------------------------------------------------- *
  * Replaces scipy.optimize.linear_sum_assignment(q) in AlloXPolicy.get_allocation
  * (scheduler/policies/allox.py:108-144).  q is implicit: for job i and column col = k*n + j,

@@ -83,6 +83,7 @@ struct swb_ctx {
   DBuf f_slots, f_prog, f_mend, f_mns, f_remfb, f_bffb, f_ampok, f_ampfb, f_ftest, f_ncal;
   swb::ForecastLaunch last_fc;   // descriptor of the latest forecast (for the calibration commit)
   bool have_fc = false;
+  DBuf lp_colp, lp_rowi, lp_val, lp_c, lp_b, lp_Binv, lp_Bm, lp_vec, lp_basis, lp_where, lp_x, lp_out;   // swb_lp_solve
   DBuf ax_p, ax_t, ax_wt, ax_u, ax_v, ax_spc, ax_c4r, ax_r4c, ax_path, ax_sc, ax_sr, ax_out;   // swb_allox_assign
   DBuf pol_coef, pol_sf, pol_t, pol_n, pol_den, pol_x, pol_out;          // swb_policy_pooled
   DBuf het_a, het_N, het_x;                                                 // swb_policy_hetero
@@ -141,7 +142,7 @@ void swb_destroy(swb_ctx *c) {
                  &c->snmax, &c->sn, &c->gmask, &c->sncap, &c->seated, &c->scth, &c->sRr, &c->sths, &c->sn0, &c->snfc, &c->t_off, &c->t_E, &c->t_nm, &c->t_g, &c->t_ns, &c->t_ts,
                  &c->t_modes, &c->t_mm, &c->t_amp, &c->s_r0, &c->s_rl, &c->s_cnt, &c->s_vl, &c->s_acc, &c->t_mu, &c->t_sg, &c->ens_z, &c->gv_in, &c->gv_out, &c->rr_items,
                  &c->pool_pp, &c->pool_bs, &c->f_slots, &c->f_prog, &c->f_mend, &c->f_mns, &c->f_remfb,
-                 &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal, &c->ax_p, &c->ax_t, &c->ax_wt, &c->ax_u, &c->ax_v, &c->ax_spc, &c->ax_c4r, &c->ax_r4c,
+                 &c->f_bffb, &c->f_ampok, &c->f_ampfb, &c->f_ftest, &c->f_ncal, &c->lp_colp, &c->lp_rowi, &c->lp_val, &c->lp_c, &c->lp_b, &c->lp_Binv, &c->lp_Bm, &c->lp_vec, &c->lp_basis, &c->lp_where, &c->lp_x, &c->lp_out, &c->ax_p, &c->ax_t, &c->ax_wt, &c->ax_u, &c->ax_v, &c->ax_spc, &c->ax_c4r, &c->ax_r4c,
                  &c->ax_path, &c->ax_sc, &c->ax_sr, &c->ax_out, &c->pol_coef, &c->pol_sf, &c->pol_t,
                  &c->pol_n, &c->pol_den, &c->pol_x, &c->pol_out, &c->mc_R0, &c->mc_mu, &c->mc_sigma, &c->mc_H, &c->mc_out,
                  &c->m_theta, &c->m_rowp, &c->m_colload,
@@ -1144,6 +1145,57 @@ int swb_allox_assign(swb_ctx *c, int32_t m, int32_t n, int32_t W, const double *
   CK(cudaStreamSynchronize(c->st));
   if (total_cost) *total_cost = tot;
   return 0;
+}
+
+int swb_lp_solve(swb_ctx *c, int32_t S, int32_t m, int32_t n, int32_t nnz, const int32_t *colp, const int32_t *rowi,
+                 const double *val, const double *cost, const double *b, int32_t max_iter, double *x,
+                 double *objective, int32_t *status, int32_t *stats) {
+  if (!c || !colp || !rowi || !val || !cost || !b || !x || !objective || !status)
+    return fail(SWB_ERR_ARG, "swb_lp_solve: null argument");
+  if (S <= 0 || S > 4096 || m <= 0 || m > 2048 || n <= 0 || n > (1 << 22) || nnz < 0 || max_iter <= 0)
+    return fail(SWB_ERR_ARG, "swb_lp_solve: need 1 <= S <= 4096, 1 <= m <= 2048, 1 <= n <= 2^22, max_iter > 0");
+  if ((size_t)S * m * m * 16 > ((size_t)8 << 30))
+    return fail(SWB_ERR_ARG, "swb_lp_solve: S * m^2 * 16 bytes of basis inverses exceed 8 GiB");
+  if (colp[0] != 0 || colp[n] != nnz) return fail(SWB_ERR_ARG, "swb_lp_solve: colp[0] must be 0 and colp[n] == nnz");
+  for (int j = 0; j < n; ++j)
+    if (colp[j + 1] < colp[j]) return fail(SWB_ERR_ARG, "swb_lp_solve: colp must be non-decreasing");
+  for (int k = 0; k < nnz; ++k)
+    if (rowi[k] < 0 || rowi[k] >= m) return fail(SWB_ERR_ARG, "swb_lp_solve: row index out of range");
+  CK(cudaSetDevice(c->device));
+  const size_t sm = (size_t)S * m, sn = (size_t)S * n, snz = (size_t)S * (nnz > 0 ? nnz : 1);
+  CK(c->lp_colp.need((size_t)(n + 1) * 4, c->st)); CK(c->lp_rowi.need((size_t)(nnz > 0 ? nnz : 1) * 4, c->st));
+  CK(c->lp_val.need(snz * 8, c->st)); CK(c->lp_c.need(sn * 8, c->st)); CK(c->lp_b.need(sm * 8, c->st));
+  CK(c->lp_Binv.need(sm * m * 8, c->st)); CK(c->lp_Bm.need(sm * m * 8, c->st)); CK(c->lp_vec.need(sm * 5 * 8, c->st));
+  CK(c->lp_basis.need(sm * 4, c->st)); CK(c->lp_where.need((size_t)S * (n + m + 1) * 4, c->st));
+  CK(c->lp_x.need(sn * 8, c->st)); CK(c->lp_out.need((size_t)S * 64, c->st));
+  CK(cudaMemcpyAsync(c->lp_colp.p, colp, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, c->st));
+  if (nnz > 0) {
+    CK(cudaMemcpyAsync(c->lp_rowi.p, rowi, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->lp_val.p, val, (size_t)S * nnz * 8, cudaMemcpyHostToDevice, c->st));
+  }
+  CK(cudaMemcpyAsync(c->lp_c.p, cost, sn * 8, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->lp_b.p, b, sm * 8, cudaMemcpyHostToDevice, c->st));
+  swb::LpLaunch L;
+  L.S = S; L.m = m; L.n = n; L.nnz = nnz; L.max_iter = max_iter;
+  L.colp = c->lp_colp.as<int>(); L.rowi = c->lp_rowi.as<int>();
+  L.val = c->lp_val.as<double>(); L.c = c->lp_c.as<double>(); L.b = c->lp_b.as<double>();
+  L.Binv = c->lp_Binv.as<double>(); L.Bm = c->lp_Bm.as<double>(); L.vec = c->lp_vec.as<double>();
+  L.basis = c->lp_basis.as<int>(); L.where = c->lp_where.as<int>();
+  L.x = c->lp_x.as<double>(); L.out = c->lp_out.as<double>();
+  CK(swb::launch_lp(L, c->st));
+  std::vector<double> out((size_t)S * 8);
+  CK(cudaMemcpyAsync(x, c->lp_x.p, sn * 8, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(out.data(), c->lp_out.p, (size_t)S * 64, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  int worst = 0;
+  for (int s = 0; s < S; ++s) {
+    objective[s] = out[(size_t)s * 8];
+    status[s] = (int32_t)out[(size_t)s * 8 + 1];
+    if (status[s] > worst) worst = status[s];
+    if (stats)
+      for (int k = 0; k < 4; ++k) stats[s * 4 + k] = (int32_t)out[(size_t)s * 8 + 2 + k];
+  }
+  return worst >= 3 ? fail(SWB_ERR_STATE, "swb_lp_solve: a program hit the pivot limit or a singular basis (see status[])") : 0;
 }
 
 int swb_last_timings(swb_ctx *c, double *ms_solve, double *ms_place, int32_t *passes) {

@@ -229,4 +229,17 @@ cudaError_t launch_gbm_apply(const GbmApplyLaunch &L, cudaStream_t st);
 cudaError_t launch_gbm_ensemble(int S, int J, double P_total, const double *sums, const double *z, double *rem_out,
                                 cudaStream_t st);
 
+// batch of S linear programs  max c'x : A x <= b, x >= 0  with a shared CSC pattern (lp.cu / lp_core.cuh)
+struct LpLaunch {
+  int S, m, n, nnz, max_iter;
+  const int *colp, *rowi;        // [n + 1], [nnz]  shared by the batch
+  const double *val, *c, *b;     // [S][nnz], [S][n], [S][m]
+  double *Binv, *Bm;             // [S][m * m] each
+  double *vec;                   // [S][5 * m]
+  int *basis, *where;            // [S][m], [S][n + m + 1]
+  double *x;                     // [S][n] out
+  double *out;                   // [S][8] out: objective, status, pivots, phase-I pivots, refactorisations, Bland pivots
+};
+cudaError_t launch_lp(const LpLaunch &L, cudaStream_t st);
+
 }  // namespace swb

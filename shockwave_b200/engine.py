@@ -59,7 +59,7 @@ class RoundArgs(C.Structure):
 
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
            "swb_solve", "swb_job_add", "swb_job_remove", "swb_job_table_stats", "swb_job_set_gbm", "swb_gbm_ensemble", "swb_gavel_round", "swb_round_solve", "swb_forecast",
-           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_policy_hetero", "swb_policy_waterfill_step", "swb_gbm_forecast", "swb_market_pgd", "swb_set_option", "swb_allox_assign"]
+           "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_policy_hetero", "swb_policy_waterfill_step", "swb_gbm_forecast", "swb_market_pgd", "swb_set_option", "swb_allox_assign", "swb_lp_solve"]
 
 _lib = None
 
@@ -352,6 +352,31 @@ class Engine:
         self._check(self.lib.swb_allox_assign(self.h, m, n, W, _ptr(p), _ptr(t), _ptr(wtype), _ptr(cols),
                                               C.byref(tot)), "swb_allox_assign")
         return cols, tot.value
+
+    def lp_solve(self, colp, rowi, val, c, b, max_iter=0):
+        """Batch of S linear programs  max c'x : A x <= b, x >= 0  with a shared CSC pattern (swb_lp_solve).
+        colp [n+1], rowi [nnz] int32; val [S, nnz], c [S, n], b [S, m] float64 (1-D arrays mean S = 1).
+        Returns x [S, n], objective [S], status [S], stats [S, 4]."""
+        colp = np.ascontiguousarray(colp, dtype=np.int32); rowi = np.ascontiguousarray(rowi, dtype=np.int32)
+        val = np.atleast_2d(np.ascontiguousarray(val, dtype=np.float64))
+        c = np.atleast_2d(np.ascontiguousarray(c, dtype=np.float64))
+        b = np.atleast_2d(np.ascontiguousarray(b, dtype=np.float64))
+        S, n = c.shape
+        m = b.shape[1]
+        nnz = len(rowi)
+        if val.shape != (S, nnz) or b.shape[0] != S or len(colp) != n + 1:
+            raise ValueError("lp_solve: inconsistent array shapes")
+        x = np.zeros((S, n)); obj = np.zeros(S); status = np.zeros(S, dtype=np.int32)
+        stats = np.zeros((S, 4), dtype=np.int32)
+        if max_iter <= 0:
+            max_iter = 50 * (m + n) + 1000
+        self.lib.swb_lp_solve.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 5 + [C.c_int32] + \
+                                         [C.c_void_p] * 4
+        self.lib.swb_lp_solve.restype = C.c_int
+        self._check(self.lib.swb_lp_solve(self.h, S, m, n, nnz, _ptr(colp), _ptr(rowi), _ptr(val), _ptr(c), _ptr(b),
+                                          int(max_iter), _ptr(x), _ptr(obj), _ptr(status), _ptr(stats)),
+                    "swb_lp_solve")
+        return x, obj, status, stats
 
     def last_timings(self):
         a, b, n = C.c_double(), C.c_double(), C.c_int32()

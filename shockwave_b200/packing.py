@@ -1,0 +1,339 @@
+"""The packing policies (space sharing: two jobs co-located on one accelerator) behind the reference's signatures.
+
+Mirrors scheduler/policies/policy.py:68-193 (`PolicyWithPacking`) and the four *WithPacking classes that hand an LP
+over (job combination x worker type) columns to cvxpy:
+  MaxMinFairnessPolicyWithPacking ............... max_min_fairness.py:116-121, 317-410
+  FinishTimeFairnessPolicyWithPacking ........... finish_time_fairness.py:160-290   (stateful)
+  MinTotalDurationPolicyWithPacking ............. min_total_duration.py:138-234
+  ThroughputNormalizedByCostSumWithPackingSLOs .. max_sum_throughput.py:111-200
+Keys of `unflattened_throughputs` are the reference's `JobIdPair` objects (duck-typed: is_pair(), singletons(),
+as_tuple(), sortable, hashable); a pair's value per worker type is the two members' throughputs when co-located.
+
+Every program is solved on the GPU by swb_lp_solve (lp.cu: revised simplex, one CTA per program) — there is no CPU
+path.  The host side only assembles the sparse columns (vectorised; the reference materialises a dense
+[n_single x n_comb x W] tensor in Python loops) and, for finish-time fairness, drives a 16-way multi-section over
+the scalar ratio with one launch of 16 programs per pass.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from . import policies as _pol
+from .policies import Policy
+
+_SECTIONS = 16      # candidate ratios per launch of the finish-time-fairness search
+
+
+def _lp(colp, rowi, val, c, b, max_iter=0):
+    """All LPs of this module go through here (tests swap in a CPU oracle backend to exercise the host logic)."""
+    return _pol._engine().lp_solve(colp, rowi, val, c, b, max_iter)
+
+
+class _Columns:
+    """Sparse column model of one packed program: columns (combination c, worker type w) with capacity and share
+    rows (policy.py:172-193), plus per-single-job linear forms T_i(x) = sum over relevant combinations."""
+
+    def __init__(self, d, scale_factors, cluster_spec, priority_weights=None):
+        job_ids = sorted(list(d.keys()))
+        worker_types = sorted(list(d[job_ids[0]].keys()))
+        singles = [j for j in job_ids if not j.is_pair()]
+        pos = {s: i for i, s in enumerate(singles)}
+        M, W, Ns = len(job_ids), len(worker_types), len(singles)
+        self.job_ids, self.worker_types, self.singles = job_ids, worker_types, singles
+        self.M, self.W, self.Ns = M, W, Ns
+        self.N = np.array([cluster_spec[w] for w in worker_types], dtype=np.float64)
+        mem = np.full((M, 2), -1, dtype=np.int64)          # single-job index of each member (-1: none / not a key)
+        thr = np.zeros((M, 2, W), dtype=np.float32)        # float32 like the reference's all_m (policy.py:132)
+        sfc = np.zeros(M, dtype=np.float64)                # common scale factor of the combination, 0 on mismatch
+        for c, jid in enumerate(job_ids):
+            row = d[jid]
+            if not jid.is_pair():
+                mem[c, 0] = pos[jid]
+                thr[c, 0] = [row[w] for w in worker_types]
+                sfc[c] = scale_factors[jid]
+            else:
+                tup = jid.as_tuple()
+                sf = None
+                for s in jid.singletons():
+                    # policy.py:75-85
+                    sf = 0 if (sf is not None and sf != scale_factors[s]) else scale_factors[s]
+                    k = tup.index(s[0])
+                    if s in pos:
+                        mem[c, k] = pos[s]
+                        thr[c, k] = [row[w][k] for w in worker_types]
+                sfc[c] = sf
+        if priority_weights is not None:                   # policy.py:158-159, in float32 like the reference
+            for c in range(M):
+                for k in range(2):
+                    if mem[c, k] >= 0:
+                        thr[c, k] /= priority_weights[singles[mem[c, k]]]
+        self.mem, self.thr, self.sfc = mem, thr.astype(np.float64), sfc
+        self.thr_single = np.array([[d[s][w] for w in worker_types] for s in singles], dtype=np.float64)
+        self.sf_single = np.array([scale_factors[s] for s in singles], dtype=np.float64)
+        # live columns: effective scale factor != 0 (the reference pins the others to 0, max_min_fairness.py:396-399)
+        # and a worker type with capacity (capacity 0 forces the column to 0 through the capacity row)
+        live_w = np.flatnonzero(self.N > 0)
+        cc, ww = np.meshgrid(np.flatnonzero(sfc != 0), live_w, indexing="ij")
+        self.col_c, self.col_w = cc.ravel(), ww.ravel()
+        self.nv = len(self.col_c)
+        self.live_w = live_w
+        self.wrow = {int(w): r for r, w in enumerate(live_w)}
+
+    # ---- linear forms ----
+    def form(self, with_sf=False):
+        """COO triplets (single i, column v, coefficient) of T_i(x) for every single job."""
+        ii, vv, aa = [], [], []
+        v = np.arange(self.nv)
+        for k in range(2):
+            i = self.mem[self.col_c, k]
+            sel = i >= 0
+            a = self.thr[self.col_c, k, self.col_w]
+            if with_sf:
+                a = a * self.sfc[self.col_c]
+            ii.append(i[sel]); vv.append(v[sel]); aa.append(a[sel])
+        return np.concatenate(ii), np.concatenate(vv), np.concatenate(aa)
+
+    def base_rows(self):
+        """COO triplets of the capacity rows (0 .. Wl-1) and the share rows (Wl .. Wl+Ns-1), and their right sides."""
+        Wl = len(self.live_w)
+        v = np.arange(self.nv)
+        rr = [np.array([self.wrow[int(w)] for w in self.col_w], dtype=np.int64)]
+        vv = [v]
+        aa = [self.sfc[self.col_c]]
+        for k in range(2):
+            i = self.mem[self.col_c, k]
+            sel = i >= 0
+            rr.append(Wl + i[sel]); vv.append(v[sel]); aa.append(np.ones(int(sel.sum())))
+        b = np.concatenate([self.N[self.live_w], np.ones(self.Ns)])
+        return np.concatenate(rr), np.concatenate(vv), np.concatenate(aa), b
+
+    def expand(self, xv):
+        """Column values -> the reference's (n_comb x W) matrix, clipped to [0, 1] like every policy's return."""
+        x = np.zeros((self.M, self.W))
+        x[self.col_c, self.col_w] = xv
+        return np.clip(x, 0.0, 1.0)
+
+    def rates(self, xv):
+        """T_i(x) for every single job."""
+        i, v, a = self.form()
+        return np.bincount(i, weights=a * xv[v], minlength=self.Ns)
+
+
+def _csc(rows, cols, vals, n):
+    """COO -> (colp, rowi, order): `order` sorts any per-entry value array into the CSC layout."""
+    order = np.lexsort((rows, cols))
+    colp = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(np.bincount(cols, minlength=n), out=colp[1:])
+    return colp, rows[order].astype(np.int32), order
+
+
+def _max_min(C, fi, fv, fa_batch):
+    """max z : z <= sum_v fa[i, v] x_v for every single job i, base rows.  fa_batch is [S, nnz_form] (one program per
+    row).  Returns x [S, nv], z [S]."""
+    fa_batch = np.atleast_2d(fa_batch)
+    S = fa_batch.shape[0]
+    br, bv, ba, bb = C.base_rows()
+    m0 = len(bb)
+    nz = C.nv                                   # column index of z
+    rows = np.concatenate([br, m0 + fi, m0 + np.arange(C.Ns)])
+    cols = np.concatenate([bv, fv, np.full(C.Ns, nz)])
+    colp, rowi, order = _csc(rows, cols, None, C.nv + 1)
+    val = np.empty((S, len(rows)))
+    for s in range(S):
+        val[s] = np.concatenate([ba, -fa_batch[s], np.ones(C.Ns)])[order]
+    c = np.zeros((S, C.nv + 1))
+    c[:, nz] = 1.0
+    b = np.tile(np.concatenate([bb, np.zeros(C.Ns)]), (S, 1))
+    x, obj, status, stats = _lp(colp, rowi, val, c, b)
+    if np.any(status != 0):
+        raise RuntimeError(f"packed max-min program: simplex status {status.tolist()}")
+    _max_min.last_stats = stats
+    return x[:, :C.nv], x[:, nz]
+
+
+class PolicyWithPacking(Policy):
+    """policy.py:68-193 (host side).  `flatten`/`unflatten` keep the reference's index tuple."""
+
+    def __init__(self, solver="ECOS"):
+        Policy.__init__(self, solver)
+
+    def _columns(self, d, scale_factors, cluster_spec, priority_weights=None):
+        if len(d) == 0:
+            return None
+        first = d[next(iter(d))]
+        if len(first) == 0:
+            return None
+        C = _Columns(d, scale_factors, cluster_spec, priority_weights)
+        self._num_workers = [cluster_spec[w] for w in C.worker_types]
+        return C
+
+    @staticmethod
+    def _unflatten(C, x):
+        return {jid: dict(zip(C.worker_types, row)) for jid, row in zip(C.job_ids, x.tolist())}
+
+
+def _proportional(thr, N):
+    """proportional.py:14-43: x_iw = (N_w / m) / max row sum -> N_w / sum N."""
+    return thr @ (N / N.sum())
+
+
+def _isolated(thr, sf, N):
+    """isolated.py:14-53."""
+    m = thr.shape[0]
+    x = (N[None, :] / m) / sf[:, None]
+    x = x / np.maximum(x.sum(axis=1), 1.0)[:, None]
+    return (thr * x).sum(axis=1)
+
+
+class MaxMinFairnessPolicyWithPacking(PolicyWithPacking):
+    def __init__(self, solver):
+        PolicyWithPacking.__init__(self, solver)
+        self._name = "MaxMinFairness_Packing"
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, unflattened_priority_weights, cluster_spec):
+        C = self._columns(unflattened_throughputs, scale_factors, cluster_spec, unflattened_priority_weights)
+        if C is None or C.Ns == 0:
+            return None
+        prop = _proportional(C.thr_single, C.N)                     # max_min_fairness.py:352-360
+        fi, fv, fa = C.form(with_sf=True)                           # :367-381
+        xv, z = _max_min(C, fi, fv, fa / prop[fi])
+        self.last_objective = float(z[0])
+        return self._unflatten(C, C.expand(xv[0]))
+
+
+class FinishTimeFairnessPolicyWithPacking(PolicyWithPacking):
+    def __init__(self, solver):
+        PolicyWithPacking.__init__(self, solver)
+        self._name = "FinishTimeFairness_Packing"
+        self._cumulative_isolated_time = {}
+        self._isolated_throughputs_prev_iteration = {}
+        self._num_steps_remaining_prev_iteration = {}
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, unflattened_priority_weights,
+                       times_since_start, num_steps_remaining, cluster_spec):
+        C = self._columns(unflattened_throughputs, scale_factors, cluster_spec, unflattened_priority_weights)
+        if C is None or C.Ns == 0:
+            self._isolated_throughputs_prev_iteration = {}
+            self._num_steps_remaining_prev_iteration = {}
+            return None
+        iso = _isolated(C.thr_single, C.sf_single, C.N)             # finish_time_fairness.py:199-210
+        for s in C.singles:                                          # :214-230
+            if s not in self._cumulative_isolated_time:
+                self._cumulative_isolated_time[s] = 0
+            if s in self._num_steps_remaining_prev_iteration:
+                self._cumulative_isolated_time[s] += (
+                    self._num_steps_remaining_prev_iteration[s] - num_steps_remaining[s]
+                ) / self._isolated_throughputs_prev_iteration[s]
+        n = np.array([num_steps_remaining[s] for s in C.singles], dtype=np.float64)
+        t = np.array([times_since_start[s] for s in C.singles], dtype=np.float64)
+        den = np.array([self._cumulative_isolated_time[s] for s in C.singles], dtype=np.float64) + n / iso
+        fi, fv, fa = C.form()
+
+        def ratio(xv):      # the reference's objective at x (:232-246)
+            T = C.rates(xv)
+            with np.errstate(divide="ignore"):
+                return float(np.max((t + n / np.where(T > 0, T, 0.0)) / den))
+
+        # minimise max_i (t_i + n_i / T_i(x)) / den_i: rho is attainable iff max_x min_i T_i(x) / r_i(rho) >= 1 with
+        # r_i = n_i / (rho den_i - t_i).  Every x bounds rho* from above by its own ratio, every failed rho from below.
+        lo = float(np.max(t / den))
+        xv0, _ = _max_min(C, fi, fv, fa * (den / n)[fi])
+        best_x, hi = xv0[0], ratio(xv0[0])
+        if not np.isfinite(hi):
+            raise RuntimeError("FinishTimeFairness_Packing: a job has no column with positive throughput")
+        passes = 1
+        while hi - lo > 1e-9 * hi and passes < 16:
+            rho = lo + (hi - lo) * (np.arange(1, _SECTIONS + 1) / (_SECTIONS + 1.0))
+            r = n[None, :] / (rho[:, None] * den[None, :] - t[None, :])          # [S, Ns] needed throughputs
+            xv, z = _max_min(C, fi, fv, fa[None, :] / r[:, fi])
+            passes += 1
+            for k in range(_SECTIONS):
+                rk = ratio(xv[k])
+                if rk < hi:
+                    hi, best_x = rk, xv[k]
+                if z[k] < 1.0 - 1e-9:
+                    lo = max(lo, float(rho[k]))
+            lo = min(lo, hi)
+        self.last_objective, self.last_passes = hi, passes
+        self._num_steps_remaining_prev_iteration = copy.copy(num_steps_remaining)
+        self._isolated_throughputs_prev_iteration = {s: iso[i] for i, s in enumerate(C.singles)}
+        return self._unflatten(C, C.expand(best_x))
+
+
+class MinTotalDurationPolicyWithPacking(PolicyWithPacking):
+    def __init__(self, solver):
+        PolicyWithPacking.__init__(self, solver)
+        self._name = "MinTotalDuration_Packing"
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, num_steps_remaining, cluster_spec):
+        C = self._columns(unflattened_throughputs, scale_factors, cluster_spec)
+        if C is None or C.Ns == 0:
+            return None
+        n = np.array([num_steps_remaining[s] for s in C.singles], dtype=np.float64)
+        fi, fv, fa = C.form()
+        # T is attainable iff some x has T_i(x) >= n_i / T for all i  <=>  T >= 1 / max_x min_i T_i(x) / n_i: ONE
+        # program instead of the reference's ~14 feasibility probes; the probes are then replayed on the verdicts
+        Tref = 1.0e4
+        xv, z = _max_min(C, fi, fv, fa * (Tref / n)[fi])
+        if not z[0] > 0:
+            raise RuntimeError("MinTotalDuration_Packing: a job cannot make progress on this cluster")
+        T_star = Tref / float(z[0])
+        max_T, min_T, last_max_T, last_T = 1000000.0, 100.0, 1000000.0, None      # min_total_duration.py:206-230
+        while last_T is None:
+            while 1.05 * min_T < max_T:
+                T = (min_T + max_T) / 2.0
+                if T >= T_star * (1.0 - 1e-9):
+                    last_T, max_T = T, T
+                else:
+                    min_T = T
+            max_T, min_T = last_max_T * 10.0, last_max_T
+            last_max_T *= 10
+        self.last_objective, self.last_T_star = last_T, T_star
+        return self._unflatten(C, C.expand(xv[0]))
+
+
+class ThroughputNormalizedByCostSumWithPackingSLOs(PolicyWithPacking):
+    def __init__(self, solver):
+        Policy.__init__(self, solver)
+        self._name = "ThroughputNormalizedByCostSum_PackingSLOs"
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, cluster_spec, instance_costs=None, SLOs={},
+                       num_steps_remaining={}):
+        C = self._columns(unflattened_throughputs, scale_factors, cluster_spec)
+        if C is None or C.Ns == 0:
+            return None
+        cost = np.ones(C.W)
+        if instance_costs is not None:
+            cost = np.array([instance_costs[w] for w in C.worker_types], dtype=np.float64)
+        fi, fv, fa = C.form()
+        cvec = np.bincount(fv, weights=fa / cost[C.col_w[fv]], minlength=C.nv)    # max_sum_throughput.py:146-163
+        br, bv, ba, bb = C.base_rows()
+        m0 = len(bb)
+        need = {}
+        for job_id in SLOs:                                                       # :170-183
+            i = C.job_ids.index(job_id)
+            assert job_id in num_steps_remaining
+            need[i] = num_steps_remaining[job_id] / SLOs[job_id]
+
+        def solve(with_slos):
+            rows, cols, vals, b = [br], [bv], [ba], [bb]
+            if with_slos:
+                for k, (i, nd) in enumerate(need.items()):          # -T_i(x) / need_i <= -1
+                    sel = fi == i
+                    rows.append(np.full(int(sel.sum()), m0 + k)); cols.append(fv[sel]); vals.append(-fa[sel] / nd)
+                b.append(-np.ones(len(need)))
+            rows, cols, vals, b = map(np.concatenate, (rows, cols, vals, b))
+            colp, rowi, order = _csc(rows, cols, None, C.nv)
+            return _lp(colp, rowi, vals[order], cvec, b)
+
+        x, obj, status, _ = solve(bool(need))
+        self.used_SLOs = bool(need) and status[0] == 0
+        if need and status[0] == 1:       # "x.value is None": the reference warns and solves again without the SLO rows
+            print("WARNING: No allocation possible with provided SLOs!")
+            x, obj, status, _ = solve(False)
+        if status[0] != 0:
+            raise RuntimeError(f"ThroughputNormalizedByCostSum_PackingSLOs: simplex status {int(status[0])}")
+        self.last_objective = float(obj[0])
+        return self._unflatten(C, C.expand(x[0]))

@@ -752,6 +752,13 @@ def get_policy(policy_name, solver=None, seed=None, priority_reweighting_policie
         "max_min_fairness_strategy_proof": lambda: MaxMinFairnessStrategyProofPolicy(solver=solver),
         "max_min_fairness_strategy_proof_perf": lambda: MaxMinFairnessStrategyProofPolicyWithPerf(solver=solver),
     }
+    packed = {"max_min_fairness_packed": "MaxMinFairnessPolicyWithPacking",
+              "finish_time_fairness_packed": "FinishTimeFairnessPolicyWithPacking",
+              "min_total_duration_packed": "MinTotalDurationPolicyWithPacking",
+              "max_sum_throughput_normalized_by_cost_packed_SLOs": "ThroughputNormalizedByCostSumWithPackingSLOs"}
+    if policy_name in packed:       # the *_packed names of utils.py:626-672 (packing.py: LPs on swb_lp_solve)
+        from . import packing
+        return getattr(packing, packed[policy_name])(solver=solver)
     if policy_name.startswith("allox"):
         return AlloXPolicy(alpha=0.2 if policy_name == "allox" else float(policy_name.split("allox_alpha=")[1]))
     if policy_name not in table:

@@ -1,0 +1,243 @@
+"""CPU tests of the packing-policy path (no GPU):
+  * the oracle's array construction (oracle/gavel_packed.py flatten / scale_factors_array) is pinned BIT FOR BIT on the
+    reference's own `PolicyWithPacking` (policy.py:68-160), imported from the staged reference with a stub `cvxpy`
+    (those methods are pure numpy; only the solve needs cvxpy);
+  * shockwave_b200/packing.py's HOST logic (sparse column model, multi-section, stateful bookkeeping, the bisection
+    replay) against the oracle, with HiGHS standing in for swb_lp_solve through the module's `_lp` hook;
+  * the DEVICE simplex source (csrc/lp_core.cuh) compiled for the host (tests/native/lp_host.cpp, one thread) against
+    HiGHS on random programs — optimal, infeasible, unbounded, degenerate — and on packed programs."""
+import ctypes as C
+import importlib
+import os
+import shutil
+import subprocess
+import sys
+import types
+
+import numpy as np
+import pytest
+from scipy.optimize import linprog
+
+from oracle import gavel_packed as gp
+from oracle import ref_harness
+from tests.packing_fixtures import JobId, instance
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SPEC = {"v100": 8, "p100": 6, "k80": 4}
+COSTS = {"k80": 1.0, "p100": 2.0, "v100": 3.0}
+
+
+@pytest.fixture()
+def highs_backend(monkeypatch):
+    from shockwave_b200 import packing as pk
+    monkeypatch.setattr(pk, "_lp", gp.lp_backend)
+    return pk
+
+
+def _base_ok(alloc, thr, sf, spec):
+    ids = sorted(alloc.keys())
+    wts = sorted(spec.keys())
+    x = np.array([[alloc[c][w] for w in wts] for c in ids])
+    assert x.min() >= 0 and x.max() <= 1 + 1e-12
+    sfc = gp.scale_factors_array(sf, ids, len(ids), len(wts))
+    assert np.all((x * sfc).sum(axis=0) <= np.array([spec[w] for w in wts]) * (1 + 1e-9) + 1e-9)
+    assert np.all(x[sfc == 0] == 0)
+    for s in [c for c in ids if not c.is_pair()]:
+        share = sum(x[i].sum() for i, c in enumerate(ids) if s in c.singletons())
+        assert share <= 1 + 1e-9
+    return x
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="staged reference not present")
+def test_oracle_flatten_pinned_on_reference():
+    pol_dir = os.path.join(ref_harness.REF, "policies")
+    saved = {k: sys.modules.get(k) for k in ("cvxpy", "policy", "job_id_pair")}
+    sys.modules["cvxpy"] = types.ModuleType("cvxpy")          # policy.py imports it at the top; flatten never calls it
+    sys.path[:0] = [pol_dir, ref_harness.REF]
+    try:
+        for k in ("policy", "job_id_pair"):
+            sys.modules.pop(k, None)
+        ref_policy = importlib.import_module("policy")
+        ref_pair = importlib.import_module("job_id_pair").JobIdPair
+        for ns, pf, seed in [(5, 1.0, 1), (12, 0.6, 2), (20, 0.3, 3)]:
+            thr, sf, prio, _, _, spec, _ = instance(ns, SPEC, seed, pf, make_id=ref_pair)
+            for pw in (None, prio):
+                P = ref_policy.PolicyWithPacking()
+                ref_m, ref_idx = P.flatten(thr, spec, priority_weights=pw)
+                my_m, my_idx = gp.flatten(thr, spec, priority_weights=pw)
+                assert ref_m.dtype == my_m.dtype and np.array_equal(ref_m, my_m)
+                assert list(ref_idx[0]) == list(my_idx[0]) and list(ref_idx[1]) == list(my_idx[1])
+                assert ref_idx[2] == my_idx[2] and ref_idx[3] == my_idx[3]
+                m, n = ref_m[0].shape
+                assert np.array_equal(P.scale_factors_array(sf, ref_idx[0], m, n),
+                                      gp.scale_factors_array(sf, my_idx[0], m, n))
+            # the tests' own JobId orders, hashes and splits like the reference's JobIdPair
+            a = sorted(thr.keys())
+            b = sorted(JobId(*k.as_tuple()) for k in thr)
+            assert [k.as_tuple() for k in a] == [k.as_tuple() for k in b]
+    finally:
+        sys.path[:] = [p for p in sys.path if p not in (pol_dir, ref_harness.REF)]
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+@pytest.mark.parametrize("ns,pf", [(6, 1.0), (14, 0.5), (24, 1.0)])
+def test_host_logic_against_oracle(highs_backend, ns, pf):
+    pk = highs_backend
+    thr, sf, prio, t0, steps, spec, singles = instance(ns, SPEC, seed=100 + ns, pair_fraction=pf)
+    z, _, _ = gp.max_min_fairness_packed(thr, sf, prio, spec)
+    pol = pk.MaxMinFairnessPolicyWithPacking("ECOS")
+    _base_ok(pol.get_allocation(thr, sf, prio, spec), thr, sf, spec)
+    assert abs(pol.last_objective - z) <= 1e-7 * z
+
+    T, _, _ = gp.min_total_duration_packed(thr, sf, steps, spec)
+    pol = pk.MinTotalDurationPolicyWithPacking("ECOS")
+    x = _base_ok(pol.get_allocation(thr, sf, steps, spec), thr, sf, spec)
+    assert pol.last_objective == T                      # the same probe sequence as the reference's bisection
+    ids = sorted(thr.keys())
+    P = gp.Packed(thr, sf, spec)
+    for i, s in enumerate(singles):                     # every job finishes within the returned T
+        assert P.coef(i) @ x.ravel() >= steps[s] / T * (1 - 1e-7)
+
+    # two stateful rounds of finish-time fairness (cumulative isolated time carried over)
+    pol = pk.FinishTimeFairnessPolicyWithPacking("ECOS")
+    cum = {s: 0.0 for s in singles}
+    steps_now = dict(steps)
+    iso_prev = None
+    for rnd in range(2):
+        if rnd == 1:
+            Pk = gp.Packed(thr, sf, spec, prio)
+            iso = gp.isolated_throughputs(Pk.thr_single, Pk.sf_single, Pk.N)
+            steps_next = {s: steps_now[s] * 0.9 for s in singles}
+            for i, s in enumerate(singles):
+                cum[s] += (steps_now[s] - steps_next[s]) / iso[i]
+            steps_now = steps_next
+        rho, _, _ = gp.finish_time_fairness_packed(thr, sf, prio, t0, steps_now, cum, spec)
+        _base_ok(pol.get_allocation(thr, sf, prio, t0, steps_now, spec), thr, sf, spec)
+        assert abs(pol.last_objective - rho) <= 1e-6 * rho, (rnd, pol.last_objective, rho)
+        assert pol.last_passes <= 12
+
+    slo = {singles[i]: steps[singles[i]] / (thr[singles[i]]["k80"] * 0.1) for i in range(0, ns, 5)}
+    o, _, used, _ = gp.max_sum_throughput_packed_slos(thr, sf, spec, COSTS, slo, steps)
+    pol = pk.ThroughputNormalizedByCostSumWithPackingSLOs("ECOS")
+    _base_ok(pol.get_allocation(thr, sf, spec, COSTS, slo, steps), thr, sf, spec)
+    assert pol.used_SLOs == used and abs(pol.last_objective - o) <= 1e-7 * o
+    # impossible SLOs: the reference's "solve again without the SLO rows"
+    slo_bad = {singles[0]: 1e-3}
+    o2, _, used2, _ = gp.max_sum_throughput_packed_slos(thr, sf, spec, COSTS, slo_bad, steps)
+    pol.get_allocation(thr, sf, spec, COSTS, slo_bad, steps)
+    assert not used2 and not pol.used_SLOs and abs(pol.last_objective - o2) <= 1e-7 * o2
+
+
+def test_packed_without_pairs_is_the_perf_program(highs_backend):
+    """Only single-job keys: the packed program IS MaxMinFairnessPolicyWithPerf's LP (max_min_fairness.py:53-113)."""
+    from oracle import gavel_lp as gl
+    pk = highs_backend
+    thr, sf, prio, _, _, spec, singles = instance(18, SPEC, seed=5, pair_fraction=0.0)
+    pol = pk.MaxMinFairnessPolicyWithPacking("ECOS")
+    pol.get_allocation(thr, sf, prio, spec)
+    wts = sorted(spec.keys())
+    a = np.array([[thr[s][w] for w in wts] for s in singles])
+    z, _ = gl.max_min_fairness_perf(a, np.array([sf[s] for s in singles], float),
+                                    np.array([prio[s] for s in singles]), [spec[w] for w in wts])
+    assert abs(pol.last_objective - z) <= 1e-6 * z       # all_m is float32 in the packed classes (policy.py:132)
+
+
+def test_empty_and_mismatched_scale_factors(highs_backend):
+    pk = highs_backend
+    assert pk.MaxMinFairnessPolicyWithPacking("ECOS").get_allocation({}, {}, {}, SPEC) is None
+    thr, sf, prio, _, _, spec, singles = instance(4, SPEC, seed=9, pair_fraction=1.0)
+    sf = {s: (1 if i % 2 == 0 else 2) for i, s in enumerate(singles)}        # pairs (0,1), (0,3), ... mismatch
+    alloc = pk.MaxMinFairnessPolicyWithPacking("ECOS").get_allocation(thr, sf, prio, spec)
+    for c, row in alloc.items():
+        if c.is_pair() and sf[c.singletons()[0]] != sf[c.singletons()[1]]:
+            assert all(v == 0 for v in row.values())
+    z, _, _ = gp.max_min_fairness_packed(thr, sf, prio, spec)
+    # a cluster with an empty worker type
+    spec0 = dict(spec, k80=0)
+    alloc = pk.MaxMinFairnessPolicyWithPacking("ECOS").get_allocation(thr, sf, prio, spec0)
+    assert all(row["k80"] == 0 for row in alloc.values())
+
+
+# ---- the device simplex source on the host ----
+@pytest.fixture(scope="module")
+def host_simplex():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    src = os.path.join(ROOT, "tests", "native", "lp_host.cpp")
+    out = os.path.join(ROOT, "tests", "native", "liblp_host.so")
+    core = os.path.join(ROOT, "shockwave_b200", "csrc", "lp_core.cuh")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", src, "-o", out])
+    lib = C.CDLL(out)
+    lib.lp_host_solve.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
+
+    def solve(colp, rowi, val, c, b, max_iter=0):
+        val = np.atleast_2d(np.ascontiguousarray(val, float)); c = np.atleast_2d(np.ascontiguousarray(c, float))
+        b = np.atleast_2d(np.ascontiguousarray(b, float))
+        colp = np.ascontiguousarray(colp, np.int32); rowi = np.ascontiguousarray(rowi, np.int32)
+        S, n = c.shape
+        m = b.shape[1]
+        x = np.zeros((S, n)); obj = np.zeros(S); st = np.zeros(S, np.int32); stats = np.zeros((S, 4), np.int32)
+        p = lambda a: a.ctypes.data
+        for s in range(S):
+            out8 = np.zeros(8)
+            v, cc, bb = (np.ascontiguousarray(a[s]) for a in (val, c, b))
+            lib.lp_host_solve(m, n, p(colp), p(rowi), p(v), p(cc), p(bb), max_iter or 50 * (m + n) + 1000, p(x[s]), p(out8))
+            obj[s], st[s], stats[s] = out8[0], int(out8[1]), out8[2:6]
+        return x, obj, st, stats
+    return solve
+
+
+def random_lp(rng, kind):
+    import scipy.sparse as sp
+    m = int(rng.integers(2, 40)); n = int(rng.integers(2, 80))
+    A = sp.random(m, n, density=rng.uniform(0.05, 0.5), random_state=int(rng.integers(1 << 30)),
+                  data_rvs=lambda k: rng.uniform(-1, 2, k)).tocsc()
+    A.sort_indices()
+    b = rng.uniform(0.5, 5, m) if kind == 0 else rng.uniform(-2, 5, m)
+    if kind == 2:
+        b = np.round(b)            # ties in the ratio test, zero right-hand sides
+    return A, b, rng.uniform(-1, 2, n)
+
+
+def test_device_simplex_source_on_random_programs(host_simplex):
+    rng = np.random.default_rng(0)
+    seen = set()
+    for trial in range(240):
+        A, b, c = random_lp(rng, trial % 3)
+        x, obj, st, _ = host_simplex(A.indptr, A.indices, A.data, c, b)
+        r = linprog(-c, A_ub=A, b_ub=b, bounds=(0, None), method="highs")
+        if r.status == 4:
+            continue
+        assert int(st[0]) == {0: 0, 2: 1, 3: 2}[r.status], (trial, st, r.status)
+        seen.add(int(st[0]))
+        if r.status == 0:
+            assert abs(obj[0] + r.fun) <= 1e-7 * (1 + abs(r.fun))
+            assert (A @ x[0] - b).max() <= 1e-7 and x[0].min() >= -1e-9
+    assert seen == {0, 1, 2}
+
+
+def test_device_simplex_source_on_packed_programs(host_simplex, monkeypatch):
+    from shockwave_b200 import packing as pk
+    monkeypatch.setattr(pk, "_lp", host_simplex)
+    for ns, pf, ident in [(16, 1.0, False), (30, 0.5, False), (24, 1.0, True)]:
+        thr, sf, prio, t0, steps, spec, singles = instance(ns, SPEC, seed=ns, pair_fraction=pf)
+        if ident:       # every job alike: maximally degenerate max-min program (Bland's rule engages)
+            for k in thr:
+                for w in thr[k]:
+                    thr[k][w] = [0.6, 0.6] if k.is_pair() else 1.0
+            sf = {s: 1 for s in singles}
+            prio = {s: 1.0 for s in singles}
+        z, _, _ = gp.max_min_fairness_packed(thr, sf, prio, spec)
+        pol = pk.MaxMinFairnessPolicyWithPacking("ECOS")
+        _base_ok(pol.get_allocation(thr, sf, prio, spec), thr, sf, spec)
+        assert abs(pol.last_objective - z) <= 1e-9 * z
+        cum = {s: 0.0 for s in singles}
+        rho, _, _ = gp.finish_time_fairness_packed(thr, sf, prio, t0, steps, cum, spec)
+        pol = pk.FinishTimeFairnessPolicyWithPacking("ECOS")
+        pol.get_allocation(thr, sf, prio, t0, steps, spec)
+        assert abs(pol.last_objective - rho) <= 1e-6 * rho
