@@ -227,6 +227,53 @@ def max_sum_throughput_packed_slos(thr, scale_factors, cluster_spec, instance_co
     return -r.fun, r.x.reshape(P.m, P.n), used, P
 
 
+def water_filling_packed(thr, scale_factors, priority_weights, cluster_spec, **kw):
+    """MaxMinFairnessWaterFillingPolicyWithPacking.get_allocation (max_min_fairness_water_filling.py:569-718): the
+    iteration loop of oracle/gavel_waterfill.run_iterations around the two programs restated over the packed columns
+    (LP :81-189 on HiGHS, bottleneck MILP :191-305 on scipy.optimize.milp).
+    Returns (x [m, n] clipped, normalised effective throughputs, iterations, log, Packed)."""
+    from scipy.optimize import Bounds, LinearConstraint, milp
+    from oracle import gavel_waterfill as wf
+    P = Packed(thr, scale_factors, cluster_spec)
+    Ns, nv = len(P.singles), P.m * P.n
+    prop = proportional_throughputs(P.thr_single, P.N)
+    net = np.array([P.coef(i) / prop[i] for i in range(Ns)])                     # net_i(x) = net[i] . x
+    M = max(np.max(P.coef(i, with_sf=True)) / prop[i] for i in range(Ns))        # _get_M :583-602
+    A, b, bounds = P.base()
+
+    def lp(_thr, _sf, _N, _prop, lower, mult, add, so_far):
+        rows = [np.concatenate([-net[i] * mult[i], [1.0]]) for i in range(Ns)]   # c <= (net_i - so_far_i) mult_i + add_i
+        rhs = [add[i] - so_far[i] * mult[i] for i in range(Ns)]
+        rows += [np.concatenate([-net[i], [0.0]]) for i in range(Ns)]            # net_i >= lower_i
+        rhs += [-lower[i] for i in range(Ns)]
+        cost = np.zeros(nv + 1); cost[-1] = -1.0
+        r = linprog(cost, A_ub=np.vstack([np.hstack([A, np.zeros((A.shape[0], 1))]), np.array(rows)]),
+                    b_ub=np.concatenate([b, rhs]), bounds=bounds + [(None, None)], method="highs")
+        if r.status != 0:
+            return None, None
+        return r.x[:nv].reshape(P.m, P.n), float(r.x[-1])
+
+    def bottleneck(_thr, _sf, _N, _prop, lower, so_far, zmask, M_, slack=wf.SLACK, epsilon=wf.EPSILON):
+        cons = [LinearConstraint(np.hstack([A, np.zeros((A.shape[0], Ns))]), -np.inf, b)]
+        Z = np.eye(Ns)
+        cons.append(LinearConstraint(np.hstack([net, -M_ * Z]), -np.inf, so_far * slack - epsilon))
+        cons.append(LinearConstraint(np.hstack([-net, M_ * Z]), -np.inf, M_ - so_far * slack))
+        cons.append(LinearConstraint(np.hstack([net, 0 * Z]), lower, np.inf))
+        ub = np.concatenate([[np.inf if hi is None else hi for _, hi in bounds], np.where(zmask > 0, 0.0, 1.0)])
+        res = milp(np.concatenate([np.zeros(nv), -np.ones(Ns)]), constraints=cons,
+                   integrality=np.concatenate([np.zeros(nv), np.ones(Ns)]), bounds=Bounds(np.zeros(nv + Ns), ub))
+        if res.status != 0:
+            raise RuntimeError("non-optimal allocation in _get_bottleneck_jobs")
+        return np.round(res.x[nv:])
+
+    log = []
+    x, so_far, final, it = wf.run_iterations(P.singles, None, P.sf_single, P.N, prop,
+                                             {s: priority_weights[s] for s in P.singles}, M, lp=lp,
+                                             bottleneck=bottleneck, log=log, **kw)
+    eff = net @ x.ravel()
+    return np.clip(x, 0.0, 1.0), eff, it, log, P
+
+
 # ---- CPU backend for shockwave_b200/packing.py's `_lp` hook (same signature as Engine.lp_solve) ----
 def lp_backend(colp, rowi, val, c, b, max_iter=0):
     """HiGHS stand-in for swb_lp_solve: lets the product's HOST logic (LP construction, multi-section, stateful

@@ -21,7 +21,7 @@ import copy
 import numpy as np
 
 from . import policies as _pol
-from .policies import Policy
+from .policies import Policy, WaterFillingAlgorithm
 
 _SECTIONS = 16      # candidate ratios per launch of the finish-time-fairness search
 
@@ -34,6 +34,23 @@ def _lp(colp, rowi, val, c, b, max_iter=0):
 class _Columns:
     """Sparse column model of one packed program: columns (combination c, worker type w) with capacity and share
     rows (policy.py:172-193), plus per-single-job linear forms T_i(x) = sum over relevant combinations."""
+
+    @classmethod
+    def from_matrix(cls, N, a, sf):
+        """Single jobs only, float64 coefficients: the (job x worker type) programs of the *_Perf policies."""
+        C = cls.__new__(cls)
+        J, W = a.shape
+        C.job_ids = C.singles = list(range(J))
+        C.worker_types = list(range(W))
+        C.M, C.W, C.Ns = J, W, J
+        C.N = np.asarray(N, dtype=np.float64)
+        C.mem = np.stack([np.arange(J), np.full(J, -1)], axis=1)
+        C.thr = np.zeros((J, 2, W))
+        C.thr[:, 0, :] = a
+        C.sfc = np.asarray(sf, dtype=np.float64)
+        C.thr_single, C.sf_single = np.asarray(a, dtype=np.float64), C.sfc
+        C._live()
+        return C
 
     def __init__(self, d, scale_factors, cluster_spec, priority_weights=None):
         job_ids = sorted(list(d.keys()))
@@ -72,10 +89,13 @@ class _Columns:
         self.mem, self.thr, self.sfc = mem, thr.astype(np.float64), sfc
         self.thr_single = np.array([[d[s][w] for w in worker_types] for s in singles], dtype=np.float64)
         self.sf_single = np.array([scale_factors[s] for s in singles], dtype=np.float64)
+        self._live()
+
+    def _live(self):
         # live columns: effective scale factor != 0 (the reference pins the others to 0, max_min_fairness.py:396-399)
         # and a worker type with capacity (capacity 0 forces the column to 0 through the capacity row)
         live_w = np.flatnonzero(self.N > 0)
-        cc, ww = np.meshgrid(np.flatnonzero(sfc != 0), live_w, indexing="ij")
+        cc, ww = np.meshgrid(np.flatnonzero(self.sfc != 0), live_w, indexing="ij")
         self.col_c, self.col_w = cc.ravel(), ww.ravel()
         self.nv = len(self.col_c)
         self.live_w = live_w
@@ -151,6 +171,119 @@ def _max_min(C, fi, fv, fa_batch):
         raise RuntimeError(f"packed max-min program: simplex status {status.tolist()}")
     _max_min.last_stats = stats
     return x[:, :C.nv], x[:, nz]
+
+
+def _ftf_search(C, t, n, den):
+    """minimise max_i (t_i + n_i / T_i(x)) / den_i  (finish_time_fairness.py:232-246): rho is attainable iff
+    max_x min_i T_i(x) / r_i(rho) >= 1 with r_i = n_i / (rho den_i - t_i).  Every x bounds rho* from above by its own
+    ratio, every failed rho from below; 16 candidate ratios per launch.  Returns (rho, column values, launches)."""
+    fi, fv, fa = C.form()
+
+    def ratio(xv):
+        T = C.rates(xv)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return float(np.max((t + np.where(n > 0, n / T, 0.0)) / den))
+
+    lo = float(np.max(t / den))
+    xv0, _ = _max_min(C, fi, fv, fa * (den / n)[fi])
+    best_x, hi = xv0[0], ratio(xv0[0])
+    if not np.isfinite(hi):
+        return hi, None, 1
+    passes = 1
+    while hi - lo > 1e-9 * hi and passes < 16:
+        rho = lo + (hi - lo) * (np.arange(1, _SECTIONS + 1) / (_SECTIONS + 1.0))
+        r = n[None, :] / (rho[:, None] * den[None, :] - t[None, :])          # [S, Ns] needed throughputs
+        xv, z = _max_min(C, fi, fv, fa[None, :] / r[:, fi])
+        passes += 1
+        for k in range(_SECTIONS):
+            rk = ratio(xv[k])
+            if rk < hi:
+                hi, best_x = rk, xv[k]
+            if z[k] < 1.0 - 1e-9:
+                lo = max(lo, float(rho[k]))
+        lo = min(lo, hi)
+    return hi, best_x, passes
+
+
+def _mtd(C, n):
+    """min_total_duration.py:176-234.  T is attainable iff some x has T_i(x) >= n_i / T for all i  <=>
+    T >= 1 / max_x min_i T_i(x) / n_i: ONE program instead of the reference's ~14 feasibility probes; the probes are
+    then replayed on the verdicts.  Returns (T of the last feasible probe, T*, column values)."""
+    fi, fv, fa = C.form()
+    Tref = 1.0e4
+    xv, z = _max_min(C, fi, fv, fa * (Tref / n)[fi])
+    if not z[0] > 0:
+        return None, np.inf, xv[0]
+    T_star = Tref / float(z[0])
+    max_T, min_T, last_max_T, last_T = 1000000.0, 100.0, 1000000.0, None      # min_total_duration.py:206-230
+    while last_T is None:
+        while 1.05 * min_T < max_T:
+            T = (min_T + max_T) / 2.0
+            if T >= T_star * (1.0 - 1e-9):
+                last_T, max_T = T, T
+            else:
+                min_T = T
+        max_T, min_T = last_max_T * 10.0, last_max_T
+        last_max_T *= 10
+    return last_T, T_star, xv[0]
+
+
+def _max_sum(C, cvec, need):
+    """max cvec . x under the base rows and  T_i(x) >= need[i]  for the singles in `need` (a dict).
+    Returns (column values, objective, status)."""
+    fi, fv, fa = C.form()
+    br, bv, ba, bb = C.base_rows()
+    m0 = len(bb)
+    rows, cols, vals, b = [br], [bv], [ba], [bb]
+    for k, (i, nd) in enumerate(need.items()):          # -T_i(x) / need_i <= -1
+        sel = fi == i
+        rows.append(np.full(int(sel.sum()), m0 + k)); cols.append(fv[sel]); vals.append(-fa[sel] / nd)
+    b.append(-np.ones(len(need)))
+    rows, cols, vals, b = map(np.concatenate, (rows, cols, vals, b))
+    colp, rowi, order = _csc(rows, cols, None, C.nv)
+    x, obj, status, _ = _lp(colp, rowi, vals[order], cvec, b)
+    return x[0], float(obj[0]), int(status[0])
+
+
+def hetero_lp(mode, N, a, sf, t=None, n=None, den=None):
+    """policies._hetero for MORE worker types than hetero.cu's Dantzig-Wolfe master enumerates (W > 4, max-sum W > 3,
+    e.g. all six types of tacc_throughputs.json): the same programs (max_min_fairness.py:53-113,
+    finish_time_fairness.py:66-157, min_total_duration.py:55-135, max_sum_throughput.py:49-108) as general LPs on
+    swb_lp_solve.  a is J x W over worker types WITH capacity.  Returns (x [J, W], objective, rc)."""
+    a = np.asarray(a, dtype=np.float64)
+    J, W = a.shape
+    if W + 2 * J > 2048:
+        raise NotImplementedError("more than 4 worker types with capacity: the general LP path holds W + 2 J <= 2048 rows")
+    C = _Columns.from_matrix(N, a, sf)
+    back = lambda xv: C.expand(xv)
+    if mode == _pol.POL_MAXMIN:
+        fi, fv, fa = C.form()
+        xv, z = _max_min(C, fi, fv, fa)
+        return back(xv[0]), float(z[0]), 0
+    if mode == _pol.POL_FTF:
+        rho, xv, _ = _ftf_search(C, np.asarray(t, float), np.asarray(n, float), np.asarray(den, float))
+        if xv is None:
+            return np.zeros_like(a), rho, 1
+        return back(xv), rho, 0
+    if mode == _pol.POL_MTD:
+        T, _, xv = _mtd(C, np.asarray(n, float))
+        return back(xv), T, (0 if T is not None else 1)
+    if mode == _pol.POL_MAXSUM:
+        fi, fv, fa = C.form()
+        need = {}
+        if t is not None:       # SLO floors on the THROUGHPUT a * cost (policies.py: a = thr / cost, den = cost per type)
+            C2 = _Columns.from_matrix(N, a * np.asarray(den, float)[None, :], sf)
+            need = {int(i): float(v) for i, v in enumerate(np.asarray(t, float)) if v > 0}
+            cvec = np.bincount(fv, weights=fa, minlength=C.nv)
+            xv, obj, st = _max_sum(C2, cvec, need)
+        else:
+            xv, obj, st = _max_sum(C, np.bincount(fv, weights=fa, minlength=C.nv), need)
+        if st == 1:
+            return np.zeros_like(a), 0.0, 1
+        if st != 0:
+            raise RuntimeError(f"max-sum program: simplex status {st}")
+        return back(xv), obj, 0
+    raise ValueError(mode)
 
 
 class PolicyWithPacking(Policy):
@@ -229,33 +362,9 @@ class FinishTimeFairnessPolicyWithPacking(PolicyWithPacking):
         n = np.array([num_steps_remaining[s] for s in C.singles], dtype=np.float64)
         t = np.array([times_since_start[s] for s in C.singles], dtype=np.float64)
         den = np.array([self._cumulative_isolated_time[s] for s in C.singles], dtype=np.float64) + n / iso
-        fi, fv, fa = C.form()
-
-        def ratio(xv):      # the reference's objective at x (:232-246)
-            T = C.rates(xv)
-            with np.errstate(divide="ignore"):
-                return float(np.max((t + n / np.where(T > 0, T, 0.0)) / den))
-
-        # minimise max_i (t_i + n_i / T_i(x)) / den_i: rho is attainable iff max_x min_i T_i(x) / r_i(rho) >= 1 with
-        # r_i = n_i / (rho den_i - t_i).  Every x bounds rho* from above by its own ratio, every failed rho from below.
-        lo = float(np.max(t / den))
-        xv0, _ = _max_min(C, fi, fv, fa * (den / n)[fi])
-        best_x, hi = xv0[0], ratio(xv0[0])
-        if not np.isfinite(hi):
+        hi, best_x, passes = _ftf_search(C, t, n, den)
+        if best_x is None:
             raise RuntimeError("FinishTimeFairness_Packing: a job has no column with positive throughput")
-        passes = 1
-        while hi - lo > 1e-9 * hi and passes < 16:
-            rho = lo + (hi - lo) * (np.arange(1, _SECTIONS + 1) / (_SECTIONS + 1.0))
-            r = n[None, :] / (rho[:, None] * den[None, :] - t[None, :])          # [S, Ns] needed throughputs
-            xv, z = _max_min(C, fi, fv, fa[None, :] / r[:, fi])
-            passes += 1
-            for k in range(_SECTIONS):
-                rk = ratio(xv[k])
-                if rk < hi:
-                    hi, best_x = rk, xv[k]
-                if z[k] < 1.0 - 1e-9:
-                    lo = max(lo, float(rho[k]))
-            lo = min(lo, hi)
         self.last_objective, self.last_passes = hi, passes
         self._num_steps_remaining_prev_iteration = copy.copy(num_steps_remaining)
         self._isolated_throughputs_prev_iteration = {s: iso[i] for i, s in enumerate(C.singles)}
@@ -272,26 +381,11 @@ class MinTotalDurationPolicyWithPacking(PolicyWithPacking):
         if C is None or C.Ns == 0:
             return None
         n = np.array([num_steps_remaining[s] for s in C.singles], dtype=np.float64)
-        fi, fv, fa = C.form()
-        # T is attainable iff some x has T_i(x) >= n_i / T for all i  <=>  T >= 1 / max_x min_i T_i(x) / n_i: ONE
-        # program instead of the reference's ~14 feasibility probes; the probes are then replayed on the verdicts
-        Tref = 1.0e4
-        xv, z = _max_min(C, fi, fv, fa * (Tref / n)[fi])
-        if not z[0] > 0:
+        last_T, T_star, xv = _mtd(C, n)
+        if last_T is None:
             raise RuntimeError("MinTotalDuration_Packing: a job cannot make progress on this cluster")
-        T_star = Tref / float(z[0])
-        max_T, min_T, last_max_T, last_T = 1000000.0, 100.0, 1000000.0, None      # min_total_duration.py:206-230
-        while last_T is None:
-            while 1.05 * min_T < max_T:
-                T = (min_T + max_T) / 2.0
-                if T >= T_star * (1.0 - 1e-9):
-                    last_T, max_T = T, T
-                else:
-                    min_T = T
-            max_T, min_T = last_max_T * 10.0, last_max_T
-            last_max_T *= 10
         self.last_objective, self.last_T_star = last_T, T_star
-        return self._unflatten(C, C.expand(xv[0]))
+        return self._unflatten(C, C.expand(xv))
 
 
 class ThroughputNormalizedByCostSumWithPackingSLOs(PolicyWithPacking):
@@ -309,31 +403,87 @@ class ThroughputNormalizedByCostSumWithPackingSLOs(PolicyWithPacking):
             cost = np.array([instance_costs[w] for w in C.worker_types], dtype=np.float64)
         fi, fv, fa = C.form()
         cvec = np.bincount(fv, weights=fa / cost[C.col_w[fv]], minlength=C.nv)    # max_sum_throughput.py:146-163
-        br, bv, ba, bb = C.base_rows()
-        m0 = len(bb)
         need = {}
         for job_id in SLOs:                                                       # :170-183
             i = C.job_ids.index(job_id)
             assert job_id in num_steps_remaining
             need[i] = num_steps_remaining[job_id] / SLOs[job_id]
-
-        def solve(with_slos):
-            rows, cols, vals, b = [br], [bv], [ba], [bb]
-            if with_slos:
-                for k, (i, nd) in enumerate(need.items()):          # -T_i(x) / need_i <= -1
-                    sel = fi == i
-                    rows.append(np.full(int(sel.sum()), m0 + k)); cols.append(fv[sel]); vals.append(-fa[sel] / nd)
-                b.append(-np.ones(len(need)))
-            rows, cols, vals, b = map(np.concatenate, (rows, cols, vals, b))
-            colp, rowi, order = _csc(rows, cols, None, C.nv)
-            return _lp(colp, rowi, vals[order], cvec, b)
-
-        x, obj, status, _ = solve(bool(need))
-        self.used_SLOs = bool(need) and status[0] == 0
-        if need and status[0] == 1:       # "x.value is None": the reference warns and solves again without the SLO rows
+        xv, obj, status = _max_sum(C, cvec, need)
+        self.used_SLOs = bool(need) and status == 0
+        if need and status == 1:          # "x.value is None": the reference warns and solves again without the SLO rows
             print("WARNING: No allocation possible with provided SLOs!")
-            x, obj, status, _ = solve(False)
+            xv, obj, status = _max_sum(C, cvec, {})
+        if status != 0:
+            raise RuntimeError(f"ThroughputNormalizedByCostSum_PackingSLOs: simplex status {status}")
+        self.last_objective = obj
+        return self._unflatten(C, C.expand(xv))
+
+
+class MaxMinFairnessWaterFillingPolicyWithPacking(PolicyWithPacking, WaterFillingAlgorithm):
+    """max_min_fairness_water_filling.py:569-718.  The iteration loop, the entity re-weighting and the MILP's
+    infeasibility quirk are WaterFillingAlgorithm's (policies.py); the two programs of an iteration run on swb_lp_solve
+    over the (combination, worker type) columns:
+      _get_allocation (:81-189)        max c :  c / mult_i - net_i(x) <= -so_far_i (active i),  net_i >= lower_i,  c <= M
+      _get_bottleneck_jobs (:191-305)  max sum z :  net_i >= so_far_i (1 + (slack - 1) z_i),  0 <= z_i <= 1 (active i)
+    — the second is the tight relaxation of the reference's big-M MILP (z_i < 0.5 reads as "job i is a bottleneck"),
+    the same reading swb_policy_waterfill_step uses for the unpacked classes."""
+
+    def __init__(self, priority_reweighting_policies=None):
+        WaterFillingAlgorithm.__init__(self, priority_reweighting_policies)
+        PolicyWithPacking.__init__(self, solver=None)
+        self._name = "MaxMinFairnessWaterFilling_Packing"
+
+    def _waterfill_step(self, N, thr, sf, prop, lower, mult, M, slack):
+        C = self._C
+        fi, fv, fa = C.form()
+        fa = fa / prop[fi]                                  # net_i(x) = T_i(x) / prop_i
+        br, bv, ba, bb = C.base_rows()
+        m0, Ns = len(bb), C.Ns
+        active = mult > 0
+        # ---- LP: columns x (nv) and c ----
+        nc = C.nv
+        rows = np.concatenate([br, m0 + fi, m0 + np.flatnonzero(active), [m0 + Ns]])
+        cols = np.concatenate([bv, fv, np.full(int(active.sum()), nc), [nc]])
+        vals = np.concatenate([ba, -fa, 1.0 / mult[active], [1.0]])
+        b = np.concatenate([bb, -lower, [M]])               # lower_i == so_far_i for the active jobs
+        colp, rowi, order = _csc(rows, cols, None, C.nv + 1)
+        cost = np.zeros(C.nv + 1)
+        cost[nc] = 1.0
+        x, obj, status, _ = _lp(colp, rowi, vals[order], cost, b)
         if status[0] != 0:
-            raise RuntimeError(f"ThroughputNormalizedByCostSum_PackingSLOs: simplex status {int(status[0])}")
-        self.last_objective = float(obj[0])
-        return self._unflatten(C, C.expand(x[0]))
+            return None, None, None
+        xs, c = x[0, :C.nv], float(x[0, nc])
+        so_far = lower + np.where(active, c / np.where(active, mult, 1.0), 0.0)
+        # ---- bottleneck program: columns x (nv) and z_i for the active jobs ----
+        act = np.flatnonzero(active)
+        na = len(act)
+        zcol = C.nv + np.arange(na)
+        rows = np.concatenate([br, m0 + fi, m0 + act, m0 + Ns + np.arange(na)])
+        cols = np.concatenate([bv, fv, zcol, zcol])
+        vals = np.concatenate([ba, -fa, so_far[act] * (slack - 1.0), np.ones(na)])
+        b = np.concatenate([bb, -so_far, np.ones(na)])
+        colp, rowi, order = _csc(rows, cols, None, C.nv + na)
+        cost = np.zeros(C.nv + na)
+        cost[zcol] = 1.0
+        x2, _, status2, _ = _lp(colp, rowi, vals[order], cost, b)
+        z = np.zeros(Ns)
+        if status2[0] == 0:
+            z[act] = x2[0, zcol]
+        return xs, c, z
+
+    def get_allocation(self, unflattened_throughputs, scale_factors, unflattened_priority_weights, cluster_spec,
+                       entity_weights=None, entity_to_job_mapping=None, verbose=False,
+                       return_effective_throughputs=False):
+        C = self._columns(unflattened_throughputs, scale_factors, cluster_spec)
+        if C is None or C.Ns == 0:
+            return None
+        self._C = C
+        prop = _proportional(C.thr_single, C.N)                                   # :640-652
+        fi, fv, fa = C.form(with_sf=True)
+        self._M = float(np.max(fa / prop[fi]))                                    # _get_M :583-602
+        xv = self._run_get_allocation_iterations(C.singles, None, C.sf_single, C.N, prop, self._M, entity_weights,
+                                                 unflattened_priority_weights, entity_to_job_mapping, verbose)
+        x = C.expand(xv)
+        if return_effective_throughputs:
+            return C.rates(xv) / prop, C.singles
+        return self._unflatten(C, x)

@@ -11,7 +11,8 @@ The LP each policy hands to cvxpy is solved on the GPU (no CPU fallback):
     homogeneous clusters Shockwave targets: closed forms / 1-D searches;
   * swb_policy_hetero (hetero.cu) for genuinely heterogeneous *_Perf calls with up to 3 worker types that have
     capacity (k80 / p100 / v100): bisection on the scalar objective + Dantzig-Wolfe on the capacity rows.
-More than 4 live worker types (3 for max-sum) raise NotImplementedError.
+More than 4 live worker types (3 for max-sum; e.g. all six of tacc_throughputs.json) go to swb_lp_solve as general
+LPs (packing.hetero_lp; up to ~1000 jobs), and so do the *_packed policies (packing.py).
 """
 from __future__ import annotations
 
@@ -68,6 +69,13 @@ def _pooled(mode, N, coef, sf, t=None, n=None, den=None):
 
 def _hetero(mode, N, a, sf, t=None, n=None, den=None):
     """swb_policy_hetero on the live worker types: a is J x W, N has W entries > 0.  Returns (x[J,W], objective, rc)."""
+    W_ = np.shape(a)[1]
+    if W_ > 4 or (mode == POL_MAXSUM and W_ > 3):
+        # beyond the basis enumeration of hetero.cu's master: the same program as a general LP on swb_lp_solve
+        from . import packing
+        out = packing.hetero_lp(mode, N, a, sf, t=t, n=n, den=den)
+        _hetero.last_stats = (0, 0)
+        return out
     eng = _engine()
     lib = eng.lib
     if not getattr(lib, "_het_bound", False):
@@ -78,8 +86,6 @@ def _hetero(mode, N, a, sf, t=None, n=None, den=None):
     arr = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
     a, sf, t, n, den, N = arr(a), arr(sf), arr(t), arr(n), arr(den), arr(N)
     J, W = a.shape
-    if W > 4 or (mode == POL_MAXSUM and W > 3):
-        raise NotImplementedError("more than 4 worker types with capacity (3 for max-sum): not solved on the GPU in this release")
     x = np.zeros((J, W), dtype=np.float64)
     obj = C.c_double()
     stats = np.zeros(2, dtype=np.int32)
@@ -335,7 +341,9 @@ class WaterFillingAlgorithm:
             active = (~is_final) & (pw > 0.0)
             mult = np.where(active, pw * sf, 0.0)
             lower = np.where(is_final, np.array([final.get(j, 0.0) for j in job_ids]), so_far)
-            xs, c, z = _waterfill_step(N, thr, sf, prop, lower, mult, M, self.SLACK)
+            # the packing class (packing.py) substitutes its own step: general LPs over (combination, type) columns
+            step = getattr(self, "_waterfill_step", None) or _waterfill_step
+            xs, c, z = step(N, thr, sf, prop, lower, mult, M, self.SLACK)
             if xs is None:                       # "x is None" / solver exception: keep the previous iterate, stop
                 done = True
                 z = np.zeros(J)
@@ -756,6 +764,10 @@ def get_policy(policy_name, solver=None, seed=None, priority_reweighting_policie
               "finish_time_fairness_packed": "FinishTimeFairnessPolicyWithPacking",
               "min_total_duration_packed": "MinTotalDurationPolicyWithPacking",
               "max_sum_throughput_normalized_by_cost_packed_SLOs": "ThroughputNormalizedByCostSumWithPackingSLOs"}
+    if policy_name == "max_min_fairness_water_filling_packed":
+        from . import packing
+        return packing.MaxMinFairnessWaterFillingPolicyWithPacking(
+            priority_reweighting_policies=priority_reweighting_policies)
     if policy_name in packed:       # the *_packed names of utils.py:626-672 (packing.py: LPs on swb_lp_solve)
         from . import packing
         return getattr(packing, packed[policy_name])(solver=solver)

@@ -41,7 +41,8 @@ def test_lp_solve_batch_shared_pattern():
     eng = P._engine()
     rng = np.random.default_rng(1)
     m, n, S = 60, 400, 48
-    A = sp.random(m, n, density=0.05, random_state=3, data_rvs=lambda k: rng.uniform(0.1, 2, k)).tocsc()
+    A = sp.vstack([sp.random(m - 1, n, density=0.05, random_state=3, data_rvs=lambda k: rng.uniform(0.1, 2, k)),
+                   sp.csr_matrix(np.ones((1, n)))]).tocsc()       # the last row bounds every column
     A.sort_indices()
     val = A.data[None, :] * rng.uniform(0.5, 1.5, (S, A.nnz))
     c = rng.uniform(0, 1, (S, n))
@@ -124,3 +125,24 @@ def test_packing_degenerate_and_large():
     z, _, _ = gp.max_min_fairness_packed(thr, sf, prio, spec)
     pol.get_allocation(thr, sf, prio, spec)
     assert abs(pol.last_objective - z) <= 1e-8 * z
+
+
+@pytest.mark.parametrize("J,seed", [(40, 11), (300, 12)])
+def test_six_worker_types(J, seed):
+    """All six worker types of tacc_throughputs.json live: policies._hetero routes to the general LP (W > 4)."""
+    from tests.test_oracle_packed import check_six_types
+    check_six_types(P, J, seed)
+
+
+@pytest.mark.parametrize("ns,pf,seed", [(6, 1.0, 1), (10, 1.0, 2), (20, 0.4, 4), (12, 0.7, 6)])
+def test_water_filling_packed(ns, pf, seed):
+    """max_min_fairness_water_filling_packed: iteration by iteration against the reference's loop with its LP on HiGHS
+    and its bottleneck MILP on scipy.optimize.milp (same number of iterations, same water levels)."""
+    thr, sf, prio, _, _, spec, singles = instance(ns, SPEC, seed=seed, pair_fraction=pf)
+    x, eff, it, log, _ = gp.water_filling_packed(thr, sf, prio, spec)
+    pol = P.get_policy("max_min_fairness_water_filling_packed")
+    assert pol.name == "MaxMinFairnessWaterFilling_Packing"
+    e2, ids = pol.get_allocation(thr, sf, prio, spec, return_effective_throughputs=True)
+    assert ids == singles and pol.last_iterations == it
+    assert np.max(np.abs(eff - e2) / np.maximum(eff, 1e-9)) <= 1e-6
+    _base_ok(pol.get_allocation(thr, sf, prio, spec), thr, sf, spec)

@@ -241,3 +241,98 @@ def test_device_simplex_source_on_packed_programs(host_simplex, monkeypatch):
         pol = pk.FinishTimeFairnessPolicyWithPacking("ECOS")
         pol.get_allocation(thr, sf, prio, t0, steps, spec)
         assert abs(pol.last_objective - rho) <= 1e-6 * rho
+
+
+WT6 = ["k80", "k80_unconsolidated", "p100", "p100_unconsolidated", "v100", "v100_unconsolidated"]
+
+
+def six_type_instance(J, seed):
+    """All six worker types of tacc_throughputs.json with capacity: beyond hetero.cu's master (W <= 4)."""
+    rng = np.random.default_rng(seed)
+    speed = np.array([1.0, 0.8, 2.2, 1.9, 3.5, 3.0])
+    thr = {j: {w: float(rng.uniform(0.5, 20.0) * speed[k] * rng.uniform(0.6, 1.0)) for k, w in enumerate(WT6)}
+           for j in range(J)}
+    sf = {j: int(rng.choice([1, 2, 4], p=[0.7, 0.2, 0.1])) for j in range(J)}
+    prio = {j: float(rng.choice([1.0, 2.0, 5.0])) for j in range(J)}
+    t0 = {j: float(rng.uniform(0.0, 5000.0)) for j in range(J)}
+    steps = {j: float(rng.uniform(2e3, 4e5)) for j in range(J)}
+    spec = {w: int(n) for w, n in zip(WT6, [6, 3, 5, 2, 8, 4])}
+    return thr, sf, prio, t0, steps, spec
+
+
+def check_six_types(P, J, seed):
+    """Shared by the CPU test (HiGHS / host simplex behind packing._lp) and the GPU test."""
+    from oracle import gavel_backend as gb
+    from oracle import gavel_lp as gl
+    thr, sf, prio, t0, steps, spec = six_type_instance(J, seed)
+    a = np.array([[thr[j][w] for w in WT6] for j in range(J)])
+    s = np.array([sf[j] for j in range(J)], float)
+    N = np.array([spec[w] for w in WT6], float)
+
+    def mat(alloc):
+        x = np.array([[alloc[j][w] for w in WT6] for j in range(J)])
+        assert x.min() >= 0 and np.all(x.sum(axis=1) <= 1 + 1e-9) and np.all((x * s[:, None]).sum(axis=0) <= N * (1 + 1e-9))
+        return x
+    pol = P.MaxMinFairnessPolicyWithPerf(solver="ECOS")
+    mat(pol.get_allocation(thr, sf, prio, spec))
+    z, _ = gl.max_min_fairness_perf(a, s, np.array([prio[j] for j in range(J)]), N)
+    assert abs(pol.last_objective - z) <= 1e-6 * z
+    pol = P.MinTotalDurationPolicyWithPerf(solver="ECOS")
+    x = mat(pol.get_allocation(thr, sf, steps, spec))
+    n = np.array([steps[j] for j in range(J)])
+    T, _ = gl.min_total_duration_perf(a, s, n, N)
+    assert pol.last_objective == T and np.all((a * x).sum(axis=1) >= n / T * (1 - 1e-7))
+    pol = P.FinishTimeFairnessPolicyWithPerf(solver="ECOS")
+    x = mat(pol.get_allocation(thr, sf, prio, t0, steps, spec))
+    iso = gp.isolated_throughputs(a, s, N)
+    t = np.array([t0[j] for j in range(J)])
+    _, rho = gb._ftf(a, s, t, n, n / iso, N)
+    assert abs(pol.last_objective - rho) <= 1e-6 * rho
+    assert np.max((t + n / (a * x).sum(axis=1)) / (n / iso)) <= rho * (1 + 1e-6)
+    costs = {w: c for w, c in zip(WT6, [1.0, 0.9, 2.0, 1.8, 3.0, 2.7])}
+    slo = {j: steps[j] / (thr[j]["k80"] * 0.2) for j in range(0, J, 4)}
+    pol = P.ThroughputNormalizedByCostSumWithPerfSLOs(solver="ECOS")
+    x = mat(pol.get_allocation(thr, sf, spec, instance_costs=costs, SLOs=slo, num_steps_remaining=steps))
+    need = np.zeros(J)
+    for j in slo:
+        need[j] = steps[j] / slo[j]
+    cst = np.array([costs[w] for w in WT6])
+    v, _ = gl.max_sum_throughput(a, s, N, costs=cst, need=need)
+    assert v is not None and abs(pol.last_objective - v) <= 1e-6 * v
+    assert np.all((a * x).sum(axis=1) >= need * (1 - 1e-7))
+
+
+@pytest.mark.parametrize("backend", ["highs", "host_simplex"])
+def test_six_worker_types_host_logic(backend, monkeypatch, request):
+    from shockwave_b200 import packing as pk
+    from shockwave_b200 import policies as P
+    monkeypatch.setattr(pk, "_lp", gp.lp_backend if backend == "highs" else request.getfixturevalue("host_simplex"))
+    # IsolatedPolicy._alloc (finish-time fairness) is a device call too: restate it for this CPU test
+    monkeypatch.setattr(P.IsolatedPolicy, "_alloc", lambda self, thr, sf: (
+        lambda x: x / np.maximum(x.sum(axis=1), 1.0)[:, None])((np.asarray(self._num_workers, float)[None, :] / len(sf)) / sf[:, None]))
+    check_six_types(P, 40, seed=11)
+
+
+@pytest.mark.parametrize("backend", ["highs", "host_simplex"])
+def test_water_filling_packed_host_logic(backend, monkeypatch, request):
+    """The packed water-filling class: tight LP relaxation of the bottleneck MILP vs the MILP itself (scipy milp),
+    iteration by iteration, with entity re-weighting on the last instance."""
+    from shockwave_b200 import packing as pk
+    monkeypatch.setattr(pk, "_lp", gp.lp_backend if backend == "highs" else request.getfixturevalue("host_simplex"))
+    for ns, pf, seed in [(6, 1.0, 1), (10, 1.0, 2), (14, 0.5, 3), (12, 0.7, 6)]:
+        thr, sf, prio, _, _, spec, singles = instance(ns, SPEC, seed=seed, pair_fraction=pf)
+        x, eff, it, log, _ = gp.water_filling_packed(thr, sf, prio, spec)
+        pol = pk.MaxMinFairnessWaterFillingPolicyWithPacking()
+        e2, ids = pol.get_allocation(thr, sf, prio, spec, return_effective_throughputs=True)
+        assert ids == singles and pol.last_iterations == it
+        assert np.max(np.abs(eff - e2) / np.maximum(eff, 1e-9)) <= 1e-6
+        _base_ok(pol.get_allocation(thr, sf, prio, spec), thr, sf, spec)
+    ent = {"A": singles[:5], "B": singles[5:]}
+    ew = {"A": 1.0, "B": 2.0}
+    pols = {"A": "fairness", "B": "fifo"}
+    x, eff, it, log, _ = gp.water_filling_packed(thr, sf, prio, spec, entity_weights=ew,
+                                                 entity_to_job_mapping={k: list(v) for k, v in ent.items()}, policies=pols)
+    pol = pk.MaxMinFairnessWaterFillingPolicyWithPacking(priority_reweighting_policies=pols)
+    e2, _ = pol.get_allocation(thr, sf, prio, spec, entity_weights=ew,
+                               entity_to_job_mapping={k: list(v) for k, v in ent.items()}, return_effective_throughputs=True)
+    assert pol.last_iterations == it and np.max(np.abs(eff - e2) / np.maximum(eff, 1e-9)) <= 1e-6
