@@ -682,6 +682,25 @@ def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):
                 call()
             pol_ms[f"{name}_{tag}"] = (time.perf_counter() - t0) / 3 * 1e3
     out["gavel_get_allocation_ms_J2048"] = pol_ms
+
+    # ---- packing policies (space sharing): LPs over (job combination x worker type) columns on swb_lp_solve ----
+    from shockwave_b200 import packing as PK
+    from tests.packing_fixtures import instance as packed_instance
+    pk_ms = {}
+    for ns in (32, 64):
+        thr_p, sf_p, pr_p, t_p, st_p, spec_p, _ = packed_instance(ns, {"v100": 16, "p100": 12, "k80": 8}, seed=ns)
+        for name, call in (
+                ("max_min_fairness_packed", lambda: GP.get_policy("max_min_fairness_packed", "ECOS").get_allocation(
+                    thr_p, sf_p, pr_p, spec_p)),
+                ("finish_time_fairness_packed", lambda: GP.get_policy("finish_time_fairness_packed", "ECOS").get_allocation(
+                    thr_p, sf_p, pr_p, t_p, st_p, spec_p))):
+            call()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                call()
+            pk_ms[f"{name}_{ns}jobs_{len(thr_p)}combinations"] = (time.perf_counter() - t0) / 3 * 1e3
+        pk_ms[f"simplex_pivots_{ns}jobs"] = int(PK._max_min.last_stats[:, 0].max())
+    out["packed_get_allocation_ms"] = pk_ms
     return out
 
 

@@ -290,3 +290,104 @@ def lp_backend(colp, rowi, val, c, b, max_iter=0):
         if r.status == 0:
             x[s], obj[s] = r.x, -r.fun
     return x, obj, status, np.zeros((S, 4), dtype=np.int32)
+
+
+# ---- the job-TYPE formulation (max_min_fairness.py:122-316) ----
+def convert_job_type_allocation(allocation, job_id_to_job_type_key, make_pair):
+    """policy.py:195-260: job x job-type allocation -> job x job allocation (x_ij = x_i,type(j) x_j,type(i) / sum)."""
+    job_ids = sorted(allocation.keys())
+    worker_types = sorted(allocation[job_ids[0]].keys())
+    keys = sorted(set(job_id_to_job_type_key[j] for j in job_ids))
+    jt = {w: {k: {o: 0.0 for o in [None] + keys} for k in keys} for w in worker_types}
+    for w in worker_types:
+        for j in allocation:
+            k = job_id_to_job_type_key[j]
+            for o in allocation[j][w]:
+                jt[w][k][o] += allocation[j][w][o]
+    out = {}
+    for i, j in enumerate(job_ids):
+        out[j] = {}
+        k = job_id_to_job_type_key[j]
+        for w in worker_types:
+            out[j][w] = allocation[j][w][None]
+        for j2 in job_ids[i + 1:]:
+            k2 = job_id_to_job_type_key[j2]
+            merged = make_pair(j[0], j2[0])
+            out[merged] = {}
+            for w in worker_types:
+                cur = jt[w][k][k2]
+                if cur > 0.0:
+                    if k == k2:
+                        cur -= allocation[j][w][k]
+                    out[merged][w] = allocation[j][w][k2] * allocation[j2][w][k] / cur
+                else:
+                    out[merged][w] = 0.0
+    return out
+
+
+def max_min_fairness_job_types(thr, job_id_to_job_type_key, scale_factors, priority_weights, cluster_spec):
+    """MaxMinFairnessPolicyWithPacking.get_allocation_using_job_type_throughputs (max_min_fairness.py:122-316) before
+    the conversion: returns (objective, x [n, (1 + a) m], (job_ids, job_type_keys, worker_types))."""
+    job_ids = sorted(job_id_to_job_type_key.keys())
+    keys = sorted(thr.keys())
+    wts = sorted(cluster_spec.keys())
+    N = [cluster_spec[w] for w in wts]
+    members = {}
+    for i, j in enumerate(job_ids):
+        members.setdefault(job_id_to_job_type_key[j], []).append(i)
+    n, a, m = len(job_ids), len(keys), len(wts)
+    nv1 = 1 + a
+    nx = n * nv1 * m
+    idx = lambda i, k, j: i * nv1 * m + k * nv1 + j
+    sf = np.array([scale_factors[j] for j in job_ids], dtype=float)
+    flat = np.zeros((a, nv1 * m), dtype=np.float32)
+    for i, key in enumerate(keys):
+        for k, w in enumerate(wts):
+            for j, other in enumerate([None] + keys):
+                flat[i, k * nv1 + j] = 0.0 if (j > 0 and other[1] != key[1]) else thr[key][w][other]
+    A_ub, b_ub, A_eq, b_eq = [], [], [], []
+    for i in range(n):                                  # sum of allocation values of a job <= 1
+        r = np.zeros(nx); r[i * nv1 * m:(i + 1) * nv1 * m] = 1.0
+        A_ub.append(r); b_ub.append(1.0)
+    for k in range(m):                                  # capacity per worker type, pairs counted half
+        r = np.zeros(nx)
+        for i in range(n):
+            for j in range(nv1):
+                r[idx(i, k, j)] = sf[i] * (1.0 if j == 0 else 0.5)
+        A_ub.append(r); b_ub.append(N[k])
+    for i, k0 in enumerate(keys):                       # type a with type b == type b with type a
+        for j, k1 in enumerate(keys):
+            if j <= i or k0[1] != k1[1]:
+                continue
+            for k in range(m):
+                r = np.zeros(nx)
+                for ji in members.get(k0, []):
+                    r[idx(ji, k, 1 + j)] += 1.0
+                for ji in members.get(k1, []):
+                    r[idx(ji, k, 1 + i)] -= 1.0
+                A_eq.append(r); b_eq.append(0.0)
+    for i, key in enumerate(keys):                      # i-A variables of the jobs of type A all equal
+        for k in range(m):
+            mem = members.get(key, [])
+            for ja, jb in zip(mem[:-1], mem[1:]):
+                r = np.zeros(nx); r[idx(ja, k, 1 + i)] = 1.0; r[idx(jb, k, 1 + i)] = -1.0
+                A_eq.append(r); b_eq.append(0.0)
+    alone = np.array([[thr[job_id_to_job_type_key[j]][w][None] for w in wts] for j in job_ids], dtype=float)
+    prop = proportional_throughputs(alone, N)
+    coef = np.zeros((n, nx))
+    ub = np.full(nx, np.inf)
+    for i, j in enumerate(job_ids):
+        key = job_id_to_job_type_key[j]
+        ti = keys.index(key)
+        if len(members[key]) == 1:
+            for k in range(m):
+                ub[idx(i, k, 1 + ti)] = 0.0
+        coef[i, i * nv1 * m:(i + 1) * nv1 * m] = flat[ti] * sf[i] / (priority_weights[j] * prop[i])
+    Az = np.hstack([-coef, np.ones((n, 1))])
+    pad = lambda M_: np.hstack([np.asarray(M_).reshape(-1, nx), np.zeros((len(M_), 1))])
+    cost = np.zeros(nx + 1); cost[-1] = -1.0
+    r = linprog(cost, A_ub=np.vstack([pad(A_ub), Az]), b_ub=np.concatenate([b_ub, np.zeros(n)]),
+                A_eq=pad(A_eq) if A_eq else None, b_eq=b_eq if A_eq else None,
+                bounds=[(0.0, u if np.isfinite(u) else None) for u in ub] + [(None, None)], method="highs")
+    assert r.status == 0, r.message
+    return -r.fun, r.x[:nx].reshape(n, nv1 * m), (job_ids, keys, wts)

@@ -336,6 +336,145 @@ class MaxMinFairnessPolicyWithPacking(PolicyWithPacking):
         return self._unflatten(C, C.expand(xv[0]))
 
 
+    def get_allocation_using_job_type_throughputs(self, unflattened_throughputs, job_id_to_job_type_key,
+                                                  scale_factors, unflattened_priority_weights, cluster_spec):
+        """max_min_fairness.py:122-316: the job x JOB-TYPE formulation (O(n a) instead of O(n^2) variables).
+        `unflattened_throughputs[type][worker_type][other_type or None]`, job types are (name, scale_factor) keys.
+        The reference's equality rows are folded into the columns: the "i paired with its own type" variables of one
+        type are ONE column (the reference constrains them all equal, :256-271), variables the reference pins to 0
+        (types with a single job, :295-298) or whose throughput it zeroes (other scale factor, :171-172) are dropped;
+        "a with b == b with a" (:226-254) stays as a pair of inequality rows."""
+        job_ids = sorted(job_id_to_job_type_key.keys())
+        if len(job_ids) == 0:
+            return None
+        keys = sorted(unflattened_throughputs.keys())
+        wts = sorted(cluster_spec.keys())
+        N = np.array([cluster_spec[w] for w in wts], dtype=np.float64)
+        n, a = len(job_ids), len(keys)
+        kidx = {k: i for i, k in enumerate(keys)}
+        tof = np.array([kidx[job_id_to_job_type_key[j]] for j in job_ids])          # type of job i
+        members = [np.flatnonzero(tof == A) for A in range(a)]
+        sf = np.array([scale_factors[j] for j in job_ids], dtype=np.float64)
+        pw = np.array([unflattened_priority_weights[j] for j in job_ids], dtype=np.float64)
+        flat = np.zeros((a, len(wts), 1 + a), dtype=np.float32)                     # :165-180, float32 like the reference
+        for A, key in enumerate(keys):
+            for k, w in enumerate(wts):
+                for j, other in enumerate([None] + keys):
+                    flat[A, k, j] = 0.0 if (j > 0 and other[1] != key[1]) else unflattened_throughputs[key][w][other]
+        flat = flat.astype(np.float64)
+        alone = np.array([[unflattened_throughputs[keys[A]][w][None] for w in wts] for A in range(a)], dtype=np.float64)
+        prop = _proportional(alone[tof], N)                                         # :273-284 (float64, not all_m's float32)
+        scale = sf / (pw * prop)                                                    # :286-301
+        live = np.flatnonzero(N > 0)
+        Wl = len(live)
+        # ---- columns: (kind, i or A, k, B) ----
+        cols = []            # tuples (kind, owner, k, other): kind 0 isolated, 1 cross (job i with type B), 2 same (type A)
+        for i in range(n):
+            for k in live:
+                cols.append((0, i, k, -1))
+        for i in range(n):
+            A = tof[i]
+            for B in range(a):
+                if B != A and keys[B][1] == keys[A][1]:
+                    for k in live:
+                        cols.append((1, i, k, B))
+        for A in range(a):
+            if len(members[A]) >= 2:
+                for k in live:
+                    cols.append((2, A, k, A))
+        nv = len(cols)
+        wrow = {int(k): r for r, k in enumerate(live)}
+        R_cap, R_share, R_epi = 0, Wl, Wl + n
+        rows, cidx, vals = [], [], []
+
+        def put(r, v, x):
+            rows.append(r); cidx.append(v); vals.append(x)
+        pair_rows = {}
+        R_eq = Wl + 2 * n
+        for A in range(a):
+            for B in range(A + 1, a):
+                if keys[A][1] == keys[B][1]:
+                    for k in live:
+                        pair_rows[(A, B, int(k))] = R_eq
+                        R_eq += 2
+        for v, (kind, o, k, B) in enumerate(cols):
+            if kind == 0:
+                put(R_cap + wrow[int(k)], v, sf[o]); put(R_share + o, v, 1.0)
+                put(R_epi + o, v, -flat[tof[o], k, 0] * scale[o])
+            elif kind == 1:
+                A = tof[o]
+                put(R_cap + wrow[int(k)], v, 0.5 * sf[o]); put(R_share + o, v, 1.0)
+                put(R_epi + o, v, -flat[A, k, 1 + B] * scale[o])
+                r = pair_rows[(min(A, B), max(A, B), int(k))]
+                sgn = 1.0 if A < B else -1.0
+                put(r, v, sgn); put(r + 1, v, -sgn)
+            else:
+                put(R_cap + wrow[int(k)], v, 0.5 * sf[members[o]].sum())
+                for i in members[o]:
+                    put(R_share + i, v, 1.0)
+                    put(R_epi + i, v, -flat[o, k, 1 + o] * scale[i])
+        for i in range(n):
+            put(R_epi + i, nv, 1.0)
+        m = R_eq
+        b = np.zeros(m)
+        b[:Wl] = N[live]
+        b[R_share:R_share + n] = 1.0
+        rows, cidx, vals = np.array(rows), np.array(cidx), np.array(vals)
+        keep = vals != 0.0
+        colp, rowi, order = _csc(rows[keep], cidx[keep], None, nv + 1)
+        cost = np.zeros(nv + 1)
+        cost[nv] = 1.0
+        x, obj, status, stats = _lp(colp, rowi, vals[keep][order], cost, b)
+        if status[0] != 0:
+            raise RuntimeError(f"MaxMinFairness_Packing (job types): simplex status {int(status[0])}")
+        self.last_objective = float(obj[0])
+        xv = np.clip(x[0, :nv], 0.0, 1.0)
+        # ---- back to the reference's nested dict, then policy.py:195-260 ----
+        alloc = {j: {w: {o: 0.0 for o in [None] + keys} for w in wts} for j in job_ids}
+        for v, (kind, o, k, B) in enumerate(cols):
+            if kind == 0:
+                alloc[job_ids[o]][wts[k]][None] = float(xv[v])
+            elif kind == 1:
+                alloc[job_ids[o]][wts[k]][keys[B]] = float(xv[v])
+            else:
+                for i in members[o]:
+                    alloc[job_ids[i]][wts[k]][keys[o]] = float(xv[v])
+        self.last_job_type_allocation = alloc
+        return self.convert_job_type_allocation(alloc, job_id_to_job_type_key)
+
+    @staticmethod
+    def convert_job_type_allocation(allocation, job_id_to_job_type_key):
+        """policy.py:195-260: x_{i,j} = x_{i,type(j)} x_{j,type(i)} / sum_k x_{k,type(j)} over the jobs k of type(i)."""
+        job_ids = sorted(allocation.keys())
+        wts = sorted(allocation[job_ids[0]].keys())
+        keys = sorted(set(job_id_to_job_type_key[j] for j in job_ids))
+        make_pair = type(job_ids[0])
+        tot = {w: {k: {o: 0.0 for o in keys} for k in keys} for w in wts}
+        for j in job_ids:
+            k = job_id_to_job_type_key[j]
+            for w in wts:
+                row = allocation[j][w]
+                for o in keys:
+                    tot[w][k][o] += row.get(o, 0.0)
+        out = {}
+        for i, j in enumerate(job_ids):
+            k = job_id_to_job_type_key[j]
+            out[j] = {w: allocation[j][w][None] for w in wts}
+            for j2 in job_ids[i + 1:]:
+                k2 = job_id_to_job_type_key[j2]
+                d = {}
+                for w in wts:
+                    cur = tot[w][k][k2]
+                    if cur > 0.0:
+                        if k == k2:
+                            cur -= allocation[j][w][k]
+                        d[w] = allocation[j][w][k2] * allocation[j2][w][k] / cur
+                    else:
+                        d[w] = 0.0
+                out[make_pair(j[0], j2[0])] = d
+        return out
+
+
 class FinishTimeFairnessPolicyWithPacking(PolicyWithPacking):
     def __init__(self, solver):
         PolicyWithPacking.__init__(self, solver)

@@ -72,3 +72,29 @@ def instance(ns, spec, seed, pair_fraction=1.0, make_id=JobId):
     t0 = {s: float(rng.uniform(0.0, 5000.0)) for s in singles}
     steps = {s: float(rng.uniform(2e3, 4e5)) for s in singles}
     return thr, sf, prio, t0, steps, dict(spec), singles
+
+
+def job_type_instance(n, ntypes, spec, seed):
+    """n jobs of `ntypes` job types (name, scale_factor); throughputs[type][worker_type][other type or None] as the
+    reference's job-type formulation takes them (max_min_fairness.py:122-180)."""
+    rng = np.random.default_rng(seed)
+    speed = {"k80": 1.0, "p100": 2.2, "v100": 3.5}
+    keys = [(f"model{t}", int(rng.choice([1, 1, 2]))) for t in range(ntypes)]
+    base = rng.uniform(0.5, 20.0, ntypes)
+    thr = {}
+    slow = rng.uniform(0.35, 0.95, (ntypes, ntypes))
+    for a, ka in enumerate(keys):
+        thr[ka] = {}
+        for w in spec:
+            row = {None: float(base[a] * speed.get(w, 1.5))}
+            for b, kb in enumerate(keys):
+                row[kb] = float(base[a] * speed.get(w, 1.5) * slow[a, b])
+            thr[ka][w] = row
+    job_ids = [JobId(i, None) for i in range(n)]
+    tof = list(rng.integers(0, ntypes, n))
+    for t in range(min(ntypes, n)):            # every type present once at least, one type possibly a singleton
+        tof[t] = t
+    j2k = {j: keys[t] for j, t in zip(job_ids, tof)}
+    sf = {j: j2k[j][1] for j in job_ids}
+    prio = {j: float(rng.choice([1.0, 2.0])) for j in job_ids}
+    return thr, j2k, sf, prio

@@ -146,3 +146,24 @@ def test_water_filling_packed(ns, pf, seed):
     assert ids == singles and pol.last_iterations == it
     assert np.max(np.abs(eff - e2) / np.maximum(eff, 1e-9)) <= 1e-6
     _base_ok(pol.get_allocation(thr, sf, prio, spec), thr, sf, spec)
+
+
+@pytest.mark.parametrize("n,nt,seed", [(6, 2, 1), (30, 5, 3), (120, 8, 5)])
+def test_job_type_formulation(n, nt, seed):
+    """max_min_fairness.py:122-316 (job x job-type columns) on swb_lp_solve vs the HiGHS restatement."""
+    from tests.packing_fixtures import JobId, job_type_instance
+    thr, j2k, sf, prio = job_type_instance(n, nt, SPEC, seed)
+    z, _, (job_ids, keys, wts) = gp.max_min_fairness_job_types(thr, j2k, sf, prio, SPEC)
+    pol = pk.MaxMinFairnessPolicyWithPacking("ECOS")
+    out = pol.get_allocation_using_job_type_throughputs(thr, j2k, sf, prio, SPEC)
+    assert abs(pol.last_objective - z) <= 1e-7 * max(1.0, abs(z))
+    al = pol.last_job_type_allocation
+    for w in wts:
+        used = sum(sf[j] * (al[j][w][None] + 0.5 * sum(al[j][w][o] for o in keys)) for j in job_ids)
+        assert used <= SPEC[w] + 1e-6
+    ref = gp.convert_job_type_allocation(al, j2k, JobId)
+    byrepr = {repr(k): v for k, v in out.items()}
+    assert set(map(repr, ref)) == set(byrepr)
+    for k, row in ref.items():
+        for w in wts:
+            assert abs(row[w] - byrepr[repr(k)][w]) <= 1e-12

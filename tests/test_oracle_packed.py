@@ -336,3 +336,75 @@ def test_water_filling_packed_host_logic(backend, monkeypatch, request):
     e2, _ = pol.get_allocation(thr, sf, prio, spec, entity_weights=ew,
                                entity_to_job_mapping={k: list(v) for k, v in ent.items()}, return_effective_throughputs=True)
     assert pol.last_iterations == it and np.max(np.abs(eff - e2) / np.maximum(eff, 1e-9)) <= 1e-6
+
+
+# ---- the job-TYPE formulation (max_min_fairness.py:122-316 + policy.py:195-260) ----
+@pytest.mark.parametrize("backend", ["highs", "host_simplex"])
+def test_job_type_formulation_host_logic(backend, monkeypatch, request):
+    from shockwave_b200 import packing as pk
+    from tests.packing_fixtures import job_type_instance
+    monkeypatch.setattr(pk, "_lp", gp.lp_backend if backend == "highs" else request.getfixturevalue("host_simplex"))
+    for n, nt, seed in [(6, 2, 1), (12, 3, 2), (30, 5, 3), (9, 9, 4)]:
+        thr, j2k, sf, prio = job_type_instance(n, nt, SPEC, seed)
+        z, x_or, (job_ids, keys, wts) = gp.max_min_fairness_job_types(thr, j2k, sf, prio, SPEC)
+        pol = pk.MaxMinFairnessPolicyWithPacking("ECOS")
+        out = pol.get_allocation_using_job_type_throughputs(thr, j2k, sf, prio, SPEC)
+        assert abs(pol.last_objective - z) <= 1e-7 * max(1.0, abs(z)), (n, nt, pol.last_objective, z)
+        # the job x job-type point satisfies the reference's rows
+        al = pol.last_job_type_allocation
+        for j in job_ids:
+            assert sum(al[j][w][o] for w in wts for o in [None] + keys) <= 1 + 1e-7
+        for w in wts:
+            used = sum(sf[j] * (al[j][w][None] + 0.5 * sum(al[j][w][o] for o in keys)) for j in job_ids)
+            assert used <= SPEC[w] + 1e-6
+            for a_i, ka in enumerate(keys):
+                mem_a = [j for j in job_ids if j2k[j] == ka]
+                vals = [al[j][w][ka] for j in mem_a]
+                assert max(vals) - min(vals) <= 1e-9                      # i-A variables of type A all equal
+                for kb in keys[a_i + 1:]:
+                    if kb[1] != ka[1]:
+                        continue
+                    mem_b = [j for j in job_ids if j2k[j] == kb]
+                    assert abs(sum(al[j][w][kb] for j in mem_a) - sum(al[j][w][ka] for j in mem_b)) <= 1e-7
+        # conversion: the oracle's restatement of policy.py:195-260 on the same job-type point
+        ref = gp.convert_job_type_allocation(al, j2k, JobId)
+        assert set(map(repr, ref)) == set(map(repr, out))
+        byrepr = {repr(k): v for k, v in out.items()}
+        for k, row in ref.items():
+            for w in wts:
+                assert abs(row[w] - byrepr[repr(k)][w]) <= 1e-12
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="staged reference not present")
+def test_job_type_conversion_pinned_on_reference():
+    """oracle convert_job_type_allocation == the reference's Policy.convert_job_type_allocation (policy.py:195-260)
+    on a random job-type point, with the reference's own JobIdPair."""
+    from tests.packing_fixtures import job_type_instance
+    pol_dir = os.path.join(ref_harness.REF, "policies")
+    saved = {k: sys.modules.get(k) for k in ("cvxpy", "policy", "job_id_pair")}
+    sys.modules["cvxpy"] = types.ModuleType("cvxpy")
+    sys.path[:0] = [pol_dir, ref_harness.REF]
+    try:
+        for k in ("policy", "job_id_pair"):
+            sys.modules.pop(k, None)
+        ref_policy = importlib.import_module("policy")
+        ref_pair = importlib.import_module("job_id_pair").JobIdPair
+        rng = np.random.default_rng(5)
+        for n, nt, seed in [(10, 3, 7), (7, 2, 8)]:
+            thr, j2k, sf, prio = job_type_instance(n, nt, SPEC, seed)
+            j2k = {ref_pair(j[0], None): k for j, k in j2k.items()}
+            keys = sorted(thr.keys())
+            al = {j: {w: {o: float(rng.uniform(0, 0.2)) for o in [None] + keys} for w in sorted(SPEC)} for j in j2k}
+            want = ref_policy.PolicyWithPacking().convert_job_type_allocation(al, j2k)
+            got = gp.convert_job_type_allocation(al, j2k, lambda a, b: ref_pair(a, b))
+            assert set(want.keys()) == set(got.keys())
+            for k in want:
+                for w in want[k]:
+                    assert abs(want[k][w] - got[k][w]) <= 1e-15
+    finally:
+        sys.path[:] = [p for p in sys.path if p not in (pol_dir, ref_harness.REF)]
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
