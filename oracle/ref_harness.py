@@ -115,8 +115,9 @@ def import_reference(dst, shockwave_scheduler_cls=None):
 def simulate(policy_name, shockwave_scheduler_cls=None, policy_obj=None,
              config="configurations/tacc_32gpus.json", cluster="32:0:0", trace=CANONICAL_TRACE,
              throughputs="tacc_throughputs.json", time_per_iteration=120, seed=0, scratch=None,
-             max_rounds=None, scheduler_mixin=None):
-    """Mirror of simulate_scheduler_with_trace.py:main for one policy.  Returns the result dict."""
+             max_rounds=None, scheduler_mixin=None, extract=None):
+    """Mirror of simulate_scheduler_with_trace.py:main for one policy.  Returns the result dict (+ `extra` =
+    extract(scheduler, jobs, arrival_times) when a callback is given: internal records for the simulator pins)."""
     dst = prepare_tree(scratch, trace)
     cwd = os.getcwd()
     os.chdir(dst)
@@ -156,6 +157,8 @@ def simulate(policy_name, shockwave_scheduler_cls=None, policy_obj=None,
         out = dict(makespan=makespan, avg_jct=avg_jct, jct_list=jct_list, cluster_util=util,
                    finish_time_fairness_list=ftf_list,
                    per_round_schedule=sched.get_per_round_schedule())
+        if extract is not None:
+            out["extra"] = extract(sched, jobs, arrival_times)
         sched.shutdown()
         return out
     finally:
