@@ -372,6 +372,62 @@ typedef struct swb_market_args {
 } swb_market_args;
 int swb_market_pgd(swb_ctx *ctx, const swb_market_args *a);
 
+/* ---- simulator round loop on the device ---------------------------------------- *
+ * The round loop of `Scheduler.simulate()` (scheduler/scheduler.py:1878-2250: jump to the next event, book the progress
+ * of the jobs that ran, retire finished jobs, admit arrivals) with the pieces of `_get_job_steps_and_finish_times`
+ * (:1467-1512), `_get_num_steps` (:1425-1465), `_done_callback` (:4341-4700), `_update_throughput` (:549-571),
+ * `_remove_job` (:808-830) and `_update_shockwave_scheduler` (:2270-2342) that act on STATIC jobs of a trace on one
+ * worker type — for S what-if scenarios of the same trace at once, one CTA per scenario, state resident in HBM.
+ * The policy stays outside: every step takes the jobs chosen for the round (chosen[S][J], 1 = run) — from
+ * ShockwaveScheduler.round_schedule(), a Gavel policy + swb_gavel_round, or a recorded schedule (swb_sim_replay runs
+ * ALL rounds in one launch, no host in the loop).  Arithmetic = the reference's, in its order (IEEE double / int64):
+ * completion times, makespan and measured throughputs are bit-identical to the reference loop on the same schedule
+ * (tests/test_oracle_sim_loop.py, tests/test_gpu_sim.py).  Not covered (rejected with SWB_ERR_ARG / reported in err):
+ * accordion / gns batch-size rescaling (`_simulate_accordion`, `_simulate_gns`, `_scale_bs_and_iters`), job pairs,
+ * several worker types, micro-task failures. */
+typedef struct swb_sim swb_sim;
+typedef struct swb_sim_trace {
+  int32_t J;
+  int32_t reserved;
+  const double *arrival;          /* [J] non-decreasing (scheduler.py:1842-1843) */
+  const int64_t *total_steps;     /* [J] job.total_steps */
+  const int32_t *scale_factor;    /* [J] gang width */
+  const double *throughput;       /* [J] steps/s of the job on the worker type (oracle throughputs, "null" co-location) */
+  const double *duration;         /* [J] job.duration (over-deadline rule: run time > int(1.5 duration)) */
+  const int32_t *batch_size;      /* [J] */
+  const int64_t *dataset_len;     /* [J] samples per epoch (scheduler.py:73-81 dataset_size_dict) */
+  const int32_t *adaptation_mode; /* [J] or NULL: 0 = static; anything else is rejected */
+} swb_sim_trace;
+typedef struct swb_sim_scn {      /* per scenario, after a step */
+  double now;                     /* Scheduler._current_timestamp; at the end of the run: the makespan */
+  double round_start, round_end;  /* current_round_start_time / _end_time (NaN = None) */
+  int32_t rounds;                 /* completed rounds (_num_completed_rounds) */
+  int32_t remaining;              /* jobs of the trace not completed yet */
+  int32_t n_active;               /* live jobs (len(self._jobs)) */
+  int32_t done;                   /* 1: the reference's loop has left (all jobs completed, or no live job) */
+  int32_t err;                    /* bit 0: chosen gangs exceed ngpus; bit 1: nothing running and no arrival left
+                                     (the reference raises); bit 2: micro-task failure branch */
+  int32_t reserved;
+} swb_sim_scn;
+int swb_sim_create(int32_t device, const swb_sim_trace *trace, int32_t S, int32_t ngpus, double time_per_iteration,
+                   double round_duration, swb_sim **out);
+void swb_sim_destroy(swb_sim *sim);
+/* iteration 0: timestamp = first arrival, admit the jobs that have arrived.  status[S][J] (may be NULL): 0 queued,
+ * 1 live, 2 completed. */
+int swb_sim_begin(swb_sim *sim, swb_sim_scn *scn, uint8_t *status);
+/* run one round with chosen[S][J] (host) and advance to the next decision point.  Outputs (host, any may be NULL):
+ * scn[S]; status[S][J]; epoch[S][J] = epoch progress of the jobs that ran (-1: the job completed; untouched otherwise);
+ * tl_ns[S][J], tl_end[S][J] = measured-samples sum and last measured round of the throughput timeline
+ * (JobMetaData.py:235-249) — what ShockwaveScheduler's forecast takes per job. */
+int swb_sim_step(swb_sim *sim, const uint8_t *chosen, swb_sim_scn *scn, uint8_t *status, int32_t *epoch, double *tl_ns,
+                 int32_t *tl_end);
+/* begin + R rounds in ONE launch from a known schedule: schedule[R][J] shared by the scenarios (per_scenario = 0) or
+ * schedule[R][S][J]; scenarios that finish earlier ignore the rest. */
+int swb_sim_replay(swb_sim *sim, const uint8_t *schedule, int32_t R, int32_t per_scenario, swb_sim_scn *scn);
+/* per-job results [S][J] (host, any may be NULL): completion time - arrival (NaN: not completed), steps run, cumulative
+ * run time, throughput measured in the job's latest round. */
+int swb_sim_results(swb_sim *sim, double *jct, int64_t *steps_run, double *run_time, double *measured_throughput);
+
 /* Device time (CUDA events on the context's stream) of the two kernels of the latest solve pass and
  * the number of solve+place passes that call took (1 + packing-feedback re-solves). */
 int swb_last_timings(swb_ctx *ctx, double *ms_solve, double *ms_place, int32_t *passes);

@@ -109,6 +109,7 @@ extern "C" {
 void swb_destroy(swb_ctx *c);
 int swb_version(void) { return 101; }
 const char *swb_last_error(void) { return g_err.c_str(); }
+int swb_set_error(int code, const char *msg) { return fail(code, msg ? msg : ""); }
 
 int swb_create(swb_ctx **out, int device) {
   if (!out) return fail(SWB_ERR_ARG, "swb_create: out is null");

@@ -1,0 +1,243 @@
+// swb_sim_*: the reference simulator's round loop for S what-if scenarios of one static trace, on the device
+// (sim_core.cuh).  One CTA per scenario; a launch runs R rounds back to back (R = 1 when a policy on the
+// host / another kernel chooses the jobs of every round, R = all rounds when the schedule is known: replay).
+#include <math.h>
+#include <new>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "swb_internal.h"
+#include "sim_core.cuh"
+
+#define SIM_THREADS 256
+
+namespace swb {
+
+struct SimLaunch {
+  sim::Trace T;
+  sim::State X;            // [S][J] bases
+  sim::Scn *scn;           // [S]
+  const unsigned char *chosen;
+  long long stride_r, stride_s;   // chosen[r * stride_r + s * stride_s + j]
+  int R, begin, ngpus;
+  double tpi, grd;
+};
+
+__global__ void __launch_bounds__(SIM_THREADS) sim_kernel(SimLaunch L) {
+  __shared__ double sd[SIM_THREADS];
+  __shared__ long long si[SIM_THREADS];
+  const size_t o = (size_t)blockIdx.x * L.T.J;
+  sim::State X = L.X;
+  X.status += o; X.ranprev += o; X.steps_run += o; X.nsteps += o; X.run_time += o; X.latest += o; X.jct += o;
+  X.fin += o; X.tl_ns += o; X.thr_meas += o; X.tl_prev += o; X.tl_end += o; X.epoch += o;
+  sim::Shared sh{sd, si};
+  sim::Scn *scn = L.scn + blockIdx.x;
+  if (L.begin) sim::scenario_begin(L.T, X, scn, sh);
+  for (int r = 0; r < L.R; ++r)
+    sim::scenario_step(L.T, X, scn, L.chosen + (size_t)r * L.stride_r + (size_t)blockIdx.x * L.stride_s, L.ngpus, L.tpi,
+                       L.grd, sh);
+}
+
+}  // namespace swb
+
+struct swb_sim {
+  int device = 0, S = 0, J = 0, ngpus = 0, begun = 0;
+  double tpi = 0, grd = 0;
+  cudaStream_t st = nullptr;
+  void *arena = nullptr;        // trace + state, one allocation
+  unsigned char *d_chosen = nullptr;
+  size_t chosen_cap = 0;
+  unsigned char *h_pin = nullptr;   // pinned staging of the per-step outputs
+  size_t pin_cap = 0;
+  swb::sim::Trace T;
+  swb::sim::State X;
+  swb::sim::Scn *scn = nullptr;
+};
+
+#define SCK(call)                                                                                   \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) return swb_set_error(SWB_ERR_CUDA, (std::string(#call) + ": " + cudaGetErrorString(e_)).c_str()); \
+  } while (0)
+
+static size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
+
+extern "C" {
+
+void swb_sim_destroy(swb_sim *m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->st) cudaStreamSynchronize(m->st);
+  if (m->arena) cudaFree(m->arena);
+  if (m->d_chosen) cudaFree(m->d_chosen);
+  if (m->h_pin) cudaFreeHost(m->h_pin);
+  if (m->st) cudaStreamDestroy(m->st);
+  delete m;
+}
+
+int swb_sim_create(int32_t device, const swb_sim_trace *tr, int32_t S, int32_t ngpus, double time_per_iteration,
+                   double round_duration, swb_sim **out) {
+  if (!tr || !out) return swb_set_error(SWB_ERR_ARG, "swb_sim_create: null argument");
+  *out = nullptr;
+  const int J = tr->J;
+  if (J <= 0 || J > (1 << 20) || S <= 0 || S > 65535 || ngpus <= 0 || !(time_per_iteration > 0) || !(round_duration > 0))
+    return swb_set_error(SWB_ERR_ARG, "swb_sim_create: need 1 <= J <= 2^20, 1 <= S <= 65535, ngpus > 0, durations > 0");
+  if (!tr->arrival || !tr->total_steps || !tr->scale_factor || !tr->throughput || !tr->duration || !tr->batch_size ||
+      !tr->dataset_len)
+    return swb_set_error(SWB_ERR_ARG, "swb_sim_create: null trace array");
+  std::vector<double> dur15(J);
+  std::vector<long long> spe(J);
+  for (int j = 0; j < J; ++j) {
+    if (j && tr->arrival[j] < tr->arrival[j - 1])
+      return swb_set_error(SWB_ERR_ARG, "swb_sim_create: arrival times must be non-decreasing (scheduler.py:1842-1843)");
+    if (!(tr->throughput[j] > 0) || tr->total_steps[j] <= 0 || tr->scale_factor[j] <= 0 || tr->batch_size[j] <= 0 ||
+        tr->dataset_len[j] <= 0 || !(tr->duration[j] >= 0) || !(tr->arrival[j] >= 0))
+      return swb_set_error(SWB_ERR_ARG, "swb_sim_create: throughput, total_steps, scale_factor, batch_size, dataset_len "
+                                        "must be positive, duration / arrival non-negative");
+    if (tr->adaptation_mode && tr->adaptation_mode[j] != 0)
+      return swb_set_error(SWB_ERR_ARG, "swb_sim_create: only static jobs (accordion / gns batch-size rescaling is not part "
+                                        "of the device loop)");
+    dur15[j] = (double)(long long)(tr->duration[j] * 1.5);
+    spe[j] = (tr->dataset_len[j] + tr->batch_size[j] - 1) / tr->batch_size[j];
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return swb_set_error(SWB_ERR_CUDA, "swb_sim_create: no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return swb_set_error(SWB_ERR_ARG, "swb_sim_create: bad device index");
+  swb_sim *m = new (std::nothrow) swb_sim;
+  if (!m) return swb_set_error(SWB_ERR_CUDA, "swb_sim_create: out of memory");
+  m->device = device; m->S = S; m->J = J; m->ngpus = ngpus; m->tpi = time_per_iteration; m->grd = round_duration;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
+  const size_t sj = (size_t)S * J;
+  // arena: trace [J] (5 x 8 B + 2 x 4 B), state [S][J], scenario scalars [S]
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
+  const size_t o_arr = take((size_t)J * 8), o_tot = take((size_t)J * 8), o_thr = take((size_t)J * 8),
+               o_d15 = take((size_t)J * 8), o_spe = take((size_t)J * 8), o_sf = take((size_t)J * 4), o_bs = take((size_t)J * 4);
+  const size_t o_status = take(sj), o_ranprev = take(sj), o_steps = take(sj * 8), o_nsteps = take(sj * 8),
+               o_rt = take(sj * 8), o_latest = take(sj * 8), o_jct = take(sj * 8), o_fin = take(sj * 8),
+               o_tlns = take(sj * 8), o_tm = take(sj * 8), o_tlprev = take(sj * 4), o_tlend = take(sj * 4),
+               o_epoch = take(sj * 4), o_scn = take((size_t)S * sizeof(swb::sim::Scn));
+  if (e == cudaSuccess) e = cudaMalloc(&m->arena, off);
+  if (e != cudaSuccess) {
+    swb_sim_destroy(m);
+    return swb_set_error(SWB_ERR_CUDA, (std::string("swb_sim_create: ") + cudaGetErrorString(e)).c_str());
+  }
+  char *b = (char *)m->arena;
+  auto up = [&](size_t o, const void *src, size_t bytes) {
+    return cudaMemcpyAsync(b + o, src, bytes, cudaMemcpyHostToDevice, m->st);
+  };
+  e = up(o_arr, tr->arrival, (size_t)J * 8);
+  if (e == cudaSuccess) e = up(o_tot, tr->total_steps, (size_t)J * 8);
+  if (e == cudaSuccess) e = up(o_thr, tr->throughput, (size_t)J * 8);
+  if (e == cudaSuccess) e = up(o_d15, dur15.data(), (size_t)J * 8);
+  if (e == cudaSuccess) e = up(o_spe, spe.data(), (size_t)J * 8);
+  if (e == cudaSuccess) e = up(o_sf, tr->scale_factor, (size_t)J * 4);
+  if (e == cudaSuccess) e = up(o_bs, tr->batch_size, (size_t)J * 4);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(m->st);      // dur15 / spe are locals
+  if (e != cudaSuccess) {
+    swb_sim_destroy(m);
+    return swb_set_error(SWB_ERR_CUDA, (std::string("swb_sim_create: ") + cudaGetErrorString(e)).c_str());
+  }
+  m->T = swb::sim::Trace{J, (const double *)(b + o_arr), (const long long *)(b + o_tot), (const int *)(b + o_sf),
+                         (const double *)(b + o_thr), (const double *)(b + o_d15), (const int *)(b + o_bs),
+                         (const long long *)(b + o_spe)};
+  m->X.status = (unsigned char *)(b + o_status); m->X.ranprev = (unsigned char *)(b + o_ranprev);
+  m->X.steps_run = (long long *)(b + o_steps); m->X.nsteps = (long long *)(b + o_nsteps);
+  m->X.run_time = (double *)(b + o_rt); m->X.latest = (double *)(b + o_latest); m->X.jct = (double *)(b + o_jct);
+  m->X.fin = (double *)(b + o_fin); m->X.tl_ns = (double *)(b + o_tlns); m->X.thr_meas = (double *)(b + o_tm);
+  m->X.tl_prev = (int *)(b + o_tlprev); m->X.tl_end = (int *)(b + o_tlend); m->X.epoch = (int *)(b + o_epoch);
+  m->scn = (swb::sim::Scn *)(b + o_scn);
+  *out = m;
+  return 0;
+}
+
+// shared tail of begin / step / replay: launch, bring the requested per-step views back through pinned memory
+static int sim_run(swb_sim *m, const unsigned char *d_chosen, long long stride_r, long long stride_s, int R, int begin,
+                   swb_sim_scn *scn, uint8_t *status, int32_t *epoch, double *tl_ns, int32_t *tl_end) {
+  swb::SimLaunch L;
+  L.T = m->T; L.X = m->X; L.scn = m->scn; L.chosen = d_chosen; L.stride_r = stride_r; L.stride_s = stride_s;
+  L.R = R; L.begin = begin; L.ngpus = m->ngpus; L.tpi = m->tpi; L.grd = m->grd;
+  swb::sim_kernel<<<m->S, SIM_THREADS, 0, m->st>>>(L);
+  SCK(cudaGetLastError());
+  const size_t sj = (size_t)m->S * m->J;
+  const size_t need = al((size_t)m->S * sizeof(swb_sim_scn)) + al(sj) + 2 * al(sj * 4) + al(sj * 8);
+  if (need > m->pin_cap) {
+    if (m->h_pin) cudaFreeHost(m->h_pin);
+    m->h_pin = nullptr; m->pin_cap = 0;
+    SCK(cudaMallocHost((void **)&m->h_pin, need));
+    m->pin_cap = need;
+  }
+  unsigned char *p = m->h_pin;
+  unsigned char *p_scn = p; p += al((size_t)m->S * sizeof(swb_sim_scn));
+  unsigned char *p_st = p; p += al(sj);
+  unsigned char *p_ep = p; p += al(sj * 4);
+  unsigned char *p_te = p; p += al(sj * 4);
+  unsigned char *p_ns = p;
+  if (scn) SCK(cudaMemcpyAsync(p_scn, m->scn, (size_t)m->S * sizeof(swb_sim_scn), cudaMemcpyDeviceToHost, m->st));
+  if (status) SCK(cudaMemcpyAsync(p_st, m->X.status, sj, cudaMemcpyDeviceToHost, m->st));
+  if (epoch) SCK(cudaMemcpyAsync(p_ep, m->X.epoch, sj * 4, cudaMemcpyDeviceToHost, m->st));
+  if (tl_end) SCK(cudaMemcpyAsync(p_te, m->X.tl_end, sj * 4, cudaMemcpyDeviceToHost, m->st));
+  if (tl_ns) SCK(cudaMemcpyAsync(p_ns, m->X.tl_ns, sj * 8, cudaMemcpyDeviceToHost, m->st));
+  SCK(cudaStreamSynchronize(m->st));
+  if (scn) memcpy(scn, p_scn, (size_t)m->S * sizeof(swb_sim_scn));
+  if (status) memcpy(status, p_st, sj);
+  if (epoch) memcpy(epoch, p_ep, sj * 4);
+  if (tl_end) memcpy(tl_end, p_te, sj * 4);
+  if (tl_ns) memcpy(tl_ns, p_ns, sj * 8);
+  return 0;
+}
+
+static int sim_upload(swb_sim *m, const uint8_t *chosen, size_t bytes) {
+  if (bytes > m->chosen_cap) {
+    if (m->d_chosen) cudaFree(m->d_chosen);
+    m->d_chosen = nullptr; m->chosen_cap = 0;
+    SCK(cudaMalloc((void **)&m->d_chosen, bytes));
+    m->chosen_cap = bytes;
+  }
+  SCK(cudaMemcpyAsync(m->d_chosen, chosen, bytes, cudaMemcpyHostToDevice, m->st));
+  return 0;
+}
+
+int swb_sim_begin(swb_sim *m, swb_sim_scn *scn, uint8_t *status) {
+  if (!m) return swb_set_error(SWB_ERR_ARG, "swb_sim_begin: null handle");
+  SCK(cudaSetDevice(m->device));
+  m->begun = 1;
+  return sim_run(m, nullptr, 0, 0, 0, 1, scn, status, nullptr, nullptr, nullptr);
+}
+
+int swb_sim_step(swb_sim *m, const uint8_t *chosen, swb_sim_scn *scn, uint8_t *status, int32_t *epoch, double *tl_ns,
+                 int32_t *tl_end) {
+  if (!m || !chosen) return swb_set_error(SWB_ERR_ARG, "swb_sim_step: null argument");
+  if (!m->begun) return swb_set_error(SWB_ERR_STATE, "swb_sim_step: call swb_sim_begin first");
+  SCK(cudaSetDevice(m->device));
+  const size_t sj = (size_t)m->S * m->J;
+  if (int rc = sim_upload(m, chosen, sj)) return rc;
+  return sim_run(m, m->d_chosen, 0, m->J, 1, 0, scn, status, epoch, tl_ns, tl_end);
+}
+
+int swb_sim_replay(swb_sim *m, const uint8_t *schedule, int32_t R, int32_t per_scenario, swb_sim_scn *scn) {
+  if (!m || !schedule || R <= 0) return swb_set_error(SWB_ERR_ARG, "swb_sim_replay: null argument or R <= 0");
+  SCK(cudaSetDevice(m->device));
+  const size_t per_round = per_scenario ? (size_t)m->S * m->J : (size_t)m->J;
+  if (per_round * (size_t)R > ((size_t)4 << 30)) return swb_set_error(SWB_ERR_ARG, "swb_sim_replay: schedule above 4 GiB");
+  if (int rc = sim_upload(m, schedule, per_round * (size_t)R)) return rc;
+  m->begun = 1;
+  return sim_run(m, m->d_chosen, (long long)per_round, per_scenario ? m->J : 0, R, 1, scn, nullptr, nullptr, nullptr, nullptr);
+}
+
+int swb_sim_results(swb_sim *m, double *jct, int64_t *steps_run, double *run_time, double *measured_throughput) {
+  if (!m) return swb_set_error(SWB_ERR_ARG, "swb_sim_results: null handle");
+  SCK(cudaSetDevice(m->device));
+  const size_t sj = (size_t)m->S * m->J;
+  if (jct) SCK(cudaMemcpyAsync(jct, m->X.jct, sj * 8, cudaMemcpyDeviceToHost, m->st));
+  if (steps_run) SCK(cudaMemcpyAsync(steps_run, m->X.steps_run, sj * 8, cudaMemcpyDeviceToHost, m->st));
+  if (run_time) SCK(cudaMemcpyAsync(run_time, m->X.run_time, sj * 8, cudaMemcpyDeviceToHost, m->st));
+  if (measured_throughput) SCK(cudaMemcpyAsync(measured_throughput, m->X.thr_meas, sj * 8, cudaMemcpyDeviceToHost, m->st));
+  SCK(cudaStreamSynchronize(m->st));
+  return 0;
+}
+
+}  // extern "C"

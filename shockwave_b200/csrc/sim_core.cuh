@@ -1,0 +1,231 @@
+// Round loop of the reference simulator for trace-driven runs of STATIC jobs on one worker type, one CTA per what-if
+// scenario: `Scheduler.simulate()` scheduler/scheduler.py:1878-2250 with the parts of `_get_job_steps_and_finish_times`
+// :1467-1512, `_get_num_steps` :1425-1465, `_done_callback` :4341-4700, `_update_throughput` :549-571, `_remove_job`
+// :808-830 and `_update_shockwave_scheduler` :2270-2342 that act on such jobs.
+//
+// One step = "run round k with the jobs the policy chose, jump to the next event, book the progress, retire finished
+// jobs, admit arrivals": phases (C) and (A) of the reference's loop fused, so the policy's selection is the only thing
+// that happens between two steps.  All arithmetic is the reference's own, in its order, in IEEE double / int64:
+//   steps of the round     n   = min(int(throughput * time_per_iteration), total_steps - steps_run)
+//   finish time            fin = now + n / throughput
+//   next timestamp         max over the running jobs (else the next arrival)
+//   preemption overhead    a job that did NOT run in the previous round loses 20 s of a (nearly) full round:
+//                          slow = (ex - 20) / ex, ex -= 20, n = int(n * slow)               (scheduler.py:1935-1965)
+//   over-deadline rule     cumulative run time > int(1.5 * duration) retires the job       (scheduler.py:4378-4395)
+//   measured throughput    n / ex, appended to the job's timeline under the round index     (scheduler.py:549-571)
+//   timeline summary       ns += bs * (thr * round_duration * (round - previous round))      (JobMetaData.py:235-249,
+//                          kept as a running sum: what ShockwaveScheduler's forecast reads)
+//   epoch progress         floor(steps_run / ceil(dataset / batch size))                    (scheduler.py:2332-2335)
+//
+// The SAME source compiles for the host (one "thread", barriers are no-ops): tests/native/sim_host.cpp builds it with
+// g++ so the bookkeeping is checked bit for bit against the pinned restatement (oracle/sim_loop.py) without a GPU.
+// That host build is test tooling only — libswb200 has no CPU path.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define SIM_HD __host__ __device__ __forceinline__
+#else
+#define SIM_HD inline
+#endif
+
+#ifdef __CUDA_ARCH__
+#define SIM_TID ((int)threadIdx.x)
+#define SIM_NT ((int)blockDim.x)
+#define SIM_SYNC() __syncthreads()
+// no FMA contraction where the reference rounds twice (a * b, then + c)
+#define SIM_MUL(a, b) __dmul_rn((a), (b))
+#define SIM_ADD(a, b) __dadd_rn((a), (b))
+#else
+#define SIM_MUL(a, b) ((a) * (b))
+#define SIM_ADD(a, b) ((a) + (b))
+#define SIM_TID 0
+#define SIM_NT 1
+#define SIM_SYNC() ((void)0)
+#endif
+
+namespace swb {
+namespace sim {
+
+enum { ERR_CAPACITY = 1, ERR_NO_EVENT = 2, ERR_MICROTASK = 4 };
+enum { QUEUED = 0, LIVE = 1, COMPLETED = 2 };
+#define SIM_PREEMPTION_OVERHEAD 20.0
+
+struct Trace {            // [J], shared by the scenarios
+  int J;
+  const double *arrival;
+  const long long *total;
+  const int *sf;
+  const double *thr;
+  const double *dur15;    // (double) int(1.5 * duration)
+  const int *bs;
+  const long long *spe;   // steps per epoch = ceil(dataset / batch size)
+};
+
+struct Scn {              // == swb_sim_scn
+  double now, round_start, round_end;   // round_end: NaN = the reference's None
+  int rounds, remaining, n_active, done, err, pad;
+};
+
+struct State {            // [J] of ONE scenario
+  unsigned char *status, *ranprev;
+  long long *steps_run, *nsteps;
+  double *run_time, *latest, *jct, *fin, *tl_ns, *thr_meas;
+  int *tl_prev, *tl_end, *epoch;
+};
+
+struct Shared {           // SIM_NT entries each
+  double *sd;
+  long long *si;
+};
+
+SIM_HD double blk_max(double v, const Shared &sh) {
+  sh.sd[SIM_TID] = v;
+  SIM_SYNC();
+  if (SIM_TID == 0) {
+    double r = sh.sd[0];
+    for (int i = 1; i < SIM_NT; ++i) r = sh.sd[i] > r ? sh.sd[i] : r;
+    sh.sd[0] = r;
+  }
+  SIM_SYNC();
+  const double r = sh.sd[0];
+  SIM_SYNC();
+  return r;
+}
+SIM_HD double blk_min(double v, const Shared &sh) { return -blk_max(-v, sh); }
+SIM_HD long long blk_sum(long long v, const Shared &sh) {
+  sh.si[SIM_TID] = v;
+  SIM_SYNC();
+  if (SIM_TID == 0) {
+    long long r = 0;
+    for (int i = 0; i < SIM_NT; ++i) r += sh.si[i];
+    sh.si[0] = r;
+  }
+  SIM_SYNC();
+  const long long r = sh.si[0];
+  SIM_SYNC();
+  return r;
+}
+
+// admission of the jobs that have arrived by `now` (scheduler.py:2040-2052) + count of the live jobs
+SIM_HD int admit(const Trace &T, const State &X, double now, const Shared &sh) {
+  long long live = 0;
+  for (int j = SIM_TID; j < T.J; j += SIM_NT) {
+    if (X.status[j] == QUEUED && T.arrival[j] <= now) X.status[j] = LIVE;
+    live += X.status[j] == LIVE;
+  }
+  return (int)blk_sum(live, sh);
+}
+
+// iteration 0 of the loop: current timestamp = first arrival (scheduler.py:1847), nothing has run yet
+SIM_HD void scenario_begin(const Trace &T, const State &X, Scn *scn, const Shared &sh) {
+  for (int j = SIM_TID; j < T.J; j += SIM_NT) {
+    X.status[j] = QUEUED; X.ranprev[j] = 0; X.steps_run[j] = 0; X.nsteps[j] = -1;
+    X.run_time[j] = 0.0; X.latest[j] = NAN; X.jct[j] = NAN; X.fin[j] = 0.0; X.tl_ns[j] = 0.0; X.thr_meas[j] = 0.0;
+    X.tl_prev[j] = 0; X.tl_end[j] = -1; X.epoch[j] = 0;
+  }
+  SIM_SYNC();
+  const double now = T.arrival[0];
+  const int live = admit(T, X, now, sh);
+  if (SIM_TID == 0) {
+    scn->now = now; scn->round_start = 0.0; scn->round_end = NAN;      // scheduler.py:1819-1820
+    scn->rounds = 0; scn->remaining = T.J; scn->n_active = live; scn->done = live == 0; scn->err = 0; scn->pad = 0;
+  }
+  SIM_SYNC();
+}
+
+// run round `scn->rounds` with the jobs flagged in chosen[J], then the head of the next iteration
+SIM_HD void scenario_step(const Trace &T, const State &X, Scn *scn, const unsigned char *chosen, int ngpus, double tpi,
+                          double grd, const Shared &sh) {
+  Scn z = *scn;
+  SIM_SYNC();
+  if (z.done) return;
+  // ---- (C) steps and finish times of the chosen jobs (scheduler.py:2224-2236)
+  double mx = 0.0;
+  long long used = 0, nrun = 0;
+  for (int j = SIM_TID; j < T.J; j += SIM_NT) {
+    if (chosen[j] && X.status[j] == LIVE) {
+      const long long rem = T.total[j] - X.steps_run[j];
+      long long n = (long long)SIM_MUL(T.thr[j], tpi);
+      if (n > rem) n = rem;
+      const double fin = z.now + (double)n / T.thr[j];
+      X.nsteps[j] = n; X.fin[j] = fin;
+      mx = fin > mx ? fin : mx;
+      used += T.sf[j]; ++nrun;
+    } else {
+      X.nsteps[j] = -1;
+    }
+  }
+  mx = blk_max(mx, sh);
+  used = blk_sum(used, sh);
+  nrun = blk_sum(nrun, sh);
+  if (used > ngpus) z.err |= ERR_CAPACITY;
+  // ---- head of iteration c = k + 1: jump to the next event (scheduler.py:1901-1915)
+  const int c = z.rounds + 1;
+  double max_ts = 0.0;
+  if (nrun > 0 && mx > 0.0) {
+    max_ts = mx;
+    if (!isnan(z.round_end)) z.round_start = z.round_end;
+    z.round_end = mx;
+  }
+  double na = INFINITY;
+  for (int j = SIM_TID; j < T.J; j += SIM_NT)
+    if (X.status[j] == QUEUED && T.arrival[j] < na) na = T.arrival[j];
+  na = blk_min(na, sh);
+  if (max_ts > 0.0) z.now = max_ts;
+  else if (na < INFINITY) z.now = na;
+  else { z.err |= ERR_NO_EVENT; z.done = 1; }      // the reference would add None to a float here
+  // ---- completions of the round (scheduler.py:1921-2014 + _done_callback)
+  long long completed = 0, bad = 0;
+  if (!z.done)
+    for (int j = SIM_TID; j < T.J; j += SIM_NT) {
+      const long long n0 = X.nsteps[j];
+      if (n0 >= 0) {
+        double ex = X.fin[j] - z.round_start;
+        long long n = n0;
+        if (c != 1 && !X.ranprev[j]) {
+          if (ex != 0.0 && tpi - 5.0 < ex) {
+            const double slow = (ex - SIM_PREEMPTION_OVERHEAD) / ex;
+            ex -= SIM_PREEMPTION_OVERHEAD;
+            n = (long long)SIM_MUL((double)n, slow);
+          }
+        }
+        if (n <= 0 && ex <= 0.0) ++bad;             // micro-task failure branch: not restated
+        X.latest[j] = X.fin[j];
+        X.run_time[j] += ex;
+        const bool over = X.run_time[j] > T.dur15[j];
+        X.steps_run[j] += n;
+        const double tm = ex <= 0.0 ? 0.0 : (double)n / ex;
+        X.thr_meas[j] = tm;
+        X.tl_ns[j] = SIM_ADD(X.tl_ns[j], SIM_MUL((double)T.bs[j], SIM_MUL(SIM_MUL(tm, grd), (double)(c - X.tl_prev[j]))));
+        X.tl_prev[j] = c; X.tl_end[j] = c;
+        if (T.total[j] - X.steps_run[j] <= 0 || over) {
+          X.status[j] = COMPLETED;
+          X.jct[j] = X.latest[j] - T.arrival[j];
+          X.epoch[j] = -1;                          // the caller retires the job (its progress = all epochs)
+          ++completed;
+        } else {
+          X.epoch[j] = (int)(X.steps_run[j] / T.spe[j]);
+        }
+      }
+      X.ranprev[j] = n0 >= 0;
+    }
+  completed = blk_sum(completed, sh);
+  bad = blk_sum(bad, sh);
+  if (bad) z.err |= ERR_MICROTASK;
+  z.remaining -= (int)completed;
+  // ---- arrivals (scheduler.py:2040-2052), end-of-run tests (:1895-1899, :2173-2178)
+  int live = z.n_active;
+  if (!z.done) {
+    live = admit(T, X, z.now, sh);
+    z.rounds = c;
+    z.done = (z.remaining == 0 || live == 0) ? 1 : 0;
+  }
+  z.n_active = live;
+  if (SIM_TID == 0) *scn = z;
+  SIM_SYNC();
+}
+
+}  // namespace sim
+}  // namespace swb

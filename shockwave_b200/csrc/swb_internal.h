@@ -14,6 +14,9 @@
 #define SWB_MAX_REPLAN 6             /* packing-feedback re-solves (caps written by place_kernel) */
 #define SWB_MAX_J 8192              /* 13 index bits in the placement sort key */
 
+// error hook for the .cu files that carry their own extern "C" entry points (sim.cu): sets swb_last_error()
+extern "C" int swb_set_error(int code, const char *msg);
+
 namespace swb {
 
 struct SolveLaunch {

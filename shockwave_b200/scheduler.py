@@ -333,6 +333,26 @@ class ShockwaveScheduler(object):
             if self._timeline_check == "dirty":
                 self._touch_timeline(slot, jobid, job)
 
+    def schedule_progress_batch(self, jobids, epoch_progress, measured_nsamples, end_round):
+        """schedule_progress() for many jobs at once, with the throughput-timeline summaries
+        (JobMetaData.py:235-249: measured samples, last measured round) supplied by the caller instead of being read
+        from each job's `throughput_measurements` dict: the entry point of the device round loop (simulate.py /
+        swb_sim_step), which keeps those sums as running state.  Needs timeline_check="dirty" (the default)."""
+        if self._timeline_check != "dirty":
+            raise RuntimeError("schedule_progress_batch needs timeline_check='dirty'")
+        if len(jobids) == 0:
+            return
+        slots = np.fromiter(map(self._slots.__getitem__, jobids), dtype=np.int64, count=len(jobids))
+        ep = np.asarray(epoch_progress, dtype=np.int64)
+        for jid, e in zip(jobids, ep.tolist()):
+            job = self.metadata[jid]
+            job.set_epoch_progress(e)
+            job.reset_waiting_delay()
+        self._prog[slots] = ep
+        self._tl_ns[slots] = np.asarray(measured_nsamples, dtype=np.float64)
+        self._tl_end[slots] = np.asarray(end_round, dtype=self._tl_end.dtype)
+        self._tl_len[slots] = 0                      # summaries are caller-owned from now on: never re-derived from the dict
+
     def deschedule_waiting_delay(self, jobid, delay):
         if jobid in self.metadata.keys():
             self.metadata[jobid].add_waiting_delay(delay)

@@ -1,0 +1,258 @@
+"""What-if ensembles of a trace on the device: the round loop of the reference simulator
+(`Scheduler.simulate()` scheduler/scheduler.py:1878-2250) as `swb_sim_*` (csrc/sim.cu) — time advance, progress,
+preemption overhead, retirement, arrivals and the measured-throughput timeline of S scenarios per launch — with the
+policy of every scenario deciding between two steps:
+
+* `DeviceSim`            ctypes binding of swb_sim_* (begin / step / replay / results);
+* `ShockwaveEnsemble`    S `ShockwaveScheduler` what-ifs (k, lambda, rhomax, future rounds ... per scenario) of one trace
+                          in lock-step: per round ONE step launch for all scenarios + one `round_schedule()` per
+                          scenario; the per-job Python of the reference's loop (`_done_callback`, `_update_throughput`,
+                          `_update_shockwave_scheduler`: O(jobs) dict work per round) is replaced by array updates taken
+                          from the step's outputs (`ShockwaveScheduler.schedule_progress_batch`).
+
+Static jobs on one worker type only (swb_sim_create rejects anything else); dynamic-adaptation traces keep running
+through the reference's own loop with the kernels behind `round_schedule()` (tests/test_closed_loop.py).
+No CPU path: the binding raises when libswb200.so or the GPU is missing."""
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import numpy as np
+
+from . import engine as _eng
+from .scheduler import ShockwaveScheduler
+
+REOPT_ROUNDS = 8          # scheduler/scheduler.py:71
+
+
+class SimTrace(C.Structure):
+    _fields_ = [("J", C.c_int32), ("reserved", C.c_int32), ("arrival", C.c_void_p), ("total_steps", C.c_void_p),
+                ("scale_factor", C.c_void_p), ("throughput", C.c_void_p), ("duration", C.c_void_p),
+                ("batch_size", C.c_void_p), ("dataset_len", C.c_void_p), ("adaptation_mode", C.c_void_p)]
+
+
+class SimScn(C.Structure):
+    _fields_ = [("now", C.c_double), ("round_start", C.c_double), ("round_end", C.c_double), ("rounds", C.c_int32),
+                ("remaining", C.c_int32), ("n_active", C.c_int32), ("done", C.c_int32), ("err", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+SCN_DTYPE = np.dtype([("now", "f8"), ("round_start", "f8"), ("round_end", "f8"), ("rounds", "i4"), ("remaining", "i4"),
+                      ("n_active", "i4"), ("done", "i4"), ("err", "i4"), ("reserved", "i4")])
+assert SCN_DTYPE.itemsize == C.sizeof(SimScn) == 48
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    lib = _eng.load_library()
+    if not _bound:
+        lib.swb_sim_create.argtypes = [C.c_int32, C.POINTER(SimTrace), C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                       C.POINTER(C.c_void_p)]
+        lib.swb_sim_destroy.argtypes = [C.c_void_p]
+        lib.swb_sim_destroy.restype = None
+        lib.swb_sim_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.swb_sim_step.argtypes = [C.c_void_p] * 7
+        lib.swb_sim_replay.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        lib.swb_sim_results.argtypes = [C.c_void_p] * 5
+        for f in ("swb_sim_create", "swb_sim_begin", "swb_sim_step", "swb_sim_replay", "swb_sim_results"):
+            getattr(lib, f).restype = C.c_int
+        _bound = True
+    return lib
+
+
+TRACE_KEYS = (("arrival", np.float64), ("total_steps", np.int64), ("scale_factor", np.int32), ("throughput", np.float64),
+              ("duration", np.float64), ("batch_size", np.int32), ("dataset_len", np.int64))
+
+
+class DeviceSim:
+    """swb_sim_*: S scenarios of one static trace.  trace: dict of [J] sequences (TRACE_KEYS) + optional
+    `adaptation_mode` ([J] int, 0 = static)."""
+
+    def __init__(self, trace, S, ngpus, time_per_iteration=120.0, round_duration=None, device=0):
+        self._lib = _lib()
+        self._h = None
+        self.S, self.J = int(S), len(trace["arrival"])
+        self._arr = {k: np.ascontiguousarray(trace[k], dtype=dt) for k, dt in TRACE_KEYS}
+        for k, a in self._arr.items():
+            if a.shape != (self.J,):
+                raise ValueError(f"trace[{k!r}] must have one entry per job")
+        t = SimTrace()
+        t.J = self.J
+        for k, _ in TRACE_KEYS:
+            setattr(t, k, self._arr[k].ctypes.data)
+        if trace.get("adaptation_mode") is not None:
+            self._arr["adaptation_mode"] = np.ascontiguousarray(trace["adaptation_mode"], dtype=np.int32)
+            t.adaptation_mode = self._arr["adaptation_mode"].ctypes.data
+        h = C.c_void_p()
+        rd = time_per_iteration if round_duration is None else round_duration
+        self._ck(self._lib.swb_sim_create(int(device), C.byref(t), self.S, int(ngpus), float(time_per_iteration),
+                                          float(rd), C.byref(h)))
+        self._h = h
+        S, J = self.S, self.J
+        self.scn = np.zeros(S, dtype=SCN_DTYPE)
+        self.status = np.zeros((S, J), np.uint8)
+        self.epoch = np.zeros((S, J), np.int32)
+        self.tl_ns = np.zeros((S, J), np.float64)
+        self.tl_end = np.full((S, J), -1, np.int32)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"libswb200: {self._lib.swb_last_error().decode()} (code {rc})")
+
+    def begin(self):
+        self._ck(self._lib.swb_sim_begin(self._h, self.scn.ctypes.data, self.status.ctypes.data))
+        return self.scn
+
+    def step(self, chosen):
+        ch = np.ascontiguousarray(chosen, dtype=np.uint8)
+        if ch.shape != (self.S, self.J):
+            raise ValueError("chosen must be [S][J]")
+        self._ck(self._lib.swb_sim_step(self._h, ch.ctypes.data, self.scn.ctypes.data, self.status.ctypes.data,
+                                        self.epoch.ctypes.data, self.tl_ns.ctypes.data, self.tl_end.ctypes.data))
+        return self.scn
+
+    def replay(self, schedule):
+        """schedule [R][J] (shared) or [R][S][J]: begin + all rounds in one launch."""
+        sc = np.ascontiguousarray(schedule, dtype=np.uint8)
+        if sc.ndim == 2 and sc.shape[1] == self.J:
+            per = 0
+        elif sc.ndim == 3 and sc.shape[1:] == (self.S, self.J):
+            per = 1
+        else:
+            raise ValueError("schedule must be [R][J] or [R][S][J]")
+        self._ck(self._lib.swb_sim_replay(self._h, sc.ctypes.data, sc.shape[0], per, self.scn.ctypes.data))
+        return self.scn
+
+    def results(self):
+        S, J = self.S, self.J
+        jct = np.zeros((S, J)); steps = np.zeros((S, J), np.int64); rt = np.zeros((S, J)); tm = np.zeros((S, J))
+        self._ck(self._lib.swb_sim_results(self._h, jct.ctypes.data, steps.ctypes.data, rt.ctypes.data, tm.ctypes.data))
+        return dict(jct=jct, steps_run=steps, run_time=rt, measured_throughput=tm)
+
+    def close(self):
+        if self._h is not None:
+            self._lib.swb_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TraceJob:
+    """What ShockwaveScheduler reads of a job (the attribute surface of the reference's JobMetaData,
+    scheduler/JobMetaData.py:40-110), built from the reference's profile dict (utils.generate_pickle_file)."""
+
+    def __init__(self, jobid, profile, round_duration, overclock=1.0):
+        self.jobid = jobid
+        self.nworkers = int(profile.get("scale_factor", 1))
+        self.epochs = int(profile["num_epochs"])
+        self.epoch_nsamples = profile["num_samples_per_epoch"]
+        dur = [max(1.0, round(d)) for d in profile["duration_every_epoch"]]        # JobMetaData.py:112-115
+        dur = [max(1.0, d / float(overclock)) for d in dur]                         # :117-121
+        assert len(dur) == self.epochs
+        self.epoch_duration = dur
+        self.epoch_duration_preprofiled = list(dur)
+        self.bs_schedule = list(profile["bs_every_epoch"])
+        assert len(self.bs_schedule) == self.epochs
+        self.throughput_measurements = OrderedDict()    # stays empty: the summaries come from the device step
+        self.gavel_round_duration = round_duration
+        self.epoch_progress = 0
+        self.timestamp_submit = None
+        self.waiting_delay = 0
+
+    def set_epoch_progress(self, p):
+        assert 0 <= p <= self.epochs
+        self.epoch_progress = p
+
+    def add_waiting_delay(self, d):
+        self.waiting_delay += d
+
+    def reset_waiting_delay(self):
+        self.waiting_delay = 0
+
+
+class ShockwaveEnsemble:
+    """S Shockwave what-ifs of one static trace.  `scenarios`: list of dicts overriding `config` (the reference's
+    shockwave_config json keys: future_rounds, k, lambda, rhomax, log_approximation_bases, ...) per scenario."""
+
+    def __init__(self, trace, profiles, config, scenarios, ngpus, time_per_iteration=120, device=0,
+                 scheduler_kwargs=None):
+        if float(trace["arrival"][0]) != 0.0:
+            # the reference's loop iterates `_scheduled_jobs_in_current_round = None` when the first round does not
+            # start at t = 0 (scheduler.py:359, :2273-2277): its shockwave traces all start at 0
+            raise ValueError("the first job of a shockwave trace must arrive at t = 0")
+        self.trace, self.profiles, self.ngpus = trace, profiles, int(ngpus)
+        self.tpi = time_per_iteration
+        self.S, self.J = len(scenarios), len(trace["arrival"])
+        self.sim = DeviceSim(trace, self.S, ngpus, time_per_iteration, time_per_iteration, device)
+        self.scheds = []
+        for ov in scenarios:
+            cfg = dict(config)
+            cfg.update(ov)
+            bases = cfg["log_approximation_bases"]
+            origin = cfg.get("log_approximation_origin", {0.0: 1e-6})
+            origin = {float(k): v for k, v in origin.items()}
+            self.scheds.append(ShockwaveScheduler(
+                ngpus=self.ngpus, gram=cfg.get("gpu_ram", 32), init_metadata=OrderedDict(),
+                future_nrounds=cfg["future_rounds"], round_duration=time_per_iteration,
+                solver_preference=cfg.get("solver_preference", ["GUROBI"]), solver_rel_gap=cfg.get("solver_rel_gap", 1e-3),
+                solver_num_threads=cfg.get("solver_num_threads", 1), solver_timeout=cfg.get("solver_timeout", 15),
+                n_epoch_vars_max=max(cfg["future_rounds"], 30), logapx_bases=bases, logapx_origin=origin,
+                k=cfg["k"], lam=cfg["lambda"], rhomax=cfg["rhomax"], device=device, **(scheduler_kwargs or {})))
+        self.per_round_schedule = [[] for _ in range(self.S)]
+        self.resolves = np.zeros(self.S, np.int64)
+
+    def run(self, max_rounds=None):
+        sim, S, J = self.sim, self.S, self.J
+        scn = sim.begin()
+        status = sim.status.copy()
+        live_prev = np.zeros((S, J), bool)
+        chosen_prev = np.zeros((S, J), np.uint8)
+        ireopt = [0] * S
+        c = 0
+        while not scn["done"].all():
+            chosen = np.zeros((S, J), np.uint8)
+            for s in range(S):
+                if scn["done"][s]:
+                    continue
+                sch = self.scheds[s]
+                live = status[s] == 1
+                if c > 0 and scn["now"][s] != 0.0:
+                    # _update_shockwave_scheduler (scheduler.py:2270-2375) for the round that just ended
+                    ran = np.flatnonzero((chosen_prev[s] == 1) & live)
+                    sch.schedule_progress_batch(ran.tolist(), sim.epoch[s, ran], sim.tl_ns[s, ran], sim.tl_end[s, ran])
+                    sch.increment_round_ptr()
+                    ireopt[s] += 1
+                    if ireopt[s] >= REOPT_ROUNDS:
+                        ireopt[s] = 0
+                        sch.set_resolve()
+                for j in np.flatnonzero(live_prev[s] & ~live).tolist():        # _remove_job -> remove_metadata
+                    sch.remove_metadata(j)
+                for j in np.flatnonzero(live & ~live_prev[s]).tolist():        # add_job -> add_metadata
+                    job = TraceJob(j, self.profiles[j], self.tpi)
+                    job.timestamp_submit = float(scn["now"][s])                 # register_job_submit(current timestamp)
+                    sch.add_metadata(j, job)
+                live_prev[s] = live
+                was = sch.resolve
+                ids = sch.round_schedule()
+                self.resolves[s] += bool(was)
+                ids = [j for j in ids if live[j]]
+                chosen[s, ids] = 1
+                self.per_round_schedule[s].append(sorted(ids))
+            scn = sim.step(chosen)
+            if (scn["err"] != 0).any():
+                raise RuntimeError(f"swb_sim_step: error flags {scn['err'].tolist()}")
+            status = sim.status.copy()
+            chosen_prev = chosen
+            c += 1
+            if max_rounds is not None and c >= max_rounds:
+                break
+        res = sim.results()
+        res.update(makespan=scn["now"].copy(), rounds=scn["rounds"].copy(), per_round_schedule=self.per_round_schedule,
+                   resolves=self.resolves.copy(), avg_jct=np.nanmean(res["jct"], axis=1))
+        return res
