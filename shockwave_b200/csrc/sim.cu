@@ -160,7 +160,9 @@ static int sim_run(swb_sim *m, const unsigned char *d_chosen, long long stride_r
   swb::SimLaunch L;
   L.T = m->T; L.X = m->X; L.scn = m->scn; L.chosen = d_chosen; L.stride_r = stride_r; L.stride_s = stride_s;
   L.R = R; L.begin = begin; L.ngpus = m->ngpus; L.tpi = m->tpi; L.grd = m->grd;
-  swb::sim_kernel<<<m->S, SIM_THREADS, 0, m->st>>>(L);
+  // block size: a multiple of 32 (the reductions shuffle over full warps), one job per thread up to 256
+  const int threads = m->J <= 32 ? 32 : m->J <= 64 ? 64 : m->J <= 128 ? 128 : SIM_THREADS;
+  swb::sim_kernel<<<m->S, threads, 0, m->st>>>(L);
   SCK(cudaGetLastError());
   const size_t sj = (size_t)m->S * m->J;
   const size_t need = al((size_t)m->S * sizeof(swb_sim_scn)) + al(sj) + 2 * al(sj * 4) + al(sj * 8);

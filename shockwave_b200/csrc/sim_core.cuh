@@ -81,6 +81,19 @@ struct Shared {           // SIM_NT entries each
 };
 
 SIM_HD double blk_max(double v, const Shared &sh) {
+#ifdef __CUDA_ARCH__
+  // warp shuffles, then one value per warp through shared memory (max is order-independent: same result as the loop)
+  for (int o = 16; o; o >>= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w > v ? w : v;
+  }
+  if ((SIM_TID & 31) == 0) sh.sd[SIM_TID >> 5] = v;
+  SIM_SYNC();
+  double r = sh.sd[0];
+  for (int i = 1; i < (SIM_NT >> 5); ++i) r = sh.sd[i] > r ? sh.sd[i] : r;
+  SIM_SYNC();
+  return r;
+#else
   sh.sd[SIM_TID] = v;
   SIM_SYNC();
   if (SIM_TID == 0) {
@@ -92,9 +105,19 @@ SIM_HD double blk_max(double v, const Shared &sh) {
   const double r = sh.sd[0];
   SIM_SYNC();
   return r;
+#endif
 }
 SIM_HD double blk_min(double v, const Shared &sh) { return -blk_max(-v, sh); }
 SIM_HD long long blk_sum(long long v, const Shared &sh) {
+#ifdef __CUDA_ARCH__
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);      // integer sum: exact in any order
+  if ((SIM_TID & 31) == 0) sh.si[SIM_TID >> 5] = v;
+  SIM_SYNC();
+  long long r = 0;
+  for (int i = 0; i < (SIM_NT >> 5); ++i) r += sh.si[i];
+  SIM_SYNC();
+  return r;
+#else
   sh.si[SIM_TID] = v;
   SIM_SYNC();
   if (SIM_TID == 0) {
@@ -106,6 +129,7 @@ SIM_HD long long blk_sum(long long v, const Shared &sh) {
   const long long r = sh.si[0];
   SIM_SYNC();
   return r;
+#endif
 }
 
 // admission of the jobs that have arrived by `now` (scheduler.py:2040-2052) + count of the live jobs

@@ -154,6 +154,13 @@ class HostDeviceSim:
             self.status[s], self.epoch[s], self.tl_ns[s], self.tl_end[s] = m.status, m.epoch, m.tl_ns, m.tl_end
         return self.scn
 
+    def replay(self, schedule):
+        self.begin()
+        for r in range(len(schedule)):
+            ch = schedule[r] if schedule.ndim == 3 else np.broadcast_to(schedule[r], (self.S, self.J))
+            self.step(ch)
+        return self.scn
+
     def results(self):
         r = [m.results() for m in self.sims]
         return dict(jct=np.stack([x[0] for x in r]), steps_run=np.stack([x[1] for x in r]),
