@@ -21,18 +21,21 @@ import math
 import numpy as np
 
 PREEMPTION_OVERHEAD = 20.0       # scheduler.py:1947-1949
+MAX_FAILED_ATTEMPTS = 5          # scheduler.py:66
 
 
 def steps_and_finish(now, thr, tpi, remaining):
     """scheduler.py:1441-1465 + :1500-1508 for a single static job: (num_steps, finish_time)."""
-    n = min(int(thr * tpi), remaining)
-    return n, now + n / thr
+    n = min(int(thr * tpi), remaining)               # negative after a rescale that rounds the progress up past the total
+    return n, max(now, now + n / thr)                # max_finish_time starts at the current timestamp (:1470, :1507)
 
 
-def run(trace, select, tpi=120.0, on_round=None, max_rounds=None):
+def run(trace, select, tpi=120.0, on_round=None, max_rounds=None, dyn=None):
     """trace: dict of equal-length sequences `arrival, total_steps, scale_factor, throughput, duration, batch_size,
     dataset_len`.  select(c, now, active) -> iterable of job indices to run in round c (active = ascending list of live
     jobs).  on_round(c, now, info) sees what the shockwave hook would see (epoch progress, measured throughput).
+    dyn: tables of the dynamic-adaptation jobs (accordion / gns batch-size rescaling, scheduler.py:1604-1727 and
+    :4731-4935) as shockwave_b200.simulate.build_dynamic_tables lays them out; None = every job static.
     Returns dict(makespan, rounds, jct[J] (nan = never completed), timeline {job: [(round, throughput, bs)]},
     per_round_schedule)."""
     arrival = [float(a) for a in trace["arrival"]]
@@ -42,7 +45,12 @@ def run(trace, select, tpi=120.0, on_round=None, max_rounds=None):
     sf = [int(v) for v in trace["scale_factor"]]
     dur = [float(v) for v in trace["duration"]]
     bs = [int(v) for v in trace["batch_size"]]
-    spe = [math.ceil(d / b) for d, b in zip(trace["dataset_len"], bs)]       # steps per epoch, scheduler.py:2332-2335
+    ds = [int(v) for v in trace["dataset_len"]]
+    spe = [math.ceil(d / b) for d, b in zip(ds, bs)]                          # steps per epoch, scheduler.py:2332-2335
+    orig_bs = list(bs)
+    fails = [0] * J                                       # _num_failures_per_job
+    flag = [0] * J                                        # 1 = big_bs, 2 = small_bs (scheduler.py:_bs_flags)
+    errs = set()
     assert all(arrival[i] <= arrival[i + 1] for i in range(J - 1))            # scheduler.py:1842-1843
     status = [0] * J                                      # 0 queued, 1 live, 2 completed
     steps_run = [0] * J
@@ -56,6 +64,62 @@ def run(trace, select, tpi=120.0, on_round=None, max_rounds=None):
     now = arrival[0]                                      # scheduler.py:1847
     round_start, round_end = 0.0, None                    # scheduler.py:1819-1820
     remaining_jobs = J
+
+    def request(j):
+        """_simulate_accordion :1658-1727 / _simulate_gns :1604-1656: raise a rescale request from the job's progress."""
+        cur = -(-steps_run[j] // spe[j])                  # _get_num_epochs: ceil(steps / ceil(dataset / bs))
+        pat = dyn["pattern"][j]
+        if dyn["mode"][j] == 1:
+            if dyn["acc_skip"][j]:
+                return
+            if cur >= len(pat):
+                errs.add("pattern")
+                return
+            crit = bool(pat[cur])
+            if bs[j] == orig_bs[j] and not crit:
+                if bs[j] != dyn["bs_max"][j]:
+                    flag[j] = 1
+            elif bs[j] != orig_bs[j] and crit:
+                if bs[j] != dyn["bs_min"][j]:
+                    flag[j] = 2
+        else:
+            if cur + 1 >= len(pat):
+                errs.add("pattern")
+                return
+            # bs_gns = get_gns_bs_pattern(.., max(760, cur + 2), ..): its last entry is never scaled (utils.py:801-1010)
+            nxt = orig_bs[j] if cur + 1 >= 759 else pat[cur + 1]
+            if nxt > bs[j] or pat[cur] > bs[j]:
+                if bs[j] != dyn["bs_max"][j]:
+                    flag[j] = 1
+
+    def rescale(j):
+        """_scale_bs_and_iters :4731-4935 for one job whose request flag is up."""
+        if dyn["orig_locked"][j]:
+            return
+        old = bs[j]
+        if dyn["mode"][j] == 2:
+            new = 2 * old
+        elif flag[j] == 1:
+            new = dyn["bs_big"][j]
+        else:
+            new = orig_bs[j]
+        lv = dyn["lvl_bs"][j]
+        if new not in lv or not (dyn["lvl_thr"][j][lv.index(new)] > 0):
+            return                                        # :4803-4818: batch size not in the throughput file
+        factor = new / old
+        it = 1 / factor
+        bs[j] = new
+        thr[j] = dyn["lvl_thr"][j][lv.index(new)]
+        spe_old, spe_new = math.ceil(ds[j] / old), math.ceil(ds[j] / new)
+        old_epochs = math.ceil(total[j] / spe_old)
+        new_total = math.ceil(total[j] * it)
+        if math.ceil(new_total / spe_new) != old_epochs:
+            new_total = spe_new * old_epochs
+        done_epochs = math.ceil(steps_run[j] / spe_old)
+        total[j] = new_total
+        steps_run[j] = done_epochs * spe_new
+        spe[j] = spe_new
+
     c = 0
     while True:
         if remaining_jobs == 0:
@@ -82,14 +146,27 @@ def run(trace, select, tpi=120.0, on_round=None, max_rounds=None):
             n = int(n * slow)
             run_time[j] += ex
             over = run_time[j] > int(dur[j] * 1.5)
-            steps_run[j] += n
+            if n <= 0 and ex <= 0:                        # micro-task failure, scheduler.py:4497-4570: no progress booked,
+                fails[j] += 1                             # the job is dropped after MAX_FAILED_ATTEMPTS in a row
+                done = fails[j] >= MAX_FAILED_ATTEMPTS
+            else:
+                fails[j] = 0
+                steps_run[j] += n
+                done = total[j] - steps_run[j] <= 0 or over
             timeline[j].append((c, 0.0 if ex <= 0 else n / ex, bs[j]))
-            if total[j] - steps_run[j] <= 0 or over:
+            if dyn is not None and flag[j]:
+                rescale(j)
+            flag[j] = 0                                   # scheduler.py:4700-4712: reset in every _done_callback
+            if done:
                 status[j] = 2
                 jct[j] = latest[j] - arrival[j]
                 remaining_jobs -= 1
             ran.append(j)
         running = []
+        if dyn is not None:                               # scheduler.py:2019-2027: every live job, every iteration
+            for j in range(J):
+                if status[j] == 1 and dyn["mode"][j]:
+                    request(j)
         if on_round is not None and now != 0.0:
             prev = schedule[c - 1] if c >= 1 else []
             on_round(c, now, dict(scheduled=list(prev), epoch={j: (None if status[j] == 2 else steps_run[j] // spe[j])
@@ -109,7 +186,7 @@ def run(trace, select, tpi=120.0, on_round=None, max_rounds=None):
         if max_rounds is not None and c >= max_rounds:
             break
     return dict(makespan=now, rounds=c, jct=jct, timeline=timeline, per_round_schedule=[sorted(s) for s in schedule],
-                steps_run=steps_run)
+                steps_run=steps_run, errs=sorted(errs), final_bs=bs)
 
 
 def trace_arrays(rec):

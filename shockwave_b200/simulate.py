@@ -256,3 +256,78 @@ class ShockwaveEnsemble:
         res.update(makespan=scn["now"].copy(), rounds=scn["rounds"].copy(), per_round_schedule=self.per_round_schedule,
                    resolves=self.resolves.copy(), avg_jct=np.nanmean(res["jct"], axis=1))
         return res
+
+
+# ---- dynamic adaptation (accordion / gns batch-size rescaling) as tables -------------------------------------------
+# The reference decides rescale requests from per-model rules hard-wired into its simulator.  The device loop takes
+# them as tables; this builder lays the tables out from the same rules (constants cited line by line) plus two things
+# only the caller has: the throughput file and the reference's own gns pattern generator.
+AT_MAX_BS = {"ResNet-18": 256, "ResNet-50": 128, "Transformer": 128, "LM": 80, "Recommendation": 8192}   # scheduler.py:1636-1646
+AT_MIN_BS = {"ResNet-18": 16, "ResNet-50": 16, "Transformer": 16, "LM": 5, "Recommendation": 512}       # scheduler.py:1711-1721
+MAX_BS_DICT = {"LM": 80, "ResNet-18": 256, "ResNet-50": 128, "Recommendation": 8192}                    # scheduler.py:4756-4761
+MODE_CODE = {"static": 0, "accordion": 1, "gns": 2}
+GNS_PATTERN_EPOCHS = 760                                                                                # scheduler.py:1619
+MAX_LEVELS = 8
+
+
+def accordion_critical(model, original_bs, epoch):
+    """in_critical_regime of _simulate_accordion (scheduler.py:1670-1692); None where the reference leaves it unset."""
+    if model == "LM":
+        return epoch < 10
+    if model == "Recommendation":
+        if original_bs in (512, 1024):
+            return epoch < 30
+        if original_bs == 2048:
+            return epoch < 40
+        if original_bs in (4096, 8192):
+            return epoch < 10
+        return None
+    if model == "ResNet-50":
+        return (epoch % 30) < 10
+    if model == "ResNet-18":
+        head = 20 if original_bs == 256 else 10
+        return (0 <= epoch < head) or (150 <= epoch < 160) or (250 <= epoch < 260)
+    return None
+
+
+def build_dynamic_tables(models, modes, trace, throughput_of, gns_pattern):
+    """Tables for swb_sim_set_dynamic.  models[j]: "ResNet-18", "LM", ...; modes[j]: "static" / "accordion" / "gns";
+    trace: the static arrays (batch_size = ORIGINAL batch size, total_steps, dataset_len, scale_factor);
+    throughput_of(model, batch_size, scale_factor) -> steps/s on the worker type or None when the throughput file has no
+    such entry; gns_pattern(job_type, batch_size, num_epochs, scale_factor) -> list: the reference's
+    utils.get_gns_bs_pattern (scheduler/utils.py:801-1010), called exactly as _simulate_gns does."""
+    J = len(models)
+    out = dict(mode=np.zeros(J, np.int32), bs_max=np.zeros(J, np.int32), bs_min=np.zeros(J, np.int32),
+               bs_big=np.full(J, -1, np.int32), orig_locked=np.zeros(J, np.int32), acc_skip=np.zeros(J, np.int32),
+               pattern=[], lvl_bs=[], lvl_thr=[])
+    for j in range(J):
+        model, bs0, sf = models[j], int(trace["batch_size"][j]), int(trace["scale_factor"][j])
+        mode = MODE_CODE[modes[j]]
+        out["mode"][j] = mode
+        out["bs_max"][j] = AT_MAX_BS.get(model, -1)
+        out["bs_min"][j] = AT_MIN_BS.get(model, -1)
+        out["bs_big"][j] = MAX_BS_DICT.get(model, -1)
+        out["orig_locked"][j] = int(model in MAX_BS_DICT and bs0 == MAX_BS_DICT[model])      # scheduler.py:4767-4775
+        cand = sorted({bs0 * (1 << i) for i in range(MAX_LEVELS)} | ({MAX_BS_DICT[model]} if model in MAX_BS_DICT else set()))
+        lv = [(b, throughput_of(model, b, sf)) for b in cand]
+        lv = [(b, t) for b, t in lv if t is not None][:MAX_LEVELS]
+        out["lvl_bs"].append([b for b, _ in lv])
+        out["lvl_thr"].append([float(t) for _, t in lv])
+        if mode == 1:
+            out["acc_skip"][j] = int(model == "Transformer")                                  # scheduler.py:1667-1669
+            spe = math.ceil(int(trace["dataset_len"][j]) / bs0)
+            n = math.ceil(int(trace["total_steps"][j]) / spe) + 8
+            crit = [accordion_critical(model, bs0, e) for e in range(n)]
+            if not out["acc_skip"][j] and any(v is None for v in crit):
+                raise ValueError(f"job {j}: the reference has no accordion rule for {model} at batch size {bs0}")
+            out["pattern"].append([int(bool(v)) for v in crit])
+        elif mode == 2:
+            # _simulate_gns asks for max(760, epoch + 2) epochs and reads entries epoch and epoch + 1 (:1617-1632).  The
+            # generator never scales the LAST entry of what it returns, every other entry does not depend on the length:
+            # one long table + the rule "entry epoch + 1 is the original batch size once epoch + 1 >= 759" (sim_core.cuh)
+            spe = math.ceil(int(trace["dataset_len"][j]) / bs0)
+            n = max(GNS_PATTERN_EPOCHS + 2, math.ceil(int(trace["total_steps"][j]) / spe) + 8)
+            out["pattern"].append([int(v) for v in gns_pattern(f"{model} (batch size {bs0})", bs0, n, sf)])
+        else:
+            out["pattern"].append([])
+    return out

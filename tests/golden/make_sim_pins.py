@@ -55,6 +55,53 @@ def extract(sched, jobs, arrival_times):
                 timeline=tl, jct=jct, rounds=int(sched._num_completed_rounds))
 
 
+def dynamic_inputs(jobs, sched):
+    """What shockwave_b200.simulate.build_dynamic_tables needs beside the static arrays, taken from the reference."""
+    import utils as ref_utils
+    models = [j.model for j in jobs]
+    modes = [j.mode for j in jobs]
+    table = sched._oracle_throughputs["v100"]
+
+    def throughput_of(model, bs, sf):
+        key = (f"{model} (batch size {bs})", sf)
+        return float(table[key]["null"]) if key in table else None
+    return models, modes, throughput_of, ref_utils.get_gns_bs_pattern
+
+
+def extract_dynamic(sched, jobs, arrival_times):
+    from shockwave_b200.simulate import build_dynamic_tables
+    rec = extract(sched, jobs, arrival_times)
+    models, modes, thr_of, gns = dynamic_inputs(jobs, sched)
+    # the jobs have been rescaled by the time the run ends: the ORIGINAL batch sizes / step counts are the trace's
+    rec["batch_size"] = [int(sched._original_bs[j._job_id]) for j in jobs]
+    rec["total_steps"] = [int(sched._original_num_steps[j._job_id]) for j in jobs]
+    rec["throughput"] = [thr_of(m, b, s) for m, b, s in zip(models, rec["batch_size"], rec["scale_factor"])]
+    dyn = build_dynamic_tables(models, modes, rec, thr_of, gns)
+    rec["models"], rec["modes"] = models, modes
+    rec["dyn"] = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in dyn.items()}
+    return rec
+
+
+def main_dynamic():
+    """Same records on the canonical trace AS SHIPPED (59 accordion, 57 gns, 4 static jobs)."""
+    scratch = tempfile.mkdtemp(prefix="swsimd_")
+    rh.prepare_tree(scratch)
+    out = {}
+    for policy, ngpu in (("fifo", 32), ("max_min_fairness", 32), ("max_min_fairness", 12)):
+        with gb.cpu_backend() as P:
+            pol = P.get_policy(policy, solver="ECOS", seed=0) if policy != "fifo" else None
+            r = rh.simulate(policy, policy_obj=pol, scratch=scratch, cluster=f"{ngpu}:0:0", extract=extract_dynamic)
+        rec = r["extra"]
+        rec.update(makespan=float(r["makespan"]), avg_jct=float(r["avg_jct"]), ngpus=ngpu, time_per_iteration=120,
+                   per_round_schedule=[sorted(int(k) for k in rnd.keys()) for rnd in r["per_round_schedule"]])
+        if out:                                   # the tables are the same for every run of the trace: keep them once
+            rec.pop("dyn")
+        out[f"{policy}_{ngpu}"] = rec
+        print(policy, ngpu, rec["makespan"], rec["rounds"], len(rec["per_round_schedule"]))
+    with open(os.path.join(ROOT, "tests", "golden", "sim_dynamic_pins.json"), "w") as f:
+        json.dump(out, f)
+
+
 def main():
     scratch = tempfile.mkdtemp(prefix="swsim_")
     stage_static_trace(scratch)
@@ -73,4 +120,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["dynamic"]:
+        main_dynamic()
+    else:
+        main()

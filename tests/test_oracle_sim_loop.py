@@ -116,3 +116,28 @@ def test_device_loop_source_on_random_traces(host_lib, J, ngpus, seed, gap):
             assert got == (-1 if e is None else e), (c, j)
     if gap:
         assert np.isnan(host["jct"]).any() or host["remaining"] == 0      # the reference stops when the cluster drains
+
+
+# ---- dynamic adaptation (accordion / gns): the canonical trace as shipped ----
+DPINS = os.path.join(os.path.dirname(__file__), "golden", "sim_dynamic_pins.json")
+
+
+def load_dynamic():
+    with open(DPINS) as f:
+        d = json.load(f)
+    dyn = d["fifo_32"]["dyn"]
+    return d, dyn
+
+
+@pytest.mark.parametrize("name", ["fifo_32", "max_min_fairness_32", "max_min_fairness_12"])
+def test_dynamic_replay_reproduces_the_reference(name):
+    d, dyn = load_dynamic()
+    rec = d[name]
+    sched = rec["per_round_schedule"]
+    out = sim_loop.run(rec, lambda c, now, active: sched[c], tpi=rec["time_per_iteration"], dyn=dyn)
+    assert out["errs"] == []
+    assert out["rounds"] == rec["rounds"] == len(sched)
+    assert out["makespan"] == rec["makespan"]
+    for j in range(len(rec["arrival"])):
+        assert out["jct"][j] == rec["jct"][str(j)], j
+        assert out["timeline"][j] == [(r, t, b) for r, t, b in rec["timeline"][str(j)]], j
