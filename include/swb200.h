@@ -382,9 +382,10 @@ int swb_market_pgd(swb_ctx *ctx, const swb_market_args *a);
  * ShockwaveScheduler.round_schedule(), a Gavel policy + swb_gavel_round, or a recorded schedule (swb_sim_replay runs
  * ALL rounds in one launch, no host in the loop).  Arithmetic = the reference's, in its order (IEEE double / int64):
  * completion times, makespan and measured throughputs are bit-identical to the reference loop on the same schedule
- * (tests/test_oracle_sim_loop.py, tests/test_gpu_sim.py).  Not covered (rejected with SWB_ERR_ARG / reported in err):
- * accordion / gns batch-size rescaling (`_simulate_accordion`, `_simulate_gns`, `_scale_bs_and_iters`), job pairs,
- * several worker types, micro-task failures. */
+ * (tests/test_oracle_sim_loop.py, tests/test_gpu_sim.py).  Dynamic adaptation — accordion / gns batch-size rescaling,
+ * `_simulate_accordion` :1658-1727, `_simulate_gns` :1604-1656, `_scale_bs_and_iters` :4731-4935 — runs from tables
+ * (swb_sim_set_dynamic); the micro-task failure branch of `_done_callback` (:4497-4570, five empty rounds in a row drop
+ * the job) is part of the loop.  Not covered: job pairs (packing), several worker types, the `ideal` mode. */
 typedef struct swb_sim swb_sim;
 typedef struct swb_sim_trace {
   int32_t J;
@@ -396,8 +397,28 @@ typedef struct swb_sim_trace {
   const double *duration;         /* [J] job.duration (over-deadline rule: run time > int(1.5 duration)) */
   const int32_t *batch_size;      /* [J] */
   const int64_t *dataset_len;     /* [J] samples per epoch (scheduler.py:73-81 dataset_size_dict) */
-  const int32_t *adaptation_mode; /* [J] or NULL: 0 = static; anything else is rejected */
+  const int32_t *adaptation_mode; /* [J] or NULL: 0 static, 1 accordion, 2 gns; a trace with non-static jobs needs
+                                     swb_sim_set_dynamic before the first round */
 } swb_sim_trace;
+/* Tables of the dynamic-adaptation jobs; batch_size / total_steps / throughput of the trace are the ORIGINAL values.
+ * shockwave_b200/simulate.py::build_dynamic_tables lays them out from the reference's rules. */
+typedef struct swb_sim_dynamic {
+  const int32_t *mode;        /* [J] 0 static, 1 accordion, 2 gns */
+  const int32_t *bs_max;      /* [J] batch size at which no scale-up is requested (scheduler.py:1636-1646, :1699-1709) */
+  const int32_t *bs_min;      /* [J] batch size at which no scale-down is requested (:1711-1721) */
+  const int32_t *bs_big;      /* [J] accordion's scale-up target max_bs_dict[model] (:4756-4761); <= 0: none */
+  const int32_t *orig_locked; /* [J] 1: the original batch size is max_bs_dict[model]: every request is dropped (:4767-4775) */
+  const int32_t *acc_skip;    /* [J] 1: accordion never applies (Transformer, :1667-1669) */
+  const int64_t *pat_off;     /* [J+1] offsets into pattern */
+  const int32_t *pattern;     /* accordion: 1 = critical regime at that epoch (:1670-1692); gns: batch size at that epoch
+                                 (utils.get_gns_bs_pattern with >= 762 epochs; the loop applies the reference's
+                                 "last entry is never scaled" rule for epochs >= 758 itself) */
+  int32_t n_levels;           /* K <= 8 */
+  int32_t reserved;
+  const int32_t *lvl_bs;      /* [J][K] batch sizes the job can move to (0 = unused) */
+  const double *lvl_thr;      /* [J][K] throughput of the job at that batch size (<= 0: not in the throughput file) */
+} swb_sim_dynamic;
+int swb_sim_set_dynamic(swb_sim *sim, const swb_sim_dynamic *tables);
 typedef struct swb_sim_scn {      /* per scenario, after a step */
   double now;                     /* Scheduler._current_timestamp; at the end of the run: the makespan */
   double round_start, round_end;  /* current_round_start_time / _end_time (NaN = None) */
@@ -406,7 +427,7 @@ typedef struct swb_sim_scn {      /* per scenario, after a step */
   int32_t n_active;               /* live jobs (len(self._jobs)) */
   int32_t done;                   /* 1: the reference's loop has left (all jobs completed, or no live job) */
   int32_t err;                    /* bit 0: chosen gangs exceed ngpus; bit 1: nothing running and no arrival left
-                                     (the reference raises); bit 2: micro-task failure branch */
+                                     (the reference raises); bit 2: a job's epoch left its dynamic-adaptation table */
   int32_t reserved;
 } swb_sim_scn;
 int swb_sim_create(int32_t device, const swb_sim_trace *trace, int32_t S, int32_t ngpus, double time_per_iteration,

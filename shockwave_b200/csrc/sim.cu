@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(SIM_THREADS) sim_kernel(SimLaunch L) {
   sim::State X = L.X;
   X.status += o; X.ranprev += o; X.steps_run += o; X.nsteps += o; X.run_time += o; X.latest += o; X.jct += o;
   X.fin += o; X.tl_ns += o; X.thr_meas += o; X.tl_prev += o; X.tl_end += o; X.epoch += o;
+  X.running += o; X.flag += o; X.fails += o; X.cbs += o; X.ctotal += o; X.cspe += o; X.cthr += o;
   sim::Shared sh{sd, si};
   sim::Scn *scn = L.scn + blockIdx.x;
   if (L.begin) sim::scenario_begin(L.T, X, scn, sh);
@@ -46,6 +47,8 @@ struct swb_sim {
   double tpi = 0, grd = 0;
   cudaStream_t st = nullptr;
   void *arena = nullptr;        // trace + state, one allocation
+  void *dyn_arena = nullptr;    // tables of swb_sim_set_dynamic
+  int needs_dynamic = 0;        // the trace names non-static jobs: tables are required before the first round
   unsigned char *d_chosen = nullptr;
   size_t chosen_cap = 0;
   unsigned char *h_pin = nullptr;   // pinned staging of the per-step outputs
@@ -70,6 +73,7 @@ void swb_sim_destroy(swb_sim *m) {
   cudaSetDevice(m->device);
   if (m->st) cudaStreamSynchronize(m->st);
   if (m->arena) cudaFree(m->arena);
+  if (m->dyn_arena) cudaFree(m->dyn_arena);
   if (m->d_chosen) cudaFree(m->d_chosen);
   if (m->h_pin) cudaFreeHost(m->h_pin);
   if (m->st) cudaStreamDestroy(m->st);
@@ -88,6 +92,7 @@ int swb_sim_create(int32_t device, const swb_sim_trace *tr, int32_t S, int32_t n
     return swb_set_error(SWB_ERR_ARG, "swb_sim_create: null trace array");
   std::vector<double> dur15(J);
   std::vector<long long> spe(J);
+  int any_dynamic = 0;
   for (int j = 0; j < J; ++j) {
     if (j && tr->arrival[j] < tr->arrival[j - 1])
       return swb_set_error(SWB_ERR_ARG, "swb_sim_create: arrival times must be non-decreasing (scheduler.py:1842-1843)");
@@ -95,9 +100,9 @@ int swb_sim_create(int32_t device, const swb_sim_trace *tr, int32_t S, int32_t n
         tr->dataset_len[j] <= 0 || !(tr->duration[j] >= 0) || !(tr->arrival[j] >= 0))
       return swb_set_error(SWB_ERR_ARG, "swb_sim_create: throughput, total_steps, scale_factor, batch_size, dataset_len "
                                         "must be positive, duration / arrival non-negative");
-    if (tr->adaptation_mode && tr->adaptation_mode[j] != 0)
-      return swb_set_error(SWB_ERR_ARG, "swb_sim_create: only static jobs (accordion / gns batch-size rescaling is not part "
-                                        "of the device loop)");
+    if (tr->adaptation_mode && (tr->adaptation_mode[j] < 0 || tr->adaptation_mode[j] > 2))
+      return swb_set_error(SWB_ERR_ARG, "swb_sim_create: adaptation_mode must be 0 (static), 1 (accordion) or 2 (gns)");
+    if (tr->adaptation_mode && tr->adaptation_mode[j] != 0) any_dynamic = 1;
     dur15[j] = (double)(long long)(tr->duration[j] * 1.5);
     spe[j] = (tr->dataset_len[j] + tr->batch_size[j] - 1) / tr->batch_size[j];
   }
@@ -107,6 +112,7 @@ int swb_sim_create(int32_t device, const swb_sim_trace *tr, int32_t S, int32_t n
   if (device < 0 || device >= ndev) return swb_set_error(SWB_ERR_ARG, "swb_sim_create: bad device index");
   swb_sim *m = new (std::nothrow) swb_sim;
   if (!m) return swb_set_error(SWB_ERR_CUDA, "swb_sim_create: out of memory");
+  m->needs_dynamic = any_dynamic;
   m->device = device; m->S = S; m->J = J; m->ngpus = ngpus; m->tpi = time_per_iteration; m->grd = round_duration;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
@@ -115,11 +121,14 @@ int swb_sim_create(int32_t device, const swb_sim_trace *tr, int32_t S, int32_t n
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
   const size_t o_arr = take((size_t)J * 8), o_tot = take((size_t)J * 8), o_thr = take((size_t)J * 8),
-               o_d15 = take((size_t)J * 8), o_spe = take((size_t)J * 8), o_sf = take((size_t)J * 4), o_bs = take((size_t)J * 4);
+               o_d15 = take((size_t)J * 8), o_spe = take((size_t)J * 8), o_ds = take((size_t)J * 8), o_sf = take((size_t)J * 4),
+               o_bs = take((size_t)J * 4);
   const size_t o_status = take(sj), o_ranprev = take(sj), o_steps = take(sj * 8), o_nsteps = take(sj * 8),
                o_rt = take(sj * 8), o_latest = take(sj * 8), o_jct = take(sj * 8), o_fin = take(sj * 8),
                o_tlns = take(sj * 8), o_tm = take(sj * 8), o_tlprev = take(sj * 4), o_tlend = take(sj * 4),
-               o_epoch = take(sj * 4), o_scn = take((size_t)S * sizeof(swb::sim::Scn));
+               o_epoch = take(sj * 4), o_running = take(sj), o_flag = take(sj), o_fails = take(sj), o_cbs = take(sj * 4),
+               o_ctotal = take(sj * 8), o_cspe = take(sj * 8), o_cthr = take(sj * 8),
+               o_scn = take((size_t)S * sizeof(swb::sim::Scn));
   if (e == cudaSuccess) e = cudaMalloc(&m->arena, off);
   if (e != cudaSuccess) {
     swb_sim_destroy(m);
@@ -134,6 +143,7 @@ int swb_sim_create(int32_t device, const swb_sim_trace *tr, int32_t S, int32_t n
   if (e == cudaSuccess) e = up(o_thr, tr->throughput, (size_t)J * 8);
   if (e == cudaSuccess) e = up(o_d15, dur15.data(), (size_t)J * 8);
   if (e == cudaSuccess) e = up(o_spe, spe.data(), (size_t)J * 8);
+  if (e == cudaSuccess) e = up(o_ds, tr->dataset_len, (size_t)J * 8);
   if (e == cudaSuccess) e = up(o_sf, tr->scale_factor, (size_t)J * 4);
   if (e == cudaSuccess) e = up(o_bs, tr->batch_size, (size_t)J * 4);
   if (e == cudaSuccess) e = cudaStreamSynchronize(m->st);      // dur15 / spe are locals
@@ -141,14 +151,18 @@ int swb_sim_create(int32_t device, const swb_sim_trace *tr, int32_t S, int32_t n
     swb_sim_destroy(m);
     return swb_set_error(SWB_ERR_CUDA, (std::string("swb_sim_create: ") + cudaGetErrorString(e)).c_str());
   }
-  m->T = swb::sim::Trace{J, (const double *)(b + o_arr), (const long long *)(b + o_tot), (const int *)(b + o_sf),
-                         (const double *)(b + o_thr), (const double *)(b + o_d15), (const int *)(b + o_bs),
-                         (const long long *)(b + o_spe)};
+  m->T = swb::sim::Trace{};
+  m->T.J = J; m->T.arrival = (const double *)(b + o_arr); m->T.total = (const long long *)(b + o_tot);
+  m->T.sf = (const int *)(b + o_sf); m->T.thr = (const double *)(b + o_thr); m->T.dur15 = (const double *)(b + o_d15);
+  m->T.bs = (const int *)(b + o_bs); m->T.spe = (const long long *)(b + o_spe); m->T.ds = (const long long *)(b + o_ds);
   m->X.status = (unsigned char *)(b + o_status); m->X.ranprev = (unsigned char *)(b + o_ranprev);
   m->X.steps_run = (long long *)(b + o_steps); m->X.nsteps = (long long *)(b + o_nsteps);
   m->X.run_time = (double *)(b + o_rt); m->X.latest = (double *)(b + o_latest); m->X.jct = (double *)(b + o_jct);
   m->X.fin = (double *)(b + o_fin); m->X.tl_ns = (double *)(b + o_tlns); m->X.thr_meas = (double *)(b + o_tm);
   m->X.tl_prev = (int *)(b + o_tlprev); m->X.tl_end = (int *)(b + o_tlend); m->X.epoch = (int *)(b + o_epoch);
+  m->X.running = (unsigned char *)(b + o_running); m->X.flag = (unsigned char *)(b + o_flag);
+  m->X.fails = (unsigned char *)(b + o_fails); m->X.cbs = (int *)(b + o_cbs); m->X.ctotal = (long long *)(b + o_ctotal);
+  m->X.cspe = (long long *)(b + o_cspe); m->X.cthr = (double *)(b + o_cthr);
   m->scn = (swb::sim::Scn *)(b + o_scn);
   *out = m;
   return 0;
@@ -203,8 +217,54 @@ static int sim_upload(swb_sim *m, const uint8_t *chosen, size_t bytes) {
   return 0;
 }
 
+int swb_sim_set_dynamic(swb_sim *m, const swb_sim_dynamic *d) {
+  if (!m || !d) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: null argument");
+  if (!d->mode || !d->bs_max || !d->bs_min || !d->bs_big || !d->orig_locked || !d->acc_skip || !d->pat_off || !d->lvl_bs ||
+      !d->lvl_thr)
+    return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: null table");
+  const int J = m->J, K = d->n_levels;
+  if (K <= 0 || K > SIM_MAX_LEVELS) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: n_levels must be in [1, 8]");
+  if (d->pat_off[0] != 0) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: pat_off[0] must be 0");
+  for (int j = 0; j < J; ++j) {
+    if (d->pat_off[j + 1] < d->pat_off[j]) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: pat_off must be non-decreasing");
+    if (d->mode[j] < 0 || d->mode[j] > 2) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: mode must be 0, 1 or 2");
+    if (d->mode[j] == 2 && d->pat_off[j + 1] - d->pat_off[j] < 762)
+      return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: a gns job needs a pattern of >= 762 epochs (scheduler.py:1617-1622)");
+  }
+  const long long np = d->pat_off[J];
+  if (np > 0 && !d->pattern) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: null pattern");
+  SCK(cudaSetDevice(m->device));
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += al(bytes ? bytes : 1); return o; };
+  const size_t o_mode = take((size_t)J * 4), o_max = take((size_t)J * 4), o_min = take((size_t)J * 4), o_big = take((size_t)J * 4),
+               o_lock = take((size_t)J * 4), o_skip = take((size_t)J * 4), o_off = take((size_t)(J + 1) * 8),
+               o_pat = take((size_t)np * 4), o_lb = take((size_t)J * K * 4), o_lt = take((size_t)J * K * 8);
+  SCK(cudaStreamSynchronize(m->st));
+  if (m->dyn_arena) cudaFree(m->dyn_arena);
+  m->dyn_arena = nullptr;
+  SCK(cudaMalloc(&m->dyn_arena, off));
+  char *b = (char *)m->dyn_arena;
+  auto up = [&](size_t o, const void *src, size_t bytes) {
+    return bytes ? cudaMemcpyAsync(b + o, src, bytes, cudaMemcpyHostToDevice, m->st) : cudaSuccess;
+  };
+  SCK(up(o_mode, d->mode, (size_t)J * 4)); SCK(up(o_max, d->bs_max, (size_t)J * 4)); SCK(up(o_min, d->bs_min, (size_t)J * 4));
+  SCK(up(o_big, d->bs_big, (size_t)J * 4)); SCK(up(o_lock, d->orig_locked, (size_t)J * 4));
+  SCK(up(o_skip, d->acc_skip, (size_t)J * 4)); SCK(up(o_off, d->pat_off, (size_t)(J + 1) * 8));
+  SCK(up(o_pat, d->pattern, (size_t)np * 4)); SCK(up(o_lb, d->lvl_bs, (size_t)J * K * 4));
+  SCK(up(o_lt, d->lvl_thr, (size_t)J * K * 8));
+  SCK(cudaStreamSynchronize(m->st));
+  m->T.mode = (const int *)(b + o_mode); m->T.bs_max = (const int *)(b + o_max); m->T.bs_min = (const int *)(b + o_min);
+  m->T.bs_big = (const int *)(b + o_big); m->T.orig_locked = (const int *)(b + o_lock); m->T.acc_skip = (const int *)(b + o_skip);
+  m->T.pat_off = (const long long *)(b + o_off); m->T.pattern = (const int *)(b + o_pat); m->T.K = K;
+  m->T.lvl_bs = (const int *)(b + o_lb); m->T.lvl_thr = (const double *)(b + o_lt);
+  m->needs_dynamic = 0;
+  return 0;
+}
+
 int swb_sim_begin(swb_sim *m, swb_sim_scn *scn, uint8_t *status) {
   if (!m) return swb_set_error(SWB_ERR_ARG, "swb_sim_begin: null handle");
+  if (m->needs_dynamic)
+    return swb_set_error(SWB_ERR_STATE, "swb_sim_begin: the trace has accordion / gns jobs: call swb_sim_set_dynamic first");
   SCK(cudaSetDevice(m->device));
   m->begun = 1;
   return sim_run(m, nullptr, 0, 0, 0, 1, scn, status, nullptr, nullptr, nullptr);
@@ -225,6 +285,8 @@ int swb_sim_replay(swb_sim *m, const uint8_t *schedule, int32_t R, int32_t per_s
   SCK(cudaSetDevice(m->device));
   const size_t per_round = per_scenario ? (size_t)m->S * m->J : (size_t)m->J;
   if (per_round * (size_t)R > ((size_t)4 << 30)) return swb_set_error(SWB_ERR_ARG, "swb_sim_replay: schedule above 4 GiB");
+  if (m->needs_dynamic)
+    return swb_set_error(SWB_ERR_STATE, "swb_sim_replay: the trace has accordion / gns jobs: call swb_sim_set_dynamic first");
   if (int rc = sim_upload(m, schedule, per_round * (size_t)R)) return rc;
   m->begun = 1;
   return sim_run(m, m->d_chosen, (long long)per_round, per_scenario ? m->J : 0, R, 1, scn, nullptr, nullptr, nullptr, nullptr);

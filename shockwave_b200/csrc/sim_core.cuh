@@ -17,6 +17,13 @@
 //                          kept as a running sum: what ShockwaveScheduler's forecast reads)
 //   epoch progress         floor(steps_run / ceil(dataset / batch size))                    (scheduler.py:2332-2335)
 //
+// Dynamic adaptation (accordion / gns batch-size rescaling) is table-driven: `_simulate_accordion` :1658-1727 and
+// `_simulate_gns` :1604-1656 raise a request from the job's epoch (tables: critical-regime flag / gns batch size per
+// epoch), `_scale_bs_and_iters` :4731-4935 applies it at the job's next completion callback (new batch size, throughput
+// of that batch size from the throughput file, total steps and progress rescaled with the epoch count preserved).
+// The micro-task failure branch (:4497-4570: a round with no steps and no run time; five in a row drop the job) is part
+// of the loop: the canonical trace reaches it after a rescale rounds a job's progress up past its total.
+//
 // The SAME source compiles for the host (one "thread", barriers are no-ops): tests/native/sim_host.cpp builds it with
 // g++ so the bookkeeping is checked bit for bit against the pinned restatement (oracle/sim_loop.py) without a GPU.
 // That host build is test tooling only — libswb200 has no CPU path.
@@ -48,7 +55,9 @@
 namespace swb {
 namespace sim {
 
-enum { ERR_CAPACITY = 1, ERR_NO_EVENT = 2, ERR_MICROTASK = 4 };
+enum { ERR_CAPACITY = 1, ERR_NO_EVENT = 2, ERR_PATTERN = 4 };
+#define SIM_MAX_FAILED_ATTEMPTS 5 /* scheduler.py:53 */
+#define SIM_MAX_LEVELS 8
 enum { QUEUED = 0, LIVE = 1, COMPLETED = 2 };
 #define SIM_PREEMPTION_OVERHEAD 20.0
 
@@ -59,8 +68,17 @@ struct Trace {            // [J], shared by the scenarios
   const int *sf;
   const double *thr;
   const double *dur15;    // (double) int(1.5 * duration)
-  const int *bs;
-  const long long *spe;   // steps per epoch = ceil(dataset / batch size)
+  const int *bs;          // ORIGINAL batch size
+  const long long *spe;   // steps per epoch at the original batch size = ceil(dataset / batch size)
+  const long long *ds;    // dataset length
+  // dynamic adaptation (all null / 0 when every job is static)
+  const int *mode;        // 0 static, 1 accordion, 2 gns
+  const int *bs_max, *bs_min, *bs_big, *orig_locked, *acc_skip;
+  const long long *pat_off;   // [J + 1]
+  const int *pattern;
+  int K;                  // levels per job
+  const int *lvl_bs;      // [J][K]
+  const double *lvl_thr;  // [J][K]
 };
 
 struct Scn {              // == swb_sim_scn
@@ -73,6 +91,11 @@ struct State {            // [J] of ONE scenario
   long long *steps_run, *nsteps;
   double *run_time, *latest, *jct, *fin, *tl_ns, *thr_meas;
   int *tl_prev, *tl_end, *epoch;
+  // mutable copies of the trace constants a rescale changes + request / failure counters
+  unsigned char *running, *flag, *fails;
+  int *cbs;
+  long long *ctotal, *cspe;
+  double *cthr;
 };
 
 struct Shared {           // SIM_NT entries each
@@ -132,6 +155,59 @@ SIM_HD long long blk_sum(long long v, const Shared &sh) {
 #endif
 }
 
+SIM_HD long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
+
+// _simulate_accordion :1658-1727 / _simulate_gns :1604-1656: raise a rescale request from the job's progress.
+// Returns 1 when the job's epoch is outside its table.
+SIM_HD int request(const Trace &T, const State &X, int j) {
+  const long long cur = ceil_div(X.steps_run[j], X.cspe[j]);          // _get_num_epochs :4722-4729
+  const int *pat = T.pattern + T.pat_off[j];
+  const long long len = T.pat_off[j + 1] - T.pat_off[j];
+  const int bs = X.cbs[j], orig = T.bs[j];
+  if (T.mode[j] == 1) {
+    if (T.acc_skip[j]) return 0;
+    if (cur >= len) return 1;
+    const bool crit = pat[cur] != 0;
+    if (bs == orig && !crit) {
+      if (bs != T.bs_max[j]) X.flag[j] = 1;
+    } else if (bs != orig && crit) {
+      if (bs != T.bs_min[j]) X.flag[j] = 2;
+    }
+  } else {
+    if (cur + 1 >= len) return 1;
+    // get_gns_bs_pattern(.., max(760, cur + 2), ..) never scales its last entry (utils.py:801-1010)
+    const int nxt = cur + 1 >= 759 ? orig : pat[cur + 1];
+    if (nxt > bs || pat[cur] > bs) {
+      if (bs != T.bs_max[j]) X.flag[j] = 1;
+    }
+  }
+  return 0;
+}
+
+// _scale_bs_and_iters :4731-4935 for a job whose request flag is up
+SIM_HD int rescale(const Trace &T, const State &X, int j) {
+  if (T.orig_locked[j]) return 0;
+  const int old = X.cbs[j];
+  const int nw = T.mode[j] == 2 ? 2 * old : (X.flag[j] == 1 ? T.bs_big[j] : T.bs[j]);
+  int k = -1;
+  for (int i = 0; i < T.K; ++i)
+    if (T.lvl_bs[(size_t)j * T.K + i] == nw && T.lvl_thr[(size_t)j * T.K + i] > 0.0) k = i;
+  if (k < 0 || nw <= 0) return 0;                    // batch size not in the throughput file: request dropped (:4803-4818)
+  const double factor = (double)nw / (double)old;
+  const double it = 1.0 / factor;
+  const long long spe_old = ceil_div(T.ds[j], old), spe_new = ceil_div(T.ds[j], nw);
+  const long long old_epochs = ceil_div(X.ctotal[j], spe_old);
+  long long new_total = (long long)ceil(SIM_MUL((double)X.ctotal[j], it));
+  if (ceil_div(new_total, spe_new) != old_epochs) new_total = spe_new * old_epochs;
+  const long long done_epochs = ceil_div(X.steps_run[j], spe_old);
+  X.ctotal[j] = new_total;
+  X.steps_run[j] = done_epochs * spe_new;
+  X.cspe[j] = spe_new;
+  X.cbs[j] = nw;
+  X.cthr[j] = T.lvl_thr[(size_t)j * T.K + k];
+  return 0;
+}
+
 // admission of the jobs that have arrived by `now` (scheduler.py:2040-2052) + count of the live jobs
 SIM_HD int admit(const Trace &T, const State &X, double now, const Shared &sh) {
   long long live = 0;
@@ -148,6 +224,8 @@ SIM_HD void scenario_begin(const Trace &T, const State &X, Scn *scn, const Share
     X.status[j] = QUEUED; X.ranprev[j] = 0; X.steps_run[j] = 0; X.nsteps[j] = -1;
     X.run_time[j] = 0.0; X.latest[j] = NAN; X.jct[j] = NAN; X.fin[j] = 0.0; X.tl_ns[j] = 0.0; X.thr_meas[j] = 0.0;
     X.tl_prev[j] = 0; X.tl_end[j] = -1; X.epoch[j] = 0;
+    X.running[j] = 0; X.flag[j] = 0; X.fails[j] = 0;
+    X.cbs[j] = T.bs[j]; X.ctotal[j] = T.total[j]; X.cspe[j] = T.spe[j]; X.cthr[j] = T.thr[j];
   }
   SIM_SYNC();
   const double now = T.arrival[0];
@@ -170,15 +248,16 @@ SIM_HD void scenario_step(const Trace &T, const State &X, Scn *scn, const unsign
   long long used = 0, nrun = 0;
   for (int j = SIM_TID; j < T.J; j += SIM_NT) {
     if (chosen[j] && X.status[j] == LIVE) {
-      const long long rem = T.total[j] - X.steps_run[j];
-      long long n = (long long)SIM_MUL(T.thr[j], tpi);
+      const long long rem = X.ctotal[j] - X.steps_run[j];      // negative after a rescale that rounds the progress up
+      long long n = (long long)SIM_MUL(X.cthr[j], tpi);
       if (n > rem) n = rem;
-      const double fin = z.now + (double)n / T.thr[j];
-      X.nsteps[j] = n; X.fin[j] = fin;
+      double fin = z.now + (double)n / X.cthr[j];
+      if (!(fin > z.now)) fin = z.now;                          // max_finish_time starts at the current timestamp (:1470)
+      X.nsteps[j] = n; X.fin[j] = fin; X.running[j] = 1;
       mx = fin > mx ? fin : mx;
       used += T.sf[j]; ++nrun;
     } else {
-      X.nsteps[j] = -1;
+      X.running[j] = 0;
     }
   }
   mx = blk_max(mx, sh);
@@ -204,10 +283,10 @@ SIM_HD void scenario_step(const Trace &T, const State &X, Scn *scn, const unsign
   long long completed = 0, bad = 0;
   if (!z.done)
     for (int j = SIM_TID; j < T.J; j += SIM_NT) {
-      const long long n0 = X.nsteps[j];
-      if (n0 >= 0) {
+      const bool ran = X.running[j] != 0;
+      if (ran) {
         double ex = X.fin[j] - z.round_start;
-        long long n = n0;
+        long long n = X.nsteps[j];
         if (c != 1 && !X.ranprev[j]) {
           if (ex != 0.0 && tpi - 5.0 < ex) {
             const double slow = (ex - SIM_PREEMPTION_OVERHEAD) / ex;
@@ -215,29 +294,39 @@ SIM_HD void scenario_step(const Trace &T, const State &X, Scn *scn, const unsign
             n = (long long)SIM_MUL((double)n, slow);
           }
         }
-        if (n <= 0 && ex <= 0.0) ++bad;             // micro-task failure branch: not restated
         X.latest[j] = X.fin[j];
         X.run_time[j] += ex;
         const bool over = X.run_time[j] > T.dur15[j];
-        X.steps_run[j] += n;
+        bool done;
+        if (n <= 0 && ex <= 0.0) {                  // micro-task failure (scheduler.py:4497-4570): nothing is booked
+          X.fails[j] = (unsigned char)(X.fails[j] + 1);
+          done = X.fails[j] >= SIM_MAX_FAILED_ATTEMPTS;
+        } else {
+          X.fails[j] = 0;
+          X.steps_run[j] += n;
+          done = X.ctotal[j] - X.steps_run[j] <= 0 || over;
+        }
         const double tm = ex <= 0.0 ? 0.0 : (double)n / ex;
         X.thr_meas[j] = tm;
-        X.tl_ns[j] = SIM_ADD(X.tl_ns[j], SIM_MUL((double)T.bs[j], SIM_MUL(SIM_MUL(tm, grd), (double)(c - X.tl_prev[j]))));
+        X.tl_ns[j] = SIM_ADD(X.tl_ns[j], SIM_MUL((double)X.cbs[j], SIM_MUL(SIM_MUL(tm, grd), (double)(c - X.tl_prev[j]))));
         X.tl_prev[j] = c; X.tl_end[j] = c;
-        if (T.total[j] - X.steps_run[j] <= 0 || over) {
+        if (X.flag[j] && T.mode) bad += rescale(T, X, j);
+        X.flag[j] = 0;                              // reset in every completion callback (scheduler.py:4700-4712)
+        if (done) {
           X.status[j] = COMPLETED;
           X.jct[j] = X.latest[j] - T.arrival[j];
           X.epoch[j] = -1;                          // the caller retires the job (its progress = all epochs)
           ++completed;
         } else {
-          X.epoch[j] = (int)(X.steps_run[j] / T.spe[j]);
+          X.epoch[j] = (int)(X.steps_run[j] / X.cspe[j]);
         }
       }
-      X.ranprev[j] = n0 >= 0;
+      X.ranprev[j] = ran;
+      if (T.mode && T.mode[j] && X.status[j] == LIVE) bad += request(T, X, j);     // scheduler.py:2019-2027
     }
   completed = blk_sum(completed, sh);
   bad = blk_sum(bad, sh);
-  if (bad) z.err |= ERR_MICROTASK;
+  if (bad) z.err |= ERR_PATTERN;
   z.remaining -= (int)completed;
   // ---- arrivals (scheduler.py:2040-2052), end-of-run tests (:1895-1899, :2173-2178)
   int live = z.n_active;

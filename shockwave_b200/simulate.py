@@ -10,8 +10,9 @@ policy of every scenario deciding between two steps:
                           `_update_shockwave_scheduler`: O(jobs) dict work per round) is replaced by array updates taken
                           from the step's outputs (`ShockwaveScheduler.schedule_progress_batch`).
 
-Static jobs on one worker type only (swb_sim_create rejects anything else); dynamic-adaptation traces keep running
-through the reference's own loop with the kernels behind `round_schedule()` (tests/test_closed_loop.py).
+One worker type, single jobs (no packing).  Dynamic adaptation (accordion / gns batch-size rescaling) runs from
+tables: `build_dynamic_tables` lays them out from the reference's rules, the throughput file and the reference's own
+gns pattern generator.
 No CPU path: the binding raises when libswb200.so or the GPU is missing."""
 import ctypes as C
 import math
@@ -29,6 +30,32 @@ class SimTrace(C.Structure):
     _fields_ = [("J", C.c_int32), ("reserved", C.c_int32), ("arrival", C.c_void_p), ("total_steps", C.c_void_p),
                 ("scale_factor", C.c_void_p), ("throughput", C.c_void_p), ("duration", C.c_void_p),
                 ("batch_size", C.c_void_p), ("dataset_len", C.c_void_p), ("adaptation_mode", C.c_void_p)]
+
+
+class SimDynamic(C.Structure):
+    _fields_ = [("mode", C.c_void_p), ("bs_max", C.c_void_p), ("bs_min", C.c_void_p), ("bs_big", C.c_void_p),
+                ("orig_locked", C.c_void_p), ("acc_skip", C.c_void_p), ("pat_off", C.c_void_p), ("pattern", C.c_void_p),
+                ("n_levels", C.c_int32), ("reserved", C.c_int32), ("lvl_bs", C.c_void_p), ("lvl_thr", C.c_void_p)]
+
+
+def pack_dynamic_tables(dyn, J):
+    """build_dynamic_tables() output -> the flat arrays of swb_sim_dynamic (kept alive by the returned dict)."""
+    K = max(1, max(len(v) for v in dyn["lvl_bs"]))
+    if K > MAX_LEVELS:
+        raise ValueError("more than 8 batch-size levels for one job")
+    a = {k: np.ascontiguousarray(dyn[k], dtype=np.int32) for k in ("mode", "bs_max", "bs_min", "bs_big", "orig_locked", "acc_skip")}
+    off = np.zeros(J + 1, np.int64)
+    off[1:] = np.cumsum([len(p) for p in dyn["pattern"]])
+    a["pat_off"] = off
+    a["pattern"] = np.ascontiguousarray(np.concatenate([np.asarray(p, np.int32) for p in dyn["pattern"]] + [np.zeros(1, np.int32)]))
+    lb = np.zeros((J, K), np.int32)
+    lt = np.zeros((J, K), np.float64)
+    for j in range(J):
+        n = len(dyn["lvl_bs"][j])
+        lb[j, :n] = dyn["lvl_bs"][j]
+        lt[j, :n] = dyn["lvl_thr"][j]
+    a["lvl_bs"], a["lvl_thr"], a["K"] = lb, lt, K
+    return a
 
 
 class SimScn(C.Structure):
@@ -56,7 +83,8 @@ def _lib():
         lib.swb_sim_step.argtypes = [C.c_void_p] * 7
         lib.swb_sim_replay.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         lib.swb_sim_results.argtypes = [C.c_void_p] * 5
-        for f in ("swb_sim_create", "swb_sim_begin", "swb_sim_step", "swb_sim_replay", "swb_sim_results"):
+        lib.swb_sim_set_dynamic.argtypes = [C.c_void_p, C.POINTER(SimDynamic)]
+        for f in ("swb_sim_set_dynamic", "swb_sim_create", "swb_sim_begin", "swb_sim_step", "swb_sim_replay", "swb_sim_results"):
             getattr(lib, f).restype = C.c_int
         _bound = True
     return lib
@@ -100,6 +128,15 @@ class DeviceSim:
     def _ck(self, rc):
         if rc != 0:
             raise RuntimeError(f"libswb200: {self._lib.swb_last_error().decode()} (code {rc})")
+
+    def set_dynamic(self, dyn):
+        """dyn: build_dynamic_tables() output (accordion / gns jobs)."""
+        a = pack_dynamic_tables(dyn, self.J)
+        d = SimDynamic()
+        for k in ("mode", "bs_max", "bs_min", "bs_big", "orig_locked", "acc_skip", "pat_off", "pattern", "lvl_bs", "lvl_thr"):
+            setattr(d, k, a[k].ctypes.data)
+        d.n_levels = a["K"]
+        self._ck(self._lib.swb_sim_set_dynamic(self._h, C.byref(d)))
 
     def begin(self):
         self._ck(self._lib.swb_sim_begin(self._h, self.scn.ctypes.data, self.status.ctypes.data))
@@ -181,7 +218,7 @@ class ShockwaveEnsemble:
     shockwave_config json keys: future_rounds, k, lambda, rhomax, log_approximation_bases, ...) per scenario."""
 
     def __init__(self, trace, profiles, config, scenarios, ngpus, time_per_iteration=120, device=0,
-                 scheduler_kwargs=None):
+                 scheduler_kwargs=None, dynamic=None):
         if float(trace["arrival"][0]) != 0.0:
             # the reference's loop iterates `_scheduled_jobs_in_current_round = None` when the first round does not
             # start at t = 0 (scheduler.py:359, :2273-2277): its shockwave traces all start at 0
@@ -190,6 +227,8 @@ class ShockwaveEnsemble:
         self.tpi = time_per_iteration
         self.S, self.J = len(scenarios), len(trace["arrival"])
         self.sim = DeviceSim(trace, self.S, ngpus, time_per_iteration, time_per_iteration, device)
+        if dynamic is not None:                      # build_dynamic_tables(): accordion / gns jobs
+            self.sim.set_dynamic(dynamic)
         self.scheds = []
         for ov in scenarios:
             cfg = dict(config)

@@ -21,14 +21,15 @@ from oracle import ref_harness as rh            # noqa: E402
 REL = "traces/reproduce/static120.trace"
 
 
-def stage_static_trace(scratch, keep=None):
+def stage_static_trace(scratch, keep=None, static=True):
     dst = rh.prepare_tree(scratch)
     with open(os.path.join(dst, rh.CANONICAL_TRACE)) as f, open(os.path.join(dst, REL), "w") as g:
         for i, line in enumerate(f):
             if keep is not None and i >= keep:
                 break
             p = line.rstrip("\n").split("\t")
-            p[7] = "static"
+            if static:
+                p[7] = "static"
             g.write("\t".join(p) + "\n")
     return dst
 

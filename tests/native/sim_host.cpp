@@ -10,12 +10,20 @@ using namespace swb::sim;
 struct HostSim {
   int J;
   std::vector<double> arrival, thr, dur15;
-  std::vector<long long> total, spe;
+  std::vector<long long> total, spe, ds;
   std::vector<int> sf, bs;
   std::vector<unsigned char> status, ranprev;
   std::vector<long long> steps_run, nsteps;
   std::vector<double> run_time, latest, jct, fin, tl_ns, thr_meas;
   std::vector<int> tl_prev, tl_end, epoch;
+  std::vector<unsigned char> running, flag, fails;
+  std::vector<int> cbs;
+  std::vector<long long> ctotal, cspe;
+  std::vector<double> cthr;
+  // dynamic tables
+  std::vector<int> mode, bs_max, bs_min, bs_big, orig_locked, acc_skip, pattern, lvl_bs;
+  std::vector<long long> pat_off;
+  std::vector<double> lvl_thr;
   Scn scn;
   double sd[1];
   long long si[1];
@@ -29,7 +37,7 @@ extern "C" void *sim_host_create(int J, const double *arrival, const long long *
   HostSim *h = new HostSim;
   h->J = J;
   h->arrival.assign(arrival, arrival + J); h->thr.assign(thr, thr + J); h->total.assign(total, total + J);
-  h->sf.assign(sf, sf + J); h->bs.assign(bs, bs + J);
+  h->sf.assign(sf, sf + J); h->bs.assign(bs, bs + J); h->ds.assign(dataset_len, dataset_len + J);
   h->dur15.resize(J); h->spe.resize(J);
   for (int j = 0; j < J; ++j) {
     h->dur15[j] = (double)(long long)(duration[j] * 1.5);
@@ -38,12 +46,32 @@ extern "C" void *sim_host_create(int J, const double *arrival, const long long *
   h->status.resize(J); h->ranprev.resize(J); h->steps_run.resize(J); h->nsteps.resize(J);
   h->run_time.resize(J); h->latest.resize(J); h->jct.resize(J); h->fin.resize(J); h->tl_ns.resize(J); h->thr_meas.resize(J);
   h->tl_prev.resize(J); h->tl_end.resize(J); h->epoch.resize(J);
-  h->T = Trace{J, h->arrival.data(), h->total.data(), h->sf.data(), h->thr.data(), h->dur15.data(), h->bs.data(), h->spe.data()};
+  h->running.resize(J); h->flag.resize(J); h->fails.resize(J); h->cbs.resize(J); h->ctotal.resize(J); h->cspe.resize(J);
+  h->cthr.resize(J);
+  h->T = Trace{};
+  h->T.J = J; h->T.arrival = h->arrival.data(); h->T.total = h->total.data(); h->T.sf = h->sf.data();
+  h->T.thr = h->thr.data(); h->T.dur15 = h->dur15.data(); h->T.bs = h->bs.data(); h->T.spe = h->spe.data(); h->T.ds = h->ds.data();
   h->X = State{h->status.data(), h->ranprev.data(), h->steps_run.data(), h->nsteps.data(), h->run_time.data(),
                h->latest.data(), h->jct.data(), h->fin.data(), h->tl_ns.data(), h->thr_meas.data(), h->tl_prev.data(),
-               h->tl_end.data(), h->epoch.data()};
+               h->tl_end.data(), h->epoch.data(), h->running.data(), h->flag.data(), h->fails.data(), h->cbs.data(),
+               h->ctotal.data(), h->cspe.data(), h->cthr.data()};
   h->sh = Shared{h->sd, h->si};
   return h;
+}
+
+extern "C" void sim_host_set_dynamic(void *p, const int *mode, const int *bs_max, const int *bs_min, const int *bs_big,
+                                     const int *orig_locked, const int *acc_skip, const long long *pat_off,
+                                     const int *pattern, int K, const int *lvl_bs, const double *lvl_thr) {
+  HostSim *h = (HostSim *)p;
+  const int J = h->J;
+  h->mode.assign(mode, mode + J); h->bs_max.assign(bs_max, bs_max + J); h->bs_min.assign(bs_min, bs_min + J);
+  h->bs_big.assign(bs_big, bs_big + J); h->orig_locked.assign(orig_locked, orig_locked + J);
+  h->acc_skip.assign(acc_skip, acc_skip + J); h->pat_off.assign(pat_off, pat_off + J + 1);
+  h->pattern.assign(pattern, pattern + pat_off[J]); h->pattern.push_back(0);
+  h->lvl_bs.assign(lvl_bs, lvl_bs + (size_t)J * K); h->lvl_thr.assign(lvl_thr, lvl_thr + (size_t)J * K);
+  h->T.mode = h->mode.data(); h->T.bs_max = h->bs_max.data(); h->T.bs_min = h->bs_min.data(); h->T.bs_big = h->bs_big.data();
+  h->T.orig_locked = h->orig_locked.data(); h->T.acc_skip = h->acc_skip.data(); h->T.pat_off = h->pat_off.data();
+  h->T.pattern = h->pattern.data(); h->T.K = K; h->T.lvl_bs = h->lvl_bs.data(); h->T.lvl_thr = h->lvl_thr.data();
 }
 
 extern "C" void sim_host_begin(void *p, Scn *out) {

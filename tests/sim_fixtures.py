@@ -29,6 +29,7 @@ def host_sim_lib():
     lib.sim_host_create.restype = C.c_void_p
     lib.sim_host_create.argtypes = [C.c_int] + [C.c_void_p] * 7
     lib.sim_host_begin.argtypes = [C.c_void_p, C.POINTER(Scn)]
+    lib.sim_host_set_dynamic.argtypes = [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 2
     lib.sim_host_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.POINTER(Scn)] + [C.c_void_p] * 5
     lib.sim_host_results.argtypes = [C.c_void_p] * 4
     lib.sim_host_destroy.argtypes = [C.c_void_p]
@@ -49,6 +50,13 @@ class HostSim:
         self.scn = Scn()
         self.status = np.zeros(J, np.uint8); self.epoch = np.zeros(J, np.int32); self.tl_ns = np.zeros(J)
         self.tl_end = np.zeros(J, np.int32); self.thr_meas = np.zeros(J)
+
+    def set_dynamic(self, dyn):
+        from shockwave_b200.simulate import pack_dynamic_tables
+        a = self._dyn = pack_dynamic_tables(dyn, self.J)
+        p = lambda k: a[k].ctypes.data
+        self.lib.sim_host_set_dynamic(self.h, p("mode"), p("bs_max"), p("bs_min"), p("bs_big"), p("orig_locked"),
+                                      p("acc_skip"), p("pat_off"), p("pattern"), a["K"], p("lvl_bs"), p("lvl_thr"))
 
     def begin(self):
         self.lib.sim_host_begin(self.h, C.byref(self.scn))
@@ -134,6 +142,10 @@ class HostDeviceSim:
         self.epoch = np.zeros((self.S, self.J), np.int32)
         self.tl_ns = np.zeros((self.S, self.J))
         self.tl_end = np.full((self.S, self.J), -1, np.int32)
+
+    def set_dynamic(self, dyn):
+        for m in self.sims:
+            m.set_dynamic(dyn)
 
     def _pull(self, s, z):
         for k in ("now", "round_start", "round_end", "rounds", "remaining", "n_active", "done", "err"):

@@ -100,9 +100,12 @@ def test_step_by_step_against_the_restatement(J, ngpus, gap):
 def test_argument_checks():
     from shockwave_b200.simulate import DeviceSim
     tr = sf_.random_trace(8, 1)
-    bad = dict(tr, adaptation_mode=np.array([0, 0, 1, 0, 0, 0, 0, 0]))
-    with pytest.raises(RuntimeError, match="static"):
-        DeviceSim(bad, 1, 4)
+    dynamic = DeviceSim(dict(tr, adaptation_mode=np.array([0, 0, 1, 0, 0, 0, 0, 0])), 1, 4)
+    with pytest.raises(RuntimeError, match="swb_sim_set_dynamic"):
+        dynamic.begin()                               # accordion job, no tables: refused, never run as a static job
+    dynamic.close()
+    with pytest.raises(RuntimeError, match="adaptation_mode"):
+        DeviceSim(dict(tr, adaptation_mode=np.full(8, 7)), 1, 4)
     with pytest.raises(RuntimeError, match="non-decreasing"):
         DeviceSim(dict(tr, arrival=tr["arrival"][::-1].copy()), 1, 4)
     sim = DeviceSim(tr, 1, 1)
@@ -112,10 +115,42 @@ def test_argument_checks():
     sim.close()
 
 
+@pytest.mark.parametrize("name", ["fifo_32", "max_min_fairness_32", "max_min_fairness_12"])
+def test_replay_of_the_reference_records_dynamic_trace(name):
+    """The canonical trace AS SHIPPED (59 accordion + 57 gns + 4 static jobs): batch-size rescaling from tables, the
+    micro-task failure branch; completion times, makespan, rounds and the timeline sums equal the reference's records."""
+    from shockwave_b200.simulate import DeviceSim
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "sim_dynamic_pins.json")))
+    rec, dyn = d[name], d["fifo_32"]["dyn"]
+    tr = dict(sim_loop.trace_arrays(rec), adaptation_mode=np.asarray(dyn["mode"]))
+    J = len(rec["arrival"])
+    sim = DeviceSim(tr, 3, rec["ngpus"], rec["time_per_iteration"])
+    sim.set_dynamic(dyn)
+    sched = _mask(rec["per_round_schedule"], J)
+    scn = sim.replay(sched)
+    res = sim.results()
+    want = np.array([rec["jct"][str(j)] for j in range(J)])
+    for s in range(3):
+        assert scn["err"][s] == 0 and scn["done"][s] == 1
+        assert scn["rounds"][s] == rec["rounds"] and scn["now"][s] == rec["makespan"]
+        assert np.array_equal(res["jct"][s], want)
+    sim2 = DeviceSim(tr, 1, rec["ngpus"], rec["time_per_iteration"])
+    sim2.set_dynamic(dyn)
+    sim2.begin()
+    for r in range(len(sched)):
+        z = sim2.step(sched[r][None, :])
+    assert z["done"].all() and np.array_equal(sim2.results()["jct"][0], want)
+    for j in range(J):
+        ns, end = sf_.timeline_summary([tuple(e) for e in rec["timeline"][str(j)]], 120.0)
+        assert sim2.tl_ns[0, j] == ns and sim2.tl_end[0, j] == end
+    sim.close(); sim2.close()
+
+
 @pytest.mark.reference
 @pytest.mark.skipif(not rh.reference_available(), reason="needs the (staged) reference simulator")
-def test_shockwave_ensemble_against_the_reference_loop():
-    """Static 120-job trace, 32 GPUs.  (a) the UNMODIFIED reference loop drives the product's ShockwaveScheduler;
+@pytest.mark.parametrize("static", [True, False])
+def test_shockwave_ensemble_against_the_reference_loop(static):
+    """The 120-job trace on 32 GPUs, with every job static and as shipped (accordion / gns jobs).  (a) the UNMODIFIED reference loop drives the product's ShockwaveScheduler;
     (b) ShockwaveEnsemble runs the same scenario + two what-ifs on the device loop.  Same kernels, same inputs: the
     scenario equal to (a) must land on the same end-to-end metrics (tolerance 1 % for solver-level tie-breaks; the
     exact-equality flags are recorded in gpurun_out/sim_ensemble.json)."""
@@ -123,10 +158,10 @@ def test_shockwave_ensemble_against_the_reference_loop():
     from shockwave_b200.simulate import ShockwaveEnsemble
     from tests.golden import make_sim_pins as pins
     scratch = tempfile.mkdtemp(prefix="swens_")
-    dst = pins.stage_static_trace(scratch)
+    dst = pins.stage_static_trace(scratch, static=static)
 
     def extract(sched, jobs, arrival_times):
-        rec = pins.extract(sched, jobs, arrival_times)
+        rec = (pins.extract if static else pins.extract_dynamic)(sched, jobs, arrival_times)
         rec["profiles"] = [dict(p) for p in sched._profiles[:len(jobs)]]
         return rec
     t0 = time.perf_counter()
@@ -138,7 +173,8 @@ def test_shockwave_ensemble_against_the_reference_loop():
     tr = {k: np.asarray(rec[k]) for k in ("arrival", "total_steps", "scale_factor", "throughput", "duration", "batch_size",
                                           "dataset_len")}
     scen = [{}, {"k": cfg["k"] * 10}, {"lambda": cfg["lambda"] * 2}, {"future_rounds": cfg["future_rounds"] + 10}]
-    ens = ShockwaveEnsemble(tr, rec["profiles"], cfg, scen, ngpus=32, time_per_iteration=120)
+    ens = ShockwaveEnsemble(tr, rec["profiles"], cfg, scen, ngpus=32, time_per_iteration=120,
+                            dynamic=None if static else rec["dyn"])
     t0 = time.perf_counter()
     out = ens.run()
     t_ens = time.perf_counter() - t0
@@ -151,8 +187,12 @@ def test_shockwave_ensemble_against_the_reference_loop():
                resolves=out["resolves"].tolist(),
                schedule_identical=bool(out["per_round_schedule"][0] == want_sched),
                jct_identical=bool(np.array_equal(out["jct"][0], want_jct)))
+    row["trace"] = "canonical 120-job trace, every job static" if static else "canonical 120-job trace as shipped (dynamic)"
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(row, open(os.path.join(ROOT, "gpurun_out", "sim_ensemble.json"), "w"), indent=1)
+    path = os.path.join(ROOT, "gpurun_out", "sim_ensemble.json")
+    rows = json.load(open(path)) if os.path.exists(path) else []
+    rows = [r for r in (rows if isinstance(rows, list) else []) if r.get("trace") != row["trace"]] + [row]
+    json.dump(rows, open(path, "w"), indent=1)
     assert np.isfinite(out["jct"]).all()
     assert abs(out["makespan"][0] - ref["makespan"]) <= 0.01 * ref["makespan"]
     assert abs(out["avg_jct"][0] - ref["avg_jct"]) <= 0.01 * ref["avg_jct"]

@@ -141,3 +141,59 @@ def test_dynamic_replay_reproduces_the_reference(name):
     for j in range(len(rec["arrival"])):
         assert out["jct"][j] == rec["jct"][str(j)], j
         assert out["timeline"][j] == [(r, t, b) for r, t, b in rec["timeline"][str(j)]], j
+
+
+def run_host_dyn(lib, rec, dyn, select):
+    tr = sim_loop.trace_arrays(rec)
+    sim = sf_.HostSim(lib, tr, rec["ngpus"], rec["time_per_iteration"], 120.0)
+    sim.set_dynamic(dyn)
+    scn = sim.begin()
+    status = (tr["arrival"] <= scn.now).astype(np.uint8)
+    per_round, eps = [], []
+    c = 0
+    while not scn.done:
+        active = [int(j) for j in np.flatnonzero(status == 1)]
+        chosen = [j for j in select(c, scn.now, active) if status[j] == 1]
+        per_round.append(sorted(chosen))
+        scn = sim.step(chosen)
+        status = sim.status.copy()
+        eps.append(sim.epoch.copy())
+        c += 1
+    jct, steps_run, run_time = sim.results()
+    return dict(makespan=scn.now, rounds=scn.rounds, err=scn.err, jct=jct, steps_run=steps_run, per_round_schedule=per_round,
+                tl_ns=sim.tl_ns.copy(), tl_end=sim.tl_end.copy(), epochs=eps)
+
+
+@pytest.mark.parametrize("name", ["fifo_32", "max_min_fairness_32", "max_min_fairness_12"])
+def test_device_loop_source_on_the_canonical_dynamic_trace(host_lib, name):
+    """Host build of sim_core.cuh with the dynamic tables == the reference's records on the trace as shipped (59
+    accordion + 57 gns jobs; a ResNet-50 job ends through the micro-task failure branch)."""
+    d, dyn = load_dynamic()
+    rec = d[name]
+    sched = rec["per_round_schedule"]
+    host = run_host_dyn(host_lib, rec, dyn, lambda c, now, active: sched[c])
+    assert host["err"] == 0 and host["rounds"] == rec["rounds"] and host["makespan"] == rec["makespan"]
+    for j in range(len(rec["arrival"])):
+        assert host["jct"][j] == rec["jct"][str(j)], j
+        tl = [tuple(e) for e in rec["timeline"][str(j)]]
+        ns, end = sf_.timeline_summary(tl, 120.0)
+        assert host["tl_ns"][j] == ns and host["tl_end"][j] == end, j
+
+
+def test_device_loop_source_dynamic_random_policy(host_lib):
+    """Another schedule than the recorded ones (random gang selection on 16 GPUs): host build == restatement, including
+    the epoch progress handed to the shockwave hook after every round."""
+    d, dyn = load_dynamic()
+    rec = dict(d["fifo_32"], ngpus=16)
+    sel = sf_.random_policy(rec, 16, 3)
+    seen = {}
+    ora = sim_loop.run(rec, sel, tpi=120.0, dyn=dyn, on_round=lambda c, now, info: seen.__setitem__(c, info["epoch"]))
+    host = run_host_dyn(host_lib, rec, dyn, sel)
+    assert host["err"] == 0 and ora["errs"] == []
+    assert host["rounds"] == ora["rounds"] and host["makespan"] == ora["makespan"]
+    assert host["per_round_schedule"] == ora["per_round_schedule"]
+    assert np.array_equal(host["jct"], np.array(ora["jct"]), equal_nan=True)
+    assert np.array_equal(host["steps_run"], np.array(ora["steps_run"]))
+    for c, ep in seen.items():
+        for j, e in ep.items():
+            assert host["epochs"][c - 1][j] == (-1 if e is None else e), (c, j)

@@ -17,20 +17,20 @@ from tests import sim_fixtures as sf_
 pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="staged reference not present")
 
 
-@pytest.mark.parametrize("keep,ngpus", [(24, 8), (60, 16)])
-def test_ensemble_driver_equals_the_reference_loop(monkeypatch, keep, ngpus):
+@pytest.mark.parametrize("keep,ngpus,static", [(24, 8, True), (60, 16, True), (60, 16, False), (120, 32, False)])
+def test_ensemble_driver_equals_the_reference_loop(monkeypatch, keep, ngpus, static):
     if sf_.host_sim_lib() is None:
         pytest.skip("g++ not available")
     from shockwave_b200 import simulate as sim
     from tests.golden import make_sim_pins as pins
     scratch = tempfile.mkdtemp(prefix="swens_")
-    dst = pins.stage_static_trace(scratch, keep=keep)
+    dst = pins.stage_static_trace(scratch, keep=keep, static=static)
     Rule = sf_.make_rule_scheduler_cls()
     ref_log = []
     Rule.log = ref_log
 
     def extract(sched, jobs, arrival_times):
-        rec = pins.extract(sched, jobs, arrival_times)
+        rec = (pins.extract if static else pins.extract_dynamic)(sched, jobs, arrival_times)
         rec["profiles"] = [dict(p) for p in sched._profiles[:len(jobs)]]
         return rec
     ref = rh.simulate("shockwave", shockwave_scheduler_cls=Rule, trace=pins.REL, scratch=scratch,
@@ -45,7 +45,7 @@ def test_ensemble_driver_equals_the_reference_loop(monkeypatch, keep, ngpus):
     tr = {k: np.asarray(rec[k]) for k in ("arrival", "total_steps", "scale_factor", "throughput", "duration", "batch_size",
                                           "dataset_len")}
     ens = sim.ShockwaveEnsemble(tr, rec["profiles"], cfg, [{}, {}, {"future_rounds": cfg["future_rounds"] + 3}],
-                                ngpus=ngpus, time_per_iteration=120)
+                                ngpus=ngpus, time_per_iteration=120, dynamic=None if static else rec["dyn"])
     Rule.log = None
     out = ens.run()
     want = [sorted(int(k) for k in rnd.keys()) for rnd in ref["per_round_schedule"]]
