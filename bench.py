@@ -684,6 +684,20 @@ def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):
     out["gavel_get_allocation_ms_J2048"] = pol_ms
 
     # ---- packing policies (space sharing): LPs over (job combination x worker type) columns on swb_lp_solve ----
+    try:
+        out["packed_get_allocation_ms"] = bench_packed(GP)
+    except Exception as e:            # an auxiliary leg: never take the headline down with it
+        out["packed_get_allocation_ms"] = {"error": repr(e)}
+
+    # ---- simulator round loop (SURVEY 8f-4): what-if replays of the reference's recorded 643-round schedule ----
+    try:
+        out["sim_round_loop"] = bench_sim_loop(local)
+    except Exception as e:            # an auxiliary leg: never take the headline down with it
+        out["sim_round_loop"] = {"error": repr(e)}
+    return out
+
+
+def bench_packed(GP):
     from shockwave_b200 import packing as PK
     from tests.packing_fixtures import instance as packed_instance
     pk_ms = {}
@@ -699,15 +713,10 @@ def run_extras(args, eng, dev, dist, world, rank, local, est, flush, W, pbs):
             for _ in range(3):
                 call()
             pk_ms[f"{name}_{ns}jobs_{len(thr_p)}combinations"] = (time.perf_counter() - t0) / 3 * 1e3
-        pk_ms[f"simplex_pivots_{ns}jobs"] = int(PK._max_min.last_stats[:, 0].max())
-    out["packed_get_allocation_ms"] = pk_ms
-
-    # ---- simulator round loop (SURVEY 8f-4): what-if replays of the reference's recorded 643-round schedule ----
-    try:
-        out["sim_round_loop"] = bench_sim_loop(local)
-    except Exception as e:            # an auxiliary leg: never take the headline down with it
-        out["sim_round_loop"] = {"error": repr(e)}
-    return out
+        stats = getattr(getattr(PK, "_max_min", None), "last_stats", None)
+        if stats is not None:
+            pk_ms[f"simplex_pivots_{ns}jobs"] = int(np.asarray(stats)[:, 0].max())
+    return pk_ms
 
 
 def bench_sim_loop(device):
