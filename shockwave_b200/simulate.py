@@ -294,7 +294,52 @@ class ShockwaveEnsemble:
         res = sim.results()
         res.update(makespan=scn["now"].copy(), rounds=scn["rounds"].copy(), per_round_schedule=self.per_round_schedule,
                    resolves=self.resolves.copy(), avg_jct=np.nanmean(res["jct"], axis=1))
+        self.last = res
         return res
+
+    def result_dicts(self, res=None, trace_file=None):
+        """One dict per scenario with the keys of the result pickle `simulate_scheduler_with_trace.py` writes
+        (scripts/drivers/simulate_scheduler_with_trace.py:128-151), so `aggregate_result.py` / `plotting.py` can read
+        what a sweep produced.  Filled: makespan, avg_jct, geometric / harmonic mean (scheduler.py:2779-2840),
+        jct_list, finish_time_fairness_list (:2865-2925: completion time / (isolated run time x max(1, jobs / GPUs)),
+        rounded to 5 digits), cluster_util (GPU-seconds used / (GPUs x makespan): the mean of the reference's per-worker
+        figures before its per-worker rounding), per_round_schedule (job ids per round; no worker ids), job_run_time,
+        time_per_iteration.  Absent: everything that needs worker identities (utilization_list, envy lists, lease
+        extension counts) — the device loop does not assign worker ids."""
+        res = self.last if res is None else res
+        J = self.J
+        iso = np.array([sum(p["duration_every_epoch"]) for p in self.profiles[:J]], dtype=np.float64)
+        contention = max(1.0, J / self.ngpus)
+        sf = np.asarray(self.trace["scale_factor"], dtype=np.float64)
+        out = []
+        for s in range(self.S):
+            jct = res["jct"][s]
+            done = np.isfinite(jct)
+            jl = [float(v) for v in jct[done]]
+            ftf = [round(float(jct[j]) / (float(iso[j]) * contention), 5) for j in range(J) if done[j]]
+            out.append({
+                "trace_file": trace_file, "policy": "shockwave", "scenario": s,
+                "makespan": float(res["makespan"][s]), "avg_jct": float(np.mean(jl)) if jl else None,
+                "geometric_mean_jct": float(np.exp(np.mean(np.log(jl)))) if jl else None,
+                "harmonic_mean_jct": float(len(jl) / np.sum(1.0 / np.asarray(jl))) if jl else None,
+                "jct_list": jl, "finish_time_fairness_list": ftf,
+                "cluster_util": float((sf * res["run_time"][s]).sum() / (self.ngpus * res["makespan"][s])),
+                "per_round_schedule": [{j: None for j in rnd} for rnd in res["per_round_schedule"][s]],
+                "job_run_time": {j: float(res["run_time"][s, j]) for j in range(J)},
+                "time_per_iteration": self.tpi})
+        return out
+
+    def write_result_pickles(self, directory, res=None, trace_file=None, prefix="shockwave_scenario"):
+        import os
+        import pickle
+        os.makedirs(directory, exist_ok=True)
+        paths = []
+        for d in self.result_dicts(res, trace_file):
+            path = os.path.join(directory, f"{prefix}_{d['scenario']}.pickle")
+            with open(path, "wb") as f:
+                pickle.dump(d, f)
+            paths.append(path)
+        return paths
 
 
 # ---- dynamic adaptation (accordion / gns batch-size rescaling) as tables -------------------------------------------

@@ -55,3 +55,12 @@ def test_ensemble_driver_equals_the_reference_loop(monkeypatch, keep, ngpus, sta
         for j in range(keep):
             assert out["jct"][s, j] == rec["jct"][str(j)]
     assert np.isfinite(out["jct"][2]).all()
+    # the result dict of a scenario against what the reference computes from its own run (scheduler.py:2779-2925, :3037-3058)
+    d = ens.result_dicts()[0]
+    assert d["finish_time_fairness_list"] == list(ref["finish_time_fairness_list"])
+    assert d["jct_list"] == [rec["jct"][str(j)] for j in range(keep)]
+    assert d["avg_jct"] == pytest.approx(ref["avg_jct"], rel=1e-12) and d["makespan"] == ref["makespan"]
+    assert d["cluster_util"] == pytest.approx(float(ref["cluster_util"]), abs=2e-5)
+    paths = ens.write_result_pickles(os.path.join(scratch, "results"))
+    import pickle
+    assert pickle.load(open(paths[1], "rb"))["makespan"] == ref["makespan"]
