@@ -415,3 +415,36 @@ def build_dynamic_tables(models, modes, trace, throughput_of, gns_pattern):
         else:
             out["pattern"].append([])
     return out
+
+
+# ---- several GPUs: what-if scenarios are independent, so they shard with no data-path collective ----------------------
+def shard_scenarios(n_scenarios, rank, world):
+    """Indices of the scenarios rank `rank` runs (round-robin: neighbouring sweep points usually cost alike)."""
+    return list(range(rank, n_scenarios, world))
+
+
+def run_sharded(trace, profiles, config, scenarios, ngpus, rank=0, world=1, gather=None, device=None, **kw):
+    """One process per GPU: every rank runs ShockwaveEnsemble on its slice of `scenarios` (device = its GPU), then the
+    small per-scenario results are exchanged with `gather` (e.g. `lambda obj: all_gather_object(...)` over NCCL/gloo —
+    results only, nothing on the data path).  Returns, on every rank, the result dict in the ORIGINAL scenario order."""
+    mine = shard_scenarios(len(scenarios), rank, world)
+    part = None
+    if mine:
+        ens = ShockwaveEnsemble(trace, profiles, config, [scenarios[i] for i in mine], ngpus,
+                                device=rank if device is None else device, **kw)
+        r = ens.run()
+        part = dict(index=mine, makespan=r["makespan"], rounds=r["rounds"], jct=r["jct"], avg_jct=r["avg_jct"],
+                    resolves=r["resolves"], per_round_schedule=r["per_round_schedule"], run_time=r["run_time"])
+    parts = [part] if gather is None else gather(part)
+    S, J = len(scenarios), len(trace["arrival"])
+    out = dict(makespan=np.full(S, np.nan), rounds=np.zeros(S, np.int64), jct=np.full((S, J), np.nan),
+               avg_jct=np.full(S, np.nan), resolves=np.zeros(S, np.int64), per_round_schedule=[None] * S,
+               run_time=np.zeros((S, J)))
+    for p in parts:
+        if p is None:
+            continue
+        for k, i in enumerate(p["index"]):
+            for key in ("makespan", "rounds", "jct", "avg_jct", "resolves", "run_time"):
+                out[key][i] = p[key][k]
+            out["per_round_schedule"][i] = p["per_round_schedule"][k]
+    return out
