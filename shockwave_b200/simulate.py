@@ -246,41 +246,52 @@ class ShockwaveEnsemble:
         self.per_round_schedule = [[] for _ in range(self.S)]
         self.resolves = np.zeros(self.S, np.int64)
 
-    def run(self, max_rounds=None):
+    def run(self, max_rounds=None, threads=None):
+        """threads: host threads the per-scenario scheduler calls of one round are spread over (default min(S, 8), 0 or 1
+        = serial).  Every scenario owns its scheduler, context and stream and ctypes drops the GIL inside the C call, so
+        the re-solves of different scenarios overlap on the GPU; results do not depend on it."""
         sim, S, J = self.sim, self.S, self.J
         scn = sim.begin()
         status = sim.status.copy()
         live_prev = np.zeros((S, J), bool)
         chosen_prev = np.zeros((S, J), np.uint8)
         ireopt = [0] * S
+        nthreads = min(S, 8) if threads is None else int(threads)
+        pool = None
+        if nthreads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(max_workers=nthreads)
         c = 0
+
+        def one(s):
+            sch = self.scheds[s]
+            live = status[s] == 1
+            if c > 0 and scn["now"][s] != 0.0:
+                # _update_shockwave_scheduler (scheduler.py:2270-2375) for the round that just ended
+                ran = np.flatnonzero((chosen_prev[s] == 1) & live)
+                sch.schedule_progress_batch(ran.tolist(), sim.epoch[s, ran], sim.tl_ns[s, ran], sim.tl_end[s, ran])
+                sch.increment_round_ptr()
+                ireopt[s] += 1
+                if ireopt[s] >= REOPT_ROUNDS:
+                    ireopt[s] = 0
+                    sch.set_resolve()
+            for j in np.flatnonzero(live_prev[s] & ~live).tolist():        # _remove_job -> remove_metadata
+                sch.remove_metadata(j)
+            for j in np.flatnonzero(live & ~live_prev[s]).tolist():        # add_job -> add_metadata
+                job = TraceJob(j, self.profiles[j], self.tpi)
+                job.timestamp_submit = float(scn["now"][s])                 # register_job_submit(current timestamp)
+                sch.add_metadata(j, job)
+            live_prev[s] = live
+            was = sch.resolve
+            ids = sch.round_schedule()
+            self.resolves[s] += bool(was)
+            return [j for j in ids if live[j]]
+
         while not scn["done"].all():
             chosen = np.zeros((S, J), np.uint8)
-            for s in range(S):
-                if scn["done"][s]:
-                    continue
-                sch = self.scheds[s]
-                live = status[s] == 1
-                if c > 0 and scn["now"][s] != 0.0:
-                    # _update_shockwave_scheduler (scheduler.py:2270-2375) for the round that just ended
-                    ran = np.flatnonzero((chosen_prev[s] == 1) & live)
-                    sch.schedule_progress_batch(ran.tolist(), sim.epoch[s, ran], sim.tl_ns[s, ran], sim.tl_end[s, ran])
-                    sch.increment_round_ptr()
-                    ireopt[s] += 1
-                    if ireopt[s] >= REOPT_ROUNDS:
-                        ireopt[s] = 0
-                        sch.set_resolve()
-                for j in np.flatnonzero(live_prev[s] & ~live).tolist():        # _remove_job -> remove_metadata
-                    sch.remove_metadata(j)
-                for j in np.flatnonzero(live & ~live_prev[s]).tolist():        # add_job -> add_metadata
-                    job = TraceJob(j, self.profiles[j], self.tpi)
-                    job.timestamp_submit = float(scn["now"][s])                 # register_job_submit(current timestamp)
-                    sch.add_metadata(j, job)
-                live_prev[s] = live
-                was = sch.resolve
-                ids = sch.round_schedule()
-                self.resolves[s] += bool(was)
-                ids = [j for j in ids if live[j]]
+            todo = [s for s in range(S) if not scn["done"][s]]
+            picked = list(pool.map(one, todo)) if pool is not None else [one(s) for s in todo]
+            for s, ids in zip(todo, picked):
                 chosen[s, ids] = 1
                 self.per_round_schedule[s].append(sorted(ids))
             scn = sim.step(chosen)
@@ -291,6 +302,8 @@ class ShockwaveEnsemble:
             c += 1
             if max_rounds is not None and c >= max_rounds:
                 break
+        if pool is not None:
+            pool.shutdown()
         res = sim.results()
         res.update(makespan=scn["now"].copy(), rounds=scn["rounds"].copy(), per_round_schedule=self.per_round_schedule,
                    resolves=self.resolves.copy(), avg_jct=np.nanmean(res["jct"], axis=1))
