@@ -448,6 +448,12 @@ int swb_sim_replay(swb_sim *sim, const uint8_t *schedule, int32_t R, int32_t per
 /* per-job results [S][J] (host, any may be NULL): completion time - arrival (NaN: not completed), steps run, cumulative
  * run time, throughput measured in the job's latest round. */
 int swb_sim_results(swb_sim *sim, double *jct, int64_t *steps_run, double *run_time, double *measured_throughput);
+/* what the Gavel mechanism between two rounds reads of every job [S][J] (host, any may be NULL): current total steps /
+ * throughput / batch size (they change with a rescale), execution time booked for the job's latest round and its finish
+ * time (`_job_time_so_far`, `_worker_time_so_far` accounting of `_done_callback`, scheduler.py:4660-4672, in completion
+ * order), failed attempts in a row (> 0: the latest round was a micro-task failure), ran = 1 for the jobs of that round. */
+int swb_sim_job_state(swb_sim *sim, int64_t *total_steps, double *throughput, int32_t *batch_size, double *exec_time,
+                      double *finish_time, uint8_t *failed_attempts, uint8_t *ran);
 
 /* Device time (CUDA events on the context's stream) of the two kernels of the latest solve pass and
  * the number of solve+place passes that call took (1 + packing-feedback re-solves). */

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(SIM_THREADS) sim_kernel(SimLaunch L) {
   sim::State X = L.X;
   X.status += o; X.ranprev += o; X.steps_run += o; X.nsteps += o; X.run_time += o; X.latest += o; X.jct += o;
   X.fin += o; X.tl_ns += o; X.thr_meas += o; X.tl_prev += o; X.tl_end += o; X.epoch += o;
-  X.running += o; X.flag += o; X.fails += o; X.cbs += o; X.ctotal += o; X.cspe += o; X.cthr += o;
+  X.running += o; X.flag += o; X.fails += o; X.cbs += o; X.ctotal += o; X.cspe += o; X.cthr += o; X.last_ex += o;
   sim::Shared sh{sd, si};
   sim::Scn *scn = L.scn + blockIdx.x;
   if (L.begin) sim::scenario_begin(L.T, X, scn, sh);
@@ -127,7 +127,7 @@ int swb_sim_create(int32_t device, const swb_sim_trace *tr, int32_t S, int32_t n
                o_rt = take(sj * 8), o_latest = take(sj * 8), o_jct = take(sj * 8), o_fin = take(sj * 8),
                o_tlns = take(sj * 8), o_tm = take(sj * 8), o_tlprev = take(sj * 4), o_tlend = take(sj * 4),
                o_epoch = take(sj * 4), o_running = take(sj), o_flag = take(sj), o_fails = take(sj), o_cbs = take(sj * 4),
-               o_ctotal = take(sj * 8), o_cspe = take(sj * 8), o_cthr = take(sj * 8),
+               o_ctotal = take(sj * 8), o_cspe = take(sj * 8), o_cthr = take(sj * 8), o_lastex = take(sj * 8),
                o_scn = take((size_t)S * sizeof(swb::sim::Scn));
   if (e == cudaSuccess) e = cudaMalloc(&m->arena, off);
   if (e != cudaSuccess) {
@@ -162,7 +162,7 @@ int swb_sim_create(int32_t device, const swb_sim_trace *tr, int32_t S, int32_t n
   m->X.tl_prev = (int *)(b + o_tlprev); m->X.tl_end = (int *)(b + o_tlend); m->X.epoch = (int *)(b + o_epoch);
   m->X.running = (unsigned char *)(b + o_running); m->X.flag = (unsigned char *)(b + o_flag);
   m->X.fails = (unsigned char *)(b + o_fails); m->X.cbs = (int *)(b + o_cbs); m->X.ctotal = (long long *)(b + o_ctotal);
-  m->X.cspe = (long long *)(b + o_cspe); m->X.cthr = (double *)(b + o_cthr);
+  m->X.cspe = (long long *)(b + o_cspe); m->X.cthr = (double *)(b + o_cthr); m->X.last_ex = (double *)(b + o_lastex);
   m->scn = (swb::sim::Scn *)(b + o_scn);
   *out = m;
   return 0;
@@ -300,6 +300,22 @@ int swb_sim_results(swb_sim *m, double *jct, int64_t *steps_run, double *run_tim
   if (steps_run) SCK(cudaMemcpyAsync(steps_run, m->X.steps_run, sj * 8, cudaMemcpyDeviceToHost, m->st));
   if (run_time) SCK(cudaMemcpyAsync(run_time, m->X.run_time, sj * 8, cudaMemcpyDeviceToHost, m->st));
   if (measured_throughput) SCK(cudaMemcpyAsync(measured_throughput, m->X.thr_meas, sj * 8, cudaMemcpyDeviceToHost, m->st));
+  SCK(cudaStreamSynchronize(m->st));
+  return 0;
+}
+
+int swb_sim_job_state(swb_sim *m, int64_t *total_steps, double *throughput, int32_t *batch_size, double *exec_time,
+                      double *finish_time, uint8_t *failed_attempts, uint8_t *ran) {
+  if (!m) return swb_set_error(SWB_ERR_ARG, "swb_sim_job_state: null handle");
+  SCK(cudaSetDevice(m->device));
+  const size_t sj = (size_t)m->S * m->J;
+  if (total_steps) SCK(cudaMemcpyAsync(total_steps, m->X.ctotal, sj * 8, cudaMemcpyDeviceToHost, m->st));
+  if (throughput) SCK(cudaMemcpyAsync(throughput, m->X.cthr, sj * 8, cudaMemcpyDeviceToHost, m->st));
+  if (batch_size) SCK(cudaMemcpyAsync(batch_size, m->X.cbs, sj * 4, cudaMemcpyDeviceToHost, m->st));
+  if (exec_time) SCK(cudaMemcpyAsync(exec_time, m->X.last_ex, sj * 8, cudaMemcpyDeviceToHost, m->st));
+  if (finish_time) SCK(cudaMemcpyAsync(finish_time, m->X.fin, sj * 8, cudaMemcpyDeviceToHost, m->st));
+  if (failed_attempts) SCK(cudaMemcpyAsync(failed_attempts, m->X.fails, sj, cudaMemcpyDeviceToHost, m->st));
+  if (ran) SCK(cudaMemcpyAsync(ran, m->X.ranprev, sj, cudaMemcpyDeviceToHost, m->st));
   SCK(cudaStreamSynchronize(m->st));
   return 0;
 }

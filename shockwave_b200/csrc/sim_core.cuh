@@ -96,6 +96,7 @@ struct State {            // [J] of ONE scenario
   int *cbs;
   long long *ctotal, *cspe;
   double *cthr;
+  double *last_ex;        // execution time booked for the job's latest round (the Gavel time accounting reads it)
 };
 
 struct Shared {           // SIM_NT entries each
@@ -225,7 +226,7 @@ SIM_HD void scenario_begin(const Trace &T, const State &X, Scn *scn, const Share
     X.run_time[j] = 0.0; X.latest[j] = NAN; X.jct[j] = NAN; X.fin[j] = 0.0; X.tl_ns[j] = 0.0; X.thr_meas[j] = 0.0;
     X.tl_prev[j] = 0; X.tl_end[j] = -1; X.epoch[j] = 0;
     X.running[j] = 0; X.flag[j] = 0; X.fails[j] = 0;
-    X.cbs[j] = T.bs[j]; X.ctotal[j] = T.total[j]; X.cspe[j] = T.spe[j]; X.cthr[j] = T.thr[j];
+    X.cbs[j] = T.bs[j]; X.ctotal[j] = T.total[j]; X.cspe[j] = T.spe[j]; X.cthr[j] = T.thr[j]; X.last_ex[j] = 0.0;
   }
   SIM_SYNC();
   const double now = T.arrival[0];
@@ -296,6 +297,7 @@ SIM_HD void scenario_step(const Trace &T, const State &X, Scn *scn, const unsign
         }
         X.latest[j] = X.fin[j];
         X.run_time[j] += ex;
+        X.last_ex[j] = ex;
         const bool over = X.run_time[j] > T.dur15[j];
         bool done;
         if (n <= 0 && ex <= 0.0) {                  // micro-task failure (scheduler.py:4497-4570): nothing is booked

@@ -84,6 +84,8 @@ def _lib():
         lib.swb_sim_replay.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         lib.swb_sim_results.argtypes = [C.c_void_p] * 5
         lib.swb_sim_set_dynamic.argtypes = [C.c_void_p, C.POINTER(SimDynamic)]
+        lib.swb_sim_job_state.argtypes = [C.c_void_p] * 8
+        lib.swb_sim_job_state.restype = C.c_int
         for f in ("swb_sim_set_dynamic", "swb_sim_create", "swb_sim_begin", "swb_sim_step", "swb_sim_replay", "swb_sim_results"):
             getattr(lib, f).restype = C.c_int
         _bound = True
@@ -167,6 +169,17 @@ class DeviceSim:
         jct = np.zeros((S, J)); steps = np.zeros((S, J), np.int64); rt = np.zeros((S, J)); tm = np.zeros((S, J))
         self._ck(self._lib.swb_sim_results(self._h, jct.ctypes.data, steps.ctypes.data, rt.ctypes.data, tm.ctypes.data))
         return dict(jct=jct, steps_run=steps, run_time=rt, measured_throughput=tm)
+
+    def job_state(self):
+        """Current total steps / throughput / batch size, execution and finish time of the latest round, failed attempts in
+        a row, ran-in-the-latest-round flag: [S][J] each (swb_sim_job_state)."""
+        S, J = self.S, self.J
+        out = dict(total_steps=np.zeros((S, J), np.int64), throughput=np.zeros((S, J)), batch_size=np.zeros((S, J), np.int32),
+                   exec_time=np.zeros((S, J)), finish_time=np.zeros((S, J)), failed_attempts=np.zeros((S, J), np.uint8),
+                   ran=np.zeros((S, J), np.uint8))
+        self._ck(self._lib.swb_sim_job_state(self._h, *[out[k].ctypes.data for k in (
+            "total_steps", "throughput", "batch_size", "exec_time", "finish_time", "failed_attempts", "ran")]))
+        return out
 
     def close(self):
         if self._h is not None:
@@ -461,3 +474,146 @@ def run_sharded(trace, profiles, config, scenarios, ngpus, rank=0, world=1, gath
                 out[key][i] = p[key][k]
             out["per_round_schedule"][i] = p["per_round_schedule"][k]
     return out
+
+
+# ---- Gavel policies on the device loop -----------------------------------------------------------------------------------
+class PolicyEnsemble:
+    """S what-ifs of one trace under the Gavel policies (one policy object per scenario, e.g.
+    `policies.get_policy("max_min_fairness")`, `("finish_time_fairness")`, ...): the round loop runs on the device
+    (swb_sim_step), `get_allocation()` and the priority -> selection -> worker-assignment step (swb_gavel_round) are the
+    device calls of policies.py / placement.py, and what the reference keeps in dicts between two rounds is kept here in
+    arrays, statement by statement:
+      * time accounting of `_done_callback` (scheduler.py:4660-4672): `_job_time_so_far`, `_worker_time_so_far`, added in
+        the reference's completion order (latest finish first, then job id) so the float sums are the same;
+      * `_update_priorities` (:3611-3636): when to reset the accounting and recompute the allocation
+        (`_need_to_update_allocation` after an arrival, a completion or a failed micro-task; at most once per
+        `minimum_time_between_allocation_resets`), `_reset_time_run_so_far` (:3498-3551) with its deficits;
+      * `_get_allocation_state` / `_compute_allocation` (:3205-3355): the arguments each policy family takes.
+    One worker type, single jobs (no packing).  Returns per-round schedules WITH worker ids, like the reference."""
+
+    def __init__(self, trace, policies, ngpus, time_per_iteration=120, device=0, dynamic=None, priority_weights=None,
+                 minimum_time_between_allocation_resets=1000, round_backend=None, worker_type="v100",
+                 other_worker_types=("k80", "p100")):
+        self.trace, self.policies, self.ngpus, self.tpi = trace, list(policies), int(ngpus), time_per_iteration
+        self.S, self.J = len(self.policies), len(trace["arrival"])
+        self.sim = DeviceSim(trace, self.S, ngpus, time_per_iteration, time_per_iteration, device)
+        if dynamic is not None:
+            self.sim.set_dynamic(dynamic)
+        self.min_reset = float(minimum_time_between_allocation_resets)
+        self.wt = worker_type
+        self.cluster_spec = {worker_type: self.ngpus, **{w: 0 for w in other_worker_types}}
+        self.pw = np.ones(self.J) if priority_weights is None else np.asarray(priority_weights, dtype=np.float64)
+        if round_backend is None:
+            from .placement import _DeviceBackend
+            round_backend = _DeviceBackend()
+        self.backend = round_backend
+        self.per_round_schedule = [[] for _ in range(self.S)]
+        self.allocations = np.zeros(self.S, np.int64)
+
+    def _allocation(self, s, live, now, st, steps_run):
+        """_get_allocation_state + _compute_allocation for scenario s -> alloc [J] (NaN = not in the allocation)."""
+        pol, wt = self.policies[s], self.wt
+        jobs = np.flatnonzero(live).tolist()
+        thr = {j: {wt: float(st["throughput"][s, j])} for j in jobs}
+        sf = {j: int(self.trace["scale_factor"][j]) for j in jobs}
+        pw = {j: float(self.pw[j]) for j in jobs}
+        since = {j: now - float(self.trace["arrival"][j]) for j in jobs}
+        remaining = {j: int(st["total_steps"][s, j] - steps_run[s, j]) for j in jobs}
+        name = pol.name
+        if name == "AlloX_Perf":
+            a = pol.get_allocation(thr, sf, since, remaining, [dict(r) for r in self.per_round_schedule[s]], self.cluster_spec)
+        elif name.startswith("FinishTimeFairness"):
+            a = pol.get_allocation(thr, sf, pw, since, remaining, self.cluster_spec)
+        elif name.startswith("Isolated"):
+            a = pol.get_allocation(thr, sf, self.cluster_spec)
+        elif name.startswith("MaxMinFairness"):
+            a = pol.get_allocation(thr, sf, pw, self.cluster_spec)
+        elif name.startswith("MinTotalDuration"):
+            a = pol.get_allocation(thr, sf, remaining, self.cluster_spec)
+        else:
+            a = pol.get_allocation(thr, sf, self.cluster_spec)
+        out = np.full(self.J, np.nan)
+        for j, row in (a or {}).items():
+            out[j] = row[wt]
+        self.allocations[s] += 1
+        return out
+
+    def run(self, max_rounds=None):
+        sim, S, J, G, half = self.sim, self.S, self.J, self.ngpus, self.tpi / 2.0
+        scn = sim.begin()
+        status = sim.status.copy()
+        live_prev = np.zeros((S, J), bool)
+        job_time = np.zeros((S, J)); deficit = np.zeros((S, J)); alloc = np.full((S, J), np.nan)
+        worker_time = np.zeros(S); last_reset = np.zeros(S); need_update = np.zeros(S, bool)
+        prev = [dict() for _ in range(S)]                  # job -> worker ids of the round before (lease extension)
+        sf_all = np.asarray(self.trace["scale_factor"], dtype=np.int32)
+        workers = [list(range(G))]
+        st = sim.job_state()
+        steps_run = np.zeros((S, J), np.int64)
+        c = 0
+        while not scn["done"].all():
+            chosen = np.zeros((S, J), np.uint8)
+            for s in range(S):
+                if scn["done"][s]:
+                    continue
+                now = float(scn["now"][s])
+                live = status[s] == 1
+                if c > 0:
+                    ran = np.flatnonzero(st["ran"][s])
+                    for j in sorted(ran.tolist(), key=lambda j: (-st["finish_time"][s, j], j)):
+                        if st["failed_attempts"][s, j] > 0:
+                            need_update[s] = True                              # scheduler.py:4569
+                        elif live_prev[s, j]:
+                            ex = float(st["exec_time"][s, j])                  # :4660-4672
+                            job_time[s, j] += ex
+                            worker_time[s] += ex
+                    if (live_prev[s] & ~live).any():
+                        need_update[s] = True                                  # _remove_job :903
+                new = live & ~live_prev[s]
+                if new.any():                                                   # add_job :738-744
+                    job_time[s, new] = half
+                    deficit[s, new] = 0.0
+                    alloc[s, new] = np.nan
+                    need_update[s] = True
+                live_prev[s] = live
+                # _update_priorities :3611-3636
+                since = now - last_reset[s]
+                if need_update[s] and (since >= self.min_reset or last_reset[s] == 0):
+                    jobs = np.flatnonzero(live)
+                    wsum = 0.0
+                    for j in jobs.tolist():                                     # _reset_time_run_so_far :3498-3551
+                        received = job_time[s, j] - half
+                        should = 0 if np.isnan(alloc[s, j]) else alloc[s, j] * since
+                        deficit[s, j] += should - received
+                        job_time[s, j] = half
+                        wsum += half
+                    worker_time[s] = wsum
+                    last_reset[s] = now
+                    alloc[s] = self._allocation(s, live, now, st, steps_run)
+                    need_update[s] = False
+                jobs = np.flatnonzero(live)
+                loc = {int(j): i for i, j in enumerate(jobs.tolist())}
+                pv = {loc[j]: (0, tuple(w)) for j, w in prev[s].items() if j in loc}
+                prio, sel, asg = self.backend.gavel_round(
+                    alloc[s, jobs][:, None], job_time[s, jobs][:, None], np.array([worker_time[s]]),
+                    st["throughput"][s, jobs][:, None], deficit[s, jobs][:, None], sf_all[jobs], np.array([G], np.int32), [0],
+                    workers, pv, isolated_plus=(self.policies[s].name == "Isolated_plus"),
+                    fifo=self.policies[s].name.startswith("FIFO"))
+                rnd = {int(jobs[i]): tuple(int(w) for w in ws) for i, ws in asg}
+                ids = list(rnd)                  # a selected job the allocation does not know yet gets no workers (:1363-1366)
+                prev[s] = rnd
+                chosen[s, ids] = 1
+                self.per_round_schedule[s].append({j: rnd[j] for j in ids})
+            scn = sim.step(chosen)
+            if (scn["err"] != 0).any():
+                raise RuntimeError(f"swb_sim_step: error flags {scn['err'].tolist()}")
+            status = sim.status.copy()
+            st = sim.job_state()
+            steps_run = sim.results()["steps_run"]
+            c += 1
+            if max_rounds is not None and c >= max_rounds:
+                break
+        res = sim.results()
+        res.update(makespan=scn["now"].copy(), rounds=scn["rounds"].copy(), per_round_schedule=self.per_round_schedule,
+                   allocations=self.allocations.copy(), avg_jct=np.nanmean(res["jct"], axis=1))
+        return res

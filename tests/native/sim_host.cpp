@@ -19,7 +19,7 @@ struct HostSim {
   std::vector<unsigned char> running, flag, fails;
   std::vector<int> cbs;
   std::vector<long long> ctotal, cspe;
-  std::vector<double> cthr;
+  std::vector<double> cthr, last_ex;
   // dynamic tables
   std::vector<int> mode, bs_max, bs_min, bs_big, orig_locked, acc_skip, pattern, lvl_bs;
   std::vector<long long> pat_off;
@@ -47,14 +47,14 @@ extern "C" void *sim_host_create(int J, const double *arrival, const long long *
   h->run_time.resize(J); h->latest.resize(J); h->jct.resize(J); h->fin.resize(J); h->tl_ns.resize(J); h->thr_meas.resize(J);
   h->tl_prev.resize(J); h->tl_end.resize(J); h->epoch.resize(J);
   h->running.resize(J); h->flag.resize(J); h->fails.resize(J); h->cbs.resize(J); h->ctotal.resize(J); h->cspe.resize(J);
-  h->cthr.resize(J);
+  h->cthr.resize(J); h->last_ex.resize(J);
   h->T = Trace{};
   h->T.J = J; h->T.arrival = h->arrival.data(); h->T.total = h->total.data(); h->T.sf = h->sf.data();
   h->T.thr = h->thr.data(); h->T.dur15 = h->dur15.data(); h->T.bs = h->bs.data(); h->T.spe = h->spe.data(); h->T.ds = h->ds.data();
   h->X = State{h->status.data(), h->ranprev.data(), h->steps_run.data(), h->nsteps.data(), h->run_time.data(),
                h->latest.data(), h->jct.data(), h->fin.data(), h->tl_ns.data(), h->thr_meas.data(), h->tl_prev.data(),
                h->tl_end.data(), h->epoch.data(), h->running.data(), h->flag.data(), h->fails.data(), h->cbs.data(),
-               h->ctotal.data(), h->cspe.data(), h->cthr.data()};
+               h->ctotal.data(), h->cspe.data(), h->cthr.data(), h->last_ex.data()};
   h->sh = Shared{h->sd, h->si};
   return h;
 }
@@ -94,6 +94,15 @@ extern "C" void sim_host_step(void *p, const unsigned char *chosen, int ngpus, d
 extern "C" void sim_host_results(void *p, double *jct, long long *steps_run, double *run_time) {
   HostSim *h = (HostSim *)p;
   for (int j = 0; j < h->J; ++j) { jct[j] = h->jct[j]; steps_run[j] = h->steps_run[j]; run_time[j] = h->run_time[j]; }
+}
+
+extern "C" void sim_host_job_state(void *p, long long *total, double *thr, int *bs, double *ex, double *fin,
+                                   unsigned char *fails, unsigned char *ran) {
+  HostSim *h = (HostSim *)p;
+  for (int j = 0; j < h->J; ++j) {
+    total[j] = h->ctotal[j]; thr[j] = h->cthr[j]; bs[j] = h->cbs[j]; ex[j] = h->last_ex[j]; fin[j] = h->fin[j];
+    fails[j] = h->fails[j]; ran[j] = h->ranprev[j];
+  }
 }
 
 extern "C" void sim_host_destroy(void *p) { delete (HostSim *)p; }

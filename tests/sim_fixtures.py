@@ -33,6 +33,7 @@ def host_sim_lib():
     lib.sim_host_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.POINTER(Scn)] + [C.c_void_p] * 5
     lib.sim_host_results.argtypes = [C.c_void_p] * 4
     lib.sim_host_destroy.argtypes = [C.c_void_p]
+    lib.sim_host_job_state.argtypes = [C.c_void_p] * 8
     return lib
 
 
@@ -69,6 +70,14 @@ class HostSim:
                                self.status.ctypes.data, self.epoch.ctypes.data, self.tl_ns.ctypes.data,
                                self.tl_end.ctypes.data, self.thr_meas.ctypes.data)
         return self.scn
+
+    def job_state(self):
+        J = self.J
+        o = dict(total_steps=np.zeros(J, np.int64), throughput=np.zeros(J), batch_size=np.zeros(J, np.int32),
+                 exec_time=np.zeros(J), finish_time=np.zeros(J), failed_attempts=np.zeros(J, np.uint8), ran=np.zeros(J, np.uint8))
+        self.lib.sim_host_job_state(self.h, *[o[k].ctypes.data for k in (
+            "total_steps", "throughput", "batch_size", "exec_time", "finish_time", "failed_attempts", "ran")])
+        return o
 
     def results(self):
         jct = np.zeros(self.J); sr = np.zeros(self.J, np.int64); rt = np.zeros(self.J)
@@ -177,6 +186,10 @@ class HostDeviceSim:
         r = [m.results() for m in self.sims]
         return dict(jct=np.stack([x[0] for x in r]), steps_run=np.stack([x[1] for x in r]),
                     run_time=np.stack([x[2] for x in r]), measured_throughput=np.stack([m.thr_meas for m in self.sims]))
+
+    def job_state(self):
+        parts = [m.job_state() for m in self.sims]
+        return {k: np.stack([p[k] for p in parts]) for k in parts[0]}
 
     def close(self):
         pass
