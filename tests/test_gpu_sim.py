@@ -213,3 +213,45 @@ def test_shockwave_ensemble_against_the_reference_loop(static):
     assert abs(out["makespan"][0] - ref["makespan"]) <= 0.01 * ref["makespan"]
     assert abs(out["avg_jct"][0] - ref["avg_jct"]) <= 0.01 * ref["avg_jct"]
     assert abs(int(out["rounds"][0]) - rec["rounds"]) <= 3
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not rh.reference_available(), reason="needs the (staged) reference simulator")
+@pytest.mark.parametrize("policy", ["max_min_fairness", "finish_time_fairness"])
+def test_policy_ensemble_against_the_reference_loop(policy):
+    """Gavel policies: (a) the unmodified reference loop with the product's policies and round step (GavelRoundMixin) on
+    the canonical trace as shipped; (b) PolicyEnsemble: same device calls, the loop and the mechanism's bookkeeping off
+    the reference's dicts.  Same inputs into the same kernels: the schedules must coincide (1 % tolerance on the
+    end-to-end metrics as the assertion, exactness recorded)."""
+    from shockwave_b200 import policies as P
+    from shockwave_b200.placement import GavelRoundMixin
+    from shockwave_b200.simulate import PolicyEnsemble
+    from tests.golden import make_sim_pins as pins
+    scratch = tempfile.mkdtemp(prefix="swpol_")
+    rh.prepare_tree(scratch)
+    t0 = time.perf_counter()
+    ref = rh.simulate(policy, policy_obj=P.get_policy(policy, solver="ECOS", seed=0), scratch=scratch, cluster="32:0:0",
+                      extract=pins.extract_dynamic, scheduler_mixin=GavelRoundMixin)
+    t_ref = time.perf_counter() - t0
+    rec = ref["extra"]
+    tr = {k: np.asarray(rec[k]) for k in ("arrival", "total_steps", "scale_factor", "throughput", "duration", "batch_size",
+                                          "dataset_len")}
+    ens = PolicyEnsemble(tr, [P.get_policy(policy, solver="ECOS", seed=0) for _ in range(2)], 32, dynamic=rec["dyn"])
+    t0 = time.perf_counter()
+    out = ens.run()
+    t_ens = time.perf_counter() - t0
+    want = [{int(k): tuple(v) for k, v in rnd.items()} for rnd in ref["per_round_schedule"]]
+    J = len(rec["arrival"])
+    want_jct = np.array([rec["jct"][str(j)] for j in range(J)])
+    row = dict(trace=f"canonical trace as shipped, {policy} (PolicyEnsemble)", reference_loop_s=round(t_ref, 2),
+               ensemble_s=round(t_ens, 2), scenarios=2, makespan_ref=ref["makespan"], makespan=out["makespan"].tolist(),
+               rounds_ref=rec["rounds"], rounds=out["rounds"].tolist(), allocations=out["allocations"].tolist(),
+               schedule_identical=bool(out["per_round_schedule"][0] == want),
+               jct_identical=bool(np.array_equal(out["jct"][0], want_jct)))
+    path = os.path.join(ROOT, "gpurun_out", "sim_ensemble.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    rows = json.load(open(path)) if os.path.exists(path) else []
+    json.dump([r for r in rows if r.get("trace") != row["trace"]] + [row], open(path, "w"), indent=1)
+    assert np.isfinite(out["jct"]).all()
+    assert abs(out["makespan"][0] - ref["makespan"]) <= 0.01 * ref["makespan"]
+    assert abs(np.mean(out["jct"][0]) - ref["avg_jct"]) <= 0.01 * ref["avg_jct"]
