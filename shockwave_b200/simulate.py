@@ -546,6 +546,8 @@ class PolicyEnsemble:
         job_time = np.zeros((S, J)); deficit = np.zeros((S, J)); alloc = np.full((S, J), np.nan)
         worker_time = np.zeros(S); last_reset = np.zeros(S); need_update = np.zeros(S, bool)
         prev = [dict() for _ in range(S)]                  # job -> worker ids of the round before (lease extension)
+        wtime = np.zeros((S, G))                           # _cumulative_worker_time_so_far
+        lease_ext = np.zeros(S, np.int64); lease_opp = np.zeros(S, np.int64)
         sf_all = np.asarray(self.trace["scale_factor"], dtype=np.int32)
         workers = [list(range(G))]
         st = sim.job_state()
@@ -553,22 +555,12 @@ class PolicyEnsemble:
         c = 0
         while not scn["done"].all():
             chosen = np.zeros((S, J), np.uint8)
-            for s in range(S):
-                if scn["done"][s]:
-                    continue
+            active = [s for s in range(S) if not scn["done"][s]]
+            for s in active:
                 now = float(scn["now"][s])
                 live = status[s] == 1
-                if c > 0:
-                    ran = np.flatnonzero(st["ran"][s])
-                    for j in sorted(ran.tolist(), key=lambda j: (-st["finish_time"][s, j], j)):
-                        if st["failed_attempts"][s, j] > 0:
-                            need_update[s] = True                              # scheduler.py:4569
-                        elif live_prev[s, j]:
-                            ex = float(st["exec_time"][s, j])                  # :4660-4672
-                            job_time[s, j] += ex
-                            worker_time[s] += ex
-                    if (live_prev[s] & ~live).any():
-                        need_update[s] = True                                  # _remove_job :903
+                if c > 0 and (live_prev[s] & ~live).any():
+                    need_update[s] = True                                      # _remove_job :903
                 new = live & ~live_prev[s]
                 if new.any():                                                   # add_job :738-744
                     job_time[s, new] = half
@@ -601,6 +593,8 @@ class PolicyEnsemble:
                     fifo=self.policies[s].name.startswith("FIFO"))
                 rnd = {int(jobs[i]): tuple(int(w) for w in ws) for i, ws in asg}
                 ids = list(rnd)                  # a selected job the allocation does not know yet gets no workers (:1363-1366)
+                lease_opp[s] += sum(1 for j in prev[s] if live[j])              # scheduler.py:2198-2213
+                lease_ext[s] += sum(1 for j, ws in rnd.items() if j in prev[s] and set(prev[s][j]) == set(ws))
                 prev[s] = rnd
                 chosen[s, ids] = 1
                 self.per_round_schedule[s].append({j: rnd[j] for j in ids})
@@ -610,10 +604,56 @@ class PolicyEnsemble:
             status = sim.status.copy()
             st = sim.job_state()
             steps_run = sim.results()["steps_run"]
+            for s in active:                                                    # the round's completion callbacks
+                ran = np.flatnonzero(st["ran"][s])
+                for j in sorted(ran.tolist(), key=lambda j: (-st["finish_time"][s, j], j)):
+                    if st["failed_attempts"][s, j] > 0:
+                        need_update[s] = True                                  # scheduler.py:4569
+                    else:
+                        ex = float(st["exec_time"][s, j])                      # :4660-4676
+                        job_time[s, j] += ex
+                        worker_time[s] += ex
+                        for w in prev[s].get(j, ()):
+                            wtime[s, w] += ex
             c += 1
             if max_rounds is not None and c >= max_rounds:
                 break
         res = sim.results()
         res.update(makespan=scn["now"].copy(), rounds=scn["rounds"].copy(), per_round_schedule=self.per_round_schedule,
-                   allocations=self.allocations.copy(), avg_jct=np.nanmean(res["jct"], axis=1))
+                   allocations=self.allocations.copy(), avg_jct=np.nanmean(res["jct"], axis=1),
+                   worker_time=wtime, num_lease_extensions=lease_ext, num_lease_extension_opportunities=lease_opp)
+        self.last = res
         return res
+
+    def result_dicts(self, isolated_durations, res=None, trace_file=None):
+        """One dict per scenario with the keys of the reference's result pickle
+        (scripts/drivers/simulate_scheduler_with_trace.py:128-151) — here WITH the worker-dependent ones: per-worker
+        utilisation (scheduler.py:3037-3058), lease-extension counts (:2198-2213, :3086-3107), `{job: worker ids}` per
+        round.  isolated_durations[j] = sum(profile["duration_every_epoch"]) (finish-time fairness, :2865-2925).
+        Absent: envy lists, the Themis variant of the fairness list, the throughput timeline."""
+        res = self.last if res is None else res
+        J, G = self.J, self.ngpus
+        contention = max(1.0, J / G)
+        out = []
+        for s in range(self.S):
+            jct = res["jct"][s]
+            done = np.isfinite(jct)
+            jl = [float(v) for v in jct[done]]
+            util = [round(float(t) / float(res["makespan"][s]), 5) for t in res["worker_time"][s]]
+            opp = int(res["num_lease_extension_opportunities"][s])
+            ext = int(res["num_lease_extensions"][s])
+            out.append({
+                "trace_file": trace_file, "policy": self.policies[s].name, "scenario": s,
+                "makespan": float(res["makespan"][s]), "avg_jct": float(np.mean(jl)) if jl else None,
+                "geometric_mean_jct": float(np.exp(np.mean(np.log(jl)))) if jl else None,
+                "harmonic_mean_jct": float(len(jl) / np.sum(1.0 / np.asarray(jl))) if jl else None,
+                "jct_list": jl,
+                "finish_time_fairness_list": [round(float(jct[j]) / (float(isolated_durations[j]) * contention), 5)
+                                              for j in range(J) if done[j]],
+                "cluster_util": float(np.mean(util)), "utilization_list": util,
+                "extension_percentage": (100.0 * ext) / opp if opp > 0 else 0,
+                "num_lease_extensions": ext, "num_lease_extension_opportunities": opp,
+                "per_round_schedule": res["per_round_schedule"][s],
+                "job_run_time": {j: float(res["run_time"][s, j]) for j in range(J)},
+                "time_per_iteration": self.tpi})
+        return out

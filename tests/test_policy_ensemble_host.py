@@ -27,9 +27,16 @@ def test_policy_ensemble_equals_the_reference_loop(monkeypatch, policy, keep, ng
     from tests.golden import make_sim_pins as pins
     scratch = tempfile.mkdtemp(prefix="swpol_")
     pins.stage_static_trace(scratch, keep=keep, static=static)
+    def extract(sched, jobs, arrival_times):
+        rec = (pins.extract if static else pins.extract_dynamic)(sched, jobs, arrival_times)
+        rec["lease"] = list(sched.get_num_lease_extensions(verbose=False))
+        rec["isolated"] = [sum(sched._profiles[j]["duration_every_epoch"]) for j in range(len(jobs))]
+        rec["utilization_list"] = [float(u) for u in sched.get_cluster_utilization()[1]]
+        return rec
+
     with gb.cpu_backend() as P:
         ref = rh.simulate(policy, policy_obj=P.get_policy(policy, solver="ECOS", seed=0), trace=pins.REL, scratch=scratch,
-                          cluster=f"{ngpus}:0:0", extract=pins.extract if static else pins.extract_dynamic)
+                          cluster=f"{ngpus}:0:0", extract=extract)
         rec = ref["extra"]
         monkeypatch.setattr(sim, "DeviceSim", sf_.HostDeviceSim)
         tr = {k: np.asarray(rec[k]) for k in ("arrival", "total_steps", "scale_factor", "throughput", "duration", "batch_size",
@@ -37,6 +44,10 @@ def test_policy_ensemble_equals_the_reference_loop(monkeypatch, policy, keep, ng
         ens = sim.PolicyEnsemble(tr, [P.get_policy(policy, solver="ECOS", seed=0) for _ in range(2)], ngpus,
                                  dynamic=None if static else rec["dyn"], round_backend=OracleBackend())
         out = ens.run()
+    d = ens.result_dicts(rec["isolated"])[0]
+    assert d["finish_time_fairness_list"] == list(ref["finish_time_fairness_list"])
+    assert d["utilization_list"] == rec["utilization_list"] and d["cluster_util"] == float(ref["cluster_util"])
+    assert [d["extension_percentage"], d["num_lease_extensions"], d["num_lease_extension_opportunities"]] == rec["lease"]
     want = [{int(k): tuple(v) for k, v in rnd.items()} for rnd in ref["per_round_schedule"]]
     for s in (0, 1):
         got = out["per_round_schedule"][s]
