@@ -719,6 +719,34 @@ def bench_packed(GP):
     return pk_ms
 
 
+def bench_policy_ensemble(device):
+    """8 what-ifs of the canonical 120-job trace AS SHIPPED (accordion / gns jobs) under max-min fairness on 32 GPUs:
+    allocation kernels + swb_gavel_round + the device round loop, no reference code in the loop.  The reference's own run
+    of this policy on this trace is on record (tests/golden/sim_dynamic_pins.json, unmodified simulator): the makespan and
+    every completion time must come out the same."""
+    from shockwave_b200 import policies as GP
+    from shockwave_b200.simulate import PolicyEnsemble
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "sim_dynamic_pins.json")))
+    rec, dyn = d["max_min_fairness_32"], d["fifo_32"]["dyn"]
+    tr = {k: np.asarray(rec[k]) for k in ("arrival", "total_steps", "scale_factor", "throughput", "duration", "batch_size",
+                                          "dataset_len")}
+    S = 8
+    ens = PolicyEnsemble(tr, [GP.get_policy("max_min_fairness", solver="ECOS", seed=0) for _ in range(S)], rec["ngpus"],
+                         time_per_iteration=rec["time_per_iteration"], device=device, dynamic=dyn)
+    t0 = time.perf_counter()
+    out = ens.run()
+    dt = time.perf_counter() - t0
+    J = len(rec["arrival"])
+    want = np.array([rec["jct"][str(j)] for j in range(J)])
+    return {"what": "PolicyEnsemble: max_min_fairness, canonical trace as shipped, 32 GPUs", "scenarios": S,
+            "rounds": int(out["rounds"][0]), "seconds": dt, "seconds_per_scenario": dt / S,
+            "allocations_per_scenario": int(out["allocations"][0]),
+            "makespan": float(out["makespan"][0]), "reference_makespan": rec["makespan"],
+            "completion_times_identical_to_the_reference_run": bool(np.array_equal(out["jct"][S - 1], want)),
+            "reference_loop_seconds_note": "1.5-2.1 s per run of the unmodified loop with the same device policies "
+                                           "(profiles/sim_ensemble_r02.json)"}
+
+
 def bench_sim_loop(device):
     """S scenarios x R rounds of the static 120-job trace in ONE swb_sim_replay launch (the schedule the unmodified
     reference recorded under max_min_fairness on 12 GPUs, tests/golden/sim_static_pins.json), checked against the
@@ -750,7 +778,13 @@ def bench_sim_loop(device):
     sched = rec["per_round_schedule"]
     ora = sim_loop.run(rec, lambda c, now, active: sched[c], tpi=rec["time_per_iteration"])
     t_cpu = time.perf_counter() - t0
-    return {"what": "swb_sim_replay: begin + all rounds of S what-if scenarios in one launch, wall time incl. the H2D of "
+    ens = {}
+    try:
+        ens = bench_policy_ensemble(device)
+    except Exception as e:
+        ens = {"error": repr(e)}
+    return {"policy_ensemble": ens,
+            "what": "swb_sim_replay: begin + all rounds of S what-if scenarios in one launch, wall time incl. the H2D of "
                     "the schedule and the D2H of the scenario records",
             "scenarios": S, "rounds": R, "jobs": J, "ms_per_replay": dt * 1e3,
             "scenario_rounds_per_s": S * R / dt, "bit_identical_to_reference_records": ok,
