@@ -742,7 +742,10 @@ def bench_policy_ensemble(device):
             "rounds": int(out["rounds"][0]), "seconds": dt, "seconds_per_scenario": dt / S,
             "allocations_per_scenario": int(out["allocations"][0]),
             "makespan": float(out["makespan"][0]), "reference_makespan": rec["makespan"],
-            "completion_times_identical_to_the_reference_run": bool(np.array_equal(out["jct"][S - 1], want)),
+            "jobs_with_identical_completion_time": int((out["jct"][S - 1] == want).sum()), "jobs": J,
+            "max_rel_completion_time_difference": float(np.max(np.abs(out["jct"][S - 1] / want - 1.0))),
+            "note": "the recorded run used the HiGHS-backed policy code (build container); the device policy returns the "
+                    "same optimal value and its own point of the optimal face, so single completion times may move",
             "reference_loop_seconds_note": "1.5-2.1 s per run of the unmodified loop with the same device policies "
                                            "(profiles/sim_ensemble_r02.json)"}
 
