@@ -210,7 +210,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the batched / dense / policy legs")
     ap.add_argument("--ref-procs", type=int, default=32, help="reference arm: concurrent HiGHS processes")
-    ap.add_argument("--ref-time-limit", type=float, default=900.0, help="reference arm: HiGHS limit per MILP (s)")
+    ap.add_argument("--ref-time-limit", type=float, default=450.0,
+                    help="reference arm: HiGHS limit per MILP (s); measured on one core: 120-190 s per config-D scenario, 192 s for a "
+                         "fallback scenario (two MILPs), so the whole arm ends within a few minutes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

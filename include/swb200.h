@@ -385,7 +385,8 @@ int swb_market_pgd(swb_ctx *ctx, const swb_market_args *a);
  * (tests/test_oracle_sim_loop.py, tests/test_gpu_sim.py).  Dynamic adaptation — accordion / gns batch-size rescaling,
  * `_simulate_accordion` :1658-1727, `_simulate_gns` :1604-1656, `_scale_bs_and_iters` :4731-4935 — runs from tables
  * (swb_sim_set_dynamic); the micro-task failure branch of `_done_callback` (:4497-4570, five empty rounds in a row drop
- * the job) is part of the loop.  Not covered: job pairs (packing), several worker types, the `ideal` mode. */
+ * the job) is part of the loop.  Several worker types (static jobs): swb_sim_set_worker_types.  Not covered: job pairs
+ * (packing), the `ideal` mode. */
 typedef struct swb_sim swb_sim;
 typedef struct swb_sim_trace {
   int32_t J;
@@ -419,6 +420,14 @@ typedef struct swb_sim_dynamic {
   const double *lvl_thr;      /* [J][K] throughput of the job at that batch size (<= 0: not in the throughput file) */
 } swb_sim_dynamic;
 int swb_sim_set_dynamic(swb_sim *sim, const swb_sim_dynamic *tables);
+/* Several worker types (the heterogeneity-aware Gavel policies on mixed clusters): per-type throughputs
+ * throughput[J][W] (`Scheduler._throughputs[job][worker_type]`, read by `_get_job_steps_and_finish_times`
+ * scheduler.py:1467-1512; 0 = the job cannot run on that type) and worker counts ngpus[W], W <= 8.  Afterwards
+ * chosen[s][j] = 1 + index of the type job j runs on in the round (0 = not chosen), capacity is checked per type, and the
+ * `throughput` / `ngpus` of swb_sim_create are not used.  Static jobs only (the reference's batch-size rescale keeps its
+ * progress counters on v100 alone, :4896-4925): refused for a trace with adaptation modes, and swb_sim_set_dynamic is
+ * refused afterwards.  Call before swb_sim_begin. */
+int swb_sim_set_worker_types(swb_sim *sim, int32_t W, const double *throughput, const int32_t *ngpus);
 typedef struct swb_sim_scn {      /* per scenario, after a step */
   double now;                     /* Scheduler._current_timestamp; at the end of the run: the makespan */
   double round_start, round_end;  /* current_round_start_time / _end_time (NaN = None) */
@@ -427,7 +436,9 @@ typedef struct swb_sim_scn {      /* per scenario, after a step */
   int32_t n_active;               /* live jobs (len(self._jobs)) */
   int32_t done;                   /* 1: the reference's loop has left (all jobs completed, or no live job) */
   int32_t err;                    /* bit 0: chosen gangs exceed ngpus; bit 1: nothing running and no arrival left
-                                     (the reference raises); bit 2: a job's epoch left its dynamic-adaptation table */
+                                     (the reference raises); bit 2: a job's epoch left its dynamic-adaptation table;
+                                     bit 3: a job was chosen on a worker type where its throughput is 0 (the reference
+                                     raises, scheduler.py:1494-1504) */
   int32_t reserved;
 } swb_sim_scn;
 int swb_sim_create(int32_t device, const swb_sim_trace *trace, int32_t S, int32_t ngpus, double time_per_iteration,

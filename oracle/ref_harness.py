@@ -170,10 +170,14 @@ def simulate(policy_name, shockwave_scheduler_cls=None, policy_obj=None,
 # by (a) the REFERENCE's own JobMetaData methods for the forecast and (b) oracle/shockwave_milp.py
 # (HiGHS) for the solve.  Used to pin the oracle against the golden pickles and to record fixtures.
 # ---------------------------------------------------------------------------------------------
-def make_oracle_scheduler_cls(record=None, rel_gap=1e-3, time_limit=15.0, placement=None):
+def make_oracle_scheduler_cls(record=None, rel_gap=1e-3, time_limit=15.0, placement=None, key_stats=None):
     """placement: optional callable(n, g, G, T, bfkey, fallback=, w=) -> dict(x=...) that replaces the solver's own x
     (and the re-rank MILP) by a placement RULE applied to the solver's round counts — used to run the product's placement
-    rule (tests/ref_placement.py, the numpy restatement of place.cu) closed-loop."""
+    rule (tests/ref_placement.py, the numpy restatement of place.cu) closed-loop.
+    key_stats: optional dict; filled with how often the reference's PER-ROUND back-fill sort keys (one
+    dirichlet_posterior_remaining_runtime() call per idle round and unscheduled job, each of which recalibrates:
+    shockwave.py:261-267 -> JobMetaData.py:355 -> :302) differ from the job's FIRST key of the same re-solve, and how many
+    rounds would be back-filled differently with first keys only (what place.cu sorts on)."""
     import random as _random
 
     import numpy as _np
@@ -263,6 +267,27 @@ def make_oracle_scheduler_cls(record=None, rel_gap=1e-3, time_limit=15.0, placem
                     if t == 0:
                         for i, v in keys.items():
                             bfkey0[i] = v
+                    if key_stats is not None:
+                        first = key_stats.setdefault("_first", {})
+                        for i, v in keys.items():
+                            first.setdefault((r, jobids[i]), v)
+                        k0 = {i: first[(r, jobids[i])] for i in non}
+                        key_stats["keys"] = key_stats.get("keys", 0) + len(keys)
+                        key_stats["keys_differ"] = key_stats.get("keys_differ", 0) + sum(1 for i in non if keys[i] != k0[i])
+                        key_stats["idle_rounds"] = key_stats.get("idle_rounds", 0) + 1
+                        a = sorted(non, key=lambda i: keys[i], reverse=True)
+                        b = sorted(non, key=lambda i: k0[i], reverse=True)
+                        def fill(order, idle=idle):
+                            got = []
+                            for i in order:
+                                if g[i] <= idle:
+                                    idle -= int(g[i]); got.append(i)
+                                if idle <= 0:
+                                    break
+                            return got
+                        key_stats["rounds_filled_differently"] = key_stats.get("rounds_filled_differently", 0) + (fill(a) != fill(b))
+                        key_stats["first_rounds_filled_differently"] = key_stats.get("first_rounds_filled_differently", 0) + (
+                            t == 0 and fill(a) != fill(b))
                     for i in sorted(non, key=lambda i: keys[i], reverse=True):
                         if g[i] <= idle:
                             idle -= int(g[i])

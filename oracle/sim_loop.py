@@ -10,7 +10,9 @@ demands the same completion time of every job, the same makespan, the same numbe
 throughput timeline, to the last bit.
 
 Not restated (rejected by the product too): accordion / gns batch-size rescaling (`_simulate_accordion`, `_simulate_gns`,
-`_scale_bs_and_iters`), job pairs (packing), several worker types, the `ideal` and generated-arrival modes.
+`_scale_bs_and_iters`) on more than one worker type, job pairs (packing), the `ideal` and generated-arrival modes
+(the generated-arrival mode cannot run in the reference itself: `Scheduler.__init__` opens its trace pickle
+unconditionally, scheduler.py:437).
 One quirk is kept on purpose: the over-deadline rule sums `_cumulative_run_time` per worker id and divides by the scale
 factor (scheduler.py:4378-4390); here it is the running sum of the per-round execution times — the same real number,
 possibly another rounding when a gang moves between workers (matters only at an exact tie with int(1.5 duration)).
@@ -30,8 +32,11 @@ def steps_and_finish(now, thr, tpi, remaining):
     return n, max(now, now + n / thr)                # max_finish_time starts at the current timestamp (:1470, :1507)
 
 
-def run(trace, select, tpi=120.0, on_round=None, max_rounds=None, dyn=None):
-    """trace: dict of equal-length sequences `arrival, total_steps, scale_factor, throughput, duration, batch_size,
+def run(trace, select, tpi=120.0, on_round=None, max_rounds=None, dyn=None, throughput_w=None):
+    """throughput_w: [J][W] per-worker-type throughputs (`Scheduler._throughputs[job][worker_type]`, static jobs only);
+    select() then returns {job: worker type index} and the round's steps / finish time use the throughput of that type
+    (`_get_job_steps_and_finish_times(job_id, worker_type)`, scheduler.py:1467-1512).
+    trace: dict of equal-length sequences `arrival, total_steps, scale_factor, throughput, duration, batch_size,
     dataset_len`.  select(c, now, active) -> iterable of job indices to run in round c (active = ascending list of live
     jobs).  on_round(c, now, info) sees what the shockwave hook would see (epoch progress, measured throughput).
     dyn: tables of the dynamic-adaptation jobs (accordion / gns batch-size rescaling, scheduler.py:1604-1727 and
@@ -177,10 +182,12 @@ def run(trace, select, tpi=120.0, on_round=None, max_rounds=None, dyn=None):
         active = [j for j in range(J) if status[j] == 1]
         if not active:
             break                                         # scheduler.py:2173-2178 (even with jobs still queued)
-        chosen = [j for j in select(c, now, active) if status[j] == 1]
+        picked = select(c, now, active)
+        chosen = [j for j in picked if status[j] == 1]
         schedule.append(set(chosen))
         for j in chosen:
-            n, fin = steps_and_finish(now, thr[j], tpi, total[j] - steps_run[j])
+            th = thr[j] if throughput_w is None else float(throughput_w[j][picked[j]])
+            n, fin = steps_and_finish(now, th, tpi, total[j] - steps_run[j])
             running.append((fin, j, n))
         c += 1
         if max_rounds is not None and c >= max_rounds:

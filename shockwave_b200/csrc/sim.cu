@@ -48,6 +48,7 @@ struct swb_sim {
   cudaStream_t st = nullptr;
   void *arena = nullptr;        // trace + state, one allocation
   void *dyn_arena = nullptr;    // tables of swb_sim_set_dynamic
+  void *wt_arena = nullptr;     // tables of swb_sim_set_worker_types
   int needs_dynamic = 0;        // the trace names non-static jobs: tables are required before the first round
   unsigned char *d_chosen = nullptr;
   size_t chosen_cap = 0;
@@ -74,6 +75,7 @@ void swb_sim_destroy(swb_sim *m) {
   if (m->st) cudaStreamSynchronize(m->st);
   if (m->arena) cudaFree(m->arena);
   if (m->dyn_arena) cudaFree(m->dyn_arena);
+  if (m->wt_arena) cudaFree(m->wt_arena);
   if (m->d_chosen) cudaFree(m->d_chosen);
   if (m->h_pin) cudaFreeHost(m->h_pin);
   if (m->st) cudaStreamDestroy(m->st);
@@ -222,6 +224,7 @@ int swb_sim_set_dynamic(swb_sim *m, const swb_sim_dynamic *d) {
   if (!d->mode || !d->bs_max || !d->bs_min || !d->bs_big || !d->orig_locked || !d->acc_skip || !d->pat_off || !d->lvl_bs ||
       !d->lvl_thr)
     return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: null table");
+  if (m->T.thr_w) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: several worker types run static jobs only");
   const int J = m->J, K = d->n_levels;
   if (K <= 0 || K > SIM_MAX_LEVELS) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: n_levels must be in [1, 8]");
   if (d->pat_off[0] != 0) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_dynamic: pat_off[0] must be 0");
@@ -258,6 +261,31 @@ int swb_sim_set_dynamic(swb_sim *m, const swb_sim_dynamic *d) {
   m->T.pat_off = (const long long *)(b + o_off); m->T.pattern = (const int *)(b + o_pat); m->T.K = K;
   m->T.lvl_bs = (const int *)(b + o_lb); m->T.lvl_thr = (const double *)(b + o_lt);
   m->needs_dynamic = 0;
+  return 0;
+}
+
+int swb_sim_set_worker_types(swb_sim *m, int32_t W, const double *throughput, const int32_t *ngpus) {
+  if (!m || !throughput || !ngpus) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_worker_types: null argument");
+  if (W < 1 || W > SIM_MAX_TYPES) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_worker_types: need 1 <= W <= 8");
+  if (m->needs_dynamic || m->T.mode)
+    return swb_set_error(SWB_ERR_ARG, "swb_sim_set_worker_types: several worker types run static jobs only (the reference "
+                                      "rescales a job's progress on v100 alone, scheduler.py:4896-4925)");
+  const int J = m->J;
+  for (int w = 0; w < W; ++w)
+    if (ngpus[w] < 0) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_worker_types: negative worker count");
+  for (size_t i = 0; i < (size_t)J * W; ++i)
+    if (!(throughput[i] >= 0.0)) return swb_set_error(SWB_ERR_ARG, "swb_sim_set_worker_types: throughput must be >= 0 (0 = the job cannot run on that type)");
+  SCK(cudaSetDevice(m->device));
+  const size_t o_thr = 0, o_cap = al((size_t)J * W * 8), total = o_cap + al((size_t)W * 4);
+  SCK(cudaStreamSynchronize(m->st));
+  if (m->wt_arena) cudaFree(m->wt_arena);
+  m->wt_arena = nullptr; m->T.thr_w = nullptr; m->T.cap_w = nullptr; m->T.W = 0;
+  SCK(cudaMalloc(&m->wt_arena, total));
+  char *b = (char *)m->wt_arena;
+  SCK(cudaMemcpyAsync(b + o_thr, throughput, (size_t)J * W * 8, cudaMemcpyHostToDevice, m->st));
+  SCK(cudaMemcpyAsync(b + o_cap, ngpus, (size_t)W * 4, cudaMemcpyHostToDevice, m->st));
+  SCK(cudaStreamSynchronize(m->st));
+  m->T.W = W; m->T.thr_w = (const double *)(b + o_thr); m->T.cap_w = (const int *)(b + o_cap);
   return 0;
 }
 

@@ -55,7 +55,8 @@
 namespace swb {
 namespace sim {
 
-enum { ERR_CAPACITY = 1, ERR_NO_EVENT = 2, ERR_PATTERN = 4 };
+enum { ERR_CAPACITY = 1, ERR_NO_EVENT = 2, ERR_PATTERN = 4, ERR_THROUGHPUT = 8 };
+#define SIM_MAX_TYPES 8
 #define SIM_MAX_FAILED_ATTEMPTS 5 /* scheduler.py:53 */
 #define SIM_MAX_LEVELS 8
 enum { QUEUED = 0, LIVE = 1, COMPLETED = 2 };
@@ -79,6 +80,10 @@ struct Trace {            // [J], shared by the scenarios
   int K;                  // levels per job
   const int *lvl_bs;      // [J][K]
   const double *lvl_thr;  // [J][K]
+  // several worker types (static jobs only; null / 0 = one type): chosen[j] = 1 + index of the type the job runs on
+  int W;
+  const double *thr_w;    // [J][W] steps/s of the job on each type (<= 0: the job cannot run there, scheduler.py:1494-1504)
+  const int *cap_w;       // [W] workers of each type
 };
 
 struct Scn {              // == swb_sim_scn
@@ -246,13 +251,27 @@ SIM_HD void scenario_step(const Trace &T, const State &X, Scn *scn, const unsign
   if (z.done) return;
   // ---- (C) steps and finish times of the chosen jobs (scheduler.py:2224-2236)
   double mx = 0.0;
-  long long used = 0, nrun = 0;
+  long long used = 0, nrun = 0, badthr = 0;
+  const bool het = T.thr_w != nullptr;                         // several worker types: throughput of the round's type
+  long long used_w[SIM_MAX_TYPES];
+  for (int w = 0; w < SIM_MAX_TYPES; ++w) used_w[w] = 0;
   for (int j = SIM_TID; j < T.J; j += SIM_NT) {
     if (chosen[j] && X.status[j] == LIVE) {
+      double th = X.cthr[j];
+      if (het) {
+        int w = (int)chosen[j] - 1;
+        if (w >= T.W) { w = T.W - 1; used_w[w] += (long long)ngpus + 1; }     // unknown type: reported as a capacity error
+        th = T.thr_w[(size_t)j * T.W + w];
+        used_w[w] += T.sf[j];
+      }
+      if (!(th > 0.0)) {                                        // the reference raises here (scheduler.py:1494-1504)
+        ++badthr; X.running[j] = 0;
+        continue;
+      }
       const long long rem = X.ctotal[j] - X.steps_run[j];      // negative after a rescale that rounds the progress up
-      long long n = (long long)SIM_MUL(X.cthr[j], tpi);
+      long long n = (long long)SIM_MUL(th, tpi);
       if (n > rem) n = rem;
-      double fin = z.now + (double)n / X.cthr[j];
+      double fin = z.now + (double)n / th;
       if (!(fin > z.now)) fin = z.now;                          // max_finish_time starts at the current timestamp (:1470)
       X.nsteps[j] = n; X.fin[j] = fin; X.running[j] = 1;
       mx = fin > mx ? fin : mx;
@@ -264,7 +283,11 @@ SIM_HD void scenario_step(const Trace &T, const State &X, Scn *scn, const unsign
   mx = blk_max(mx, sh);
   used = blk_sum(used, sh);
   nrun = blk_sum(nrun, sh);
-  if (used > ngpus) z.err |= ERR_CAPACITY;
+  if (het) {
+    for (int w = 0; w < T.W; ++w)
+      if (blk_sum(used_w[w], sh) > (long long)T.cap_w[w]) z.err |= ERR_CAPACITY;
+    if (blk_sum(badthr, sh)) z.err |= ERR_THROUGHPUT;
+  } else if (used > ngpus) z.err |= ERR_CAPACITY;
   // ---- head of iteration c = k + 1: jump to the next event (scheduler.py:1901-1915)
   const int c = z.rounds + 1;
   double max_ts = 0.0;

@@ -60,7 +60,7 @@ class RoundArgs(C.Structure):
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_stream", "swb_sync",
            "swb_solve", "swb_job_add", "swb_job_remove", "swb_job_table_stats", "swb_job_set_gbm", "swb_gbm_ensemble", "swb_gavel_round", "swb_round_solve", "swb_forecast",
            "swb_forecast_commit", "swb_last_timings", "swb_policy_pooled", "swb_policy_hetero", "swb_policy_waterfill_step", "swb_gbm_forecast", "swb_market_pgd", "swb_set_option", "swb_allox_assign", "swb_lp_solve",
-           "swb_sim_create", "swb_sim_destroy", "swb_sim_begin", "swb_sim_step", "swb_sim_replay", "swb_sim_results", "swb_sim_set_dynamic", "swb_sim_job_state"]
+           "swb_sim_create", "swb_sim_destroy", "swb_sim_begin", "swb_sim_step", "swb_sim_replay", "swb_sim_results", "swb_sim_set_dynamic", "swb_sim_job_state", "swb_sim_set_worker_types"]
 
 _lib = None
 

@@ -86,6 +86,8 @@ def _lib():
         lib.swb_sim_set_dynamic.argtypes = [C.c_void_p, C.POINTER(SimDynamic)]
         lib.swb_sim_job_state.argtypes = [C.c_void_p] * 8
         lib.swb_sim_job_state.restype = C.c_int
+        lib.swb_sim_set_worker_types.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.swb_sim_set_worker_types.restype = C.c_int
         for f in ("swb_sim_set_dynamic", "swb_sim_create", "swb_sim_begin", "swb_sim_step", "swb_sim_replay", "swb_sim_results"):
             getattr(lib, f).restype = C.c_int
         _bound = True
@@ -139,6 +141,16 @@ class DeviceSim:
             setattr(d, k, a[k].ctypes.data)
         d.n_levels = a["K"]
         self._ck(self._lib.swb_sim_set_dynamic(self._h, C.byref(d)))
+
+    def set_worker_types(self, throughput, ngpus):
+        """Several worker types (static jobs): throughput [J][W] (`Scheduler._throughputs[job][worker_type]`, 0 = the
+        job cannot run there), ngpus [W].  Afterwards chosen[s][j] = 1 + index of the type job j runs on."""
+        thr = np.ascontiguousarray(throughput, dtype=np.float64)
+        cap = np.ascontiguousarray(ngpus, dtype=np.int32)
+        if thr.ndim != 2 or thr.shape != (self.J, cap.shape[0]):
+            raise ValueError("throughput must be [J][W] and ngpus [W]")
+        self._ck(self._lib.swb_sim_set_worker_types(self._h, int(cap.shape[0]), thr.ctypes.data, cap.ctypes.data))
+        self.W = int(cap.shape[0])
 
     def begin(self):
         self._ck(self._lib.swb_sim_begin(self._h, self.scn.ctypes.data, self.status.ctypes.data))

@@ -24,6 +24,8 @@ struct HostSim {
   std::vector<int> mode, bs_max, bs_min, bs_big, orig_locked, acc_skip, pattern, lvl_bs;
   std::vector<long long> pat_off;
   std::vector<double> lvl_thr;
+  std::vector<double> thr_w;
+  std::vector<int> cap_w;
   Scn scn;
   double sd[1];
   long long si[1];
@@ -72,6 +74,12 @@ extern "C" void sim_host_set_dynamic(void *p, const int *mode, const int *bs_max
   h->T.mode = h->mode.data(); h->T.bs_max = h->bs_max.data(); h->T.bs_min = h->bs_min.data(); h->T.bs_big = h->bs_big.data();
   h->T.orig_locked = h->orig_locked.data(); h->T.acc_skip = h->acc_skip.data(); h->T.pat_off = h->pat_off.data();
   h->T.pattern = h->pattern.data(); h->T.K = K; h->T.lvl_bs = h->lvl_bs.data(); h->T.lvl_thr = h->lvl_thr.data();
+}
+
+extern "C" void sim_host_set_worker_types(void *p, int W, const double *thr, const int *cap) {
+  HostSim *h = (HostSim *)p;
+  h->thr_w.assign(thr, thr + (size_t)h->J * W); h->cap_w.assign(cap, cap + W);
+  h->T.W = W; h->T.thr_w = h->thr_w.data(); h->T.cap_w = h->cap_w.data();
 }
 
 extern "C" void sim_host_begin(void *p, Scn *out) {

@@ -34,6 +34,7 @@ def host_sim_lib():
     lib.sim_host_results.argtypes = [C.c_void_p] * 4
     lib.sim_host_destroy.argtypes = [C.c_void_p]
     lib.sim_host_job_state.argtypes = [C.c_void_p] * 8
+    lib.sim_host_set_worker_types.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -59,13 +60,26 @@ class HostSim:
         self.lib.sim_host_set_dynamic(self.h, p("mode"), p("bs_max"), p("bs_min"), p("bs_big"), p("orig_locked"),
                                       p("acc_skip"), p("pat_off"), p("pattern"), a["K"], p("lvl_bs"), p("lvl_thr"))
 
+    def set_worker_types(self, throughput, ngpus):
+        self._wt = (np.ascontiguousarray(throughput, dtype=np.float64), np.ascontiguousarray(ngpus, dtype=np.int32))
+        assert self._wt[0].shape == (self.J, self._wt[1].shape[0])
+        self.lib.sim_host_set_worker_types(self.h, int(self._wt[1].shape[0]), self._wt[0].ctypes.data, self._wt[1].ctypes.data)
+
     def begin(self):
         self.lib.sim_host_begin(self.h, C.byref(self.scn))
         return self.scn
 
     def step(self, chosen):
-        ch = np.zeros(self.J, np.uint8)
-        ch[list(chosen)] = 1
+        """chosen: job indices (one worker type), {job: worker type index}, or the [J] uint8 row swb_sim_step takes."""
+        if isinstance(chosen, np.ndarray) and chosen.shape == (self.J,) and chosen.dtype == np.uint8:
+            ch = np.ascontiguousarray(chosen)
+        else:
+            ch = np.zeros(self.J, np.uint8)
+            if isinstance(chosen, dict):
+                for j, w in chosen.items():
+                    ch[j] = 1 + w
+            else:
+                ch[list(chosen)] = 1
         self.lib.sim_host_step(self.h, ch.ctypes.data, self.ngpus, self.tpi, self.grd, C.byref(self.scn),
                                self.status.ctypes.data, self.epoch.ctypes.data, self.tl_ns.ctypes.data,
                                self.tl_end.ctypes.data, self.thr_meas.ctypes.data)
@@ -156,6 +170,10 @@ class HostDeviceSim:
         for m in self.sims:
             m.set_dynamic(dyn)
 
+    def set_worker_types(self, throughput, ngpus):
+        for m in self.sims:
+            m.set_worker_types(throughput, ngpus)
+
     def _pull(self, s, z):
         for k in ("now", "round_start", "round_end", "rounds", "remaining", "n_active", "done", "err"):
             self.scn[k][s] = getattr(z, k)
@@ -170,7 +188,7 @@ class HostDeviceSim:
 
     def step(self, chosen):
         for s, m in enumerate(self.sims):
-            z = m.step(np.flatnonzero(chosen[s]).tolist())
+            z = m.step(np.ascontiguousarray(chosen[s], dtype=np.uint8))
             self._pull(s, z)
             self.status[s], self.epoch[s], self.tl_ns[s], self.tl_end[s] = m.status, m.epoch, m.tl_ns, m.tl_end
         return self.scn
