@@ -501,19 +501,48 @@ class PolicyEnsemble:
         (`_need_to_update_allocation` after an arrival, a completion or a failed micro-task; at most once per
         `minimum_time_between_allocation_resets`), `_reset_time_run_so_far` (:3498-3551) with its deficits;
       * `_get_allocation_state` / `_compute_allocation` (:3205-3355): the arguments each policy family takes.
-    One worker type, single jobs (no packing).  Returns per-round schedules WITH worker ids, like the reference."""
+    Single jobs (no packing).  One worker type by default; `worker_types=dict(names=[...], throughput=[J][W],
+    ngpus=[W])` runs a MIXED cluster of static jobs (swb_sim_set_worker_types): names in the reference's sorted order
+    (`sorted(cluster_spec)`, scheduler.py:1826 — worker ids are handed out type by type in that order), per-type
+    throughputs as in `Scheduler._throughputs[job][worker_type]`; the types are walked in the reference's round order
+    v100, p100, k80 (:1290-1301; shuffled by its `_worker_type_shuffler` for policies without "Perf" / "Packing" in
+    their name, seed + 5).  Returns per-round schedules WITH worker ids, like the reference."""
+
+    ROUND_ORDER = ("v100", "p100", "k80")              # scheduler.py:1290
 
     def __init__(self, trace, policies, ngpus, time_per_iteration=120, device=0, dynamic=None, priority_weights=None,
                  minimum_time_between_allocation_resets=1000, round_backend=None, worker_type="v100",
-                 other_worker_types=("k80", "p100")):
-        self.trace, self.policies, self.ngpus, self.tpi = trace, list(policies), int(ngpus), time_per_iteration
+                 other_worker_types=("k80", "p100"), worker_types=None, seed=0):
+        self.trace, self.policies, self.tpi = trace, list(policies), time_per_iteration
         self.S, self.J = len(self.policies), len(trace["arrival"])
+        if worker_types is not None:
+            if dynamic is not None:
+                raise ValueError("several worker types run static jobs only")
+            self.types = list(worker_types["names"])
+            if self.types != sorted(self.types):
+                raise ValueError("worker type names must be in sorted order (the reference registers workers that way)")
+            self.cap = np.asarray(worker_types["ngpus"], dtype=np.int32)
+            self.thr_w = np.ascontiguousarray(worker_types["throughput"], dtype=np.float64)
+            if self.thr_w.shape != (self.J, len(self.types)) or self.cap.shape != (len(self.types),) or (self.cap <= 0).any():
+                raise ValueError("worker_types: throughput [J][W], ngpus [W] > 0, names [W]")
+            ngpus = int(self.cap.sum())
+        else:
+            self.types, self.cap, self.thr_w = [worker_type], np.array([int(ngpus)], np.int32), None
+        self.W = len(self.types)
+        self.ngpus = int(ngpus)
         self.sim = DeviceSim(trace, self.S, ngpus, time_per_iteration, time_per_iteration, device)
         if dynamic is not None:
             self.sim.set_dynamic(dynamic)
+        if self.thr_w is not None:
+            self.sim.set_worker_types(self.thr_w, self.cap)
         self.min_reset = float(minimum_time_between_allocation_resets)
         self.wt = worker_type
-        self.cluster_spec = {worker_type: self.ngpus, **{w: 0 for w in other_worker_types}}
+        if self.thr_w is not None:
+            self.cluster_spec = {w: int(c) for w, c in zip(self.types, self.cap)}
+        else:
+            self.cluster_spec = {worker_type: self.ngpus, **{w: 0 for w in other_worker_types}}
+        import random as _random
+        self._shufflers = [_random.Random(seed + 5) for _ in range(self.S)]    # scheduler.py:508-509
         self.pw = np.ones(self.J) if priority_weights is None else np.asarray(priority_weights, dtype=np.float64)
         if round_backend is None:
             from .placement import _DeviceBackend
@@ -526,7 +555,10 @@ class PolicyEnsemble:
         """_get_allocation_state + _compute_allocation for scenario s -> alloc [J] (NaN = not in the allocation)."""
         pol, wt = self.policies[s], self.wt
         jobs = np.flatnonzero(live).tolist()
-        thr = {j: {wt: float(st["throughput"][s, j])} for j in jobs}
+        if self.thr_w is not None:
+            thr = {j: {w: float(self.thr_w[j, i]) for i, w in enumerate(self.types)} for j in jobs}
+        else:
+            thr = {j: {wt: float(st["throughput"][s, j])} for j in jobs}
         sf = {j: int(self.trace["scale_factor"][j]) for j in jobs}
         pw = {j: float(self.pw[j]) for j in jobs}
         since = {j: now - float(self.trace["arrival"][j]) for j in jobs}
@@ -544,24 +576,30 @@ class PolicyEnsemble:
             a = pol.get_allocation(thr, sf, remaining, self.cluster_spec)
         else:
             a = pol.get_allocation(thr, sf, self.cluster_spec)
-        out = np.full(self.J, np.nan)
+        out = np.full((self.J, self.W), np.nan)
         for j, row in (a or {}).items():
-            out[j] = row[wt]
+            for i, w in enumerate(self.types):
+                out[j, i] = row[w]
         self.allocations[s] += 1
         return out
 
     def run(self, max_rounds=None):
-        sim, S, J, G, half = self.sim, self.S, self.J, self.ngpus, self.tpi / 2.0
+        sim, S, J, G, W, half = self.sim, self.S, self.J, self.ngpus, self.W, self.tpi / 2.0
         scn = sim.begin()
         status = sim.status.copy()
         live_prev = np.zeros((S, J), bool)
-        job_time = np.zeros((S, J)); deficit = np.zeros((S, J)); alloc = np.full((S, J), np.nan)
-        worker_time = np.zeros(S); last_reset = np.zeros(S); need_update = np.zeros(S, bool)
+        job_time = np.zeros((S, J, W)); deficit = np.zeros((S, J, W)); alloc = np.full((S, J, W), np.nan)
+        worker_time = np.zeros((S, W)); last_reset = np.zeros(S); need_update = np.zeros(S, bool)
         prev = [dict() for _ in range(S)]                  # job -> worker ids of the round before (lease extension)
         wtime = np.zeros((S, G))                           # _cumulative_worker_time_so_far
         lease_ext = np.zeros(S, np.int64); lease_opp = np.zeros(S, np.int64)
         sf_all = np.asarray(self.trace["scale_factor"], dtype=np.int32)
-        workers = [list(range(G))]
+        # worker ids are handed out type by type in sorted type order (scheduler.py:1826-1832)
+        first = np.concatenate([[0], np.cumsum(self.cap)])
+        ids_of = [list(range(int(first[i]), int(first[i + 1]))) for i in range(W)]
+        type_of_worker = np.repeat(np.arange(W), self.cap)
+        base_order = [self.types.index(w) for w in self.ROUND_ORDER if w in self.types] + \
+                     [i for i, w in enumerate(self.types) if w not in self.ROUND_ORDER]
         st = sim.job_state()
         steps_run = np.zeros((S, J), np.int64)
         c = 0
@@ -584,31 +622,39 @@ class PolicyEnsemble:
                 since = now - last_reset[s]
                 if need_update[s] and (since >= self.min_reset or last_reset[s] == 0):
                     jobs = np.flatnonzero(live)
-                    wsum = 0.0
-                    for j in jobs.tolist():                                     # _reset_time_run_so_far :3498-3551
-                        received = job_time[s, j] - half
-                        should = 0 if np.isnan(alloc[s, j]) else alloc[s, j] * since
-                        deficit[s, j] += should - received
-                        job_time[s, j] = half
-                        wsum += half
-                    worker_time[s] = wsum
+                    for w in range(W):                                          # _reset_time_run_so_far :3498-3551
+                        wsum = 0.0
+                        for j in jobs.tolist():
+                            received = job_time[s, j, w] - half
+                            should = 0 if np.isnan(alloc[s, j, w]) else alloc[s, j, w] * since
+                            deficit[s, j, w] += should - received
+                            job_time[s, j, w] = half
+                            wsum += half
+                        worker_time[s, w] = wsum
                     last_reset[s] = now
                     alloc[s] = self._allocation(s, live, now, st, steps_run)
                     need_update[s] = False
                 jobs = np.flatnonzero(live)
                 loc = {int(j): i for i, j in enumerate(jobs.tolist())}
-                pv = {loc[j]: (0, tuple(w)) for j, w in prev[s].items() if j in loc}
+                pv = {loc[j]: (int(type_of_worker[w[0]]), tuple(w)) for j, w in prev[s].items() if j in loc}
+                name = self.policies[s].name
+                order = list(base_order)
+                if "Perf" not in name and "Packing" not in name and W > 1:
+                    names = [self.types[i] for i in order]
+                    self._shufflers[s].shuffle(names)                          # scheduler.py:1297-1301
+                    order = [self.types.index(w) for w in names]
+                thr = self.thr_w[jobs] if self.thr_w is not None else st["throughput"][s, jobs][:, None]
                 prio, sel, asg = self.backend.gavel_round(
-                    alloc[s, jobs][:, None], job_time[s, jobs][:, None], np.array([worker_time[s]]),
-                    st["throughput"][s, jobs][:, None], deficit[s, jobs][:, None], sf_all[jobs], np.array([G], np.int32), [0],
-                    workers, pv, isolated_plus=(self.policies[s].name == "Isolated_plus"),
-                    fifo=self.policies[s].name.startswith("FIFO"))
+                    alloc[s, jobs], job_time[s, jobs], worker_time[s].copy(), thr, deficit[s, jobs], sf_all[jobs],
+                    self.cap.copy(), order, [ids_of[i] for i in order], pv,
+                    isolated_plus=(name == "Isolated_plus"), fifo=name.startswith("FIFO"))
                 rnd = {int(jobs[i]): tuple(int(w) for w in ws) for i, ws in asg}
                 ids = list(rnd)                  # a selected job the allocation does not know yet gets no workers (:1363-1366)
                 lease_opp[s] += sum(1 for j in prev[s] if live[j])              # scheduler.py:2198-2213
                 lease_ext[s] += sum(1 for j, ws in rnd.items() if j in prev[s] and set(prev[s][j]) == set(ws))
                 prev[s] = rnd
-                chosen[s, ids] = 1
+                for j in ids:
+                    chosen[s, j] = 1 + int(type_of_worker[rnd[j][0]])
                 self.per_round_schedule[s].append({j: rnd[j] for j in ids})
             scn = sim.step(chosen)
             if (scn["err"] != 0).any():
@@ -623,10 +669,11 @@ class PolicyEnsemble:
                         need_update[s] = True                                  # scheduler.py:4569
                     else:
                         ex = float(st["exec_time"][s, j])                      # :4660-4676
-                        job_time[s, j] += ex
-                        worker_time[s] += ex
-                        for w in prev[s].get(j, ()):
-                            wtime[s, w] += ex
+                        w = int(chosen[s, j]) - 1
+                        job_time[s, j, w] += ex
+                        worker_time[s, w] += ex
+                        for wid in prev[s].get(j, ()):
+                            wtime[s, wid] += ex
             c += 1
             if max_rounds is not None and c >= max_rounds:
                 break

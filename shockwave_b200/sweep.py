@@ -13,7 +13,10 @@ Trace parsing, profile generation and the throughput file stay the reference's (
 `utils.read_all_throughputs_json_v2`, `utils.get_gns_bs_pattern`: imported from --reference-dir, exactly the calls its own
 driver makes, simulate_scheduler_with_trace.py:28-43); everything after that runs here.  One result pickle per point with
 the keys of the reference's pickle (see `ShockwaveEnsemble.result_dicts` / `PolicyEnsemble.result_dicts`), readable by
-`aggregate_result.py`.  One worker type (the first count of --cluster_spec), single jobs."""
+`aggregate_result.py`.  Single jobs.  Shockwave runs on one worker type (the first count of --cluster_spec, as in the
+reference: "we assume homogeneous hardware"); the Gavel policies also run MIXED clusters (`--cluster_spec 8:4:4` =
+v100:p100:k80) of static traces — per-type throughputs from the same throughput file, worker ids handed out like the
+reference does (PolicyEnsemble(worker_types=...), swb_sim_set_worker_types)."""
 import argparse
 import importlib
 import itertools
@@ -54,6 +57,18 @@ def load_reference_inputs(reference_dir, trace_file, throughputs_file, worker_ty
     return trace, profiles, [j.model for j in jobs], [j.mode for j in jobs], throughput_of, utils.get_gns_bs_pattern, iso
 
 
+def per_type_throughputs(reference_dir, throughputs_file, models, trace, names):
+    """[J][W] throughputs of the trace's jobs on the worker types `names` (`Scheduler._set_initial_throughput`,
+    scheduler.py:579-590: the "null" co-location entry of the job type at its scale factor)."""
+    utils = importlib.import_module("utils")
+    tables = utils.read_all_throughputs_json_v2(throughputs_file)
+    out = np.zeros((len(models), len(names)))
+    for j, (m, bs, sf) in enumerate(zip(models, trace["batch_size"], trace["scale_factor"])):
+        for i, w in enumerate(names):
+            out[j, i] = float(tables[w][(f"{m} (batch size {int(bs)})", int(sf))]["null"])
+    return out
+
+
 def grid(sets):
     """--set k=1e-3,1e-2 --set lambda=12,24 -> [{k: 1e-3, lambda: 12}, ...] (cartesian product, first key slowest)."""
     keys, vals = [], []
@@ -69,7 +84,7 @@ def main(argv=None):
     ap.add_argument("--reference-dir", required=True, help="the reference's scheduler/ directory (utils.py, job.py ...)")
     ap.add_argument("-t", "--trace_file", required=True)
     ap.add_argument("--throughputs_file", required=True)
-    ap.add_argument("-c", "--cluster_spec", default="32:0:0", help="v100:p100:k80 like the reference; only v100 may be > 0")
+    ap.add_argument("-c", "--cluster_spec", default="32:0:0", help="v100:p100:k80 like the reference (shockwave: v100 only)")
     ap.add_argument("-p", "--policy", default="shockwave", help="shockwave, or a comma-separated list of Gavel policies")
     ap.add_argument("--config", help="shockwave_config json (reference: configurations/*.json)")
     ap.add_argument("--set", action="append", help="shockwave hyper-parameter values, e.g. k=1e-3,1e-2 (repeatable)")
@@ -79,13 +94,22 @@ def main(argv=None):
     ap.add_argument("--output_dir", required=True)
     args = ap.parse_args(argv)
     counts = [int(v) for v in args.cluster_spec.split(":")]
-    if any(counts[1:]):
-        raise SystemExit("the device round loop runs one worker type: use a v100-only --cluster_spec")
+    mixed = any(counts[1:])
+    if mixed and args.policy == "shockwave":
+        raise SystemExit("shockwave assumes homogeneous hardware (as the reference does): use a v100-only --cluster_spec")
     trace, profiles, models, modes, thr_of, gns, iso = load_reference_inputs(args.reference_dir, args.trace_file,
                                                                              args.throughputs_file)
     dyn = None
     if any(m != "static" for m in modes):
+        if mixed:
+            raise SystemExit("mixed clusters run static traces only (the reference keeps a rescaled job's progress on "
+                             "v100 alone, scheduler.py:4896-4925)")
         dyn = _sim.build_dynamic_tables(models, modes, trace, thr_of, gns)
+    worker_types = None
+    if mixed:
+        names = sorted(n for n, c in zip(("v100", "p100", "k80"), counts) if c > 0)
+        worker_types = dict(names=names, ngpus=[counts[("v100", "p100", "k80").index(n)] for n in names],
+                            throughput=per_type_throughputs(args.reference_dir, args.throughputs_file, models, trace, names))
     os.makedirs(args.output_dir, exist_ok=True)
     stem = os.path.splitext(os.path.basename(args.trace_file))[0]
     paths = []
@@ -107,7 +131,8 @@ def main(argv=None):
         names = args.policy.split(",")
         pols = [P.get_policy(n, solver="ECOS", seed=args.seed) for n in names]
         ens = _sim.PolicyEnsemble(trace, pols, counts[0], time_per_iteration=args.time_per_iteration, device=args.device,
-                                  dynamic=dyn, priority_weights=trace["priority_weight"])
+                                  dynamic=dyn, priority_weights=trace["priority_weight"], worker_types=worker_types,
+                                  seed=args.seed)
         ens.run()
         for d, n in zip(ens.result_dicts(iso, trace_file=args.trace_file), names):
             d["policy"] = n

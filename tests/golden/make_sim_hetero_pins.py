@@ -36,12 +36,20 @@ def extract(sched, jobs, arrival_times):
     return rec
 
 
-def record(policy, keep, cluster, scratch=None):
+def record(policy, keep, cluster, scratch=None, product=False):
+    """product=False: the reference loop as shipped with the HiGHS-backed policies (CPU).  product=True: the reference
+    loop driving the PRODUCT's policies and round step on the device (GavelRoundMixin; needs a B200)."""
     scratch = scratch or tempfile.mkdtemp(prefix="swsimh_")
     pins.stage_static_trace(scratch, keep=keep, static=True)
-    with gb.cpu_backend() as P:
+    if product:
+        from shockwave_b200 import policies as P
+        from shockwave_b200.placement import GavelRoundMixin
         r = rh.simulate(policy, policy_obj=P.get_policy(policy, solver="ECOS", seed=0), trace=pins.REL, scratch=scratch,
-                        cluster=cluster, extract=extract)
+                        cluster=cluster, extract=extract, scheduler_mixin=GavelRoundMixin)
+    else:
+        with gb.cpu_backend() as P:
+            r = rh.simulate(policy, policy_obj=P.get_policy(policy, solver="ECOS", seed=0), trace=pins.REL,
+                            scratch=scratch, cluster=cluster, extract=extract)
     rec = r["extra"]
     wt = rec["worker_type_of_id"]
     # {job: worker type index} per round, in the reference's dict insertion order

@@ -62,3 +62,39 @@ def test_sweep_cli_policies_and_shockwave(monkeypatch):
     assert ds[0]["makespan"] == ref["makespan"] and ds[0]["jct_list"] == list(ref["jct_list"])
     assert ds[0]["finish_time_fairness_list"] == list(ref["finish_time_fairness_list"])
     assert ds[2]["per_round_schedule"] != ds[0]["per_round_schedule"]
+
+
+def test_sweep_cli_gavel_policies_on_a_mixed_cluster(monkeypatch):
+    """--cluster_spec 4:3:2 (v100:p100:k80), static trace: the pickles of the heterogeneity-aware policies carry the
+    reference loop's makespan, completion times, utilisation and `{job: worker ids}` schedule."""
+    if sf_.host_sim_lib() is None:
+        pytest.skip("g++ not available")
+    from shockwave_b200 import simulate as sim
+    from shockwave_b200 import sweep
+    from tests.golden import make_sim_pins as pins
+    scratch = tempfile.mkdtemp(prefix="swclih_")
+    dst = pins.stage_static_trace(scratch, keep=40, static=True)
+    trace = os.path.join(dst, pins.REL)
+    thr = os.path.join(dst, "tacc_throughputs.json")
+    out = os.path.join(scratch, "results")
+    monkeypatch.setattr(sim, "DeviceSim", sf_.HostDeviceSim)
+    orig = sim.PolicyEnsemble.__init__
+    monkeypatch.setattr(sim.PolicyEnsemble, "__init__",
+                        lambda self, *a, **k: orig(self, *a, **{**k, "round_backend": OracleBackend()}))
+    names = ["max_min_fairness_perf", "max_min_fairness"]
+    with gb.cpu_backend() as P:
+        refs = {n: rh.simulate(n, policy_obj=P.get_policy(n, solver="ECOS", seed=0), trace=pins.REL, scratch=scratch,
+                               cluster="4:3:2") for n in names}
+        paths = sweep.main(["--reference-dir", dst, "-t", trace, "--throughputs_file", thr, "-c", "4:3:2",
+                            "-p", ",".join(names), "--output_dir", out])
+        with pytest.raises(SystemExit):
+            sweep.main(["--reference-dir", dst, "-t", trace, "--throughputs_file", thr, "-c", "4:3:2", "-p", "shockwave",
+                        "--config", os.path.join(dst, "configurations", "tacc_32gpus.json"), "--output_dir", out])
+    for n, p in zip(names, paths):
+        d = pickle.load(open(p, "rb"))
+        r = refs[n]
+        assert d["policy"] == n and d["makespan"] == r["makespan"]
+        assert d["jct_list"] == list(r["jct_list"])
+        assert d["cluster_util"] == float(r["cluster_util"])
+        assert [dict(x) for x in d["per_round_schedule"]] == [{int(k): tuple(v) for k, v in rnd.items()}
+                                                              for rnd in r["per_round_schedule"]]

@@ -124,3 +124,41 @@ def test_worker_types_argument_checks_and_error_flags():
     with pytest.raises(RuntimeError):                     # several worker types run static jobs only
         sim.set_worker_types(thr_w, [2, 2])
     sim.close()
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("policy,keep,cluster", [("max_min_fairness_perf", 40, "4:3:2"), ("finish_time_fairness_perf", 36, "2:4:4"),
+                                                  ("max_min_fairness", 40, "4:3:2")])
+def test_policy_ensemble_on_a_mixed_cluster_against_the_reference_loop(policy, keep, cluster):
+    """(a) the unmodified reference loop on a v100 + p100 + k80 cluster with the product's policies (hetero.cu) and round
+    step (gavel.cu, GavelRoundMixin); (b) PolicyEnsemble(worker_types=...): the same device calls, the loop on
+    swb_sim_step and the per-type bookkeeping off the reference's dicts.  Same inputs into the same kernels: the schedules
+    must coincide (1 % on the end-to-end metrics as the assertion, exactness recorded in gpurun_out/sim_ensemble.json).
+    The host logic is held to exact equality on the CPU (tests/test_policy_ensemble_hetero_host.py)."""
+    from oracle import ref_harness as rh
+    from oracle import sim_loop
+    if not rh.reference_available():
+        pytest.skip("needs the (staged) reference simulator")
+    from shockwave_b200 import policies as P
+    from shockwave_b200.simulate import PolicyEnsemble
+    from tests.golden import make_sim_hetero_pins as gen
+    rec = gen.record(policy, keep, cluster, product=True)
+    tr = sim_loop.trace_arrays(rec)
+    wt = dict(names=rec["worker_types"], throughput=np.asarray(rec["throughput_w"]), ngpus=rec["ngpus_w"])
+    ens = PolicyEnsemble(tr, [P.get_policy(policy, solver="ECOS", seed=0) for _ in range(2)], None, worker_types=wt, seed=0)
+    out = ens.run()
+    want = [{j: tuple(ws) for j, ws in rnd} for rnd in rec["per_round_workers"]]
+    want_jct = np.array([rec["jct"][str(j)] for j in range(keep)])
+    row = dict(trace=f"first {keep} jobs of the canonical trace (static), cluster {cluster}, {policy} (PolicyEnsemble, "
+                     f"several worker types)", makespan_ref=rec["makespan"], makespan=out["makespan"].tolist(),
+               rounds_ref=rec["rounds"], rounds=out["rounds"].tolist(), allocations=out["allocations"].tolist(),
+               schedule_identical=bool(out["per_round_schedule"][0] == want),
+               jct_identical=bool(np.array_equal(out["jct"][0], want_jct)))
+    root = os.path.dirname(HERE)
+    path = os.path.join(root, "gpurun_out", "sim_ensemble.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    rows = json.load(open(path)) if os.path.exists(path) else []
+    json.dump([r for r in rows if r.get("trace") != row["trace"]] + [row], open(path, "w"), indent=1)
+    assert np.isfinite(out["jct"]).all()
+    assert abs(out["makespan"][0] - rec["makespan"]) <= 0.01 * rec["makespan"]
+    assert abs(np.mean(out["jct"][0]) - rec["avg_jct"]) <= 0.01 * rec["avg_jct"]
