@@ -1,8 +1,8 @@
 """B200: the device round loop on several worker types (swb_sim_set_worker_types) replays the schedules the UNMODIFIED
 reference recorded on mixed v100 / p100 / k80 clusters (tests/golden/sim_hetero_pins.json) — completion times, makespan
 and rounds bit-identical — in one launch and step by step; random per-scenario schedules equal the restatement
-oracle/sim_loop.py round by round.  (File name sorts last on purpose: this path was added after the round's last GPU
-session and has only run on the host build of the same source.)"""
+oracle/sim_loop.py round by round; PolicyEnsemble on mixed clusters against the reference loop driving the same kernels.
+B200 record: profiles/gputests_sim_hetero_r02.txt, profiles/sim_ensemble_hetero_r02.json."""
 import json
 import os
 
