@@ -96,5 +96,6 @@ def test_sweep_cli_gavel_policies_on_a_mixed_cluster(monkeypatch):
         assert d["policy"] == n and d["makespan"] == r["makespan"]
         assert d["jct_list"] == list(r["jct_list"])
         assert d["cluster_util"] == float(r["cluster_util"])
+        assert d["finish_time_fairness_list"] == list(r["finish_time_fairness_list"])
         assert [dict(x) for x in d["per_round_schedule"]] == [{int(k): tuple(v) for k, v in rnd.items()}
                                                               for rnd in r["per_round_schedule"]]
