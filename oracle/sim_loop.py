@@ -10,7 +10,8 @@ demands the same completion time of every job, the same makespan, the same numbe
 throughput timeline, to the last bit.
 
 Not restated (rejected by the product too): accordion / gns batch-size rescaling (`_simulate_accordion`, `_simulate_gns`,
-`_scale_bs_and_iters`) on more than one worker type, job pairs (packing), the `ideal` and generated-arrival modes
+`_scale_bs_and_iters`) on more than one worker type, job pairs (packing: the reference's loop raises on the first scheduled pair,
+scheduler.py:1408, tests/test_closed_loop_packed_host.py), the `ideal` and generated-arrival modes
 (the generated-arrival mode cannot run in the reference itself: `Scheduler.__init__` opens its trace pickle
 unconditionally, scheduler.py:437).
 One quirk is kept on purpose: the over-deadline rule sums `_cumulative_run_time` per worker id and divides by the scale
