@@ -117,3 +117,21 @@ def test_packed_policy_in_the_unmodified_reference_loop_reaches_the_first_pair(b
         share = sum(v["v100"] for k, v in alloc.items() if j.overlaps_with(k))
         assert share <= 1.0 + 1e-6
     assert sum(v["v100"] for v in alloc.values()) <= 6.0 + 1e-6
+
+
+def test_generated_arrival_mode_does_not_start_in_the_reference():
+    """`simulate_scheduler_with_generated_jobs.py` / `scripts/sweeps/run_sweep_*.py` build a Scheduler WITHOUT a trace
+    pickle (drivers/simulate_scheduler_with_generated_jobs.py:45-56); this fork's `Scheduler.__init__` opens the pickle
+    unconditionally (scheduler.py:437), so the generated-arrival mode cannot run in the reference: nothing to drop into."""
+    with gb.cpu_backend() as P:
+        dst = rh.prepare_tree(None)
+        cwd = os.getcwd()
+        os.chdir(dst)
+        try:
+            ref_sched, _ = rh.import_reference(dst)
+            with pytest.raises(TypeError):
+                ref_sched.Scheduler(P.get_policy("max_min_fairness", solver="ECOS", seed=0),
+                                    throughputs_file=os.path.join(dst, "tacc_throughputs.json"), simulate=True, seed=0,
+                                    time_per_iteration=120)
+        finally:
+            os.chdir(cwd)
