@@ -488,6 +488,38 @@ def run_sharded(trace, profiles, config, scenarios, ngpus, rank=0, world=1, gath
     return out
 
 
+def run_policies_sharded(trace, policy_names, ngpus, rank=0, world=1, gather=None, device=None, make_policy=None, **kw):
+    """The Gavel-policy counterpart of run_sharded: every rank runs PolicyEnsemble on its round-robin slice of
+    `policy_names` (what-ifs = policies, one per scenario; the policy kernels and the round step run on the rank's GPU),
+    then only the per-scenario results travel through `gather`.  make_policy(name) builds one policy object (default:
+    `policies.get_policy(name, solver="ECOS")`); **kw goes to PolicyEnsemble (dynamic=, worker_types=, ...).  Returns, on
+    every rank, the result dict in the ORIGINAL order."""
+    from . import policies as _pol
+    mine = shard_scenarios(len(policy_names), rank, world)
+    dev = rank if device is None else device
+    part = None
+    if mine:
+        _pol.set_device(dev)
+        mk = make_policy or (lambda n: _pol.get_policy(n, solver="ECOS", seed=0))
+        ens = PolicyEnsemble(trace, [mk(policy_names[i]) for i in mine], ngpus, device=dev, **kw)
+        r = ens.run()
+        part = dict(index=mine, makespan=r["makespan"], rounds=r["rounds"], jct=r["jct"], avg_jct=r["avg_jct"],
+                    allocations=r["allocations"], per_round_schedule=r["per_round_schedule"], run_time=r["run_time"])
+    parts = [part] if gather is None else gather(part)
+    S, J = len(policy_names), len(trace["arrival"])
+    out = dict(makespan=np.full(S, np.nan), rounds=np.zeros(S, np.int64), jct=np.full((S, J), np.nan),
+               avg_jct=np.full(S, np.nan), allocations=np.zeros(S, np.int64), per_round_schedule=[None] * S,
+               run_time=np.zeros((S, J)))
+    for p in parts:
+        if p is None:
+            continue
+        for k, i in enumerate(p["index"]):
+            for key in ("makespan", "rounds", "jct", "avg_jct", "allocations", "run_time"):
+                out[key][i] = p[key][k]
+            out["per_round_schedule"][i] = p["per_round_schedule"][k]
+    return out
+
+
 # ---- Gavel policies on the device loop -----------------------------------------------------------------------------------
 class PolicyEnsemble:
     """S what-ifs of one trace under the Gavel policies (one policy object per scenario, e.g.
